@@ -1,0 +1,393 @@
+"""
+Oracle (test infrastructure): collective variables and their autodiff Jacobians.
+
+Restates pysages/colvars/{core,coordinates,angles,shape,orientation,utils}.py
+with torch (CPU) in place of jax.numpy and torch.autograd in place of
+jax.grad / jax.jacrev.  dtype promotion follows JAX's x64 rules: Python floats
+are weakly typed, f32 (+) f64 arrays -> f64.
+"""
+
+import math
+from inspect import signature
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------- #
+# index / group processing  (pysages/colvars/core.py:277-295, 178-181)
+# --------------------------------------------------------------------------- #
+
+
+def _is_group(obj):
+    # core.py:302-314 -- an index is an int or a range; a group is a sequence of them
+    if isinstance(obj, (int, np.integer, range)):
+        return False
+    if isinstance(obj, (list, tuple, np.ndarray)):
+        return True
+    raise ValueError(f"Invalid indices or group: {obj}")
+
+
+def _group_size(obj):
+    # core.py:317-329
+    if isinstance(obj, (int, np.integer)):
+        return 1
+    if isinstance(obj, range):
+        return len(obj)
+    return sum(_group_size(o) for o in obj)
+
+
+def _flatten(obj, out):
+    if isinstance(obj, (int, np.integer)):
+        out.append(int(obj))
+    elif isinstance(obj, range):
+        out.extend(obj)
+    else:
+        for o in obj:
+            _flatten(o, out)
+
+
+def process_groups(indices):
+    """core.py:277-295 -> (flat uint32 index array, list of arange slices, one per group)"""
+    total = 0
+    collected = []
+    groups = []
+    for obj in indices:
+        found = _is_group(obj)
+        _flatten(obj, collected)
+        n = _group_size(obj)
+        if found:
+            groups.append(np.arange(total, total + n, dtype=np.int64))
+        total += n
+    return np.asarray(collected, dtype=np.uint32), groups
+
+
+def _check_groups_size(indices, groups, group_length):
+    # core.py:171-176
+    input_length = np.size(indices, 0) - sum(np.size(g, 0) - 1 for g in groups)
+    if input_length != group_length:
+        raise ValueError(
+            f"Exactly {group_length} indices or groups must be provided (got {input_length})"
+        )
+
+
+class CollectiveVariable:
+    """core.py:24-63"""
+
+    multicomponent = False
+
+    def __init__(self, indices, group_length=None):
+        indices, groups = process_groups(indices)
+        if group_length is not None:
+            _check_groups_size(indices, groups, group_length)
+        self.indices = indices
+        self.groups = groups
+        self.requires_box_unwrapping = True
+
+
+# --------------------------------------------------------------------------- #
+# coordinates.py
+# --------------------------------------------------------------------------- #
+
+
+def barycenter(positions):
+    # coordinates.py:14-28
+    return torch.sum(positions, dim=0) / positions.shape[0]
+
+
+def weighted_barycenter(positions, weights):
+    # coordinates.py:31-53 (the reference loops over atoms; same sum, vectorised)
+    return torch.sum(weights.reshape(-1, 1) * positions, dim=0)
+
+
+def distance(r1, r2):
+    # coordinates.py:91-109
+    return torch.linalg.norm(r1 - r2)
+
+
+class Component(CollectiveVariable):
+    # core.py:67-86 (AxisCV) + coordinates.py:56-71
+    def __init__(self, indices, axis, group_length=None):
+        if axis not in (0, 1, 2):
+            raise RuntimeError(f"Invalid Cartesian axis {axis} index choose 0 (X), 1 (Y), 2 (Z)")
+        super().__init__(indices, group_length)
+        self.axis = axis
+
+    @property
+    def function(self):
+        return lambda rs: barycenter(rs)[self.axis]
+
+
+class Distance(CollectiveVariable):
+    # coordinates.py:74-88
+    def __init__(self, indices):
+        super().__init__(indices, 2)
+
+    @property
+    def function(self):
+        if len(self.groups) == 0:
+            return distance
+        return lambda r1, r2: distance(barycenter(r1), barycenter(r2))
+
+
+class Displacement(CollectiveVariable):
+    # coordinates.py:112-148
+    multicomponent = True
+
+    def __init__(self, indices):
+        super().__init__(indices, 2)
+
+    @property
+    def function(self):
+        if len(self.groups) == 0:
+            return lambda r1, r2: r2 - r1
+        return lambda r1, r2: barycenter(r2) - barycenter(r1)
+
+
+# --------------------------------------------------------------------------- #
+# angles.py
+# --------------------------------------------------------------------------- #
+
+
+def angle(p1, p2, p3):
+    # angles.py:46-74
+    q = p1 - p2
+    r = p3 - p2
+    return torch.atan2(torch.linalg.norm(torch.linalg.cross(q, r)), torch.dot(q, r))
+
+
+def dihedral_angle(p1, p2, p3, p4):
+    # angles.py:95-128
+    q = p3 - p2
+    r = torch.linalg.cross(p2 - p1, q)
+    s = torch.linalg.cross(q, p4 - p3)
+    return torch.atan2(
+        torch.dot(torch.linalg.cross(r, s), q), torch.dot(r, s) * torch.linalg.norm(q)
+    )
+
+
+class Angle(CollectiveVariable):
+    # angles.py:24-43
+    def __init__(self, indices):
+        super().__init__(indices, 3)
+
+    @property
+    def function(self):
+        return angle
+
+
+class DihedralAngle(CollectiveVariable):
+    # angles.py:77-92
+    def __init__(self, indices):
+        super().__init__(indices, 4)
+
+    @property
+    def function(self):
+        return dihedral_angle
+
+
+# --------------------------------------------------------------------------- #
+# shape.py
+# --------------------------------------------------------------------------- #
+
+
+def radius_of_gyration(positions):
+    # shape.py:38-57: sum_i r_i.r_i / n, broadcast onto a 3-vector (quirk kept)
+    n = positions.shape[0]
+    rog = torch.zeros(3, dtype=positions.dtype) + torch.sum(positions * positions)
+    return rog / n
+
+
+class RadiusOfGyration(CollectiveVariable):
+    """
+    shape.py:14-35.  The reference returns a (3,) vector whose components are all
+    equal and cannot differentiate it (not @multicomponent, so jax.grad rejects
+    it).  PARITY UNPINNED for the Jacobian: the oracle defines the scalar CV as
+    component 0 of the reference vector and differentiates that.
+    """
+
+    @property
+    def function(self):
+        return lambda rs: radius_of_gyration(rs)[0]
+
+    @property
+    def reference_vector_function(self):
+        return radius_of_gyration
+
+
+# --------------------------------------------------------------------------- #
+# orientation.py (RMSD)
+# --------------------------------------------------------------------------- #
+
+
+def fitted_positions(positions, weights):
+    # orientation.py:27-30
+    return positions - weighted_barycenter(positions, weights)
+
+
+def kabsch(P, Q):
+    # orientation.py:33-73
+    C = P.T @ Q
+    V, S, W = torch.linalg.svd(C, full_matrices=False)
+    dh = torch.linalg.det(V) * torch.linalg.det(W)
+    sgn = torch.sign(dh)
+    scale = torch.ones(3, dtype=P.dtype)
+    scale[-1] = sgn  # V[:, -1] *= sign(dh)
+    V = V * scale.reshape(1, 3)
+    return V @ W
+
+
+def rmsd(r1, Q, w_0, optimal_rotation):
+    # orientation.py:76-95
+    P = fitted_positions(r1, w_0)
+    U = optimal_rotation(P, Q)
+    optimal_P = P @ U
+    return torch.sqrt(torch.sum(torch.square(optimal_P - Q)) / P.shape[0])
+
+
+class RMSD(CollectiveVariable):
+    # orientation.py:98-126
+    def __init__(self, indices, references, weights=None):
+        if weights is not None and len(indices) != len(weights):
+            raise RuntimeError("Indices and weights must be of the same length")
+        super().__init__(indices)
+        self.references = torch.as_tensor(np.asarray(references, dtype=np.float64))
+        n = len(indices)
+        if weights is None:
+            self.weights = torch.ones(n, dtype=torch.float64) / n
+        else:
+            self.weights = torch.as_tensor(np.asarray(weights, dtype=np.float64))
+        self.Q = fitted_positions(self.references, self.weights)
+
+    @property
+    def function(self):
+        return lambda r: rmsd(r, self.Q, self.weights, kabsch)
+
+
+# --------------------------------------------------------------------------- #
+# CoordinationNumber -- ABSENT from the reference (PARITY UNPINNED).
+# Defined here (and in DESIGN.md) as the PLUMED-style rational switching
+# function summed over all A x B pairs, pushed through the reference's
+# CV-extension hook (a CollectiveVariable whose `function` takes two groups).
+# --------------------------------------------------------------------------- #
+
+
+class CoordinationNumber(CollectiveVariable):
+    def __init__(self, indices, r0=1.0, n=6, m=12):
+        super().__init__(indices, 2)
+        if len(self.groups) != 2:
+            raise ValueError("CoordinationNumber needs two groups of atoms")
+        self.r0, self.n, self.m = float(r0), int(n), int(m)
+
+    @property
+    def function(self):
+        r0, n, m = self.r0, self.n, self.m
+
+        def coordination(ra, rb, chunk=512):
+            total = torch.zeros((), dtype=ra.dtype)
+            for s in range(0, ra.shape[0], chunk):
+                d = ra[s : s + chunk, None, :] - rb[None, :, :]
+                x2 = torch.sum(d * d, dim=-1) / (r0 * r0)
+                if m == 2 * n and n % 2 == 0:
+                    sw = 1.0 / (1.0 + x2 ** (n // 2))
+                else:
+                    x = torch.sqrt(x2)
+                    sw = (1.0 - x**n) / (1.0 - x**m)
+                total = total + torch.sum(sw)
+            return total
+
+        return coordination
+
+
+# --------------------------------------------------------------------------- #
+# build  (core.py:184-274)
+# --------------------------------------------------------------------------- #
+
+
+def _get_nargs(function):
+    return len(signature(function).parameters)
+
+
+def _evaluator(cv):
+    xi = cv.function
+    idx = torch.as_tensor(cv.indices.astype(np.int64))
+    gps = [torch.as_tensor(g) for g in cv.groups]
+
+    if _get_nargs(xi) == 1:  # core.py:190-194
+
+        def evaluate(positions, ids):
+            pos = positions[ids[idx]]
+            return xi(pos)
+
+    elif len(gps) == 0:  # core.py:196-200
+
+        def evaluate(positions, ids):
+            pos = positions[ids[idx]]
+            return xi(*pos)
+
+    else:  # core.py:202-207 (bare indices mixed with groups are silently dropped)
+
+        def evaluate(positions, ids):
+            pos = positions[ids[idx]]
+            pos = [pos[g] for g in gps]
+            return xi(*pos)
+
+    return evaluate
+
+
+def _build(cv, differentiate=True):
+    evaluate = _evaluator(cv)
+
+    def apply(pos, ids):
+        if not differentiate:
+            with torch.no_grad():
+                return evaluate(pos, ids).reshape(1, -1)
+        p = pos.detach().clone().requires_grad_(True)
+        val = evaluate(p, ids)
+        xi = val.detach().reshape(1, -1)
+        comps = val.reshape(-1)
+        rows = []
+        for c in range(comps.shape[0]):  # grad (scalar) / jacrev (multicomponent), core.py:298-299
+            (g,) = torch.autograd.grad(comps[c], p, retain_graph=c + 1 < comps.shape[0])
+            rows.append(g.reshape(1, -1))
+        return xi, torch.cat(rows, dim=0)  # core.py:216-217
+
+    return apply
+
+
+def build(*cvs, differentiate=True):
+    """core.py:228-274 -> apply(data) with data.positions (N, >=3), data.indices (N,)"""
+    fns = [_build(cv, differentiate) for cv in cvs]
+
+    def apply(data):
+        pos = torch.as_tensor(data.positions)[:, :3]
+        ids = torch.as_tensor(np.asarray(data.indices).astype(np.int64))
+        if differentiate:
+            xis, grads = [], []
+            for f in fns:
+                xi, J = f(pos, ids)
+                xis.append(xi)
+                grads.append(J)
+            return torch.hstack(xis), torch.vstack(grads)
+        return torch.hstack([f(pos, ids) for f in fns])
+
+    return apply
+
+
+# --------------------------------------------------------------------------- #
+# utils.py
+# --------------------------------------------------------------------------- #
+
+
+def get_periods(cvs):
+    # colvars/utils.py:13-19 -- exact type match, subclasses are NOT periodic
+    return torch.tensor(
+        [2 * math.pi if type(cv) in (Angle, DihedralAngle) else math.inf for cv in cvs],
+        dtype=torch.float64,
+    )
+
+
+def wrap(x, P):
+    # colvars/utils.py:22-26 (the inf branch is masked out before the arithmetic so that
+    # autograd never sees 0 * inf; the selected values are identical)
+    Pf = torch.where(torch.isinf(P), torch.ones_like(P), P)
+    return torch.where(torch.isinf(P), x, x - (torch.abs(x) > Pf / 2) * torch.sign(x) * Pf)

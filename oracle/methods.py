@@ -1,0 +1,418 @@
+"""
+Oracle (test infrastructure): sampling-method state machines.
+
+Restates, in torch-fp64 (CPU):
+  pysages/methods/harmonic_bias.py:78-132   HarmonicBias
+  pysages/methods/metad.py:156-323          Metadynamics (standard / well-tempered, direct / grid)
+  pysages/methods/abf.py:142-258            ABF
+  pysages/methods/funn.py:187-210,271-273   FUNN per-step accumulation (shares ABF's scatter)
+  pysages/methods/restraints.py:49-73       CVRestraints
+  pysages/methods/core.py:463-474           generalize
+  pysages/utils/core.py:113-136             gaussian, linear_solver
+Every `update(snapshot, state)` is a pure function like the reference's jitted one.
+Out-of-bounds indexing follows JAX's defaults: gathers clamp, scatters drop.
+"""
+
+from typing import Any, NamedTuple
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from . import colvars, grids
+
+F64 = torch.float64
+
+
+# --------------------------------------------------------------------------- #
+# restraints.py
+# --------------------------------------------------------------------------- #
+
+
+class CVRestraints(NamedTuple):  # restraints.py:14-37
+    lower: Any
+    upper: Any
+    kl: Any
+    ku: Any
+
+
+def canonicalize(restraints, cvs):
+    # restraints.py:49-61
+    if restraints is None:
+        return None
+    lower, upper, kl, ku = restraints
+    kl = np.asarray(kl, dtype=np.float64).flatten()
+    ku = np.asarray(ku, dtype=np.float64).flatten()
+    lower = np.where(kl == 0, -np.inf, np.asarray(lower, dtype=np.float64).flatten())
+    upper = np.where(ku == 0, np.inf, np.asarray(upper, dtype=np.float64).flatten())
+    return CVRestraints(lower, upper, kl, ku)
+
+
+def apply_restraints(lo, hi, kl, kh, xi):
+    # restraints.py:68-73
+    lo, hi, kl, kh = (torch.as_tensor(v, dtype=F64) for v in (lo, hi, kl, kh))
+    zero = torch.zeros_like(xi)
+    return torch.where(xi < lo, kl * (xi - lo), torch.where(xi > hi, kh * (xi - hi), zero))
+
+
+# --------------------------------------------------------------------------- #
+# JAX indexing semantics
+# --------------------------------------------------------------------------- #
+
+
+def _gather(arr, I):
+    """arr[I] with every index clamped into range (JAX default gather mode)."""
+    idx = tuple(min(int(i), arr.shape[d] - 1) for d, i in enumerate(I))
+    return arr[idx]
+
+
+def _in_bounds(arr, I):
+    return all(int(i) < arr.shape[d] for d, i in enumerate(I))
+
+
+def _scatter_add(arr, I, val):
+    """arr.at[I].add(val): dropped when any index is out of range (JAX default scatter mode)."""
+    out = arr.clone()
+    if _in_bounds(arr, I):
+        idx = tuple(int(i) for i in I)
+        out[idx] = out[idx] + val
+    return out
+
+
+def _scatter_set(arr, i, val):
+    out = arr.clone()
+    if int(i) < arr.shape[0]:
+        out[int(i)] = val
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# base  (methods/core.py:81-153, 463-474)
+# --------------------------------------------------------------------------- #
+
+
+class SamplingMethod:
+    snapshot_flags = set()
+
+    def __init__(self, cvs, **kwargs):
+        self.cvs = cvs
+        self.cv = colvars.build(*cvs, differentiate=kwargs.get("cv_grad", True))
+        self.requires_box_unwrapping = any(cv.requires_box_unwrapping for cv in cvs)
+        self.kwargs = kwargs
+
+
+def generalize(concrete_update, helpers):
+    # core.py:463-474
+    def update(snapshot, state):
+        return concrete_update(state, helpers.query(snapshot))
+
+    return update
+
+
+def _natoms(snapshot):
+    return np.shape(snapshot.positions)[0]
+
+
+# --------------------------------------------------------------------------- #
+# HarmonicBias
+# --------------------------------------------------------------------------- #
+
+
+class HarmonicBiasState(NamedTuple):  # harmonic_bias.py:23-39
+    xi: Any
+    bias: Any
+    ncalls: int = 0
+
+
+class HarmonicBias(SamplingMethod):
+    snapshot_flags = {"positions", "indices"}  # bias.py:32
+
+    def __init__(self, cvs, kspring, center, **kwargs):
+        super().__init__(cvs, **kwargs)
+        N = len(cvs)
+        center = np.asarray(center, dtype=np.float64)
+        if center.shape == ():
+            center = center.reshape(1)
+        if len(center.shape) != 1 or center.shape[0] != N:  # bias.py:62-65
+            raise RuntimeError(f"Invalid center shape expected {N} got {center.shape}.")
+        self.center = center
+        kspring = np.asarray(kspring, dtype=np.float64)  # harmonic_bias.py:88-107
+        shape = kspring.shape
+        if len(shape) > 2:
+            raise RuntimeError(f"Wrong kspring shape {shape} (expected scalar, 1D or 2D)")
+        if len(shape) == 2:
+            if shape != (N, N):
+                raise RuntimeError(f"2D kspring with wrong shape, expected ({N}, {N}), got {shape}")
+            if not np.allclose(kspring, kspring.T):
+                raise RuntimeError("Spring matrix is not symmetric")
+            self.kspring = kspring
+        else:
+            if kspring.size not in (N, 1):
+                raise RuntimeError(f"Wrong kspring size, expected 1 or {N}, got {kspring.size}.")
+            self.kspring = np.identity(N) * kspring
+
+    def build(self, snapshot, helpers):
+        # harmonic_bias.py:113-132
+        cv = self.cv
+        center = torch.as_tensor(self.center)
+        kspring = torch.as_tensor(self.kspring)
+        natoms = _natoms(snapshot)
+
+        def initialize():
+            xi, _ = cv(helpers.query(snapshot))
+            bias = torch.zeros((natoms, helpers.dimensionality()), dtype=F64)
+            return HarmonicBiasState(xi, bias)
+
+        def update(state, data):
+            xi, Jxi = cv(data)
+            forces = kspring @ (xi - center).flatten()  # no periodic wrap (quirk kept)
+            bias = -Jxi.T.to(forces.dtype) @ forces.flatten()
+            bias = bias.reshape(state.bias.shape)
+            return HarmonicBiasState(xi, bias, state.ncalls + 1)
+
+        return snapshot, initialize, generalize(update, helpers)
+
+    def bias_energy(self, xi):
+        """Not computed by the reference; defined as 1/2 (xi-c)^T K (xi-c)."""
+        d = (torch.as_tensor(xi, dtype=F64).flatten() - torch.as_tensor(self.center)).flatten()
+        return float(0.5 * d @ (torch.as_tensor(self.kspring) @ d))
+
+
+# --------------------------------------------------------------------------- #
+# Metadynamics
+# --------------------------------------------------------------------------- #
+
+
+class MetadynamicsState(NamedTuple):  # metad.py:26-69
+    xi: Any
+    bias: Any
+    heights: Any
+    centers: Any
+    sigmas: Any
+    grid_potential: Any
+    grid_gradient: Any
+    idx: int
+    ncalls: int = 0
+
+
+def gaussian(a, sigma, x):
+    # utils/core.py:113-117
+    return a * torch.exp(-torch.sum(((x / sigma) ** 2).reshape(x.shape[0], -1), dim=1) / 2)
+
+
+def sum_of_gaussians(xi, heights, centers, sigmas, periods):
+    # metad.py:318-323
+    delta_x = colvars.wrap(xi - centers, periods)
+    return gaussian(heights, sigmas, delta_x).sum()
+
+
+class Metadynamics(SamplingMethod):
+    snapshot_flags = {"positions", "indices"}
+
+    def __init__(self, cvs, height, sigma, stride, ngaussians, deltaT=None, **kwargs):
+        if deltaT is not None and "kB" not in kwargs:  # metad.py:133-138
+            raise KeyError("For well-tempered Metadynamics a keyword argument `kB` must be provided.")
+        super().__init__(cvs, **kwargs)
+        self.grid = kwargs.get("grid", None)
+        self.restraints = canonicalize(kwargs.get("restraints", None), cvs)
+        if self.grid is not None and len(cvs) != self.grid.shape.size:  # core.py:435-438
+            raise ValueError("Grid and Collective Variable dimensions must match.")
+        self.height = height
+        self.sigma = sigma
+        self.stride = stride
+        self.ngaussians = ngaussians
+        self.deltaT = deltaT
+        self.kB = kwargs.get("kB", None)
+
+    def build(self, snapshot, helpers):
+        # metad.py:156-205
+        method = self
+        cv = self.cv
+        stride, ngaussians = self.stride, self.ngaussians
+        natoms = _natoms(snapshot)
+        periods = colvars.get_periods(self.cvs)
+        height_0, deltaT, grid, kB = self.height, self.deltaT, self.grid, self.kB
+        restraints = self.restraints
+
+        if grid is not None:
+            grid_mesh = torch.as_tensor(grids.compute_mesh(grid))
+            get_grid_index = grids.build_indexer(grid)
+            gshape = tuple(int(s) for s in grid.shape)
+
+        def out_of_bounds(I):
+            return any(int(i) == s for i, s in zip(I, gshape))
+
+        def initialize():  # metad.py:166-185
+            xi, _ = cv(helpers.query(snapshot))
+            bias = torch.zeros((natoms, helpers.dimensionality()), dtype=F64)
+            heights = torch.zeros(ngaussians, dtype=F64)
+            centers = torch.zeros((ngaussians, xi.numel()), dtype=F64)
+            sigmas = torch.as_tensor(np.array(method.sigma, dtype=np.float64, ndmin=2))
+            if grid is None:
+                gp = gg = None
+            else:
+                gp = torch.zeros(gshape, dtype=F64) if deltaT else None
+                gg = torch.zeros((*gshape, len(gshape)), dtype=F64)
+            return MetadynamicsState(xi, bias, heights, centers, sigmas, gp, gg, 0)
+
+        def next_height(xi, heights, centers, sigmas, gp, I):  # metad.py:219-229
+            if deltaT is None:
+                return torch.as_tensor(float(height_0), dtype=F64)
+            if grid is None:
+                V = sum_of_gaussians(xi.to(F64), heights, centers, sigmas, periods)
+            else:
+                V = _gather(gp, I)
+            return height_0 * torch.exp(-V / (deltaT * kB))
+
+        def update_grids(gp, gg, height, xi, sigmas):  # metad.py:251-256
+            mesh = grid_mesh.clone().requires_grad_(True)
+            # sum over mesh points of the (independent) per-point Gaussians: its gradient
+            # w.r.t. the mesh is exactly vmap(grad(current_gaussian))(grid_mesh)
+            delta = colvars.wrap(mesh - xi.detach().reshape(1, -1).to(F64), periods)
+            vals = gaussian(height, sigmas, delta)
+            (grads,) = torch.autograd.grad(vals.sum(), mesh)
+            vals = vals.detach()
+            new_gp = gp + vals.reshape(gp.shape) if deltaT is not None else gp
+            new_gg = gg + grads.reshape(gg.shape)
+            return new_gp, new_gg
+
+        def update(state, data):  # metad.py:187-203
+            xi, Jxi = cv(data)
+            ncalls = state.ncalls + 1
+            in_deposition_step = (ncalls > 1) and (ncalls % stride == 1)
+
+            heights, centers, sigmas = state.heights, state.centers, state.sigmas
+            gp, gg, idx = state.grid_potential, state.grid_gradient, state.idx
+            I_xi = get_grid_index(xi.detach().numpy()) if grid is not None else None
+            should = in_deposition_step and (grid is None or not out_of_bounds(I_xi))
+            if should:  # metad.py:262-271
+                h = next_height(xi, heights, centers, sigmas, gp, I_xi)
+                heights = _scatter_set(heights, idx, h)
+                centers = _scatter_set(centers, idx, xi.flatten().to(F64))
+                if grid is not None:
+                    gp, gg = update_grids(gp, gg, h, xi, sigmas)
+                idx = idx + 1
+
+            # metad.py:282-314
+            if grid is None:
+                x = xi.detach().clone().to(F64).requires_grad_(True)
+                V = sum_of_gaussians(x, heights, centers, sigmas, periods)
+                (generalized_force,) = torch.autograd.grad(V, x)
+            elif out_of_bounds(I_xi):
+                if restraints:
+                    lo, hi, kl, kh = restraints
+                    generalized_force = apply_restraints(
+                        lo, hi, kl, kh, xi.reshape(len(gshape)).to(F64)
+                    )
+                else:
+                    generalized_force = torch.zeros(len(gshape), dtype=F64)
+            else:
+                generalized_force = _gather(gg, I_xi)
+
+            bias = -Jxi.T.to(F64) @ generalized_force.flatten()
+            bias = bias.reshape(state.bias.shape)
+            return MetadynamicsState(xi, bias, heights, centers, sigmas, gp, gg, idx, ncalls)
+
+        return snapshot, initialize, generalize(update, helpers)
+
+    def bias_energy(self, state):
+        """V(xi) of the state (direct sum, or the binned grid potential when available)."""
+        periods = colvars.get_periods(self.cvs)
+        if self.grid is None or state.grid_potential is None:
+            return float(
+                sum_of_gaussians(
+                    state.xi.to(F64), state.heights, state.centers, state.sigmas, periods
+                )
+            )
+        I = grids.build_indexer(self.grid)(state.xi.detach().numpy())
+        return float(_gather(state.grid_potential, I))
+
+
+# --------------------------------------------------------------------------- #
+# ABF (+ FUNN accumulation)
+# --------------------------------------------------------------------------- #
+
+
+class ABFState(NamedTuple):  # abf.py:32-72
+    xi: Any
+    bias: Any
+    hist: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    ncalls: int = 0
+
+
+def linear_solver(use_pinv):
+    # utils/core.py:120-136 + utils/compat.py:105-111
+    if use_pinv:
+
+        def tsolve(A, B):
+            return torch.linalg.pinv(A.T) @ B
+
+    else:
+
+        def tsolve(A, B):
+            a = (A @ A.T).numpy()
+            b = (A @ B).numpy()
+            return torch.as_tensor(scipy.linalg.solve(a, b, assume_a="pos"))
+
+    return tsolve
+
+
+class ABF(SamplingMethod):
+    snapshot_flags = {"positions", "indices", "momenta"}  # abf.py:114
+
+    def __init__(self, cvs, grid, **kwargs):
+        if len(cvs) != grid.shape.size:
+            raise ValueError("Grid and Collective Variable dimensions must match.")
+        super().__init__(cvs, **kwargs)
+        self.grid = grid
+        self.restraints = canonicalize(kwargs.get("restraints", None), cvs)
+        self.N = np.asarray(kwargs.get("N", 500))
+        self.use_pinv = kwargs.get("use_pinv", False)
+
+    def build(self, snapshot, helpers):
+        # abf.py:142-227
+        cv, grid = self.cv, self.grid
+        dt = snapshot.dt
+        dims = grid.shape.size
+        gshape = tuple(int(s) for s in grid.shape)
+        natoms = _natoms(snapshot)
+        tsolve = linear_solver(self.use_pinv)
+        get_grid_index = grids.build_indexer(grid)
+        N = int(self.N)
+        restraints = self.restraints
+        query, dimensionality, to_force_units = helpers
+
+        def estimate_force(xi, I_xi, Fsum, hist):  # abf.py:230-258
+            ob = any(int(i) == s for i, s in zip(I_xi, gshape))
+            if restraints is not None and ob:
+                lo, hi, kl, kh = restraints
+                return apply_restraints(lo, hi, kl, kh, xi.reshape(dims).to(F64))
+            return _gather(Fsum, I_xi) / max(N, int(_gather(hist, I_xi)))
+
+        def initialize():  # abf.py:173-190
+            xi, _ = cv(query(snapshot))
+            bias = torch.zeros((natoms, dimensionality()), dtype=F64)
+            hist = torch.zeros(gshape, dtype=torch.int64)  # uint32 in the reference
+            Fsum = torch.zeros((*gshape, dims), dtype=F64)
+            force = torch.zeros(dims, dtype=F64)
+            return ABFState(xi, bias, hist, Fsum, force, torch.zeros(dims, dtype=F64),
+                            torch.zeros(dims, dtype=F64))
+
+        def update(state, data):  # abf.py:192-225
+            xi, Jxi = cv(data)
+            p = torch.as_tensor(data.momenta)
+            Jd = Jxi.to(F64) if (Jxi.dtype == F64 or p.dtype == F64) else Jxi
+            Wp = tsolve(Jd, p.to(Jd.dtype)).to(F64)
+            dWp_dt = (1.5 * Wp - 2.0 * state.Wp + 0.5 * state.Wp_) / dt
+            I_xi = get_grid_index(xi.detach().numpy())
+            hist = _scatter_add(state.hist, I_xi, 1)
+            Fsum = _scatter_add(state.Fsum, I_xi, to_force_units(dWp_dt) + state.force)
+            force = estimate_force(xi, I_xi, Fsum, hist).reshape(dims)
+            bias = (-Jxi.T.to(F64) @ force).reshape(state.bias.shape)
+            return ABFState(xi, bias, hist, Fsum, force, Wp, state.Wp, state.ncalls + 1)
+
+        return snapshot, initialize, generalize(update, helpers)
