@@ -1,0 +1,230 @@
+/*
+ * pysages_b200.h -- C ABI of the B200-native PySAGES bias step.
+ *
+ * Drop-in boundary for the per-timestep hot path of PySAGES (reference checkout
+ * paths below are relative to the reference repository root):
+ *
+ *   engine force compute -> [ snapshot read -> CVs + Jacobians -> method bias
+ *                             -> in-place force scatter ] -> engine integrator
+ *
+ * Nothing comparable exists in the reference (it is 100 % Python/JAX); every
+ * entry point states which reference interface it replaces.  All pointers in
+ * `psb_snapshot` are raw CUDA device pointers taken from the engine's DLPack
+ * capsules (DLTensor::data + byte_offset); no torch / DLPack / Python types
+ * appear in any signature.  All work is enqueued on the caller's CUDA stream
+ * (the engine's stream) and the calls return without synchronising, unless a
+ * function says otherwise.  There is no CPU fallback: every function fails with
+ * PSB_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Error convention: functions return a psb_status; the message is available from
+ * psb_last_error() (thread-local).  The Python layer maps PSB_ERR_VALUE ->
+ * ValueError, PSB_ERR_RUNTIME / PSB_ERR_CUDA -> RuntimeError, PSB_ERR_KEY ->
+ * KeyError, matching the reference's exception types.
+ */
+#ifndef PYSAGES_B200_H
+#define PYSAGES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_MAX_CVS 4        /* collective variables per method            */
+#define PSB_MAX_K 4          /* total CV components (xi has shape (1, k))  */
+#define PSB_MAX_GROUPS 16    /* atom groups ("points") over all CVs        */
+#define PSB_MAX_GRID_DIMS 4
+
+typedef struct psb_handle psb_handle;
+
+typedef enum {
+  PSB_OK = 0,
+  PSB_ERR_VALUE = 1,   /* ValueError   */
+  PSB_ERR_RUNTIME = 2, /* RuntimeError */
+  PSB_ERR_KEY = 3,     /* KeyError     */
+  PSB_ERR_CUDA = 4,    /* CUDA failure / no device / extension missing */
+  PSB_ERR_UNSUPPORTED = 5
+} psb_status;
+
+/* ---- collective variables: pysages/colvars/*.py ----------------------------------- */
+typedef enum {
+  PSB_CV_COMPONENT = 1,    /* colvars/coordinates.py:56-71   */
+  PSB_CV_DISTANCE = 2,     /* colvars/coordinates.py:74-109  */
+  PSB_CV_DISPLACEMENT = 3, /* colvars/coordinates.py:112-148 (3 components) */
+  PSB_CV_ANGLE = 4,        /* colvars/angles.py:24-74        */
+  PSB_CV_DIHEDRAL = 5,     /* colvars/angles.py:77-128       */
+  PSB_CV_ROG = 6,          /* colvars/shape.py:14-57 (value = <r.r>, reference quirk) */
+  PSB_CV_RMSD = 7,         /* colvars/orientation.py:27-126  */
+  PSB_CV_COORDINATION = 8  /* extension, absent from the reference */
+} psb_cv_kind;
+
+/* One CV after the reference's index processing (colvars/core.py:184-207, 277-295):
+ * `tags` holds the particle tags of all groups back to back; group g spans
+ * tags[group_offsets[g] .. group_offsets[g+1]).  Point CVs take the barycentre of each
+ * group as one point (a bare index is a group of one). */
+typedef struct {
+  int32_t kind;                  /* psb_cv_kind */
+  int32_t axis;                  /* Component: 0,1,2 */
+  int32_t n_groups;              /* Component/RoG/RMSD: 1; Distance/Displacement/Coordination: 2;
+                                    Angle: 3; Dihedral: 4 */
+  int32_t reserved;
+  const uint32_t* tags;          /* host pointer, group_offsets[n_groups] entries */
+  const uint32_t* group_offsets; /* host pointer, n_groups + 1 entries */
+  const double* reference;       /* RMSD: (n, 3) reference coordinates (host) */
+  const double* weights;         /* RMSD: n weights, or NULL for uniform 1/n  */
+  double r0;                     /* Coordination: switching radius */
+  int32_t nn, mm;                /* Coordination: exponents (default 6, 12) */
+} psb_cv_desc;
+
+/* ---- grids: pysages/grids.py:30-158 ----------------------------------------------- */
+typedef enum { PSB_GRID_NONE = 0, PSB_GRID_REGULAR = 1, PSB_GRID_PERIODIC = 2, PSB_GRID_CHEBYSHEV = 3 } psb_grid_kind;
+
+typedef struct {
+  int32_t kind; /* psb_grid_kind */
+  int32_t ndim;
+  double lower[PSB_MAX_GRID_DIMS];
+  double upper[PSB_MAX_GRID_DIMS];
+  int32_t shape[PSB_MAX_GRID_DIMS];
+} psb_grid_desc;
+
+/* ---- methods: pysages/methods/{harmonic_bias,metad,abf,funn,restraints}.py --------- */
+typedef enum {
+  PSB_METHOD_UNBIASED = 0, /* CVs only, no force (methods/unbiased.py:64-75) */
+  PSB_METHOD_HARMONIC = 1, /* methods/harmonic_bias.py:113-132 */
+  PSB_METHOD_METAD = 2,    /* methods/metad.py:156-323 */
+  PSB_METHOD_ABF = 3       /* methods/abf.py:142-258 (FUNN's per-step accumulation, funn.py:187-210,
+                              is the same update with `force` supplied by psb_set_state) */
+} psb_method_kind;
+
+typedef struct {
+  int32_t kind; /* psb_method_kind */
+  int32_t reserved;
+  /* HarmonicBias: harmonic_bias.py:78-107 canonical (k x k) spring matrix, row-major; center (k) */
+  double kspring[PSB_MAX_K * PSB_MAX_K];
+  double center[PSB_MAX_K];
+  /* Metadynamics: metad.py:140-150 */
+  double height;
+  double sigma[PSB_MAX_K];
+  double periods[PSB_MAX_K]; /* colvars/utils.py:13-19: 2*pi for exact Angle/DihedralAngle, else +inf */
+  int64_t stride;
+  int64_t ngaussians;
+  int32_t well_tempered; /* deltaT is not None */
+  int32_t shared_hills;  /* extension: multiple walkers exchange hills (psb_walker_*) */
+  double deltaT;
+  double kB;
+  /* ABF: abf.py:116-118 */
+  int64_t abf_N;
+  int32_t use_pinv;
+  int32_t has_restraints;
+  /* CVRestraints after canonicalize (restraints.py:49-61) */
+  double r_lower[PSB_MAX_K], r_upper[PSB_MAX_K], r_kl[PSB_MAX_K], r_ku[PSB_MAX_K];
+  /* helpers.to_force_units (backends/lammps.py:33,137-139); 1.0 elsewhere */
+  double force_unit_factor;
+  psb_grid_desc grid; /* kind == PSB_GRID_NONE when the method has no grid */
+} psb_method_desc;
+
+/* ---- engine memory layouts: pysages/backends/{hoomd,openmm,lammps}.py -------------- */
+typedef enum {
+  /* hoomd.py:148-202: positions (N,4) xyz+type, vel_mass (N,4) vxyz+mass, forces (N,4) fxyz+pe,
+     ids = rtag (N,) u32 tag->slot, images (N,3) i32 */
+  PSB_LAYOUT_HOOMD = 1,
+  /* openmm.py:64-89,100-143 on the CUDA platform: positions (Np,4), vel_mass (Np,4) w = 1/m,
+     forces (3,Np) int64 fixed point 2^32, ids (Np,) i32 slot->atom (argsort'ed every step) */
+  PSB_LAYOUT_OPENMM_CUDA = 2,
+  /* lammps.py:87-113,182-223: x,v,f (N,3); ids = tags_map (N+1,) i32 with tag t at [t+1];
+     images (N,) packed i32 (10/10/10 bits); masses per type (double) + types (N,) i32 */
+  PSB_LAYOUT_LAMMPS = 3,
+  /* openmm.py on the CPU/Reference platforms, staged on the device: positions, velocities,
+     forces (N,3); masses = inverse masses (N,); ids (N,) i32 or NULL (identity);
+     images (N,3) i32 or NULL */
+  PSB_LAYOUT_PLAIN3 = 4
+} psb_layout_kind;
+
+typedef struct {
+  int32_t layout;     /* psb_layout_kind */
+  int32_t real_bytes; /* 4 or 8: dtype of positions / velocities / (non fixed-point) forces */
+  int64_t natoms;     /* rows of `positions` (padded count for OpenMM-CUDA) */
+  int32_t unwrap;     /* method.requires_box_unwrapping (colvars/core.py:50; hoomd.py:177-186) */
+  int32_t need_momenta; /* "momenta" in method.snapshot_flags (abf.py:114) */
+  int32_t dense_outputs; /* 1: also keep the reference's dense state.bias (N,3) and J (k,3N) */
+  int32_t ntypes;        /* LAMMPS: entries of the per-type mass array (ntypes + 1) */
+} psb_layout_desc;
+
+/* Device pointers of one snapshot (backends/snapshot.py:34-46).  Unused ones may be NULL. */
+typedef struct {
+  const void* positions;
+  const void* vel_mass;
+  void* forces; /* modified in place (hoomd.py:219-230, openmm.py:160-170, lammps.py:163-170) */
+  const void* ids;
+  const void* images;
+  const void* masses; /* LAMMPS: per-type masses (double); PLAIN3: inverse masses */
+  const void* types;  /* LAMMPS: per-atom types (i32) */
+  double box_diag[3]; /* diag(H) -- the reference unwraps with the diagonal only (hoomd.py:180) */
+  double dt;
+} psb_snapshot;
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+
+/* Replaces SamplingMethod.build(snapshot, helpers) + initialize() (methods/core.py:108-116,
+ * e.g. metad.py:152-185): validates, uploads index tables, allocates device state. */
+psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_desc* method,
+                      const psb_layout_desc* layout, psb_handle** out);
+void psb_destroy(psb_handle* h);
+const char* psb_last_error(void);
+
+/* Replaces Sampler._update_callback: method_update + bias (hoomd.py:168-171 and the openmm /
+ * lammps equivalents): one fused launch sequence on `cuda_stream`, no host sync. */
+psb_status psb_step(psb_handle* h, const psb_snapshot* snap, int64_t timestep, void* cuda_stream);
+
+/* Replaces the first CV evaluation done by initialize() (e.g. harmonic_bias.py:119-122):
+ * evaluates xi on `snap` without touching forces, state counters or histograms. */
+psb_status psb_evaluate_cvs(psb_handle* h, const psb_snapshot* snap, void* cuda_stream);
+
+/* Engine-loop emulation for benchmarks: calls psb_step on snaps[i % nsnaps] for nsteps steps. */
+psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnaps, int64_t nsteps,
+                         void* cuda_stream);
+
+/* Same step with HOST snapshot buffers (engine running on the CPU, bias on the GPU): copies
+ * the arrays the method needs to the device, steps, copies forces back, and synchronises. */
+psb_status psb_step_host(psb_handle* h, const psb_snapshot* host_snap, int64_t timestep,
+                         void* cuda_stream, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* ---- state access (callbacks, checkpoint/restart: serialization.py:44-93) -------------- */
+/* Field names follow the reference State tuples: "xi", "bias", "ncalls", "heights",
+ * "centers", "sigmas", "grid_potential", "grid_gradient", "idx", "hist", "Fsum", "force",
+ * "Wp", "Wp_"; extensions: "cv_force" (dV/dxi), "energy" (bias energy), "jacobian". */
+psb_status psb_state_info(psb_handle* h, const char* field, int64_t* nbytes, int32_t* dtype_code,
+                          void** device_ptr);
+psb_status psb_get_state(psb_handle* h, const char* field, void* dst_host, int64_t nbytes,
+                         void* cuda_stream);
+psb_status psb_set_state(psb_handle* h, const char* field, const void* src_host, int64_t nbytes,
+                         void* cuda_stream);
+
+/* ---- multiple walkers (extension) ---------------------------------------- */
+/* Deposit steps are split so an all-gather can sit between the two halves:
+ *   psb_walker_begin : CVs + this walker's candidate hill -> `record` (k + 2 doubles:
+ *                      centre[k], height, valid) in device memory;
+ *   (caller all-gathers the records over NCCL on the same stream)
+ *   psb_walker_finish: appends `nwalkers` records in rank order, then bias + force scatter. */
+psb_status psb_walker_begin(psb_handle* h, const psb_snapshot* snap, int64_t timestep,
+                            double* record_dev, void* cuda_stream);
+psb_status psb_walker_finish(psb_handle* h, const psb_snapshot* snap, const double* records_dev,
+                             int32_t nwalkers, void* cuda_stream);
+int32_t psb_walker_record_doubles(psb_handle* h);
+/* 1 when the NEXT psb_step call is a deposit step (host mirror of metad.py:192-193). */
+int32_t psb_next_step_deposits(psb_handle* h);
+
+/* ---- utilities ----------------------------------------------------------------------- */
+/* grids.py:109-158 on the device: bin indices of n points x (n, ndim) -> out (n, ndim) u32. */
+psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64_t n,
+                          uint32_t* out_host);
+/* Kernel launches issued since creation (for bench.py's gpu_launches) and the launch shape. */
+int64_t psb_launch_count(psb_handle* h);
+psb_status psb_launch_info(psb_handle* h, int32_t* grid_blocks, int32_t* block_threads,
+                           int32_t* cooperative, int64_t* algorithmic_bytes_per_step);
+int32_t psb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYSAGES_B200_H */

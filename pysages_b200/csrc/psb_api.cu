@@ -1,0 +1,741 @@
+// psb_api.cu -- host side of the C ABI declared in include/pysages_b200.h.
+// Builds the device tables once (psb_create), then every psb_step is: [OpenMM inverse
+// permutation] [coordination gather + pair kernels] one fused cooperative step kernel, all on the
+// caller's stream, no host synchronisation.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "psb_launch.cuh"
+
+using namespace psb;
+
+namespace {
+
+thread_local std::string g_error;
+
+psb_status fail(psb_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(PSB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e),      \
+                  __FILE__, __LINE__, #expr);                                               \
+  } while (0)
+
+struct CoordWork {
+  int cv = -1;
+  int nA = 0, nB = 0, na_pad = 0, nb_pad = 0, nrt = 0, ncs = 0, R = 1, H = 3;
+  double* xa = nullptr;
+  double* xb = nullptr;
+};
+
+}  // namespace
+
+struct psb_handle {
+  Model model;
+  psb_layout_desc layout;
+  psb_method_desc method;
+  std::vector<void*> allocs;
+  std::vector<CoordWork> coord;
+  int device = 0;
+  int num_sms = 0;
+  int grid = 1;
+  size_t dyn_smem = 0;
+  int cooperative = 0;
+  long long launches = 0;
+  long long host_ncalls = 0;  // mirror of the device ncalls (deterministic)
+  long long algo_bytes = 0;
+  int record_doubles = 0;
+  // staging for psb_step_host
+  psb_snapshot dev_snap{};
+  bool have_staging = false;
+  size_t hpad = 0;
+};
+
+namespace {
+
+template <typename T>
+psb_status dev_alloc(psb_handle* h, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  if (zero) CUDA_TRY(cudaMemset(p, 0, bytes));
+  h->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return PSB_OK;
+}
+
+template <typename T>
+psb_status dev_upload(psb_handle* h, T** out, const std::vector<T>& v) {
+  psb_status st = dev_alloc(h, out, v.size(), false);
+  if (st != PSB_OK) return st;
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return PSB_OK;
+}
+
+int expected_groups(int kind) {
+  switch (kind) {
+    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: return 1;
+    case PSB_CV_DISTANCE: case PSB_CV_DISPLACEMENT: case PSB_CV_COORDINATION: return 2;
+    case PSB_CV_ANGLE: return 3;
+    case PSB_CV_DIHEDRAL: return 4;
+    default: return -1;
+  }
+}
+
+const StepVTable* pick_vtable(const psb_layout_desc& L) {
+  const bool f32 = L.real_bytes == 4;
+  switch (L.layout) {
+    case PSB_LAYOUT_HOOMD: return f32 ? &vt_hoomd_f32 : &vt_hoomd_f64;
+    case PSB_LAYOUT_OPENMM_CUDA: return f32 ? &vt_openmm_f32 : &vt_openmm_f64;
+    case PSB_LAYOUT_LAMMPS: return &vt_lammps_f64;
+    case PSB_LAYOUT_PLAIN3: return f32 ? &vt_plain3_f32 : &vt_plain3_f64;
+    default: return nullptr;
+  }
+}
+
+bool is_point(int kind) { return kind >= PSB_CV_COMPONENT && kind <= PSB_CV_DIHEDRAL; }
+
+Snap make_snap(const psb_handle* h, const psb_snapshot* s, int mode) {
+  Snap S{};
+  S.positions = s->positions;
+  S.vel_mass = s->vel_mass;
+  S.forces = s->forces;
+  S.ids = s->ids;
+  S.images = s->images;
+  S.masses = s->masses;
+  S.types = s->types;
+  for (int d = 0; d < 3; ++d) S.L[d] = s->box_diag[d];
+  S.dt = s->dt;
+  S.natoms = h->layout.natoms;
+  S.unwrap = h->layout.unwrap && h->layout.layout != PSB_LAYOUT_OPENMM_CUDA;
+  S.need_momenta = h->layout.need_momenta;
+  S.mode = mode;
+  return S;
+}
+
+psb_status check_snapshot(const psb_handle* h, const psb_snapshot* s, bool need_forces) {
+  if (!s) return fail(PSB_ERR_VALUE, "snapshot is NULL");
+  if (!s->positions) return fail(PSB_ERR_VALUE, "snapshot.positions is NULL");
+  if (need_forces && !s->forces && h->method.kind != PSB_METHOD_UNBIASED)
+    return fail(PSB_ERR_VALUE, "snapshot.forces is NULL");
+  const int L = h->layout.layout;
+  if ((L == PSB_LAYOUT_HOOMD || L == PSB_LAYOUT_OPENMM_CUDA || L == PSB_LAYOUT_LAMMPS) && !s->ids)
+    return fail(PSB_ERR_VALUE, "snapshot.ids is NULL");
+  if (h->layout.unwrap && (L == PSB_LAYOUT_HOOMD || L == PSB_LAYOUT_LAMMPS) && !s->images)
+    return fail(PSB_ERR_VALUE, "snapshot.images is NULL but the method requires box unwrapping");
+  if (h->layout.need_momenta) {
+    if (!s->vel_mass) return fail(PSB_ERR_VALUE, "snapshot.vel_mass is NULL but momenta are required");
+    if ((L == PSB_LAYOUT_LAMMPS && (!s->masses || !s->types)) || (L == PSB_LAYOUT_PLAIN3 && !s->masses))
+      return fail(PSB_ERR_VALUE, "snapshot.masses/types are NULL but momenta are required");
+    if (!(s->dt > 0.0)) return fail(PSB_ERR_VALUE, "snapshot.dt must be positive");
+  }
+  return PSB_OK;
+}
+
+// Enqueue everything one step needs.  mode: MODE_*
+psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t stream,
+                   const double* records, int nwalkers, double* record_out) {
+  Snap S = make_snap(h, s, mode);
+  S.records = records;
+  S.nwalkers = nwalkers;
+  S.record_out = record_out;
+  const Model& M = h->model;
+  const bool eval_cvs = (mode != MODE_WALKER_FINISH);
+
+  if (eval_cvs && h->layout.layout == PSB_LAYOUT_OPENMM_CUDA) {
+    const long long n = h->layout.natoms;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * h->num_sms);
+    launch_inverse_permutation(reinterpret_cast<const int*>(s->ids), M.inv_perm, n, blocks, stream);
+    ++h->launches;
+  }
+  if (eval_cvs) {
+    for (const CoordWork& cw : h->coord) {
+      pick_vtable(h->layout)->launch_gather(&M, &S, cw.cv, cw.xa, cw.na_pad, cw.xb, cw.nb_pad, stream);
+      const CvDev& cv = M.cv[cw.cv];
+      pair_launcher(cw.R, cw.H)(cw.nrt * cw.ncs, stream, cw.xa, cw.na_pad, cw.xb, cw.nb_pad, cw.nA, cw.nB,
+                                cw.nrt, 1.0 / (cv.r0 * cv.r0), cv.grad, cv.grad + 3 * (size_t)cw.nA,
+                                cv.xi_part);
+      h->launches += 2;
+    }
+  }
+  if (M.bias_dense && mode != MODE_EVAL && mode != MODE_WALKER_BEGIN) {
+    CUDA_TRY(cudaMemsetAsync(M.bias_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms, stream));
+    if (M.jac_dense)
+      CUDA_TRY(cudaMemsetAsync(M.jac_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms * M.k, stream));
+  }
+  CUDA_TRY(pick_vtable(h->layout)->launch_step(&h->model, &S, h->grid, h->dyn_smem, stream));
+  ++h->launches;
+  return PSB_OK;
+}
+
+bool host_next_deposits(const psb_handle* h) {
+  if (h->method.kind != PSB_METHOD_METAD) return false;
+  const long long n = h->host_ncalls + 1;
+  return n > 1 && (n % h->method.stride == 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* psb_last_error(void) { return g_error.c_str(); }
+int32_t psb_abi_version(void) { return 1; }
+
+void psb_destroy(psb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_desc* method,
+                      const psb_layout_desc* layout, psb_handle** out) {
+  if (!cvs || !method || !layout || !out) return fail(PSB_ERR_VALUE, "NULL argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PSB_ERR_CUDA, "no CUDA device available: pysages_b200 has no CPU fallback");
+  if (ncvs < 1 || ncvs > PSB_MAX_CVS)
+    return fail(PSB_ERR_VALUE, "between 1 and %d collective variables are supported (got %d)", PSB_MAX_CVS, ncvs);
+  if (layout->real_bytes != 4 && layout->real_bytes != 8)
+    return fail(PSB_ERR_VALUE, "layout.real_bytes must be 4 or 8");
+  if (layout->layout == PSB_LAYOUT_LAMMPS && layout->real_bytes != 8)
+    return fail(PSB_ERR_VALUE, "the LAMMPS layout is double precision");
+  if (!pick_vtable(*layout)) return fail(PSB_ERR_VALUE, "Invalid backend layout %d", layout->layout);
+  if (layout->natoms < 1) return fail(PSB_ERR_VALUE, "layout.natoms must be positive");
+
+  psb_handle* h = new psb_handle();
+  h->layout = *layout;
+  h->method = *method;
+  cudaGetDevice(&h->device);
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, h->device);
+  h->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete h;
+    return fail(PSB_ERR_CUDA, "pysages_b200 kernels are built for sm_100a; device is sm_%d%d", prop.major, prop.minor);
+  }
+  Model& M = h->model;
+  memset(&M, 0, sizeof(M));
+  M.ncv = ncvs;
+  M.natoms = layout->natoms;
+
+  auto bail = [&](psb_status st) {
+    psb_destroy(h);
+    return st;
+  };
+
+  // ---- terms, groups, components (colvars/core.py:184-207, 277-295) -------------------------
+  std::vector<uint32_t> term_tag;
+  std::vector<uint8_t> term_group;
+  int k = 0, ng = 0;
+  M.all_point = 1;
+  for (int c = 0; c < ncvs; ++c) {
+    const psb_cv_desc& d = cvs[c];
+    const int want = expected_groups(d.kind);
+    if (want < 0) return bail(fail(PSB_ERR_VALUE, "unknown collective variable kind %d", d.kind));
+    if (d.n_groups != want)
+      return bail(fail(PSB_ERR_VALUE, "Exactly %d indices or groups must be provided (got %d)", want, d.n_groups));
+    if (!d.tags || !d.group_offsets) return bail(fail(PSB_ERR_VALUE, "CV %d has no indices", c));
+    if (ng + d.n_groups > PSB_MAX_GROUPS)
+      return bail(fail(PSB_ERR_VALUE, "too many atom groups (max %d)", PSB_MAX_GROUPS));
+    CvDev& cv = M.cv[c];
+    cv.kind = d.kind;
+    cv.axis = d.axis;
+    if (d.kind == PSB_CV_COMPONENT && (d.axis < 0 || d.axis > 2))
+      return bail(fail(PSB_ERR_RUNTIME, "Invalid Cartesian axis %d index choose 0 (X), 1 (Y), 2 (Z)", d.axis));
+    cv.comp0 = k;
+    cv.ncomp = d.kind == PSB_CV_DISPLACEMENT ? 3 : 1;
+    k += cv.ncomp;
+    if (k > PSB_MAX_K) return bail(fail(PSB_ERR_VALUE, "at most %d CV components are supported", PSB_MAX_K));
+    cv.g0 = ng;
+    cv.ngroups = d.n_groups;
+    cv.t0 = (uint32_t)term_tag.size();
+    for (int g = 0; g < d.n_groups; ++g) {
+      const uint32_t a = d.group_offsets[g], b = d.group_offsets[g + 1];
+      if (b <= a) return bail(fail(PSB_ERR_VALUE, "CV %d: group %d is empty", c, g));
+      GroupDev& G = M.grp[ng];
+      G.t0 = (uint32_t)term_tag.size();
+      for (uint32_t i = a; i < b; ++i) {
+        if ((long long)d.tags[i] >= layout->natoms)
+          return bail(fail(PSB_ERR_VALUE, "CV %d: particle index %u out of range (natoms = %lld)", c, d.tags[i],
+                           (long long)layout->natoms));
+        term_tag.push_back(d.tags[i]);
+        term_group.push_back((uint8_t)ng);
+      }
+      G.t1 = (uint32_t)term_tag.size();
+      G.cv = c;
+      G.local = g;
+      G.inv_n = 1.0 / (double)(b - a);
+      ++ng;
+    }
+    cv.t1 = (uint32_t)term_tag.size();
+    if (!is_point(d.kind)) M.all_point = 0;
+    if (d.kind == PSB_CV_RMSD) M.any_rmsd = 1;
+    if (d.kind == PSB_CV_COORDINATION) M.any_coord = 1;
+  }
+  M.k = k;
+  M.ngroups = ng;
+  M.T = (uint32_t)term_tag.size();
+
+  // ---- method validation -----------------------------------------------------------------------
+  MethodDev& m = M.m;
+  m.kind = method->kind;
+  m.k = k;
+  const psb_grid_desc& gd = method->grid;
+  const bool gridded = gd.kind != PSB_GRID_NONE;
+  if (method->kind < PSB_METHOD_UNBIASED || method->kind > PSB_METHOD_ABF)
+    return bail(fail(PSB_ERR_VALUE, "unknown method kind %d", method->kind));
+  if (method->kind == PSB_METHOD_ABF && !gridded) return bail(fail(PSB_ERR_VALUE, "ABF requires a grid"));
+  if (gridded && (method->kind == PSB_METHOD_ABF || method->kind == PSB_METHOD_METAD)) {
+    if (gd.ndim != k)  // methods/core.py:435-438
+      return bail(fail(PSB_ERR_VALUE, "Grid and Collective Variable dimensions must match."));
+    m.grid_kind = gd.kind;
+    m.grid_ndim = gd.ndim;
+    m.grid_points = 1;
+    for (int d = 0; d < gd.ndim; ++d) {
+      if (gd.shape[d] < 1) return bail(fail(PSB_ERR_VALUE, "grid shape must be positive"));
+      m.g_lower[d] = gd.lower[d];
+      m.g_upper[d] = gd.upper[d];
+      m.g_shape[d] = gd.shape[d];
+      m.grid_points *= gd.shape[d];
+    }
+  }
+  memcpy(m.kspring, method->kspring, sizeof(m.kspring));
+  memcpy(m.center, method->center, sizeof(m.center));
+  m.height = method->height;
+  for (int c = 0; c < MAXK; ++c) {
+    m.sigma[c] = method->sigma[c];
+    m.periods[c] = method->periods[c];
+    m.r_lower[c] = method->r_lower[c];
+    m.r_upper[c] = method->r_upper[c];
+    m.r_kl[c] = method->r_kl[c];
+    m.r_ku[c] = method->r_ku[c];
+  }
+  m.stride = method->stride;
+  m.ngaussians = method->ngaussians;
+  m.well_tempered = method->well_tempered;
+  m.shared_hills = method->shared_hills;
+  m.deltaT_kB = method->deltaT * method->kB;
+  m.abf_N = method->abf_N;
+  m.use_pinv = method->use_pinv;
+  m.has_restraints = method->has_restraints;
+  m.force_unit_factor = method->force_unit_factor == 0.0 ? 1.0 : method->force_unit_factor;
+  if (method->kind == PSB_METHOD_METAD) {
+    if (method->stride < 1) return bail(fail(PSB_ERR_VALUE, "Metadynamics stride must be >= 1"));
+    if (method->ngaussians < 1) return bail(fail(PSB_ERR_VALUE, "Metadynamics ngaussians must be >= 1"));
+    for (int c = 0; c < k; ++c)
+      if (!(method->sigma[c] > 0.0)) return bail(fail(PSB_ERR_VALUE, "Metadynamics sigma must be positive"));
+  }
+  if (method->kind == PSB_METHOD_ABF && !layout->need_momenta)
+    return bail(fail(PSB_ERR_VALUE, "ABF needs momenta (layout.need_momenta)"));
+  M.abf_fast = (method->kind == PSB_METHOD_ABF && M.all_point) ? 1 : 0;
+
+  // ---- unique atoms (CSR) and group overlaps ---------------------------------------------------
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> order(M.T);
+    for (uint32_t t = 0; t < M.T; ++t) order[t] = {term_tag[t], t};
+    std::sort(order.begin(), order.end());
+    std::vector<uint32_t> uptr, uterm(M.T);
+    uptr.reserve(M.T + 1);
+    for (uint32_t i = 0; i < M.T;) {
+      uint32_t j = i;
+      uptr.push_back(i);
+      while (j < M.T && order[j].first == order[i].first) ++j;
+      for (uint32_t a = i; a < j; ++a) {
+        uterm[a] = order[a].second;
+        for (uint32_t b2 = i; b2 < j; ++b2)
+          M.ov[term_group[order[a].second]][term_group[order[b2].second]] += 1u;
+      }
+      i = j;
+    }
+    uptr.push_back(M.T);
+    M.Su = (uint32_t)uptr.size() - 1;
+    M.all_unique = (M.Su == M.T) ? 1 : 0;
+    psb_status st;
+    if (!M.all_unique) {
+      uint32_t* p = nullptr;
+      if ((st = dev_upload(h, &p, uptr)) != PSB_OK) return bail(st);
+      M.uniq_ptr = p;
+      if ((st = dev_upload(h, &p, uterm)) != PSB_OK) return bail(st);
+      M.uniq_term = p;
+    }
+    uint32_t* tt = nullptr;
+    uint8_t* tg = nullptr;
+    if ((st = dev_upload(h, &tt, term_tag)) != PSB_OK) return bail(st);
+    if ((st = dev_upload(h, &tg, term_group)) != PSB_OK) return bail(st);
+    M.term_tag = tt;
+    M.term_group = tg;
+    if ((st = dev_alloc(h, &M.term_slot, M.T)) != PSB_OK) return bail(st);
+  }
+
+  // ---- per-CV device data ------------------------------------------------------------------------
+  for (int c = 0; c < ncvs; ++c) {
+    const psb_cv_desc& d = cvs[c];
+    CvDev& cv = M.cv[c];
+    const uint32_t n = cv.t1 - cv.t0;
+    psb_status st;
+    if (d.kind == PSB_CV_RMSD) {
+      if (!d.reference) return bail(fail(PSB_ERR_VALUE, "RMSD needs reference coordinates"));
+      // orientation.py:121: Q = references - weighted_barycenter(references, weights)
+      std::vector<double> w(n, 1.0 / (double)n), Q(3 * (size_t)n);
+      if (d.weights) std::copy(d.weights, d.weights + n, w.begin());
+      double cen[3] = {0, 0, 0};
+      for (uint32_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) cen[a] += w[i] * d.reference[3 * (size_t)i + a];
+      for (int a = 0; a < 3; ++a) cv.sumQ[a] = 0.0;
+      for (uint32_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+          Q[3 * (size_t)i + a] = d.reference[3 * (size_t)i + a] - cen[a];
+          cv.sumQ[a] += Q[3 * (size_t)i + a];
+        }
+      double* p = nullptr;
+      if ((st = dev_upload(h, &p, Q)) != PSB_OK) return bail(st);
+      cv.ref = p;
+      if (d.weights) {
+        if ((st = dev_upload(h, &p, w)) != PSB_OK) return bail(st);
+        cv.w = p;
+      }
+    }
+    if (d.kind == PSB_CV_COORDINATION) {
+      const int nn = d.nn == 0 ? 6 : d.nn, mm = d.mm == 0 ? 12 : d.mm;
+      if (!(d.r0 > 0.0)) return bail(fail(PSB_ERR_VALUE, "CoordinationNumber r0 must be positive"));
+      if (mm != 2 * nn || nn % 2 != 0 || !pair_launcher(1, nn / 2))
+        return bail(fail(PSB_ERR_UNSUPPORTED, "CoordinationNumber supports even n in {2,4,6,8,12} with m = 2n (got n=%d, m=%d)", nn, mm));
+      cv.r0 = d.r0;
+      cv.nn = nn;
+      cv.mm = mm;
+      CoordWork cw;
+      cw.cv = c;
+      cw.H = nn / 2;
+      cw.nA = (int)(M.grp[cv.g0].t1 - M.grp[cv.g0].t0);
+      cw.nB = (int)(M.grp[cv.g0 + 1].t1 - M.grp[cv.g0 + 1].t0);
+      cw.na_pad = (cw.nA + 31) / 32 * 32;
+      cw.nb_pad = (cw.nB + 31) / 32 * 32;
+      cw.R = cw.nA > 2048 ? 4 : 1;
+      const int rows_per_cta = PAIR_BLOCK * cw.R;
+      cw.nrt = (cw.nA + rows_per_cta - 1) / rows_per_cta;
+      const int ctiles = cw.nb_pad / 32;
+      cw.ncs = std::max(1, std::min(ctiles, (2 * h->num_sms) / cw.nrt));
+      if ((st = dev_alloc(h, &cw.xa, 3 * (size_t)cw.na_pad)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &cw.xb, 3 * (size_t)cw.nb_pad)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &cv.grad, 3 * (size_t)n)) != PSB_OK) return bail(st);
+      cv.n_part = cw.nrt * cw.ncs;
+      if ((st = dev_alloc(h, &cv.xi_part, (size_t)cv.n_part)) != PSB_OK) return bail(st);
+      h->coord.push_back(cw);
+    }
+  }
+
+  // ---- state -------------------------------------------------------------------------------------
+  {
+    psb_status st;
+    StateDev& s = M.st;
+    if ((st = dev_alloc(h, &s.xi, MAXK)) != PSB_OK) return bail(st);
+    if ((st = dev_alloc(h, &s.F, MAXK)) != PSB_OK) return bail(st);
+    if ((st = dev_alloc(h, &s.energy, 1)) != PSB_OK) return bail(st);
+    if ((st = dev_alloc(h, &s.ncalls, 1)) != PSB_OK) return bail(st);
+    if (method->kind == PSB_METHOD_METAD) {
+      h->hpad = ((size_t)method->ngaussians + 2) & ~(size_t)1;
+      if ((st = dev_alloc(h, &s.heights, h->hpad)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &s.centers, h->hpad * k)) != PSB_OK) return bail(st);
+      std::vector<double> sig(method->sigma, method->sigma + MAXK);
+      if ((st = dev_upload(h, &s.sigmas, sig)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &s.idx, 1)) != PSB_OK) return bail(st);
+      if (gridded) {
+        if (method->well_tempered && (st = dev_alloc(h, &s.gp, (size_t)m.grid_points)) != PSB_OK) return bail(st);
+        if ((st = dev_alloc(h, &s.gg, (size_t)m.grid_points * k)) != PSB_OK) return bail(st);
+      }
+      h->record_doubles = k + 2;
+    }
+    if (method->kind == PSB_METHOD_ABF) {
+      if ((st = dev_alloc(h, &s.hist, (size_t)m.grid_points)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &s.Fsum, (size_t)m.grid_points * k)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &s.force, MAXK)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &s.Wp, MAXK)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &s.Wp_, MAXK)) != PSB_OK) return bail(st);
+    }
+    if ((st = dev_alloc(h, &M.fin, 1)) != PSB_OK) return bail(st);
+    if ((st = dev_alloc(h, &M.bars, 8)) != PSB_OK) return bail(st);
+    if (layout->layout == PSB_LAYOUT_OPENMM_CUDA &&
+        (st = dev_alloc(h, &M.inv_perm, (size_t)layout->natoms)) != PSB_OK)
+      return bail(st);
+    if (layout->dense_outputs) {
+      if ((st = dev_alloc(h, &M.bias_dense, 3 * (size_t)layout->natoms)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &M.jac_dense, 3 * (size_t)layout->natoms * k)) != PSB_OK) return bail(st);
+    }
+  }
+
+  // ---- launch shape --------------------------------------------------------------------------------
+  const bool metad_direct = (method->kind == PSB_METHOD_METAD && !gridded);
+  if (metad_direct) {
+    M.hill_chunk = (int)((HILL_STAGE_BYTES / ((k + 1) * 8)) & ~1);
+    h->dyn_smem = 2 * (size_t)M.hill_chunk * (k + 1) * 8;
+  }
+  const int occ = pick_vtable(*layout)->occupancy(h->dyn_smem);
+  if (occ < 1)
+    return bail(fail(PSB_ERR_CUDA, "step kernel cannot be made resident (%s)", cudaGetErrorString(cudaGetLastError())));
+  const long long max_blocks = (long long)std::min(occ, 2) * h->num_sms;
+  long long want = ((long long)M.T + BLOCK * 4 - 1) / (BLOCK * 4);
+  if (metad_direct) want = std::max(want, (long long)((method->ngaussians + M.hill_chunk - 1) / M.hill_chunk));
+  if (method->kind == PSB_METHOD_METAD && gridded)
+    want = std::max(want, (m.grid_points + BLOCK * 8 - 1) / (BLOCK * 8));
+  if (const char* env = getenv("PSB_GRID_BLOCKS")) want = atoll(env);
+  h->grid = (int)std::max(1LL, std::min(want, max_blocks));
+  h->cooperative = h->grid > 1;
+  if (h->cooperative) {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    if (!coop) return bail(fail(PSB_ERR_CUDA, "device does not support cooperative launches"));
+  }
+  {
+    psb_status st = dev_alloc(h, &M.partials, (size_t)(MAXG + 1) * NACC * h->grid);
+    if (st != PSB_OK) return bail(st);
+  }
+
+  // ---- algorithmic bytes per step ----------------------------------------------------
+  {
+    const long long rb = layout->real_bytes;
+    long long pos = 0, frc = 0, vel = 0, img = 0, idb = 8;  // index + tag->slot map
+    switch (layout->layout) {
+      case PSB_LAYOUT_HOOMD: pos = 4 * rb; frc = 8 * rb; vel = 4 * rb; img = layout->unwrap ? 12 : 0; break;
+      case PSB_LAYOUT_OPENMM_CUDA: pos = 4 * rb; frc = 48; vel = 4 * rb; break;
+      case PSB_LAYOUT_LAMMPS: pos = 24; frc = 48; vel = 24 + 4 + 8; img = layout->unwrap ? 4 : 0; break;
+      default: pos = 3 * rb; frc = 6 * rb; vel = 4 * rb; break;
+    }
+    long long per_term = idb + pos + img + (layout->need_momenta ? vel : 0);
+    long long bytes = (long long)M.T * per_term + (long long)M.Su * frc;
+    for (int c = 0; c < ncvs; ++c)
+      if (M.cv[c].kind == PSB_CV_RMSD) bytes += (long long)(M.cv[c].t1 - M.cv[c].t0) * (24 + (M.cv[c].w ? 8 : 0));
+    if (layout->layout == PSB_LAYOUT_OPENMM_CUDA) bytes += layout->natoms * 8;
+    if (metad_direct) bytes += method->ngaussians * (k + 1) * 8;
+    if (method->kind == PSB_METHOD_METAD && gridded) bytes += (k + 1) * 8;
+    if (method->kind == PSB_METHOD_ABF) bytes += 2 * (4 + 8 * k);
+    h->algo_bytes = bytes;
+  }
+  if (method->kind == PSB_METHOD_UNBIASED) h->algo_bytes -= 0;
+  *out = h;
+  return PSB_OK;
+}
+
+psb_status psb_step(psb_handle* h, const psb_snapshot* snap, int64_t timestep, void* cuda_stream) {
+  (void)timestep;
+  if (!h) return fail(PSB_ERR_VALUE, "NULL handle");
+  psb_status st = check_snapshot(h, snap, true);
+  if (st != PSB_OK) return st;
+  st = enqueue(h, snap, MODE_STEP, (cudaStream_t)cuda_stream, nullptr, 0, nullptr);
+  if (st == PSB_OK) ++h->host_ncalls;
+  return st;
+}
+
+psb_status psb_evaluate_cvs(psb_handle* h, const psb_snapshot* snap, void* cuda_stream) {
+  if (!h) return fail(PSB_ERR_VALUE, "NULL handle");
+  psb_status st = check_snapshot(h, snap, false);
+  if (st != PSB_OK) return st;
+  return enqueue(h, snap, MODE_EVAL, (cudaStream_t)cuda_stream, nullptr, 0, nullptr);
+}
+
+psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnaps, int64_t nsteps,
+                         void* cuda_stream) {
+  if (!h || !snaps || nsnaps < 1) return fail(PSB_ERR_VALUE, "invalid arguments");
+  for (int i = 0; i < nsnaps; ++i) {
+    psb_status st = check_snapshot(h, snaps + i, true);
+    if (st != PSB_OK) return st;
+  }
+  for (int64_t i = 0; i < nsteps; ++i) {
+    psb_status st = enqueue(h, snaps + (i % nsnaps), MODE_STEP, (cudaStream_t)cuda_stream, nullptr, 0, nullptr);
+    if (st != PSB_OK) return st;
+    ++h->host_ncalls;
+  }
+  return PSB_OK;
+}
+
+psb_status psb_walker_begin(psb_handle* h, const psb_snapshot* snap, int64_t timestep,
+                            double* record_dev, void* cuda_stream) {
+  (void)timestep;
+  if (!h || !record_dev) return fail(PSB_ERR_VALUE, "NULL argument");
+  if (h->method.kind != PSB_METHOD_METAD) return fail(PSB_ERR_VALUE, "walkers need Metadynamics");
+  psb_status st = check_snapshot(h, snap, true);
+  if (st != PSB_OK) return st;
+  return enqueue(h, snap, MODE_WALKER_BEGIN, (cudaStream_t)cuda_stream, nullptr, 0, record_dev);
+}
+
+psb_status psb_walker_finish(psb_handle* h, const psb_snapshot* snap, const double* records_dev,
+                             int32_t nwalkers, void* cuda_stream) {
+  if (!h || !records_dev || nwalkers < 1) return fail(PSB_ERR_VALUE, "invalid arguments");
+  if (h->method.kind != PSB_METHOD_METAD) return fail(PSB_ERR_VALUE, "walkers need Metadynamics");
+  psb_status st = check_snapshot(h, snap, true);
+  if (st != PSB_OK) return st;
+  st = enqueue(h, snap, MODE_WALKER_FINISH, (cudaStream_t)cuda_stream, records_dev, nwalkers, nullptr);
+  if (st == PSB_OK) ++h->host_ncalls;
+  return st;
+}
+
+int32_t psb_walker_record_doubles(psb_handle* h) { return h ? h->record_doubles : 0; }
+int32_t psb_next_step_deposits(psb_handle* h) { return (h && host_next_deposits(h)) ? 1 : 0; }
+
+psb_status psb_state_info(psb_handle* h, const char* field, int64_t* nbytes, int32_t* dtype_code,
+                          void** device_ptr) {
+  if (!h || !field) return fail(PSB_ERR_VALUE, "NULL argument");
+  const Model& M = h->model;
+  const StateDev& s = M.st;
+  const long long k = M.k, G = M.m.grid_points, H = M.m.ngaussians;
+  const std::string f(field);
+  void* p = nullptr;
+  long long n = 0;
+  int code = 0;  // 0 f64, 1 i64, 2 u32
+  if (f == "xi") { p = s.xi; n = 8 * k; }
+  else if (f == "cv_force") { p = s.F; n = 8 * k; }
+  else if (f == "energy") { p = s.energy; n = 8; }
+  else if (f == "ncalls") { p = s.ncalls; n = 8; code = 1; }
+  else if (f == "heights") { p = s.heights; n = 8 * H; }
+  else if (f == "centers") { p = s.centers; n = 8 * H * k; }
+  else if (f == "sigmas") { p = s.sigmas; n = 8 * k; }
+  else if (f == "grid_potential") { p = s.gp; n = 8 * G; }
+  else if (f == "grid_gradient") { p = s.gg; n = 8 * G * k; }
+  else if (f == "idx") { p = s.idx; n = 8; code = 1; }
+  else if (f == "hist") { p = s.hist; n = 4 * G; code = 2; }
+  else if (f == "Fsum") { p = s.Fsum; n = 8 * G * k; }
+  else if (f == "force") { p = s.force; n = 8 * k; }
+  else if (f == "Wp") { p = s.Wp; n = 8 * k; }
+  else if (f == "Wp_") { p = s.Wp_; n = 8 * k; }
+  else if (f == "bias") { p = M.bias_dense; n = 8 * 3 * M.natoms; }
+  else if (f == "jacobian") { p = M.jac_dense; n = 8 * 3 * M.natoms * k; }
+  else return fail(PSB_ERR_KEY, "unknown state field '%s'", field);
+  if (!p) return fail(PSB_ERR_KEY, "state field '%s' does not exist for this method", field);
+  if (nbytes) *nbytes = n;
+  if (dtype_code) *dtype_code = code;
+  if (device_ptr) *device_ptr = p;
+  return PSB_OK;
+}
+
+psb_status psb_get_state(psb_handle* h, const char* field, void* dst_host, int64_t nbytes, void* cuda_stream) {
+  int64_t n = 0;
+  void* p = nullptr;
+  psb_status st = psb_state_info(h, field, &n, nullptr, &p);
+  if (st != PSB_OK) return st;
+  if (nbytes != n) return fail(PSB_ERR_VALUE, "state field '%s' has %lld bytes (got %lld)", field, (long long)n, (long long)nbytes);
+  CUDA_TRY(cudaMemcpyAsync(dst_host, p, n, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  return PSB_OK;
+}
+
+psb_status psb_set_state(psb_handle* h, const char* field, const void* src_host, int64_t nbytes, void* cuda_stream) {
+  int64_t n = 0;
+  void* p = nullptr;
+  psb_status st = psb_state_info(h, field, &n, nullptr, &p);
+  if (st != PSB_OK) return st;
+  if (nbytes != n) return fail(PSB_ERR_VALUE, "state field '%s' has %lld bytes (got %lld)", field, (long long)n, (long long)nbytes);
+  CUDA_TRY(cudaMemcpyAsync(p, src_host, n, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (std::string(field) == "ncalls") h->host_ncalls = *reinterpret_cast<const long long*>(src_host);
+  return PSB_OK;
+}
+
+psb_status psb_step_host(psb_handle* h, const psb_snapshot* hs, int64_t timestep, void* cuda_stream,
+                         int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  const long long N = h->layout.natoms, rb = h->layout.real_bytes;
+  size_t b_pos = 0, b_vel = 0, b_frc = 0, b_ids = 0, b_img = 0, b_mass = 0, b_types = 0;
+  switch (h->layout.layout) {
+    case PSB_LAYOUT_HOOMD: b_pos = b_vel = b_frc = 4 * rb * N; b_ids = 4 * N; b_img = 12 * N; break;
+    case PSB_LAYOUT_OPENMM_CUDA: b_pos = b_vel = 4 * rb * N; b_frc = 24 * N; b_ids = 4 * N; break;
+    case PSB_LAYOUT_LAMMPS: b_pos = b_vel = b_frc = 24 * N; b_ids = 4 * (N + 1); b_img = 4 * N; b_types = 4 * N; b_mass = 8 * (size_t)std::max(h->layout.ntypes, 1); break;
+    default: b_pos = b_vel = b_frc = 3 * rb * N; b_ids = hs->ids ? 4 * N : 0; b_img = hs->images ? 12 * N : 0; b_mass = rb * N; break;
+  }
+  if (!h->layout.unwrap) b_img = 0;
+  if (!h->layout.need_momenta) b_vel = b_mass = b_types = 0;
+  if (!h->have_staging) {
+    psb_status st;
+    char* p;
+    auto grab = [&](size_t bytes, const void** dst) -> psb_status {
+      if (!bytes) { *dst = nullptr; return PSB_OK; }
+      if ((st = dev_alloc(h, &p, bytes, false)) != PSB_OK) return st;
+      *dst = p;
+      return PSB_OK;
+    };
+    const void* f = nullptr;
+    if (grab(b_pos, &h->dev_snap.positions) || grab(b_vel, &h->dev_snap.vel_mass) || grab(b_frc, &f) ||
+        grab(b_ids, &h->dev_snap.ids) || grab(b_img, &h->dev_snap.images) ||
+        grab(b_mass, &h->dev_snap.masses) || grab(b_types, &h->dev_snap.types))
+      return PSB_ERR_CUDA;
+    h->dev_snap.forces = const_cast<void*>(f);
+    h->have_staging = true;
+  }
+  psb_snapshot d = h->dev_snap;
+  memcpy(d.box_diag, hs->box_diag, sizeof(d.box_diag));
+  d.dt = hs->dt;
+  int64_t up = 0;
+  auto push = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes || !src) return cudaSuccess;
+    up += (int64_t)bytes;
+    return cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, stream);
+  };
+  CUDA_TRY(push(d.positions, hs->positions, b_pos));
+  CUDA_TRY(push(d.vel_mass, hs->vel_mass, b_vel));
+  CUDA_TRY(push(d.forces, hs->forces, b_frc));
+  CUDA_TRY(push(d.ids, hs->ids, b_ids));
+  CUDA_TRY(push(d.images, hs->images, b_img));
+  CUDA_TRY(push(d.masses, hs->masses, b_mass));
+  CUDA_TRY(push(d.types, hs->types, b_types));
+  psb_status st = psb_step(h, &d, timestep, cuda_stream);
+  if (st != PSB_OK) return st;
+  if (h->method.kind != PSB_METHOD_UNBIASED)
+    CUDA_TRY(cudaMemcpyAsync(hs->forces, d.forces, b_frc, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = (int64_t)b_frc;
+  return PSB_OK;
+}
+
+psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64_t n, uint32_t* out_host) {
+  if (!grid || !x_host || !out_host || n < 0) return fail(PSB_ERR_VALUE, "invalid arguments");
+  if (grid->kind < PSB_GRID_REGULAR || grid->kind > PSB_GRID_CHEBYSHEV || grid->ndim < 1 || grid->ndim > PSB_MAX_GRID_DIMS)
+    return fail(PSB_ERR_VALUE, "invalid grid");
+  if (n == 0) return PSB_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PSB_ERR_CUDA, "no CUDA device available: pysages_b200 has no CPU fallback");
+  const size_t cnt = (size_t)n * grid->ndim;
+  double* dx = nullptr;
+  uint32_t* di = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, cnt * 8));
+  CUDA_TRY(cudaMalloc(&di, cnt * 4));
+  CUDA_TRY(cudaMemcpy(dx, x_host, cnt * 8, cudaMemcpyHostToDevice));
+  launch_grid_index(*grid, dx, n, di);
+  cudaError_t e = cudaMemcpy(out_host, di, cnt * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(di);
+  if (e != cudaSuccess) return fail(PSB_ERR_CUDA, "CUDA error %s in psb_grid_index", cudaGetErrorString(e));
+  return PSB_OK;
+}
+
+int64_t psb_launch_count(psb_handle* h) { return h ? h->launches : 0; }
+
+psb_status psb_launch_info(psb_handle* h, int32_t* grid_blocks, int32_t* block_threads,
+                           int32_t* cooperative, int64_t* algorithmic_bytes_per_step) {
+  if (!h) return fail(PSB_ERR_VALUE, "NULL handle");
+  if (grid_blocks) *grid_blocks = h->grid;
+  if (block_threads) *block_threads = BLOCK;
+  if (cooperative) *cooperative = h->cooperative;
+  if (algorithmic_bytes_per_step) *algorithmic_bytes_per_step = h->algo_bytes;
+  return PSB_OK;
+}
+
+}  // extern "C"

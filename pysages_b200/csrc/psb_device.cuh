@@ -1,0 +1,308 @@
+// psb_device.cuh -- device-side data model of the fused bias step (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pysages_b200.h"
+#include "psb_math.cuh"
+
+namespace psb {
+
+constexpr int MAXK = PSB_MAX_K;
+constexpr int MAXG = PSB_MAX_GROUPS;
+constexpr int MAXCV = PSB_MAX_CVS;
+constexpr int NACC = 16;           // fp64 accumulators per group and pass
+constexpr int VGROUP = MAXG;       // virtual group slot used by grid-wide method reductions
+constexpr int BLOCK = 256;         // threads per CTA of the step kernel
+constexpr int NWARPS = BLOCK / 32;
+constexpr int HILL_STAGE_BYTES = 20480;  // per TMA stage (2 stages)
+constexpr int PAIR_BLOCK = 256;          // threads per CTA of the pair kernel
+
+struct GroupDev {
+  uint32_t t0, t1;  // term range
+  int32_t cv;       // owning CV
+  int32_t local;    // index of this group among the CV's groups
+  double inv_n;     // 1 / group size
+};
+
+struct CvDev {
+  int32_t kind, axis, comp0, ncomp, g0, ngroups;
+  uint32_t t0, t1;
+  const double* ref;  // RMSD: centred reference Q (n,3), device
+  const double* w;    // RMSD: weights (n), device, or nullptr (uniform 1/n)
+  double sumQ[3];     // RMSD: sum_i Q_i (0 up to rounding for uniform weights)
+  double r0;          // coordination
+  int32_t nn, mm;
+  double* grad;       // coordination: per-term gradient workspace (T_cv, 3), device
+  double* xi_part;    // coordination: per-CTA partial sums of the pair kernel
+  int32_t n_part;
+  int32_t pad;
+};
+
+struct MethodDev {
+  int32_t kind;
+  int32_t k;
+  double kspring[MAXK * MAXK];
+  double center[MAXK];
+  double height;
+  double sigma[MAXK];
+  double periods[MAXK];
+  long long stride;
+  long long ngaussians;
+  int32_t well_tempered;
+  int32_t shared_hills;
+  double deltaT_kB;  // deltaT * kB
+  long long abf_N;
+  int32_t use_pinv;
+  int32_t has_restraints;
+  double r_lower[MAXK], r_upper[MAXK], r_kl[MAXK], r_ku[MAXK];
+  double force_unit_factor;
+  int32_t grid_kind, grid_ndim;
+  double g_lower[PSB_MAX_GRID_DIMS], g_upper[PSB_MAX_GRID_DIMS];
+  int32_t g_shape[PSB_MAX_GRID_DIMS];
+  long long grid_points;
+};
+
+struct StateDev {
+  double* xi;        // (k)
+  double* F;         // (k) generalized force dV/dxi
+  double* energy;    // (1)
+  long long* ncalls; // (1)
+  // metadynamics
+  double* heights;   // (Hpad)
+  double* centers;   // (Hpad, k)
+  double* sigmas;    // (k)
+  double* gp;        // grid_potential (G) or nullptr
+  double* gg;        // grid_gradient (G, k) or nullptr
+  long long* idx;    // (1)
+  // ABF
+  uint32_t* hist;    // (G)
+  double* Fsum;      // (G, k)
+  double* force;     // (k)
+  double* Wp;        // (k)
+  double* Wp_;       // (k)
+};
+
+// Results of the in-kernel finalizers, global memory, written by one CTA, read by all.
+struct Fin {
+  double xi[MAXK];
+  double F[MAXK];
+  double energy;
+  double fg[MAXG][3];       // -sum_c F_c dxi_c/dpoint_g / n_g   (point CVs)
+  double gpt[MAXG][3][3];   // dxi_{comp0+j}/dpoint_g
+  double cvx[MAXCV][20];    // RMSD: U[0..8], rbar[9..11], sumD[12..14], coef[15]; RoG: coef[0]
+  double hill[MAXK + 2];    // candidate / deposited hill: centre[k], height, valid
+  uint32_t I[PSB_MAX_GRID_DIMS];
+  int32_t oob;
+  int32_t deposit;
+  long long nh;             // number of hills summed this step
+};
+
+struct BarrierState {
+  unsigned long long arrive;
+  unsigned long long release;
+};
+
+struct Model {
+  int32_t ncv, k, ngroups, all_unique;
+  uint32_t T, Su;
+  int32_t any_rmsd, any_coord, abf_fast, all_point;
+  CvDev cv[MAXCV];
+  GroupDev grp[MAXG];
+  uint32_t ov[MAXG][MAXG];    // group overlap counts (ABF fast path)
+  const uint32_t* term_tag;   // (T)
+  const uint8_t* term_group;  // (T)
+  uint32_t* term_slot;        // (T) workspace: slot of each term, written in pass A
+  const uint32_t* uniq_ptr;   // (Su+1) CSR over unique atoms -> terms (nullptr if all_unique)
+  const uint32_t* uniq_term;  // (T)
+  MethodDev m;
+  StateDev st;
+  Fin* fin;
+  double* partials;           // ((MAXG+1) * NACC, gridDim) fp64
+  BarrierState* bars;         // (8)
+  uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
+  double* bias_dense;         // (N,3) or nullptr
+  double* jac_dense;          // (k,3N) or nullptr
+  long long natoms;
+  int32_t hill_chunk;         // hills per TMA stage
+  int32_t pad;
+};
+
+struct Snap {
+  const void* positions;
+  const void* vel_mass;
+  void* forces;
+  const void* ids;
+  const void* images;
+  const void* masses;
+  const void* types;
+  double L[3];
+  double dt;
+  long long natoms;
+  int32_t unwrap;
+  int32_t need_momenta;
+  int32_t mode;  // 0 full step, 1 evaluate CVs only, 2 walker begin, 3 walker finish
+  int32_t nwalkers;
+  const double* records;  // walker finish: gathered hill records
+  double* record_out;     // walker begin: this walker's record
+};
+
+enum { MODE_STEP = 0, MODE_EVAL = 1, MODE_WALKER_BEGIN = 2, MODE_WALKER_FINISH = 3 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- engine layouts -------------------------------------------------------------------------
+template <int LAYOUT, typename Real>
+struct Access;
+
+template <typename Real>
+struct Real4;
+template <>
+struct Real4<float> { using type = float4; };
+template <>
+struct Real4<double> { using type = double4; };
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// hoomd.py:148-202
+template <typename Real>
+struct Access<PSB_LAYOUT_HOOMD, Real> {
+  using R4 = typename Real4<Real>::type;
+  static __device__ __forceinline__ uint32_t slot(const Snap& s, const Model&, uint32_t tag) {
+    return __ldg(reinterpret_cast<const uint32_t*>(s.ids) + tag);
+  }
+  static __device__ __forceinline__ V3 position(const Snap& s, uint32_t slot) {
+    const R4 p = ldg4(reinterpret_cast<const R4*>(s.positions) + slot);
+    V3 r = v3((double)p.x, (double)p.y, (double)p.z);
+    if (s.unwrap) {  // hoomd.py:179-181: pos + diag(H) * images, in fp64
+      const int* im = reinterpret_cast<const int*>(s.images) + 3 * (size_t)slot;
+      r.x = __dadd_rn(r.x, __dmul_rn(s.L[0], (double)__ldg(im + 0)));
+      r.y = __dadd_rn(r.y, __dmul_rn(s.L[1], (double)__ldg(im + 1)));
+      r.z = __dadd_rn(r.z, __dmul_rn(s.L[2], (double)__ldg(im + 2)));
+    }
+    return r;
+  }
+  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) {
+    // hoomd.py:192-196: (M * V) in the array's own dtype, promoted afterwards
+    const R4 v = ldg4(reinterpret_cast<const R4*>(s.vel_mass) + slot);
+    return v3((double)(Real)(v.w * v.x), (double)(Real)(v.w * v.y), (double)(Real)(v.w * v.z));
+  }
+  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
+    // hoomd.py:229: forces[:, :3] += biases  (fp64 sum, rounded once to the force dtype)
+    R4* f = reinterpret_cast<R4*>(s.forces) + slot;
+    R4 v = *f;
+    v.x = (Real)((double)v.x + b.x);
+    v.y = (Real)((double)v.y + b.y);
+    v.z = (Real)((double)v.z + b.z);
+    *f = v;
+  }
+};
+
+// openmm.py:64-89, 100-143 (CUDA platform)
+template <typename Real>
+struct Access<PSB_LAYOUT_OPENMM_CUDA, Real> {
+  using R4 = typename Real4<Real>::type;
+  static __device__ __forceinline__ uint32_t slot(const Snap&, const Model& m, uint32_t tag) {
+    return __ldcg(m.inv_perm + tag);  // ids.argsort()[tag] (openmm.py:106-107)
+  }
+  static __device__ __forceinline__ V3 position(const Snap& s, uint32_t slot) {
+    const R4 p = ldg4(reinterpret_cast<const R4*>(s.positions) + slot);
+    return v3((double)p.x, (double)p.y, (double)p.z);  // never unwrapped (openmm.py:122-123)
+  }
+  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) {
+    // openmm.py:96-97,125-127: v / invM, or v when invM == 0
+    const R4 v = ldg4(reinterpret_cast<const R4*>(s.vel_mass) + slot);
+    if (v.w == (Real)0) return v3((double)v.x, (double)v.y, (double)v.z);
+    return v3((double)(Real)(v.x / v.w), (double)(Real)(v.y / v.w), (double)(Real)(v.z / v.w));
+  }
+  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
+    // openmm.py:141-143,167-169: int64(2**32 * bias.T) added to forces (3, Np)
+    long long* f = reinterpret_cast<long long*>(s.forces);
+    f[0 * s.natoms + slot] += (long long)(4294967296.0 * b.x);
+    f[1 * s.natoms + slot] += (long long)(4294967296.0 * b.y);
+    f[2 * s.natoms + slot] += (long long)(4294967296.0 * b.z);
+  }
+};
+
+// (N,3) arrays: LAMMPS (lammps.py:87-113,182-223) and OpenMM CPU-platform style (PLAIN3)
+template <typename Real>
+struct Plain3 {
+  static __device__ __forceinline__ V3 load3(const void* base, uint32_t slot) {
+    const Real* p = reinterpret_cast<const Real*>(base) + 3 * (size_t)slot;
+    return v3((double)__ldg(p), (double)__ldg(p + 1), (double)__ldg(p + 2));
+  }
+  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
+    Real* f = reinterpret_cast<Real*>(s.forces) + 3 * (size_t)slot;
+    f[0] = (Real)((double)f[0] + b.x);
+    f[1] = (Real)((double)f[1] + b.y);
+    f[2] = (Real)((double)f[2] + b.z);
+  }
+};
+
+template <typename Real>
+struct Access<PSB_LAYOUT_LAMMPS, Real> {
+  static __device__ __forceinline__ uint32_t slot(const Snap& s, const Model&, uint32_t tag) {
+    return (uint32_t)__ldg(reinterpret_cast<const int*>(s.ids) + tag + 1);  // ids = tags_map[1:]
+  }
+  static __device__ __forceinline__ V3 position(const Snap& s, uint32_t slot) {
+    V3 r = Plain3<Real>::load3(s.positions, slot);
+    if (s.unwrap) {  // lammps.py:188-202: (image >> bits & mask) - kImgMax, SMALLBIG packing
+      const int im = __ldg(reinterpret_cast<const int*>(s.images) + slot);
+      const int ix = (im & 1023) - 512, iy = ((im >> 10) & 1023) - 512, iz = (im >> 20) - 512;
+      r.x = __dadd_rn(r.x, __dmul_rn(s.L[0], (double)ix));
+      r.y = __dadd_rn(r.y, __dmul_rn(s.L[1], (double)iy));
+      r.z = __dadd_rn(r.z, __dmul_rn(s.L[2], (double)iz));
+    }
+    return r;
+  }
+  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) {
+    // lammps.py:213-217: masses[types] * v
+    const int ty = __ldg(reinterpret_cast<const int*>(s.types) + slot);
+    const double mass = __ldg(reinterpret_cast<const double*>(s.masses) + ty);
+    const V3 v = Plain3<Real>::load3(s.vel_mass, slot);
+    return v3(mass * v.x, mass * v.y, mass * v.z);
+  }
+  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
+    Plain3<Real>::add_force(s, slot, b);
+  }
+};
+
+template <typename Real>
+struct Access<PSB_LAYOUT_PLAIN3, Real> {
+  static __device__ __forceinline__ uint32_t slot(const Snap& s, const Model&, uint32_t tag) {
+    return s.ids ? (uint32_t)__ldg(reinterpret_cast<const int*>(s.ids) + tag) : tag;
+  }
+  static __device__ __forceinline__ V3 position(const Snap& s, uint32_t slot) {
+    V3 r = Plain3<Real>::load3(s.positions, slot);
+    if (s.unwrap && s.images) {
+      const int* im = reinterpret_cast<const int*>(s.images) + 3 * (size_t)slot;
+      r.x = __dadd_rn(r.x, __dmul_rn(s.L[0], (double)__ldg(im + 0)));
+      r.y = __dadd_rn(r.y, __dmul_rn(s.L[1], (double)__ldg(im + 1)));
+      r.z = __dadd_rn(r.z, __dmul_rn(s.L[2], (double)__ldg(im + 2)));
+    }
+    return r;
+  }
+  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) {
+    // openmm.py:96-97,125-127 with (velocities, invMass) stored separately
+    const V3 v = Plain3<Real>::load3(s.vel_mass, slot);
+    const Real im = __ldg(reinterpret_cast<const Real*>(s.masses) + slot);
+    if (im == (Real)0) return v;
+    return v3((double)(Real)((Real)v.x / im), (double)(Real)((Real)v.y / im),
+              (double)(Real)((Real)v.z / im));
+  }
+  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
+    Plain3<Real>::add_force(s, slot, b);
+  }
+};
+
+}  // namespace psb

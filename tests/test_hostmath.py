@@ -1,0 +1,137 @@
+"""
+CPU unit tests of the scalar fp64 building blocks the CUDA kernels are made of
+(pysages_b200/csrc/psb_math.cuh compiled for the host by tests/hostmath), checked against the
+oracle's autodiff and the reference's known answers.  No GPU needed.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import colvars, grids
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    src = os.path.join(HERE, "hostmath", "hostmath.cpp")
+    out = os.path.join(HERE, "hostmath", "_hostmath.so")
+    hdr = os.path.join(HERE, "..", "pysages_b200", "csrc", "psb_math.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-ffp-contract=off", src, "-o", out])
+    lib = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    for name in ("hm_distance", "hm_angle", "hm_dihedral"):
+        getattr(lib, name).restype = ctypes.c_double
+        getattr(lib, name).argtypes = [dp, dp]
+    lib.hm_kabsch.argtypes = [dp, dp]
+    lib.hm_grid_index.restype = ctypes.c_uint
+    lib.hm_grid_index.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+    lib.hm_mesh_coord.restype = ctypes.c_double
+    lib.hm_mesh_coord.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+    lib.hm_chol_solve.argtypes = [ctypes.c_int, dp, dp, dp]
+    lib.hm_pinv_solve.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double]
+    lib.hm_wrap.restype = ctypes.c_double
+    lib.hm_wrap.argtypes = [ctypes.c_double, ctypes.c_double]
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+@pytest.mark.parametrize("name, fn, npts", [("hm_distance", colvars.distance, 2), ("hm_angle", colvars.angle, 3),
+                                            ("hm_dihedral", colvars.dihedral_angle, 4)])
+def test_point_cv_gradients_match_autodiff(hm, name, fn, npts):
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        p = rng.normal(size=(npts, 3)) * rng.uniform(0.5, 5.0)
+        g = np.zeros((npts, 3))
+        val = getattr(hm, name)(_ptr(p), _ptr(g))
+        t = torch.tensor(p, requires_grad=True)
+        ref = fn(*t)
+        (gref,) = torch.autograd.grad(ref, t)
+        assert abs(val - ref.item()) <= 1e-13 * max(1.0, abs(ref.item()))
+        assert np.allclose(g, gref.numpy(), rtol=1e-10, atol=1e-13)
+
+
+def test_kabsch_matches_svd_reference(hm, golden):
+    rng = np.random.default_rng(3)
+    pairs = [(golden["ci2_1"], golden["ci2_2"]), (golden["ci2_1"], golden["ci2_1t"]), (golden["ci2_2"], golden["ci2_12"])]
+    for _ in range(20):
+        P = rng.normal(size=(30, 3)); Q = rng.normal(size=(30, 3))
+        pairs.append((P, Q))
+    for P, Q in pairs:
+        P = P - P.mean(0); Q = Q - Q.mean(0)
+        C = np.ascontiguousarray(P.T @ Q)
+        U = np.zeros((3, 3))
+        hm.hm_kabsch(_ptr(C), _ptr(U))
+        Uref = colvars.kabsch(torch.tensor(P), torch.tensor(Q)).numpy()
+        assert np.allclose(U, Uref, atol=1e-12)
+        assert abs(np.linalg.det(U) - 1) < 1e-12
+
+
+def test_kabsch_reflection_case(hm):
+    # covariance with negative determinant: the proper rotation, not the reflection
+    rng = np.random.default_rng(5)
+    P = rng.normal(size=(8, 3)); P -= P.mean(0)
+    Q = P * np.array([1.0, 1.0, -1.0]) + 0.01 * rng.normal(size=(8, 3)); Q -= Q.mean(0)
+    C = np.ascontiguousarray(P.T @ Q)
+    assert np.linalg.det(C) < 0
+    U = np.zeros((3, 3))
+    hm.hm_kabsch(_ptr(C), _ptr(U))
+    Uref = colvars.kabsch(torch.tensor(P), torch.tensor(Q)).numpy()
+    assert np.allclose(U, Uref, atol=1e-10)
+
+
+def test_grid_index_bit_exact(hm, golden):
+    pi = np.pi
+    for tag, kind in (("regular", 1), ("periodic", 2), ("cheb", 3)):
+        for x, i in zip(golden[f"grid1d_x_{tag}"], golden[f"grid1d_i_{tag}"]):
+            assert hm.hm_grid_index(kind, float(x), -pi, pi, 64) == int(i)
+    rng = np.random.default_rng(11)
+    for kind, gk in ((1, grids.Regular), (2, grids.Periodic), (3, grids.Chebyshev)):
+        for lower, upper, shape in ((-pi, pi, 50), (0.0, 1.0, 10), (-2.5, 7.25, 64), (0.0, 23.2, 64)):
+            g = grids.Grid((lower,), (upper,), (shape,), kind=gk)
+            get_index = grids.build_indexer(g)
+            h = (upper - lower) / shape
+            xs = np.concatenate([lower + h * np.arange(-2, shape + 3), rng.uniform(lower - 1, upper + 1, 2000),
+                                 np.nextafter(lower + h * np.arange(shape + 1), np.inf),
+                                 np.nextafter(lower + h * np.arange(shape + 1), -np.inf)])
+            for x in xs:
+                assert hm.hm_grid_index(kind, float(x), lower, upper, shape) == int(get_index(x)[0]), (kind, x)
+
+
+def test_mesh_and_wrap(hm):
+    g = grids.Grid((-np.pi,), (np.pi,), (50,))
+    mesh = grids.compute_mesh(g)[:, 0]
+    got = np.array([hm.hm_mesh_coord(1, k, -np.pi, np.pi, 50) for k in range(50)])
+    assert np.array_equal(mesh, got)
+    gc = grids.Grid((-1.0,), (3.0,), (16,), kind=grids.Chebyshev)
+    got = np.array([hm.hm_mesh_coord(3, k, -1.0, 3.0, 16) for k in range(16)])
+    assert np.allclose(grids.compute_mesh(gc)[:, 0], got, rtol=1e-15, atol=1e-15)
+    P = torch.tensor([2 * np.pi, np.inf], dtype=torch.float64)
+    for x in (-7.0, -3.2, -0.1, 0.0, 2.9, 3.3, 6.0):
+        w = colvars.wrap(torch.tensor([x, x], dtype=torch.float64), P).numpy()
+        assert hm.hm_wrap(x, 2 * np.pi) == w[0] and hm.hm_wrap(x, np.inf) == w[1]
+
+
+def test_small_solvers(hm):
+    rng = np.random.default_rng(2)
+    for k in (1, 2, 3, 4):
+        J = rng.normal(size=(k, 12))
+        A = J @ J.T
+        b = rng.normal(size=k)
+        A4 = np.zeros((4, 4)); A4[:k, :k] = A
+        x = np.zeros(4)
+        assert hm.hm_chol_solve(k, _ptr(A4), _ptr(b), _ptr(x)) == 1
+        assert np.allclose(x[:k], np.linalg.solve(A, b), rtol=1e-11)
+        x2 = np.zeros(4)
+        hm.hm_pinv_solve(k, _ptr(A4), _ptr(b), _ptr(x2), 1e-14)
+        assert np.allclose(x2[:k], np.linalg.pinv(A) @ b, rtol=1e-9)
+    A4 = np.zeros((4, 4)); A4[0, 0] = -1.0
+    assert hm.hm_chol_solve(1, _ptr(A4), _ptr(np.ones(1)), _ptr(np.zeros(4))) == 0
