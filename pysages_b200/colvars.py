@@ -1,0 +1,245 @@
+"""
+Collective variables: host-side descriptors for the fused CUDA step.
+
+Mirrors the reference constructors (pysages/colvars/core.py:24-147, coordinates.py, angles.py,
+shape.py:14-35, orientation.py:98-126): same names, same index / group conventions, same errors.
+No numerical work happens here; `describe()` lowers a CV to the `psb_cv_desc` consumed by
+psb_create (include/pysages_b200.h) and the kernels in csrc/psb_step.cuh evaluate the CV and its
+closed-form Jacobian on the device.
+"""
+
+import math
+from numbers import Integral
+
+import numpy as np
+
+from . import _native as N
+
+
+def _is_group(obj):
+    # colvars/core.py:302-314
+    if isinstance(obj, (Integral, np.integer, range)):
+        return False
+    if isinstance(obj, (list, tuple, np.ndarray)):
+        return True
+    raise ValueError(f"Invalid indices or group: {obj}")
+
+
+def _flatten(obj, out):
+    if isinstance(obj, (Integral, np.integer)):
+        out.append(int(obj))
+    elif isinstance(obj, range):
+        out.extend(obj)
+    else:
+        for o in obj:
+            _flatten(o, out)
+
+
+def _process_groups(indices):
+    """colvars/core.py:277-295: flat uint32 indices + one arange slice per group."""
+    total = 0
+    collected, groups = [], []
+    for obj in indices:
+        found = _is_group(obj)
+        before = len(collected)
+        _flatten(obj, collected)
+        n = len(collected) - before
+        if found:
+            groups.append(np.arange(total, total + n, dtype=np.uint32))
+        total += n
+    if any(i < 0 for i in collected):
+        raise ValueError("particle indices must be non-negative")
+    return np.asarray(collected, dtype=np.uint32), groups
+
+
+def _check_groups_size(indices, groups, group_length):
+    # colvars/core.py:171-176
+    input_length = np.size(indices, 0) - sum(np.size(g, 0) - 1 for g in groups)
+    if input_length != group_length:
+        raise ValueError(
+            f"Exactly {group_length} indices or groups must be provided (got {input_length})"
+        )
+
+
+class CollectiveVariable:
+    """colvars/core.py:24-63"""
+
+    _multicomponent = False
+    _kind = None
+    _nargs = 1  # arity of the reference's `function` (colvars/core.py:190-207)
+
+    def __init__(self, indices, group_length=None):
+        indices, groups = _process_groups(indices)
+        if group_length is not None:
+            _check_groups_size(indices, groups, group_length)
+        self.indices = indices
+        self.groups = groups
+        self.requires_box_unwrapping = True
+
+    @property
+    def multicomponent(self):
+        return self._multicomponent
+
+    @property
+    def ncomponents(self):
+        return 3 if self._multicomponent else 1
+
+    def points(self):
+        """
+        The atom groups whose barycentres are the CV's arguments, following the three
+        evaluation modes of colvars/core.py:190-207:
+          1-argument functions get the whole gathered block;
+          without groups every index is one point;
+          with groups only the groups are used (bare indices are silently dropped -- quirk kept).
+        """
+        if self._nargs == 1:
+            return [self.indices]
+        if len(self.groups) == 0:
+            return [self.indices[i : i + 1] for i in range(len(self.indices))]
+        return [self.indices[g] for g in self.groups]
+
+    def describe(self, keep):
+        """-> psb_cv_desc; `keep` collects the numpy buffers the descriptor points into."""
+        pts = self.points()
+        if len(pts) != self._nargs:
+            raise ValueError(
+                f"Exactly {self._nargs} indices or groups must be provided (got {len(pts)})"
+            )
+        tags = np.ascontiguousarray(np.concatenate(pts), dtype=np.uint32)
+        offsets = np.zeros(len(pts) + 1, dtype=np.uint32)
+        offsets[1:] = np.cumsum([len(p) for p in pts])
+        keep += [tags, offsets]
+        d = N.CvDesc()
+        d.kind = self._kind
+        d.axis = getattr(self, "axis", 0)
+        d.n_groups = len(pts)
+        d.tags = tags.ctypes.data_as(N.POINTER(N.c_uint32))
+        d.group_offsets = offsets.ctypes.data_as(N.POINTER(N.c_uint32))
+        return d
+
+
+class AxisCV(CollectiveVariable):
+    """colvars/core.py:67-86"""
+
+    def __init__(self, indices, axis, group_length=None):
+        if axis not in (0, 1, 2):
+            raise RuntimeError(f"Invalid Cartesian axis {axis} index choose 0 (X), 1 (Y), 2 (Z)")
+        super().__init__(indices, group_length)
+        self.axis = axis
+
+
+class TwoPointCV(CollectiveVariable):
+    _nargs = 2
+
+    def __init__(self, indices):
+        super().__init__(indices, 2)
+
+
+class ThreePointCV(CollectiveVariable):
+    _nargs = 3
+
+    def __init__(self, indices):
+        super().__init__(indices, 3)
+
+
+class FourPointCV(CollectiveVariable):
+    _nargs = 4
+
+    def __init__(self, indices):
+        super().__init__(indices, 4)
+
+
+class Component(AxisCV):
+    """colvars/coordinates.py:56-71: Cartesian component of the barycentre of the selection."""
+
+    _kind = N.CV_COMPONENT
+
+
+class Distance(TwoPointCV):
+    """colvars/coordinates.py:74-109: distance between two points / group barycentres."""
+
+    _kind = N.CV_DISTANCE
+
+
+class Displacement(TwoPointCV):
+    """colvars/coordinates.py:112-148 (multicomponent, k = 3): r2 - r1."""
+
+    _kind = N.CV_DISPLACEMENT
+    _multicomponent = True
+
+
+class Angle(ThreePointCV):
+    """colvars/angles.py:24-74.  Groups are taken as barycentres (extension: the reference only
+    works with three bare indices)."""
+
+    _kind = N.CV_ANGLE
+
+
+class DihedralAngle(FourPointCV):
+    """colvars/angles.py:77-128."""
+
+    _kind = N.CV_DIHEDRAL
+
+
+class RadiusOfGyration(CollectiveVariable):
+    """
+    colvars/shape.py:14-57.  Value parity with the reference quirk: sum_i r_i.r_i / n (uncentred,
+    squared, no sqrt); the reference returns it replicated on a 3-vector and cannot differentiate
+    it, here it is one scalar component with Jacobian 2 r_i / n (parity unpinned).
+    """
+
+    _kind = N.CV_ROG
+
+
+class RMSD(CollectiveVariable):
+    """colvars/orientation.py:98-126 (Kabsch-fitted RMSD to `references`)."""
+
+    _kind = N.CV_RMSD
+
+    def __init__(self, indices, references, weights=None):
+        if weights is not None and len(indices) != len(weights):
+            raise RuntimeError("Indices and weights must be of the same length")
+        super().__init__(indices)
+        self.references = np.ascontiguousarray(references, dtype=np.float64)
+        if self.references.shape != (len(self.indices), 3):
+            raise ValueError("references must have shape (len(indices), 3)")
+        self.weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+
+    def describe(self, keep):
+        d = super().describe(keep)
+        keep.append(self.references)
+        d.reference = self.references.ctypes.data_as(N.POINTER(N.c_double))
+        if self.weights is not None:
+            keep.append(self.weights)
+            d.weights = self.weights.ctypes.data_as(N.POINTER(N.c_double))
+        return d
+
+
+class CoordinationNumber(TwoPointCV):
+    """
+    Pairwise coordination number between two groups (extension; absent from the reference):
+    xi = sum_{i in A, j in B} (1 - x^n) / (1 - x^m), x = r_ij / r0, defaults n = 6, m = 12.
+    """
+
+    _kind = N.CV_COORDINATION
+
+    def __init__(self, indices, r0=1.0, n=6, m=12):
+        super().__init__(indices)
+        if len(self.groups) != 2:
+            raise ValueError("CoordinationNumber needs two groups of atoms")
+        self.r0, self.n, self.m = float(r0), int(n), int(m)
+
+    def describe(self, keep):
+        d = super().describe(keep)
+        d.r0, d.nn, d.mm = self.r0, self.n, self.m
+        return d
+
+
+def get_periods(cvs):
+    """colvars/utils.py:13-19: 2*pi for EXACT Angle / DihedralAngle types, inf otherwise;
+    one entry per CV component."""
+    out = []
+    for cv in cvs:
+        p = 2 * math.pi if type(cv) in (Angle, DihedralAngle) else math.inf
+        out += [p] * cv.ncomponents
+    return out

@@ -1,0 +1,134 @@
+"""
+`run` / `Result` orchestration (pysages/methods/core.py:34-59, 160-413; umbrella_integration.py:128-203).
+
+One simulation = one process = one GPU; replicas are independent tasks on an Executor exactly as in
+the reference (`ReplicasConfiguration`).  For multi-GPU runs launch one process per GPU
+(`torchrun`) and use `pysages_b200.parallel` to partition windows / share hills.
+"""
+
+from copy import deepcopy
+
+from .backends.core import SamplingContext
+from .methods import SamplingMethod, UmbrellaIntegration
+from .utils import ReplicasConfiguration, SerialExecutor
+
+
+class Result:
+    """methods/core.py:34-59"""
+
+    def __init__(self, method, states, callbacks, snapshots):
+        self.method = method
+        self.states = states
+        self.callbacks = callbacks
+        self.snapshots = snapshots
+
+
+class ReplicaResult(Result):
+    pass
+
+
+def _run(method_or_result, context_generator, timesteps, context_args=None, callback=None,
+         post_run_action=None, **kwargs):
+    """methods/core.py:327-413 (fresh run, or restart from a ReplicaResult)."""
+    timesteps = int(timesteps)
+    context_args = {} if context_args is None else context_args
+    restart = isinstance(method_or_result, ReplicaResult)
+    method = method_or_result.method if restart else method_or_result
+    if restart:
+        callback = method_or_result.callbacks
+    sampling_context = SamplingContext(method, context_generator, callback, context_args)
+    context_args["context"] = sampling_context.context
+    sampler = sampling_context.sampler
+    if restart:
+        sampler.restore(method_or_result.snapshots)
+        native = sampler._method_update.native
+        prev = method_or_result.states
+        for field in prev._fields:
+            value = getattr(prev, field)
+            if value is not None and field != "bias":
+                native.set_state(field, value.cpu().numpy() if hasattr(value, "cpu") else value)
+        sampler.state = method._make_state(native)
+    with sampling_context:
+        sampling_context.run(timesteps, **kwargs)
+        if post_run_action:
+            post_run_action(**context_args)
+    return ReplicaResult(method, sampler.state, callback, sampler.take_snapshot())
+
+
+def run(method_or_result, context_generator, timesteps, callback=None, context_args=None,
+        post_run_action=None, config=None, executor=None, executor_shutdown=True, **kwargs):
+    """pysages.run: dispatches on the method type like the reference's plum table."""
+    context_args = {} if context_args is None else context_args
+    method = method_or_result.method if isinstance(method_or_result, Result) else method_or_result
+    if isinstance(method, UmbrellaIntegration):
+        return _run_umbrella(method_or_result, context_generator, timesteps, context_args,
+                             post_run_action, executor or SerialExecutor(), executor_shutdown, **kwargs)
+    if not isinstance(method, SamplingMethod):
+        raise TypeError(f"{method!r} is not a SamplingMethod")
+    config = config or ReplicasConfiguration()
+    if isinstance(method_or_result, Result):  # methods/core.py:239-318
+        result = method_or_result
+        futures = [
+            config.executor.submit(
+                _run, ReplicaResult(method, result.states[i], _nth(result.callbacks, i), result.snapshots[i]),
+                context_generator, timesteps, deepcopy(context_args), None, post_run_action, **kwargs)
+            for i in range(len(result.states))
+        ]
+    else:
+        futures = [
+            config.executor.submit(_run, method, context_generator, timesteps, deepcopy(context_args),
+                                   callback, post_run_action, **kwargs)
+            for _ in range(config.copies)
+        ]
+    results = [f.result() for f in futures]
+    callbacks = None if (callback is None and not isinstance(method_or_result, Result)) else [r.callbacks for r in results]
+    return Result(method, [r.states for r in results], callbacks, [r.snapshots for r in results])
+
+
+def _nth(seq, i):
+    return None if seq is None else seq[i]
+
+
+def _run_umbrella(method_or_result, context_generator, timesteps, context_args, post_run_action,
+                  executor, executor_shutdown, windows=None, **kwargs):
+    """umbrella_integration.py:128-203; `windows` restricts the run to a subset (multi-GPU partition)."""
+    restart = isinstance(method_or_result, Result)
+    method = method_or_result.method if restart else method_or_result
+    todo = list(range(len(method.submethods))) if windows is None else list(windows)
+    futures = []
+    for n in todo:
+        replica_args = deepcopy(context_args)
+        replica_args["replica_num"] = n
+        if restart:
+            r = method_or_result
+            arg = ReplicaResult(method.submethods[n], r.states[n], method.histograms[n], r.snapshots[n])
+            futures.append(executor.submit(_run, arg, context_generator, timesteps, replica_args, None,
+                                           post_run_action, **kwargs))
+        else:
+            futures.append(executor.submit(_run, method.submethods[n], context_generator, timesteps,
+                                           replica_args, method.histograms[n], post_run_action, **kwargs))
+    results = [f.result() for f in futures]
+    if executor_shutdown:
+        executor.shutdown()
+    return Result(method, [r.states for r in results], [r.callbacks for r in results],
+                  [r.snapshots for r in results])
+
+
+def analyze(result):
+    """umbrella_integration.py:220-261 (host-side, trivial) -- other methods' analysis is out of scope."""
+    import numpy as np
+
+    method = result.method
+    if not isinstance(method, UmbrellaIntegration):
+        raise NotImplementedError("analyze() is implemented for UmbrellaIntegration only (DESIGN.md scope)")
+    ksprings = [s.kspring for s in method.submethods]
+    centers = [s.center for s in method.submethods]
+    hist_means = [cb.get_means() for cb in result.callbacks]
+    mean_forces, free_energy = [], [0.0]
+    for i, (k, c, mean) in enumerate(zip(ksprings, centers, hist_means)):
+        mean_forces.append(-(k @ (mean - c)))  # eq. 13 of doi:10.1063/1.3175798
+        if i > 0:
+            free_energy.append(free_energy[i - 1] + mean_forces[i - 1].T @ (centers[i] - centers[i - 1]))
+    return dict(ksprings=np.asarray(ksprings), centers=np.asarray(centers), histograms=result.callbacks,
+                histogram_means=np.asarray(hist_means), mean_forces=np.asarray(mean_forces),
+                free_energy=np.asarray(free_energy, dtype=np.float64))

@@ -12,6 +12,15 @@
 #define PSB_HD inline
 #endif
 
+// exact (never FMA-contracted) multiply / add, for arithmetic whose bits must match the reference
+#ifdef __CUDA_ARCH__
+#define PSB_MUL(a, b) __dmul_rn((a), (b))
+#define PSB_ADD(a, b) __dadd_rn((a), (b))
+#else
+#define PSB_MUL(a, b) ((a) * (b))
+#define PSB_ADD(a, b) ((a) + (b))
+#endif
+
 namespace psb {
 
 struct V3 {
@@ -137,7 +146,7 @@ PSB_HD double mesh_coord(int kind, int32_t k, double lower, double upper, int32_
     u = -cos(((double)k + 0.5) * 3.141592653589793 / n);
   else
     u = -1.0 + (2.0 * (double)k + 1.0) / n;
-  return (u + 1.0) / 2.0 * (upper - lower) + lower;
+  return PSB_ADD(PSB_MUL((u + 1.0) / 2.0, upper - lower), lower);
 }
 
 // ---- small dense linear algebra -------------------------------------------------------------

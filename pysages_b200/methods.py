@@ -1,0 +1,524 @@
+"""
+Sampling methods (pysages/methods/*.py) backed by the fused CUDA bias step.
+
+Same classes, constructor arguments, validation errors and `build(snapshot, helpers) ->
+(snapshot, initialize, update)` contract as the reference (methods/core.py:81-153):
+
+    HarmonicBias        methods/harmonic_bias.py:42-132
+    Metadynamics        methods/metad.py:72-205 (standard / well-tempered, direct sum / grid)
+    ABF                 methods/abf.py:75-227
+    Unbiased            methods/unbiased.py:36-75
+    UmbrellaIntegration methods/umbrella_integration.py:37-125
+    CVRestraints        methods/restraints.py:14-73
+
+`update(snapshot, state)` enqueues ONE fused launch on the current CUDA stream: gather of the
+selected atoms, CVs + closed-form Jacobians, the method's bias and the in-place scatter into the
+engine's force array.  It never synchronises with the host; state fields are zero-copy views of
+device memory owned by the native handle.
+"""
+
+import ctypes
+import math
+from typing import Any, NamedTuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import colvars as _colvars
+from .backends import snapshot as _snap
+from .grids import Grid
+
+
+# --------------------------------------------------------------------------------------------
+# restraints (methods/restraints.py)
+# --------------------------------------------------------------------------------------------
+class CVRestraints(NamedTuple):
+    """Harmonic restraint parameters (restraints.py:14-37)."""
+
+    lower: Any
+    upper: Any
+    kl: Any
+    ku: Any
+
+
+def canonicalize(restraints, cvs):
+    """restraints.py:49-61: infinite bounds wherever the spring constant is zero."""
+    if restraints is None:
+        return None
+    lower, upper, kl, ku = restraints
+    kl = np.asarray(kl, dtype=np.float64).flatten()
+    ku = np.asarray(ku, dtype=np.float64).flatten()
+    lower = np.where(kl == 0, -np.inf, np.asarray(lower, dtype=np.float64).flatten())
+    upper = np.where(ku == 0, np.inf, np.asarray(upper, dtype=np.float64).flatten())
+    ncomp = sum(cv.ncomponents for cv in cvs)
+    if not (len(lower) == len(upper) == len(kl) == len(ku) == ncomp):
+        raise ValueError("The number of restraints must equal the number of CVs.")
+    return CVRestraints(lower, upper, kl, ku)
+
+
+# --------------------------------------------------------------------------------------------
+# device state views
+# --------------------------------------------------------------------------------------------
+class _DeviceBuffer:
+    """Exposes handle-owned device memory through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape),
+            "typestr": typestr,
+            "data": (int(ptr), False),
+            "version": 2,
+        }
+        self._owner = owner
+
+
+_TYPESTR = {0: "<f8", 1: "<i8", 2: "<i4"}  # u32 histograms are viewed as int32 (torch has no uint32 ops)
+
+
+class HarmonicBiasState(NamedTuple):  # harmonic_bias.py:23-39
+    xi: Any
+    bias: Any
+    ncalls: int = 0
+
+
+class UnbiasedState(NamedTuple):  # unbiased.py:17-33
+    xi: Any
+    bias: Any
+    ncalls: int = 0
+
+
+class MetadynamicsState(NamedTuple):  # metad.py:26-69
+    xi: Any
+    bias: Any
+    heights: Any
+    centers: Any
+    sigmas: Any
+    grid_potential: Any
+    grid_gradient: Any
+    idx: Any
+    ncalls: int = 0
+
+
+class ABFState(NamedTuple):  # abf.py:32-72
+    xi: Any
+    bias: Any
+    hist: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    ncalls: int = 0
+
+
+class NativeStep:
+    """Owns one psb_handle: the device-resident method state + index tables of one simulation."""
+
+    def __init__(self, method, snapshot, helpers, dense_outputs=False):
+        if not snapshot.positions.is_cuda:
+            raise RuntimeError(
+                "pysages_b200 runs the bias step on a CUDA device only (no CPU fallback): "
+                "snapshot arrays must be CUDA tensors"
+            )
+        self.lib = N.load()
+        self.method = method
+        self.layout = helpers.layout
+        self.device = snapshot.positions.device
+        keep = []
+        cvs = (N.CvDesc * len(method.cvs))(*[cv.describe(keep) for cv in method.cvs])
+        mdesc = method.describe(helpers)
+        ldesc = _snap.describe_layout(
+            snapshot,
+            self.layout,
+            unwrap=method.requires_box_unwrapping,
+            need_momenta="momenta" in method.snapshot_flags,
+            dense_outputs=dense_outputs,
+        )
+        self.k = sum(cv.ncomponents for cv in method.cvs)
+        self.natoms = int(ldesc.natoms)
+        self.dense_outputs = bool(dense_outputs)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.psb_create(cvs, len(method.cvs), ctypes.byref(mdesc), ctypes.byref(ldesc),
+                                        ctypes.byref(handle)))
+        self.handle = handle
+        self._snapdesc = N.SnapshotDesc()
+        self._views = {}
+        self.ncalls = 0
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self.lib.psb_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+
+    # ---- stepping ------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _desc(self, snapshot):
+        return _snap.describe_snapshot(snapshot, self.layout, self._snapdesc)
+
+    def evaluate(self, snapshot):
+        N.check(self.lib.psb_evaluate_cvs(self.handle, ctypes.byref(self._desc(snapshot)), self._stream()))
+
+    def step(self, snapshot, timestep=0):
+        N.check(self.lib.psb_step(self.handle, ctypes.byref(self._desc(snapshot)), int(timestep), self._stream()))
+        self.ncalls += 1
+
+    def next_step_deposits(self):
+        return bool(self.lib.psb_next_step_deposits(self.handle))
+
+    def walker_begin(self, snapshot, record, timestep=0):
+        N.check(self.lib.psb_walker_begin(self.handle, ctypes.byref(self._desc(snapshot)), int(timestep),
+                                          ctypes.c_void_p(record.data_ptr()), self._stream()))
+
+    def walker_finish(self, snapshot, records, nwalkers):
+        N.check(self.lib.psb_walker_finish(self.handle, ctypes.byref(self._desc(snapshot)),
+                                           ctypes.c_void_p(records.data_ptr()), int(nwalkers), self._stream()))
+        self.ncalls += 1
+
+    @property
+    def record_doubles(self):
+        return int(self.lib.psb_walker_record_doubles(self.handle))
+
+    def launch_info(self):
+        g, b, c, nbytes = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        N.check(self.lib.psb_launch_info(self.handle, ctypes.byref(g), ctypes.byref(b), ctypes.byref(c),
+                                         ctypes.byref(nbytes)))
+        return dict(grid_blocks=g.value, block_threads=b.value, cooperative=bool(c.value),
+                    algorithmic_bytes_per_step=nbytes.value, launches=int(self.lib.psb_launch_count(self.handle)))
+
+    # ---- state ---------------------------------------------------------------------------
+    def view(self, field, shape=None):
+        """Zero-copy torch view of a state field (None when the method has no such field)."""
+        if field in self._views:
+            return self._views[field]
+        nbytes, code, ptr = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_void_p()
+        st = self.lib.psb_state_info(self.handle, field.encode(), ctypes.byref(nbytes), ctypes.byref(code),
+                                     ctypes.byref(ptr))
+        if st == N.ERR_KEY:
+            self._views[field] = None
+            return None
+        N.check(st)
+        itemsize = 4 if code.value == 2 else 8
+        n = nbytes.value // itemsize
+        buf = _DeviceBuffer(ptr.value, (n,), _TYPESTR[code.value], self)
+        t = torch.as_tensor(buf, device=self.device)
+        if shape is not None:
+            t = t.reshape(shape)
+        self._views[field] = t
+        return t
+
+    def set_state(self, field, value):
+        t = self.view(field)
+        if t is None:
+            raise KeyError(field)
+        src = torch.as_tensor(np.asarray(value), device=self.device).to(t.dtype).reshape(t.shape)
+        t.copy_(src)
+        if field == "ncalls":
+            n = np.asarray(int(np.asarray(value).reshape(-1)[0]), dtype=np.int64)
+            N.check(self.lib.psb_set_state(self.handle, b"ncalls", n.ctypes.data_as(ctypes.c_void_p), 8, self._stream()))
+            self.ncalls = int(n)
+
+
+# --------------------------------------------------------------------------------------------
+# base classes (methods/core.py:81-153)
+# --------------------------------------------------------------------------------------------
+class SamplingMethod:
+    """methods/core.py:81-116"""
+
+    snapshot_flags = set()
+    _kind = N.METHOD_UNBIASED
+
+    def __init__(self, cvs, **kwargs):
+        cvs = list(cvs)
+        if not cvs:
+            raise ValueError("at least one collective variable is required")
+        for cv in cvs:
+            if not isinstance(cv, _colvars.CollectiveVariable):
+                raise TypeError(f"{cv!r} is not a CollectiveVariable")
+        self.cvs = cvs
+        self.requires_box_unwrapping = any(cv.requires_box_unwrapping for cv in cvs)
+        self.kwargs = kwargs
+        self.dense_bias = bool(kwargs.get("dense_bias", False))
+
+    @property
+    def ncomponents(self):
+        return sum(cv.ncomponents for cv in self.cvs)
+
+    # -- lowering to psb_method_desc --------------------------------------------------------
+    def _base_desc(self, helpers):
+        d = N.MethodDesc()
+        d.kind = self._kind
+        for i in range(N.MAX_K):
+            d.periods[i] = math.inf
+            d.sigma[i] = 1.0
+            d.r_lower[i], d.r_upper[i] = -math.inf, math.inf
+        d.force_unit_factor = float(helpers.layout.force_unit_factor)
+        d.grid.kind = N.GRID_NONE
+        return d
+
+    def describe(self, helpers):
+        return self._base_desc(helpers)
+
+    def _set_grid(self, d):
+        grid = getattr(self, "grid", None)
+        if grid is not None:
+            d.grid = grid.describe()
+        restraints = getattr(self, "restraints", None)
+        if restraints is not None:
+            d.has_restraints = 1
+            for i in range(len(restraints.lower)):
+                d.r_lower[i] = float(restraints.lower[i])
+                d.r_upper[i] = float(restraints.upper[i])
+                d.r_kl[i] = float(restraints.kl[i])
+                d.r_ku[i] = float(restraints.ku[i])
+
+    # -- build contract ---------------------------------------------------------------------
+    _state_type = UnbiasedState
+
+    def _make_state(self, native):
+        k = native.k
+        bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+        return self._state_type(native.view("xi", (1, k)), bias, native.ncalls)
+
+    def build(self, snapshot, helpers, *args, **kwargs):
+        """methods/core.py:108-116 -> (snapshot, initialize, update)"""
+        native = NativeStep(self, snapshot, helpers, dense_outputs=self.dense_bias)
+        self.native = native  # most recent handle, for introspection (launch_info, tests)
+
+        def initialize():
+            native.evaluate(snapshot)  # xi of the initial snapshot, e.g. harmonic_bias.py:119-122
+            return self._make_state(native)
+
+        def update(snapshot, state, timestep=0):
+            native.step(snapshot, timestep)
+            return self._make_state(native)
+
+        update.native = native
+        return snapshot, initialize, update
+
+
+class GriddedSamplingMethod(SamplingMethod):
+    """methods/core.py:119-140"""
+
+    def __init__(self, cvs, grid, **kwargs):
+        check_dims(cvs, grid)
+        super().__init__(cvs, **kwargs)
+        self.grid = grid
+        self.restraints = canonicalize(kwargs.get("restraints", None), self.cvs)
+
+
+def check_dims(cvs, grid):
+    # methods/core.py:435-443
+    if grid is not None and len(list(cvs)) != grid.shape.size:
+        raise ValueError("Grid and Collective Variable dimensions must match.")
+
+
+# --------------------------------------------------------------------------------------------
+# concrete methods
+# --------------------------------------------------------------------------------------------
+class Unbiased(SamplingMethod):
+    """methods/unbiased.py:36-75: evaluates the CVs every step, applies no bias."""
+
+    snapshot_flags = {"positions", "indices"}
+    _kind = N.METHOD_UNBIASED
+
+
+class Bias(SamplingMethod):
+    """methods/bias.py:17-73"""
+
+    snapshot_flags = {"positions", "indices"}
+
+    def __init__(self, cvs, center, **kwargs):
+        super().__init__(cvs, **kwargs)
+        self.cv_dimension = len(self.cvs)
+        self.center = center
+
+    @property
+    def center(self):
+        return self._center
+
+    @center.setter
+    def center(self, center):
+        center = np.asarray(center, dtype=np.float64)
+        if center.shape == ():
+            center = center.reshape(1)
+        if len(center.shape) != 1 or center.shape[0] != self.cv_dimension:
+            raise RuntimeError(f"Invalid center shape expected {self.cv_dimension} got {center.shape}.")
+        self._center = center
+
+
+class HarmonicBias(Bias):
+    """methods/harmonic_bias.py:42-132: F = K (xi - center), bias = -J^T F."""
+
+    _kind = N.METHOD_HARMONIC
+    _state_type = HarmonicBiasState
+
+    def __init__(self, cvs, kspring, center, **kwargs):
+        super().__init__(cvs, center, **kwargs)
+        self.kspring = kspring
+
+    @property
+    def kspring(self):
+        return self._kspring
+
+    @kspring.setter
+    def kspring(self, kspring):
+        # harmonic_bias.py:78-107
+        kspring = np.asarray(kspring, dtype=np.float64)
+        shape = kspring.shape
+        n = self.cv_dimension
+        if len(shape) > 2:
+            raise RuntimeError(f"Wrong kspring shape {shape} (expected scalar, 1D or 2D)")
+        if len(shape) == 2:
+            if shape != (n, n):
+                raise RuntimeError(f"2D kspring with wrong shape, expected ({n}, {n}), got {shape}")
+            if not np.allclose(kspring, kspring.T):
+                raise RuntimeError("Spring matrix is not symmetric")
+            self._kspring = kspring
+        else:
+            if kspring.size not in (n, 1):
+                raise RuntimeError(f"Wrong kspring size, expected 1 or {n}, got {kspring.size}.")
+            self._kspring = np.identity(n) * kspring
+
+    def describe(self, helpers):
+        d = self._base_desc(helpers)
+        n = self.cv_dimension
+        if self.ncomponents != n:
+            raise ValueError("HarmonicBias needs scalar collective variables")
+        for a in range(n):
+            d.center[a] = float(self._center[a])
+            for b in range(n):
+                d.kspring[a * N.MAX_K + b] = float(self._kspring[a, b])
+        return d
+
+
+class Metadynamics(SamplingMethod):
+    """methods/metad.py:72-205."""
+
+    snapshot_flags = {"positions", "indices"}
+    _kind = N.METHOD_METAD
+    _state_type = MetadynamicsState
+
+    def __init__(self, cvs, height, sigma, stride, ngaussians, deltaT=None, **kwargs):
+        if deltaT is not None and "kB" not in kwargs:  # metad.py:133-138
+            raise KeyError(
+                "For well-tempered Metadynamics a keyword argument `kB` for "
+                "the value of the Boltzmann constant (that matches the "
+                "internal units of the backend) must be provided."
+            )
+        kwargs["grid"] = kwargs.get("grid", None)
+        kwargs["restraints"] = kwargs.get("restraints", None)
+        check_dims(cvs, kwargs["grid"])
+        super().__init__(cvs, **kwargs)
+        self.grid = kwargs["grid"]
+        self.restraints = canonicalize(kwargs["restraints"], self.cvs)
+        self.height = height
+        self.sigma = sigma
+        self.stride = stride
+        self.ngaussians = ngaussians
+        self.deltaT = deltaT
+        self.kB = kwargs.get("kB", None)
+        self.shared_hills = bool(kwargs.get("shared_hills", False))
+
+    def describe(self, helpers):
+        d = self._base_desc(helpers)
+        k = self.ncomponents
+        sigma = np.asarray(self.sigma, dtype=np.float64).flatten()
+        if sigma.size == 1:
+            sigma = np.repeat(sigma, k)
+        if sigma.size != k:
+            raise ValueError("sigma must have one entry per collective variable")
+        d.height = float(self.height)
+        periods = _colvars.get_periods(self.cvs)
+        for i in range(k):
+            d.sigma[i] = float(sigma[i])
+            d.periods[i] = periods[i]
+        d.stride = int(self.stride)
+        d.ngaussians = int(self.ngaussians)
+        d.well_tempered = int(self.deltaT is not None)
+        d.shared_hills = int(self.shared_hills)
+        d.deltaT = float(self.deltaT) if self.deltaT is not None else 0.0
+        d.kB = float(self.kB) if self.kB is not None else 0.0
+        self._set_grid(d)
+        return d
+
+    def _make_state(self, native):
+        k = native.k
+        bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+        gshape = tuple(int(s) for s in self.grid.shape) if self.grid is not None else None
+        gp = native.view("grid_potential", gshape) if gshape else None
+        gg = native.view("grid_gradient", (*gshape, k)) if gshape else None
+        return MetadynamicsState(
+            native.view("xi", (1, k)), bias, native.view("heights"), native.view("centers", (-1, k)),
+            native.view("sigmas", (1, -1))[:, :k], gp, gg, native.view("idx", ()), native.ncalls,
+        )
+
+
+class ABF(GriddedSamplingMethod):
+    """methods/abf.py:75-227."""
+
+    snapshot_flags = {"positions", "indices", "momenta"}
+    _kind = N.METHOD_ABF
+    _state_type = ABFState
+
+    def __init__(self, cvs, grid, **kwargs):
+        super().__init__(cvs, grid, **kwargs)
+        self.N = np.asarray(self.kwargs.get("N", 500))
+        self.use_pinv = self.kwargs.get("use_pinv", False)
+
+    def describe(self, helpers):
+        d = self._base_desc(helpers)
+        d.abf_N = int(self.N)
+        d.use_pinv = int(bool(self.use_pinv))
+        self._set_grid(d)
+        return d
+
+    def _make_state(self, native):
+        k = native.k
+        gshape = tuple(int(s) for s in self.grid.shape)
+        bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+        return ABFState(
+            native.view("xi", (1, k)), bias, native.view("hist", gshape), native.view("Fsum", (*gshape, k)),
+            native.view("force")[:k], native.view("Wp")[:k], native.view("Wp_")[:k], native.ncalls,
+        )
+
+
+class UmbrellaIntegration(SamplingMethod):
+    """methods/umbrella_integration.py:37-125: one HarmonicBias window per centre + histograms."""
+
+    def __init__(self, cvs_or_biasers, *args, **kwargs):
+        from .utils import HistogramLogger, listify
+
+        first = list(cvs_or_biasers)
+        if first and isinstance(first[0], Bias):  # umbrella_integration.py:88-114
+            biasers = first
+            hist_periods = args[0] if args else kwargs.pop("hist_periods")
+            hist_offsets = args[1] if len(args) > 1 else kwargs.pop("hist_offsets", 0)
+            cvs = biasers[0].cvs
+            for b in biasers[1:]:
+                if b.cvs != cvs:
+                    raise RuntimeError("Attempted run of UmbrellaSampling with different CVs for the individual biaser.")
+            super().__init__(cvs, **kwargs)
+            self.submethods = biasers
+        else:  # umbrella_integration.py:51-86
+            names = ("ksprings", "centers", "hist_periods", "hist_offsets")
+            vals = dict(zip(names, args))
+            vals.update({n: kwargs.pop(n) for n in names if n in kwargs})
+            ksprings, centers = vals["ksprings"], vals["centers"]
+            hist_periods, hist_offsets = vals["hist_periods"], vals.get("hist_offsets", 0)
+            super().__init__(first, **kwargs)
+            replicas = len(centers)
+            ksprings = listify(ksprings, replicas, "ksprings", float)
+            self.submethods = [HarmonicBias(self.cvs, k, c) for (k, c) in zip(ksprings, centers)]
+        replicas = len(self.submethods)
+        periods = listify(hist_periods, replicas, "hist_periods", int)
+        offsets = listify(hist_offsets, replicas, "hist_offsets", int)
+        self.histograms = [HistogramLogger(p, o) for (p, o) in zip(periods, offsets)]
+
+    def build(self):  # pylint: disable=arguments-differ
+        """The sampling work is delegated to the HarmonicBias windows (umbrella_integration.py:123-125)."""

