@@ -229,7 +229,7 @@ def test_metadynamics_regular_grid_out_of_bounds(restraints):
 
 def test_metadynamics_many_hills_multi_cta():
     """Direct sum over enough hills to need several CTAs and several TMA stages per CTA."""
-    snap = snapshot("hoomd", np.float64, n=300)
+    snap = snapshot("hoomd", np.float64, n=600)
     H = 40000
     kw = dict(height=0.8, sigma=[0.5, 0.7], stride=5, ngaussians=H, deltaT=1000.0, kB=0.0083144626)
     run = ParityRun(snap, POINT_CVS["two-distances"], ("Metadynamics", kw))
