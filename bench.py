@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""
+bench.py -- bias-steps/s of the PySAGES per-timestep bias hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-series]
+
+One "step" = one pass of the hot path over one synthetic snapshot: snapshot read -> CVs +
+Jacobians -> method bias -> in-place force scatter, state left on the device.
+
+Headline workload (BASELINE.json configs[1]): ABF on two Distance CVs between
+four disjoint groups of 25 000 atoms (S = N = 100 000 selected atoms), HOOMD-blue fp32 DLPack
+layout, 2-D 64x64 grid with restraint walls, N = 500, dt = 0.005.  Inputs cycle over 64 distinct
+device-resident snapshots (410 MB > 126 MB L2) so no step finds its inputs in L2.
+
+`value`  : steps/s with the snapshots resident in HBM, CUDA events on the launching stream.
+`e2e`    : the same step through the C-ABI host-buffer entry point (psb_step_host): pinned host
+           snapshot -> H2D -> step -> D2H forces, every step inside the timed region.
+`roofline`, `cpu_baseline`, `clocks`, `gpu_launches`, `series`: see DESIGN.md "Measurement".
+With --gpus N > 1 (torchrun) every rank runs the workload on its own GPU as an independent
+replica (umbrella-window style, no data-path collective): weak scaling, value = aggregate steps/s.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NFRAMES = 64
+METRIC = "bias-steps/sec (CV+Jacobian+bias+force apply)"
+UNIT = "steps/s"
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic device snapshots (generated with torch on the device for speed)
+# ------------------------------------------------------------------------------------------------------
+def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, globule=False):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    L = float((natoms / 0.8) ** (1.0 / 3.0))
+    if globule:
+        x0 = torch.randn((natoms, 3), generator=g, device=device, dtype=torch.float64) * 0.3 * natoms ** (1 / 3)
+    else:
+        x0 = (torch.rand((natoms, 3), generator=g, device=device, dtype=torch.float64) - 0.5) * L
+    frames = []
+    cur = x0
+    for _ in range(nframes):
+        cur = cur + 0.02 * torch.randn((natoms, 3), generator=g, device=device, dtype=torch.float64)
+        pos = torch.zeros((natoms, 4), device=device, dtype=dtype)
+        pos[:, :3] = cur.to(dtype)
+        vm = torch.empty((natoms, 4), device=device, dtype=dtype)
+        vm[:, :3] = torch.randn((natoms, 3), generator=g, device=device, dtype=dtype)
+        vm[:, 3] = 1.0 + 15.0 * torch.rand((natoms,), generator=g, device=device, dtype=dtype)
+        f = torch.zeros((natoms, 4), device=device, dtype=dtype)
+        f[:, :3] = torch.randn((natoms, 3), generator=g, device=device, dtype=dtype)
+        rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32)
+        img = torch.randint(-1, 2, (natoms, 3), generator=g, device=device, dtype=torch.int32)
+        frames.append(dict(positions=pos, vel_mass=vm, forces=f, rtags=rtag, images=img))
+    return frames, L, x0
+
+
+def snapshots_of(frames, L, dt):
+    from pysages_b200.backends.snapshot import Box, Snapshot
+
+    box = Box(np.diag([L, L, L]), np.full(3, -L / 2))
+    return [Snapshot(f["positions"], f["vel_mass"], f["forces"], f["rtags"], box, dt, dict(images=f["images"]))
+            for f in frames]
+
+
+def host_arrays(frame, L, dt):
+    a = {k: v.cpu().numpy() for k, v in frame.items()}
+    return dict(arrays=a, box_H=np.diag([L, L, L]), origin=np.full(3, -L / 2), dt=dt, L=L, layout="hoomd",
+                natoms=a["positions"].shape[0])
+
+
+# ------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------
+def groups4(natoms):
+    q = natoms // 4
+    return [list(range(i * q, (i + 1) * q)) for i in range(4)]
+
+
+def workload_specs(name, natoms, L):
+    """-> (cv_specs, method_spec) in the format of tests/parity_utils.py"""
+    if name == "abf2d":
+        g = groups4(natoms)
+        cvs = [("Distance", ([g[0], g[1]],), {}), ("Distance", ([g[2], g[3]],), {})]
+        m = ("ABF", dict(grid=((0.0, 0.0), (L / 2, L / 2), (64, 64), "regular"), N=500,
+                         restraints=((0.0, 0.0), (L / 2, L / 2), (10.0, 10.0), (10.0, 10.0))))
+        return cvs, m
+    if name == "harmonic":
+        h = natoms // 2
+        cvs = [("Distance", ([list(range(0, h)), list(range(h, natoms))],), {})]
+        return cvs, ("HarmonicBias", dict(kspring=10.0, center=[1.0]))
+    raise ValueError(name)
+
+
+def build_ours(cv_specs, method_spec, snapshot):
+    """Public-API construction of the method (no oracle import on this path)."""
+    import pysages_b200 as ps
+    from pysages_b200.backends import mock
+    from pysages_b200.backends.snapshot import HelperMethods
+
+    cvs = [getattr(ps.colvars, n)(*a, **k) for (n, a, k) in cv_specs]
+    name, kw = method_spec
+    kw = dict(kw)
+    if kw.get("grid") is not None:
+        lower, upper, shape, kind = kw["grid"]
+        T = {"regular": ps.Regular, "periodic": ps.Periodic, "chebyshev": ps.Chebyshev}[kind]
+        kw["grid"] = ps.Grid[T](lower, upper, shape)
+    if kw.get("restraints") is not None:
+        kw["restraints"] = ps.CVRestraints(*kw["restraints"])
+    if name == "HarmonicBias":
+        method = ps.methods.HarmonicBias(cvs, kw.pop("kspring"), kw.pop("center"), **kw)
+    elif name == "ABF":
+        method = ps.methods.ABF(cvs, kw.pop("grid"), **kw)
+    else:
+        args = [kw.pop(k) for k in ("height", "sigma", "stride", "ngaussians")]
+        method = ps.methods.Metadynamics(cvs, *args, kw.pop("deltaT", None), **kw)
+    helpers = HelperMethods(None, lambda: 3, lambda x: x, mock.LAYOUTS["hoomd"])
+    _, init, update = method.build(snapshot, helpers)
+    init()
+    return method, update.native
+
+
+def snapdesc_array(native, snapshots):
+    from pysages_b200 import _native as N
+    from pysages_b200.backends import snapshot as S
+
+    arr = (N.SnapshotDesc * len(snapshots))()
+    for i, s in enumerate(snapshots):
+        S.describe_snapshot(s, native.layout, arr[i])
+    return arr
+
+
+def time_cycle(native, descs, steps, warmup, stream):
+    """CUDA-event timing of `steps` bias steps issued by the native engine-loop emulation."""
+    lib = native.lib
+    from pysages_b200 import _native as N
+
+    h = native.handle
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    N.check(lib.psb_run_cycle(h, descs, len(descs), warmup, sp))
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.psb_launch_count(h)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        N.check(lib.psb_run_cycle(h, descs, len(descs), steps, sp))
+        e1.record(stream)
+    stream.synchronize()
+    return e0.elapsed_time(e1), lib.psb_launch_count(h) - l0
+
+
+def time_e2e(native, frame, L, dt, steps, warmup, stream):
+    """psb_step_host: pinned host snapshot -> H2D -> step -> D2H forces, per step."""
+    from pysages_b200 import _native as N
+
+    host = {k: v.cpu().pin_memory() for k, v in frame.items()}
+    d = N.SnapshotDesc()
+    d.positions, d.vel_mass, d.forces = host["positions"].data_ptr(), host["vel_mass"].data_ptr(), host["forces"].data_ptr()
+    d.ids, d.images = host["rtags"].data_ptr(), host["images"].data_ptr()
+    for i in range(3):
+        d.box_diag[i] = L
+    d.dt = dt
+    h2d, d2h = ctypes.c_int64(), ctypes.c_int64()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    for _ in range(warmup):
+        N.check(native.lib.psb_step_host(native.handle, ctypes.byref(d), 0, sp, ctypes.byref(h2d), ctypes.byref(d2h)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        N.check(native.lib.psb_step_host(native.handle, ctypes.byref(d), i, sp, ctypes.byref(h2d), ctypes.byref(d2h)))
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1)
+    return steps / (ms * 1e-3), int(h2d.value), int(d2h.value)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(key):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(key)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s, max_steps=None, warmup=1):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity_utils import make_cvs, make_method, oracle_snapshot
+
+    import oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cvs = make_cvs(oracle.colvars, cv_specs)
+    method = make_method("oracle", method_spec, cvs)
+    osnap = oracle_snapshot(snap_host)
+    helpers, bias = oracle.backends.build_helpers("hoomd", method.snapshot_flags, True)
+    _, init, update = method.build(osnap, helpers)
+    state = init()
+    for _ in range(warmup):
+        state = update(osnap, state)
+        bias(osnap, state.bias.numpy())
+    n, t0 = 0, time.perf_counter()
+    while True:
+        state = update(osnap, state)
+        bias(osnap, state.bias.numpy())
+        n += 1
+        el = time.perf_counter() - t0
+        if (max_steps is not None and n >= max_steps) or (max_steps is None and el >= budget_s) or el >= 4 * budget_s:
+            break
+    return n / el, n, cores
+
+
+def run_series(device, stream, hbm):
+    """Secondary sizes / configurations (parity-tested elsewhere); short runs, same timing method."""
+    out = []
+    for name, natoms, steps in (("harmonic", 10_000, 2000), ("harmonic", 100_000, 2000), ("harmonic", 1_000_000, 500),
+                                ("abf2d", 10_000, 2000), ("abf2d", 1_000_000, 500)):
+        nfr = 64 if natoms <= 100_000 else 8
+        frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977)
+        snaps = snapshots_of(frames, L, 0.005)
+        cvs, m = workload_specs(name, natoms, L)
+        method, native = build_ours(cvs, m, snaps[0])
+        ms, _ = time_cycle(native, snapdesc_array(native, snaps), steps, 20, stream)
+        info = native.launch_info()
+        us = ms * 1e3 / steps
+        gbs = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
+        out.append(dict(workload=f"{name} S=N={natoms} hoomd-f32", steps_per_s=round(steps / (ms * 1e-3), 1),
+                        us_per_step=round(us, 3), algorithmic_bytes=info["algorithmic_bytes_per_step"],
+                        achieved_gbs=round(gbs, 1), frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"],
+                        distinct_snapshots=nfr))
+        del frames, snaps, native, method
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--natoms", type=int, default=100_000)
+    ap.add_argument("--no-series", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    natoms, dt = args.natoms, 0.005
+    L = float((natoms / 0.8) ** (1.0 / 3.0))
+    cv_specs, method_spec = workload_specs("abf2d", natoms, L)
+    config = dict(workload=f"cfg2: ABF, 2x Distance CVs over 4 disjoint groups of {natoms // 4} atoms (S=N={natoms}), "
+                           "HOOMD fp32 DLPack layout, 64x64 grid + restraints, N=500",
+                  natoms=natoms, selected_atoms=natoms, replicas=world, parallelism=f"replicas x{world}",
+                  l2="inputs cycle over 64 distinct snapshots (410 MB) > 126 MB L2")
+
+    # ---------------- reference arm: the reference's algorithm (oracle port) on the host cores -----------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rng_frames, _, _ = (None, None, None)
+        from pysages_b200 import synthetic
+
+        snap_host = synthetic.make_snapshot(natoms, layout="hoomd", dtype=np.float32, seed=20240 + 2000)
+        # warm-up measures the step cost; the timed region is capped to ~120 s of CPU work
+        rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=5.0, warmup=max(1, min(args.warmup, 3)))
+        k_eff = int(max(1, min(args.steps, rate * 120.0)))
+        rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=1e9, max_steps=k_eff, warmup=0)
+        sample = (f"{n} full bias steps of the same workload on one host snapshot (dense (k,3N) autodiff Jacobian, "
+                  f"torch-fp64 CPU, {cores} threads); reference needs JAX, not installable here -> oracle port")
+        line = dict(impl="reference", metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=n,
+                    warmup=args.warmup, ms_per_step=1e3 / rate, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                    cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample),
+                    e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ------------------------------------------------------------------------
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    device = torch.device("cuda", local_rank % torch.cuda.device_count())
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    stream = torch.cuda.Stream(device=device)
+
+    frames, L, _ = device_hoomd_frames(natoms, NFRAMES, device, seed=20240 + 2000 + rank)
+    snaps = snapshots_of(frames, L, dt)
+    method, native = build_ours(cv_specs, method_spec, snaps[0])
+    descs = snapdesc_array(native, snaps)
+    info = native.launch_info()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    time_cycle(native, descs, max(args.warmup, 3), 3, stream)  # module load, clocks up
+    barrier()
+    with ClockSampler(device.index or 0) as clocks:
+        barrier()
+        ms, launches = time_cycle(native, descs, args.steps, max(args.warmup, 3), stream)
+        barrier()
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * args.steps / (ms * 1e-3)
+
+    # e2e through the host-buffer C-ABI entry point
+    e2e_steps = max(20, min(args.steps, 300))
+    e2e_rate, h2d, d2h = time_e2e(native, frames[0], L, dt, e2e_steps, 3, stream)
+    t = torch.tensor([e2e_rate], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    e2e_value = world * float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    hbm, peak_src = peaks()
+    us = ms * 1e3 / args.steps
+    achieved = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
+    roofline = dict(bound="hbm", achieved=round(achieved, 2), peak=hbm, unit="GB/s", frac=round(achieved / hbm, 4),
+                    traffic=traffic_from_profiles("abf2d_100k"), kernel="psb::step_kernel<HOOMD,float> (1 launch/step)",
+                    algorithmic_bytes_per_launch=info["algorithmic_bytes_per_step"], peak_source=peak_src,
+                    note="latency-bound at S=1e5 (8.4 MB/step = 1.3 us of traffic); see series for S=1e6")
+
+    cpu = None
+    if world == 1 or rank == 0:
+        snap_host = host_arrays(frames[0], L, dt)
+        rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=12.0)
+        cpu = dict(value=round(rate, 3), unit=UNIT, cores=cores, kind="port",
+                   sample=f"{n} bias steps of the same workload on one snapshot (oracle: torch-fp64 autodiff, dense J)")
+
+    series = [] if (args.no_series or world > 1) else run_series(device, stream, hbm)
+
+    line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=config, clocks=clocks.summary(),
+                e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         steps=e2e_steps, path="psb_step_host (pinned host snapshot -> H2D -> step -> D2H forces)"),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, launch=info, series=series)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
