@@ -309,6 +309,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--natoms", type=int, default=100_000)
     ap.add_argument("--no-series", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -380,7 +382,10 @@ def main():
 
     # e2e through the host-buffer C-ABI entry point
     e2e_steps = max(20, min(args.steps, 300))
-    e2e_rate, h2d, d2h = time_e2e(native, frames[0], L, dt, e2e_steps, 3, stream)
+    if args.no_e2e:
+        e2e_rate, h2d, d2h = 0.0, 0, 0
+    else:
+        e2e_rate, h2d, d2h = time_e2e(native, frames[0], L, dt, e2e_steps, 3, stream)
     t = torch.tensor([e2e_rate], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -401,7 +406,7 @@ def main():
                     note="latency-bound at S=1e5 (8.4 MB/step = 1.3 us of traffic); see series for S=1e6")
 
     cpu = None
-    if world == 1 or rank == 0:
+    if not args.no_cpu:
         snap_host = host_arrays(frames[0], L, dt)
         rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=12.0)
         cpu = dict(value=round(rate, 3), unit=UNIT, cores=cores, kind="port",

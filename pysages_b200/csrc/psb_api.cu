@@ -506,6 +506,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   {
     psb_status st = dev_alloc(h, &M.partials, (size_t)(MAXG + 1) * NACC * h->grid);
     if (st != PSB_OK) return bail(st);
+    if (getenv("PSB_DEBUG_TIMING") && (st = dev_alloc(h, &M.dbg, (size_t)16 * h->grid)) != PSB_OK) return bail(st);
   }
 
   // ---- algorithmic bytes per step ----------------------------------------------------
@@ -616,6 +617,7 @@ psb_status psb_state_info(psb_handle* h, const char* field, int64_t* nbytes, int
   else if (f == "Wp_") { p = s.Wp_; n = 8 * k; }
   else if (f == "bias") { p = M.bias_dense; n = 8 * 3 * M.natoms; }
   else if (f == "jacobian") { p = M.jac_dense; n = 8 * 3 * M.natoms * k; }
+  else if (f == "debug_timing") { p = M.dbg; n = 8 * 16 * (long long)h->grid; code = 1; }
   else return fail(PSB_ERR_KEY, "unknown state field '%s'", field);
   if (!p) return fail(PSB_ERR_KEY, "state field '%s' does not exist for this method", field);
   if (nbytes) *nbytes = n;

@@ -127,6 +127,10 @@ struct Model {
   long long natoms;
   int32_t hill_chunk;         // hills per TMA stage
   int32_t pad;
+  long long* dbg;             // optional (PSB_DEBUG_TIMING=1): per-CTA phase timestamps [grid][16]
+  const int4* plan;           // partial-reduction plan: {dst = g * NACC + a, first CTA, last CTA, 0}
+  int32_t plan_off[2];        // first entry of pass A / pass B
+  int32_t plan_n[2];          // entries of pass A / pass B
 };
 
 struct Snap {
@@ -174,6 +178,19 @@ __device__ __forceinline__ double4 ldg4(const double4* p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// plain (coherent) 16/32-byte accesses for the force array
+__device__ __forceinline__ float4 ld4(const float4* p) { return *p; }
+__device__ __forceinline__ double4 ld4(const double4* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void st4(double4* p, double4 v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+  *(reinterpret_cast<double2*>(p) + 1) = make_double2(v.z, v.w);
+}
+
 // hoomd.py:148-202
 template <typename Real>
 struct Access<PSB_LAYOUT_HOOMD, Real> {
@@ -197,14 +214,17 @@ struct Access<PSB_LAYOUT_HOOMD, Real> {
     const R4 v = ldg4(reinterpret_cast<const R4*>(s.vel_mass) + slot);
     return v3((double)(Real)(v.w * v.x), (double)(Real)(v.w * v.y), (double)(Real)(v.w * v.z));
   }
-  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
-    // hoomd.py:229: forces[:, :3] += biases  (fp64 sum, rounded once to the force dtype)
-    R4* f = reinterpret_cast<R4*>(s.forces) + slot;
-    R4 v = *f;
+  // hoomd.py:229: forces[:, :3] += biases  (fp64 sum, rounded once to the force dtype); split
+  // into load / store so callers can batch several independent read-modify-writes
+  using FV = R4;
+  static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {
+    return ld4(reinterpret_cast<const R4*>(s.forces) + slot);
+  }
+  static __device__ __forceinline__ void store_force(const Snap& s, uint32_t slot, FV v, V3 b) {
     v.x = (Real)((double)v.x + b.x);
     v.y = (Real)((double)v.y + b.y);
     v.z = (Real)((double)v.z + b.z);
-    *f = v;
+    st4(reinterpret_cast<R4*>(s.forces) + slot, v);
   }
 };
 
@@ -225,12 +245,17 @@ struct Access<PSB_LAYOUT_OPENMM_CUDA, Real> {
     if (v.w == (Real)0) return v3((double)v.x, (double)v.y, (double)v.z);
     return v3((double)(Real)(v.x / v.w), (double)(Real)(v.y / v.w), (double)(Real)(v.z / v.w));
   }
-  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
-    // openmm.py:141-143,167-169: int64(2**32 * bias.T) added to forces (3, Np)
+  // openmm.py:141-143,167-169: int64(2**32 * bias.T) added to forces (3, Np)
+  struct FV { long long x, y, z; };
+  static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {
+    const long long* f = reinterpret_cast<const long long*>(s.forces);
+    return FV{f[0 * s.natoms + slot], f[1 * s.natoms + slot], f[2 * s.natoms + slot]};
+  }
+  static __device__ __forceinline__ void store_force(const Snap& s, uint32_t slot, FV v, V3 b) {
     long long* f = reinterpret_cast<long long*>(s.forces);
-    f[0 * s.natoms + slot] += (long long)(4294967296.0 * b.x);
-    f[1 * s.natoms + slot] += (long long)(4294967296.0 * b.y);
-    f[2 * s.natoms + slot] += (long long)(4294967296.0 * b.z);
+    f[0 * s.natoms + slot] = v.x + (long long)(4294967296.0 * b.x);
+    f[1 * s.natoms + slot] = v.y + (long long)(4294967296.0 * b.y);
+    f[2 * s.natoms + slot] = v.z + (long long)(4294967296.0 * b.z);
   }
 };
 
@@ -241,11 +266,16 @@ struct Plain3 {
     const Real* p = reinterpret_cast<const Real*>(base) + 3 * (size_t)slot;
     return v3((double)__ldg(p), (double)__ldg(p + 1), (double)__ldg(p + 2));
   }
-  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
+  struct FV { Real x, y, z; };
+  static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {
+    const Real* f = reinterpret_cast<const Real*>(s.forces) + 3 * (size_t)slot;
+    return FV{f[0], f[1], f[2]};
+  }
+  static __device__ __forceinline__ void store_force(const Snap& s, uint32_t slot, FV v, V3 b) {
     Real* f = reinterpret_cast<Real*>(s.forces) + 3 * (size_t)slot;
-    f[0] = (Real)((double)f[0] + b.x);
-    f[1] = (Real)((double)f[1] + b.y);
-    f[2] = (Real)((double)f[2] + b.z);
+    f[0] = (Real)((double)v.x + b.x);
+    f[1] = (Real)((double)v.y + b.y);
+    f[2] = (Real)((double)v.z + b.z);
   }
 };
 
@@ -272,8 +302,12 @@ struct Access<PSB_LAYOUT_LAMMPS, Real> {
     const V3 v = Plain3<Real>::load3(s.vel_mass, slot);
     return v3(mass * v.x, mass * v.y, mass * v.z);
   }
-  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
-    Plain3<Real>::add_force(s, slot, b);
+  using FV = typename Plain3<Real>::FV;
+  static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {
+    return Plain3<Real>::load_force(s, slot);
+  }
+  static __device__ __forceinline__ void store_force(const Snap& s, uint32_t slot, FV v, V3 b) {
+    Plain3<Real>::store_force(s, slot, v, b);
   }
 };
 
@@ -300,8 +334,12 @@ struct Access<PSB_LAYOUT_PLAIN3, Real> {
     return v3((double)(Real)((Real)v.x / im), (double)(Real)((Real)v.y / im),
               (double)(Real)((Real)v.z / im));
   }
-  static __device__ __forceinline__ void add_force(const Snap& s, uint32_t slot, V3 b) {
-    Plain3<Real>::add_force(s, slot, b);
+  using FV = typename Plain3<Real>::FV;
+  static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {
+    return Plain3<Real>::load_force(s, slot);
+  }
+  static __device__ __forceinline__ void store_force(const Snap& s, uint32_t slot, FV v, V3 b) {
+    Plain3<Real>::store_force(s, slot, v, b);
   }
 };
 

@@ -8,8 +8,11 @@
 
 #ifdef __CUDACC__
 #define PSB_HD __host__ __device__ __forceinline__
+// big, rarely executed routines: one out-of-line copy keeps the kernels' instruction footprint small
+#define PSB_HD_COLD __host__ __device__ __noinline__ inline
 #else
 #define PSB_HD inline
+#define PSB_HD_COLD inline
 #endif
 
 // exact (never FMA-contracted) multiply / add, for arithmetic whose bits must match the reference
@@ -117,7 +120,7 @@ PSB_HD double jax_remainder(double x1, double x2) {
 }
 
 // kind: 1 regular, 2 periodic, 3 Chebyshev.  Returns the uint32 index (== shape: out of bounds).
-PSB_HD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape) {
+PSB_HD_COLD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape) {
   const double size = upper - lower;
   const double n = (double)shape;
   double idx;
@@ -152,7 +155,7 @@ PSB_HD double mesh_coord(int kind, int32_t k, double lower, double upper, int32_
 // ---- small dense linear algebra -------------------------------------------------------------
 // Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 4), row-major in a[16].
 // On return a's diagonal holds the eigenvalues and v (row-major) the eigenvectors in columns.
-PSB_HD void jacobi_eig(int n, double* a, double* v) {
+PSB_HD_COLD void jacobi_eig(int n, double* a, double* v) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) v[i * 4 + j] = (i == j) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 32; ++sweep) {
@@ -193,7 +196,7 @@ PSB_HD void jacobi_eig(int n, double* a, double* v) {
 // convention, P @ U ~ Q) maximising tr(U^T C), C = P^T Q (row-major c[9]).  Computed with Horn's
 // quaternion eigenproblem (4x4 symmetric, Jacobi), which yields the same U as
 // V diag(1,1,sign(det V det W)) W from the SVD whenever the optimum is unique.
-PSB_HD void kabsch_rotation(const double* c, double* U) {
+PSB_HD_COLD void kabsch_rotation(const double* c, double* U) {
   const double Sxx = c[0], Sxy = c[1], Sxz = c[2];
   const double Syx = c[3], Syy = c[4], Syz = c[5];
   const double Szx = c[6], Szy = c[7], Szz = c[8];
@@ -223,7 +226,7 @@ PSB_HD void kabsch_rotation(const double* c, double* U) {
 
 // utils/core.py:128-134 `solve_pos_def(A A^T, A B)`: Cholesky solve of the k x k SPD system
 // (row-major, leading dimension 4).  Returns false when the matrix is not positive definite.
-PSB_HD bool chol_solve(int k, const double* A, const double* b, double* x) {
+PSB_HD_COLD bool chol_solve(int k, const double* A, const double* b, double* x) {
   double L[16];
   for (int i = 0; i < k; ++i)
     for (int j = 0; j <= i; ++j) {
@@ -253,7 +256,7 @@ PSB_HD bool chol_solve(int k, const double* A, const double* b, double* x) {
 // utils/core.py:125-126 `pinv(A.T) @ B` == pinv_sym(A A^T) (A B); cutoff follows
 // jnp.linalg.pinv's default rtol = 10 * max(M, N) * eps applied to the singular values of A^T
 // (eigenvalues of A A^T are their squares).
-PSB_HD void pinv_sym_solve(int k, const double* A, const double* b, double* x, double rtol_sv) {
+PSB_HD_COLD void pinv_sym_solve(int k, const double* A, const double* b, double* x, double rtol_sv) {
   double a[16], v[16];
   for (int i = 0; i < 16; ++i) a[i] = 0.0;
   for (int i = 0; i < k; ++i)

@@ -54,12 +54,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PSB_STAMP(slot)                                                              \
+  do {                                                                               \
+    if (M.dbg && threadIdx.x == 0) M.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
+  } while (0)
+
 struct StepShared {
   double red[NWARPS][NACC];
   double tot[MAXG + 1][NACC];
   Fin fin;  // CTA-local copy of the finalizer results
   unsigned long long gen;
-  int last;
   uint64_t mbar[2];
 };
 
@@ -82,8 +91,10 @@ __device__ __forceinline__ void block_reduce_store(StepShared& sh, const double*
   __syncthreads();
 }
 
-// Grid barrier in which the last CTA to arrive runs `finalize` (all its threads) before the
-// others are released.  Counters are monotonic and never reset; gridDim.x is fixed per handle.
+// Grid barrier with a finalizer: CTA 0 waits until every CTA has arrived, runs `finalize` (all its
+// threads) and then releases the others.  Pinning the finalizer to one CTA keeps its (large, rarely
+// executed) code resident in that SM's instruction cache from step to step.  Counters are
+// monotonic and never reset; gridDim.x is fixed per handle.
 template <typename Fn>
 __device__ __forceinline__ void grid_barrier(const Model& M, StepShared& sh, int id, Fn&& finalize) {
   if (gridDim.x == 1) {
@@ -98,11 +109,14 @@ __device__ __forceinline__ void grid_barrier(const Model& M, StepShared& sh, int
     __threadfence();
     const unsigned long long t = atomicAdd(&bs->arrive, 1ULL);
     sh.gen = t / gridDim.x;
-    sh.last = ((t % gridDim.x) == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (sh.last) {
-    __threadfence();
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      const unsigned long long want = (sh.gen + 1) * gridDim.x;
+      while (ld_acquire_u64(&bs->arrive) < want) {}
+    }
+    __syncthreads();
     finalize();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -134,7 +148,7 @@ __device__ __forceinline__ int nacc_for(const Model& M, const Snap& S, int g, in
 }
 
 // Deterministic reduction of the per-CTA partials of pass `pass` into sh.tot (run by one CTA).
-__device__ __forceinline__ void reduce_partials(const Model& M, const Snap& S, StepShared& sh,
+static __device__ __noinline__ void reduce_partials(const Model& M, const Snap& S, StepShared& sh,
                                                 int pass, int vgroup_nacc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb = gridDim.x;
@@ -185,7 +199,7 @@ __device__ inline void put3(double* dst, V3 v) {
 }
 
 // CV values and Jacobian factors after pass A.
-__device__ inline void finalize_cvs_A(const Model& M, StepShared& sh) {
+static __device__ __noinline__ void finalize_cvs_A(const Model& M, StepShared& sh) {
   Fin& f = sh.fin;
   for (int c = 0; c < M.ncv; ++c) {
     const CvDev& cv = M.cv[c];
@@ -254,7 +268,7 @@ __device__ inline void finalize_cvs_A(const Model& M, StepShared& sh) {
 }
 
 // RMSD value after pass B.
-__device__ inline void finalize_cvs_B(const Model& M, StepShared& sh) {
+static __device__ __noinline__ void finalize_cvs_B(const Model& M, StepShared& sh) {
   Fin& f = sh.fin;
   for (int c = 0; c < M.ncv; ++c) {
     const CvDev& cv = M.cv[c];
@@ -267,7 +281,7 @@ __device__ inline void finalize_cvs_B(const Model& M, StepShared& sh) {
 }
 
 // grid bin of xi; returns true when any index == shape (out of bounds marker, grids.py:120)
-__device__ inline bool grid_bin(const MethodDev& m, const double* xi, uint32_t* I) {
+static __device__ __noinline__ bool grid_bin(const MethodDev& m, const double* xi, uint32_t* I) {
   bool oob = false;
   for (int d = 0; d < m.grid_ndim; ++d) {
     I[d] = grid_index_1d(m.grid_kind, xi[d], m.g_lower[d], m.g_upper[d], m.g_shape[d]);
@@ -287,7 +301,7 @@ __device__ inline long long grid_flat_clamped(const MethodDev& m, const uint32_t
 
 // fg[g] = -sum_j F[comp0+j] dxi_{comp0+j}/dpoint_g / n_g  (the -J^T F of harmonic_bias.py:127,
 // metad.py:200, abf.py:223 restricted to one group)
-__device__ inline void compute_fg(const Model& M, Fin& f) {
+static __device__ __noinline__ void compute_fg(const Model& M, Fin& f) {
   for (int g = 0; g < M.ngroups; ++g) {
     const CvDev& cv = M.cv[M.grp[g].cv];
     double v[3] = {0, 0, 0};
@@ -298,7 +312,7 @@ __device__ inline void compute_fg(const Model& M, Fin& f) {
   }
 }
 
-__device__ inline void publish_force(const Model& M, Fin& f, long long ncalls_new) {
+static __device__ __noinline__ void publish_force(const Model& M, Fin& f, long long ncalls_new) {
   for (int c = 0; c < M.k; ++c) M.st.F[c] = f.F[c];
   *M.st.energy = f.energy;
   *M.st.ncalls = ncalls_new;
@@ -306,7 +320,7 @@ __device__ inline void publish_force(const Model& M, Fin& f, long long ncalls_ne
 }
 
 // abf.py:213-222 given W p inputs
-__device__ inline void abf_update(const Model& M, const Snap& S, Fin& f, const double* JJt,
+static __device__ __noinline__ void abf_update(const Model& M, const Snap& S, Fin& f, const double* JJt,
                                   const double* Jp) {
   const MethodDev& m = M.m;
   const int k = M.k;
@@ -367,7 +381,7 @@ __device__ __forceinline__ double hill_eval(const MethodDev& m, int k, const dou
 
 // Everything that can be decided once xi is complete (thread 0 of the finalizing CTA).
 // Returns through sh.fin; `stage_done` tells whether F / fg are final.
-__device__ inline void post_cv(const Model& M, const Snap& S, StepShared& sh) {
+static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh) {
   Fin& f = sh.fin;
   const MethodDev& m = M.m;
   const int k = M.k;
@@ -514,8 +528,8 @@ __device__ __forceinline__ int term_gradient(const Model& M, const Snap& S, cons
 }
 
 template <class A>
-__device__ __forceinline__ void apply_term_force(const Model& M, const Snap& S, uint32_t slot, V3 fo) {
-  A::add_force(S, slot, fo);
+__device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
+  A::store_force(S, slot, A::load_force(S, slot), fo);
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
@@ -535,6 +549,7 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
   const bool metad_direct = (m.kind == PSB_METHOD_METAD && m.grid_kind == PSB_GRID_NONE);
   const bool skip_cv = (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
 
+  PSB_STAMP(0);
   // ---- hill staging: kick off the first TMA bulk copies before touching any atom ------------
   long long nh = 0, h0 = 0, h1 = 0;
   const int HC = M.hill_chunk;
@@ -624,15 +639,22 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
       else block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
     }
 
+    PSB_STAMP(1);
     grid_barrier(M, sh, 0, [&] {
+      PSB_STAMP(8);
       reduce_partials(M, S, sh, 0, 0);
+      PSB_STAMP(9);
       if (tid == 0) {
         finalize_cvs_A(M, sh);
+        PSB_STAMP(10);
         if (!M.any_rmsd) post_cv(M, S, sh);
+        PSB_STAMP(11);
       }
       __syncthreads();
       fin_store(M, sh);
+      PSB_STAMP(12);
     });
+    PSB_STAMP(2);
 
     // ---- pass B: RMSD residual with the optimal rotation ------------------------------------
     if (M.any_rmsd) {
@@ -873,6 +895,7 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
 
   if (m.kind == PSB_METHOD_UNBIASED) return;
 
+  PSB_STAMP(3);
   // ---- pass S: in-place force scatter ------------------------------------------------------------
   const Fin& f = sh.fin;
   const bool dense = (M.bias_dense != nullptr);
@@ -884,7 +907,7 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
       if (is_point_kind(cv.kind)) {
         const V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
 #pragma unroll 4
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) A::add_force(S, __ldcg(M.term_slot + t), fo);
+        for (uint32_t t = lo + tid; t < hi; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fo);
       } else {
         const double Fc = -f.F[cv.comp0];
 #pragma unroll 2
@@ -892,7 +915,7 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
           const uint32_t slot = __ldcg(M.term_slot + t);
           V3 gv[3];
           term_gradient<A>(M, S, f, t, g, slot, gv);
-          A::add_force(S, slot, Fc * gv[0]);
+          add_force<A>(S, slot, Fc * gv[0]);
         }
       }
     }
@@ -920,13 +943,14 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
           }
         }
       }
-      A::add_force(S, slot, fo);
+      add_force<A>(S, slot, fo);
       if (dense) {
         double* B = M.bias_dense + 3 * (size_t)slot;
         B[0] = fo.x; B[1] = fo.y; B[2] = fo.z;
       }
     }
   }
+  PSB_STAMP(4);
 }
 
 }  // namespace psb
