@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "psb_launch.cuh"
+#include "psb_step.cuh"
 
 using namespace psb;
 
@@ -264,6 +265,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     cv.ncomp = d.kind == PSB_CV_DISPLACEMENT ? 3 : 1;
     k += cv.ncomp;
     if (k > PSB_MAX_K) return bail(fail(PSB_ERR_VALUE, "at most %d CV components are supported", PSB_MAX_K));
+    for (int j = cv.comp0; j < k; ++j) M.comp_cv[j] = c;
     cv.g0 = ng;
     cv.ngroups = d.n_groups;
     cv.t0 = (uint32_t)term_tag.size();
@@ -280,6 +282,10 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         term_group.push_back((uint8_t)ng);
       }
       G.t1 = (uint32_t)term_tag.size();
+      G.tag0 = d.tags[a];
+      G.contig = 1;
+      for (uint32_t i = a; i < b; ++i)
+        if (d.tags[i] != d.tags[a] + (i - a)) G.contig = 0;
       G.cv = c;
       G.local = g;
       G.inv_n = 1.0 / (double)(b - a);
@@ -471,7 +477,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       if ((st = dev_alloc(h, &s.Wp_, MAXK)) != PSB_OK) return bail(st);
     }
     if ((st = dev_alloc(h, &M.fin, 1)) != PSB_OK) return bail(st);
-    if ((st = dev_alloc(h, &M.bars, 8)) != PSB_OK) return bail(st);
+    if ((st = dev_alloc(h, &M.bars, NBARS)) != PSB_OK) return bail(st);
     if (layout->layout == PSB_LAYOUT_OPENMM_CUDA &&
         (st = dev_alloc(h, &M.inv_perm, (size_t)layout->natoms)) != PSB_OK)
       return bail(st);
@@ -482,21 +488,62 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   }
 
   // ---- launch shape --------------------------------------------------------------------------------
+  // gridDim.x == 1: one CTA walks every group (no grid barrier at all).  gridDim.x > 1: every CTA
+  // gathers ONE group (CTAs [cta_first[g], cta_first[g+1]) share group g evenly), at most
+  // CT * BLOCK terms per CTA when the device has room, so slots and prefetched forces stay in
+  // registers across the barrier.
   const bool metad_direct = (method->kind == PSB_METHOD_METAD && !gridded);
   if (metad_direct) {
     M.hill_chunk = (int)((HILL_STAGE_BYTES / ((k + 1) * 8)) & ~1);
     h->dyn_smem = 2 * (size_t)M.hill_chunk * (k + 1) * 8;
   }
+  M.need_term_slot = (!M.all_unique || layout->dense_outputs || (method->kind == PSB_METHOD_ABF && !M.abf_fast) ||
+                      method->shared_hills || M.any_coord)
+                         ? 1
+                         : 0;
   const int occ = pick_vtable(*layout)->occupancy(h->dyn_smem);
   if (occ < 1)
     return bail(fail(PSB_ERR_CUDA, "step kernel cannot be made resident (%s)", cudaGetErrorString(cudaGetLastError())));
   const long long max_blocks = (long long)std::min(occ, 2) * h->num_sms;
-  long long want = ((long long)M.T + BLOCK * 4 - 1) / (BLOCK * 4);
+  long long want;
+  if ((long long)M.T <= 2LL * BLOCK) {
+    want = 1;
+  } else if ((long long)M.T <= (long long)CT * BLOCK * h->num_sms) {
+    want = std::min<long long>(h->num_sms, ((long long)M.T + BLOCK - 1) / BLOCK);  // >= 1 term per thread
+  } else {
+    want = max_blocks;
+  }
   if (metad_direct) want = std::max(want, (long long)((method->ngaussians + M.hill_chunk - 1) / M.hill_chunk));
   if (method->kind == PSB_METHOD_METAD && gridded)
     want = std::max(want, (m.grid_points + BLOCK * 8 - 1) / (BLOCK * 8));
   if (const char* env = getenv("PSB_GRID_BLOCKS")) want = atoll(env);
-  h->grid = (int)std::max(1LL, std::min(want, max_blocks));
+  want = std::max(1LL, std::min(want, max_blocks));
+  if (want > 1) want = std::max<long long>(want, ng);
+  if (want > max_blocks) return bail(fail(PSB_ERR_CUDA, "device too small for %d atom groups", ng));
+  h->grid = (int)want;
+  if (h->grid > 1) {
+    // smallest per-CTA term count whose group-aligned split fits the grid
+    auto ctas_needed = [&](long long per) {
+      long long n = 0;
+      for (int g = 0; g < ng; ++g) n += ((long long)(M.grp[g].t1 - M.grp[g].t0) + per - 1) / per;
+      return n;
+    };
+    long long per = std::max(1LL, ((long long)M.T + h->grid - 1) / h->grid);
+    while (ctas_needed(per) > h->grid) per += std::max(1LL, per / 64);
+    M.cta_first[0] = 0;
+    for (int g = 0; g < ng; ++g)
+      M.cta_first[g + 1] = M.cta_first[g] + (int)(((long long)(M.grp[g].t1 - M.grp[g].t0) + per - 1) / per);
+    for (int g = ng; g < MAXG; ++g) M.cta_first[g + 1] = M.cta_first[ng];
+  }
+  {
+    const bool momenta_sums = layout->need_momenta && M.abf_fast;
+    for (int pass = 0; pass < 2; ++pass) {
+      M.row_first[pass][0] = 0;
+      for (int g = 0; g < MAXG; ++g)
+        M.row_first[pass][g + 1] =
+            M.row_first[pass][g] + (g < ng ? nacc_for_kind(M.cv[M.grp[g].cv].kind, pass, momenta_sums) : 0);
+    }
+  }
   h->cooperative = h->grid > 1;
   if (h->cooperative) {
     int coop = 0;

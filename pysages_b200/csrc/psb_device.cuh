@@ -24,6 +24,8 @@ struct GroupDev {
   int32_t cv;       // owning CV
   int32_t local;    // index of this group among the CV's groups
   double inv_n;     // 1 / group size
+  uint32_t tag0;    // first tag
+  int32_t contig;   // tags are tag0, tag0 + 1, ... (no index load needed)
 };
 
 struct CvDev {
@@ -84,7 +86,9 @@ struct StateDev {
   double* Wp_;       // (k)
 };
 
-// Results of the in-kernel finalizers, global memory, written by one CTA, read by all.
+// Results of the in-kernel finalizers.  Every CTA computes its own bit-identical copy in shared
+// memory (same inputs, same order of operations); the global copy (Model::fin) only carries the
+// CV stage from psb_walker_begin to psb_walker_finish.
 struct Fin {
   double xi[MAXK];
   double F[MAXK];
@@ -93,23 +97,43 @@ struct Fin {
   double gpt[MAXG][3][3];   // dxi_{comp0+j}/dpoint_g
   double cvx[MAXCV][20];    // RMSD: U[0..8], rbar[9..11], sumD[12..14], coef[15]; RoG: coef[0]
   double hill[MAXK + 2];    // candidate / deposited hill: centre[k], height, valid
+  double JJt[16];           // ABF: J J^T (leading dimension 4)
+  double Jp[MAXK];          // ABF: J p
+  double Wp[MAXK];          // ABF: solve(J J^T, J p)
+  double Fsum_new[MAXK];    // ABF: Fsum[I] after this step's scatter-add
+  long long flat;           // clamped flat grid offset of xi
+  long long nh;             // number of hills summed this step
   uint32_t I[PSB_MAX_GRID_DIMS];
+  uint32_t hist_new;        // ABF: hist[I] after this step's scatter-add
+  int32_t in_range;         // ABF: the scatter-add is not dropped
   int32_t oob;
   int32_t deposit;
-  long long nh;             // number of hills summed this step
+};
+
+// Method-state scalars every CTA reads before the first grid barrier (CTA 0 overwrites them after it)
+struct Pre {
+  long long ncalls, idx;
+  double Wp[MAXK], Wp_[MAXK], force[MAXK];
 };
 
 struct BarrierState {
   unsigned long long arrive;
-  unsigned long long release;
+  unsigned long long pad[15];  // one counter per 128-byte line
 };
+
+enum { BAR_A = 0, BAR_B = 1, BAR_C = 2, BAR_H = 3, BAR_D = 4, BAR_READERS = 5, BAR_PRE_D = 6, NBARS = 8 };
 
 struct Model {
   int32_t ncv, k, ngroups, all_unique;
   uint32_t T, Su;
   int32_t any_rmsd, any_coord, abf_fast, all_point;
+  int32_t need_term_slot;     // pass A must publish term -> slot (generic scatter, pass C, walkers)
+  int32_t hill_chunk;         // hills per TMA stage
   CvDev cv[MAXCV];
   GroupDev grp[MAXG];
+  int32_t comp_cv[MAXK];      // CV owning component c
+  int32_t cta_first[MAXG + 1];     // gridDim.x > 1: CTAs [cta_first[g], cta_first[g+1]) gather group g
+  int32_t row_first[2][MAXG + 1];  // prefix of accumulator rows per group, pass A / pass B
   uint32_t ov[MAXG][MAXG];    // group overlap counts (ABF fast path)
   const uint32_t* term_tag;   // (T)
   const uint8_t* term_group;  // (T)
@@ -120,17 +144,12 @@ struct Model {
   StateDev st;
   Fin* fin;
   double* partials;           // ((MAXG+1) * NACC, gridDim) fp64
-  BarrierState* bars;         // (8)
+  BarrierState* bars;         // (NBARS) monotonic arrival counters
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr
   long long natoms;
-  int32_t hill_chunk;         // hills per TMA stage
-  int32_t pad;
   long long* dbg;             // optional (PSB_DEBUG_TIMING=1): per-CTA phase timestamps [grid][16]
-  const int4* plan;           // partial-reduction plan: {dst = g * NACC + a, first CTA, last CTA, 0}
-  int32_t plan_off[2];        // first entry of pass A / pass B
-  int32_t plan_n[2];          // entries of pass A / pass B
 };
 
 struct Snap {

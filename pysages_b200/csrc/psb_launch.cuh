@@ -36,6 +36,9 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
   }                                                                                                 \
   static int NAME##_occupancy(size_t smem) {                                                        \
     int occ = 0;                                                                                    \
+    if (smem > 0 && cudaFuncSetAttribute(step_kernel<L, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem) != cudaSuccess)                                 \
+      return 0;                                                                                     \
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<L, R>, BLOCK, smem) !=      \
         cudaSuccess)                                                                                \
       return 0;                                                                                     \

@@ -1,10 +1,20 @@
 // psb_step.cuh -- the fused per-timestep bias kernel (sm_100a).
 //
-// One persistent (cooperative when gridDim.x > 1) launch per MD step:
-//   pass A   gather selected atoms (tag -> slot -> position [+ image unwrap] [+ momentum]),
-//            per-group fp64 block reductions                       (colvars/core.py:193 + CV sums)
-//   barrier  the LAST CTA to arrive reduces the per-CTA partials deterministically, evaluates
-//            the CVs + closed-form Jacobian factors and, when possible, the method update
+// One persistent (cooperative when gridDim.x > 1) launch per MD step.  The step is latency-bound
+// for every configuration below ~1e6 selected atoms, so the kernel is organised around the length
+// of its dependent chain, not around bytes:
+//
+//   prologue every CTA copies the few method-state scalars it needs into shared memory
+//   pass A   gather selected atoms (tag -> slot -> position [+ image unwrap] [+ momentum]);
+//            every CTA works on ONE atom group, keeps the slots of its (<= 4 per thread) terms in
+//            registers and PREFETCHES their force rows, so nothing is re-read after the barrier;
+//            per-group fp64 block reductions -> per-CTA partials   (colvars/core.py:193 + CV sums)
+//   barrier  one grid-wide arrive/wait.  EVERY CTA then reduces the partials in the same fixed
+//            order and evaluates CVs, closed-form Jacobian factors and the method update
+//            redundantly (warp 0, lanes split over CVs / matrix entries / grid axes), so there
+//            is no "finalizer CTA -> broadcast -> second barrier" on the critical path.  Only
+//            CTA 0 writes method state; bins other CTAs still read (ABF hist/Fsum) are written
+//            at the very end, after a non-blocking "readers done" counter.
 //   pass B   (RMSD only) residual sum with the optimal rotation    (orientation.py:76-95)
 //   pass C   (ABF with position-dependent Jacobians) J J^T and J p (abf.py:210-213)
 //   pass H   (Metadynamics, direct) hill sum over TMA-staged hills (metad.py:291, 318-323)
@@ -17,6 +27,8 @@
 #include "psb_device.cuh"
 
 namespace psb {
+
+constexpr int CT = 4;  // terms per thread kept in registers (slot, position, prefetched force)
 
 // ---- small device utilities -----------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -59,6 +71,10 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#define PSB_CLK(slot)                                                                \
+  do {                                                                               \
+    if (M.dbg && threadIdx.x == 0) M.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
 #define PSB_STAMP(slot)                                                              \
   do {                                                                               \
     if (M.dbg && threadIdx.x == 0) M.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
@@ -67,8 +83,8 @@ __device__ __forceinline__ long long global_ns() {
 struct StepShared {
   double red[NWARPS][NACC];
   double tot[MAXG + 1][NACC];
-  Fin fin;  // CTA-local copy of the finalizer results
-  unsigned long long gen;
+  Fin fin;  // this CTA's copy of the finalizer results
+  Pre pre;  // method-state scalars as they were when the step began
   uint64_t mbar[2];
 };
 
@@ -91,44 +107,21 @@ __device__ __forceinline__ void block_reduce_store(StepShared& sh, const double*
   __syncthreads();
 }
 
-// Grid barrier with a finalizer: CTA 0 waits until every CTA has arrived, runs `finalize` (all its
-// threads) and then releases the others.  Pinning the finalizer to one CTA keeps its (large, rarely
-// executed) code resident in that SM's instruction cache from step to step.  Counters are
-// monotonic and never reset; gridDim.x is fixed per handle.
-template <typename Fn>
-__device__ __forceinline__ void grid_barrier(const Model& M, StepShared& sh, int id, Fn&& finalize) {
-  if (gridDim.x == 1) {
-    __syncthreads();
-    finalize();
-    __syncthreads();
-    return;
-  }
-  BarrierState* bs = M.bars + id;
+// Grid-wide barrier on a monotonic arrival counter (never reset; gridDim.x is fixed per handle and
+// every launch that uses barrier `id` arrives on it from every CTA).
+__device__ __forceinline__ unsigned long long grid_arrive(const Model& M, int id) {
+  __threadfence();
+  const unsigned long long t = atomicAdd(&M.bars[id].arrive, 1ULL);
+  return (t / gridDim.x + 1ULL) * gridDim.x;
+}
+__device__ __forceinline__ void grid_wait(const Model& M, int id, unsigned long long want) {
+  while (ld_acquire_u64(&M.bars[id].arrive) < want) {}
+}
+__device__ __forceinline__ void grid_sync(const Model& M, int id) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long t = atomicAdd(&bs->arrive, 1ULL);
-    sh.gen = t / gridDim.x;
-  }
+  if (gridDim.x == 1) return;
+  if (threadIdx.x == 0) grid_wait(M, id, grid_arrive(M, id));
   __syncthreads();
-  if (blockIdx.x == 0) {
-    if (threadIdx.x == 0) {
-      const unsigned long long want = (sh.gen + 1) * gridDim.x;
-      while (ld_acquire_u64(&bs->arrive) < want) {}
-    }
-    __syncthreads();
-    finalize();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&bs->release, 1ULL);
-    }
-  } else {
-    if (threadIdx.x == 0) {
-      while (ld_acquire_u64(&bs->release) <= sh.gen) __nanosleep(32);
-    }
-    __syncthreads();
-  }
 }
 
 __host__ __device__ __forceinline__ bool is_point_kind(int kind) {
@@ -136,10 +129,9 @@ __host__ __device__ __forceinline__ bool is_point_kind(int kind) {
 }
 
 // accumulators per group in pass `pass` (0 = A, 1 = B)
-__device__ __forceinline__ int nacc_for(const Model& M, const Snap& S, int g, int pass) {
-  const int kind = M.cv[M.grp[g].cv].kind;
+__host__ __device__ __forceinline__ int nacc_for_kind(int kind, int pass, bool momenta_sums) {
   if (pass == 0) {
-    if (is_point_kind(kind)) return (S.need_momenta && M.abf_fast) ? 6 : 3;
+    if (is_point_kind(kind)) return momenta_sums ? 6 : 3;
     if (kind == PSB_CV_ROG) return 1;
     if (kind == PSB_CV_RMSD) return 15;
     return 0;
@@ -147,150 +139,141 @@ __device__ __forceinline__ int nacc_for(const Model& M, const Snap& S, int g, in
   return kind == PSB_CV_RMSD ? 1 : 0;
 }
 
-// Deterministic reduction of the per-CTA partials of pass `pass` into sh.tot (run by one CTA).
-static __device__ __noinline__ void reduce_partials(const Model& M, const Snap& S, StepShared& sh,
-                                                int pass, int vgroup_nacc) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Deterministic reduction of the per-CTA partials into sh.tot, done by EVERY CTA in the same
+// order.  pass 0 / 1: the rows of the atom groups (group g lives in CTAs cta_first[g] ..
+// cta_first[g+1]-1); pass >= 2: `vrows` rows of the virtual group, spanning all CTAs.
+// Eight threads share one row: 4 independent L2 loads each per round, then 3 shuffle steps.
+__device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int pass, int vrows) {
   const int nb = gridDim.x;
   if (nb > 1) {
-    const uint32_t chunk = (M.T + nb - 1) / nb;
-    const int npairs = (MAXG + 1) * NACC;
-    for (int pair = warp; pair < npairs; pair += NWARPS) {
-      const int g = pair / NACC, a = pair % NACC;
-      int blo, bhi, na;
-      if (g < MAXG) {
-        if (g >= M.ngroups) continue;
-        if (pass > 1) continue;
-        na = nacc_for(M, S, g, pass);
-        if (M.grp[g].t1 <= M.grp[g].t0) continue;
-        blo = (int)(M.grp[g].t0 / chunk);
-        bhi = (int)((M.grp[g].t1 - 1) / chunk);
-      } else {
-        na = vgroup_nacc;
-        blo = 0;
-        bhi = nb - 1;
+    const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int nrows = pass < 2 ? M.row_first[pass][M.ngroups] : vrows;
+    for (int r0 = 0; r0 < nrows; r0 += BLOCK / 8) {
+      const int r = r0 + rl;
+      double v = 0.0;
+      int dst = 0;
+      if (r < nrows) {
+        int blo, bhi;
+        if (pass < 2) {
+          int g = 0;
+          while (r >= M.row_first[pass][g + 1]) ++g;
+          dst = g * NACC + (r - M.row_first[pass][g]);
+          blo = M.cta_first[g];
+          bhi = M.cta_first[g + 1] - 1;
+        } else {
+          dst = VGROUP * NACC + r;
+          blo = 0;
+          bhi = nb - 1;
+        }
+        const double* src = M.partials + (size_t)dst * nb;
+        for (int bb = blo + sub; bb <= bhi; bb += 32) {
+          const double a0 = __ldcg(src + bb);
+          const double a1 = bb + 8 <= bhi ? __ldcg(src + bb + 8) : 0.0;
+          const double a2 = bb + 16 <= bhi ? __ldcg(src + bb + 16) : 0.0;
+          const double a3 = bb + 24 <= bhi ? __ldcg(src + bb + 24) : 0.0;
+          v += (a0 + a1) + (a2 + a3);
+        }
       }
-      if (a >= na) continue;
-      double v = 0.0;
-      for (int bb = blo + lane; bb <= bhi; bb += 32) v += __ldcg(M.partials + (size_t)pair * nb + bb);
-      v = warp_sum(v);
-      if (lane == 0) sh.tot[g][a] = v;
-    }
-  }
-  // coordination CVs: partial sums come from the pair kernel
-  if (pass == 0 && M.any_coord) {
-    for (int c = warp; c < M.ncv; c += NWARPS) {
-      if (M.cv[c].kind != PSB_CV_COORDINATION) continue;
-      double v = 0.0;
-      for (int i = lane; i < M.cv[c].n_part; i += 32) v += __ldcg(M.cv[c].xi_part + i);
-      v = warp_sum(v);
-      if (lane == 0) sh.tot[M.cv[c].g0][0] = v;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (r < nrows && sub == 0) (&sh.tot[0][0])[dst] = v;
     }
   }
   __syncthreads();
 }
 
-// ---- finalizers (thread 0 of one CTA) ----------------------------------------------------------
-__device__ inline V3 tot3(const StepShared& sh, int g, int o) {
+// ---- finalizers (warp 0 of every CTA) ----------------------------------------------------------
+__device__ __forceinline__ V3 tot3(const StepShared& sh, int g, int o) {
   return v3(sh.tot[g][o], sh.tot[g][o + 1], sh.tot[g][o + 2]);
 }
-__device__ inline void put3(double* dst, V3 v) {
+__device__ __forceinline__ void put3(double* dst, V3 v) {
   dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
 }
 
-// CV values and Jacobian factors after pass A.
-static __device__ __noinline__ void finalize_cvs_A(const Model& M, StepShared& sh) {
+// CV `c`: value and Jacobian factors after pass A (one lane per CV).
+static __device__ __noinline__ void finalize_cv_A(const Model& M, StepShared& sh, int c) {
   Fin& f = sh.fin;
-  for (int c = 0; c < M.ncv; ++c) {
-    const CvDev& cv = M.cv[c];
-    const int g0 = cv.g0;
-    V3 p[4];
-    if (is_point_kind(cv.kind))
-      for (int j = 0; j < cv.ngroups; ++j) p[j] = M.grp[g0 + j].inv_n * tot3(sh, g0 + j, 0);
-    for (int j = 0; j < cv.ngroups && is_point_kind(cv.kind); ++j)
+  const CvDev& cv = M.cv[c];
+  const int g0 = cv.g0;
+  V3 p[4];
+  if (is_point_kind(cv.kind)) {
+    for (int j = 0; j < cv.ngroups; ++j) {
+      p[j] = M.grp[g0 + j].inv_n * tot3(sh, g0 + j, 0);
       for (int q = 0; q < 3; ++q) put3(f.gpt[g0 + j][q], v3(0, 0, 0));
-    switch (cv.kind) {
-      case PSB_CV_COMPONENT: {  // coordinates.py:28,71
-        f.xi[cv.comp0] = comp(p[0], cv.axis);
-        f.gpt[g0][0][cv.axis] = 1.0;
-      } break;
-      case PSB_CV_DISTANCE: {
-        V3 a, b;
-        f.xi[cv.comp0] = distance_cv(p[0], p[1], &a, &b);
-        put3(f.gpt[g0][0], a);
-        put3(f.gpt[g0 + 1][0], b);
-      } break;
-      case PSB_CV_DISPLACEMENT: {  // coordinates.py:148: r2 - r1
-        V3 d = p[1] - p[0];
-        f.xi[cv.comp0 + 0] = d.x; f.xi[cv.comp0 + 1] = d.y; f.xi[cv.comp0 + 2] = d.z;
-        for (int q = 0; q < 3; ++q) {
-          f.gpt[g0][q][q] = -1.0;
-          f.gpt[g0 + 1][q][q] = 1.0;
-        }
-      } break;
-      case PSB_CV_ANGLE: {
-        V3 a, b, d;
-        f.xi[cv.comp0] = angle_cv(p[0], p[1], p[2], &a, &b, &d);
-        put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b); put3(f.gpt[g0 + 2][0], d);
-      } break;
-      case PSB_CV_DIHEDRAL: {
-        V3 a, b, d, e;
-        f.xi[cv.comp0] = dihedral_cv(p[0], p[1], p[2], p[3], &a, &b, &d, &e);
-        put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b);
-        put3(f.gpt[g0 + 2][0], d); put3(f.gpt[g0 + 3][0], e);
-      } break;
-      case PSB_CV_ROG: {  // shape.py:52-57: sum r.r / n ; d/dr_i = 2 r_i / n
-        f.xi[cv.comp0] = sh.tot[g0][0] * M.grp[g0].inv_n;
-        f.cvx[c][0] = 2.0 * M.grp[g0].inv_n;
-      } break;
-      case PSB_CV_RMSD: {  // orientation.py:33-73
-        const V3 rbar = tot3(sh, g0, 0);  // sum_i w_i r_i
-        const V3 sumr = tot3(sh, g0, 3);
-        double C[9];
-        const double rb[3] = {rbar.x, rbar.y, rbar.z};
-        for (int a = 0; a < 3; ++a)
-          for (int b = 0; b < 3; ++b) C[a * 3 + b] = sh.tot[g0][6 + a * 3 + b] - rb[a] * cv.sumQ[b];
-        double* x = f.cvx[c];
-        kabsch_rotation(C, x);  // U -> x[0..8]
-        put3(x + 9, rbar);
-        // sum_i D_i = sum_i P_i - (sum_i Q_i) U^T
-        const double n = 1.0 / M.grp[g0].inv_n;
-        const double sp[3] = {sumr.x - n * rbar.x, sumr.y - n * rbar.y, sumr.z - n * rbar.z};
-        for (int a = 0; a < 3; ++a)
-          x[12 + a] = sp[a] - (cv.sumQ[0] * x[a * 3 + 0] + cv.sumQ[1] * x[a * 3 + 1] + cv.sumQ[2] * x[a * 3 + 2]);
-      } break;
-      case PSB_CV_COORDINATION: {
-        f.xi[cv.comp0] = sh.tot[g0][0];
-      } break;
-      default: break;
     }
   }
+  switch (cv.kind) {
+    case PSB_CV_COMPONENT: {  // coordinates.py:28,71
+      f.xi[cv.comp0] = comp(p[0], cv.axis);
+      f.gpt[g0][0][cv.axis] = 1.0;
+    } break;
+    case PSB_CV_DISTANCE: {
+      V3 a, b;
+      f.xi[cv.comp0] = distance_cv(p[0], p[1], &a, &b);
+      put3(f.gpt[g0][0], a);
+      put3(f.gpt[g0 + 1][0], b);
+    } break;
+    case PSB_CV_DISPLACEMENT: {  // coordinates.py:148: r2 - r1
+      V3 d = p[1] - p[0];
+      f.xi[cv.comp0 + 0] = d.x; f.xi[cv.comp0 + 1] = d.y; f.xi[cv.comp0 + 2] = d.z;
+      for (int q = 0; q < 3; ++q) {
+        f.gpt[g0][q][q] = -1.0;
+        f.gpt[g0 + 1][q][q] = 1.0;
+      }
+    } break;
+    case PSB_CV_ANGLE: {
+      V3 a, b, d;
+      f.xi[cv.comp0] = angle_cv(p[0], p[1], p[2], &a, &b, &d);
+      put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b); put3(f.gpt[g0 + 2][0], d);
+    } break;
+    case PSB_CV_DIHEDRAL: {
+      V3 a, b, d, e;
+      f.xi[cv.comp0] = dihedral_cv(p[0], p[1], p[2], p[3], &a, &b, &d, &e);
+      put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b);
+      put3(f.gpt[g0 + 2][0], d); put3(f.gpt[g0 + 3][0], e);
+    } break;
+    case PSB_CV_ROG: {  // shape.py:52-57: sum r.r / n ; d/dr_i = 2 r_i / n
+      f.xi[cv.comp0] = sh.tot[g0][0] * M.grp[g0].inv_n;
+      f.cvx[c][0] = 2.0 * M.grp[g0].inv_n;
+    } break;
+    case PSB_CV_RMSD: {  // orientation.py:33-73
+      const V3 rbar = tot3(sh, g0, 0);  // sum_i w_i r_i
+      const V3 sumr = tot3(sh, g0, 3);
+      double C[9];
+      const double rb[3] = {rbar.x, rbar.y, rbar.z};
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) C[a * 3 + b] = sh.tot[g0][6 + a * 3 + b] - rb[a] * cv.sumQ[b];
+      double* x = f.cvx[c];
+      kabsch_rotation(C, x);  // U -> x[0..8]
+      put3(x + 9, rbar);
+      // sum_i D_i = sum_i P_i - (sum_i Q_i) U^T
+      const double n = 1.0 / M.grp[g0].inv_n;
+      const double sp[3] = {sumr.x - n * rbar.x, sumr.y - n * rbar.y, sumr.z - n * rbar.z};
+      for (int a = 0; a < 3; ++a)
+        x[12 + a] = sp[a] - (cv.sumQ[0] * x[a * 3 + 0] + cv.sumQ[1] * x[a * 3 + 1] + cv.sumQ[2] * x[a * 3 + 2]);
+    } break;
+    case PSB_CV_COORDINATION: {
+      f.xi[cv.comp0] = sh.tot[g0][0];
+    } break;
+    default: break;
+  }
 }
 
-// RMSD value after pass B.
-static __device__ __noinline__ void finalize_cvs_B(const Model& M, StepShared& sh) {
-  Fin& f = sh.fin;
+// coordination CVs: the pair kernel left per-CTA partial sums; warp 0 adds them up (fixed order)
+__device__ __forceinline__ void reduce_coordination(const Model& M, StepShared& sh, int lane) {
   for (int c = 0; c < M.ncv; ++c) {
-    const CvDev& cv = M.cv[c];
-    if (cv.kind != PSB_CV_RMSD) continue;
-    const double inv_n = M.grp[cv.g0].inv_n;
-    const double xi = sqrt(sh.tot[cv.g0][0] * inv_n);  // orientation.py:94
-    f.xi[cv.comp0] = xi;
-    f.cvx[c][15] = inv_n / xi;  // 1 / (n rmsd)
+    if (M.cv[c].kind != PSB_CV_COORDINATION) continue;
+    double v = 0.0;
+    for (int i = lane; i < M.cv[c].n_part; i += 32) v += __ldcg(M.cv[c].xi_part + i);
+    v = warp_sum(v);
+    if (lane == 0) sh.tot[M.cv[c].g0][0] = v;
   }
+  __syncwarp();
 }
 
-// grid bin of xi; returns true when any index == shape (out of bounds marker, grids.py:120)
-static __device__ __noinline__ bool grid_bin(const MethodDev& m, const double* xi, uint32_t* I) {
-  bool oob = false;
-  for (int d = 0; d < m.grid_ndim; ++d) {
-    I[d] = grid_index_1d(m.grid_kind, xi[d], m.g_lower[d], m.g_upper[d], m.g_shape[d]);
-    oob |= (I[d] == (uint32_t)m.g_shape[d]);
-  }
-  return oob;
-}
 // flat row-major offset with JAX's clamp-on-gather semantics
-__device__ inline long long grid_flat_clamped(const MethodDev& m, const uint32_t* I) {
+__device__ __forceinline__ long long grid_flat_clamped(const MethodDev& m, const uint32_t* I) {
   long long o = 0;
   for (int d = 0; d < m.grid_ndim; ++d) {
     uint32_t i = I[d] < (uint32_t)m.g_shape[d] ? I[d] : (uint32_t)m.g_shape[d] - 1;
@@ -299,10 +282,29 @@ __device__ inline long long grid_flat_clamped(const MethodDev& m, const uint32_t
   return o;
 }
 
-// fg[g] = -sum_j F[comp0+j] dxi_{comp0+j}/dpoint_g / n_g  (the -J^T F of harmonic_bias.py:127,
-// metad.py:200, abf.py:223 restricted to one group)
-static __device__ __noinline__ void compute_fg(const Model& M, Fin& f) {
-  for (int g = 0; g < M.ngroups; ++g) {
+// grid bin of xi, one lane per axis (grids.py:109-158); lane 0 then derives the out-of-bounds
+// flag (any index == shape, grids.py:120) and the clamped flat offset.
+__device__ __forceinline__ void grid_bin_warp(const MethodDev& m, Fin& f, int lane) {
+  if (lane < m.grid_ndim)
+    f.I[lane] = grid_index_1d(m.grid_kind, f.xi[lane], m.g_lower[lane], m.g_upper[lane], m.g_shape[lane]);
+  __syncwarp();
+  if (lane == 0) {
+    bool oob = false;
+    for (int d = 0; d < m.grid_ndim; ++d) oob |= (f.I[d] == (uint32_t)m.g_shape[d]);
+    f.oob = oob ? 1 : 0;
+    f.flat = grid_flat_clamped(m, f.I);
+  }
+  __syncwarp();
+}
+
+// F is final: fg[g] = -sum_j F[comp0+j] dxi_{comp0+j}/dpoint_g / n_g (the -J^T F of
+// harmonic_bias.py:127, metad.py:200, abf.py:223 restricted to one group; one lane per group),
+// and CTA 0 publishes the generalized force, the bias energy and the call counter.
+__device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int lane, bool cta0) {
+  Fin& f = sh.fin;
+  __syncwarp();
+  if (lane < M.ngroups) {
+    const int g = lane;
     const CvDev& cv = M.cv[M.grp[g].cv];
     double v[3] = {0, 0, 0};
     if (is_point_kind(cv.kind))
@@ -310,55 +312,67 @@ static __device__ __noinline__ void compute_fg(const Model& M, Fin& f) {
         for (int a = 0; a < 3; ++a) v[a] -= f.F[cv.comp0 + j] * f.gpt[g][j][a] * M.grp[g].inv_n;
     f.fg[g][0] = v[0]; f.fg[g][1] = v[1]; f.fg[g][2] = v[2];
   }
-}
-
-static __device__ __noinline__ void publish_force(const Model& M, Fin& f, long long ncalls_new) {
-  for (int c = 0; c < M.k; ++c) M.st.F[c] = f.F[c];
-  *M.st.energy = f.energy;
-  *M.st.ncalls = ncalls_new;
-  compute_fg(M, f);
-}
-
-// abf.py:213-222 given W p inputs
-static __device__ __noinline__ void abf_update(const Model& M, const Snap& S, Fin& f, const double* JJt,
-                                  const double* Jp) {
-  const MethodDev& m = M.m;
-  const int k = M.k;
-  double Wp[MAXK] = {0, 0, 0, 0};
-  if (m.use_pinv) {
-    pinv_sym_solve(k, JJt, Jp, Wp, 10.0 * (double)(3 * M.natoms) * 2.220446049250313e-16);
-  } else if (!chol_solve(k, JJt, Jp, Wp)) {
-    for (int c = 0; c < k; ++c) Wp[c] = nan("");
-  }
-  uint32_t I[PSB_MAX_GRID_DIMS];
-  const bool oob = grid_bin(m, f.xi, I);
-  bool in_range = true;
-  for (int d = 0; d < k; ++d) in_range &= (I[d] < (uint32_t)m.g_shape[d]);
-  const long long flat = grid_flat_clamped(m, I);
-  if (in_range) {  // scatter-add is dropped when out of range
-    M.st.hist[flat] += 1u;
-    for (int c = 0; c < k; ++c) {
-      const double dWp_dt = (1.5 * Wp[c] - 2.0 * M.st.Wp[c] + 0.5 * M.st.Wp_[c]) / S.dt;
-      M.st.Fsum[flat * k + c] += m.force_unit_factor * dWp_dt + M.st.force[c];
+  if (cta0) {
+    if (lane < M.k) M.st.F[lane] = f.F[lane];
+    if (lane == 0) {
+      *M.st.energy = f.energy;
+      *M.st.ncalls = sh.pre.ncalls + 1;
     }
   }
-  for (int c = 0; c < k; ++c) {
+}
+
+// abf.py:210-225 once f.JJt / f.Jp are known (warp 0, all lanes).  Every CTA derives the new
+// histogram count and force sum of bin I from the values the step began with; CTA 0 stores them
+// after the last reader is done (end of the kernel).
+__device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
+  Fin& f = sh.fin;
+  const MethodDev& m = M.m;
+  const int k = M.k;
+  __syncwarp();
+  if (lane == 0) {  // utils/core.py:120-136
+    double Wp[MAXK] = {0, 0, 0, 0};
+    if (m.use_pinv) {
+      pinv_sym_solve(k, f.JJt, f.Jp, Wp, 10.0 * (double)(3 * M.natoms) * 2.220446049250313e-16);
+    } else if (!chol_solve(k, f.JJt, f.Jp, Wp)) {
+      for (int c = 0; c < k; ++c) Wp[c] = nan("");
+    }
+    for (int c = 0; c < MAXK; ++c) f.Wp[c] = Wp[c];
+  }
+  PSB_CLK(12);
+  grid_bin_warp(m, f, lane);  // ends with __syncwarp
+  PSB_CLK(13);
+  const bool oob = f.oob != 0;
+  if (lane == 0) f.in_range = oob ? 0 : 1;  // .at[I].add drops out-of-range updates
+  if (lane < k) {
+    const int c = lane;
+    const long long flat = f.flat;
+    uint32_t h = __ldcg(M.st.hist + flat);  // gather clamps (JAX default)
+    double fs = __ldcg(M.st.Fsum + flat * k + c);
+    if (!oob) {
+      h += 1u;
+      const double dWp_dt = (1.5 * f.Wp[c] - 2.0 * sh.pre.Wp[c] + 0.5 * sh.pre.Wp_[c]) / S.dt;
+      fs += m.force_unit_factor * dWp_dt + sh.pre.force[c];
+    }
     double fc;
     if (m.has_restraints && oob) {
       fc = restraint_force(m.r_lower[c], m.r_upper[c], m.r_kl[c], m.r_ku[c], f.xi[c]);
-    } else {  // gather clamps
-      const unsigned long long h = M.st.hist[flat];
-      const double den = (double)((unsigned long long)m.abf_N > h ? (unsigned long long)m.abf_N : h);
-      fc = M.st.Fsum[flat * k + c] / den;
+    } else {
+      const unsigned long long hh = h;
+      const double den = (double)((unsigned long long)m.abf_N > hh ? (unsigned long long)m.abf_N : hh);
+      fc = fs / den;
     }
     f.F[c] = fc;
-    M.st.force[c] = fc;
-    M.st.Wp_[c] = M.st.Wp[c];
-    M.st.Wp[c] = Wp[c];
+    f.Fsum_new[c] = fs;
+    if (c == 0) f.hist_new = h;
+    if (cta0) {  // scalars nobody reads after the first barrier
+      M.st.force[c] = fc;
+      M.st.Wp_[c] = sh.pre.Wp[c];
+      M.st.Wp[c] = f.Wp[c];
+    }
   }
-  for (int d = 0; d < PSB_MAX_GRID_DIMS; ++d) f.I[d] = d < k ? I[d] : 0;
-  f.oob = oob;
-  f.energy = 0.0;
+  if (lane == 0) f.energy = 0.0;
+  PSB_CLK(14);
+  finish_force(M, sh, lane, cta0);
 }
 
 // Value/gradient of one Gaussian at xi (utils/core.py:113-117, metad.py:318-323)
@@ -379,105 +393,144 @@ __device__ __forceinline__ double hill_eval(const MethodDev& m, int k, const dou
   return e;
 }
 
-// Everything that can be decided once xi is complete (thread 0 of the finalizing CTA).
-// Returns through sh.fin; `stage_done` tells whether F / fg are final.
-static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh) {
+// metad.py:293-312 in grid mode: generalized force from the gradient grid (nearest bin) or, out of
+// bounds, from the restraints / zeros.  One lane per component.
+__device__ __forceinline__ void metad_grid_force(const Model& M, Fin& f, int lane) {
+  const MethodDev& m = M.m;
+  const int k = M.k;
+  if (lane < k) {
+    const int c = lane;
+    if (f.oob) {
+      f.F[c] = m.has_restraints ? restraint_force(m.r_lower[c], m.r_upper[c], m.r_kl[c], m.r_ku[c], f.xi[c]) : 0.0;
+    } else {
+      f.F[c] = __ldcg(M.st.gg + f.flat * k + c);
+    }
+  }
+  if (lane == 0) f.energy = (!f.oob && M.st.gp) ? __ldcg(M.st.gp + f.flat) : 0.0;
+}
+
+// Everything that can be decided once xi is complete (warp 0, all lanes).
+static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
   Fin& f = sh.fin;
   const MethodDev& m = M.m;
   const int k = M.k;
-  for (int c = 0; c < k; ++c) M.st.xi[c] = f.xi[c];
-  f.deposit = 0;
-  f.oob = 0;
-  f.energy = 0.0;
-  for (int c = 0; c < MAXK; ++c) f.F[c] = 0.0;
+  __syncwarp();
+  if (cta0 && lane < k) M.st.xi[lane] = f.xi[lane];
+  if (lane == 0) {
+    f.deposit = 0;
+    f.oob = 0;
+    f.energy = 0.0;
+  }
+  if (lane < MAXK) f.F[lane] = 0.0;
+  __syncwarp();
   if (S.mode == MODE_EVAL) return;
-  const long long ncalls = *M.st.ncalls + 1;
+  const long long ncalls = sh.pre.ncalls + 1;
   switch (m.kind) {
-    case PSB_METHOD_UNBIASED: publish_force(M, f, ncalls); break;
+    case PSB_METHOD_UNBIASED: finish_force(M, sh, lane, cta0); break;
     case PSB_METHOD_HARMONIC: {  // harmonic_bias.py:124-128 (no periodic wrap: quirk kept)
-      double e = 0.0;
-      for (int a = 0; a < k; ++a) {
+      if (lane < k) {
         double s = 0.0;
-        for (int b = 0; b < k; ++b) s += m.kspring[a * MAXK + b] * (f.xi[b] - m.center[b]);
-        f.F[a] = s;
-        e += 0.5 * (f.xi[a] - m.center[a]) * s;
+        for (int b = 0; b < k; ++b) s += m.kspring[lane * MAXK + b] * (f.xi[b] - m.center[b]);
+        f.F[lane] = s;
       }
-      f.energy = e;
-      publish_force(M, f, ncalls);
+      __syncwarp();
+      if (lane == 0) {
+        double e = 0.0;
+        for (int a = 0; a < k; ++a) e += 0.5 * (f.xi[a] - m.center[a]) * f.F[a];
+        f.energy = e;
+      }
+      finish_force(M, sh, lane, cta0);
     } break;
     case PSB_METHOD_ABF: {
       if (!M.abf_fast) break;  // needs pass C
-      // J J^T and J p from per-group sums: point-CV Jacobians are constant within a group
-      double JJt[16], Jp[MAXK];
-      for (int i = 0; i < 16; ++i) JJt[i] = 0.0;
-      for (int i = 0; i < MAXK; ++i) Jp[i] = 0.0;
-      for (int g = 0; g < M.ngroups; ++g) {
-        const CvDev& ca = M.cv[M.grp[g].cv];
-        const V3 ps = tot3(sh, g, 3);
-        for (int ja = 0; ja < ca.ncomp; ++ja) {
-          const double* ga = f.gpt[g][ja];
-          Jp[ca.comp0 + ja] += (ga[0] * ps.x + ga[1] * ps.y + ga[2] * ps.z) * M.grp[g].inv_n;
-          for (int h = 0; h < M.ngroups; ++h) {
-            if (M.ov[g][h] == 0) continue;
-            const CvDev& cb = M.cv[M.grp[h].cv];
-            for (int jb = 0; jb < cb.ncomp; ++jb) {
+      // J J^T and J p from per-group sums: point-CV Jacobians are constant within a group.
+      // lanes 0..15: entry (a, b) of J J^T; lanes 16..19: entry a of J p.
+      if (lane < 16) {
+        const int a = lane >> 2, bq = lane & 3;
+        double s = 0.0;
+        if (a < k && bq < k) {
+          const CvDev& ca = M.cv[M.comp_cv[a]];
+          const CvDev& cb = M.cv[M.comp_cv[bq]];
+          const int ja = a - ca.comp0, jb = bq - cb.comp0;
+          for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g)
+            for (int h = cb.g0; h < cb.g0 + cb.ngroups; ++h) {
+              if (M.ov[g][h] == 0) continue;
+              const double* ga = f.gpt[g][ja];
               const double* gb = f.gpt[h][jb];
-              JJt[(ca.comp0 + ja) * 4 + cb.comp0 + jb] += (double)M.ov[g][h] *
-                  (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * M.grp[g].inv_n * M.grp[h].inv_n;
+              s += (double)M.ov[g][h] * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * M.grp[g].inv_n *
+                   M.grp[h].inv_n;
             }
+        }
+        f.JJt[lane] = s;
+      } else if (lane < 16 + MAXK) {
+        const int a = lane - 16;
+        double s = 0.0;
+        if (a < k) {
+          const CvDev& ca = M.cv[M.comp_cv[a]];
+          const int ja = a - ca.comp0;
+          for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g) {
+            const V3 ps = tot3(sh, g, 3);
+            const double* ga = f.gpt[g][ja];
+            s += (ga[0] * ps.x + ga[1] * ps.y + ga[2] * ps.z) * M.grp[g].inv_n;
           }
         }
+        f.Jp[a] = s;
       }
-      abf_update(M, S, f, JJt, Jp);
-      publish_force(M, f, ncalls);
+      PSB_CLK(11);
+      abf_finish(M, S, sh, lane, cta0);
     } break;
     case PSB_METHOD_METAD: {
       const bool in_dep = (ncalls > 1) && (ncalls % m.stride == 1);  // metad.py:192-193
       if (m.grid_kind == PSB_GRID_NONE) {
-        f.deposit = in_dep ? 1 : 0;  // heights need V: decided after pass H
+        if (lane == 0) f.deposit = in_dep ? 1 : 0;  // heights need V: decided after pass H
         break;
       }
-      const bool oob = grid_bin(m, f.xi, f.I);
-      f.oob = oob;
-      const long long flat = grid_flat_clamped(m, f.I);
-      if (in_dep && !oob) {  // metad.py:258-271
-        double h = m.height;
-        if (m.well_tempered) h = m.height * exp(-M.st.gp[flat] / m.deltaT_kB);  // metad.py:223-229
-        for (int c = 0; c < k; ++c) f.hill[c] = f.xi[c];
-        f.hill[k] = h;
-        f.hill[k + 1] = 1.0;
-        f.deposit = 1;
-        if (S.mode == MODE_STEP) {
-          const long long idx = *M.st.idx;
-          if (idx < m.ngaussians) {
-            M.st.heights[idx] = h;
-            for (int c = 0; c < k; ++c) M.st.centers[idx * k + c] = f.xi[c];
+      grid_bin_warp(m, f, lane);
+      if (lane < k) f.hill[lane] = f.xi[lane];
+      if (in_dep && !f.oob) {  // metad.py:258-271
+        if (lane == 0) {
+          double h = m.height;
+          if (m.well_tempered) h = m.height * exp(-__ldcg(M.st.gp + f.flat) / m.deltaT_kB);  // metad.py:223-229
+          f.hill[k] = h;
+          f.hill[k + 1] = 1.0;
+          f.deposit = 1;
+          if (S.mode == MODE_STEP && cta0) {
+            const long long idx = sh.pre.idx;
+            if (idx < m.ngaussians) {
+              M.st.heights[idx] = h;
+              for (int c = 0; c < k; ++c) M.st.centers[idx * k + c] = f.xi[c];
+            }
+            *M.st.idx = idx + 1;
           }
-          *M.st.idx = idx + 1;
         }
       } else {
-        for (int c = 0; c < k; ++c) f.hill[c] = f.xi[c];
-        f.hill[k] = 0.0;
-        f.hill[k + 1] = 0.0;
+        if (lane == 0) {
+          f.hill[k] = 0.0;
+          f.hill[k + 1] = 0.0;
+        }
         if (S.mode == MODE_STEP) {
-          if (oob) {  // metad.py:293-303
-            for (int c = 0; c < k; ++c)
-              f.F[c] = m.has_restraints
-                           ? restraint_force(m.r_lower[c], m.r_upper[c], m.r_kl[c], m.r_ku[c], f.xi[c])
-                           : 0.0;
-          } else {
-            for (int c = 0; c < k; ++c) f.F[c] = M.st.gg[flat * k + c];
-            f.energy = M.st.gp ? M.st.gp[flat] : 0.0;
-          }
-          publish_force(M, f, ncalls);
+          metad_grid_force(M, f, lane);
+          finish_force(M, sh, lane, cta0);
         }
       }
     } break;
     default: break;
   }
+  __syncwarp();
 }
 
-// copy the finalizer results to global (by the finalizing CTA) / back to shared (by everyone)
+// RMSD value after pass B (one lane per CV).
+__device__ __forceinline__ void finalize_cv_B(const Model& M, StepShared& sh, int c) {
+  Fin& f = sh.fin;
+  const CvDev& cv = M.cv[c];
+  if (cv.kind != PSB_CV_RMSD) return;
+  const double inv_n = M.grp[cv.g0].inv_n;
+  const double xi = sqrt(sh.tot[cv.g0][0] * inv_n);  // orientation.py:94
+  f.xi[cv.comp0] = xi;
+  f.cvx[c][15] = inv_n / xi;  // 1 / (n rmsd)
+}
+
+// the CV stage travels from psb_walker_begin to psb_walker_finish through global memory
 __device__ __forceinline__ void fin_store(const Model& M, const StepShared& sh) {
   const double* src = reinterpret_cast<const double*>(&sh.fin);
   double* dst = reinterpret_cast<double*>(M.fin);
@@ -490,41 +543,83 @@ __device__ __forceinline__ void fin_load(const Model& M, StepShared& sh) {
   __syncthreads();
 }
 
+// ---- per-term arithmetic ------------------------------------------------------------------------
+// pass A contribution of one atom of a group of CV `cv` (position r, unwrapped, fp64; momentum p
+// only when the ABF fast path sums momenta per group)
+__device__ __forceinline__ void accumulate_term(const CvDev& cv, bool with_p, double inv_n, uint32_t t,
+                                                V3 r, V3 p, double* acc) {
+  if (cv.kind == PSB_CV_ROG) {
+    acc[0] += r.x * r.x + r.y * r.y + r.z * r.z;
+  } else if (cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
+    const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : inv_n;
+    const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
+    const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    acc[0] += w * r.x; acc[1] += w * r.y; acc[2] += w * r.z;
+    acc[3] += r.x; acc[4] += r.y; acc[5] += r.z;
+    acc[6] += r.x * q0; acc[7] += r.x * q1; acc[8] += r.x * q2;
+    acc[9] += r.y * q0; acc[10] += r.y * q1; acc[11] += r.y * q2;
+    acc[12] += r.z * q0; acc[13] += r.z * q1; acc[14] += r.z * q2;
+  } else if (is_point_kind(cv.kind)) {
+    acc[0] += r.x; acc[1] += r.y; acc[2] += r.z;
+    if (with_p) {
+      acc[3] += p.x; acc[4] += p.y; acc[5] += p.z;
+    }
+  }
+}
+
+// pass B contribution: |P_i U - Q_i|^2 (orientation.py:76-95)
+__device__ __forceinline__ double rmsd_residual(const CvDev& cv, const double* x, uint32_t t, V3 r) {
+  const double P[3] = {r.x - x[9], r.y - x[10], r.z - x[11]};
+  const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
+  double s = 0.0;
+#pragma unroll
+  for (int bb = 0; bb < 3; ++bb) {
+    const double e = P[0] * x[0 + bb] + P[1] * x[3 + bb] + P[2] * x[6 + bb] - __ldg(q + bb);
+    s += e * e;
+  }
+  return s;
+}
+
+// gradient of a non-point CV with respect to the atom of term t (unwrapped position r)
+__device__ __forceinline__ V3 nonpoint_gradient(const Fin& f, const CvDev& cv, int c, double inv_n,
+                                                uint32_t t, V3 r) {
+  if (cv.kind == PSB_CV_ROG) return f.cvx[c][0] * r;
+  if (cv.kind == PSB_CV_RMSD) {
+    const double* x = f.cvx[c];
+    const double P[3] = {r.x - x[9], r.y - x[10], r.z - x[11]};
+    const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
+    const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : inv_n;
+    double D[3];
+    for (int a = 0; a < 3; ++a)
+      D[a] = P[a] - (q0 * x[a * 3 + 0] + q1 * x[a * 3 + 1] + q2 * x[a * 3 + 2]) - w * x[12 + a];
+    return v3(x[15] * D[0], x[15] * D[1], x[15] * D[2]);
+  }
+  // coordination: the pair kernel left d xi / d r in the gradient workspace
+  const double* gr = cv.grad + 3 * (size_t)(t - cv.t0);
+  return v3(__ldcg(gr), __ldcg(gr + 1), __ldcg(gr + 2));
+}
+
 // per-term gradient of the term's CV components w.r.t. the atom; returns ncomp
 template <class A>
 __device__ __forceinline__ int term_gradient(const Model& M, const Snap& S, const Fin& f, uint32_t t,
                                              int g, uint32_t slot, V3* gv) {
   const GroupDev& G = M.grp[g];
   const CvDev& cv = M.cv[G.cv];
-  switch (cv.kind) {
-    case PSB_CV_ROG: {
-      gv[0] = f.cvx[G.cv][0] * A::position(S, slot);
-      return 1;
-    }
-    case PSB_CV_RMSD: {
-      const double* x = f.cvx[G.cv];
-      const V3 r = A::position(S, slot);
-      const double P[3] = {r.x - x[9], r.y - x[10], r.z - x[11]};
-      const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
-      const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-      const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : G.inv_n;
-      double D[3];
-      for (int a = 0; a < 3; ++a)
-        D[a] = P[a] - (q0 * x[a * 3 + 0] + q1 * x[a * 3 + 1] + q2 * x[a * 3 + 2]) - w * x[12 + a];
-      gv[0] = v3(x[15] * D[0], x[15] * D[1], x[15] * D[2]);
-      return 1;
-    }
-    case PSB_CV_COORDINATION: {
-      const double* gr = cv.grad + 3 * (size_t)(t - cv.t0);
-      gv[0] = v3(__ldcg(gr), __ldcg(gr + 1), __ldcg(gr + 2));
-      return 1;
-    }
-    default: {  // point CVs
-      for (int j = 0; j < cv.ncomp; ++j)
-        gv[j] = v3(f.gpt[g][j][0] * G.inv_n, f.gpt[g][j][1] * G.inv_n, f.gpt[g][j][2] * G.inv_n);
-      return cv.ncomp;
-    }
+  if (is_point_kind(cv.kind)) {
+    for (int j = 0; j < cv.ncomp; ++j)
+      gv[j] = v3(f.gpt[g][j][0] * G.inv_n, f.gpt[g][j][1] * G.inv_n, f.gpt[g][j][2] * G.inv_n);
+    return cv.ncomp;
   }
+  V3 r = v3(0, 0, 0);
+  if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
+  gv[0] = nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r);
+  return 1;
+}
+
+// particle tag of term t: groups given as ascending ranges need no index load at all
+__device__ __forceinline__ uint32_t term_tag_of(const Model& M, const GroupDev& G, uint32_t t) {
+  return G.contig ? G.tag0 + (t - G.t0) : __ldg(M.term_tag + t);
 }
 
 template <class A>
@@ -535,21 +630,50 @@ __device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
 // ---- the kernel -------------------------------------------------------------------------------
 template <int LAYOUT, typename Real>
 __global__ void __launch_bounds__(BLOCK, 2)
-step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
+step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S) {
   using A = Access<LAYOUT, Real>;
+  using FV = typename A::FV;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ StepShared sh;
+  __shared__ __align__(16) Model sM;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // The kernel parameters live in a constant bank that is cold at every launch; the finalizers
+  // walk the model tables in one warp, where every constant-cache miss would be serialised.  One
+  // cooperative copy into shared memory takes a single miss latency for the whole CTA instead.
+  {
+    static_assert(sizeof(Model) % 8 == 0, "Model is copied in 8-byte words");
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&Mparam);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sM);
+    for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = src[i];
+  }
+  __syncthreads();
+  const Model& M = sM;
+
   const int nb = gridDim.x, b = blockIdx.x;
+  const bool cta0 = (b == 0);
   const int k = M.k;
   const MethodDev& m = M.m;
-  const uint32_t chunk = (M.T + nb - 1) / nb;
-  const uint32_t c0 = min(M.T, (uint32_t)b * chunk), c1 = min(M.T, c0 + chunk);
   const bool metad_direct = (m.kind == PSB_METHOD_METAD && m.grid_kind == PSB_GRID_NONE);
+  const bool grid_metad = (m.kind == PSB_METHOD_METAD && m.grid_kind != PSB_GRID_NONE);
   const bool skip_cv = (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
+  const bool momenta_sums = S.need_momenta && M.abf_fast;
+  const bool will_scatter = (m.kind != PSB_METHOD_UNBIASED) &&
+                            (S.mode == MODE_STEP || S.mode == MODE_WALKER_FINISH);
 
   PSB_STAMP(0);
+  // ---- prologue: method-state scalars as they are when the step begins --------------------------
+  if (tid == 0) {
+    sh.pre.ncalls = __ldcg(M.st.ncalls);
+    sh.pre.idx = M.st.idx ? __ldcg(M.st.idx) : 0;
+  }
+  if (m.kind == PSB_METHOD_ABF && tid >= 32 && tid < 32 + 3 * MAXK) {
+    const int j = tid - 32, c = j & (MAXK - 1), which = j / MAXK;
+    const double* src = which == 0 ? M.st.Wp : (which == 1 ? M.st.Wp_ : M.st.force);
+    double* dst = which == 0 ? sh.pre.Wp : (which == 1 ? sh.pre.Wp_ : sh.pre.force);
+    dst[c] = __ldcg(src + c);
+  }
+
   // ---- hill staging: kick off the first TMA bulk copies before touching any atom ------------
   long long nh = 0, h0 = 0, h1 = 0;
   const int HC = M.hill_chunk;
@@ -587,114 +711,158 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
     }
   }
 
+  // ---- this CTA's atom segment (gridDim.x > 1: exactly one group per CTA) ----------------------
+  int seg_g = -1;
+  uint32_t lo = 0, hi = 0;
+  if (nb > 1 && !skip_cv) {
+    for (int g = 0; g < M.ngroups; ++g)
+      if (b >= M.cta_first[g] && b < M.cta_first[g + 1]) seg_g = g;
+    if (seg_g >= 0) {
+      const GroupDev& G = M.grp[seg_g];
+      const uint32_t nc = (uint32_t)(M.cta_first[seg_g + 1] - M.cta_first[seg_g]);
+      const uint32_t per = (G.t1 - G.t0 + nc - 1) / nc;
+      lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_first[seg_g]) * per);
+      hi = min(G.t1, lo + per);
+    }
+  }
+  const bool cached = (seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
+  uint32_t cslot[CT];
+  V3 cr[CT], cp[CT];
+  FV cfv[CT];
+
   // ---- pass A ---------------------------------------------------------------------------------
   if (!skip_cv) {
-    for (int g = 0; g < M.ngroups; ++g) {
-      const uint32_t lo = max(c0, M.grp[g].t0), hi = min(c1, M.grp[g].t1);
-      if (lo >= hi) continue;
-      const CvDev& cv = M.cv[M.grp[g].cv];
-      const int na = nacc_for(M, S, g, 0);
-      if (na == 0) continue;
-      double acc[NACC];
-#pragma unroll
-      for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-      if (is_point_kind(cv.kind)) {
+    if (nb > 1) {
+      if (seg_g >= 0) {
+        const GroupDev& G = M.grp[seg_g];
+        const CvDev& cv = M.cv[G.cv];
+        const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
         const bool with_p = (na == 6);
+        double acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+        if (cached) {
+#pragma unroll
+          for (int i = 0; i < CT; ++i) {
+            const uint32_t t = lo + tid + i * BLOCK;
+            cslot[i] = 0;
+            if (t < hi) {
+              cslot[i] = A::slot(S, M, term_tag_of(M, G, t));
+              if (M.need_term_slot) M.term_slot[t] = cslot[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < CT; ++i) {
+            const uint32_t t = lo + tid + i * BLOCK;
+            cp[i] = v3(0, 0, 0);
+            if (t < hi) {
+              cr[i] = A::position(S, cslot[i]);
+              if (with_p) cp[i] = A::momentum(S, cslot[i]);
+              if (will_scatter) cfv[i] = A::load_force(S, cslot[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < CT; ++i) {
+            const uint32_t t = lo + tid + i * BLOCK;
+            if (t < hi) accumulate_term(cv, with_p, G.inv_n, t, cr[i], cp[i], acc);
+          }
+        } else {
 #pragma unroll 4
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-          const uint32_t slot = A::slot(S, M, __ldg(M.term_tag + t));
-          M.term_slot[t] = slot;
-          const V3 r = A::position(S, slot);
-          acc[0] += r.x; acc[1] += r.y; acc[2] += r.z;
-          if (with_p) {
-            const V3 p = A::momentum(S, slot);
-            acc[3] += p.x; acc[4] += p.y; acc[5] += p.z;
+          for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
+            const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
+            M.term_slot[t] = slot;
+            const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
+            accumulate_term(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
           }
         }
-      } else if (cv.kind == PSB_CV_ROG) {
-#pragma unroll 4
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-          const uint32_t slot = A::slot(S, M, __ldg(M.term_tag + t));
-          M.term_slot[t] = slot;
-          const V3 r = A::position(S, slot);
-          acc[0] += r.x * r.x + r.y * r.y + r.z * r.z;
-        }
-      } else {  // RMSD: weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
+        if (na > 0) block_reduce_store(sh, acc, na, M.partials + (size_t)(seg_g * NACC) * nb + b, nb, true);
+      }
+    } else {
+      for (int g = 0; g < M.ngroups; ++g) {
+        const GroupDev& G = M.grp[g];
+        const CvDev& cv = M.cv[G.cv];
+        const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
+        const bool with_p = (na == 6);
+        double acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
 #pragma unroll 2
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-          const uint32_t slot = A::slot(S, M, __ldg(M.term_tag + t));
+        for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) {
+          const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
           M.term_slot[t] = slot;
-          const V3 r = A::position(S, slot);
-          const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : M.grp[g].inv_n;
-          const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
-          const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-          acc[0] += w * r.x; acc[1] += w * r.y; acc[2] += w * r.z;
-          acc[3] += r.x; acc[4] += r.y; acc[5] += r.z;
-          acc[6] += r.x * q0; acc[7] += r.x * q1; acc[8] += r.x * q2;
-          acc[9] += r.y * q0; acc[10] += r.y * q1; acc[11] += r.y * q2;
-          acc[12] += r.z * q0; acc[13] += r.z * q1; acc[14] += r.z * q2;
+          const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
+          accumulate_term(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
+        }
+        if (na == 0) continue;
+        if (G.t1 - G.t0 == 1) {  // a bare index: no reduction needed
+          if (tid == 0)
+            for (int a = 0; a < na; ++a) sh.tot[g][a] = acc[a];
+        } else {
+          block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
         }
       }
-      if (nb == 1) block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
-      else block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
     }
 
     PSB_STAMP(1);
-    grid_barrier(M, sh, 0, [&] {
-      PSB_STAMP(8);
-      reduce_partials(M, S, sh, 0, 0);
-      PSB_STAMP(9);
-      if (tid == 0) {
-        finalize_cvs_A(M, sh);
-        PSB_STAMP(10);
-        if (!M.any_rmsd) post_cv(M, S, sh);
-        PSB_STAMP(11);
-      }
-      __syncthreads();
-      fin_store(M, sh);
-      PSB_STAMP(12);
-    });
+    grid_sync(M, BAR_A);
     PSB_STAMP(2);
+    PSB_CLK(8);
+    reduce_rows(M, sh, 0, 0);
+    PSB_CLK(9);
+    if (warp == 0) {
+      if (M.any_coord) reduce_coordination(M, sh, lane);
+      if (lane < M.ncv) finalize_cv_A(M, sh, lane);
+      PSB_CLK(10);
+      if (!M.any_rmsd) post_cv(M, S, sh, lane, cta0);
+      PSB_CLK(15);
+    }
+    __syncthreads();
+    PSB_STAMP(3);
 
     // ---- pass B: RMSD residual with the optimal rotation ------------------------------------
     if (M.any_rmsd) {
-      fin_load(M, sh);
-      for (int g = 0; g < M.ngroups; ++g) {
-        const CvDev& cv = M.cv[M.grp[g].cv];
-        if (cv.kind != PSB_CV_RMSD) continue;
-        const uint32_t lo = max(c0, M.grp[g].t0), hi = min(c1, M.grp[g].t1);
-        if (lo >= hi) continue;
-        const double* x = sh.fin.cvx[M.grp[g].cv];
-        double acc[1] = {0.0};
-#pragma unroll 2
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-          const V3 r = A::position(S, __ldcg(M.term_slot + t));
-          const double P[3] = {r.x - x[9], r.y - x[10], r.z - x[11]};
-          const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
-          double s = 0.0;
+      if (nb > 1) {
+        if (seg_g >= 0 && M.cv[M.grp[seg_g].cv].kind == PSB_CV_RMSD) {
+          const CvDev& cv = M.cv[M.grp[seg_g].cv];
+          const double* x = sh.fin.cvx[M.grp[seg_g].cv];
+          double acc[1] = {0.0};
+          if (cached) {
 #pragma unroll
-          for (int bb = 0; bb < 3; ++bb) {
-            const double e = P[0] * x[0 + bb] + P[1] * x[3 + bb] + P[2] * x[6 + bb] - __ldg(q + bb);
-            s += e * e;
+            for (int i = 0; i < CT; ++i) {
+              const uint32_t t = lo + tid + i * BLOCK;
+              if (t < hi) acc[0] += rmsd_residual(cv, x, t, cr[i]);
+            }
+          } else {
+#pragma unroll 2
+            for (uint32_t t = lo + tid; t < hi; t += BLOCK)
+              acc[0] += rmsd_residual(cv, x, t, A::position(S, __ldcg(M.term_slot + t)));
           }
-          acc[0] += s;
+          block_reduce_store(sh, acc, 1, M.partials + (size_t)(seg_g * NACC) * nb + b, nb, true);
         }
-        if (nb == 1) block_reduce_store(sh, acc, 1, &sh.tot[g][0], 1, false);
-        else block_reduce_store(sh, acc, 1, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+      } else {
+        for (int g = 0; g < M.ngroups; ++g) {
+          const GroupDev& G = M.grp[g];
+          const CvDev& cv = M.cv[G.cv];
+          if (cv.kind != PSB_CV_RMSD) continue;
+          const double* x = sh.fin.cvx[G.cv];
+          double acc[1] = {0.0};
+#pragma unroll 2
+          for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK)
+            acc[0] += rmsd_residual(cv, x, t, A::position(S, __ldcg(M.term_slot + t)));
+          block_reduce_store(sh, acc, 1, &sh.tot[g][0], 1, false);
+        }
       }
-      grid_barrier(M, sh, 1, [&] {
-        if (nb > 1) fin_load(M, sh);  // the finalizing CTA of barrier 0 may have been another one
-        reduce_partials(M, S, sh, 1, 0);
-        if (tid == 0) {
-          finalize_cvs_B(M, sh);
-          post_cv(M, S, sh);
-        }
-        __syncthreads();
-        fin_store(M, sh);
-      });
+      grid_sync(M, BAR_B);
+      reduce_rows(M, sh, 1, 0);
+      if (warp == 0) {
+        if (lane < M.ncv) finalize_cv_B(M, sh, lane);
+        post_cv(M, S, sh, lane, cta0);
+      }
+      __syncthreads();
     }
+  } else {
+    fin_load(M, sh);
   }
-  fin_load(M, sh);
   if (S.mode == MODE_EVAL) return;
 
   // ---- pass C: J J^T and J p over unique atoms (ABF with position-dependent Jacobians) -----------
@@ -735,25 +903,22 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
     }
     if (nb == 1) block_reduce_store(sh, acc, 14, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 14, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
-    grid_barrier(M, sh, 2, [&] {
-      reduce_partials(M, S, sh, 2, 14);
-      if (tid == 0) {
-        double JJt[16], Jp[MAXK];
+    grid_sync(M, BAR_C);
+    reduce_rows(M, sh, 2, 14);
+    if (warp == 0) {
+      if (lane == 0) {
         int o = 0;
         for (int a = 0; a < MAXK; ++a)
           for (int c = a; c < MAXK; ++c) {
-            JJt[a * 4 + c] = sh.tot[VGROUP][o];
-            JJt[c * 4 + a] = sh.tot[VGROUP][o];
+            sh.fin.JJt[a * 4 + c] = sh.tot[VGROUP][o];
+            sh.fin.JJt[c * 4 + a] = sh.tot[VGROUP][o];
             ++o;
           }
-        for (int a = 0; a < MAXK; ++a) Jp[a] = sh.tot[VGROUP][10 + a];
-        abf_update(M, S, sh.fin, JJt, Jp);
-        publish_force(M, sh.fin, *M.st.ncalls + 1);
+        for (int a = 0; a < MAXK; ++a) sh.fin.Jp[a] = sh.tot[VGROUP][10 + a];
       }
-      __syncthreads();
-      fin_store(M, sh);
-    });
-    fin_load(M, sh);
+      abf_finish(M, S, sh, lane, cta0);
+    }
+    __syncthreads();
   }
 
   // ---- pass H: direct hill sum over the TMA-staged hills ---------------------------------------
@@ -788,14 +953,18 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
     }
     if (nb == 1) block_reduce_store(sh, acc, 1 + k, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 1 + k, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
-    grid_barrier(M, sh, 3, [&] {
-      reduce_partials(M, S, sh, 3, 1 + k);
-      if (tid == 0) {
-        Fin& f = sh.fin;
-        const double V = sh.tot[VGROUP][0];
-        for (int c = 0; c < k; ++c) f.F[c] = sh.tot[VGROUP][1 + c];
+    grid_sync(M, BAR_H);
+    reduce_rows(M, sh, 3, 1 + k);
+    if (warp == 0) {
+      Fin& f = sh.fin;
+      const double V = sh.tot[VGROUP][0];
+      if (lane < k) {
+        f.F[lane] = sh.tot[VGROUP][1 + lane];
+        f.hill[lane] = f.xi[lane];
+      }
+      __syncwarp();
+      if (lane == 0) {
         f.energy = V;
-        for (int c = 0; c < k; ++c) f.hill[c] = f.xi[c];
         f.hill[k] = 0.0;
         f.hill[k + 1] = 0.0;
         if (f.deposit) {  // metad.py:219-229, 262-271 (V is the potential BEFORE this hill)
@@ -803,35 +972,39 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
           f.hill[k] = h;
           f.hill[k + 1] = 1.0;
           if (S.mode == MODE_STEP) {
-            const long long idx = *M.st.idx;
-            if (idx < m.ngaussians) {
-              M.st.heights[idx] = h;
-              for (int c = 0; c < k; ++c) M.st.centers[idx * k + c] = f.xi[c];
+            if (cta0) {
+              const long long idx = sh.pre.idx;
+              if (idx < m.ngaussians) {
+                M.st.heights[idx] = h;
+                for (int c = 0; c < k; ++c) M.st.centers[idx * k + c] = f.xi[c];
+              }
+              *M.st.idx = idx + 1;
             }
-            *M.st.idx = idx + 1;
             // the new hill is centred on xi: zero gradient, energy grows by h
             f.energy = V + h;
           }
         }
-        if (S.mode == MODE_STEP) publish_force(M, f, *M.st.ncalls + 1);
       }
-      __syncthreads();
-      fin_store(M, sh);
-    });
-    fin_load(M, sh);
+      if (S.mode == MODE_STEP) finish_force(M, sh, lane, cta0);
+    }
+    __syncthreads();
   }
 
   if (S.mode == MODE_WALKER_BEGIN) {
-    if (b == 0 && tid < k + 2) S.record_out[tid] = sh.fin.hill[tid];
+    if (cta0) {
+      if (tid < k + 2) S.record_out[tid] = sh.fin.hill[tid];
+      fin_store(M, sh);
+    }
     return;
   }
 
   // ---- pass D: add newly deposited Gaussians to the grids (metad.py:251-256) ---------------------
-  const bool grid_metad = (m.kind == PSB_METHOD_METAD && m.grid_kind != PSB_GRID_NONE);
   if ((grid_metad && S.mode == MODE_STEP && sh.fin.deposit) || S.mode == MODE_WALKER_FINISH) {
     const int nrec = (S.mode == MODE_WALKER_FINISH) ? S.nwalkers : 1;
     const int rs = k + 2;
     if (grid_metad) {
+      // every CTA has read grid_potential[I] (well-tempered height) before any bin is rewritten
+      if (S.mode == MODE_STEP && m.well_tempered) grid_sync(M, BAR_PRE_D);
       for (long long p = (long long)b * BLOCK + tid; p < m.grid_points; p += (long long)nb * BLOCK) {
         double x[MAXK];
         long long rem = p;
@@ -849,108 +1022,155 @@ step_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S) {
         if (M.st.gp) M.st.gp[p] += val;
         for (int c = 0; c < k; ++c) M.st.gg[p * k + c] += dV[c];
       }
+      grid_sync(M, BAR_D);
     }
-    grid_barrier(M, sh, 4, [&] {
-      if (tid == 0) {
-        Fin& f = sh.fin;
-        long long ncalls = *M.st.ncalls + 1;
-        if (S.mode == MODE_WALKER_FINISH) {
-          // append the walkers' hills in rank order (identical on every rank)
-          long long idx = *M.st.idx;
-          for (int r = 0; r < nrec; ++r) {
-            const double* rec = S.records + (size_t)r * rs;
-            if (rec[k + 1] == 0.0) continue;
-            if (idx < m.ngaussians) {
-              M.st.heights[idx] = rec[k];
-              for (int c = 0; c < k; ++c) M.st.centers[idx * k + c] = rec[c];
-            }
-            ++idx;
-            if (!grid_metad) {  // the other walkers' new hills do push on this walker
-              double dV[MAXK] = {0, 0, 0, 0};
-              f.energy += hill_eval(m, k, f.xi, rec, rec[k], dV);
-              for (int c = 0; c < k; ++c) f.F[c] += dV[c];
-            }
+    if (warp == 0) {
+      Fin& f = sh.fin;
+      if (S.mode == MODE_WALKER_FINISH && lane == 0) {
+        // append the walkers' hills in rank order (identical on every rank)
+        long long idx = sh.pre.idx;
+        for (int r = 0; r < nrec; ++r) {
+          const double* rec = S.records + (size_t)r * rs;
+          if (rec[k + 1] == 0.0) continue;
+          if (cta0 && idx < m.ngaussians) {
+            M.st.heights[idx] = rec[k];
+            for (int c = 0; c < k; ++c) M.st.centers[idx * k + c] = rec[c];
           }
-          *M.st.idx = idx;
-        }
-        if (grid_metad) {
-          if (f.oob) {
-            for (int c = 0; c < k; ++c)
-              f.F[c] = m.has_restraints
-                           ? restraint_force(m.r_lower[c], m.r_upper[c], m.r_kl[c], m.r_ku[c], f.xi[c])
-                           : 0.0;
-          } else {
-            const long long flat = grid_flat_clamped(m, f.I);
-            for (int c = 0; c < k; ++c) f.F[c] = M.st.gg[flat * k + c];
-            f.energy = M.st.gp ? M.st.gp[flat] : 0.0;
+          ++idx;
+          if (!grid_metad) {  // the other walkers' new hills do push on this walker
+            double dV[MAXK] = {0, 0, 0, 0};
+            f.energy += hill_eval(m, k, f.xi, rec, rec[k], dV);
+            for (int c = 0; c < k; ++c) f.F[c] += dV[c];
           }
         }
-        publish_force(M, f, ncalls);
+        if (cta0) *M.st.idx = idx;
       }
-      __syncthreads();
-      fin_store(M, sh);
-    });
-    fin_load(M, sh);
+      __syncwarp();
+      if (grid_metad) metad_grid_force(M, f, lane);
+      finish_force(M, sh, lane, cta0);
+    }
+    __syncthreads();
   }
 
-  if (m.kind == PSB_METHOD_UNBIASED) return;
-
-  PSB_STAMP(3);
-  // ---- pass S: in-place force scatter ------------------------------------------------------------
-  const Fin& f = sh.fin;
-  const bool dense = (M.bias_dense != nullptr);
-  if (M.all_unique && !dense) {
-    for (int g = 0; g < M.ngroups; ++g) {
-      const uint32_t lo = max(c0, M.grp[g].t0), hi = min(c1, M.grp[g].t1);
-      if (lo >= hi) continue;
-      const CvDev& cv = M.cv[M.grp[g].cv];
-      if (is_point_kind(cv.kind)) {
-        const V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
-#pragma unroll 4
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fo);
-      } else {
-        const double Fc = -f.F[cv.comp0];
-#pragma unroll 2
-        for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-          const uint32_t slot = __ldcg(M.term_slot + t);
-          V3 gv[3];
-          term_gradient<A>(M, S, f, t, g, slot, gv);
-          add_force<A>(S, slot, Fc * gv[0]);
-        }
-      }
-    }
-  } else {
-    const uint32_t uchunk = (M.Su + nb - 1) / nb;
-    const uint32_t u0 = min(M.Su, (uint32_t)b * uchunk), u1 = min(M.Su, u0 + uchunk);
-    const size_t N3 = 3 * (size_t)M.natoms;
-    for (uint32_t u = u0 + tid; u < u1; u += BLOCK) {
-      const uint32_t e0 = M.all_unique ? u : __ldg(M.uniq_ptr + u);
-      const uint32_t e1 = M.all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
-      V3 fo = v3(0, 0, 0);
-      uint32_t slot = 0;
-      for (uint32_t e = e0; e < e1; ++e) {
-        const uint32_t t = M.all_unique ? e : __ldg(M.uniq_term + e);
-        const int g = __ldg(M.term_group + t);
-        slot = __ldcg(M.term_slot + t);
-        V3 gv[3];
-        const int nc = term_gradient<A>(M, S, f, t, g, slot, gv);
-        const int comp0 = M.cv[M.grp[g].cv].comp0;
-        for (int j = 0; j < nc; ++j) {
-          fo = fo + (-f.F[comp0 + j]) * gv[j];
-          if (dense && M.jac_dense) {
-            double* J = M.jac_dense + (size_t)(comp0 + j) * N3 + 3 * (size_t)slot;
-            atomicAdd(J + 0, gv[j].x); atomicAdd(J + 1, gv[j].y); atomicAdd(J + 2, gv[j].z);
-          }
-        }
-      }
-      add_force<A>(S, slot, fo);
-      if (dense) {
-        double* B = M.bias_dense + 3 * (size_t)slot;
-        B[0] = fo.x; B[1] = fo.y; B[2] = fo.z;
-      }
-    }
-  }
   PSB_STAMP(4);
+  // ---- pass S: in-place force scatter ------------------------------------------------------------
+  if (will_scatter) {
+    const Fin& f = sh.fin;
+    const bool dense = (M.bias_dense != nullptr);
+    if (M.all_unique && !dense) {
+      if (nb > 1) {
+        if (seg_g >= 0) {
+          const GroupDev& G = M.grp[seg_g];
+          const CvDev& cv = M.cv[G.cv];
+          const bool point = is_point_kind(cv.kind);
+          const V3 fgv = v3(f.fg[seg_g][0], f.fg[seg_g][1], f.fg[seg_g][2]);
+          const double Fc = -f.F[cv.comp0];
+          if (cached) {
+#pragma unroll
+            for (int i = 0; i < CT; ++i) {
+              const uint32_t t = lo + tid + i * BLOCK;
+              if (t < hi) {
+                const V3 fo = point ? fgv : Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, cr[i]);
+                A::store_force(S, cslot[i], cfv[i], fo);
+              }
+            }
+          } else if (point) {
+#pragma unroll 4
+            for (uint32_t t = lo + tid; t < hi; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fgv);
+          } else {
+#pragma unroll 2
+            for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
+              const uint32_t slot = __ldcg(M.term_slot + t);
+              V3 r = v3(0, 0, 0);
+              if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
+              add_force<A>(S, slot, Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r));
+            }
+          }
+        } else if (skip_cv) {
+          // walker finish: no pass A ran in this launch, spread all terms over the CTAs
+          const uint32_t chunk = (M.T + nb - 1) / nb;
+          const uint32_t c0 = min(M.T, (uint32_t)b * chunk), c1 = min(M.T, c0 + chunk);
+          for (uint32_t t = c0 + tid; t < c1; t += BLOCK) {
+            const int g = __ldg(M.term_group + t);
+            const uint32_t slot = __ldcg(M.term_slot + t);
+            V3 gv[3];
+            const int nc = term_gradient<A>(M, S, f, t, g, slot, gv);
+            const int comp0 = M.cv[M.grp[g].cv].comp0;
+            V3 fo = v3(0, 0, 0);
+            for (int j = 0; j < nc; ++j) fo = fo + (-f.F[comp0 + j]) * gv[j];
+            add_force<A>(S, slot, fo);
+          }
+        }
+      } else {
+        for (int g = 0; g < M.ngroups; ++g) {
+          const GroupDev& G = M.grp[g];
+          const CvDev& cv = M.cv[G.cv];
+          if (is_point_kind(cv.kind)) {
+            const V3 fgv = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
+#pragma unroll 2
+            for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fgv);
+          } else {
+            const double Fc = -f.F[cv.comp0];
+#pragma unroll 2
+            for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) {
+              const uint32_t slot = __ldcg(M.term_slot + t);
+              V3 r = v3(0, 0, 0);
+              if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
+              add_force<A>(S, slot, Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r));
+            }
+          }
+        }
+      }
+    } else {
+      const uint32_t uchunk = (M.Su + nb - 1) / nb;
+      const uint32_t u0 = min(M.Su, (uint32_t)b * uchunk), u1 = min(M.Su, u0 + uchunk);
+      const size_t N3 = 3 * (size_t)M.natoms;
+      for (uint32_t u = u0 + tid; u < u1; u += BLOCK) {
+        const uint32_t e0 = M.all_unique ? u : __ldg(M.uniq_ptr + u);
+        const uint32_t e1 = M.all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
+        V3 fo = v3(0, 0, 0);
+        uint32_t slot = 0;
+        for (uint32_t e = e0; e < e1; ++e) {
+          const uint32_t t = M.all_unique ? e : __ldg(M.uniq_term + e);
+          const int g = __ldg(M.term_group + t);
+          slot = __ldcg(M.term_slot + t);
+          V3 gv[3];
+          const int nc = term_gradient<A>(M, S, f, t, g, slot, gv);
+          const int comp0 = M.cv[M.grp[g].cv].comp0;
+          for (int j = 0; j < nc; ++j) {
+            fo = fo + (-f.F[comp0 + j]) * gv[j];
+            if (dense && M.jac_dense) {
+              double* J = M.jac_dense + (size_t)(comp0 + j) * N3 + 3 * (size_t)slot;
+              atomicAdd(J + 0, gv[j].x); atomicAdd(J + 1, gv[j].y); atomicAdd(J + 2, gv[j].z);
+            }
+          }
+        }
+        add_force<A>(S, slot, fo);
+        if (dense) {
+          double* B = M.bias_dense + 3 * (size_t)slot;
+          B[0] = fo.x; B[1] = fo.y; B[2] = fo.z;
+        }
+      }
+    }
+  }
+  PSB_STAMP(5);
+
+  // every bin of hist / Fsum this CTA needed was read long ago: tell CTA 0 (non-blocking, and after
+  // the scatter so the fence + atomic stay off the critical path)
+  unsigned long long readers_want = 0;
+  const bool abf_commit = (m.kind == PSB_METHOD_ABF && nb > 1 && S.mode == MODE_STEP);
+  if (abf_commit && tid == 0) readers_want = grid_arrive(M, BAR_READERS);
+
+  // ---- ABF commit: CTA 0 stores the new count / force sum of bin I (abf.py:216-218) -------------
+  if (m.kind == PSB_METHOD_ABF && cta0 && S.mode == MODE_STEP && tid == 0) {
+    if (abf_commit) grid_wait(M, BAR_READERS, readers_want);
+    const Fin& f = sh.fin;
+    if (f.in_range) {
+      M.st.hist[f.flat] = f.hist_new;
+      for (int c = 0; c < k; ++c) M.st.Fsum[f.flat * k + c] = f.Fsum_new[c];
+    }
+  }
+  PSB_STAMP(6);
 }
 
 }  // namespace psb

@@ -14,6 +14,18 @@ from pysages_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["auto", "grid24"])
+def launch_shape(request, monkeypatch):
+    """Every parity case runs twice: with the library's own launch shape (one CTA for the small
+    test snapshots) and forced onto 24 cooperative CTAs (group-aligned CTAs, grid barrier, per-CTA
+    partials, redundant finalizer, register-cached scatter)."""
+    if request.param == "grid24":
+        monkeypatch.setenv("PSB_GRID_BLOCKS", "24")
+    else:
+        monkeypatch.delenv("PSB_GRID_BLOCKS", raising=False)
+    return request.param
+
 LAYOUTS = [
     ("hoomd", np.float32),
     ("hoomd", np.float64),

@@ -1,0 +1,36 @@
+"""Per-phase timestamps of the fused step kernel (PSB_DEBUG_TIMING=1), for latency work.
+   python tools/timing_probe.py            (on the GPU box)"""
+import os, sys
+os.environ["PSB_DEBUG_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+
+dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
+cases = [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000)]
+for wl, natoms in cases:
+    frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
+    snaps = bench.snapshots_of(frames, L, 0.005)
+    cvs, m = bench.workload_specs(wl, natoms, L)
+    method, native = bench.build_ours(cvs, m, snaps[0])
+    descs = bench.snapdesc_array(native, snaps)
+    ms, _ = bench.time_cycle(native, descs, 200, 20, stream)
+    torch.cuda.synchronize()
+    t = native.view("debug_timing", (-1, 16)).cpu().numpy().astype(np.float64)
+    g = t.shape[0]
+    t0 = t[:, 0].min()
+    rel = lambda x: (x - t0) / 1e3
+    print(f"{wl} N={natoms} grid={g} us/step={ms*1e3/200:.2f}")
+    names = ["start", "passA done", "barrier passed", "finalize done", "scatter start", "scatter end", "kernel end"]
+    for i, nme in enumerate(names):
+        col = rel(t[:, i])
+        print(f"  {nme:15s}: min {col.min():6.2f} median {np.median(col):6.2f} max {col.max():6.2f}")
+    c = t[0, 8:16]
+    cn = ["pre-reduce", "reduce_rows", "finalize_cv", "JJt/Jp", "solve", "grid_bin", "hist gather+F", "finish_force(end post_cv)"]
+    base = c[0]
+    if wl == "abf2d":
+        print("  CTA0 finalize clocks (cycles since pre-reduce):", ", ".join(f"{n}={int(v - base)}" for n, v in zip(cn, c)))
+    else:
+        print("  CTA0 finalize clocks:", f"reduce_rows={int(c[1]-base)} finalize_cv={int(c[2]-base)} post_cv={int(c[7]-base)}")
+    del frames, snaps, native, method
+    torch.cuda.empty_cache()
