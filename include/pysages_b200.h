@@ -222,6 +222,14 @@ psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64
 int64_t psb_launch_count(psb_handle* h);
 psb_status psb_launch_info(psb_handle* h, int32_t* grid_blocks, int32_t* block_threads,
                            int32_t* cooperative, int64_t* algorithmic_bytes_per_step);
+/* Launch-latency floor for the bench report: enqueues `nlaunches` kernels of
+ * `grid_blocks` x 256 threads that do no work (optionally one grid-wide arrive/wait, cooperative
+ * launches only; optionally a parameter block as large as the step kernel's used to be). */
+psb_status psb_launch_floor(int32_t grid_blocks, int32_t cooperative, int32_t big_params, int32_t grid_barrier,
+                            int64_t nlaunches, void* cuda_stream);
+/* Dependent-issue latency (SM cycles per operation) of DFMA, DADD, FFMA, IMAD, LDS, sqrt, 1/x,
+ * rsqrt, floor, fmod, atan2, exp in one warp: the floor of the single-warp finalizer code. */
+psb_status psb_latency_probe(double* out_host16);
 int32_t psb_abi_version(void);
 
 #ifdef __cplusplus

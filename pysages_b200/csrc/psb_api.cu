@@ -49,6 +49,7 @@ struct CoordWork {
 
 struct psb_handle {
   Model model;
+  Model* d_model = nullptr;  // device copy read by the step kernel (uploaded at the end of psb_create)
   psb_layout_desc layout;
   psb_method_desc method;
   std::vector<void*> allocs;
@@ -58,9 +59,12 @@ struct psb_handle {
   int grid = 1;
   size_t dyn_smem = 0;
   int cooperative = 0;
+  int step_method = 0;   // StepMethod code of the kernel instantiation
+  int step_general = 0;  // 1: instantiation with non-point CVs / shared atoms / dense outputs / walkers
   long long launches = 0;
   long long host_ncalls = 0;  // mirror of the device ncalls (deterministic)
   long long algo_bytes = 0;
+  long long* dbg = nullptr;  // PSB_DEBUG_TIMING=1: [2][grid][16] phase timestamps
   int record_doubles = 0;
   // staging for psb_step_host
   psb_snapshot dev_snap{};
@@ -127,6 +131,7 @@ Snap make_snap(const psb_handle* h, const psb_snapshot* s, int mode) {
   S.unwrap = h->layout.unwrap && h->layout.layout != PSB_LAYOUT_OPENMM_CUDA;
   S.need_momenta = h->layout.need_momenta;
   S.mode = mode;
+  S.dbg = h->dbg ? h->dbg + (size_t)(h->launches & 1) * 16 * h->grid : nullptr;
   return S;
 }
 
@@ -180,7 +185,8 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
     if (M.jac_dense)
       CUDA_TRY(cudaMemsetAsync(M.jac_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms * M.k, stream));
   }
-  CUDA_TRY(pick_vtable(h->layout)->launch_step(&h->model, &S, h->grid, h->dyn_smem, stream));
+  CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, h->step_general, h->d_model, &S, h->grid,
+                                               h->dyn_smem, stream));
   ++h->launches;
   return PSB_OK;
 }
@@ -372,6 +378,11 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       i = j;
     }
     uptr.push_back(M.T);
+    for (int g = 0; g < ng; ++g) {
+      M.grp[g].self_coef = (double)M.ov[g][g] * M.grp[g].inv_n * M.grp[g].inv_n;
+      for (int g2 = 0; g2 < ng; ++g2)
+        if (g2 != g && M.ov[g][g2]) M.cross_overlap = 1;
+    }
     M.Su = (uint32_t)uptr.size() - 1;
     M.all_unique = (M.Su == M.T) ? 1 : 0;
     psb_status st;
@@ -478,6 +489,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     }
     if ((st = dev_alloc(h, &M.fin, 1)) != PSB_OK) return bail(st);
     if ((st = dev_alloc(h, &M.bars, NBARS)) != PSB_OK) return bail(st);
+    if ((st = dev_alloc(h, &M.epochs, 16)) != PSB_OK) return bail(st);
     if (layout->layout == PSB_LAYOUT_OPENMM_CUDA &&
         (st = dev_alloc(h, &M.inv_perm, (size_t)layout->natoms)) != PSB_OK)
       return bail(st);
@@ -501,7 +513,14 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
                       method->shared_hills || M.any_coord)
                          ? 1
                          : 0;
-  const int occ = pick_vtable(*layout)->occupancy(h->dyn_smem);
+  switch (method->kind) {
+    case PSB_METHOD_UNBIASED: h->step_method = SM_UNBIASED; break;
+    case PSB_METHOD_HARMONIC: h->step_method = SM_HARMONIC; break;
+    case PSB_METHOD_ABF: h->step_method = SM_ABF; break;
+    default: h->step_method = gridded ? SM_METAD_GRID : SM_METAD_DIRECT; break;
+  }
+  h->step_general = (!M.all_point || !M.all_unique || layout->dense_outputs || method->shared_hills) ? 1 : 0;
+  const int occ = pick_vtable(*layout)->occupancy(h->step_method, h->step_general, h->dyn_smem);
   if (occ < 1)
     return bail(fail(PSB_ERR_CUDA, "step kernel cannot be made resident (%s)", cudaGetErrorString(cudaGetLastError())));
   const long long max_blocks = (long long)std::min(occ, 2) * h->num_sms;
@@ -553,7 +572,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   {
     psb_status st = dev_alloc(h, &M.partials, (size_t)(MAXG + 1) * NACC * h->grid);
     if (st != PSB_OK) return bail(st);
-    if (getenv("PSB_DEBUG_TIMING") && (st = dev_alloc(h, &M.dbg, (size_t)16 * h->grid)) != PSB_OK) return bail(st);
+    if (getenv("PSB_DEBUG_TIMING") && (st = dev_alloc(h, &h->dbg, (size_t)2 * 16 * h->grid)) != PSB_OK) return bail(st);
   }
 
   // ---- algorithmic bytes per step ----------------------------------------------------
@@ -576,7 +595,12 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     if (method->kind == PSB_METHOD_ABF) bytes += 2 * (4 + 8 * k);
     h->algo_bytes = bytes;
   }
-  if (method->kind == PSB_METHOD_UNBIASED) h->algo_bytes -= 0;
+  {
+    psb_status st = dev_alloc(h, &h->d_model, 1, false);
+    if (st != PSB_OK) return bail(st);
+    cudaError_t e = cudaMemcpy(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(fail(PSB_ERR_CUDA, "CUDA error %s uploading the model", cudaGetErrorString(e)));
+  }
   *out = h;
   return PSB_OK;
 }
@@ -664,7 +688,7 @@ psb_status psb_state_info(psb_handle* h, const char* field, int64_t* nbytes, int
   else if (f == "Wp_") { p = s.Wp_; n = 8 * k; }
   else if (f == "bias") { p = M.bias_dense; n = 8 * 3 * M.natoms; }
   else if (f == "jacobian") { p = M.jac_dense; n = 8 * 3 * M.natoms * k; }
-  else if (f == "debug_timing") { p = M.dbg; n = 8 * 16 * (long long)h->grid; code = 1; }
+  else if (f == "debug_timing") { p = h->dbg; n = 2 * 8 * 16 * (long long)h->grid; code = 1; }
   else return fail(PSB_ERR_KEY, "unknown state field '%s'", field);
   if (!p) return fail(PSB_ERR_KEY, "state field '%s' does not exist for this method", field);
   if (nbytes) *nbytes = n;
@@ -772,6 +796,27 @@ psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64
   cudaFree(dx);
   cudaFree(di);
   if (e != cudaSuccess) return fail(PSB_ERR_CUDA, "CUDA error %s in psb_grid_index", cudaGetErrorString(e));
+  return PSB_OK;
+}
+
+psb_status psb_launch_floor(int32_t grid_blocks, int32_t cooperative, int32_t big_params, int32_t grid_barrier,
+                            int64_t nlaunches, void* cuda_stream) {
+  if (grid_blocks < 1 || nlaunches < 0) return fail(PSB_ERR_VALUE, "invalid arguments");
+  if (grid_barrier && !cooperative) return fail(PSB_ERR_VALUE, "a grid barrier needs a cooperative launch");
+  static unsigned long long* counter = nullptr;
+  if (!counter) CUDA_TRY(cudaMalloc(&counter, 8));
+  CUDA_TRY(launch_floor(grid_blocks, cooperative, big_params, grid_barrier, nlaunches, counter, (cudaStream_t)cuda_stream));
+  return PSB_OK;
+}
+
+psb_status psb_latency_probe(double* out_host16) {
+  if (!out_host16) return fail(PSB_ERR_VALUE, "NULL argument");
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 16 * sizeof(double)));
+  cudaError_t e = launch_latency_probe(d, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out_host16, d, 16 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(PSB_ERR_CUDA, "CUDA error %s in psb_latency_probe", cudaGetErrorString(e));
   return PSB_OK;
 }
 

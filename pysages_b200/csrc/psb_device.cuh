@@ -26,6 +26,7 @@ struct GroupDev {
   double inv_n;     // 1 / group size
   uint32_t tag0;    // first tag
   int32_t contig;   // tags are tag0, tag0 + 1, ... (no index load needed)
+  double self_coef; // (atoms of the group, counted with multiplicity^2) / n^2: its share of J J^T
 };
 
 struct CvDev {
@@ -145,11 +146,13 @@ struct Model {
   Fin* fin;
   double* partials;           // ((MAXG+1) * NACC, gridDim) fp64
   BarrierState* bars;         // (NBARS) monotonic arrival counters
+  unsigned long long* epochs; // (NBARS) completed uses of each barrier
+  int32_t cross_overlap;      // some atom belongs to two different groups
+  int32_t pad0;
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr
   long long natoms;
-  long long* dbg;             // optional (PSB_DEBUG_TIMING=1): per-CTA phase timestamps [grid][16]
 };
 
 struct Snap {
@@ -169,6 +172,7 @@ struct Snap {
   int32_t nwalkers;
   const double* records;  // walker finish: gathered hill records
   double* record_out;     // walker begin: this walker's record
+  long long* dbg;         // optional (PSB_DEBUG_TIMING=1): phase timestamps [2][grid][16], by launch parity
 };
 
 enum { MODE_STEP = 0, MODE_EVAL = 1, MODE_WALKER_BEGIN = 2, MODE_WALKER_FINISH = 3 };

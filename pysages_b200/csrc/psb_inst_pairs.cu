@@ -45,6 +45,77 @@ PairLaunchFn pair_launcher(int R, int H) {
   return nullptr;
 }
 
+// Launch-latency floor: kernels that do nothing (optionally one grid-wide arrive/wait), with a small
+// or a Model-sized parameter block, launched plainly or cooperatively.
+struct BigParams { unsigned long long w[360]; };
+__global__ void __launch_bounds__(BLOCK) floor_kernel_small(unsigned long long* counter, int use_barrier,
+                                                             unsigned long long launch_index) {
+  if (use_barrier && threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1ULL);
+    const unsigned long long want = (launch_index + 1ULL) * gridDim.x;
+    while (*((volatile unsigned long long*)counter) < want) {}
+  }
+}
+__global__ void __launch_bounds__(BLOCK) floor_kernel_big(const __grid_constant__ BigParams P, unsigned long long* counter) {
+  if (P.w[threadIdx.x] == 0x123456789ULL) *counter = 1;  // keep the parameter block alive
+}
+
+// Dependent-issue latency of the operations the single-warp finalizers are made of (cycles / op).
+__global__ void latency_probe_kernel(double* out, double seed) {
+  __shared__ double sm[64];
+  if (threadIdx.x < 64) sm[threadIdx.x] = (double)((threadIdx.x * 7 + 3) % 64);
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int N = 256;
+  double x = seed, y = 1.0 + seed * 1e-9;
+  float xf = (float)seed;
+  int xi = (int)seed + 3;
+  long long t0, t1;
+#define PROBE(slot, STMT)                                    \
+  t0 = clock64();                                            \
+  _Pragma("unroll 16") for (int i = 0; i < N; ++i) { STMT; } \
+  t1 = clock64();                                            \
+  if (threadIdx.x == 0) out[slot] = (double)(t1 - t0) / N;
+  PROBE(0, x = fma(x, y, 1e-30))
+  PROBE(1, x = x + y)
+  PROBE(2, xf = fmaf(xf, 1.0000001f, 1e-30f))
+  PROBE(3, xi = xi * 3 + 1)
+  PROBE(4, x = sm[((int)x) & 63])
+  PROBE(5, x = sqrt(x + 2.0))
+  PROBE(6, x = 1.0 / (x + 2.0))
+  PROBE(7, x = rsqrt(x + 2.0))
+  PROBE(8, x = floor(x * 1.5) + 0.25)
+  PROBE(9, x = fmod(x + 37.5, 0.7))
+  PROBE(10, x = atan2(x + 0.3, y))
+  PROBE(11, x = exp(-x * 1e-3))
+#undef PROBE
+  if (threadIdx.x == 0) out[15] = x + (double)xf + (double)xi;
+}
+
+cudaError_t launch_latency_probe(double* out_dev, cudaStream_t stream) {
+  latency_probe_kernel<<<1, 64, 0, stream>>>(out_dev, 1.5);
+  latency_probe_kernel<<<1, 64, 0, stream>>>(out_dev, 1.5);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_floor(int grid, int cooperative, int big_params, int use_barrier, long long n,
+                         unsigned long long* counter, cudaStream_t stream) {
+  BigParams P{};
+  cudaError_t e = cudaMemsetAsync(counter, 0, 8, stream);
+  for (long long i = 0; i < n && e == cudaSuccess; ++i) {
+    unsigned long long li = (unsigned long long)i;
+    int ub = use_barrier;
+    void* args_small[] = {(void*)&counter, (void*)&ub, (void*)&li};
+    void* args_big[] = {(void*)&P, (void*)&counter};
+    const void* fn = big_params ? (const void*)floor_kernel_big : (const void*)floor_kernel_small;
+    void** args = big_params ? args_big : args_small;
+    if (cooperative) e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(BLOCK), args, 0, stream);
+    else e = cudaLaunchKernel(fn, dim3(grid), dim3(BLOCK), args, 0, stream);
+  }
+  return e;
+}
+
 void launch_inverse_permutation(const int* ids, uint32_t* inv, long long n, int blocks, cudaStream_t stream) {
   inverse_permutation_kernel<<<blocks, 256, 0, stream>>>(ids, inv, n);
 }

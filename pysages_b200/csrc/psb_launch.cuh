@@ -3,12 +3,16 @@
 #pragma once
 
 #include "psb_device.cuh"
+#include "psb_step.cuh"
 
 namespace psb {
 
 struct StepVTable {
-  cudaError_t (*launch_step)(const Model* M, const Snap* S, int grid, size_t dyn_smem, cudaStream_t stream);
-  int (*occupancy)(size_t dyn_smem);
+  // `method` is a StepMethod code, `general` selects the instantiation that also handles
+  // non-point CVs, shared atoms, dense outputs and walkers (psb_step.cuh)
+  cudaError_t (*launch_step)(int method, int general, const Model* M, const Snap* S, int grid, size_t dyn_smem,
+                             cudaStream_t stream);
+  int (*occupancy)(int method, int general, size_t dyn_smem);
   void (*launch_gather)(const Model* M, const Snap* S, int cv, double* xa, int na_pad, double* xb,
                         int nb_pad, cudaStream_t stream);
 };
@@ -19,29 +23,35 @@ using PairLaunchFn = void (*)(int grid, cudaStream_t stream, const double* xa, i
 // R in {1, 4}; H = n / 2 in {1, 2, 3, 4, 6}; nullptr when unsupported
 PairLaunchFn pair_launcher(int R, int H);
 
+cudaError_t launch_floor(int grid, int cooperative, int big_params, int use_barrier, long long n,
+                         unsigned long long* counter, cudaStream_t stream);
+cudaError_t launch_latency_probe(double* out_dev, cudaStream_t stream);
 void launch_inverse_permutation(const int* ids, uint32_t* inv, long long n, int blocks, cudaStream_t stream);
 void launch_grid_index(const psb_grid_desc& g, const double* x, long long n, uint32_t* out);
 
 extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64, vt_lammps_f64,
     vt_plain3_f32, vt_plain3_f64;
 
+// kernel entry points of one (layout, dtype): [method][general]
+#define PSB_STEP_ROW(L, R, M) {(const void*)step_kernel<L, R, M, false>, (const void*)step_kernel<L, R, M, true>}
 #define PSB_DEFINE_STEP_VTABLE(NAME, L, R)                                                          \
-  static cudaError_t NAME##_launch(const Model* M, const Snap* S, int grid, size_t smem,            \
-                                   cudaStream_t stream) {                                           \
-    void* args[] = {(void*)M, (void*)S};                                                            \
-    if (grid > 1)                                                                                   \
-      return cudaLaunchCooperativeKernel((const void*)step_kernel<L, R>, dim3(grid), dim3(BLOCK),   \
-                                         args, smem, stream);                                       \
-    return cudaLaunchKernel((const void*)step_kernel<L, R>, dim3(1), dim3(BLOCK), args, smem, stream); \
+  static const void* const NAME##_entry[SM_COUNT][2] = {                                            \
+      PSB_STEP_ROW(L, R, SM_UNBIASED), PSB_STEP_ROW(L, R, SM_HARMONIC), PSB_STEP_ROW(L, R, SM_METAD_DIRECT), \
+      PSB_STEP_ROW(L, R, SM_ABF), PSB_STEP_ROW(L, R, SM_METAD_GRID)};                               \
+  static cudaError_t NAME##_launch(int method, int general, const Model* M, const Snap* S, int grid, \
+                                   size_t smem, cudaStream_t stream) {                              \
+    void* args[] = {(void*)&M, (void*)S}; /* M: device pointer, S: by value */                     \
+    const void* fn = NAME##_entry[method][general ? 1 : 0];                                         \
+    if (grid > 1) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(BLOCK), args, smem, stream); \
+    return cudaLaunchKernel(fn, dim3(1), dim3(BLOCK), args, smem, stream);                          \
   }                                                                                                 \
-  static int NAME##_occupancy(size_t smem) {                                                        \
+  static int NAME##_occupancy(int method, int general, size_t smem) {                               \
     int occ = 0;                                                                                    \
-    if (smem > 0 && cudaFuncSetAttribute(step_kernel<L, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem) != cudaSuccess)                                 \
+    const void* fn = NAME##_entry[method][general ? 1 : 0];                                         \
+    if (smem > 0 &&                                                                                 \
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
       return 0;                                                                                     \
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<L, R>, BLOCK, smem) !=      \
-        cudaSuccess)                                                                                \
-      return 0;                                                                                     \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BLOCK, smem) != cudaSuccess) return 0; \
     return occ;                                                                                     \
   }                                                                                                 \
   static void NAME##_gather(const Model* M, const Snap* S, int cv, double* xa, int na_pad,          \

@@ -119,8 +119,26 @@ PSB_HD double jax_remainder(double x1, double x2) {
   return plus ? t + x2 : t;
 }
 
+// The same value as jax_floor_divide(a, b) for b > 0 and |a / b| < 2^50, without fmod and with
+// one division: floor of the EXACT quotient.  Work on |a| like fmod does: t = floor(fl(|a| / b))
+// is off by at most one, and the remainder |a| - t * b of the correct t is exactly representable,
+// so one fma gives it exactly (for a wrong t the sign / range test below is still decided
+// correctly because rounding is monotonic).  jax's (a - mod) / b differs from the resulting
+// integer by < 2^-51 * |q|, so its final round() returns it unchanged.
+PSB_HD bool fast_floor_divide(double a, double b, double* out) {
+  const double A = fabs(a);
+  double t = floor(A / b);
+  if (!(t < 1125899906842624.0) || !(b > 0.0)) return false;  // also rejects NaN / inf
+  double r = fma(-t, b, A);
+  if (r < 0.0) t -= 1.0;
+  else if (r >= b) t += 1.0;
+  r = fma(-t, b, A);  // exact: the remainder fmod(|a|, b)
+  *out = (a >= 0.0) ? t : ((r != 0.0) ? -t - 1.0 : -t);
+  return true;
+}
+
 // kind: 1 regular, 2 periodic, 3 Chebyshev.  Returns the uint32 index (== shape: out of bounds).
-PSB_HD_COLD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape) {
+PSB_HD_COLD uint32_t grid_index_slow(int kind, double x, double lower, double upper, int32_t shape) {
   const double size = upper - lower;
   const double n = (double)shape;
   double idx;
@@ -139,6 +157,24 @@ PSB_HD_COLD uint32_t grid_index_1d(int kind, double x, double lower, double uppe
     if (isnan(idx)) idx = n;
   }
   return (uint32_t)idx;
+}
+
+// Regular / periodic grids take the division-only path; anything unusual (Chebyshev, huge or
+// non-finite quotients, non-positive bin width) goes through the literal restatement above.
+PSB_HD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape) {
+  if (kind == 1 || kind == 2) {
+    const double h = (upper - lower) / (double)shape;
+    double q;
+    if (fast_floor_divide(x - lower, h, &q)) {
+      if (kind == 1) return (q < 0.0 || q > (double)shape) ? (uint32_t)shape : (uint32_t)q;  // grids.py:117-121
+      if (fabs(q) < 2147483648.0) {  // grids.py:134-138: idx % shape (Python sign convention)
+        int r = (int)q % shape;
+        if (r < 0) r += shape;
+        return (uint32_t)r;
+      }
+    }
+  }
+  return grid_index_slow(kind, x, lower, upper, shape);
 }
 
 // approxfun/core.py:107-136: centre of bin k along one axis
@@ -251,6 +287,32 @@ PSB_HD_COLD bool chol_solve(int k, const double* A, const double* b, double* x) 
     x[i] = s / L[i * 4 + i];
   }
   return true;
+}
+
+// chol_solve for the sizes that occur in practice, straight-line: k = 1 and k = 2 in registers
+// (reciprocal square roots instead of sqrt + divisions); larger systems use the loop version.
+PSB_HD bool spd_solve(int k, const double* A, const double* b, double* x) {
+  if (k == 1) {
+    if (!(A[0] > 0.0)) return false;
+    x[0] = b[0] / A[0];
+    return true;
+  }
+  if (k == 2) {
+    const double a11 = A[0], a21 = A[4], a22 = A[5];
+    if (!(a11 > 0.0)) return false;
+    const double i11 = 1.0 / sqrt(a11);
+    const double l21 = a21 * i11;
+    const double s22 = a22 - l21 * l21;
+    if (!(s22 > 0.0)) return false;
+    const double i22 = 1.0 / sqrt(s22);
+    const double y1 = b[0] * i11;
+    const double y2 = (b[1] - l21 * y1) * i22;
+    const double x2 = y2 * i22;
+    x[1] = x2;
+    x[0] = (y1 - l21 * x2) * i11;
+    return true;
+  }
+  return chol_solve(k, A, b, x);
 }
 
 // utils/core.py:125-126 `pinv(A.T) @ B` == pinv_sym(A A^T) (A B); cutoff follows

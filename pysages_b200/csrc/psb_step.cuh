@@ -30,6 +30,13 @@ namespace psb {
 
 constexpr int CT = 4;  // terms per thread kept in registers (slot, position, prefetched force)
 
+// The step kernel is compiled once per (engine layout, dtype, method, CV class): the finalizer
+// code is executed once per launch by one warp, so it runs at instruction-fetch speed; keeping
+// every instantiation small (no code for methods / CV kinds it cannot meet) is what keeps that
+// path inside the instruction cache.  GENERAL = false: only point CVs (Component ... Dihedral),
+// no atom shared between groups, no dense outputs, no walkers.
+enum StepMethod { SM_UNBIASED = 0, SM_HARMONIC = 1, SM_METAD_DIRECT = 2, SM_ABF = 3, SM_METAD_GRID = 4, SM_COUNT = 5 };
+
 // ---- small device utilities -----------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -73,11 +80,11 @@ __device__ __forceinline__ long long global_ns() {
 }
 #define PSB_CLK(slot)                                                                \
   do {                                                                               \
-    if (M.dbg && threadIdx.x == 0) M.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
   } while (0)
 #define PSB_STAMP(slot)                                                              \
   do {                                                                               \
-    if (M.dbg && threadIdx.x == 0) M.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
   } while (0)
 
 struct StepShared {
@@ -85,6 +92,8 @@ struct StepShared {
   double tot[MAXG + 1][NACC];
   Fin fin;  // this CTA's copy of the finalizer results
   Pre pre;  // method-state scalars as they were when the step began
+  unsigned long long epoch[NBARS];  // completed uses of each grid barrier when the step began
+  uint32_t bars_used;               // barriers this launch arrived on (thread 0)
   uint64_t mbar[2];
 };
 
@@ -107,21 +116,34 @@ __device__ __forceinline__ void block_reduce_store(StepShared& sh, const double*
   __syncthreads();
 }
 
-// Grid-wide barrier on a monotonic arrival counter (never reset; gridDim.x is fixed per handle and
-// every launch that uses barrier `id` arrives on it from every CTA).
-__device__ __forceinline__ unsigned long long grid_arrive(const Model& M, int id) {
+// Grid-wide barrier on monotonic counters (never reset; gridDim.x is fixed per handle).
+// `epochs[id]` counts the launches that completed barrier `id`; every CTA reads it in the prologue,
+// so its target is known up front: the arrival is a fire-and-forget RED and the first poll can
+// already succeed (an atomic that returns the old count would cost one more L2 round trip on the
+// critical path).  CTA 0 advances the epochs it used at the end of the launch -- by then every
+// CTA has long read them.  Replay-safe (CUDA graphs): nothing depends on host-side counters.
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long grid_arrive(const Model& M, StepShared& sh, int id) {
   __threadfence();
-  const unsigned long long t = atomicAdd(&M.bars[id].arrive, 1ULL);
-  return (t / gridDim.x + 1ULL) * gridDim.x;
+  red_add_u64(&M.bars[id].arrive, 1ULL);
+  sh.bars_used |= 1u << id;
+  return (sh.epoch[id] + 1ULL) * gridDim.x;
 }
 __device__ __forceinline__ void grid_wait(const Model& M, int id, unsigned long long want) {
   while (ld_acquire_u64(&M.bars[id].arrive) < want) {}
 }
-__device__ __forceinline__ void grid_sync(const Model& M, int id) {
+__device__ __forceinline__ void grid_sync(const Model& M, StepShared& sh, int id) {
   __syncthreads();
   if (gridDim.x == 1) return;
-  if (threadIdx.x == 0) grid_wait(M, id, grid_arrive(M, id));
+  if (threadIdx.x == 0) grid_wait(M, id, grid_arrive(M, sh, id));
   __syncthreads();
+}
+// end of the launch (thread 0 of CTA 0): publish the epochs of the barriers that were used
+__device__ __forceinline__ void commit_epochs(const Model& M, const StepShared& sh) {
+  for (int id = 0; id < NBARS; ++id)
+    if (sh.bars_used & (1u << id)) M.epochs[id] = sh.epoch[id] + 1ULL;
 }
 
 __host__ __device__ __forceinline__ bool is_point_kind(int kind) {
@@ -143,41 +165,50 @@ __host__ __device__ __forceinline__ int nacc_for_kind(int kind, int pass, bool m
 // order.  pass 0 / 1: the rows of the atom groups (group g lives in CTAs cta_first[g] ..
 // cta_first[g+1]-1); pass >= 2: `vrows` rows of the virtual group, spanning all CTAs.
 // Eight threads share one row: 4 independent L2 loads each per round, then 3 shuffle steps.
-__device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int pass, int vrows) {
+// The row -> (destination, CTA range) lookup does not depend on the barrier, so the caller
+// computes it (row_plan) BEFORE waiting and only loads + shuffles remain behind the barrier.
+struct RowPlan {
+  int dst, blo, bhi;  // dst < 0: no row
+};
+__device__ __forceinline__ RowPlan row_plan(const Model& M, int pass, int vrows, int r) {
+  RowPlan p{-1, 0, -1};
+  const int nrows = pass < 2 ? M.row_first[pass][M.ngroups] : vrows;
+  if (gridDim.x == 1 || r >= nrows) return p;
+  if (pass < 2) {
+    int g = 0;
+    while (r >= M.row_first[pass][g + 1]) ++g;
+    p.dst = g * NACC + (r - M.row_first[pass][g]);
+    p.blo = M.cta_first[g];
+    p.bhi = M.cta_first[g + 1] - 1;
+  } else {
+    p.dst = VGROUP * NACC + r;
+    p.blo = 0;
+    p.bhi = (int)gridDim.x - 1;
+  }
+  return p;
+}
+__device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int pass, int vrows, RowPlan first) {
   const int nb = gridDim.x;
   if (nb > 1) {
     const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
     const int nrows = pass < 2 ? M.row_first[pass][M.ngroups] : vrows;
     for (int r0 = 0; r0 < nrows; r0 += BLOCK / 8) {
-      const int r = r0 + rl;
+      const RowPlan p = (r0 == 0) ? first : row_plan(M, pass, vrows, r0 + rl);
       double v = 0.0;
-      int dst = 0;
-      if (r < nrows) {
-        int blo, bhi;
-        if (pass < 2) {
-          int g = 0;
-          while (r >= M.row_first[pass][g + 1]) ++g;
-          dst = g * NACC + (r - M.row_first[pass][g]);
-          blo = M.cta_first[g];
-          bhi = M.cta_first[g + 1] - 1;
-        } else {
-          dst = VGROUP * NACC + r;
-          blo = 0;
-          bhi = nb - 1;
-        }
-        const double* src = M.partials + (size_t)dst * nb;
-        for (int bb = blo + sub; bb <= bhi; bb += 32) {
+      if (p.dst >= 0) {
+        const double* src = M.partials + (size_t)p.dst * nb;
+        for (int bb = p.blo + sub; bb <= p.bhi; bb += 32) {
           const double a0 = __ldcg(src + bb);
-          const double a1 = bb + 8 <= bhi ? __ldcg(src + bb + 8) : 0.0;
-          const double a2 = bb + 16 <= bhi ? __ldcg(src + bb + 16) : 0.0;
-          const double a3 = bb + 24 <= bhi ? __ldcg(src + bb + 24) : 0.0;
+          const double a1 = bb + 8 <= p.bhi ? __ldcg(src + bb + 8) : 0.0;
+          const double a2 = bb + 16 <= p.bhi ? __ldcg(src + bb + 16) : 0.0;
+          const double a3 = bb + 24 <= p.bhi ? __ldcg(src + bb + 24) : 0.0;
           v += (a0 + a1) + (a2 + a3);
         }
       }
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (r < nrows && sub == 0) (&sh.tot[0][0])[dst] = v;
+      if (p.dst >= 0 && sub == 0) (&sh.tot[0][0])[p.dst] = v;
     }
   }
   __syncthreads();
@@ -191,48 +222,54 @@ __device__ __forceinline__ void put3(double* dst, V3 v) {
   dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
 }
 
-// CV `c`: value and Jacobian factors after pass A (one lane per CV).
+// CV `c`: value and Jacobian factors after pass A (one lane per CV).  Only the rows
+// gpt[g][j < ncomp] of a CV's groups are ever read, and every case writes them completely.
+template <bool GENERAL>
 static __device__ __noinline__ void finalize_cv_A(const Model& M, StepShared& sh, int c) {
   Fin& f = sh.fin;
   const CvDev& cv = M.cv[c];
   const int g0 = cv.g0;
-  V3 p[4];
-  if (is_point_kind(cv.kind)) {
-    for (int j = 0; j < cv.ngroups; ++j) {
-      p[j] = M.grp[g0 + j].inv_n * tot3(sh, g0 + j, 0);
-      for (int q = 0; q < 3; ++q) put3(f.gpt[g0 + j][q], v3(0, 0, 0));
-    }
-  }
-  switch (cv.kind) {
-    case PSB_CV_COMPONENT: {  // coordinates.py:28,71
-      f.xi[cv.comp0] = comp(p[0], cv.axis);
-      f.gpt[g0][0][cv.axis] = 1.0;
-    } break;
-    case PSB_CV_DISTANCE: {
+  const int kind = cv.kind;
+  if (is_point_kind(kind)) {
+    // barycentres of the (up to four) groups, in registers
+    const V3 p0 = M.grp[g0].inv_n * tot3(sh, g0, 0);
+    if (kind == PSB_CV_DISTANCE) {  // coordinates.py:91-109
+      const V3 p1 = M.grp[g0 + 1].inv_n * tot3(sh, g0 + 1, 0);
       V3 a, b;
-      f.xi[cv.comp0] = distance_cv(p[0], p[1], &a, &b);
+      f.xi[cv.comp0] = distance_cv(p0, p1, &a, &b);
       put3(f.gpt[g0][0], a);
       put3(f.gpt[g0 + 1][0], b);
-    } break;
-    case PSB_CV_DISPLACEMENT: {  // coordinates.py:148: r2 - r1
-      V3 d = p[1] - p[0];
+    } else if (kind == PSB_CV_COMPONENT) {  // coordinates.py:28,71
+      f.xi[cv.comp0] = comp(p0, cv.axis);
+      put3(f.gpt[g0][0], v3(cv.axis == 0 ? 1.0 : 0.0, cv.axis == 1 ? 1.0 : 0.0, cv.axis == 2 ? 1.0 : 0.0));
+    } else if (kind == PSB_CV_DISPLACEMENT) {  // coordinates.py:148: r2 - r1
+      const V3 p1 = M.grp[g0 + 1].inv_n * tot3(sh, g0 + 1, 0);
+      const V3 d = p1 - p0;
       f.xi[cv.comp0 + 0] = d.x; f.xi[cv.comp0 + 1] = d.y; f.xi[cv.comp0 + 2] = d.z;
       for (int q = 0; q < 3; ++q) {
-        f.gpt[g0][q][q] = -1.0;
-        f.gpt[g0 + 1][q][q] = 1.0;
+        const V3 e = v3(q == 0 ? 1.0 : 0.0, q == 1 ? 1.0 : 0.0, q == 2 ? 1.0 : 0.0);
+        put3(f.gpt[g0][q], (-1.0) * e);
+        put3(f.gpt[g0 + 1][q], e);
       }
-    } break;
-    case PSB_CV_ANGLE: {
-      V3 a, b, d;
-      f.xi[cv.comp0] = angle_cv(p[0], p[1], p[2], &a, &b, &d);
-      put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b); put3(f.gpt[g0 + 2][0], d);
-    } break;
-    case PSB_CV_DIHEDRAL: {
-      V3 a, b, d, e;
-      f.xi[cv.comp0] = dihedral_cv(p[0], p[1], p[2], p[3], &a, &b, &d, &e);
-      put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b);
-      put3(f.gpt[g0 + 2][0], d); put3(f.gpt[g0 + 3][0], e);
-    } break;
+    } else {
+      const V3 p1 = M.grp[g0 + 1].inv_n * tot3(sh, g0 + 1, 0);
+      const V3 p2 = M.grp[g0 + 2].inv_n * tot3(sh, g0 + 2, 0);
+      if (kind == PSB_CV_ANGLE) {
+        V3 a, b, d;
+        f.xi[cv.comp0] = angle_cv(p0, p1, p2, &a, &b, &d);
+        put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b); put3(f.gpt[g0 + 2][0], d);
+      } else {  // PSB_CV_DIHEDRAL
+        const V3 p3 = M.grp[g0 + 3].inv_n * tot3(sh, g0 + 3, 0);
+        V3 a, b, d, e;
+        f.xi[cv.comp0] = dihedral_cv(p0, p1, p2, p3, &a, &b, &d, &e);
+        put3(f.gpt[g0][0], a); put3(f.gpt[g0 + 1][0], b);
+        put3(f.gpt[g0 + 2][0], d); put3(f.gpt[g0 + 3][0], e);
+      }
+    }
+    return;
+  }
+  if (!GENERAL) return;
+  switch (kind) {
     case PSB_CV_ROG: {  // shape.py:52-57: sum r.r / n ; d/dr_i = 2 r_i / n
       f.xi[cv.comp0] = sh.tot[g0][0] * M.grp[g0].inv_n;
       f.cvx[c][0] = 2.0 * M.grp[g0].inv_n;
@@ -307,9 +344,14 @@ __device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int
     const int g = lane;
     const CvDev& cv = M.cv[M.grp[g].cv];
     double v[3] = {0, 0, 0};
-    if (is_point_kind(cv.kind))
-      for (int j = 0; j < cv.ncomp; ++j)
-        for (int a = 0; a < 3; ++a) v[a] -= f.F[cv.comp0 + j] * f.gpt[g][j][a] * M.grp[g].inv_n;
+    if (is_point_kind(cv.kind)) {
+      const double inv_n = M.grp[g].inv_n;
+#pragma unroll 1
+      for (int j = 0; j < cv.ncomp; ++j) {
+        const double Fj = f.F[cv.comp0 + j] * inv_n;
+        v[0] -= Fj * f.gpt[g][j][0]; v[1] -= Fj * f.gpt[g][j][1]; v[2] -= Fj * f.gpt[g][j][2];
+      }
+    }
     f.fg[g][0] = v[0]; f.fg[g][1] = v[1]; f.fg[g][2] = v[2];
   }
   if (cta0) {
@@ -333,7 +375,7 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
     double Wp[MAXK] = {0, 0, 0, 0};
     if (m.use_pinv) {
       pinv_sym_solve(k, f.JJt, f.Jp, Wp, 10.0 * (double)(3 * M.natoms) * 2.220446049250313e-16);
-    } else if (!chol_solve(k, f.JJt, f.Jp, Wp)) {
+    } else if (!spd_solve(k, f.JJt, f.Jp, Wp)) {
       for (int c = 0; c < k; ++c) Wp[c] = nan("");
     }
     for (int c = 0; c < MAXK; ++c) f.Wp[c] = Wp[c];
@@ -410,6 +452,7 @@ __device__ __forceinline__ void metad_grid_force(const Model& M, Fin& f, int lan
 }
 
 // Everything that can be decided once xi is complete (warp 0, all lanes).
+template <int METHOD, bool GENERAL>
 static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
   Fin& f = sh.fin;
   const MethodDev& m = M.m;
@@ -425,9 +468,9 @@ static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepS
   __syncwarp();
   if (S.mode == MODE_EVAL) return;
   const long long ncalls = sh.pre.ncalls + 1;
-  switch (m.kind) {
-    case PSB_METHOD_UNBIASED: finish_force(M, sh, lane, cta0); break;
-    case PSB_METHOD_HARMONIC: {  // harmonic_bias.py:124-128 (no periodic wrap: quirk kept)
+  switch (METHOD) {
+    case SM_UNBIASED: finish_force(M, sh, lane, cta0); break;
+    case SM_HARMONIC: {  // harmonic_bias.py:124-128 (no periodic wrap: quirk kept)
       if (lane < k) {
         double s = 0.0;
         for (int b = 0; b < k; ++b) s += m.kspring[lane * MAXK + b] * (f.xi[b] - m.center[b]);
@@ -441,25 +484,38 @@ static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepS
       }
       finish_force(M, sh, lane, cta0);
     } break;
-    case PSB_METHOD_ABF: {
-      if (!M.abf_fast) break;  // needs pass C
+    case SM_ABF: {
+      if (GENERAL && !M.abf_fast) break;  // needs pass C
       // J J^T and J p from per-group sums: point-CV Jacobians are constant within a group.
       // lanes 0..15: entry (a, b) of J J^T; lanes 16..19: entry a of J p.
       if (lane < 16) {
         const int a = lane >> 2, bq = lane & 3;
         double s = 0.0;
         if (a < k && bq < k) {
-          const CvDev& ca = M.cv[M.comp_cv[a]];
-          const CvDev& cb = M.cv[M.comp_cv[bq]];
+          const int cia = M.comp_cv[a], cib = M.comp_cv[bq];
+          const CvDev& ca = M.cv[cia];
+          const CvDev& cb = M.cv[cib];
           const int ja = a - ca.comp0, jb = bq - cb.comp0;
-          for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g)
-            for (int h = cb.g0; h < cb.g0 + cb.ngroups; ++h) {
-              if (M.ov[g][h] == 0) continue;
+          if (cia == cib) {  // atoms of one group: (count / n_g^2) * dxi_a/dpoint . dxi_b/dpoint
+#pragma unroll 1
+            for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g) {
               const double* ga = f.gpt[g][ja];
-              const double* gb = f.gpt[h][jb];
-              s += (double)M.ov[g][h] * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * M.grp[g].inv_n *
-                   M.grp[h].inv_n;
+              const double* gb = f.gpt[g][jb];
+              s += M.grp[g].self_coef * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]);
             }
+          }
+          if (M.cross_overlap) {  // atoms shared between different groups
+#pragma unroll 1
+            for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g)
+#pragma unroll 1
+              for (int h = cb.g0; h < cb.g0 + cb.ngroups; ++h) {
+                if (g == h || M.ov[g][h] == 0) continue;
+                const double* ga = f.gpt[g][ja];
+                const double* gb = f.gpt[h][jb];
+                s += (double)M.ov[g][h] * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * M.grp[g].inv_n *
+                     M.grp[h].inv_n;
+              }
+          }
         }
         f.JJt[lane] = s;
       } else if (lane < 16 + MAXK) {
@@ -468,6 +524,7 @@ static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepS
         if (a < k) {
           const CvDev& ca = M.cv[M.comp_cv[a]];
           const int ja = a - ca.comp0;
+#pragma unroll 1
           for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g) {
             const V3 ps = tot3(sh, g, 3);
             const double* ga = f.gpt[g][ja];
@@ -479,12 +536,12 @@ static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepS
       PSB_CLK(11);
       abf_finish(M, S, sh, lane, cta0);
     } break;
-    case PSB_METHOD_METAD: {
+    case SM_METAD_DIRECT: {
       const bool in_dep = (ncalls > 1) && (ncalls % m.stride == 1);  // metad.py:192-193
-      if (m.grid_kind == PSB_GRID_NONE) {
-        if (lane == 0) f.deposit = in_dep ? 1 : 0;  // heights need V: decided after pass H
-        break;
-      }
+      if (lane == 0) f.deposit = in_dep ? 1 : 0;  // heights need V: decided after pass H
+    } break;
+    case SM_METAD_GRID: {
+      const bool in_dep = (ncalls > 1) && (ncalls % m.stride == 1);  // metad.py:192-193
       grid_bin_warp(m, f, lane);
       if (lane < k) f.hill[lane] = f.xi[lane];
       if (in_dep && !f.oob) {  // metad.py:258-271
@@ -546,11 +603,12 @@ __device__ __forceinline__ void fin_load(const Model& M, StepShared& sh) {
 // ---- per-term arithmetic ------------------------------------------------------------------------
 // pass A contribution of one atom of a group of CV `cv` (position r, unwrapped, fp64; momentum p
 // only when the ABF fast path sums momenta per group)
+template <bool GENERAL>
 __device__ __forceinline__ void accumulate_term(const CvDev& cv, bool with_p, double inv_n, uint32_t t,
                                                 V3 r, V3 p, double* acc) {
-  if (cv.kind == PSB_CV_ROG) {
+  if (GENERAL && cv.kind == PSB_CV_ROG) {
     acc[0] += r.x * r.x + r.y * r.y + r.z * r.z;
-  } else if (cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
+  } else if (GENERAL && cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
     const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : inv_n;
     const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
     const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
@@ -559,7 +617,7 @@ __device__ __forceinline__ void accumulate_term(const CvDev& cv, bool with_p, do
     acc[6] += r.x * q0; acc[7] += r.x * q1; acc[8] += r.x * q2;
     acc[9] += r.y * q0; acc[10] += r.y * q1; acc[11] += r.y * q2;
     acc[12] += r.z * q0; acc[13] += r.z * q1; acc[14] += r.z * q2;
-  } else if (is_point_kind(cv.kind)) {
+  } else if (!GENERAL || is_point_kind(cv.kind)) {
     acc[0] += r.x; acc[1] += r.y; acc[2] += r.z;
     if (with_p) {
       acc[3] += p.x; acc[4] += p.y; acc[5] += p.z;
@@ -628,9 +686,9 @@ __device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
-template <int LAYOUT, typename Real>
+template <int LAYOUT, typename Real, int METHOD, bool GENERAL>
 __global__ void __launch_bounds__(BLOCK, 2)
-step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S) {
+step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   using A = Access<LAYOUT, Real>;
   using FV = typename A::FV;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -638,14 +696,17 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
   __shared__ __align__(16) Model sM;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // The kernel parameters live in a constant bank that is cold at every launch; the finalizers
-  // walk the model tables in one warp, where every constant-cache miss would be serialised.  One
-  // cooperative copy into shared memory takes a single miss latency for the whole CTA instead.
+  PSB_STAMP(0);
+  // The model (index tables, method constants, state pointers: ~3 KB, fixed per handle) lives in
+  // device memory and is copied into shared memory by the whole CTA: one L2 round trip.  As a
+  // kernel parameter it cost 2 us of launch latency per step (measured: tools/launch_floor.py), and
+  // the finalizers, which walk it from a single warp, would take a serialised constant-cache miss
+  // per table line.
   {
     static_assert(sizeof(Model) % 8 == 0, "Model is copied in 8-byte words");
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&Mparam);
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(Mglobal);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sM);
-    for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = src[i];
+    for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const Model& M = sM;
@@ -654,20 +715,27 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
   const bool cta0 = (b == 0);
   const int k = M.k;
   const MethodDev& m = M.m;
-  const bool metad_direct = (m.kind == PSB_METHOD_METAD && m.grid_kind == PSB_GRID_NONE);
-  const bool grid_metad = (m.kind == PSB_METHOD_METAD && m.grid_kind != PSB_GRID_NONE);
-  const bool skip_cv = (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
-  const bool momenta_sums = S.need_momenta && M.abf_fast;
-  const bool will_scatter = (m.kind != PSB_METHOD_UNBIASED) &&
-                            (S.mode == MODE_STEP || S.mode == MODE_WALKER_FINISH);
+  constexpr bool metad_direct = (METHOD == SM_METAD_DIRECT);
+  constexpr bool grid_metad = (METHOD == SM_METAD_GRID);
+  constexpr bool is_abf = (METHOD == SM_ABF);
+  const bool any_rmsd = GENERAL && M.any_rmsd;
+  const bool any_coord = GENERAL && M.any_coord;
+  const bool all_unique = !GENERAL || M.all_unique;
+  const bool abf_fast = is_abf && (!GENERAL || M.abf_fast);
+  const bool need_term_slot = GENERAL && M.need_term_slot;
+  const bool skip_cv = GENERAL && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
+  const bool momenta_sums = S.need_momenta && abf_fast;
+  const bool will_scatter = (METHOD != SM_UNBIASED) &&
+                            (S.mode == MODE_STEP || (GENERAL && S.mode == MODE_WALKER_FINISH));
 
-  PSB_STAMP(0);
   // ---- prologue: method-state scalars as they are when the step begins --------------------------
   if (tid == 0) {
     sh.pre.ncalls = __ldcg(M.st.ncalls);
     sh.pre.idx = M.st.idx ? __ldcg(M.st.idx) : 0;
+    sh.bars_used = 0;
   }
-  if (m.kind == PSB_METHOD_ABF && tid >= 32 && tid < 32 + 3 * MAXK) {
+  if (tid >= 64 && tid < 64 + NBARS) sh.epoch[tid - 64] = __ldcg(M.epochs + (tid - 64));
+  if (is_abf && tid >= 32 && tid < 32 + 3 * MAXK) {
     const int j = tid - 32, c = j & (MAXK - 1), which = j / MAXK;
     const double* src = which == 0 ? M.st.Wp : (which == 1 ? M.st.Wp_ : M.st.force);
     double* dst = which == 0 ? sh.pre.Wp : (which == 1 ? sh.pre.Wp_ : sh.pre.force);
@@ -679,7 +747,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
   const int HC = M.hill_chunk;
   double* stage_c[2];
   double* stage_h[2];
-  const bool hills_here = metad_direct && (S.mode == MODE_STEP || S.mode == MODE_WALKER_BEGIN);
+  const bool hills_here = metad_direct && (S.mode == MODE_STEP || (GENERAL && S.mode == MODE_WALKER_BEGIN));
   if (hills_here) {
     stage_c[0] = reinterpret_cast<double*>(dyn_smem);
     stage_h[0] = stage_c[0] + (size_t)HC * k;
@@ -748,7 +816,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
             cslot[i] = 0;
             if (t < hi) {
               cslot[i] = A::slot(S, M, term_tag_of(M, G, t));
-              if (M.need_term_slot) M.term_slot[t] = cslot[i];
+              if (need_term_slot) M.term_slot[t] = cslot[i];
             }
           }
 #pragma unroll
@@ -764,7 +832,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
 #pragma unroll
           for (int i = 0; i < CT; ++i) {
             const uint32_t t = lo + tid + i * BLOCK;
-            if (t < hi) accumulate_term(cv, with_p, G.inv_n, t, cr[i], cp[i], acc);
+            if (t < hi) accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, cr[i], cp[i], acc);
           }
         } else {
 #pragma unroll 4
@@ -772,7 +840,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
             const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
             M.term_slot[t] = slot;
             const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
-            accumulate_term(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
+            accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
           }
         }
         if (na > 0) block_reduce_store(sh, acc, na, M.partials + (size_t)(seg_g * NACC) * nb + b, nb, true);
@@ -791,7 +859,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
           const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
           M.term_slot[t] = slot;
           const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
-          accumulate_term(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
+          accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
         }
         if (na == 0) continue;
         if (G.t1 - G.t0 == 1) {  // a bare index: no reduction needed
@@ -804,23 +872,24 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
     }
 
     PSB_STAMP(1);
-    grid_sync(M, BAR_A);
+    const RowPlan planA = row_plan(M, 0, 0, tid >> 3);
+    grid_sync(M, sh, BAR_A);
     PSB_STAMP(2);
     PSB_CLK(8);
-    reduce_rows(M, sh, 0, 0);
+    reduce_rows(M, sh, 0, 0, planA);
     PSB_CLK(9);
     if (warp == 0) {
-      if (M.any_coord) reduce_coordination(M, sh, lane);
-      if (lane < M.ncv) finalize_cv_A(M, sh, lane);
+      if (any_coord) reduce_coordination(M, sh, lane);
+      if (lane < M.ncv) finalize_cv_A<GENERAL>(M, sh, lane);
       PSB_CLK(10);
-      if (!M.any_rmsd) post_cv(M, S, sh, lane, cta0);
+      if (!any_rmsd) post_cv<METHOD, GENERAL>(M, S, sh, lane, cta0);
       PSB_CLK(15);
     }
     __syncthreads();
     PSB_STAMP(3);
 
     // ---- pass B: RMSD residual with the optimal rotation ------------------------------------
-    if (M.any_rmsd) {
+    if (any_rmsd) {
       if (nb > 1) {
         if (seg_g >= 0 && M.cv[M.grp[seg_g].cv].kind == PSB_CV_RMSD) {
           const CvDev& cv = M.cv[M.grp[seg_g].cv];
@@ -852,21 +921,25 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
           block_reduce_store(sh, acc, 1, &sh.tot[g][0], 1, false);
         }
       }
-      grid_sync(M, BAR_B);
-      reduce_rows(M, sh, 1, 0);
+      const RowPlan planB = row_plan(M, 1, 0, tid >> 3);
+      grid_sync(M, sh, BAR_B);
+      reduce_rows(M, sh, 1, 0, planB);
       if (warp == 0) {
         if (lane < M.ncv) finalize_cv_B(M, sh, lane);
-        post_cv(M, S, sh, lane, cta0);
+        post_cv<METHOD, GENERAL>(M, S, sh, lane, cta0);
       }
       __syncthreads();
     }
   } else {
     fin_load(M, sh);
   }
-  if (S.mode == MODE_EVAL) return;
+  if (S.mode == MODE_EVAL) {
+    if (cta0 && tid == 0) commit_epochs(M, sh);
+    return;
+  }
 
   // ---- pass C: J J^T and J p over unique atoms (ABF with position-dependent Jacobians) -----------
-  if (m.kind == PSB_METHOD_ABF && !M.abf_fast) {
+  if (is_abf && !abf_fast) {
     const uint32_t uchunk = (M.Su + nb - 1) / nb;
     const uint32_t u0 = min(M.Su, (uint32_t)b * uchunk), u1 = min(M.Su, u0 + uchunk);
     double acc[NACC];
@@ -876,11 +949,11 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
       V3 G[MAXK];
 #pragma unroll
       for (int c = 0; c < MAXK; ++c) G[c] = v3(0, 0, 0);
-      const uint32_t e0 = M.all_unique ? u : __ldg(M.uniq_ptr + u);
-      const uint32_t e1 = M.all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
+      const uint32_t e0 = all_unique ? u : __ldg(M.uniq_ptr + u);
+      const uint32_t e1 = all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
       uint32_t slot = 0;
       for (uint32_t e = e0; e < e1; ++e) {
-        const uint32_t t = M.all_unique ? e : __ldg(M.uniq_term + e);
+        const uint32_t t = all_unique ? e : __ldg(M.uniq_term + e);
         const int g = __ldg(M.term_group + t);
         slot = __ldcg(M.term_slot + t);
         V3 gv[3];
@@ -903,8 +976,9 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
     }
     if (nb == 1) block_reduce_store(sh, acc, 14, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 14, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
-    grid_sync(M, BAR_C);
-    reduce_rows(M, sh, 2, 14);
+    const RowPlan planC = row_plan(M, 2, 14, tid >> 3);
+    grid_sync(M, sh, BAR_C);
+    reduce_rows(M, sh, 2, 14, planC);
     if (warp == 0) {
       if (lane == 0) {
         int o = 0;
@@ -953,8 +1027,9 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
     }
     if (nb == 1) block_reduce_store(sh, acc, 1 + k, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 1 + k, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
-    grid_sync(M, BAR_H);
-    reduce_rows(M, sh, 3, 1 + k);
+    const RowPlan planH = row_plan(M, 3, 1 + k, tid >> 3);
+    grid_sync(M, sh, BAR_H);
+    reduce_rows(M, sh, 3, 1 + k, planH);
     if (warp == 0) {
       Fin& f = sh.fin;
       const double V = sh.tot[VGROUP][0];
@@ -990,21 +1065,23 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
     __syncthreads();
   }
 
-  if (S.mode == MODE_WALKER_BEGIN) {
+  if (GENERAL && S.mode == MODE_WALKER_BEGIN) {
     if (cta0) {
       if (tid < k + 2) S.record_out[tid] = sh.fin.hill[tid];
       fin_store(M, sh);
+      if (tid == 0) commit_epochs(M, sh);
     }
     return;
   }
 
   // ---- pass D: add newly deposited Gaussians to the grids (metad.py:251-256) ---------------------
-  if ((grid_metad && S.mode == MODE_STEP && sh.fin.deposit) || S.mode == MODE_WALKER_FINISH) {
-    const int nrec = (S.mode == MODE_WALKER_FINISH) ? S.nwalkers : 1;
+  if ((grid_metad && S.mode == MODE_STEP && sh.fin.deposit) || (GENERAL && S.mode == MODE_WALKER_FINISH)) {
+    const bool wfinish = GENERAL && (S.mode == MODE_WALKER_FINISH);
+    const int nrec = wfinish ? S.nwalkers : 1;
     const int rs = k + 2;
     if (grid_metad) {
       // every CTA has read grid_potential[I] (well-tempered height) before any bin is rewritten
-      if (S.mode == MODE_STEP && m.well_tempered) grid_sync(M, BAR_PRE_D);
+      if (S.mode == MODE_STEP && m.well_tempered) grid_sync(M, sh, BAR_PRE_D);
       for (long long p = (long long)b * BLOCK + tid; p < m.grid_points; p += (long long)nb * BLOCK) {
         double x[MAXK];
         long long rem = p;
@@ -1015,18 +1092,18 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
         }
         double val = 0.0, dV[MAXK] = {0, 0, 0, 0};
         for (int r = 0; r < nrec; ++r) {
-          const double* rec = (S.mode == MODE_WALKER_FINISH) ? S.records + (size_t)r * rs : sh.fin.hill;
+          const double* rec = wfinish ? S.records + (size_t)r * rs : sh.fin.hill;
           if (rec[k + 1] == 0.0) continue;
           val += hill_eval(m, k, x, rec, rec[k], dV);  // d/dx of the Gaussian centred on rec
         }
         if (M.st.gp) M.st.gp[p] += val;
         for (int c = 0; c < k; ++c) M.st.gg[p * k + c] += dV[c];
       }
-      grid_sync(M, BAR_D);
+      grid_sync(M, sh, BAR_D);
     }
     if (warp == 0) {
       Fin& f = sh.fin;
-      if (S.mode == MODE_WALKER_FINISH && lane == 0) {
+      if (wfinish && lane == 0) {
         // append the walkers' hills in rank order (identical on every rank)
         long long idx = sh.pre.idx;
         for (int r = 0; r < nrec; ++r) {
@@ -1056,13 +1133,13 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
   // ---- pass S: in-place force scatter ------------------------------------------------------------
   if (will_scatter) {
     const Fin& f = sh.fin;
-    const bool dense = (M.bias_dense != nullptr);
-    if (M.all_unique && !dense) {
+    const bool dense = GENERAL && (M.bias_dense != nullptr);
+    if (all_unique && !dense) {
       if (nb > 1) {
         if (seg_g >= 0) {
           const GroupDev& G = M.grp[seg_g];
           const CvDev& cv = M.cv[G.cv];
-          const bool point = is_point_kind(cv.kind);
+          const bool point = !GENERAL || is_point_kind(cv.kind);
           const V3 fgv = v3(f.fg[seg_g][0], f.fg[seg_g][1], f.fg[seg_g][2]);
           const double Fc = -f.F[cv.comp0];
           if (cached) {
@@ -1105,7 +1182,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
         for (int g = 0; g < M.ngroups; ++g) {
           const GroupDev& G = M.grp[g];
           const CvDev& cv = M.cv[G.cv];
-          if (is_point_kind(cv.kind)) {
+          if (!GENERAL || is_point_kind(cv.kind)) {
             const V3 fgv = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
 #pragma unroll 2
             for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fgv);
@@ -1126,12 +1203,12 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
       const uint32_t u0 = min(M.Su, (uint32_t)b * uchunk), u1 = min(M.Su, u0 + uchunk);
       const size_t N3 = 3 * (size_t)M.natoms;
       for (uint32_t u = u0 + tid; u < u1; u += BLOCK) {
-        const uint32_t e0 = M.all_unique ? u : __ldg(M.uniq_ptr + u);
-        const uint32_t e1 = M.all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
+        const uint32_t e0 = all_unique ? u : __ldg(M.uniq_ptr + u);
+        const uint32_t e1 = all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
         V3 fo = v3(0, 0, 0);
         uint32_t slot = 0;
         for (uint32_t e = e0; e < e1; ++e) {
-          const uint32_t t = M.all_unique ? e : __ldg(M.uniq_term + e);
+          const uint32_t t = all_unique ? e : __ldg(M.uniq_term + e);
           const int g = __ldg(M.term_group + t);
           slot = __ldcg(M.term_slot + t);
           V3 gv[3];
@@ -1158,11 +1235,11 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
   // every bin of hist / Fsum this CTA needed was read long ago: tell CTA 0 (non-blocking, and after
   // the scatter so the fence + atomic stay off the critical path)
   unsigned long long readers_want = 0;
-  const bool abf_commit = (m.kind == PSB_METHOD_ABF && nb > 1 && S.mode == MODE_STEP);
-  if (abf_commit && tid == 0) readers_want = grid_arrive(M, BAR_READERS);
+  const bool abf_commit = (is_abf && nb > 1 && S.mode == MODE_STEP);
+  if (abf_commit && tid == 0) readers_want = grid_arrive(M, sh, BAR_READERS);
 
   // ---- ABF commit: CTA 0 stores the new count / force sum of bin I (abf.py:216-218) -------------
-  if (m.kind == PSB_METHOD_ABF && cta0 && S.mode == MODE_STEP && tid == 0) {
+  if (is_abf && cta0 && S.mode == MODE_STEP && tid == 0) {
     if (abf_commit) grid_wait(M, BAR_READERS, readers_want);
     const Fin& f = sh.fin;
     if (f.in_range) {
@@ -1170,6 +1247,7 @@ step_kernel(const __grid_constant__ Model Mparam, const __grid_constant__ Snap S
       for (int c = 0; c < k; ++c) M.st.Fsum[f.flat * k + c] = f.Fsum_new[c];
     }
   }
+  if (cta0 && tid == 0) commit_epochs(M, sh);
   PSB_STAMP(6);
 }
 

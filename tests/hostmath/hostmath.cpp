@@ -41,6 +41,10 @@ double hm_mesh_coord(int kind, int k, double lower, double upper, int shape) {
 }
 
 int hm_chol_solve(int k, const double* A4, const double* b, double* x) { return chol_solve(k, A4, b, x) ? 1 : 0; }
+int hm_spd_solve(int k, const double* A4, const double* b, double* x) { return spd_solve(k, A4, b, x) ? 1 : 0; }
+unsigned hm_grid_index_slow(int kind, double x, double lower, double upper, int shape) {
+  return grid_index_slow(kind, x, lower, upper, shape);
+}
 
 void hm_pinv_solve(int k, const double* A4, const double* b, double* x, double rtol) {
   pinv_sym_solve(k, A4, b, x, rtol);

@@ -34,6 +34,9 @@ def hm():
     lib.hm_mesh_coord.restype = ctypes.c_double
     lib.hm_mesh_coord.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]
     lib.hm_chol_solve.argtypes = [ctypes.c_int, dp, dp, dp]
+    lib.hm_spd_solve.argtypes = [ctypes.c_int, dp, dp, dp]
+    lib.hm_grid_index_slow.restype = ctypes.c_uint
+    lib.hm_grid_index_slow.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
     lib.hm_pinv_solve.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double]
     lib.hm_wrap.restype = ctypes.c_double
     lib.hm_wrap.argtypes = [ctypes.c_double, ctypes.c_double]
@@ -106,6 +109,25 @@ def test_grid_index_bit_exact(hm, golden):
                 assert hm.hm_grid_index(kind, float(x), lower, upper, shape) == int(get_index(x)[0]), (kind, x)
 
 
+def test_grid_index_fast_path_equals_literal_restatement(hm):
+    """The division-only bin index (device fast path) against the fmod-based restatement of
+    jnp.floor_divide on edges, near-edges, far out-of-range values and non-finite inputs."""
+    rng = np.random.default_rng(5)
+    for kind in (1, 2):
+        for lower, upper, shape in ((-np.pi, np.pi, 50), (0.0, 1.0, 10), (0.0, 23.2, 64), (-1e-3, 1e3, 4096),
+                                    (0.1, 0.7, 3), (-5.0, -1.0, 1)):
+            h = (upper - lower) / shape
+            edges = lower + h * np.arange(-3 * shape, 4 * shape + 1)
+            xs = np.concatenate([edges, np.nextafter(edges, np.inf), np.nextafter(edges, -np.inf),
+                                 lower + np.arange(-shape, 2 * shape) * h + 0.5 * h,
+                                 rng.uniform(lower - 3 * (upper - lower), upper + 3 * (upper - lower), 4000),
+                                 [1e300, -1e300, 1e17, -1e17, 3e9 * h, -3e9 * h, np.inf, -np.inf, np.nan, 0.0, -0.0]])
+            for x in xs:
+                a = hm.hm_grid_index(kind, float(x), lower, upper, shape)
+                b = hm.hm_grid_index_slow(kind, float(x), lower, upper, shape)
+                assert a == b, (kind, x, lower, upper, shape, a, b)
+
+
 def test_mesh_and_wrap(hm):
     g = grids.Grid((-np.pi,), (np.pi,), (50,))
     mesh = grids.compute_mesh(g)[:, 0]
@@ -130,8 +152,14 @@ def test_small_solvers(hm):
         x = np.zeros(4)
         assert hm.hm_chol_solve(k, _ptr(A4), _ptr(b), _ptr(x)) == 1
         assert np.allclose(x[:k], np.linalg.solve(A, b), rtol=1e-11)
+        x3 = np.zeros(4)
+        assert hm.hm_spd_solve(k, _ptr(A4), _ptr(b), _ptr(x3)) == 1
+        assert np.allclose(x3[:k], np.linalg.solve(A, b), rtol=1e-11)
         x2 = np.zeros(4)
         hm.hm_pinv_solve(k, _ptr(A4), _ptr(b), _ptr(x2), 1e-14)
         assert np.allclose(x2[:k], np.linalg.pinv(A) @ b, rtol=1e-9)
     A4 = np.zeros((4, 4)); A4[0, 0] = -1.0
     assert hm.hm_chol_solve(1, _ptr(A4), _ptr(np.ones(1)), _ptr(np.zeros(4))) == 0
+    assert hm.hm_spd_solve(1, _ptr(A4), _ptr(np.ones(1)), _ptr(np.zeros(4))) == 0
+    A4 = np.zeros((4, 4)); A4[:2, :2] = [[1.0, 2.0], [2.0, 1.0]]  # indefinite
+    assert hm.hm_spd_solve(2, _ptr(A4), _ptr(np.ones(2)), _ptr(np.zeros(4))) == 0

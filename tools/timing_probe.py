@@ -16,11 +16,15 @@ for wl, natoms in cases:
     descs = bench.snapdesc_array(native, snaps)
     ms, _ = bench.time_cycle(native, descs, 200, 20, stream)
     torch.cuda.synchronize()
-    t = native.view("debug_timing", (-1, 16)).cpu().numpy().astype(np.float64)
+    tt = native.view("debug_timing", (2, -1, 16)).cpu().numpy().astype(np.float64)
+    # the two halves hold the last two launches; order them by start time
+    a, b2 = (0, 1) if tt[0, :, 0].min() < tt[1, :, 0].min() else (1, 0)
+    prev, t = tt[a], tt[b2]
     g = t.shape[0]
     t0 = t[:, 0].min()
     rel = lambda x: (x - t0) / 1e3
-    print(f"{wl} N={natoms} grid={g} us/step={ms*1e3/200:.2f}")
+    print(f"{wl} N={natoms} grid={g} us/step={ms*1e3/200:.2f}   gap (prev kernel last stamp -> this kernel first stamp) = {(t0 - prev[:, 6].max())/1e3:.2f} us;"
+          f" period by stamps = {(t0 - prev[:, 0].min())/1e3:.2f} us")
     names = ["start", "passA done", "barrier passed", "finalize done", "scatter start", "scatter end", "kernel end"]
     for i, nme in enumerate(names):
         col = rel(t[:, i])
