@@ -101,6 +101,15 @@ def workload_specs(name, natoms, L):
         h = natoms // 2
         cvs = [("Distance", ([list(range(0, h)), list(range(h, natoms))],), {})]
         return cvs, ("HarmonicBias", dict(kspring=10.0, center=[1.0]))
+    if name == "walkers":  # cfg5: well-tempered metadynamics on two dihedrals, periodic 50x50 grid, shared hills
+        cvs = [("DihedralAngle", ([4, 6, 8, 14],), {}), ("DihedralAngle", ([6, 8, 14, 16],), {})]
+        pi = float(np.pi)
+        m = ("Metadynamics", dict(height=1.2, sigma=[0.35, 0.35], stride=500, ngaussians=4096, deltaT=5000.0,
+                                  kB=0.0083144626, grid=((-pi, -pi), (pi, pi), (50, 50), "periodic"), shared_hills=True))
+        return cvs, m
+    if name == "window":  # cfg5: one umbrella window (HarmonicBias on a Component CV over 1000 atoms)
+        cvs = [("Component", (list(range(1000)), 0), {})]
+        return cvs, ("HarmonicBias", dict(kspring=50.0, center=[0.0]))
     raise ValueError(name)
 
 
@@ -125,6 +134,8 @@ def build_ours(cv_specs, method_spec, snapshot):
         method = ps.methods.ABF(cvs, kw.pop("grid"), **kw)
     else:
         args = [kw.pop(k) for k in ("height", "sigma", "stride", "ngaussians")]
+        if kw.get("grid") is None:
+            kw.pop("grid", None)
         method = ps.methods.Metadynamics(cvs, *args, kw.pop("deltaT", None), **kw)
     helpers = HelperMethods(None, lambda: 3, lambda x: x, mock.LAYOUTS["hoomd"])
     _, init, update = method.build(snapshot, helpers)
@@ -142,20 +153,32 @@ def snapdesc_array(native, snapshots):
     return arr
 
 
-def time_cycle(native, descs, steps, warmup, stream):
-    """CUDA-event timing of `steps` bias steps issued by the native engine-loop emulation."""
+def time_cycle(native, descs, steps, warmup, stream, plain=False):
+    """CUDA-event timing of `steps` bias steps issued by the native engine-loop emulation
+    (psb_run_cycle: CUDA-graph replay of the snapshot ring; plain=True: one launch per step)."""
     lib = native.lib
     from pysages_b200 import _native as N
 
     h = native.handle
     sp = ctypes.c_void_p(stream.cuda_stream)
-    N.check(lib.psb_run_cycle(h, descs, len(descs), warmup, sp))
+    n = len(descs)
+
+    def issue(k):
+        if not plain:
+            N.check(lib.psb_run_cycle(h, descs, n, k, sp))
+        else:  # fewer than two passes over the ring per call: psb_run_cycle issues plain launches
+            while k > 0:
+                c = min(k, n)
+                N.check(lib.psb_run_cycle(h, descs, n, c, sp))
+                k -= c
+
+    issue(warmup)
     stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.psb_launch_count(h)
     with torch.cuda.stream(stream):
         e0.record(stream)
-        N.check(lib.psb_run_cycle(h, descs, len(descs), steps, sp))
+        issue(steps)
         e1.record(stream)
     stream.synchronize()
     return e0.elapsed_time(e1), lib.psb_launch_count(h) - l0
@@ -278,6 +301,97 @@ def cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s, max_steps
     return n / el, n, cores
 
 
+def run_walkers(device, stream, rank, world, dist, natoms=100_000, total_steps=3000):
+    """cfg5: `world` walkers (one per GPU) share hills: plain steps run in the native engine loop,
+    every deposit step is psb_walker_begin -> NCCL all-gather of (k + 2) doubles -> psb_walker_finish."""
+    from pysages_b200 import _native as N
+    from pysages_b200 import parallel
+
+    frames, L, _ = device_hoomd_frames(natoms, 8, device, seed=20240 + 5000 + rank)
+    snaps = snapshots_of(frames, L, 0.002)
+    cvs, m = workload_specs("walkers", natoms, L)
+    method, native = build_ours(cvs, m, snaps[0])
+    descs = snapdesc_array(native, snaps)
+    engine = parallel.NativeWalkerEngine(native)
+    exchange = parallel.RecordExchange()
+    stride = m[1]["stride"]
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    calls, deposits = 0, 0
+
+    def advance(n):
+        nonlocal calls, deposits
+        done = 0
+        while done < n:
+            nxt = calls + 1
+            if nxt > 1 and nxt % stride == 1:
+                engine.walker_begin(snaps[calls % len(snaps)])
+                engine.walker_finish(snaps[calls % len(snaps)], exchange(engine.record))
+                calls += 1; done += 1; deposits += 1
+            else:
+                until = stride - (calls % stride) if calls % stride else stride  # plain steps before the next deposit
+                k = max(1, min(n - done, until))
+                N.check(native.lib.psb_run_cycle(native.handle, descs, len(descs), k, sp))
+                calls += k; done += k
+
+    with torch.cuda.stream(stream):
+        advance(stride + 5)  # warm-up incl. the first exchange (NCCL channel set-up)
+        stream.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0 = deposits
+        e0.record(stream)
+        advance(total_steps)
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    idx = int(native.view("idx").item())
+    return dict(workload=f"cfg5 walkers: WT-metad, 2 dihedral CVs, periodic 50x50 grid, stride {stride}, N={natoms} hoomd-f32, "
+                         f"{world} walker(s) sharing hills by all-gather",
+                walkers=world, steps_per_walker=total_steps, deposit_steps=deposits - d0, hills_per_walker=idx,
+                steps_per_s=round(world * total_steps / (float(t.item()) * 1e-3), 1),
+                us_per_step=round(float(t.item()) * 1e3 / total_steps, 3))
+
+
+def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, steps=2000):
+    """cfg5: UmbrellaIntegration windows partitioned round-robin over the ranks (replicas only)."""
+    from pysages_b200 import parallel
+
+    mine = parallel.partition_windows(nwindows, world, rank)
+    frames, L, _ = device_hoomd_frames(natoms, 8, device, seed=20240 + 5500 + rank)
+    snaps = snapshots_of(frames, L, 0.005)
+    cvs, m = workload_specs("window", natoms, L)
+    natives = []
+    for w in mine:
+        mm = (m[0], dict(m[1], center=[-L / 4 + (L / 2) * w / max(nwindows - 1, 1)]))
+        natives.append(build_ours(cvs, mm, snaps[0]))
+    descs = snapdesc_array(natives[0][1], snaps)
+    for _, nat in natives:
+        time_cycle(nat, descs, 20, 5, stream)
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from pysages_b200 import _native as N
+
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    e0.record(stream)
+    for _, nat in natives:
+        N.check(nat.lib.psb_run_cycle(nat.handle, descs, len(descs), steps, sp))
+    e1.record(stream)
+    stream.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    means = parallel.gather_window_means({w: nat.view("xi").cpu().numpy().ravel()[:1] for w, (_, nat) in zip(mine, natives)}, nwindows)
+    return dict(workload=f"cfg5 umbrella: {nwindows} HarmonicBias windows (Component CV over 1000 atoms, N={natoms}) "
+                         f"round-robin over {world} GPU(s), {steps} steps each",
+                windows=nwindows, steps_per_s=round(nwindows * steps / (float(t.item()) * 1e-3), 1),
+                windows_gathered=int(means.shape[0]))
+
+
 def run_series(device, stream, hbm):
     """Secondary sizes / configurations (parity-tested elsewhere); short runs, same timing method."""
     out = []
@@ -311,6 +425,7 @@ def main():
     ap.add_argument("--no-series", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the cfg5 walker / umbrella-window legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -374,11 +489,14 @@ def main():
         barrier()
         ms, launches = time_cycle(native, descs, args.steps, max(args.warmup, 3), stream)
         barrier()
+    info = native.launch_info()
+    ms_plain, _ = time_cycle(native, descs, min(args.steps, 2000), 3, stream, plain=True)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * args.steps / (ms * 1e-3)
+    info["plain_launch_us_per_step"] = round(ms_plain * 1e3 / min(args.steps, 2000), 3)
 
     # e2e through the host-buffer C-ABI entry point
     e2e_steps = max(20, min(args.steps, 300))
@@ -390,6 +508,12 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
     e2e_value = world * float(t.item())
+
+    # cfg5 legs (all ranks take part): shared-hill walkers over NCCL, umbrella windows as replicas
+    multi = None
+    if not args.no_multi:
+        multi = dict(walkers=run_walkers(device, stream, rank, world, dist),
+                     umbrella=run_windows(device, stream, rank, world, dist))
 
     if rank != 0:
         if dist is not None:
@@ -419,7 +543,8 @@ def main():
                 data="synthetic", config=config, clocks=clocks.summary(),
                 e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          steps=e2e_steps, path="psb_step_host (pinned host snapshot -> H2D -> step -> D2H forces)"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, launch=info, series=series)
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, launch=info, series=series,
+                multi_gpu=multi)
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -180,7 +180,8 @@ psb_status psb_step(psb_handle* h, const psb_snapshot* snap, int64_t timestep, v
  * evaluates xi on `snap` without touching forces, state counters or histograms. */
 psb_status psb_evaluate_cvs(psb_handle* h, const psb_snapshot* snap, void* cuda_stream);
 
-/* Engine-loop emulation for benchmarks: calls psb_step on snaps[i % nsnaps] for nsteps steps. */
+/* Engine-loop emulation for benchmarks: psb_step on snaps[i % nsnaps] for nsteps steps.  One pass
+ * over the ring is captured as a CUDA graph and replayed (PSB_NO_GRAPH=1: plain launches). */
 psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnaps, int64_t nsteps,
                          void* cuda_stream);
 
@@ -220,6 +221,8 @@ psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64
                           uint32_t* out_host);
 /* Kernel launches issued since creation (for bench.py's gpu_launches) and the launch shape. */
 int64_t psb_launch_count(psb_handle* h);
+/* 1 when the last psb_run_cycle replayed a CUDA graph, 0 when it issued plain launches. */
+int32_t psb_cycle_uses_graph(psb_handle* h);
 psb_status psb_launch_info(psb_handle* h, int32_t* grid_blocks, int32_t* block_threads,
                            int32_t* cooperative, int64_t* algorithmic_bytes_per_step);
 /* Launch-latency floor for the bench report: enqueues `nlaunches` kernels of

@@ -26,4 +26,4 @@ Pinning status (see DESIGN.md "Oracle"):
     restatement of the semantics documented in DESIGN.md.
 """
 
-from . import backends, colvars, grids, methods  # noqa: F401
+from . import backends, colvars, grids, methods, walkers  # noqa: F401

@@ -116,6 +116,7 @@ EXPORTS = {
     "psb_next_step_deposits": (c_int32, [c_void_p]),
     "psb_grid_index": (c_int32, [POINTER(GridDesc), POINTER(c_double), c_int64, POINTER(c_uint32)]),
     "psb_launch_count": (c_int64, [c_void_p]),
+    "psb_cycle_uses_graph": (c_int32, [c_void_p]),
     "psb_launch_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "psb_launch_floor": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "psb_latency_probe": (c_int32, [POINTER(c_double)]),

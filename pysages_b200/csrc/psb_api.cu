@@ -65,6 +65,12 @@ struct psb_handle {
   long long host_ncalls = 0;  // mirror of the device ncalls (deterministic)
   long long algo_bytes = 0;
   long long* dbg = nullptr;  // PSB_DEBUG_TIMING=1: [2][grid][16] phase timestamps
+  // psb_run_cycle: one pass over the snapshot ring captured as a CUDA graph
+  cudaGraphExec_t cycle_exec = nullptr;
+  std::vector<psb_snapshot> cycle_key;
+  cudaStream_t cycle_stream = nullptr;
+  long long cycle_launches = 0;  // kernel launches inside one graph replay
+  int graph_replays = 0;         // 1 when the last psb_run_cycle replayed the graph
   int record_doubles = 0;
   // staging for psb_step_host
   psb_snapshot dev_snap{};
@@ -207,6 +213,7 @@ int32_t psb_abi_version(void) { return 1; }
 void psb_destroy(psb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -519,7 +526,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     case PSB_METHOD_ABF: h->step_method = SM_ABF; break;
     default: h->step_method = gridded ? SM_METAD_GRID : SM_METAD_DIRECT; break;
   }
-  h->step_general = (!M.all_point || !M.all_unique || layout->dense_outputs || method->shared_hills) ? 1 : 0;
+  h->step_general = (!M.all_point || !M.all_unique || layout->dense_outputs) ? 1 : 0;
   const int occ = pick_vtable(*layout)->occupancy(h->step_method, h->step_general, h->dyn_smem);
   if (occ < 1)
     return bail(fail(PSB_ERR_CUDA, "step kernel cannot be made resident (%s)", cudaGetErrorString(cudaGetLastError())));
@@ -534,7 +541,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   }
   if (metad_direct) want = std::max(want, (long long)((method->ngaussians + M.hill_chunk - 1) / M.hill_chunk));
   if (method->kind == PSB_METHOD_METAD && gridded)
-    want = std::max(want, (m.grid_points + BLOCK * 8 - 1) / (BLOCK * 8));
+    want = std::max(want, m.grid_points / (BLOCK * 64));  // deposit steps are rare: 64 bins per thread is fine
   if (const char* env = getenv("PSB_GRID_BLOCKS")) want = atoll(env);
   want = std::max(1LL, std::min(want, max_blocks));
   if (want > 1) want = std::max<long long>(want, ng);
@@ -629,8 +636,49 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
     psb_status st = check_snapshot(h, snaps + i, true);
     if (st != PSB_OK) return st;
   }
-  for (int64_t i = 0; i < nsteps; ++i) {
-    psb_status st = enqueue(h, snaps + (i % nsnaps), MODE_STEP, (cudaStream_t)cuda_stream, nullptr, 0, nullptr);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  int64_t done = 0;
+  h->graph_replays = 0;
+  // Launch-bound loop: one pass over the snapshot ring is captured once as a CUDA graph and
+  // replayed (the kernels keep no host-side counters: barrier epochs and method state live on the
+  // device, so replays are exact).  PSB_NO_GRAPH=1 or debug timing fall back to plain launches.
+  static const bool no_graph = getenv("PSB_NO_GRAPH") != nullptr;
+  if (!no_graph && !h->dbg && stream != nullptr && nsteps >= 2 * (int64_t)nsnaps) {
+    const bool same = h->cycle_exec && h->cycle_stream == stream && (int)h->cycle_key.size() == nsnaps &&
+                      memcmp(h->cycle_key.data(), snaps, sizeof(psb_snapshot) * nsnaps) == 0;
+    if (!same) {
+      if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);
+      h->cycle_exec = nullptr;
+      cudaGraph_t graph = nullptr;
+      const long long l0 = h->launches;
+      if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        psb_status st = PSB_OK;
+        for (int i = 0; i < nsnaps && st == PSB_OK; ++i) st = enqueue(h, snaps + i, MODE_STEP, stream, nullptr, 0, nullptr);
+        cudaError_t e = cudaStreamEndCapture(stream, &graph);
+        if (st == PSB_OK && e == cudaSuccess && graph &&
+            cudaGraphInstantiate(&h->cycle_exec, graph, 0) == cudaSuccess) {
+          h->cycle_key.assign(snaps, snaps + nsnaps);
+          h->cycle_stream = stream;
+          h->cycle_launches = h->launches - l0;
+        } else {
+          h->cycle_exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();     // a failed capture is not an error: plain launches below
+      h->launches = l0;       // captured launches have not run yet
+    }
+    if (h->cycle_exec) {
+      const int64_t reps = nsteps / nsnaps;
+      for (int64_t r = 0; r < reps; ++r) CUDA_TRY(cudaGraphLaunch(h->cycle_exec, stream));
+      done = reps * nsnaps;
+      h->host_ncalls += done;
+      h->launches += reps * h->cycle_launches;
+      h->graph_replays = 1;
+    }
+  }
+  for (int64_t i = done; i < nsteps; ++i) {
+    psb_status st = enqueue(h, snaps + (i % nsnaps), MODE_STEP, stream, nullptr, 0, nullptr);
     if (st != PSB_OK) return st;
     ++h->host_ncalls;
   }
@@ -821,6 +869,7 @@ psb_status psb_latency_probe(double* out_host16) {
 }
 
 int64_t psb_launch_count(psb_handle* h) { return h ? h->launches : 0; }
+int32_t psb_cycle_uses_graph(psb_handle* h) { return h ? h->graph_replays : 0; }
 
 psb_status psb_launch_info(psb_handle* h, int32_t* grid_blocks, int32_t* block_threads,
                            int32_t* cooperative, int64_t* algorithmic_bytes_per_step) {

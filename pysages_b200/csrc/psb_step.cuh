@@ -603,12 +603,11 @@ __device__ __forceinline__ void fin_load(const Model& M, StepShared& sh) {
 // ---- per-term arithmetic ------------------------------------------------------------------------
 // pass A contribution of one atom of a group of CV `cv` (position r, unwrapped, fp64; momentum p
 // only when the ABF fast path sums momenta per group)
-template <bool GENERAL>
-__device__ __forceinline__ void accumulate_term(const CvDev& cv, bool with_p, double inv_n, uint32_t t,
-                                                V3 r, V3 p, double* acc) {
-  if (GENERAL && cv.kind == PSB_CV_ROG) {
+// non-point kinds are kept out of line: the general kernels then keep the compact point-CV path
+static __device__ __noinline__ void accumulate_nonpoint(const CvDev& cv, double inv_n, uint32_t t, V3 r, double* acc) {
+  if (cv.kind == PSB_CV_ROG) {
     acc[0] += r.x * r.x + r.y * r.y + r.z * r.z;
-  } else if (GENERAL && cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
+  } else if (cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
     const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : inv_n;
     const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
     const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
@@ -617,11 +616,18 @@ __device__ __forceinline__ void accumulate_term(const CvDev& cv, bool with_p, do
     acc[6] += r.x * q0; acc[7] += r.x * q1; acc[8] += r.x * q2;
     acc[9] += r.y * q0; acc[10] += r.y * q1; acc[11] += r.y * q2;
     acc[12] += r.z * q0; acc[13] += r.z * q1; acc[14] += r.z * q2;
-  } else if (!GENERAL || is_point_kind(cv.kind)) {
+  }
+}
+template <bool GENERAL>
+__device__ __forceinline__ void accumulate_term(const CvDev& cv, bool with_p, double inv_n, uint32_t t,
+                                                V3 r, V3 p, double* acc) {
+  if (!GENERAL || is_point_kind(cv.kind)) {
     acc[0] += r.x; acc[1] += r.y; acc[2] += r.z;
     if (with_p) {
       acc[3] += p.x; acc[4] += p.y; acc[5] += p.z;
     }
+  } else {
+    accumulate_nonpoint(cv, inv_n, t, r, acc);
   }
 }
 
@@ -639,8 +645,8 @@ __device__ __forceinline__ double rmsd_residual(const CvDev& cv, const double* x
 }
 
 // gradient of a non-point CV with respect to the atom of term t (unwrapped position r)
-__device__ __forceinline__ V3 nonpoint_gradient(const Fin& f, const CvDev& cv, int c, double inv_n,
-                                                uint32_t t, V3 r) {
+static __device__ __noinline__ V3 nonpoint_gradient(const Fin& f, const CvDev& cv, int c, double inv_n,
+                                                    uint32_t t, V3 r) {
   if (cv.kind == PSB_CV_ROG) return f.cvx[c][0] * r;
   if (cv.kind == PSB_CV_RMSD) {
     const double* x = f.cvx[c];
@@ -718,15 +724,16 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   constexpr bool metad_direct = (METHOD == SM_METAD_DIRECT);
   constexpr bool grid_metad = (METHOD == SM_METAD_GRID);
   constexpr bool is_abf = (METHOD == SM_ABF);
+  constexpr bool WALK = metad_direct || grid_metad;  // walker modes exist for metadynamics only
   const bool any_rmsd = GENERAL && M.any_rmsd;
   const bool any_coord = GENERAL && M.any_coord;
   const bool all_unique = !GENERAL || M.all_unique;
   const bool abf_fast = is_abf && (!GENERAL || M.abf_fast);
-  const bool need_term_slot = GENERAL && M.need_term_slot;
-  const bool skip_cv = GENERAL && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
+  const bool need_term_slot = (GENERAL || WALK) && M.need_term_slot;
+  const bool skip_cv = WALK && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
   const bool momenta_sums = S.need_momenta && abf_fast;
   const bool will_scatter = (METHOD != SM_UNBIASED) &&
-                            (S.mode == MODE_STEP || (GENERAL && S.mode == MODE_WALKER_FINISH));
+                            (S.mode == MODE_STEP || (WALK && S.mode == MODE_WALKER_FINISH));
 
   // ---- prologue: method-state scalars as they are when the step begins --------------------------
   if (tid == 0) {
@@ -747,7 +754,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   const int HC = M.hill_chunk;
   double* stage_c[2];
   double* stage_h[2];
-  const bool hills_here = metad_direct && (S.mode == MODE_STEP || (GENERAL && S.mode == MODE_WALKER_BEGIN));
+  const bool hills_here = metad_direct && (S.mode == MODE_STEP || S.mode == MODE_WALKER_BEGIN);
   if (hills_here) {
     stage_c[0] = reinterpret_cast<double*>(dyn_smem);
     stage_h[0] = stage_c[0] + (size_t)HC * k;
@@ -779,95 +786,93 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
   }
 
-  // ---- this CTA's atom segment (gridDim.x > 1: exactly one group per CTA) ----------------------
+  // ---- this CTA's terms ----------------------------------------------------------------------
+  // gridDim.x > 1: exactly one group per CTA, an even share of its terms; gridDim.x == 1: all terms.
+  // Up to CT terms per thread are "cached": slot, group, position and the prefetched force row stay
+  // in registers until the scatter.
   int seg_g = -1;
   uint32_t lo = 0, hi = 0;
-  if (nb > 1 && !skip_cv) {
-    for (int g = 0; g < M.ngroups; ++g)
-      if (b >= M.cta_first[g] && b < M.cta_first[g + 1]) seg_g = g;
-    if (seg_g >= 0) {
-      const GroupDev& G = M.grp[seg_g];
-      const uint32_t nc = (uint32_t)(M.cta_first[seg_g + 1] - M.cta_first[seg_g]);
-      const uint32_t per = (G.t1 - G.t0 + nc - 1) / nc;
-      lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_first[seg_g]) * per);
-      hi = min(G.t1, lo + per);
+  if (!skip_cv) {
+    if (nb > 1) {
+      for (int g = 0; g < M.ngroups; ++g)
+        if (b >= M.cta_first[g] && b < M.cta_first[g + 1]) seg_g = g;
+      if (seg_g >= 0) {
+        const GroupDev& G = M.grp[seg_g];
+        const uint32_t nc = (uint32_t)(M.cta_first[seg_g + 1] - M.cta_first[seg_g]);
+        const uint32_t per = (G.t1 - G.t0 + nc - 1) / nc;
+        lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_first[seg_g]) * per);
+        hi = min(G.t1, lo + per);
+      }
+    } else {
+      hi = M.T;
     }
   }
-  const bool cached = (seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
+  const bool cached = !skip_cv && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
+  const int g_begin = skip_cv ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
+  const int g_end = skip_cv ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
   uint32_t cslot[CT];
+  int cg[CT];
   V3 cr[CT], cp[CT];
   FV cfv[CT];
 
   // ---- pass A ---------------------------------------------------------------------------------
   if (!skip_cv) {
-    if (nb > 1) {
-      if (seg_g >= 0) {
-        const GroupDev& G = M.grp[seg_g];
-        const CvDev& cv = M.cv[G.cv];
-        const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
-        const bool with_p = (na == 6);
-        double acc[NACC];
+    if (cached) {
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-        if (cached) {
-#pragma unroll
-          for (int i = 0; i < CT; ++i) {
-            const uint32_t t = lo + tid + i * BLOCK;
-            cslot[i] = 0;
-            if (t < hi) {
-              cslot[i] = A::slot(S, M, term_tag_of(M, G, t));
-              if (need_term_slot) M.term_slot[t] = cslot[i];
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < CT; ++i) {
-            const uint32_t t = lo + tid + i * BLOCK;
-            cp[i] = v3(0, 0, 0);
-            if (t < hi) {
-              cr[i] = A::position(S, cslot[i]);
-              if (with_p) cp[i] = A::momentum(S, cslot[i]);
-              if (will_scatter) cfv[i] = A::load_force(S, cslot[i]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < CT; ++i) {
-            const uint32_t t = lo + tid + i * BLOCK;
-            if (t < hi) accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, cr[i], cp[i], acc);
-          }
-        } else {
-#pragma unroll 4
-          for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-            const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
-            M.term_slot[t] = slot;
-            const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
-            accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
-          }
+      for (int i = 0; i < CT; ++i) {
+        const uint32_t t = lo + tid + i * BLOCK;
+        cslot[i] = 0;
+        cg[i] = -1;
+        if (t < hi) {
+          cg[i] = (nb == 1) ? (int)__ldg(M.term_group + t) : seg_g;
+          cslot[i] = A::slot(S, M, term_tag_of(M, M.grp[cg[i]], t));
+          if (need_term_slot) M.term_slot[t] = cslot[i];
         }
-        if (na > 0) block_reduce_store(sh, acc, na, M.partials + (size_t)(seg_g * NACC) * nb + b, nb, true);
       }
-    } else {
-      for (int g = 0; g < M.ngroups; ++g) {
-        const GroupDev& G = M.grp[g];
-        const CvDev& cv = M.cv[G.cv];
-        const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
-        const bool with_p = (na == 6);
-        double acc[NACC];
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-#pragma unroll 2
-        for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) {
+      for (int i = 0; i < CT; ++i) {
+        cp[i] = v3(0, 0, 0);
+        if (cg[i] >= 0) {
+          cr[i] = A::position(S, cslot[i]);
+          if (momenta_sums) cp[i] = A::momentum(S, cslot[i]);
+          if (will_scatter) cfv[i] = A::load_force(S, cslot[i]);
+        }
+      }
+    }
+    for (int g = g_begin; g < g_end; ++g) {
+      const GroupDev& G = M.grp[g];
+      const CvDev& cv = M.cv[G.cv];
+      const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
+      const bool with_p = (na == 6);
+      double acc[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+      bool mine = false;
+      if (cached) {
+#pragma unroll
+        for (int i = 0; i < CT; ++i)
+          if (cg[i] == g) {
+            accumulate_term<GENERAL>(cv, with_p, G.inv_n, lo + tid + i * BLOCK, cr[i], cp[i], acc);
+            mine = true;
+          }
+      } else {
+        const uint32_t tlo = max(lo, G.t0), thi = min(hi, G.t1);
+#pragma unroll 4
+        for (uint32_t t = tlo + tid; t < thi; t += BLOCK) {
           const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
           M.term_slot[t] = slot;
           const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
           accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
         }
-        if (na == 0) continue;
-        if (G.t1 - G.t0 == 1) {  // a bare index: no reduction needed
-          if (tid == 0)
-            for (int a = 0; a < na; ++a) sh.tot[g][a] = acc[a];
-        } else {
-          block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
-        }
+      }
+      if (na == 0) continue;
+      if (nb > 1) {
+        block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+      } else if (G.t1 - G.t0 == 1) {  // a bare index: its owner writes the sums, no reduction
+        if (mine)
+          for (int a = 0; a < na; ++a) sh.tot[g][a] = acc[a];
+      } else {
+        block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
       }
     }
 
@@ -890,36 +895,24 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
 
     // ---- pass B: RMSD residual with the optimal rotation ------------------------------------
     if (any_rmsd) {
-      if (nb > 1) {
-        if (seg_g >= 0 && M.cv[M.grp[seg_g].cv].kind == PSB_CV_RMSD) {
-          const CvDev& cv = M.cv[M.grp[seg_g].cv];
-          const double* x = sh.fin.cvx[M.grp[seg_g].cv];
-          double acc[1] = {0.0};
-          if (cached) {
+      for (int g = g_begin; g < g_end; ++g) {
+        const GroupDev& G = M.grp[g];
+        const CvDev& cv = M.cv[G.cv];
+        if (cv.kind != PSB_CV_RMSD) continue;
+        const double* x = sh.fin.cvx[G.cv];
+        double acc[1] = {0.0};
+        if (cached) {
 #pragma unroll
-            for (int i = 0; i < CT; ++i) {
-              const uint32_t t = lo + tid + i * BLOCK;
-              if (t < hi) acc[0] += rmsd_residual(cv, x, t, cr[i]);
-            }
-          } else {
+          for (int i = 0; i < CT; ++i)
+            if (cg[i] == g) acc[0] += rmsd_residual(cv, x, lo + tid + i * BLOCK, cr[i]);
+        } else {
+          const uint32_t tlo = max(lo, G.t0), thi = min(hi, G.t1);
 #pragma unroll 2
-            for (uint32_t t = lo + tid; t < hi; t += BLOCK)
-              acc[0] += rmsd_residual(cv, x, t, A::position(S, __ldcg(M.term_slot + t)));
-          }
-          block_reduce_store(sh, acc, 1, M.partials + (size_t)(seg_g * NACC) * nb + b, nb, true);
-        }
-      } else {
-        for (int g = 0; g < M.ngroups; ++g) {
-          const GroupDev& G = M.grp[g];
-          const CvDev& cv = M.cv[G.cv];
-          if (cv.kind != PSB_CV_RMSD) continue;
-          const double* x = sh.fin.cvx[G.cv];
-          double acc[1] = {0.0};
-#pragma unroll 2
-          for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK)
+          for (uint32_t t = tlo + tid; t < thi; t += BLOCK)
             acc[0] += rmsd_residual(cv, x, t, A::position(S, __ldcg(M.term_slot + t)));
-          block_reduce_store(sh, acc, 1, &sh.tot[g][0], 1, false);
         }
+        if (nb > 1) block_reduce_store(sh, acc, 1, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+        else block_reduce_store(sh, acc, 1, &sh.tot[g][0], 1, false);
       }
       const RowPlan planB = row_plan(M, 1, 0, tid >> 3);
       grid_sync(M, sh, BAR_B);
@@ -1065,7 +1058,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     __syncthreads();
   }
 
-  if (GENERAL && S.mode == MODE_WALKER_BEGIN) {
+  if (WALK && S.mode == MODE_WALKER_BEGIN) {
     if (cta0) {
       if (tid < k + 2) S.record_out[tid] = sh.fin.hill[tid];
       fin_store(M, sh);
@@ -1075,8 +1068,8 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   }
 
   // ---- pass D: add newly deposited Gaussians to the grids (metad.py:251-256) ---------------------
-  if ((grid_metad && S.mode == MODE_STEP && sh.fin.deposit) || (GENERAL && S.mode == MODE_WALKER_FINISH)) {
-    const bool wfinish = GENERAL && (S.mode == MODE_WALKER_FINISH);
+  if ((grid_metad && S.mode == MODE_STEP && sh.fin.deposit) || (WALK && S.mode == MODE_WALKER_FINISH)) {
+    const bool wfinish = WALK && (S.mode == MODE_WALKER_FINISH);
     const int nrec = wfinish ? S.nwalkers : 1;
     const int rs = k + 2;
     if (grid_metad) {
@@ -1135,67 +1128,52 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     const Fin& f = sh.fin;
     const bool dense = GENERAL && (M.bias_dense != nullptr);
     if (all_unique && !dense) {
-      if (nb > 1) {
-        if (seg_g >= 0) {
-          const GroupDev& G = M.grp[seg_g];
-          const CvDev& cv = M.cv[G.cv];
-          const bool point = !GENERAL || is_point_kind(cv.kind);
-          const V3 fgv = v3(f.fg[seg_g][0], f.fg[seg_g][1], f.fg[seg_g][2]);
-          const double Fc = -f.F[cv.comp0];
-          if (cached) {
+      if (cached) {
 #pragma unroll
-            for (int i = 0; i < CT; ++i) {
-              const uint32_t t = lo + tid + i * BLOCK;
-              if (t < hi) {
-                const V3 fo = point ? fgv : Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, cr[i]);
-                A::store_force(S, cslot[i], cfv[i], fo);
-              }
-            }
-          } else if (point) {
-#pragma unroll 4
-            for (uint32_t t = lo + tid; t < hi; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fgv);
-          } else {
-#pragma unroll 2
-            for (uint32_t t = lo + tid; t < hi; t += BLOCK) {
-              const uint32_t slot = __ldcg(M.term_slot + t);
-              V3 r = v3(0, 0, 0);
-              if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
-              add_force<A>(S, slot, Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r));
-            }
-          }
-        } else if (skip_cv) {
-          // walker finish: no pass A ran in this launch, spread all terms over the CTAs
-          const uint32_t chunk = (M.T + nb - 1) / nb;
-          const uint32_t c0 = min(M.T, (uint32_t)b * chunk), c1 = min(M.T, c0 + chunk);
-          for (uint32_t t = c0 + tid; t < c1; t += BLOCK) {
-            const int g = __ldg(M.term_group + t);
-            const uint32_t slot = __ldcg(M.term_slot + t);
-            V3 gv[3];
-            const int nc = term_gradient<A>(M, S, f, t, g, slot, gv);
-            const int comp0 = M.cv[M.grp[g].cv].comp0;
-            V3 fo = v3(0, 0, 0);
-            for (int j = 0; j < nc; ++j) fo = fo + (-f.F[comp0 + j]) * gv[j];
-            add_force<A>(S, slot, fo);
+        for (int i = 0; i < CT; ++i) {
+          const int g = cg[i];
+          if (g >= 0) {
+            const GroupDev& G = M.grp[g];
+            const CvDev& cv = M.cv[G.cv];
+            V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
+            if (GENERAL && !is_point_kind(cv.kind))
+              fo = (-f.F[cv.comp0]) * nonpoint_gradient(f, cv, G.cv, G.inv_n, lo + tid + i * BLOCK, cr[i]);
+            A::store_force(S, cslot[i], cfv[i], fo);
           }
         }
-      } else {
-        for (int g = 0; g < M.ngroups; ++g) {
+      } else if (!skip_cv) {  // large groups: slots were published in pass A
+        for (int g = g_begin; g < g_end; ++g) {
           const GroupDev& G = M.grp[g];
           const CvDev& cv = M.cv[G.cv];
+          const uint32_t tlo = max(lo, G.t0), thi = min(hi, G.t1);
           if (!GENERAL || is_point_kind(cv.kind)) {
             const V3 fgv = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
-#pragma unroll 2
-            for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fgv);
+#pragma unroll 4
+            for (uint32_t t = tlo + tid; t < thi; t += BLOCK) add_force<A>(S, __ldcg(M.term_slot + t), fgv);
           } else {
             const double Fc = -f.F[cv.comp0];
 #pragma unroll 2
-            for (uint32_t t = G.t0 + tid; t < G.t1; t += BLOCK) {
+            for (uint32_t t = tlo + tid; t < thi; t += BLOCK) {
               const uint32_t slot = __ldcg(M.term_slot + t);
               V3 r = v3(0, 0, 0);
               if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
               add_force<A>(S, slot, Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r));
             }
           }
+        }
+      } else {
+        // walker finish: no pass A ran in this launch, spread all terms over the CTAs
+        const uint32_t chunk = (M.T + nb - 1) / nb;
+        const uint32_t c0 = min(M.T, (uint32_t)b * chunk), c1 = min(M.T, c0 + chunk);
+        for (uint32_t t = c0 + tid; t < c1; t += BLOCK) {
+          const int g = __ldg(M.term_group + t);
+          const uint32_t slot = __ldcg(M.term_slot + t);
+          V3 gv[3];
+          const int nc = term_gradient<A>(M, S, f, t, g, slot, gv);
+          const int comp0 = M.cv[M.grp[g].cv].comp0;
+          V3 fo = v3(0, 0, 0);
+          for (int j = 0; j < nc; ++j) fo = fo + (-f.F[comp0 + j]) * gv[j];
+          add_force<A>(S, slot, fo);
         }
       }
     } else {

@@ -189,7 +189,8 @@ class NativeStep:
         N.check(self.lib.psb_launch_info(self.handle, ctypes.byref(g), ctypes.byref(b), ctypes.byref(c),
                                          ctypes.byref(nbytes)))
         return dict(grid_blocks=g.value, block_threads=b.value, cooperative=bool(c.value),
-                    algorithmic_bytes_per_step=nbytes.value, launches=int(self.lib.psb_launch_count(self.handle)))
+                    algorithmic_bytes_per_step=nbytes.value, launches=int(self.lib.psb_launch_count(self.handle)),
+                    cuda_graph=bool(self.lib.psb_cycle_uses_graph(self.handle)))
 
     # ---- state ---------------------------------------------------------------------------
     def view(self, field, shape=None):

@@ -334,3 +334,72 @@ def test_grid_indices_bit_exact_on_device():
                              for x in xs], dtype=np.uint32)
             got = ps.grids.build_indexer(ps.Grid[pk]((lower,), (upper,), (shape,)))(xs.reshape(-1, 1))
             assert np.array_equal(got[:, 0], want), kind
+
+
+# ---- multiple walkers sharing hills (extension) -----------------------------------------
+@pytest.mark.parametrize("deltaT", [None, 5000.0])
+@pytest.mark.parametrize("grid", [None, ((-math.pi, -math.pi), (math.pi, math.pi), (20, 20), "periodic")])
+def test_shared_hill_walkers(golden, deltaT, grid):
+    """W walkers in lockstep on one GPU: psb_walker_begin -> records in rank order -> psb_walker_finish,
+    against the single-process restatement (oracle/walkers.py).  The all-gather itself is covered by
+    tests/test_parallel_cpu.py (gloo) and by bench.py --gpus N (NCCL)."""
+    import oracle
+    import pysages_b200 as ps
+    from parity_utils import X64_RTOL, device_helpers, device_snapshot, make_cvs, make_method, oracle_snapshot
+    from pysages_b200 import parallel
+
+    W, nsteps = 3, 8
+    kw = dict(height=1.2, sigma=[0.35, 0.35], stride=3, ngaussians=12, grid=grid)
+    if deltaT is not None:
+        kw.update(deltaT=deltaT, kB=0.0083144626)
+    base = adp(golden, layout="hoomd")
+    exchange = parallel.RecordExchange()
+    owalkers, engines, trajs, dsnaps, osnaps = [], [], [], [], []
+    for w in range(W):
+        snap = dict(base)
+        snap["arrays"] = {k: np.array(v, copy=True) for k, v in base["arrays"].items()}
+        trajs.append(perturbed(snap, nsteps, 0.02, seed=30 + w))
+        om = make_method("oracle", ("Metadynamics", kw), make_cvs(oracle.colvars, ADP_CVS))
+        helpers, bias = oracle.backends.build_helpers("hoomd", om.snapshot_flags, True)
+        osnaps.append(oracle_snapshot(snap))
+        owalkers.append(oracle.walkers.SharedHillsWalker(om, osnaps[-1], helpers, bias))
+        m = make_method("ours", ("Metadynamics", dict(kw, shared_hills=True)), make_cvs(ps.colvars, ADP_CVS))
+        dsnaps.append(device_snapshot(snap))
+        _, init, update = m.build(dsnaps[-1], device_helpers("hoomd"))
+        init()
+        engines.append(parallel.NativeWalkerEngine(update.native))
+    for t in range(nsteps):
+        for w in range(W):
+            osnaps[w] = osnaps[w]._replace(positions=np.array(trajs[w][t], copy=True))
+            dsnaps[w] = dsnaps[w]._replace(positions=torch.as_tensor(np.ascontiguousarray(trajs[w][t])).cuda())
+        if engines[0].next_step_deposits():
+            assert all(e.next_step_deposits() for e in engines) and owalkers[0].next_step_deposits()
+            orecs = torch.stack([ow.walker_begin(s) for ow, s in zip(owalkers, osnaps)])
+            recs = torch.stack([e.walker_begin(s).clone() for e, s in zip(engines, dsnaps)])
+            close(recs.cpu().numpy(), orecs.numpy(), X64_RTOL, what="hill records")
+            for ow, s in zip(owalkers, osnaps):
+                ow.walker_finish(s, orecs)
+            for e, s in zip(engines, dsnaps):
+                e.walker_finish(s, recs)
+        else:
+            for ow, s in zip(owalkers, osnaps):
+                ow.step(s)
+            for e, s in zip(engines, dsnaps):
+                parallel.walker_step(e, s, exchange)
+        torch.cuda.synchronize()
+        for w in range(W):
+            n, o = engines[w].native, owalkers[w].state
+            close(n.view("xi").cpu().numpy().ravel()[:2], o.xi.numpy().ravel(), X64_RTOL, what="xi")
+            close(n.view("heights").cpu().numpy().ravel(), o.heights.numpy(), X64_RTOL, what="heights")
+            close(n.view("centers").cpu().numpy().reshape(-1, 2), o.centers.numpy(), X64_RTOL, what="centers")
+            assert int(n.view("idx").item()) == int(o.idx) and int(n.view("ncalls").item()) == int(o.ncalls)
+            close(n.view("bias").cpu().numpy().reshape(-1, 3), o.bias.numpy(), X64_RTOL,
+                  scale=max(float(o.bias.abs().max()), 1e-300), what="bias")
+            close(dsnaps[w].forces.cpu().numpy()[:, :3], osnaps[w].forces[:, :3], 1e-12, what="forces")
+            if grid is not None:
+                close(n.view("grid_gradient").cpu().numpy().reshape(o.grid_gradient.shape), o.grid_gradient.numpy(),
+                      X64_RTOL, what="grid_gradient")
+                if deltaT is not None:
+                    close(n.view("grid_potential").cpu().numpy().reshape(o.grid_potential.shape),
+                          o.grid_potential.numpy(), X64_RTOL, what="grid_potential")
+    assert int(engines[0].native.view("idx").item()) == 2 * W

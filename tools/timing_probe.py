@@ -7,7 +7,7 @@ import numpy as np, torch
 import bench
 
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
-cases = [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000)]
+cases = [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000), ("walkers", 100_000), ("window", 100_000)]
 for wl, natoms in cases:
     frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
     snaps = bench.snapshots_of(frames, L, 0.005)
