@@ -42,7 +42,7 @@ UNIT = "steps/s"
 # ------------------------------------------------------------------------------------------------------
 # synthetic device snapshots (generated with torch on the device for speed)
 # ------------------------------------------------------------------------------------------------------
-def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, globule=False):
+def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, globule=False, sorted_tags=False):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     L = float((natoms / 0.8) ** (1.0 / 3.0))
@@ -61,7 +61,10 @@ def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, glob
         vm[:, 3] = 1.0 + 15.0 * torch.rand((natoms,), generator=g, device=device, dtype=dtype)
         f = torch.zeros((natoms, 4), device=device, dtype=dtype)
         f[:, :3] = torch.randn((natoms, 3), generator=g, device=device, dtype=dtype)
-        rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32)
+        if sorted_tags:  # a freshly sorted system: tag order == memory order
+            rtag = torch.arange(natoms, device=device, dtype=torch.int32)
+        else:  # random permutation (the worst case for the gathers)
+            rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32)
         img = torch.randint(-1, 2, (natoms, 3), generator=g, device=device, dtype=torch.int32)
         frames.append(dict(positions=pos, vel_mass=vm, forces=f, rtags=rtag, images=img))
     return frames, L, x0
@@ -395,10 +398,12 @@ def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, 
 def run_series(device, stream, hbm):
     """Secondary sizes / configurations (parity-tested elsewhere); short runs, same timing method."""
     out = []
-    for name, natoms, steps in (("harmonic", 10_000, 2000), ("harmonic", 100_000, 2000), ("harmonic", 1_000_000, 500),
-                                ("abf2d", 10_000, 2000), ("abf2d", 1_000_000, 500)):
+    for name, natoms, steps, sorted_tags in (("harmonic", 10_000, 2000, False), ("harmonic", 100_000, 2000, False),
+                                             ("harmonic", 1_000_000, 500, False), ("abf2d", 10_000, 2000, False),
+                                             ("abf2d", 1_000_000, 500, False), ("abf2d", 100_000, 2000, True),
+                                             ("abf2d", 1_000_000, 500, True)):
         nfr = 64 if natoms <= 100_000 else 8
-        frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977)
+        frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977, sorted_tags=sorted_tags)
         snaps = snapshots_of(frames, L, 0.005)
         cvs, m = workload_specs(name, natoms, L)
         method, native = build_ours(cvs, m, snaps[0])
@@ -406,7 +411,7 @@ def run_series(device, stream, hbm):
         info = native.launch_info()
         us = ms * 1e3 / steps
         gbs = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
-        out.append(dict(workload=f"{name} S=N={natoms} hoomd-f32", steps_per_s=round(steps / (ms * 1e-3), 1),
+        out.append(dict(workload=f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), steps_per_s=round(steps / (ms * 1e-3), 1),
                         us_per_step=round(us, 3), algorithmic_bytes=info["algorithmic_bytes_per_step"],
                         achieved_gbs=round(gbs, 1), frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"],
                         distinct_snapshots=nfr))

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-Xcompiler",
     "-fPIC",
-]
+] + os.environ.get("PSB_NVCC_EXTRA", "").split()  # experiments only, e.g. PSB_NVCC_EXTRA=-DPSB_GATHER_CG
 
 
 def _nvcc():

@@ -60,7 +60,7 @@ struct psb_handle {
   size_t dyn_smem = 0;
   int cooperative = 0;
   int step_method = 0;   // StepMethod code of the kernel instantiation
-  int step_general = 0;  // 1: instantiation with non-point CVs / shared atoms / dense outputs / walkers
+  int step_general = 0;  // StepClass code of the kernel instantiation
   long long launches = 0;
   long long host_ncalls = 0;  // mirror of the device ncalls (deterministic)
   long long algo_bytes = 0;
@@ -526,7 +526,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     case PSB_METHOD_ABF: h->step_method = SM_ABF; break;
     default: h->step_method = gridded ? SM_METAD_GRID : SM_METAD_DIRECT; break;
   }
-  h->step_general = (!M.all_point || !M.all_unique || layout->dense_outputs) ? 1 : 0;
+  h->step_general = (!M.all_point || !M.all_unique || layout->dense_outputs) ? SC_GENERAL : SC_POINT;
   const int occ = pick_vtable(*layout)->occupancy(h->step_method, h->step_general, h->dyn_smem);
   if (occ < 1)
     return bail(fail(PSB_ERR_CUDA, "step kernel cannot be made resident (%s)", cudaGetErrorString(cudaGetLastError())));
@@ -547,7 +547,29 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   if (want > 1) want = std::max<long long>(want, ng);
   if (want > max_blocks) return bail(fail(PSB_ERR_CUDA, "device too small for %d atom groups", ng));
   h->grid = (int)want;
-  if (h->grid > 1) {
+  // slot-ordered gather/scatter (psb_step.cuh): worth it when most atoms are selected and the terms do
+  // not fit the register cache; PSB_SLOT_MAJOR=1 forces it wherever it is valid (tests), =0 disables it
+  {
+    const bool eligible = h->grid > 1 && !h->step_general && !method->shared_hills && ng <= 4 &&
+                          layout->natoms < 0xFFFFFFF0LL;
+    bool wanted = (long long)M.T > (long long)CT * BLOCK * h->grid && 2LL * M.T >= layout->natoms;
+    if (const char* env = getenv("PSB_SLOT_MAJOR")) wanted = atoi(env) != 0;
+    M.slot_major = (eligible && wanted) ? 1 : 0;
+    if (M.slot_major &&
+        (long long)pick_vtable(*layout)->occupancy(h->step_method, SC_SLOT, h->dyn_smem) * h->num_sms < h->grid)
+      M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
+    if (M.slot_major) {
+      h->step_general = SC_SLOT;
+      psb_status st = dev_alloc(h, &M.slot_map, (size_t)layout->natoms);
+      if (st != PSB_OK) return bail(st);
+    }
+  }
+  if (h->grid > 1 && M.slot_major) {
+    for (int g = 0; g < MAXG; ++g) {
+      M.cta_lo[g] = 0;
+      M.cta_hi[g] = g < ng ? h->grid - 1 : -1;
+    }
+  } else if (h->grid > 1) {
     // smallest per-CTA term count whose group-aligned split fits the grid
     auto ctas_needed = [&](long long per) {
       long long n = 0;
@@ -556,10 +578,13 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     };
     long long per = std::max(1LL, ((long long)M.T + h->grid - 1) / h->grid);
     while (ctas_needed(per) > h->grid) per += std::max(1LL, per / 64);
-    M.cta_first[0] = 0;
-    for (int g = 0; g < ng; ++g)
-      M.cta_first[g + 1] = M.cta_first[g] + (int)(((long long)(M.grp[g].t1 - M.grp[g].t0) + per - 1) / per);
-    for (int g = ng; g < MAXG; ++g) M.cta_first[g + 1] = M.cta_first[ng];
+    int first = 0;
+    for (int g = 0; g < MAXG; ++g) {
+      const int n = g < ng ? (int)(((long long)(M.grp[g].t1 - M.grp[g].t0) + per - 1) / per) : 0;
+      M.cta_lo[g] = first;
+      M.cta_hi[g] = first + n - 1;
+      first += n;
+    }
   }
   {
     const bool momenta_sums = layout->need_momenta && M.abf_fast;

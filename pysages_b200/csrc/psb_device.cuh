@@ -122,7 +122,7 @@ struct BarrierState {
   unsigned long long pad[15];  // one counter per 128-byte line
 };
 
-enum { BAR_A = 0, BAR_B = 1, BAR_C = 2, BAR_H = 3, BAR_D = 4, BAR_READERS = 5, BAR_PRE_D = 6, NBARS = 8 };
+enum { BAR_A = 0, BAR_B = 1, BAR_C = 2, BAR_H = 3, BAR_D = 4, BAR_READERS = 5, BAR_PRE_D = 6, BAR_SLOT = 7, NBARS = 8 };
 
 struct Model {
   int32_t ncv, k, ngroups, all_unique;
@@ -133,7 +133,10 @@ struct Model {
   CvDev cv[MAXCV];
   GroupDev grp[MAXG];
   int32_t comp_cv[MAXK];      // CV owning component c
-  int32_t cta_first[MAXG + 1];     // gridDim.x > 1: CTAs [cta_first[g], cta_first[g+1]) gather group g
+  int32_t cta_lo[MAXG], cta_hi[MAXG];  // gridDim.x > 1: CTAs cta_lo[g] .. cta_hi[g] hold partial sums of group g
+  int32_t slot_major;         // gather / scatter in slot order through slot_map (most atoms selected)
+  int32_t pad1;
+  uint32_t* slot_map;         // (N) slot -> (launch stamp << 4 | group + 1), rewritten every launch
   int32_t row_first[2][MAXG + 1];  // prefix of accumulator rows per group, pass A / pass B
   uint32_t ov[MAXG][MAXG];    // group overlap counts (ABF fast path)
   const uint32_t* term_tag;   // (T)
@@ -194,12 +197,21 @@ struct Real4<float> { using type = float4; };
 template <>
 struct Real4<double> { using type = double4; };
 
+#ifdef PSB_GATHER_CG
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+#else
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ double4 ldg4(const double4* p) {
   const double2 a = __ldg(reinterpret_cast<const double2*>(p));
   const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
   return make_double4(a.x, a.y, b.x, b.y);
 }
+#endif
 
 // plain (coherent) 16/32-byte accesses for the force array
 __device__ __forceinline__ float4 ld4(const float4* p) { return *p; }

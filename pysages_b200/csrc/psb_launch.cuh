@@ -8,8 +8,7 @@
 namespace psb {
 
 struct StepVTable {
-  // `method` is a StepMethod code, `general` selects the instantiation that also handles
-  // non-point CVs, shared atoms, dense outputs and walkers (psb_step.cuh)
+  // `method` is a StepMethod code, `general` a StepClass code (psb_step.cuh)
   cudaError_t (*launch_step)(int method, int general, const Model* M, const Snap* S, int grid, size_t dyn_smem,
                              cudaStream_t stream);
   int (*occupancy)(int method, int general, size_t dyn_smem);
@@ -33,21 +32,23 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
     vt_plain3_f32, vt_plain3_f64;
 
 // kernel entry points of one (layout, dtype): [method][general]
-#define PSB_STEP_ROW(L, R, M) {(const void*)step_kernel<L, R, M, false>, (const void*)step_kernel<L, R, M, true>}
+#define PSB_STEP_ROW(L, R, M)                                                                     \
+  {(const void*)step_kernel<L, R, M, SC_POINT>, (const void*)step_kernel<L, R, M, SC_GENERAL>,    \
+   (const void*)step_kernel<L, R, M, SC_SLOT>}
 #define PSB_DEFINE_STEP_VTABLE(NAME, L, R)                                                          \
-  static const void* const NAME##_entry[SM_COUNT][2] = {                                            \
+  static const void* const NAME##_entry[SM_COUNT][SC_COUNT] = {                                            \
       PSB_STEP_ROW(L, R, SM_UNBIASED), PSB_STEP_ROW(L, R, SM_HARMONIC), PSB_STEP_ROW(L, R, SM_METAD_DIRECT), \
       PSB_STEP_ROW(L, R, SM_ABF), PSB_STEP_ROW(L, R, SM_METAD_GRID)};                               \
   static cudaError_t NAME##_launch(int method, int general, const Model* M, const Snap* S, int grid, \
                                    size_t smem, cudaStream_t stream) {                              \
     void* args[] = {(void*)&M, (void*)S}; /* M: device pointer, S: by value */                     \
-    const void* fn = NAME##_entry[method][general ? 1 : 0];                                         \
+    const void* fn = NAME##_entry[method][general];                                         \
     if (grid > 1) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(BLOCK), args, smem, stream); \
     return cudaLaunchKernel(fn, dim3(1), dim3(BLOCK), args, smem, stream);                          \
   }                                                                                                 \
   static int NAME##_occupancy(int method, int general, size_t smem) {                               \
     int occ = 0;                                                                                    \
-    const void* fn = NAME##_entry[method][general ? 1 : 0];                                         \
+    const void* fn = NAME##_entry[method][general];                                         \
     if (smem > 0 &&                                                                                 \
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
       return 0;                                                                                     \

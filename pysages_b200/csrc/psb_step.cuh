@@ -36,6 +36,10 @@ constexpr int CT = 4;  // terms per thread kept in registers (slot, position, pr
 // path inside the instruction cache.  GENERAL = false: only point CVs (Component ... Dihedral),
 // no atom shared between groups, no dense outputs, no walkers.
 enum StepMethod { SM_UNBIASED = 0, SM_HARMONIC = 1, SM_METAD_DIRECT = 2, SM_ABF = 3, SM_METAD_GRID = 4, SM_COUNT = 5 };
+// SC_POINT: the fast class above; SC_GENERAL: everything; SC_SLOT: the fast class with the slot-ordered
+// gather / scatter (most atoms of a very large system selected), kept in its own instantiation so its
+// register and code footprint stay out of the latency-critical kernels.
+enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_COUNT = 3 };
 
 // ---- small device utilities -----------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -178,8 +182,8 @@ __device__ __forceinline__ RowPlan row_plan(const Model& M, int pass, int vrows,
     int g = 0;
     while (r >= M.row_first[pass][g + 1]) ++g;
     p.dst = g * NACC + (r - M.row_first[pass][g]);
-    p.blo = M.cta_first[g];
-    p.bhi = M.cta_first[g + 1] - 1;
+    p.blo = M.cta_lo[g];
+    p.bhi = M.cta_hi[g];
   } else {
     p.dst = VGROUP * NACC + r;
     p.blo = 0;
@@ -692,9 +696,11 @@ __device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
-template <int LAYOUT, typename Real, int METHOD, bool GENERAL>
+template <int LAYOUT, typename Real, int METHOD, int CLASS>
 __global__ void __launch_bounds__(BLOCK, 2)
 step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
+  constexpr bool GENERAL = (CLASS == SC_GENERAL);
+  constexpr bool SLOT = (CLASS == SC_SLOT);
   using A = Access<LAYOUT, Real>;
   using FV = typename A::FV;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -730,8 +736,9 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   const bool all_unique = !GENERAL || M.all_unique;
   const bool abf_fast = is_abf && (!GENERAL || M.abf_fast);
   const bool need_term_slot = (GENERAL || WALK) && M.need_term_slot;
-  const bool skip_cv = WALK && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
+  const bool skip_cv = WALK && !SLOT && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
   const bool momenta_sums = S.need_momenta && abf_fast;
+  constexpr bool slot_major = SLOT;  // the host picks this instantiation only for multi-CTA, non-walker handles
   const bool will_scatter = (METHOD != SM_UNBIASED) &&
                             (S.mode == MODE_STEP || (WALK && S.mode == MODE_WALKER_FINISH));
 
@@ -793,23 +800,26 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   int seg_g = -1;
   uint32_t lo = 0, hi = 0;
   if (!skip_cv) {
-    if (nb > 1) {
+    if (slot_major) {
+      // no per-CTA group: handled by the slot-ordered passes below
+    } else if (nb > 1) {
       for (int g = 0; g < M.ngroups; ++g)
-        if (b >= M.cta_first[g] && b < M.cta_first[g + 1]) seg_g = g;
+        if (b >= M.cta_lo[g] && b <= M.cta_hi[g]) seg_g = g;
       if (seg_g >= 0) {
         const GroupDev& G = M.grp[seg_g];
-        const uint32_t nc = (uint32_t)(M.cta_first[seg_g + 1] - M.cta_first[seg_g]);
+        const uint32_t nc = (uint32_t)(M.cta_hi[seg_g] - M.cta_lo[seg_g] + 1);
         const uint32_t per = (G.t1 - G.t0 + nc - 1) / nc;
-        lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_first[seg_g]) * per);
+        lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_lo[seg_g]) * per);
         hi = min(G.t1, lo + per);
       }
     } else {
       hi = M.T;
     }
   }
-  const bool cached = !skip_cv && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
-  const int g_begin = skip_cv ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
-  const int g_end = skip_cv ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
+  const bool cached = !skip_cv && !slot_major && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
+  const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
+  const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
+  uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
   uint32_t cslot[CT];
   int cg[CT];
   V3 cr[CT], cp[CT];
@@ -839,6 +849,93 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         }
       }
     }
+    // ---- slot-major gather (most atoms selected, too many to keep in registers) ---------------
+    // A random tag -> slot permutation makes the tag-ordered gather pay one L1 tag lookup per
+    // 16-byte row (measured: ~6 lookups per atom, 1 lookup/clk/SM -> 20 us per 1e6 atoms, far
+    // below HBM speed).  Instead: pass 0 scatters one word per selected atom into slot_map
+    // (stamp | group), and the gather and the force update then stream positions, images,
+    // velocities and forces in SLOT order, fully coalesced.  At most 4 groups (fast-class only).
+    if (slot_major) {
+      __syncthreads();  // sh.epoch
+      stamp = ((uint32_t)(sh.epoch[BAR_SLOT] + 1ULL) & 0x0FFFFFFFu) << 4;
+      const uint32_t chunk0 = (M.T + nb - 1) / nb;
+      const uint32_t q0 = min(M.T, (uint32_t)b * chunk0), q1 = min(M.T, q0 + chunk0);
+      // group of a term and its tag without branches (<= 4 groups): bounds and range starts in registers
+      uint32_t gb[3], gt0[4], gtag0[4];
+      bool all_contig = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = j < M.ngroups;
+        if (j < 3) gb[j] = (j < M.ngroups - 1) ? M.grp[j].t1 : 0xFFFFFFFFu;
+        gt0[j] = ok ? M.grp[j].t0 : 0u;
+        gtag0[j] = ok ? M.grp[j].tag0 : 0u;
+        all_contig = all_contig && (!ok || M.grp[j].contig);
+      }
+      for (uint32_t base = q0 + tid; base < q1; base += 8 * BLOCK) {
+        uint32_t slot[8], word[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t t = min(base + u * BLOCK, q1 - 1);  // clamped: loads stay unconditional
+          const int g = (int)(t >= gb[0]) + (int)(t >= gb[1]) + (int)(t >= gb[2]);
+          const uint32_t t0g = g == 0 ? gt0[0] : (g == 1 ? gt0[1] : (g == 2 ? gt0[2] : gt0[3]));
+          const uint32_t tg0 = g == 0 ? gtag0[0] : (g == 1 ? gtag0[1] : (g == 2 ? gtag0[2] : gtag0[3]));
+          const uint32_t tag = all_contig ? tg0 + (t - t0g) : __ldg(M.term_tag + t);
+          slot[u] = A::slot(S, M, tag);
+          word[u] = stamp | (uint32_t)(g + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (base + u * BLOCK < q1) M.slot_map[slot[u]] = word[u];
+      }
+      PSB_STAMP(7);
+      grid_sync(M, sh, BAR_SLOT);
+      const uint32_t N = (uint32_t)M.natoms;
+      uint32_t schunk = (N + nb - 1) / nb;
+      schunk = (schunk + 31u) & ~31u;  // warp-aligned slices
+      s_lo = min(N, (uint32_t)b * schunk);
+      s_hi = min(N, s_lo + schunk);
+      double acc4[4][6];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc4[g][a] = 0.0;
+      // SU independent rows per thread in flight: every load is issued before the first use (rows of
+      // unselected slots are loaded too -- they exist, and almost every slot is selected here)
+      constexpr int SU = 4;
+      for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
+        uint32_t e[SU];
+        V3 r[SU], p[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const uint32_t sl = min(base + u * BLOCK, s_hi - 1);  // clamped: no branch around the loads
+          e[u] = __ldcg(M.slot_map + sl);
+          r[u] = A::position(S, sl);
+          p[u] = momenta_sums ? A::momentum(S, sl) : v3(0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const bool hit = (base + u * BLOCK < s_hi) && ((e[u] & ~15u) == stamp);
+          const int g = hit ? (int)(e[u] & 15u) - 1 : -1;
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {  // branch-free select: lanes of a warp hold different groups
+            const double w = (g == gg) ? 1.0 : 0.0;
+            acc4[gg][0] = fma(w, r[u].x, acc4[gg][0]);
+            acc4[gg][1] = fma(w, r[u].y, acc4[gg][1]);
+            acc4[gg][2] = fma(w, r[u].z, acc4[gg][2]);
+            if (momenta_sums) {
+              acc4[gg][3] = fma(w, p[u].x, acc4[gg][3]);
+              acc4[gg][4] = fma(w, p[u].y, acc4[gg][4]);
+              acc4[gg][5] = fma(w, p[u].z, acc4[gg][5]);
+            }
+          }
+        }
+      }
+      const int na = momenta_sums ? 6 : 3;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < M.ngroups) block_reduce_store(sh, acc4[g], na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+    }
+
     for (int g = g_begin; g < g_end; ++g) {
       const GroupDev& G = M.grp[g];
       const CvDev& cv = M.cv[G.cv];
@@ -1127,7 +1224,27 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   if (will_scatter) {
     const Fin& f = sh.fin;
     const bool dense = GENERAL && (M.bias_dense != nullptr);
-    if (all_unique && !dense) {
+    if (slot_major) {
+      constexpr int SU = 4;
+      for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
+        uint32_t e[SU];
+        FV fv[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const uint32_t sl = min(base + u * BLOCK, s_hi - 1);
+          e[u] = __ldcg(M.slot_map + sl);
+          fv[u] = A::load_force(S, sl);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const uint32_t sl = base + u * BLOCK;
+          if (sl < s_hi && (e[u] & ~15u) == stamp) {
+            const int g = (int)(e[u] & 15u) - 1;
+            A::store_force(S, sl, fv[u], v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]));
+          }
+        }
+      }
+    } else if (all_unique && !dense) {
       if (cached) {
 #pragma unroll
         for (int i = 0; i < CT; ++i) {

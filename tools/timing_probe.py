@@ -7,7 +7,7 @@ import numpy as np, torch
 import bench
 
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
-cases = [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000), ("walkers", 100_000), ("window", 100_000)]
+cases = [tuple([c.split(":")[0], int(c.split(":")[1])]) for c in sys.argv[1:]] or [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000), ("walkers", 100_000), ("window", 100_000)]
 for wl, natoms in cases:
     frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
     snaps = bench.snapshots_of(frames, L, 0.005)
@@ -25,8 +25,10 @@ for wl, natoms in cases:
     rel = lambda x: (x - t0) / 1e3
     print(f"{wl} N={natoms} grid={g} us/step={ms*1e3/200:.2f}   gap (prev kernel last stamp -> this kernel first stamp) = {(t0 - prev[:, 6].max())/1e3:.2f} us;"
           f" period by stamps = {(t0 - prev[:, 0].min())/1e3:.2f} us")
-    names = ["start", "passA done", "barrier passed", "finalize done", "scatter start", "scatter end", "kernel end"]
+    names = ["start", "passA done", "barrier passed", "finalize done", "scatter start", "scatter end", "kernel end", "pass0 done (slot-major)"]
     for i, nme in enumerate(names):
+        if i == 7 and t[:, 7].max() < t0:
+            continue
         col = rel(t[:, i])
         print(f"  {nme:15s}: min {col.min():6.2f} median {np.median(col):6.2f} max {col.max():6.2f}")
     c = t[0, 8:16]
