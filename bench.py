@@ -54,8 +54,11 @@ def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, glob
     cur = x0
     for _ in range(nframes):
         cur = cur + 0.02 * torch.randn((natoms, 3), generator=g, device=device, dtype=torch.float64)
+        img = torch.randint(-1, 2, (natoms, 3), generator=g, device=device, dtype=torch.int32)
         pos = torch.zeros((natoms, 4), device=device, dtype=dtype)
-        pos[:, :3] = cur.to(dtype)
+        # the globule is one connected object: stored positions are wrapped so that unwrapping with the
+        # image flags (hoomd.py:179-181) recovers it; the liquid-like configurations keep SURVEY 8d's spec
+        pos[:, :3] = (cur - L * img.to(torch.float64)).to(dtype) if globule else cur.to(dtype)
         vm = torch.empty((natoms, 4), device=device, dtype=dtype)
         vm[:, :3] = torch.randn((natoms, 3), generator=g, device=device, dtype=dtype)
         vm[:, 3] = 1.0 + 15.0 * torch.rand((natoms,), generator=g, device=device, dtype=dtype)
@@ -65,7 +68,6 @@ def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, glob
             rtag = torch.arange(natoms, device=device, dtype=torch.int32)
         else:  # random permutation (the worst case for the gathers)
             rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32)
-        img = torch.randint(-1, 2, (natoms, 3), generator=g, device=device, dtype=torch.int32)
         frames.append(dict(positions=pos, vel_mass=vm, forces=f, rtags=rtag, images=img))
     return frames, L, x0
 
@@ -395,28 +397,93 @@ def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, 
                 windows_gathered=int(means.shape[0]))
 
 
+def cfg4_case(device, natoms=50_000, H=100_000):
+    """cfg4: RMSD + RadiusOfGyration over a compact globule, metadynamics with H pre-filled hills."""
+    frames, L, x0 = device_hoomd_frames(natoms, 16, device, seed=20240 + 4000, globule=True)
+    gen = np.random.Generator(np.random.PCG64(20240 + 4000))
+    q, _ = np.linalg.qr(gen.normal(size=(3, 3)))
+    ref = (x0.cpu().numpy() @ q.T + gen.normal(scale=0.1, size=(natoms, 3)))
+    allatoms = list(range(natoms))
+    cvs4 = [("RMSD", (allatoms, ref), {}), ("RadiusOfGyration", (allatoms,), {})]
+
+    def prefill(native):
+        native.evaluate(snapshots_of(frames[:1], L, 0.005)[0])
+        torch.cuda.synchronize()
+        xi = native.view("xi").cpu().numpy().ravel()[:2]
+        span = np.maximum(np.abs(xi) * 0.4, 1e-3)
+        heights = gen.uniform(0.5, 1.2, H); heights[-8:] = 0.0
+        centers = xi + gen.uniform(-0.5, 0.5, size=(H, 2)) * span
+        native.set_state("heights", heights)
+        native.set_state("centers", centers)
+        native.set_state("idx", np.array([H - 8], dtype=np.int64))
+
+    md = dict(height=1.0, sigma=[0.05, 0.5], stride=500, ngaussians=H)
+    return frames, L, cvs4, md, prefill
+
+
 def run_series(device, stream, hbm):
     """Secondary sizes / configurations (parity-tested elsewhere); short runs, same timing method."""
     out = []
+
+    def measure(label, name, natoms, steps, frames, L, extra=None, specs=None):
+        snaps = snapshots_of(frames, L, 0.005)
+        cvs, m = specs if specs is not None else workload_specs(name, natoms, L)
+        method, native = build_ours(cvs, m, snaps[0])
+        if extra is not None:
+            extra(native)
+        ms, launches = time_cycle(native, snapdesc_array(native, snaps), steps, 20, stream)
+        info = native.launch_info()
+        us = ms * 1e3 / steps
+        gbs = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
+        row = dict(workload=label, steps_per_s=round(steps / (ms * 1e-3), 1), us_per_step=round(us, 3),
+                   algorithmic_bytes=info["algorithmic_bytes_per_step"], achieved_gbs=round(gbs, 1),
+                   frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"], launches_per_step=round(launches / steps, 2),
+                   distinct_snapshots=len(frames))
+        out.append(row)
+        del snaps, native, method
+        torch.cuda.empty_cache()
+        return row
+
     for name, natoms, steps, sorted_tags in (("harmonic", 10_000, 2000, False), ("harmonic", 100_000, 2000, False),
                                              ("harmonic", 1_000_000, 500, False), ("abf2d", 10_000, 2000, False),
                                              ("abf2d", 1_000_000, 500, False), ("abf2d", 100_000, 2000, True),
                                              ("abf2d", 1_000_000, 500, True)):
         nfr = 64 if natoms <= 100_000 else 8
         frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977, sorted_tags=sorted_tags)
-        snaps = snapshots_of(frames, L, 0.005)
-        cvs, m = workload_specs(name, natoms, L)
-        method, native = build_ours(cvs, m, snaps[0])
-        ms, _ = time_cycle(native, snapdesc_array(native, snaps), steps, 20, stream)
-        info = native.launch_info()
-        us = ms * 1e3 / steps
-        gbs = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
-        out.append(dict(workload=f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), steps_per_s=round(steps / (ms * 1e-3), 1),
-                        us_per_step=round(us, 3), algorithmic_bytes=info["algorithmic_bytes_per_step"],
-                        achieved_gbs=round(gbs, 1), frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"],
-                        distinct_snapshots=nfr))
-        del frames, snaps, native, method
-        torch.cuda.empty_cache()
+        measure(f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), name, natoms, steps, frames, L)
+        del frames
+
+    # cfg1: alanine-dipeptide-sized well-tempered metadynamics on two dihedrals (latency only)
+    frames, L, _ = device_hoomd_frames(22, 64, device, seed=20240 + 1000, dtype=torch.float64)
+    pi = float(np.pi)
+    dih = [("DihedralAngle", ([4, 6, 8, 14],), {}), ("DihedralAngle", ([6, 8, 14, 16],), {})]
+    wt = dict(height=1.2, sigma=[0.35, 0.35], stride=500, ngaussians=64, deltaT=5000.0, kB=0.0083144626)
+    measure("cfg1 WT-metad (phi,psi) N=22 f64, direct hill sum (64 slots)", None, 22, 4000, frames, L,
+            specs=(dih, ("Metadynamics", dict(wt))))
+    measure("cfg1 WT-metad (phi,psi) N=22 f64, periodic 50x50 grid", None, 22, 4000, frames, L,
+            specs=(dih, ("Metadynamics", dict(wt, grid=((-pi, -pi), (pi, pi), (50, 50), "periodic")))))
+    del frames
+
+    # cfg3: pairwise coordination number between two groups of 10 000 atoms in a 1M-atom system
+    natoms = 1_000_000
+    frames, L, _ = device_hoomd_frames(natoms, 4, device, seed=20240 + 3000)
+    gen = np.random.Generator(np.random.PCG64(20240 + 3000))
+    tags = gen.permutation(natoms)[:20_000]
+    ga, gb = sorted(tags[:10_000].tolist()), sorted(tags[10_000:].tolist())
+    row = measure("cfg3 CoordinationNumber 10k x 10k (1e8 pairs), HarmonicBias, N=1e6 hoomd-f32", None, natoms, 100, frames, L,
+                  specs=([("CoordinationNumber", ([ga, gb],), dict(r0=1.0))], ("HarmonicBias", dict(kspring=10.0, center=[100.0]))))
+    row["pair_gflops"] = round(32 * 1e8 / (row["us_per_step"] * 1e-6) / 1e9, 1)  # 32 flop/pair canonical count (SURVEY 8d)
+    row["note"] = "FP64-pipe bound pair kernel + gather + step kernel; frac_of_hbm is not the relevant roofline here"
+    del frames
+
+    # cfg4: RMSD + RadiusOfGyration over a 50k-atom globule, metadynamics with 1e5 pre-filled hills
+    natoms = 50_000
+    frames, L, cvs4, md, prefill = cfg4_case(device)
+    measure("cfg4 RMSD + RoG over 50k atoms, metadynamics direct sum over 1e5 hills", None, natoms, 500, frames, L,
+            extra=prefill, specs=(cvs4, ("Metadynamics", dict(md))))
+    measure("cfg4 RMSD + RoG over 50k atoms, metadynamics on a 256x256 grid", None, natoms, 1000, frames, L,
+            specs=(cvs4, ("Metadynamics", dict(md, grid=((0.0, 0.0), (40.0, 4000.0), (256, 256), "regular")))))
+    del frames
     return out
 
 

@@ -201,7 +201,7 @@ PSB_HD_COLD void jacobi_eig(int n, double* a, double* v) {
         if (i != j) off += a[i * 4 + j] * a[i * 4 + j];
         else diag += a[i * 4 + j] * a[i * 4 + j];
       }
-    if (off <= 1e-60 * diag || off == 0.0) break;
+    if (off <= 1e-36 * diag || off == 0.0) break;  // |off|_F <= 1e-18 |diag|_F: below fp64 resolution
     for (int p = 0; p < n - 1; ++p)
       for (int q = p + 1; q < n; ++q) {
         double apq = a[p * 4 + q];
@@ -229,10 +229,10 @@ PSB_HD_COLD void jacobi_eig(int n, double* a, double* v) {
 }
 
 // orientation.py:33-73 (Kabsch with the reflection fix): the proper rotation U (row-vector
-// convention, P @ U ~ Q) maximising tr(U^T C), C = P^T Q (row-major c[9]).  Computed with Horn's
+// convention, P @ U ~ Q) maximising tr(U^T C), C = P^T Q (row-major c[9]).  General path: Horn's
 // quaternion eigenproblem (4x4 symmetric, Jacobi), which yields the same U as
 // V diag(1,1,sign(det V det W)) W from the SVD whenever the optimum is unique.
-PSB_HD_COLD void kabsch_rotation(const double* c, double* U) {
+PSB_HD_COLD void kabsch_rotation_eig(const double* c, double* U) {
   const double Sxx = c[0], Sxy = c[1], Sxz = c[2];
   const double Syx = c[3], Syy = c[4], Syz = c[5];
   const double Szx = c[6], Szy = c[7], Szz = c[8];
@@ -258,6 +258,93 @@ PSB_HD_COLD void kabsch_rotation(const double* c, double* U) {
                  2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3};
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) U[i * 3 + j] = R[j * 3 + i];
+}
+
+// Fast path: the orthogonal polar factor X of C (C = X H, H symmetric positive semi-definite,
+// X = V W from the SVD) by the scaled Newton iteration X <- (g X + X^-T / g) / 2,
+// g = sqrt(|X^-1|_F / |X|_F) (Higham): quadratic convergence, ~6 iterations of straight-line 3x3
+// arithmetic in registers instead of several Jacobi sweeps over a 4x4 matrix in local memory (the
+// finalizer runs this in ONE thread per CTA, on the critical path of every step).
+//   det C > 0: U = X.
+//   det C < 0: the reflection fix of orientation.py:66-71 flips the direction of the smallest
+//              singular value: U = V diag(1,1,-1) W = X (I - 2 w w^T), w = eigenvector of
+//              H = X^T C for its smallest eigenvalue (closed-form symmetric 3x3 eigenvalue,
+//              eigenvector from the best-conditioned cross product of rows of H - lambda I).
+// Rank-deficient / badly conditioned covariances, a (near-)degenerate smallest singular value or a
+// non-converging iteration take the eigen path above.
+PSB_HD void kabsch_rotation(const double* c, double* U) {
+  double x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], x4 = c[4], x5 = c[5], x6 = c[6], x7 = c[7], x8 = c[8];
+  const double fro2 = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3 + x4 * x4 + x5 * x5 + x6 * x6 + x7 * x7 + x8 * x8;
+  const double det0 = x0 * (x4 * x8 - x5 * x7) - x1 * (x3 * x8 - x5 * x6) + x2 * (x3 * x7 - x4 * x6);
+  bool ok = fabs(det0) > 1e-6 * fro2 * sqrt(fro2) && fro2 > 0.0;  // sigma_min / sigma_max >~ 1e-6
+  bool converged = false;
+  for (int it = 0; ok && it < 16; ++it) {
+    // adjugate^T / det = X^-T
+    const double a0 = x4 * x8 - x5 * x7, a1 = x5 * x6 - x3 * x8, a2 = x3 * x7 - x4 * x6;
+    const double a3 = x2 * x7 - x1 * x8, a4 = x0 * x8 - x2 * x6, a5 = x1 * x6 - x0 * x7;
+    const double a6 = x1 * x5 - x2 * x4, a7 = x2 * x3 - x0 * x5, a8 = x0 * x4 - x1 * x3;
+    const double det = x0 * a0 + x1 * a1 + x2 * a2;
+    if (det == 0.0 || (det > 0.0) != (det0 > 0.0)) break;
+    const double id = 1.0 / det;
+    const double nx = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3 + x4 * x4 + x5 * x5 + x6 * x6 + x7 * x7 + x8 * x8;
+    const double na = (a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7 + a8 * a8) * id * id;
+    const double g = sqrt(sqrt(na / nx));  // sqrt(|X^-1|_F / |X|_F)
+    const double p = 0.5 * g, q = 0.5 * id / g;
+    const double y0 = p * x0 + q * a0, y1 = p * x1 + q * a1, y2 = p * x2 + q * a2;
+    const double y3 = p * x3 + q * a3, y4 = p * x4 + q * a4, y5 = p * x5 + q * a5;
+    const double y6 = p * x6 + q * a6, y7 = p * x7 + q * a7, y8 = p * x8 + q * a8;
+    const double d2 = (y0 - x0) * (y0 - x0) + (y1 - x1) * (y1 - x1) + (y2 - x2) * (y2 - x2) + (y3 - x3) * (y3 - x3) +
+                      (y4 - x4) * (y4 - x4) + (y5 - x5) * (y5 - x5) + (y6 - x6) * (y6 - x6) + (y7 - x7) * (y7 - x7) +
+                      (y8 - x8) * (y8 - x8);
+    x0 = y0; x1 = y1; x2 = y2; x3 = y3; x4 = y4; x5 = y5; x6 = y6; x7 = y7; x8 = y8;
+    if (d2 <= 1e-30) {  // |X_k+1 - X_k|_F <= 1e-15 with |X|_F = sqrt(3): converged (quadratically)
+      converged = true;
+      break;
+    }
+  }
+  if (converged && det0 > 0.0) {
+    U[0] = x0; U[1] = x1; U[2] = x2; U[3] = x3; U[4] = x4; U[5] = x5; U[6] = x6; U[7] = x7; U[8] = x8;
+    return;
+  }
+  if (converged) {  // improper polar factor: reflect the direction of the smallest singular value
+    // H = X^T C (symmetric)
+    const double h00 = x0 * c[0] + x3 * c[3] + x6 * c[6], h01 = x0 * c[1] + x3 * c[4] + x6 * c[7];
+    const double h02 = x0 * c[2] + x3 * c[5] + x6 * c[8], h11 = x1 * c[1] + x4 * c[4] + x7 * c[7];
+    const double h12 = x1 * c[2] + x4 * c[5] + x7 * c[8], h22 = x2 * c[2] + x5 * c[5] + x8 * c[8];
+    const double p1 = h01 * h01 + h02 * h02 + h12 * h12;
+    const double qm = (h00 + h11 + h22) / 3.0;
+    const double p2 = (h00 - qm) * (h00 - qm) + (h11 - qm) * (h11 - qm) + (h22 - qm) * (h22 - qm) + 2.0 * p1;
+    const double pp = sqrt(p2 / 6.0);
+    if (pp > 0.0) {
+      const double b00 = (h00 - qm) / pp, b11 = (h11 - qm) / pp, b22 = (h22 - qm) / pp;
+      const double b01 = h01 / pp, b02 = h02 / pp, b12 = h12 / pp;
+      double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+      r = fmin(1.0, fmax(-1.0, r));
+      const double phi = acos(r) / 3.0;
+      const double lam = qm + 2.0 * pp * cos(phi + 2.0943951023931953);  // smallest eigenvalue
+      // rows of H - lam I; the eigenvector is orthogonal to all of them
+      const double r00 = h00 - lam, r11 = h11 - lam, r22 = h22 - lam;
+      const double ax = h01 * h12 - h02 * r11, ay = h02 * h01 - r00 * h12, az = r00 * r11 - h01 * h01;   // row0 x row1
+      const double bx = h01 * r22 - h02 * h12, by = h02 * h02 - r00 * r22, bz = r00 * h12 - h01 * h02;   // row0 x row2
+      const double cx = r11 * r22 - h12 * h12, cy = h12 * h02 - h01 * r22, cz = h01 * h12 - r11 * h02;   // row1 x row2
+      const double na2 = ax * ax + ay * ay + az * az, nb2 = bx * bx + by * by + bz * bz, nc2 = cx * cx + cy * cy + cz * cz;
+      double wx = ax, wy = ay, wz = az, nw = na2;
+      if (nb2 > nw) { wx = bx; wy = by; wz = bz; nw = nb2; }
+      if (nc2 > nw) { wx = cx; wy = cy; wz = cz; nw = nc2; }
+      const double hs = h00 * h00 + h11 * h11 + h22 * h22 + 2.0 * p1;  // |H|_F^2; cross products scale like |H|^2
+      if (nw > 1e-12 * hs * hs) {  // smallest singular value well separated from the middle one
+        const double inv = 1.0 / sqrt(nw);
+        wx *= inv; wy *= inv; wz *= inv;
+        const double t0 = 2.0 * (x0 * wx + x1 * wy + x2 * wz), t1 = 2.0 * (x3 * wx + x4 * wy + x5 * wz),
+                     t2 = 2.0 * (x6 * wx + x7 * wy + x8 * wz);  // 2 X w
+        U[0] = x0 - t0 * wx; U[1] = x1 - t0 * wy; U[2] = x2 - t0 * wz;
+        U[3] = x3 - t1 * wx; U[4] = x4 - t1 * wy; U[5] = x5 - t1 * wz;
+        U[6] = x6 - t2 * wx; U[7] = x7 - t2 * wy; U[8] = x8 - t2 * wz;
+        return;
+      }
+    }
+  }
+  kabsch_rotation_eig(c, U);
 }
 
 // utils/core.py:128-134 `solve_pos_def(A A^T, A B)`: Cholesky solve of the k x k SPD system

@@ -31,6 +31,7 @@ double hm_dihedral(const double* p, double* g) {
 }
 
 void hm_kabsch(const double* C, double* U) { kabsch_rotation(C, U); }
+void hm_kabsch_eig(const double* C, double* U) { kabsch_rotation_eig(C, U); }
 
 unsigned hm_grid_index(int kind, double x, double lower, double upper, int shape) {
   return grid_index_1d(kind, x, lower, upper, shape);

@@ -29,6 +29,7 @@ def hm():
         getattr(lib, name).restype = ctypes.c_double
         getattr(lib, name).argtypes = [dp, dp]
     lib.hm_kabsch.argtypes = [dp, dp]
+    lib.hm_kabsch_eig.argtypes = [dp, dp]
     lib.hm_grid_index.restype = ctypes.c_uint
     lib.hm_grid_index.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
     lib.hm_mesh_coord.restype = ctypes.c_double
@@ -76,6 +77,48 @@ def test_kabsch_matches_svd_reference(hm, golden):
         Uref = colvars.kabsch(torch.tensor(P), torch.tensor(Q)).numpy()
         assert np.allclose(U, Uref, atol=1e-12)
         assert abs(np.linalg.det(U) - 1) < 1e-12
+
+
+def test_kabsch_polar_fast_path_equals_eigen_path(hm):
+    """Newton polar iteration (fast path) vs Horn's quaternion eigenproblem on well- and badly-
+    conditioned covariances, near-identity rotations, near-planar point sets and large scales."""
+    rng = np.random.default_rng(17)
+    cases = []
+    for n, noise, scale in ((1000, 0.1, 1.0), (1000, 1e-6, 1.0), (50, 1.0, 1e3), (50, 0.3, 1e-4), (2000, 0.05, 30.0)):
+        for _ in range(6):
+            P = scale * rng.normal(size=(n, 3)); P -= P.mean(0)
+            R, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            if np.linalg.det(R) < 0:
+                R[:, 0] *= -1
+            Q = P @ R + scale * noise * rng.normal(size=(n, 3)); Q -= Q.mean(0)
+            cases.append(np.ascontiguousarray(P.T @ Q))
+    for n, noise in ((500, 0.05), (40, 0.5), (3000, 1e-3)):  # improper covariances: reflection fix on the fast path
+        for _ in range(8):
+            P = rng.normal(size=(n, 3)) * rng.uniform(0.5, 2.0, size=3); P -= P.mean(0)
+            R, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            if np.linalg.det(R) > 0:
+                R[:, 0] *= -1
+            Q = P @ R + noise * rng.normal(size=(n, 3)); Q -= Q.mean(0)
+            C = np.ascontiguousarray(P.T @ Q)
+            assert np.linalg.det(C) < 0
+            cases.append(C)
+    for _ in range(20):  # arbitrary full-rank matrices of either handedness
+        cases.append(np.ascontiguousarray(rng.normal(size=(3, 3)) * 10 ** rng.uniform(-3, 3)))
+    flat = rng.normal(size=(200, 3)) * np.array([1.0, 1.0, 1e-5]); flat -= flat.mean(0)  # nearly planar: eigen path
+    cases.append(np.ascontiguousarray(flat.T @ (flat + 1e-7 * rng.normal(size=flat.shape))))
+    cases.append(np.eye(3) * 5.0)
+    for C in cases:
+        U, V = np.zeros((3, 3)), np.zeros((3, 3))
+        hm.hm_kabsch(_ptr(C), _ptr(U))
+        hm.hm_kabsch_eig(_ptr(C), _ptr(V))
+        sv = np.linalg.svd(C, compute_uv=False)
+        if np.linalg.det(C) < 0 and (sv[1] - sv[2]) < 1e-3 * sv[0]:
+            continue  # (near-)degenerate reflection direction: the optimum itself is ill-defined
+        assert np.allclose(U, V, atol=5e-12 * max(1.0, sv[0] / max(sv[1] - sv[2], 1e-300) if np.linalg.det(C) < 0 else 1.0)), np.abs(U - V).max()
+        assert np.allclose(U @ U.T, np.eye(3), atol=1e-13) and abs(np.linalg.det(U) - 1) < 1e-13
+        W, _, Zt = np.linalg.svd(C)
+        if np.linalg.det(W @ Zt) > 0 and np.linalg.cond(C) < 1e5:
+            assert np.allclose(U, W @ Zt, atol=1e-11)
 
 
 def test_kabsch_reflection_case(hm):

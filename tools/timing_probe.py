@@ -9,10 +9,20 @@ import bench
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
 cases = [tuple([c.split(":")[0], int(c.split(":")[1])]) for c in sys.argv[1:]] or [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000), ("walkers", 100_000), ("window", 100_000)]
 for wl, natoms in cases:
-    frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
-    snaps = bench.snapshots_of(frames, L, 0.005)
-    cvs, m = bench.workload_specs(wl, natoms, L)
-    method, native = bench.build_ours(cvs, m, snaps[0])
+    if wl.startswith("cfg4"):
+        frames, L, cvs, md, prefill = bench.cfg4_case(dev)
+        if wl == "cfg4grid":
+            md = dict(md, grid=((0.0, 0.0), (40.0, 4000.0), (256, 256), "regular"))
+        m = ("Metadynamics", md)
+        snaps = bench.snapshots_of(frames, L, 0.005)
+        method, native = bench.build_ours(cvs, m, snaps[0])
+        if wl == "cfg4":
+            prefill(native)
+    else:
+        frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
+        snaps = bench.snapshots_of(frames, L, 0.005)
+        cvs, m = bench.workload_specs(wl, natoms, L)
+        method, native = bench.build_ours(cvs, m, snaps[0])
     descs = bench.snapdesc_array(native, snaps)
     ms, _ = bench.time_cycle(native, descs, 200, 20, stream)
     torch.cuda.synchronize()
