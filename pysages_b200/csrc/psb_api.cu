@@ -595,6 +595,36 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
             M.row_first[pass][g] + (g < ng ? nacc_for_kind(M.cv[M.grp[g].cv].kind, pass, momenta_sums) : 0);
     }
   }
+  // ---- ABF: constant J J^T (see post_cv) ---------------------------------------------------------------
+  if (method->kind == PSB_METHOD_ABF && M.abf_fast && !method->use_pinv) {
+    bool constant = true;
+    for (int c = 0; c < ncvs; ++c) {
+      const int kd = M.cv[c].kind;
+      if (kd != PSB_CV_COMPONENT && kd != PSB_CV_DISTANCE && kd != PSB_CV_DISPLACEMENT) constant = false;
+    }
+    for (int g = 0; g < ng && constant; ++g)
+      for (int g2 = 0; g2 < ng; ++g2)
+        if (M.grp[g].cv != M.grp[g2].cv && M.ov[g][g2]) constant = false;  // atoms shared between CVs
+    if (constant) {
+      double A[16] = {0};
+      for (int c = 0; c < ncvs; ++c) {
+        const CvDev& cv = M.cv[c];
+        double d = M.grp[cv.g0].self_coef;
+        if (cv.ngroups == 2) {  // gradients of the two centroids are opposite unit vectors / +-identity
+          const int g1 = cv.g0, g2 = cv.g0 + 1;
+          d += M.grp[g2].self_coef - 2.0 * (double)M.ov[g1][g2] * M.grp[g1].inv_n * M.grp[g2].inv_n;
+        }
+        for (int j = 0; j < cv.ncomp; ++j) A[(cv.comp0 + j) * 4 + cv.comp0 + j] = d;
+      }
+      bool ok = true;  // diagonal by construction (no cross-CV overlap): invert entry by entry
+      for (int a = 0; a < k; ++a) ok = ok && A[a * 4 + a] > 1e-300;
+      if (ok) {
+        M.jjt_const = 1;
+        for (int a = 0; a < k; ++a) M.jjt_inv[a * 4 + a] = 1.0 / A[a * 4 + a];
+      }
+    }
+    if (getenv("PSB_NO_CONST_JJT")) M.jjt_const = 0;
+  }
   h->cooperative = h->grid > 1;
   if (h->cooperative) {
     int coop = 0;

@@ -102,6 +102,8 @@ struct Fin {
   double Jp[MAXK];          // ABF: J p
   double Wp[MAXK];          // ABF: solve(J J^T, J p)
   double Fsum_new[MAXK];    // ABF: Fsum[I] after this step's scatter-add
+  double Fsum_old[MAXK];    // ABF: Fsum[I] as gathered (helper warp)
+  unsigned long long hist_old;  // ABF: hist[I] as gathered (helper warp)
   long long flat;           // clamped flat grid offset of xi
   long long nh;             // number of hills summed this step
   uint32_t I[PSB_MAX_GRID_DIMS];
@@ -151,7 +153,8 @@ struct Model {
   BarrierState* bars;         // (NBARS) monotonic arrival counters
   unsigned long long* epochs; // (NBARS) completed uses of each barrier
   int32_t cross_overlap;      // some atom belongs to two different groups
-  int32_t pad0;
+  int32_t jjt_const;          // ABF: J J^T does not depend on positions; jjt_inv holds its inverse
+  double jjt_inv[MAXK * MAXK];  // (leading dimension 4)
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr

@@ -150,6 +150,11 @@ __device__ __forceinline__ void commit_epochs(const Model& M, const StepShared& 
     if (sh.bars_used & (1u << id)) M.epochs[id] = sh.epoch[id] + 1ULL;
 }
 
+// named barrier between warp 0 (finalizer) and warp 1 (its helper): 64 threads
+__device__ __forceinline__ void pair_sync(int id) {
+  asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory");
+}
+
 __host__ __device__ __forceinline__ bool is_point_kind(int kind) {
   return kind >= PSB_CV_COMPONENT && kind <= PSB_CV_DIHEDRAL;
 }
@@ -370,12 +375,24 @@ __device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int
 // abf.py:210-225 once f.JJt / f.Jp are known (warp 0, all lanes).  Every CTA derives the new
 // histogram count and force sum of bin I from the values the step began with; CTA 0 stores them
 // after the last reader is done (end of the kernel).
-__device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
+// warp 1, concurrently with warp 0's J J^T / solve: bin index of xi and the gather of hist[I] / Fsum[I]
+__device__ __forceinline__ void abf_helper(const Model& M, StepShared& sh, int lane) {
+  Fin& f = sh.fin;
+  pair_sync(1);  // xi is final
+  grid_bin_warp(M.m, f, lane);
+  if (lane < M.k) f.Fsum_old[lane] = __ldcg(M.st.Fsum + f.flat * M.k + lane);
+  if (lane == 0) f.hist_old = __ldcg(M.st.hist + f.flat);  // gather clamps (JAX default)
+  __syncwarp();
+  pair_sync(2);  // bin + gathered values are in shared memory
+}
+
+__device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0,
+                                           bool helped, bool have_Wp) {
   Fin& f = sh.fin;
   const MethodDev& m = M.m;
   const int k = M.k;
   __syncwarp();
-  if (lane == 0) {  // utils/core.py:120-136
+  if (lane == 0 && !have_Wp) {  // utils/core.py:120-136
     double Wp[MAXK] = {0, 0, 0, 0};
     if (m.use_pinv) {
       pinv_sym_solve(k, f.JJt, f.Jp, Wp, 10.0 * (double)(3 * M.natoms) * 2.220446049250313e-16);
@@ -385,15 +402,22 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
     for (int c = 0; c < MAXK; ++c) f.Wp[c] = Wp[c];
   }
   PSB_CLK(12);
-  grid_bin_warp(m, f, lane);  // ends with __syncwarp
+  if (helped) {
+    __syncwarp();
+    pair_sync(2);  // warp 1 has binned xi and gathered hist[I], Fsum[I]
+  } else {
+    grid_bin_warp(m, f, lane);  // ends with __syncwarp
+    if (lane < k) f.Fsum_old[lane] = __ldcg(M.st.Fsum + f.flat * k + lane);
+    if (lane == 0) f.hist_old = __ldcg(M.st.hist + f.flat);  // gather clamps (JAX default)
+    __syncwarp();
+  }
   PSB_CLK(13);
   const bool oob = f.oob != 0;
   if (lane == 0) f.in_range = oob ? 0 : 1;  // .at[I].add drops out-of-range updates
   if (lane < k) {
     const int c = lane;
-    const long long flat = f.flat;
-    uint32_t h = __ldcg(M.st.hist + flat);  // gather clamps (JAX default)
-    double fs = __ldcg(M.st.Fsum + flat * k + c);
+    uint32_t h = (uint32_t)f.hist_old;
+    double fs = f.Fsum_old[c];
     if (!oob) {
       h += 1u;
       const double dWp_dt = (1.5 * f.Wp[c] - 2.0 * sh.pre.Wp[c] + 0.5 * sh.pre.Wp_[c]) / S.dt;
@@ -490,7 +514,40 @@ static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepS
     } break;
     case SM_ABF: {
       if (GENERAL && !M.abf_fast) break;  // needs pass C
+      if (!GENERAL) {  // point-CV kernels: warp 1 bins xi and gathers the histogram meanwhile
+        __syncwarp();
+        pair_sync(1);
+      }
       // J J^T and J p from per-group sums: point-CV Jacobians are constant within a group.
+      if (M.jjt_const) {
+        // Component / Distance / Displacement CVs without atoms shared between CVs: J J^T is a constant
+        // of the index tables (|d distance / d centroid| = 1); its inverse comes from psb_create and
+        // solve(J J^T, J p) (abf.py:211, utils/core.py:128-134) is a k x k matrix-vector product.
+        if (lane < MAXK) {
+          const int a = lane;
+          double s = 0.0;
+          if (a < k) {
+            const CvDev& ca = M.cv[M.comp_cv[a]];
+            const int ja = a - ca.comp0;
+#pragma unroll 1
+            for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g) {
+              const V3 ps = tot3(sh, g, 3);
+              const double* ga = f.gpt[g][ja];
+              s += (ga[0] * ps.x + ga[1] * ps.y + ga[2] * ps.z) * M.grp[g].inv_n;
+            }
+          }
+          f.Jp[a] = s;
+        }
+        __syncwarp();
+        if (lane < MAXK) {
+          double w = 0.0;
+          for (int bq = 0; bq < k; ++bq) w += M.jjt_inv[lane * MAXK + bq] * f.Jp[bq];
+          f.Wp[lane] = lane < k ? w : 0.0;
+        }
+        PSB_CLK(11);
+        abf_finish(M, S, sh, lane, cta0, !GENERAL, true);
+        break;
+      }
       // lanes 0..15: entry (a, b) of J J^T; lanes 16..19: entry a of J p.
       if (lane < 16) {
         const int a = lane >> 2, bq = lane & 3;
@@ -538,7 +595,7 @@ static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepS
         f.Jp[a] = s;
       }
       PSB_CLK(11);
-      abf_finish(M, S, sh, lane, cta0);
+      abf_finish(M, S, sh, lane, cta0, !GENERAL, false);
     } break;
     case SM_METAD_DIRECT: {
       const bool in_dep = (ncalls > 1) && (ncalls % m.stride == 1);  // metad.py:192-193
@@ -986,6 +1043,8 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       PSB_CLK(10);
       if (!any_rmsd) post_cv<METHOD, GENERAL>(M, S, sh, lane, cta0);
       PSB_CLK(15);
+    } else if (warp == 1 && is_abf && !GENERAL && S.mode != MODE_EVAL) {
+      abf_helper(M, sh, lane);
     }
     __syncthreads();
     PSB_STAMP(3);
@@ -1080,7 +1139,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
           }
         for (int a = 0; a < MAXK; ++a) sh.fin.Jp[a] = sh.tot[VGROUP][10 + a];
       }
-      abf_finish(M, S, sh, lane, cta0);
+      abf_finish(M, S, sh, lane, cta0, false, false);
     }
     __syncthreads();
   }
