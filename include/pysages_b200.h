@@ -189,6 +189,9 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
  * the arrays the method needs to the device, steps, copies forces back, and synchronises. */
 psb_status psb_step_host(psb_handle* h, const psb_snapshot* host_snap, int64_t timestep,
                          void* cuda_stream, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* psb_evaluate_cvs for HOST snapshot buffers (initial xi of an engine running on the CPU,
+ * openmm.py:64-89 with the CPU / Reference platform); synchronises. */
+psb_status psb_evaluate_cvs_host(psb_handle* h, const psb_snapshot* host_snap, void* cuda_stream);
 
 /* ---- state access (callbacks, checkpoint/restart: serialization.py:44-93) -------------- */
 /* Field names follow the reference State tuples: "xi", "bias", "ncalls", "heights",

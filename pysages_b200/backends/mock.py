@@ -19,13 +19,7 @@ from torch.utils.dlpack import from_dlpack, to_dlpack
 from .. import _native as N
 from .snapshot import Box, HelperMethods, Layout, Snapshot, copy, restore
 
-LAYOUTS = {
-    "hoomd": Layout(N.LAYOUT_HOOMD, "hoomd"),
-    "openmm-cuda": Layout(N.LAYOUT_OPENMM_CUDA, "openmm-cuda"),
-    "openmm-cpu": Layout(N.LAYOUT_PLAIN3, "openmm-cpu"),
-    "lammps": Layout(N.LAYOUT_LAMMPS, "lammps"),
-}
-LAMMPS_CONVERSION = {"real": 2390.0573615334906, "metal": 1.0364269e-4, "electron": 1.06657236}
+from ._common import LAMMPS_CONVERSION, LAYOUTS  # noqa: E402,F401
 
 
 class MockEngine:

@@ -823,10 +823,9 @@ psb_status psb_set_state(psb_handle* h, const char* field, const void* src_host,
   return PSB_OK;
 }
 
-psb_status psb_step_host(psb_handle* h, const psb_snapshot* hs, int64_t timestep, void* cuda_stream,
-                         int64_t* h2d_bytes, int64_t* d2h_bytes) {
-  if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
-  cudaStream_t stream = (cudaStream_t)cuda_stream;
+// host snapshot -> the handle's device staging buffers (allocated on first use)
+static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cudaStream_t stream, bool with_forces,
+                                      psb_snapshot* out, int64_t* h2d_bytes, size_t* force_bytes) {
   const long long N = h->layout.natoms, rb = h->layout.real_bytes;
   size_t b_pos = 0, b_vel = 0, b_frc = 0, b_ids = 0, b_img = 0, b_mass = 0, b_types = 0;
   switch (h->layout.layout) {
@@ -865,18 +864,43 @@ psb_status psb_step_host(psb_handle* h, const psb_snapshot* hs, int64_t timestep
   };
   CUDA_TRY(push(d.positions, hs->positions, b_pos));
   CUDA_TRY(push(d.vel_mass, hs->vel_mass, b_vel));
-  CUDA_TRY(push(d.forces, hs->forces, b_frc));
+  if (with_forces) CUDA_TRY(push(d.forces, hs->forces, b_frc));
   CUDA_TRY(push(d.ids, hs->ids, b_ids));
   CUDA_TRY(push(d.images, hs->images, b_img));
   CUDA_TRY(push(d.masses, hs->masses, b_mass));
   CUDA_TRY(push(d.types, hs->types, b_types));
-  psb_status st = psb_step(h, &d, timestep, cuda_stream);
+  *out = d;
+  if (h2d_bytes) *h2d_bytes = up;
+  if (force_bytes) *force_bytes = b_frc;
+  return PSB_OK;
+}
+
+psb_status psb_step_host(psb_handle* h, const psb_snapshot* hs, int64_t timestep, void* cuda_stream,
+                         int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  psb_snapshot d;
+  size_t b_frc = 0;
+  psb_status st = stage_host_snapshot(h, hs, stream, true, &d, h2d_bytes, &b_frc);
+  if (st != PSB_OK) return st;
+  st = psb_step(h, &d, timestep, cuda_stream);
   if (st != PSB_OK) return st;
   if (h->method.kind != PSB_METHOD_UNBIASED)
     CUDA_TRY(cudaMemcpyAsync(hs->forces, d.forces, b_frc, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
-  if (h2d_bytes) *h2d_bytes = up;
-  if (d2h_bytes) *d2h_bytes = (int64_t)b_frc;
+  if (d2h_bytes) *d2h_bytes = h->method.kind != PSB_METHOD_UNBIASED ? (int64_t)b_frc : 0;
+  return PSB_OK;
+}
+
+psb_status psb_evaluate_cvs_host(psb_handle* h, const psb_snapshot* hs, void* cuda_stream) {
+  if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  psb_snapshot d;
+  psb_status st = stage_host_snapshot(h, hs, stream, false, &d, nullptr, nullptr);
+  if (st != PSB_OK) return st;
+  st = psb_evaluate_cvs(h, &d, cuda_stream);
+  if (st != PSB_OK) return st;
+  CUDA_TRY(cudaStreamSynchronize(stream));
   return PSB_OK;
 }
 

@@ -82,6 +82,10 @@ class Grid(metaclass=_GridMeta):
         if (not periodic and T is Periodic) or (periodic and T in (Regular, Chebyshev)):
             raise ValueError("Incompatible type parameter and keyword argument")
 
+    def __reduce__(self):
+        # the parametrised classes Grid[T] are created on demand and cannot be found by name
+        return (build_grid, (type(self).type_parameter, self.lower, self.upper, self.shape))
+
     def __eq__(self, other):
         return (
             isinstance(other, Grid)

@@ -115,15 +115,18 @@ class NativeStep:
     """Owns one psb_handle: the device-resident method state + index tables of one simulation."""
 
     def __init__(self, method, snapshot, helpers, dense_outputs=False):
-        if not snapshot.positions.is_cuda:
+        if not torch.cuda.is_available():
             raise RuntimeError(
-                "pysages_b200 runs the bias step on a CUDA device only (no CPU fallback): "
-                "snapshot arrays must be CUDA tensors"
+                "pysages_b200 runs the bias step on a CUDA device only (no CPU fallback): no CUDA device found"
             )
+        # Engine arrays on the host (OpenMM CPU / Reference platforms, LAMMPS without Kokkos-CUDA):
+        # every step stages them through the device (psb_step_host) -- still no CPU compute path.
+        self.host_buffers = not snapshot.positions.is_cuda
         self.lib = N.load()
         self.method = method
         self.layout = helpers.layout
-        self.device = snapshot.positions.device
+        self.device = (torch.device("cuda", torch.cuda.current_device()) if self.host_buffers
+                       else snapshot.positions.device)
         keep = []
         cvs = (N.CvDesc * len(method.cvs))(*[cv.describe(keep) for cv in method.cvs])
         mdesc = method.describe(helpers)
@@ -162,10 +165,15 @@ class NativeStep:
         return _snap.describe_snapshot(snapshot, self.layout, self._snapdesc)
 
     def evaluate(self, snapshot):
-        N.check(self.lib.psb_evaluate_cvs(self.handle, ctypes.byref(self._desc(snapshot)), self._stream()))
+        fn = self.lib.psb_evaluate_cvs_host if self.host_buffers else self.lib.psb_evaluate_cvs
+        N.check(fn(self.handle, ctypes.byref(self._desc(snapshot)), self._stream()))
 
     def step(self, snapshot, timestep=0):
-        N.check(self.lib.psb_step(self.handle, ctypes.byref(self._desc(snapshot)), int(timestep), self._stream()))
+        if self.host_buffers:  # H2D of the arrays the method needs -> step -> D2H forces (synchronous)
+            N.check(self.lib.psb_step_host(self.handle, ctypes.byref(self._desc(snapshot)), int(timestep),
+                                           self._stream(), None, None))
+        else:
+            N.check(self.lib.psb_step(self.handle, ctypes.byref(self._desc(snapshot)), int(timestep), self._stream()))
         self.ncalls += 1
 
     def next_step_deposits(self):

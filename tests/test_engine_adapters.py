@@ -1,0 +1,120 @@
+"""
+The real engine adapters (backends/hoomd.py, openmm.py, lammps.py) driven through `pysages_b200.run`
+on stand-in engine modules (tests/fake_engines.py): same states and forces as the (oracle-checked)
+mock backend, on device arrays and -- OpenMM CPU platform, LAMMPS without Kokkos -- on host arrays.
+"""
+import numpy as np
+import pytest
+import torch
+
+import fake_engines
+import pysages_b200 as ps
+from pysages_b200 import synthetic
+from pysages_b200.backends import mock
+
+pytestmark = pytest.mark.gpu
+
+G1, G2 = list(range(0, 30)), list(range(100, 160))
+NSTEPS = 6
+
+
+def method():
+    cvs = [ps.colvars.Distance([G1, G2]), ps.colvars.Component([5, 6, 7], 1)]
+    grid = ps.Grid[ps.Regular]((0.0, -6.0), (12.0, 6.0), (16, 16))
+    return ps.methods.ABF(cvs, grid, N=2)
+
+
+def reference_run(snap, traj, units=None):
+    """The same trajectory through the mock backend (device arrays)."""
+    eng = mock.MockEngine(snap["layout"], snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda",
+                          trajectory=traj, units=units)
+    res = ps.run(method(), lambda **kw: eng, NSTEPS)
+    torch.cuda.synchronize()
+    return res.states[0], eng.t["forces"].cpu().numpy()
+
+
+def check(result, forces, ref_state, ref_forces):
+    s = result.states[0]
+    torch.cuda.synchronize()
+    for name in ("xi", "hist", "Fsum", "force", "Wp", "Wp_"):
+        np.testing.assert_array_equal(getattr(s, name).cpu().numpy(), getattr(ref_state, name).cpu().numpy(), err_msg=name)
+    assert int(s.ncalls) == NSTEPS
+    np.testing.assert_array_equal(forces, ref_forces)
+
+
+def test_hoomd_adapter():
+    snap = synthetic.make_snapshot(400, layout="hoomd", dtype=np.float32, seed=5)
+    traj = synthetic.make_trajectory(snap, frames=NSTEPS, step=0.05)
+    ref_state, ref_forces = reference_run(snap, traj)
+    Simulation = fake_engines.install_hoomd()
+    eng = fake_engines.engine(snap, "cuda", traj)
+    seen = []
+    res = ps.run(method(), lambda **kw: Simulation(eng), NSTEPS, callback=lambda snapshot, state, t: seen.append(t))
+    check(res, eng.t["forces"].cpu().numpy(), ref_state, ref_forces)
+    assert seen == list(range(NSTEPS))
+    from pysages_b200.backends import hoomd as adapter
+    assert len(adapter.CONTEXTS_SAMPLERS) == 1
+    adapter.detach(next(iter(adapter.CONTEXTS_SAMPLERS)))
+    assert not adapter.CONTEXTS_SAMPLERS
+
+
+@pytest.mark.parametrize("layout, device", [("openmm-cuda", "cuda"), ("openmm-cpu", "cpu")])
+def test_openmm_adapter(layout, device):
+    snap = synthetic.make_snapshot(400, layout=layout, dtype=np.float64, seed=6)
+    traj = synthetic.make_trajectory(snap, frames=NSTEPS, step=0.05)
+    ref_state, ref_forces = reference_run(snap, traj)
+    Simulation = fake_engines.install_openmm()
+    eng = fake_engines.engine(snap, device, traj)
+    res = ps.run(method(), lambda **kw: Simulation(eng), NSTEPS)
+    check(res, eng.t["forces"].cpu().numpy(), ref_state, ref_forces)
+
+
+@pytest.mark.parametrize("kokkos_cuda", [True, False])
+def test_lammps_adapter(kokkos_cuda):
+    snap = synthetic.make_snapshot(400, layout="lammps", dtype=np.float64, seed=7)
+    traj = synthetic.make_trajectory(snap, frames=NSTEPS, step=0.05)
+    ref_state, ref_forces = reference_run(snap, traj, units="real")
+    lammps = fake_engines.install_lammps(kokkos_cuda)
+    eng = fake_engines.engine(snap, "cuda" if kokkos_cuda else "cpu", traj, units="real")
+    ctx = lammps(eng)
+    res = ps.run(method(), lambda **kw: ctx, NSTEPS)
+    check(res, eng.t["forces"].cpu().numpy(), ref_state, ref_forces)
+
+
+def test_openmm_variable_step_integrators_are_rejected():
+    Simulation = fake_engines.install_openmm()
+    import openmm
+
+    snap = synthetic.make_snapshot(64, layout="openmm-cuda", dtype=np.float64, seed=8)
+    sim = Simulation(fake_engines.engine(snap, "cuda"))
+    sim.context.getIntegrator = lambda: openmm.VariableVerletIntegrator()
+    with pytest.raises(ValueError, match="Variable step size"):
+        ps.run(ps.methods.Unbiased([ps.colvars.Component([1], 0)]), lambda **kw: sim, 1)
+
+
+def test_save_load_restart_matches_uninterrupted_run(tmp_path):
+    """serialization.py:44-93 + methods/core.py:239-318: 4 steps, save, load, 4 more steps ==
+    8 uninterrupted steps (metadynamics: hills, grids, counters all travel through the pickle)."""
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=8, step=0.05)
+
+    def make_method():
+        cvs = [ps.colvars.Distance([G1, G2])]
+        grid = ps.Grid[ps.Regular]((0.0,), (12.0,), (32,))
+        return ps.methods.Metadynamics(cvs, 1.0, [0.4], 2, 16, deltaT=300.0, kB=0.0083, grid=grid)
+
+    def generator(first=0, **kw):
+        return mock.MockEngine("hoomd", snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda",
+                               trajectory=traj[first:])
+
+    full = ps.run(make_method(), generator, 8)
+    part = ps.run(make_method(), generator, 4)
+    ps.save(part, tmp_path / "ckpt.pkl")
+    loaded = ps.load(tmp_path / "ckpt.pkl")
+    assert isinstance(loaded.states[0].heights, np.ndarray) and int(loaded.states[0].ncalls) == 4
+    resumed = ps.run(loaded, generator, 4, context_args=dict(first=4))
+    torch.cuda.synchronize()
+    a, b = resumed.states[0], full.states[0]
+    for name in ("xi", "heights", "centers", "grid_potential", "grid_gradient"):
+        np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=name)
+    assert int(a.idx) == int(b.idx) == 3 and int(a.ncalls) == int(b.ncalls) == 8
