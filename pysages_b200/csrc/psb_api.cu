@@ -371,14 +371,17 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     std::vector<std::pair<uint32_t, uint32_t>> order(M.T);
     for (uint32_t t = 0; t < M.T; ++t) order[t] = {term_tag[t], t};
     std::sort(order.begin(), order.end());
-    std::vector<uint32_t> uptr, uterm(M.T);
+    std::vector<uint32_t> uptr, uterm(M.T), utag;
+    std::vector<uint8_t> ugrp(M.T);
     uptr.reserve(M.T + 1);
     for (uint32_t i = 0; i < M.T;) {
       uint32_t j = i;
       uptr.push_back(i);
+      utag.push_back(order[i].first);
       while (j < M.T && order[j].first == order[i].first) ++j;
       for (uint32_t a = i; a < j; ++a) {
         uterm[a] = order[a].second;
+        ugrp[a] = term_group[order[a].second];
         for (uint32_t b2 = i; b2 < j; ++b2)
           M.ov[term_group[order[a].second]][term_group[order[b2].second]] += 1u;
       }
@@ -399,6 +402,11 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       M.uniq_ptr = p;
       if ((st = dev_upload(h, &p, uterm)) != PSB_OK) return bail(st);
       M.uniq_term = p;
+      if ((st = dev_upload(h, &p, utag)) != PSB_OK) return bail(st);
+      M.uniq_tag = p;
+      uint8_t* q = nullptr;
+      if ((st = dev_upload(h, &q, ugrp)) != PSB_OK) return bail(st);
+      M.uniq_grp = q;
     }
     uint32_t* tt = nullptr;
     uint8_t* tg = nullptr;

@@ -146,6 +146,8 @@ struct Model {
   uint32_t* term_slot;        // (T) workspace: slot of each term, written in pass A
   const uint32_t* uniq_ptr;   // (Su+1) CSR over unique atoms -> terms (nullptr if all_unique)
   const uint32_t* uniq_term;  // (T)
+  const uint32_t* uniq_tag;   // (Su) particle tag of each unique atom
+  const uint8_t* uniq_grp;    // (T) group of uniq_term[e]
   MethodDev m;
   StateDev st;
   Fin* fin;

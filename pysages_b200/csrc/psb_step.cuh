@@ -726,9 +726,8 @@ static __device__ __noinline__ V3 nonpoint_gradient(const Fin& f, const CvDev& c
 }
 
 // per-term gradient of the term's CV components w.r.t. the atom; returns ncomp
-template <class A>
-__device__ __forceinline__ int term_gradient(const Model& M, const Snap& S, const Fin& f, uint32_t t,
-                                             int g, uint32_t slot, V3* gv) {
+// (r: unwrapped position of the atom, needed by the non-point kinds only)
+__device__ __forceinline__ int term_gradient_at(const Model& M, const Fin& f, uint32_t t, int g, V3 r, V3* gv) {
   const GroupDev& G = M.grp[g];
   const CvDev& cv = M.cv[G.cv];
   if (is_point_kind(cv.kind)) {
@@ -736,10 +735,31 @@ __device__ __forceinline__ int term_gradient(const Model& M, const Snap& S, cons
       gv[j] = v3(f.gpt[g][j][0] * G.inv_n, f.gpt[g][j][1] * G.inv_n, f.gpt[g][j][2] * G.inv_n);
     return cv.ncomp;
   }
-  V3 r = v3(0, 0, 0);
-  if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
   gv[0] = nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r);
   return 1;
+}
+template <class A>
+__device__ __forceinline__ int term_gradient(const Model& M, const Snap& S, const Fin& f, uint32_t t,
+                                             int g, uint32_t slot, V3* gv) {
+  V3 r = v3(0, 0, 0);
+  const int kind = M.cv[M.grp[g].cv].kind;
+  if (!is_point_kind(kind) && kind != PSB_CV_COORDINATION) r = A::position(S, slot);
+  return term_gradient_at(M, f, t, g, r, gv);
+}
+// Unique atom u of the selection: its tag, slot and CSR range of terms.  The slot comes straight from
+// the tag (not from term_slot), so the chain is {tag, range} -> {slot, terms} -> {force, position}.
+template <class A>
+__device__ __forceinline__ void unique_atom(const Model& M, const Snap& S, bool all_unique, uint32_t u,
+                                            uint32_t& e0, uint32_t& e1, uint32_t& slot) {
+  uint32_t tag;
+  if (all_unique) {
+    e0 = u; e1 = u + 1;
+    tag = __ldg(M.term_tag + u);
+  } else {
+    e0 = __ldg(M.uniq_ptr + u); e1 = __ldg(M.uniq_ptr + u + 1);
+    tag = __ldg(M.uniq_tag + u);
+  }
+  slot = A::slot(S, M, tag);
 }
 
 // particle tag of term t: groups given as ascending ranges need no index load at all
@@ -905,6 +925,16 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
           if (will_scatter) cfv[i] = A::load_force(S, cslot[i]);
         }
       }
+      if (nb == 1) {  // bare indices (groups of one atom): the owner writes the "sums", no reduction
+#pragma unroll
+        for (int i = 0; i < CT; ++i)
+          if (cg[i] >= 0 && M.grp[cg[i]].t1 - M.grp[cg[i]].t0 == 1 &&
+              (!GENERAL || is_point_kind(M.cv[M.grp[cg[i]].cv].kind))) {
+            double* tot = sh.tot[cg[i]];
+            tot[0] = cr[i].x; tot[1] = cr[i].y; tot[2] = cr[i].z;
+            tot[3] = cp[i].x; tot[4] = cp[i].y; tot[5] = cp[i].z;
+          }
+      }
     }
     // ---- slot-major gather (most atoms selected, too many to keep in registers) ---------------
     // A random tag -> slot permutation makes the tag-ordered gather pay one L1 tag lookup per
@@ -996,19 +1026,16 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     for (int g = g_begin; g < g_end; ++g) {
       const GroupDev& G = M.grp[g];
       const CvDev& cv = M.cv[G.cv];
+      if (nb == 1 && cached && G.t1 - G.t0 == 1 && (!GENERAL || is_point_kind(cv.kind))) continue;  // done above
       const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
       const bool with_p = (na == 6);
       double acc[NACC];
 #pragma unroll
       for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-      bool mine = false;
       if (cached) {
 #pragma unroll
         for (int i = 0; i < CT; ++i)
-          if (cg[i] == g) {
-            accumulate_term<GENERAL>(cv, with_p, G.inv_n, lo + tid + i * BLOCK, cr[i], cp[i], acc);
-            mine = true;
-          }
+          if (cg[i] == g) accumulate_term<GENERAL>(cv, with_p, G.inv_n, lo + tid + i * BLOCK, cr[i], cp[i], acc);
       } else {
         const uint32_t tlo = max(lo, G.t0), thi = min(hi, G.t1);
 #pragma unroll 4
@@ -1022,9 +1049,6 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       if (na == 0) continue;
       if (nb > 1) {
         block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
-      } else if (G.t1 - G.t0 == 1) {  // a bare index: its owner writes the sums, no reduction
-        if (mine)
-          for (int a = 0; a < na; ++a) sh.tot[g][a] = acc[a];
       } else {
         block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
       }
@@ -1098,15 +1122,14 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       V3 G[MAXK];
 #pragma unroll
       for (int c = 0; c < MAXK; ++c) G[c] = v3(0, 0, 0);
-      const uint32_t e0 = all_unique ? u : __ldg(M.uniq_ptr + u);
-      const uint32_t e1 = all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
-      uint32_t slot = 0;
+      uint32_t e0, e1, slot;
+      unique_atom<A>(M, S, all_unique, u, e0, e1, slot);
+      const V3 r = M.all_point ? v3(0, 0, 0) : A::position(S, slot);
       for (uint32_t e = e0; e < e1; ++e) {
         const uint32_t t = all_unique ? e : __ldg(M.uniq_term + e);
-        const int g = __ldg(M.term_group + t);
-        slot = __ldcg(M.term_slot + t);
+        const int g = all_unique ? (int)__ldg(M.term_group + t) : (int)__ldg(M.uniq_grp + e);
         V3 gv[3];
-        const int nc = term_gradient<A>(M, S, sh.fin, t, g, slot, gv);
+        const int nc = term_gradient_at(M, sh.fin, t, g, r, gv);
         const int comp0 = M.cv[M.grp[g].cv].comp0;
         for (int j = 0; j < nc; ++j) {
 #pragma unroll
@@ -1278,6 +1301,19 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     __syncthreads();
   }
 
+  // ABF: this CTA's reads of hist[I] / Fsum[I] have RETURNED (their values were consumed and sit in
+  // shared memory, two block barriers ago), so CTA 0 may overwrite the bin once every CTA has said so.
+  // Only that write-after-read order is needed: a load that has delivered its value cannot observe a
+  // later store, so a relaxed RED with no fence is enough (a release would stall ~0.5 us on a MEMBAR
+  // right before the scatter).  Issued here, before the scatter, CTA 0 finds the counter complete when
+  // its own scatter is done (no tail wait).
+  unsigned long long readers_want = 0;
+  const bool abf_commit = (is_abf && nb > 1 && S.mode == MODE_STEP);
+  if (abf_commit && tid == 0) {
+    red_add_u64(&M.bars[BAR_READERS].arrive, 1ULL);
+    sh.bars_used |= 1u << BAR_READERS;
+    readers_want = (sh.epoch[BAR_READERS] + 1ULL) * gridDim.x;
+  }
   PSB_STAMP(4);
   // ---- pass S: in-place force scatter ------------------------------------------------------------
   if (will_scatter) {
@@ -1357,16 +1393,16 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       const uint32_t u0 = min(M.Su, (uint32_t)b * uchunk), u1 = min(M.Su, u0 + uchunk);
       const size_t N3 = 3 * (size_t)M.natoms;
       for (uint32_t u = u0 + tid; u < u1; u += BLOCK) {
-        const uint32_t e0 = all_unique ? u : __ldg(M.uniq_ptr + u);
-        const uint32_t e1 = all_unique ? u + 1 : __ldg(M.uniq_ptr + u + 1);
+        uint32_t e0, e1, slot;
+        unique_atom<A>(M, S, all_unique, u, e0, e1, slot);
+        const FV fv = A::load_force(S, slot);  // in flight while the gradients are assembled
+        const V3 r = M.all_point ? v3(0, 0, 0) : A::position(S, slot);
         V3 fo = v3(0, 0, 0);
-        uint32_t slot = 0;
         for (uint32_t e = e0; e < e1; ++e) {
           const uint32_t t = all_unique ? e : __ldg(M.uniq_term + e);
-          const int g = __ldg(M.term_group + t);
-          slot = __ldcg(M.term_slot + t);
+          const int g = all_unique ? (int)__ldg(M.term_group + t) : (int)__ldg(M.uniq_grp + e);
           V3 gv[3];
-          const int nc = term_gradient<A>(M, S, f, t, g, slot, gv);
+          const int nc = term_gradient_at(M, f, t, g, r, gv);
           const int comp0 = M.cv[M.grp[g].cv].comp0;
           for (int j = 0; j < nc; ++j) {
             fo = fo + (-f.F[comp0 + j]) * gv[j];
@@ -1376,7 +1412,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
             }
           }
         }
-        add_force<A>(S, slot, fo);
+        A::store_force(S, slot, fv, fo);
         if (dense) {
           double* B = M.bias_dense + 3 * (size_t)slot;
           B[0] = fo.x; B[1] = fo.y; B[2] = fo.z;
@@ -1385,12 +1421,6 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
   }
   PSB_STAMP(5);
-
-  // every bin of hist / Fsum this CTA needed was read long ago: tell CTA 0 (non-blocking, and after
-  // the scatter so the fence + atomic stay off the critical path)
-  unsigned long long readers_want = 0;
-  const bool abf_commit = (is_abf && nb > 1 && S.mode == MODE_STEP);
-  if (abf_commit && tid == 0) readers_want = grid_arrive(M, sh, BAR_READERS);
 
   // ---- ABF commit: CTA 0 stores the new count / force sum of bin I (abf.py:216-218) -------------
   if (is_abf && cta0 && S.mode == MODE_STEP && tid == 0) {

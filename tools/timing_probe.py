@@ -9,7 +9,16 @@ import bench
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
 cases = [tuple([c.split(":")[0], int(c.split(":")[1])]) for c in sys.argv[1:]] or [("abf2d", 100_000), ("harmonic", 10_000), ("harmonic", 100_000), ("harmonic", 1_000_000), ("abf2d", 1_000_000), ("walkers", 100_000), ("window", 100_000)]
 for wl, natoms in cases:
-    if wl.startswith("cfg4"):
+    if wl.startswith("cfg1"):
+        frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1, dtype=torch.float64)
+        snaps = bench.snapshots_of(frames, L, 0.002)
+        pi = float(np.pi)
+        cvs = [("DihedralAngle", ([4, 6, 8, 14],), {}), ("DihedralAngle", ([6, 8, 14, 16],), {})]
+        md = dict(height=1.2, sigma=[0.35, 0.35], stride=500, ngaussians=64, deltaT=5000.0, kB=0.0083144626)
+        if wl == "cfg1grid":
+            md["grid"] = ((-pi, -pi), (pi, pi), (50, 50), "periodic")
+        method, native = bench.build_ours(cvs, ("Metadynamics", md), snaps[0])
+    elif wl.startswith("cfg4"):
         frames, L, cvs, md, prefill = bench.cfg4_case(dev)
         if wl == "cfg4grid":
             md = dict(md, grid=((0.0, 0.0), (40.0, 4000.0), (256, 256), "regular"))
