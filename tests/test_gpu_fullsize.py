@@ -1,0 +1,155 @@
+"""
+Parity at BASELINE.json's FULL sizes (the other GPU tests use sizes the dense oracle finishes in
+milliseconds): the oracle itself where it is still affordable (cfg2 at 1e5 atoms, the 1e6-atom
+series incl. the slot-ordered kernels, cfg4 at 5e4 atoms), and independent numpy known answers plus
+conservation laws where the dense formulation is not (cfg3: 1e8 pairs).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from parity_utils import ParityRun, close
+from pysages_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def groups4(n):
+    q = n // 4
+    return [list(range(i * q, (i + 1) * q)) for i in range(4)]
+
+
+def test_cfg2_abf_100k_against_oracle():
+    n = 100_000
+    snap = synthetic.make_snapshot(n, layout="hoomd", dtype=np.float32, seed=20240 + 2000)
+    g = groups4(n)
+    L = snap["L"]
+    cvs = [("Distance", ([g[0], g[1]],), {}), ("Distance", ([g[2], g[3]],), {})]
+    spec = ("ABF", dict(grid=((0.0, 0.0), (L / 2, L / 2), (64, 64), "regular"), N=500,
+                        restraints=((0.0, 0.0), (L / 2, L / 2), (10.0, 10.0), (10.0, 10.0))))
+    run = ParityRun(snap, cvs, spec)
+    assert run.native.launch_info()["grid_blocks"] > 1
+    traj = synthetic.make_trajectory(snap, frames=3, step=0.02)
+    for f in range(3):
+        s, o = run.step(traj[f])
+    # conservation: a distance between two centroids pushes the two groups with opposite total force
+    bias = s.bias.cpu().numpy()
+    assert np.abs(bias.sum(axis=0)).max() <= 1e-9 * max(np.abs(bias).max(), 1e-300) * n
+    assert int(s.hist.sum().item()) == 3
+
+
+@pytest.mark.parametrize("method", ["harmonic", "abf"])
+def test_million_atoms_slot_ordered_kernels_against_oracle(method, monkeypatch):
+    """S = N = 1e6: the library picks the slot-ordered gather / scatter by itself."""
+    monkeypatch.delenv("PSB_SLOT_MAJOR", raising=False)
+    monkeypatch.delenv("PSB_GRID_BLOCKS", raising=False)
+    n = 1_000_000
+    snap = synthetic.make_snapshot(n, layout="hoomd", dtype=np.float32, seed=20240 + 7)
+    L = snap["L"]
+    if method == "harmonic":
+        cvs = [("Distance", ([list(range(0, n // 2)), list(range(n // 2, n))],), {})]
+        spec = ("HarmonicBias", dict(kspring=10.0, center=[1.0]))
+    else:
+        g = groups4(n)
+        cvs = [("Distance", ([g[0], g[1]],), {}), ("Distance", ([g[2], g[3]],), {})]
+        spec = ("ABF", dict(grid=((0.0, 0.0), (L / 2, L / 2), (64, 64), "regular"), N=500))
+    run = ParityRun(snap, cvs, spec)
+    run.step()
+    # dense outputs (parity harness) select the general kernels; the production handle is slot-ordered:
+    import bench
+
+    dev = torch.device("cuda:0")
+    frames, L2, _ = bench.device_hoomd_frames(n, 1, dev, seed=5)
+    snaps = bench.snapshots_of(frames, L2, 0.005)
+    cv2, m2 = bench.workload_specs("harmonic" if method == "harmonic" else "abf2d", n, L2)
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "0")
+    _, tagmajor = bench.build_ours(cv2, m2, snaps[0])
+    monkeypatch.delenv("PSB_SLOT_MAJOR")
+    _, slotmajor = bench.build_ours(cv2, m2, snaps[0])
+    f0 = frames[0]["forces"].clone()
+    outs = []
+    for native in (tagmajor, slotmajor):
+        frames[0]["forces"].copy_(f0)
+        native.step(snaps[0])
+        native.step(snaps[0])
+        torch.cuda.synchronize()
+        outs.append((native.view("xi").cpu().numpy().copy(), native.view("cv_force").cpu().numpy().copy(),
+                     frames[0]["forces"].cpu().numpy().copy()))
+    close(outs[1][0], outs[0][0], 1e-12, what="xi slot- vs tag-ordered")
+    close(outs[1][1], outs[0][1], 1e-9, what="generalized force slot- vs tag-ordered")
+    assert np.abs(outs[1][2] - outs[0][2]).max() <= 2e-7 * np.abs(outs[0][2]).max()
+    assert np.abs(outs[0][2] - f0.cpu().numpy()).max() > 0  # the bias was applied
+
+
+def test_cfg3_coordination_1e8_pairs_known_answer():
+    """10k x 10k CoordinationNumber in a 1e6-atom system: value against chunked numpy, Newton's third
+    law (the two groups receive opposite total forces) and the harmonic force magnitude."""
+    import pysages_b200 as ps
+    from parity_utils import device_helpers, device_snapshot
+
+    n = 1_000_000
+    snap = synthetic.make_snapshot(n, layout="hoomd", dtype=np.float32, seed=20240 + 3000)
+    rng = np.random.Generator(np.random.PCG64(20240 + 3000))
+    tags = rng.permutation(n)[:20_000]
+    ga, gb = np.sort(tags[:10_000]), np.sort(tags[10_000:])
+    r0, kspring, center = 1.0, 10.0, 100.0
+    method = ps.methods.HarmonicBias([ps.colvars.CoordinationNumber([ga.tolist(), gb.tolist()], r0=r0)], kspring, [center])
+    dsnap = device_snapshot(snap)
+    f0 = dsnap.forces.clone()
+    _, init, update = method.build(dsnap, device_helpers("hoomd"))
+    state = update(dsnap, init())
+    torch.cuda.synchronize()
+    # numpy: unwrap, then sum 1 / (1 + (r / r0)^6) over all pairs, 500 rows at a time
+    a = snap["arrays"]
+    L = snap["L"]
+    slot = a["rtags"]
+    pos = a["positions"][:, :3].astype(np.float64) + L * a["images"].astype(np.float64)
+    xa, xb = pos[slot[ga]], pos[slot[gb]]
+    total = 0.0
+    for i in range(0, len(xa), 500):
+        d2 = ((xa[i : i + 500, None, :] - xb[None, :, :]) ** 2).sum(-1)
+        total += (1.0 / (1.0 + (d2 / r0**2) ** 3)).sum()
+    xi = float(state.xi.cpu().numpy().ravel()[0])
+    assert abs(xi - total) <= 1e-10 * abs(total), (xi, total)
+    df = (dsnap.forces - f0).cpu().numpy()[:, :3].astype(np.float64)
+    fa, fb = df[slot[ga]].sum(0), df[slot[gb]].sum(0)
+    scale = np.abs(df).max() * 1e4
+    assert np.abs(fa + fb).max() <= 1e-5 * scale  # fp32 force array: one rounding per atom
+    untouched = np.ones(n, bool); untouched[slot[ga]] = False; untouched[slot[gb]] = False
+    assert not df[untouched].any()
+    F = float(update.native.view("cv_force").cpu().numpy().ravel()[0])
+    assert abs(F - kspring * (xi - center)) <= 1e-12 * abs(F)
+
+
+def test_cfg4_rmsd_rog_50k_direct_hills_against_oracle_and_numpy():
+    n, H = 50_000, 20_000
+    snap = synthetic.make_snapshot(n, layout="hoomd", dtype=np.float64, seed=20240 + 4000, globule=True)
+    snap["arrays"]["images"][:] = 0
+    rng = np.random.default_rng(4)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    pos_by_tag = snap["arrays"]["positions"][snap["arrays"]["rtags"]][:, :3]
+    ref = pos_by_tag @ q.T + rng.normal(scale=0.1, size=(n, 3))
+    allatoms = list(range(n))
+    cvs = [("RMSD", (allatoms, ref), {}), ("RadiusOfGyration", (allatoms,), {})]
+    kw = dict(height=1.0, sigma=[0.05, 5.0], stride=3, ngaussians=H)
+    run = ParityRun(snap, cvs, ("Metadynamics", kw))
+    xi0 = run.state.xi.cpu().numpy().ravel()
+    # known answers at full size, independent of the oracle: numpy Kabsch + <r.r>
+    P = pos_by_tag - pos_by_tag.mean(0); Q = ref - ref.mean(0)
+    V, S, Wt = np.linalg.svd(P.T @ Q)
+    d = np.sign(np.linalg.det(V) * np.linalg.det(Wt)); V[:, -1] *= d
+    rmsd = math.sqrt((((P @ (V @ Wt)) - Q) ** 2).sum() / n)
+    assert abs(xi0[0] - rmsd) <= 1e-10 * rmsd
+    assert abs(xi0[1] - (pos_by_tag**2).sum() / n) <= 1e-12 * xi0[1]
+    # pre-filled hills on both sides, then steps through a deposit
+    heights = np.zeros(H); heights[: H - 5] = rng.uniform(0.5, 1.2, H - 5)
+    centers = np.zeros((H, 2)); centers[: H - 5] = xi0 + rng.normal(size=(H - 5, 2)) * np.array([0.05, 5.0])
+    run.native.set_state("heights", heights); run.native.set_state("centers", centers)
+    run.native.set_state("idx", np.array([H - 5], dtype=np.int64))
+    run.ostate = run.ostate._replace(heights=torch.tensor(heights), centers=torch.tensor(centers), idx=H - 5)
+    traj = synthetic.make_trajectory(snap, frames=4, step=0.01)
+    for f in range(4):
+        run.step(traj[f])
+    assert int(run.state.idx) == H - 4
