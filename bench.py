@@ -490,7 +490,7 @@ def run_series(device, stream, hbm):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--natoms", type=int, default=100_000)
@@ -560,6 +560,11 @@ def main():
     with ClockSampler(device.index or 0) as clocks:
         barrier()
         ms, launches = time_cycle(native, descs, args.steps, max(args.warmup, 3), stream)
+        # a short timed region can end before nvidia-smi (100 ms period) has sampled it: keep the SAME load
+        # running, untimed, until a few samples under load exist (the timed number above is not touched)
+        t_end = time.perf_counter() + 1.5
+        while len(clocks.rows) < 5 and time.perf_counter() < t_end:
+            time_cycle(native, descs, 4000, 0, stream)
         barrier()
     info = native.launch_info()
     ms_plain, _ = time_cycle(native, descs, min(args.steps, 2000), 3, stream, plain=True)
@@ -593,13 +598,32 @@ def main():
             dist.destroy_process_group()
         return
 
+    # launch-latency floor on this box: empty kernels of the same shape, back to back
+    from pysages_b200 import _native as N
+
+    def floor(barrier_flag):
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        N.check(native.lib.psb_launch_floor(info["grid_blocks"], 1, 0, barrier_flag, 200, sp))
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        N.check(native.lib.psb_launch_floor(info["grid_blocks"], 1, 0, barrier_flag, 2000, sp))
+        e1.record(stream)
+        stream.synchronize()
+        return round(e0.elapsed_time(e1) * 1e3 / 2000, 3)
+
+    info["floor_us"] = dict(empty_cooperative_launch=floor(0), empty_launch_with_one_grid_barrier=floor(1))
+
     hbm, peak_src = peaks()
     us = ms * 1e3 / args.steps
     achieved = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
     roofline = dict(bound="hbm", achieved=round(achieved, 2), peak=hbm, unit="GB/s", frac=round(achieved / hbm, 4),
-                    traffic=traffic_from_profiles("abf2d_100k"), kernel="psb::step_kernel<HOOMD,float> (1 launch/step)",
+                    traffic=traffic_from_profiles("abf2d_100k"),
+                    kernel="psb::step_kernel<HOOMD,float,ABF,point> (1 cooperative launch per step, CUDA-graph replay)",
                     algorithmic_bytes_per_launch=info["algorithmic_bytes_per_step"], peak_source=peak_src,
-                    note="latency-bound at S=1e5 (8.4 MB/step = 1.3 us of traffic); see series for S=1e6")
+                    note="latency-bound at S=1e5: 8.4 MB/step is 1.3 us of HBM time inside a ~12 us dependent chain "
+                         "(gather -> grid barrier -> finalizer -> scatter), see launch.floor_us and DESIGN.md 4.1; "
+                         "the S=N=1e6 rows of `series` are the bandwidth regime")
 
     cpu = None
     if not args.no_cpu:
