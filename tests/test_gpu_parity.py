@@ -406,3 +406,81 @@ def test_shared_hill_walkers(golden, deltaT, grid):
                     close(n.view("grid_potential").cpu().numpy().reshape(o.grid_potential.shape),
                           o.grid_potential.numpy(), X64_RTOL, what="grid_potential")
     assert int(engines[0].native.view("idx").item()) == 2 * W
+
+
+# ---- engine-loop emulation: CUDA-graph replay of the snapshot ring ---------------------------------------
+@pytest.mark.parametrize("method", ["abf", "metad-grid", "metad-direct"])
+def test_run_cycle_graph_replay_matches_single_steps_and_oracle(method, launch_shape):
+    """psb_run_cycle captures one pass over the snapshot ring as a CUDA graph and replays it (barrier
+    epochs, deposit decisions and all method state live on the device): bitwise equal to issuing
+    psb_step per step, and equal to the oracle after a few hundred steps."""
+    import ctypes
+
+    import oracle
+    import pysages_b200 as ps
+    from parity_utils import X64_RTOL, device_helpers, device_snapshot, make_cvs, make_method, oracle_snapshot
+    from pysages_b200 import _native as N
+    from pysages_b200.backends import snapshot as S
+
+    nring, nsteps = 3, 121
+    snap = snapshot("hoomd", np.float64, n=800, seed=20250)
+    traj = synthetic.make_trajectory(snap, frames=nring, step=0.03)
+    cvs = POINT_CVS["two-distances"]
+    if method == "abf":
+        spec = ("ABF", dict(grid=((0.0, 0.0), (14.0, 14.0), (24, 24), "regular"), N=5))
+    elif method == "metad-grid":
+        spec = ("Metadynamics", dict(height=0.7, sigma=[0.4, 0.6], stride=7, ngaussians=64, deltaT=900.0, kB=0.0083,
+                                     grid=((0.0, 0.0), (14.0, 14.0), (40, 40), "regular")))
+    else:
+        spec = ("Metadynamics", dict(height=0.7, sigma=[0.4, 0.6], stride=7, ngaussians=64, deltaT=900.0, kB=0.0083))
+
+    def build():
+        m = make_method("ours", spec, make_cvs(ps.colvars, cvs))
+        m.dense_bias = False
+        dsnaps = [device_snapshot(snap, positions=traj[i]) for i in range(nring)]
+        _, init, update = m.build(dsnaps[0], device_helpers("hoomd"))
+        init()
+        return update.native, dsnaps
+
+    # (a) graph replay (capture needs a non-default stream, like an engine's own stream)
+    stream = torch.cuda.Stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        nat_g, snaps_g = build()
+        descs = (N.SnapshotDesc * nring)()
+        for i, s in enumerate(snaps_g):
+            S.describe_snapshot(s, nat_g.layout, descs[i])
+        N.check(nat_g.lib.psb_run_cycle(nat_g.handle, descs, nring, nsteps, sp))
+    stream.synchronize()
+    assert nat_g.lib.psb_cycle_uses_graph(nat_g.handle) == 1
+    # (b) one psb_step per step
+    nat_s, snaps_s = build()
+    for t in range(nsteps):
+        nat_s.step(snaps_s[t % nring], t)
+    torch.cuda.synchronize()
+    fields = ["xi", "cv_force", "ncalls"] + (["hist", "Fsum", "force", "Wp", "Wp_"] if method == "abf" else
+                                             ["heights", "centers", "idx"] + (["grid_potential", "grid_gradient"] if method == "metad-grid" else []))
+    for f in fields:
+        assert torch.equal(nat_g.view(f), nat_s.view(f)), f
+    for a, b in zip(snaps_g, snaps_s):
+        assert torch.equal(a.forces, b.forces)
+    # (c) the oracle over the same ring
+    om = make_method("oracle", spec, make_cvs(oracle.colvars, cvs))
+    helpers, bias = oracle.backends.build_helpers("hoomd", om.snapshot_flags, True)
+    osnaps = [oracle_snapshot(snap, positions=traj[i]) for i in range(nring)]
+    _, oinit, oupdate = om.build(osnaps[0], helpers)
+    ostate = oinit()
+    for t in range(nsteps):
+        ostate = oupdate(osnaps[t % nring], ostate)
+        bias(osnaps[t % nring], ostate.bias.numpy())
+    close(nat_g.view("xi").cpu().numpy().ravel()[:2], ostate.xi.numpy().ravel(), X64_RTOL, what="xi")
+    if method == "abf":
+        assert np.array_equal(nat_g.view("hist").cpu().numpy().reshape(24, 24).astype(np.int64), ostate.hist.numpy())
+        close(nat_g.view("Fsum").cpu().numpy().reshape(24, 24, 2), ostate.Fsum.numpy(), 1e-8, what="Fsum")
+    else:
+        assert int(nat_g.view("idx").item()) == int(ostate.idx) == (nsteps - 1) // 7
+        close(nat_g.view("heights").cpu().numpy().ravel(), ostate.heights.numpy(), 1e-9, what="heights")
+        close(nat_g.view("centers").cpu().numpy().reshape(-1, 2), ostate.centers.numpy(), X64_RTOL, what="centers")
+    for a, o in zip(snaps_g, osnaps):
+        close(a.forces.cpu().numpy()[:, :3], o.forces[:, :3], 1e-9, what="forces after %d steps" % nsteps)
