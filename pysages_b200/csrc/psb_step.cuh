@@ -86,6 +86,16 @@ __device__ __forceinline__ long long global_ns() {
   do {                                                                               \
     if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
   } while (0)
+#ifdef PSB_PROBE_PASSA  // experiment builds: clock stamps inside pass A instead of the finalizer
+#define PSB_CLKA(slot)                                                               \
+  do {                                                                               \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
+#undef PSB_CLK
+#define PSB_CLK(slot) do {} while (0)
+#else
+#define PSB_CLKA(slot) do {} while (0)
+#endif
 #define PSB_STAMP(slot)                                                              \
   do {                                                                               \
     if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
@@ -799,6 +809,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   }
   __syncthreads();
   const Model& M = sM;
+  PSB_CLKA(8);
 
   const int nb = gridDim.x, b = blockIdx.x;
   const bool cta0 = (b == 0);
@@ -820,18 +831,35 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
                             (S.mode == MODE_STEP || (WALK && S.mode == MODE_WALKER_FINISH));
 
   // ---- prologue: method-state scalars as they are when the step begins --------------------------
+  // The loads are issued here but land in shared memory only after this thread has issued its
+  // gather loads (commit_pre below): storing them right away would stall warps 0-2 for one L2 round
+  // trip before they even start gathering.
+  long long pre_ncalls = 0, pre_idx = 0;
+  unsigned long long pre_epoch = 0;
+  double pre_abf = 0.0;
   if (tid == 0) {
-    sh.pre.ncalls = __ldcg(M.st.ncalls);
-    sh.pre.idx = M.st.idx ? __ldcg(M.st.idx) : 0;
-    sh.bars_used = 0;
+    pre_ncalls = __ldcg(M.st.ncalls);
+    pre_idx = M.st.idx ? __ldcg(M.st.idx) : 0;
   }
-  if (tid >= 64 && tid < 64 + NBARS) sh.epoch[tid - 64] = __ldcg(M.epochs + (tid - 64));
+  if (tid >= 64 && tid < 64 + NBARS) pre_epoch = __ldcg(M.epochs + (tid - 64));
   if (is_abf && tid >= 32 && tid < 32 + 3 * MAXK) {
     const int j = tid - 32, c = j & (MAXK - 1), which = j / MAXK;
     const double* src = which == 0 ? M.st.Wp : (which == 1 ? M.st.Wp_ : M.st.force);
-    double* dst = which == 0 ? sh.pre.Wp : (which == 1 ? sh.pre.Wp_ : sh.pre.force);
-    dst[c] = __ldcg(src + c);
+    pre_abf = __ldcg(src + c);
   }
+  auto commit_pre = [&]() {
+    if (tid == 0) {
+      sh.pre.ncalls = pre_ncalls;
+      sh.pre.idx = pre_idx;
+      sh.bars_used = 0;
+    }
+    if (tid >= 64 && tid < 64 + NBARS) sh.epoch[tid - 64] = pre_epoch;
+    if (is_abf && tid >= 32 && tid < 32 + 3 * MAXK) {
+      const int j = tid - 32, c = j & (MAXK - 1), which = j / MAXK;
+      double* dst = which == 0 ? sh.pre.Wp : (which == 1 ? sh.pre.Wp_ : sh.pre.force);
+      dst[c] = pre_abf;
+    }
+  };
 
   // ---- hill staging: kick off the first TMA bulk copies before touching any atom ------------
   long long nh = 0, h0 = 0, h1 = 0;
@@ -903,6 +931,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   FV cfv[CT];
 
   // ---- pass A ---------------------------------------------------------------------------------
+  PSB_CLKA(9);
   if (!skip_cv) {
     if (cached) {
 #pragma unroll
@@ -936,6 +965,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
           }
       }
     }
+    commit_pre();
     // ---- slot-major gather (most atoms selected, too many to keep in registers) ---------------
     // A random tag -> slot permutation makes the tag-ordered gather pay one L1 tag lookup per
     // 16-byte row (measured: ~6 lookups per atom, 1 lookup/clk/SM -> 20 us per 1e6 atoms, far
@@ -1047,8 +1077,10 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         }
       }
       if (na == 0) continue;
+      PSB_CLKA(10);
       if (nb > 1) {
         block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+        PSB_CLKA(11);
       } else {
         block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
       }
@@ -1104,6 +1136,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       __syncthreads();
     }
   } else {
+    commit_pre();
     fin_load(M, sh);
   }
   if (S.mode == MODE_EVAL) {

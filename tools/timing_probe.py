@@ -53,7 +53,10 @@ for wl, natoms in cases:
     c = t[0, 8:16]
     cn = ["pre-reduce", "reduce_rows", "finalize_cv", "JJt/Jp", "solve", "grid_bin", "hist gather+F", "finish_force(end post_cv)"]
     base = c[0]
-    if wl == "abf2d":
+    if os.environ.get("PSB_PROBE_PASSA"):
+        t0c = t[0, 8]
+        print("  CTA0 pass-A clocks (cycles since model copy done): segment+prologue=%d, loads+accumulate=%d, block reduce=%d" % (c[1] - t0c, c[2] - t0c, c[3] - t0c))
+    elif wl == "abf2d":
         print("  CTA0 finalize clocks (cycles since pre-reduce):", ", ".join(f"{n}={int(v - base)}" for n, v in zip(cn, c)))
     else:
         print("  CTA0 finalize clocks:", f"reduce_rows={int(c[1]-base)} finalize_cv={int(c[2]-base)} post_cv={int(c[7]-base)}")
