@@ -55,8 +55,20 @@ typedef enum {
   PSB_CV_DIHEDRAL = 5,     /* colvars/angles.py:77-128       */
   PSB_CV_ROG = 6,          /* colvars/shape.py:14-57 (value = <r.r>, reference quirk) */
   PSB_CV_RMSD = 7,         /* colvars/orientation.py:27-126  */
-  PSB_CV_COORDINATION = 8  /* extension, absent from the reference */
+  PSB_CV_COORDINATION = 8, /* extension, absent from the reference */
+  PSB_CV_GYRATION = 9      /* colvars/shape.py:85-344: functions of the eigenvalues of the (uncentred)
+                              gyration tensor sum_i r_i r_i^T / n; `axis` selects the function */
 } psb_cv_kind;
+
+/* psb_cv_desc.axis for PSB_CV_GYRATION (eigenvalues ascending, l[0] <= l[1] <= l[2]) */
+typedef enum {
+  PSB_GYR_MOMENT_0 = 0,    /* PrincipalMoment(axis = 0, 1, 2): l[axis] (shape.py:85-176) */
+  PSB_GYR_MOMENT_1 = 1,
+  PSB_GYR_MOMENT_2 = 2,
+  PSB_GYR_ASPHERICITY = 3,  /* l[2] - (l[0] + l[1]) / 2 (shape.py:203-221) */
+  PSB_GYR_ACYLINDRICITY = 4, /* l[mm] - l[nn] with the reference's index pairs (shape.py:224-287) */
+  PSB_GYR_ANISOTROPY = 5    /* (3 sum l^2 / (sum l)^2 - 1) / 2 (shape.py:290-344) */
+} psb_gyration_mode;
 
 /* One CV after the reference's index processing (colvars/core.py:184-207, 277-295):
  * `tags` holds the particle tags of all groups back to back; group g spans
@@ -65,7 +77,7 @@ typedef enum {
 typedef struct {
   int32_t kind;                  /* psb_cv_kind */
   int32_t axis;                  /* Component: 0,1,2 */
-  int32_t n_groups;              /* Component/RoG/RMSD: 1; Distance/Displacement/Coordination: 2;
+  int32_t n_groups;              /* Component/RoG/RMSD/Gyration: 1; Distance/Displacement/Coordination: 2;
                                     Angle: 3; Dihedral: 4 */
   int32_t reserved;
   const uint32_t* tags;          /* host pointer, group_offsets[n_groups] entries */
@@ -73,7 +85,8 @@ typedef struct {
   const double* reference;       /* RMSD: (n, 3) reference coordinates (host) */
   const double* weights;         /* RMSD: n weights, or NULL for uniform 1/n  */
   double r0;                     /* Coordination: switching radius */
-  int32_t nn, mm;                /* Coordination: exponents (default 6, 12) */
+  int32_t nn, mm;                /* Coordination: exponents (default 6, 12); Gyration acylindricity:
+                                    eigenvalue indices (l[mm] - l[nn]) */
 } psb_cv_desc;
 
 /* ---- grids: pysages/grids.py:30-158 ----------------------------------------------- */

@@ -214,6 +214,72 @@ class RadiusOfGyration(CollectiveVariable):
         return radius_of_gyration
 
 
+def gyration_tensor(positions):
+    # shape.py:118-135: sum_i outer(r_i, r_i) / n  (uncentred)
+    return positions.T @ positions / positions.shape[0]
+
+
+def principal_moments(positions):
+    # shape.py:161-176: eigvalsh (ascending)
+    return torch.linalg.eigvalsh(gyration_tensor(positions))
+
+
+def asphericity(positions):
+    # shape.py:203-221
+    l1, l2, l3 = principal_moments(positions)
+    return l3 - (l1 + l2) / 2
+
+
+def acylindricity(positions, axes):
+    # shape.py:267-287; jnp indexing clamps out-of-range indices (the reference's pairs go up to 3)
+    lambdas = principal_moments(positions)
+    l1, l2 = [lambdas[min(i, 2)] for i in axes]
+    return l2 - l1
+
+
+def shape_anisotropy(positions):
+    # shape.py:318-344
+    l1, l2, l3 = principal_moments(positions)
+    return (3 * (l1**2 + l2**2 + l3**2) / (l1 + l2 + l3) ** 2 - 1) / 2
+
+
+class PrincipalMoment(Component):
+    # shape.py:85-115 (AxisCV)
+    @property
+    def function(self):
+        return lambda rs: principal_moments(rs)[self.axis]
+
+
+class Asphericity(CollectiveVariable):
+    # shape.py:179-200
+    @property
+    def function(self):
+        return asphericity
+
+
+class Acylindricity(CollectiveVariable):
+    # shape.py:224-264
+    symmetry_axes = {"xy": (1, 2), "yz": (2, 3), "xz": (1, 3)}
+
+    def __init__(self, indices, axes="xy", group_length=None):
+        axes = "".join(sorted(axes.lower()))
+        if axes not in self.symmetry_axes:
+            raise RuntimeError(f"Invalid acylindrity axes specification {axes}.")
+        super().__init__(indices, group_length)
+        self.axes = axes
+
+    @property
+    def function(self):
+        return lambda rs: acylindricity(rs, self.symmetry_axes[self.axes])
+
+
+class ShapeAnisotropy(CollectiveVariable):
+    # shape.py:290-315
+    @property
+    def function(self):
+        return shape_anisotropy
+
+
 # --------------------------------------------------------------------------- #
 # orientation.py (RMSD)
 # --------------------------------------------------------------------------- #

@@ -191,6 +191,63 @@ class RadiusOfGyration(CollectiveVariable):
     _kind = N.CV_ROG
 
 
+class _GyrationCV(CollectiveVariable):
+    """Functions of the eigenvalues of the reference's (uncentred) gyration tensor sum_i r_i r_i^T / n
+    (colvars/shape.py:118-176): one scalar component, Jacobian (2/n) W r_i."""
+
+    _kind = N.CV_GYRATION
+    _mode = 0
+    _pair = (0, 0)
+
+    def describe(self, keep):
+        d = super().describe(keep)
+        d.axis = self._mode
+        d.nn, d.mm = self._pair
+        return d
+
+
+class PrincipalMoment(_GyrationCV):
+    """colvars/shape.py:85-176: eigenvalue `axis` (ascending) of the gyration tensor."""
+
+    def __init__(self, indices, axis, group_length=None):
+        if axis not in (0, 1, 2):
+            raise RuntimeError(f"Invalid Cartesian axis {axis} index choose 0 (X), 1 (Y), 2 (Z)")
+        super().__init__(indices, group_length)
+        self.axis = axis
+        self._mode = axis
+
+
+class Asphericity(_GyrationCV):
+    """colvars/shape.py:179-221: l3 - (l1 + l2) / 2."""
+
+    _mode = N.GYR_ASPHERICITY
+
+
+class Acylindricity(_GyrationCV):
+    """colvars/shape.py:224-287: l_k - l_j.  The reference indexes the (0-based) eigenvalue array with
+    the pairs xy -> (1, 2), yz -> (2, 3), xz -> (1, 3); JAX clamps the out-of-range 3 to 2, so "yz" is
+    identically 0 and "xz" equals "xy" -- reproduced here."""
+
+    _mode = N.GYR_ACYLINDRICITY
+    symmetry_axes = {"xy": (1, 2), "yz": (2, 3), "xz": (1, 3)}
+
+    def __init__(self, indices, axes="xy", group_length=None):
+        axes = "".join(sorted(axes.lower()))
+        if axes not in self.symmetry_axes:
+            raise RuntimeError(f"Invalid acylindrity axes specification {axes}."
+                               f" Valid options are: {tuple(self.symmetry_axes.keys())}.")
+        super().__init__(indices, group_length)
+        self.axes = axes
+        j, k = self.symmetry_axes[axes]
+        self._pair = (min(j, 2), min(k, 2))
+
+
+class ShapeAnisotropy(_GyrationCV):
+    """colvars/shape.py:290-344: (3 sum l^2 / (sum l)^2 - 1) / 2."""
+
+    _mode = N.GYR_ANISOTROPY
+
+
 class RMSD(CollectiveVariable):
     """colvars/orientation.py:98-126 (Kabsch-fitted RMSD to `references`)."""
 

@@ -101,7 +101,7 @@ psb_status dev_upload(psb_handle* h, T** out, const std::vector<T>& v) {
 
 int expected_groups(int kind) {
   switch (kind) {
-    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: return 1;
+    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: case PSB_CV_GYRATION: return 1;
     case PSB_CV_DISTANCE: case PSB_CV_DISPLACEMENT: case PSB_CV_COORDINATION: return 2;
     case PSB_CV_ANGLE: return 3;
     case PSB_CV_DIHEDRAL: return 4;
@@ -444,6 +444,14 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         if ((st = dev_upload(h, &p, w)) != PSB_OK) return bail(st);
         cv.w = p;
       }
+    }
+    if (d.kind == PSB_CV_GYRATION) {
+      if (d.axis < PSB_GYR_MOMENT_0 || d.axis > PSB_GYR_ANISOTROPY)
+        return bail(fail(PSB_ERR_VALUE, "CV %d: unknown gyration-tensor function %d", c, d.axis));
+      if (d.axis == PSB_GYR_ACYLINDRICITY && (d.nn < 0 || d.nn > 2 || d.mm < 0 || d.mm > 2))
+        return bail(fail(PSB_ERR_VALUE, "CV %d: acylindricity eigenvalue indices must be 0, 1 or 2", c));
+      cv.nn = d.nn;
+      cv.mm = d.mm;
     }
     if (d.kind == PSB_CV_COORDINATION) {
       const int nn = d.nn == 0 ? 6 : d.nn, mm = d.mm == 0 ? 12 : d.mm;

@@ -228,6 +228,47 @@ PSB_HD_COLD void jacobi_eig(int n, double* a, double* v) {
   }
 }
 
+// Gyration-tensor CVs (colvars/shape.py:85-344).  g = (xx, xy, xz, yy, yz, zz) of sum_i r_i r_i^T / n.
+// Returns the CV value f(l) for `mode` (psb_gyration_mode; eigenvalues l ascending like
+// jnp.linalg.eigvalsh) and W = sum_k (df/dl_k) v_k v_k^T (row-major 3x3): the gradient with respect
+// to atom i is (2 / n) W r_i (first-order perturbation of a simple eigenvalue).
+PSB_HD_COLD double gyration_cv(int mode, int ja, int jb, const double* g, double* W) {
+  double a[16], v[16];
+  for (int i = 0; i < 16; ++i) a[i] = 0.0;
+  a[0] = g[0]; a[1] = g[1]; a[2] = g[2];
+  a[4] = g[1]; a[5] = g[3]; a[6] = g[4];
+  a[8] = g[2]; a[9] = g[4]; a[10] = g[5];
+  jacobi_eig(3, a, v);
+  int o[3] = {0, 1, 2};  // ascending order of the diagonal
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2 - i; ++j)
+      if (a[o[j] * 4 + o[j]] > a[o[j + 1] * 4 + o[j + 1]]) { int t = o[j]; o[j] = o[j + 1]; o[j + 1] = t; }
+  const double l0 = a[o[0] * 4 + o[0]], l1 = a[o[1] * 4 + o[1]], l2 = a[o[2] * 4 + o[2]];
+  const double l[3] = {l0, l1, l2};
+  double w[3] = {0.0, 0.0, 0.0}, xi;
+  if (mode <= 2) {
+    xi = l[mode];
+    w[mode] = 1.0;
+  } else if (mode == 3) {
+    xi = l2 - (l0 + l1) / 2;
+    w[0] = -0.5; w[1] = -0.5; w[2] = 1.0;
+  } else if (mode == 4) {
+    xi = l[jb] - l[ja];
+    w[jb] += 1.0; w[ja] -= 1.0;
+  } else {
+    const double s1 = l0 + l1 + l2, s2 = l0 * l0 + l1 * l1 + l2 * l2;
+    xi = (3 * s2 / (s1 * s1) - 1) / 2;
+    for (int k = 0; k < 3; ++k) w[k] = 3.0 * l[k] / (s1 * s1) - 3.0 * s2 / (s1 * s1 * s1);
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += w[k] * v[i * 4 + o[k]] * v[j * 4 + o[k]];
+      W[i * 3 + j] = s;
+    }
+  return xi;
+}
+
 // orientation.py:33-73 (Kabsch with the reflection fix): the proper rotation U (row-vector
 // convention, P @ U ~ Q) maximising tr(U^T C), C = P^T Q (row-major c[9]).  General path: Horn's
 // quaternion eigenproblem (4x4 symmetric, Jacobi), which yields the same U as

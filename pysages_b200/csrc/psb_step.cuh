@@ -174,6 +174,7 @@ __host__ __device__ __forceinline__ int nacc_for_kind(int kind, int pass, bool m
   if (pass == 0) {
     if (is_point_kind(kind)) return momenta_sums ? 6 : 3;
     if (kind == PSB_CV_ROG) return 1;
+    if (kind == PSB_CV_GYRATION) return 6;
     if (kind == PSB_CV_RMSD) return 15;
     return 0;
   }
@@ -311,6 +312,14 @@ static __device__ __noinline__ void finalize_cv_A(const Model& M, StepShared& sh
     } break;
     case PSB_CV_COORDINATION: {
       f.xi[cv.comp0] = sh.tot[g0][0];
+    } break;
+    case PSB_CV_GYRATION: {  // shape.py:85-344
+      const double inv_n = M.grp[g0].inv_n;
+      double gt[6];
+      for (int a = 0; a < 6; ++a) gt[a] = sh.tot[g0][a] * inv_n;
+      double* x = f.cvx[c];
+      f.xi[cv.comp0] = gyration_cv(cv.axis, cv.nn, cv.mm, gt, x);
+      for (int a = 0; a < 9; ++a) x[a] *= 2.0 * inv_n;  // d xi / d r_i = x r_i
     } break;
     default: break;
   }
@@ -678,6 +687,9 @@ __device__ __forceinline__ void fin_load(const Model& M, StepShared& sh) {
 static __device__ __noinline__ void accumulate_nonpoint(const CvDev& cv, double inv_n, uint32_t t, V3 r, double* acc) {
   if (cv.kind == PSB_CV_ROG) {
     acc[0] += r.x * r.x + r.y * r.y + r.z * r.z;
+  } else if (cv.kind == PSB_CV_GYRATION) {  // shape.py:118-135: sum_i r_i r_i^T (uncentred, like the reference)
+    acc[0] += r.x * r.x; acc[1] += r.x * r.y; acc[2] += r.x * r.z;
+    acc[3] += r.y * r.y; acc[4] += r.y * r.z; acc[5] += r.z * r.z;
   } else if (cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
     const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : inv_n;
     const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
@@ -719,6 +731,11 @@ __device__ __forceinline__ double rmsd_residual(const CvDev& cv, const double* x
 static __device__ __noinline__ V3 nonpoint_gradient(const Fin& f, const CvDev& cv, int c, double inv_n,
                                                     uint32_t t, V3 r) {
   if (cv.kind == PSB_CV_ROG) return f.cvx[c][0] * r;
+  if (cv.kind == PSB_CV_GYRATION) {
+    const double* x = f.cvx[c];
+    return v3(x[0] * r.x + x[1] * r.y + x[2] * r.z, x[3] * r.x + x[4] * r.y + x[5] * r.z,
+              x[6] * r.x + x[7] * r.y + x[8] * r.z);
+  }
   if (cv.kind == PSB_CV_RMSD) {
     const double* x = f.cvx[c];
     const double P[3] = {r.x - x[9], r.y - x[10], r.z - x[11]};

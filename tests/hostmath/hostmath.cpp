@@ -30,6 +30,7 @@ double hm_dihedral(const double* p, double* g) {
   return v;
 }
 
+double hm_gyration(int mode, int ja, int jb, const double* g6, double* W9) { return gyration_cv(mode, ja, jb, g6, W9); }
 void hm_kabsch(const double* C, double* U) { kabsch_rotation(C, U); }
 void hm_kabsch_eig(const double* C, double* U) { kabsch_rotation_eig(C, U); }
 

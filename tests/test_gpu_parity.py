@@ -484,3 +484,37 @@ def test_run_cycle_graph_replay_matches_single_steps_and_oracle(method, launch_s
         close(nat_g.view("centers").cpu().numpy().reshape(-1, 2), ostate.centers.numpy(), X64_RTOL, what="centers")
     for a, o in zip(snaps_g, osnaps):
         close(a.forces.cpu().numpy()[:, :3], o.forces[:, :3], 1e-9, what="forces after %d steps" % nsteps)
+
+
+# ---- gyration-tensor CVs (colvars/shape.py:85-344) -------------------------------------
+GYRATION_CVS = {
+    "principal-moments": [("PrincipalMoment", (list(range(20, 220)), 0), {}), ("PrincipalMoment", (list(range(20, 220)), 2), {})],
+    "asphericity+anisotropy": [("Asphericity", (list(range(20, 220)),), {}), ("ShapeAnisotropy", (list(range(250, 330)),), {})],
+    "acylindricity-xy-xz": [("Acylindricity", (list(range(20, 220)),), dict(axes="xy")),
+                            ("Acylindricity", (list(range(230, 300)),), dict(axes="xz"))],
+    "acylindricity-yz-is-zero": [("Acylindricity", (list(range(20, 220)),), dict(axes="yz")),
+                                 ("PrincipalMoment", (list(range(230, 300)), 1), {})],
+}
+
+
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float32), ("hoomd", np.float64), ("lammps", np.float64),
+                                           ("openmm-cuda", np.float64)])
+@pytest.mark.parametrize("cvname", list(GYRATION_CVS))
+def test_gyration_tensor_cvs_harmonic(layout, dtype, cvname):
+    snap = snapshot(layout, dtype, n=400, globule=True)
+    run = ParityRun(snap, GYRATION_CVS[cvname], harmonic([0.7, 0.3], [1.0, 2.0]))
+    traj = synthetic.make_trajectory(snap, frames=2, step=0.05)
+    for f in range(2):
+        run.step(traj[f])
+    if cvname == "acylindricity-yz-is-zero":  # the reference's index quirk (shape.py:240, 285)
+        assert float(run.state.xi.cpu().numpy().ravel()[0]) == 0.0
+
+
+def test_gyration_tensor_metadynamics_grid():
+    snap = snapshot("hoomd", np.float64, n=400, globule=True)
+    cvs = [("Asphericity", (list(range(0, 300)),), {})]
+    kw = dict(height=0.5, sigma=[0.3], stride=2, ngaussians=8, grid=((0.0,), (40.0,), (64,), "regular"))
+    run = ParityRun(snap, cvs, ("Metadynamics", kw))
+    for pos in synthetic.make_trajectory(snap, frames=5, step=0.05):
+        run.step(pos)
+    assert int(run.state.idx) == 2

@@ -29,6 +29,8 @@ def hm():
         getattr(lib, name).restype = ctypes.c_double
         getattr(lib, name).argtypes = [dp, dp]
     lib.hm_kabsch.argtypes = [dp, dp]
+    lib.hm_gyration.restype = ctypes.c_double
+    lib.hm_gyration.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
     lib.hm_kabsch_eig.argtypes = [dp, dp]
     lib.hm_grid_index.restype = ctypes.c_uint
     lib.hm_grid_index.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
@@ -61,6 +63,30 @@ def test_point_cv_gradients_match_autodiff(hm, name, fn, npts):
         (gref,) = torch.autograd.grad(ref, t)
         assert abs(val - ref.item()) <= 1e-13 * max(1.0, abs(ref.item()))
         assert np.allclose(g, gref.numpy(), rtol=1e-10, atol=1e-13)
+
+
+def test_gyration_tensor_cvs_match_autodiff(hm):
+    """shape.py:85-344: value and per-atom gradient (2/n) W r_i against torch autograd through eigvalsh."""
+    rng = np.random.default_rng(21)
+    fns = [(0, 0, 0, lambda r: colvars.principal_moments(r)[0]), (1, 0, 0, lambda r: colvars.principal_moments(r)[1]),
+           (2, 0, 0, lambda r: colvars.principal_moments(r)[2]), (3, 0, 0, colvars.asphericity),
+           (4, 1, 2, lambda r: colvars.acylindricity(r, (1, 2))), (4, 2, 2, lambda r: colvars.acylindricity(r, (2, 3))),
+           (4, 1, 2, lambda r: colvars.acylindricity(r, (1, 3))), (5, 0, 0, colvars.shape_anisotropy)]
+    for n in (5, 40, 700):
+        r = torch.tensor(rng.normal(size=(n, 3)) * np.array([1.0, 2.0, 0.5]) + rng.normal(size=3), requires_grad=True)
+        G = (r.detach().numpy().T @ r.detach().numpy()) / n
+        g6 = np.array([G[0, 0], G[0, 1], G[0, 2], G[1, 1], G[1, 2], G[2, 2]])
+        for mode, ja, jb, fn in fns:
+            W = np.zeros(9)
+            val = hm.hm_gyration(mode, ja, jb, _ptr(g6), _ptr(W))
+            ref = fn(r)
+            if ref.requires_grad:
+                (gref,) = torch.autograd.grad(ref, r)
+            else:
+                gref = torch.zeros_like(r)
+            assert abs(val - ref.item()) <= 1e-12 * max(1.0, abs(ref.item()))
+            grad = (2.0 / n) * r.detach().numpy() @ W.reshape(3, 3).T
+            assert np.allclose(grad, gref.numpy(), rtol=1e-9, atol=1e-12 * np.abs(gref.numpy()).max() + 1e-15)
 
 
 def test_kabsch_matches_svd_reference(hm, golden):
