@@ -6,6 +6,7 @@ runs in hand-written sm_100a CUDA kernels behind the C ABI of include/pysages_b2
 """
 
 from . import backends, colvars, grids, methods  # noqa: F401
+from .backends.core import supported_backends  # noqa: F401
 from .core import Result, analyze, run  # noqa: F401
 from .grids import Chebyshev, Grid, Periodic, Regular  # noqa: F401
 from .methods import CVRestraints  # noqa: F401

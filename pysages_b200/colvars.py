@@ -300,3 +300,13 @@ def get_periods(cvs):
         p = 2 * math.pi if type(cv) in (Angle, DihedralAngle) else math.inf
         out += [p] * cv.ncomponents
     return out
+
+
+def wrap(x, P):
+    """colvars/utils.py:22-26: x - [|x| > P/2] * sign(x) * P, identity where P is inf (host helper for
+    analysis code; on the device the same rule is `wrap_period` in csrc/psb_math.cuh)."""
+    x = np.asarray(x, dtype=np.float64)
+    P = np.asarray(P, dtype=np.float64)
+    finite = np.isfinite(P)
+    Pf = np.where(finite, P, 0.0)
+    return np.where(finite & (np.abs(x) > Pf / 2), x - np.sign(x) * Pf, x)

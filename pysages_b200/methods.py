@@ -531,3 +531,7 @@ class UmbrellaIntegration(SamplingMethod):
 
     def build(self):  # pylint: disable=arguments-differ
         """The sampling work is delegated to the HarmonicBias windows (umbrella_integration.py:123-125)."""
+
+
+# names the reference exports from pysages.methods (methods/__init__.py)
+from .utils import HistogramLogger, MetaDLogger, ReplicasConfiguration, SerialExecutor  # noqa: E402,F401
