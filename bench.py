@@ -366,25 +366,33 @@ def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, 
     from pysages_b200 import parallel
 
     mine = parallel.partition_windows(nwindows, world, rank)
-    frames, L, _ = device_hoomd_frames(natoms, 8, device, seed=20240 + 5500 + rank)
-    snaps = snapshots_of(frames, L, 0.005)
-    cvs, m = workload_specs("window", natoms, L)
-    natives = []
-    for w in mine:
+    natives, all_descs, keep = [], [], []
+    for w in mine:  # every window is its own simulation: own engine arrays, own handle
+        frames, L, _ = device_hoomd_frames(natoms, 4, device, seed=20240 + 5500 + w)
+        snaps = snapshots_of(frames, L, 0.005)
+        cvs, m = workload_specs("window", natoms, L)
         mm = (m[0], dict(m[1], center=[-L / 4 + (L / 2) * w / max(nwindows - 1, 1)]))
         natives.append(build_ours(cvs, mm, snaps[0]))
-    descs = snapdesc_array(natives[0][1], snaps)
-    for _, nat in natives:
-        time_cycle(nat, descs, 20, 5, stream)
+        all_descs.append(snapdesc_array(natives[-1][1], snaps))
+        keep.append((frames, snaps))
+    from pysages_b200 import _native as N
+
+    # one CUDA stream per window: the windows are independent simulations whose small step kernels
+    # (a few CTAs each) run concurrently on the one GPU
+    streams = [torch.cuda.Stream(device=device) for _ in natives]
+    for (_, nat), descs, st in zip(natives, all_descs, streams):
+        time_cycle(nat, descs, 20, 5, st)
+    torch.cuda.synchronize(device)
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    from pysages_b200 import _native as N
-
-    sp = ctypes.c_void_p(stream.cuda_stream)
     e0.record(stream)
-    for _, nat in natives:
-        N.check(nat.lib.psb_run_cycle(nat.handle, descs, len(descs), steps, sp))
+    for st in streams:
+        st.wait_stream(stream)
+    for (_, nat), descs, st in zip(natives, all_descs, streams):
+        N.check(nat.lib.psb_run_cycle(nat.handle, descs, len(descs), steps, ctypes.c_void_p(st.cuda_stream)))
+    for st in streams:
+        stream.wait_stream(st)
     e1.record(stream)
     stream.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -392,7 +400,7 @@ def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     means = parallel.gather_window_means({w: nat.view("xi").cpu().numpy().ravel()[:1] for w, (_, nat) in zip(mine, natives)}, nwindows)
     return dict(workload=f"cfg5 umbrella: {nwindows} HarmonicBias windows (Component CV over 1000 atoms, N={natoms}) "
-                         f"round-robin over {world} GPU(s), {steps} steps each",
+                         f"round-robin over {world} GPU(s), one CUDA stream per window, {steps} steps each",
                 windows=nwindows, steps_per_s=round(nwindows * steps / (float(t.item()) * 1e-3), 1),
                 windows_gathered=int(means.shape[0]))
 
