@@ -80,6 +80,29 @@ def snapshots_of(frames, L, dt):
             for f in frames]
 
 
+def device_layout_snapshots(layout, dtype, natoms, nframes, device, seed):
+    """Snapshots in any engine layout (numpy generator of pysages_b200.synthetic, uploaded once): every frame
+    owns its arrays; positions follow a random-walk trajectory."""
+    from pysages_b200 import synthetic
+    from pysages_b200.backends.snapshot import Box, Snapshot
+
+    base = synthetic.make_snapshot(natoms, layout=layout, dtype=dtype, seed=seed)
+    traj = synthetic.make_trajectory(base, frames=nframes, step=0.02)
+    box = Box(base["box_H"], base["origin"])
+    out = []
+    for f in range(nframes):
+        a = {k: torch.as_tensor(np.ascontiguousarray(v)).to(device) for k, v in base["arrays"].items()}
+        a["positions"] = torch.as_tensor(np.ascontiguousarray(traj[f])).to(device)
+        if layout == "openmm-cuda":
+            out.append(Snapshot(a["positions"], a["vel_mass"], a["forces"], a["ids"], box, base["dt"]))
+        elif layout == "lammps":
+            out.append(Snapshot(a["positions"], (a["velocities"], (a["masses"], a["types"])), a["forces"],
+                                a["tags_map"][1:], box, base["dt"], dict(images=a["images"])))
+        else:
+            raise ValueError(layout)
+    return out, base["L"]
+
+
 def host_arrays(frame, L, dt):
     a = {k: v.cpu().numpy() for k, v in frame.items()}
     return dict(arrays=a, box_H=np.diag([L, L, L]), origin=np.full(3, -L / 2), dt=dt, L=L, layout="hoomd",
@@ -118,7 +141,7 @@ def workload_specs(name, natoms, L):
     raise ValueError(name)
 
 
-def build_ours(cv_specs, method_spec, snapshot):
+def build_ours(cv_specs, method_spec, snapshot, layout="hoomd"):
     """Public-API construction of the method (no oracle import on this path)."""
     import pysages_b200 as ps
     from pysages_b200.backends import mock
@@ -142,7 +165,7 @@ def build_ours(cv_specs, method_spec, snapshot):
         if kw.get("grid") is None:
             kw.pop("grid", None)
         method = ps.methods.Metadynamics(cvs, *args, kw.pop("deltaT", None), **kw)
-    helpers = HelperMethods(None, lambda: 3, lambda x: x, mock.LAYOUTS["hoomd"])
+    helpers = HelperMethods(None, lambda: 3, lambda x: x, mock.LAYOUTS[layout])
     _, init, update = method.build(snapshot, helpers)
     init()
     return method, update.native
@@ -460,6 +483,24 @@ def run_series(device, stream, hbm):
         frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977, sorted_tags=sorted_tags)
         measure(f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), name, natoms, steps, frames, L)
         del frames
+
+    # the headline workload on the other engine layouts (OpenMM-CUDA: fixed-point forces, permuted order,
+    # one extra inverse-permutation kernel per step; LAMMPS: (N,3) doubles, packed images, per-type masses)
+    for layout, dtype in (("openmm-cuda", np.float32), ("lammps", np.float64)):
+        snaps, L = device_layout_snapshots(layout, dtype, 100_000, 16, device, seed=20240 + 2000)
+        cvs, m = workload_specs("abf2d", 100_000, L)
+        method, native = build_ours(cvs, m, snaps[0], layout=layout)
+        ms, launches = time_cycle(native, snapdesc_array(native, snaps), 2000, 20, stream)
+        info = native.launch_info()
+        us = ms * 1e3 / 2000
+        gbs = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
+        out.append(dict(workload=f"abf2d S=N=100000 {layout}-{'f32' if dtype == np.float32 else 'f64'}",
+                        steps_per_s=round(2000 / (ms * 1e-3), 1), us_per_step=round(us, 3),
+                        algorithmic_bytes=info["algorithmic_bytes_per_step"], achieved_gbs=round(gbs, 1),
+                        frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"],
+                        launches_per_step=round(launches / 2000, 2), distinct_snapshots=len(snaps)))
+        del snaps, native, method
+        torch.cuda.empty_cache()
 
     # cfg1: alanine-dipeptide-sized well-tempered metadynamics on two dihedrals (latency only)
     frames, L, _ = device_hoomd_frames(22, 64, device, seed=20240 + 1000, dtype=torch.float64)
