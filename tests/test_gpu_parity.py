@@ -518,3 +518,28 @@ def test_gyration_tensor_metadynamics_grid():
     for pos in synthetic.make_trajectory(snap, frames=5, step=0.05):
         run.step(pos)
     assert int(run.state.idx) == 2
+
+
+# ---- ABF: the J J^T special cases -----------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["component+distance-disjoint", "distances-sharing-atoms",
+                                  "distance-overlapping-own-groups", "four-components"])
+def test_abf_jjt_cases(case):
+    """psb_create inverts J J^T once when it cannot depend on positions (Component / Distance /
+    Displacement CVs, no atom shared between CVs); every other combination assembles it per step."""
+    snap = snapshot("hoomd", np.float64, n=500, seed=77)
+    X, Y = list(range(10, 60)), list(range(200, 230))
+    if case == "component+distance-disjoint":
+        cvs = [("Component", (list(range(300, 340)), 1), {}), ("Distance", ([X, Y],), {})]
+        grid = ((-12.0, 0.0), (12.0, 14.0), (8, 8), "regular")
+    elif case == "distances-sharing-atoms":  # atoms 40..59 belong to both CVs: J J^T has off-diagonal terms
+        cvs = [("Distance", ([X, Y],), {}), ("Distance", ([list(range(40, 90)), list(range(300, 320))],), {})]
+        grid = ((0.0, 0.0), (14.0, 14.0), (8, 8), "regular")
+    elif case == "distance-overlapping-own-groups":  # the two groups of ONE Distance CV overlap
+        cvs = [("Distance", ([list(range(10, 60)), list(range(40, 100))],), {})]
+        grid = ((0.0,), (14.0,), (16,), "regular")
+    else:
+        cvs = [("Component", (list(range(i * 50, i * 50 + 30)), i % 3), {}) for i in range(4)]
+        grid = ((-12.0,) * 4, (12.0,) * 4, (4, 4, 4, 4), "regular")
+    run = ParityRun(snap, cvs, ("ABF", dict(grid=grid, N=3)))
+    for pos in perturbed(snap, 5, 0.08):
+        run.step(pos)
