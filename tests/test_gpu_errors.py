@@ -1,0 +1,54 @@
+"""C-ABI error behaviour on the GPU box: status codes map to the reference's exception types and a
+failed psb_create leaves nothing behind."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import pysages_b200 as ps
+from parity_utils import device_helpers, device_snapshot
+from pysages_b200 import _native as N
+from pysages_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def build(method, snap, layout="hoomd"):
+    return method.build(device_snapshot(snap), device_helpers(layout))
+
+
+def test_create_errors_map_to_reference_exception_types():
+    snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
+    with pytest.raises(ValueError, match="out of range"):
+        build(ps.methods.HarmonicBias([ps.colvars.Distance([5, 100])], 1.0, [0.0]), snap)
+    with pytest.raises(ValueError, match="between 1 and 4 collective variables"):
+        cvs = [ps.colvars.DihedralAngle([i, i + 1, i + 2, i + 3]) for i in range(0, 20, 4)]
+        build(ps.methods.Unbiased(cvs[:4] + [ps.colvars.Component([50], 0)]), snap)
+    with pytest.raises(ValueError, match="at most"):
+        build(ps.methods.Unbiased([ps.colvars.Displacement([0, 1]), ps.colvars.Displacement([2, 3])]), snap)
+    with pytest.raises(ValueError, match="sigma must be positive"):
+        build(ps.methods.Metadynamics([ps.colvars.Distance([0, 1])], 1.0, [0.0], 5, 10), snap)
+    with pytest.raises(ValueError, match="stride"):
+        build(ps.methods.Metadynamics([ps.colvars.Distance([0, 1])], 1.0, [0.1], 0, 10), snap)
+    with pytest.raises(NotImplementedError, match="CoordinationNumber supports"):
+        build(ps.methods.HarmonicBias([ps.colvars.CoordinationNumber([[0, 1], [2, 3]], n=5, m=10)], 1.0, [0.0]), snap)
+    with pytest.raises(ValueError, match="references"):  # wrong number of reference rows
+        ps.colvars.RMSD(list(range(10)), np.zeros((9, 3)))
+
+
+def test_step_errors():
+    snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
+    _, init, update = build(ps.methods.HarmonicBias([ps.colvars.Distance([1, 2])], 1.0, [0.0]), snap)
+    native = update.native
+    d = N.SnapshotDesc()  # all pointers NULL
+    assert native.lib.psb_step(native.handle, ctypes.byref(d), 0, None) == N.ERR_VALUE
+    assert b"positions is NULL" in native.lib.psb_last_error()
+    with pytest.raises(KeyError):
+        native.set_state("hist", np.zeros(4))  # HarmonicBias has no histogram
+    assert native.view("heights") is None
+    n = ctypes.c_int64()
+    assert native.lib.psb_state_info(native.handle, b"no-such-field", ctypes.byref(n), None, None) == N.ERR_KEY
+    state = update(device_snapshot(snap), init())
+    torch.cuda.synchronize()
+    assert int(state.ncalls) == 1
