@@ -456,6 +456,29 @@ class Metadynamics(SamplingMethod):
         self._set_grid(d)
         return d
 
+    def build(self, snapshot, helpers, *args, **kwargs):
+        """With `shared_hills=True` (multiple walkers, one process per walker / GPU under torchrun) every
+        deposit step becomes psb_walker_begin -> all-gather of the hill records -> psb_walker_finish;
+        with a single process the exchange is the identity and the result equals plain metadynamics."""
+        snapshot, initialize, update = super().build(snapshot, helpers, *args, **kwargs)
+        if not self.shared_hills:
+            return snapshot, initialize, update
+        from . import parallel
+
+        native = update.native
+        if native.host_buffers:
+            raise NotImplementedError("shared-hill walkers need device-resident engine arrays")
+        engine = parallel.NativeWalkerEngine(native)
+        exchange = kwargs.get("exchange") or parallel.RecordExchange()
+
+        def walker_update(snapshot, state, timestep=0):
+            parallel.walker_step(engine, snapshot, exchange, timestep)
+            return self._make_state(native)
+
+        walker_update.native = native
+        walker_update.exchange = exchange
+        return snapshot, initialize, walker_update
+
     def _make_state(self, native):
         k = native.k
         bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None

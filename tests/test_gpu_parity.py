@@ -543,3 +543,19 @@ def test_abf_jjt_cases(case):
     run = ParityRun(snap, cvs, ("ABF", dict(grid=grid, N=3)))
     for pos in perturbed(snap, 5, 0.08):
         run.step(pos)
+
+
+@pytest.mark.parametrize("grid", [None, ((-math.pi, -math.pi), (math.pi, math.pi), (20, 20), "periodic")])
+def test_shared_hills_single_walker_equals_plain_metadynamics(golden, grid):
+    """Metadynamics(shared_hills=True) through the public build()/update() path with one process: the
+    begin -> (identity exchange) -> finish split of a deposit step reproduces the fused step."""
+    kw = dict(height=1.2, sigma=[0.35, 0.35], stride=3, ngaussians=12, grid=grid, deltaT=5000.0, kB=0.0083144626)
+    snap = adp(golden, layout="hoomd")
+    plain = ParityRun(snap, ADP_CVS, ("Metadynamics", kw))
+    shared = ParityRun(snap, ADP_CVS, ("Metadynamics", dict(kw, shared_hills=True)))
+    for pos in perturbed(snap, 10, 0.02):
+        plain.step(pos)
+        shared.step(pos)  # also checked against the oracle's plain metadynamics
+    for name in ("heights", "centers", "idx"):
+        assert torch.equal(getattr(plain.state, name), getattr(shared.state, name)), name
+    assert int(shared.state.idx) == 3
