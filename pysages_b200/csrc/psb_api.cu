@@ -571,9 +571,16 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     bool wanted = (long long)M.T > (long long)CT * BLOCK * h->grid && 2LL * M.T >= layout->natoms;
     if (const char* env = getenv("PSB_SLOT_MAJOR")) wanted = atoi(env) != 0;
     M.slot_major = (eligible && wanted) ? 1 : 0;
-    if (M.slot_major &&
-        (long long)pick_vtable(*layout)->occupancy(h->step_method, SC_SLOT, h->dyn_smem) * h->num_sms < h->grid)
-      M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
+    if (M.slot_major) {
+      const int occ_slot = pick_vtable(*layout)->occupancy(h->step_method, SC_SLOT, h->dyn_smem);
+      if (occ_slot < 1) {
+        M.slot_major = 0;
+      } else if (!getenv("PSB_GRID_BLOCKS")) {
+        h->grid = std::min(occ_slot, SLOT_CTAS_PER_SM) * h->num_sms;  // streaming: fill the machine
+      } else if ((long long)occ_slot * h->num_sms < h->grid) {
+        M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
+      }
+    }
     if (M.slot_major) {
       h->step_general = SC_SLOT;
       psb_status st = dev_alloc(h, &M.slot_map, (size_t)layout->natoms);

@@ -40,6 +40,10 @@ enum StepMethod { SM_UNBIASED = 0, SM_HARMONIC = 1, SM_METAD_DIRECT = 2, SM_ABF 
 // gather / scatter (most atoms of a very large system selected), kept in its own instantiation so its
 // register and code footprint stay out of the latency-critical kernels.
 enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_COUNT = 3 };
+#ifndef PSB_SLOT_CTAS
+#define PSB_SLOT_CTAS 2
+#endif
+constexpr int SLOT_CTAS_PER_SM = PSB_SLOT_CTAS;  // streaming class: more resident warps, fewer registers
 
 // ---- small device utilities -----------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -801,7 +805,7 @@ __device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
 
 // ---- the kernel -------------------------------------------------------------------------------
 template <int LAYOUT, typename Real, int METHOD, int CLASS>
-__global__ void __launch_bounds__(BLOCK, 2)
+__global__ void __launch_bounds__(BLOCK, (CLASS == SC_SLOT) ? SLOT_CTAS_PER_SM : 2)
 step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   constexpr bool GENERAL = (CLASS == SC_GENERAL);
   constexpr bool SLOT = (CLASS == SC_SLOT);
