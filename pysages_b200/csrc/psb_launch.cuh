@@ -2,6 +2,8 @@
 // for one engine layout / dtype and exports one table, so translation units build in parallel.
 #pragma once
 
+#include <cstdlib>
+
 #include "psb_device.cuh"
 #include "psb_step.cuh"
 
@@ -43,6 +45,20 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
                                    size_t smem, cudaStream_t stream) {                              \
     void* args[] = {(void*)&M, (void*)S}; /* M: device pointer, S: by value */                     \
     const void* fn = NAME##_entry[method][general];                                         \
+    /* programmatic dependent launch: the next step's launch + model copy overlap this step's tail   \
+       (griddepcontrol.* in step_kernel); PSB_NO_PDL=1 falls back to plain stream order */          \
+    static const bool pdl = getenv("PSB_NO_PDL") == nullptr;                                        \
+    if (pdl) {                                                                                      \
+      cudaLaunchConfig_t cfg = {};                                                                  \
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
+      cudaLaunchAttribute at[2];                                                                    \
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                \
+      at[0].val.programmaticStreamSerializationAllowed = 1;                                         \
+      at[1].id = cudaLaunchAttributeCooperative;                                                    \
+      at[1].val.cooperative = grid > 1 ? 1 : 0;                                                     \
+      cfg.attrs = at; cfg.numAttrs = 2;                                                             \
+      return cudaLaunchKernelExC(&cfg, fn, args);                                                   \
+    }                                                                                               \
     if (grid > 1) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(BLOCK), args, smem, stream); \
     return cudaLaunchKernel(fn, dim3(1), dim3(BLOCK), args, smem, stream);                          \
   }                                                                                                 \

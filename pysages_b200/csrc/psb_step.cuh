@@ -826,7 +826,12 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     static_assert(sizeof(Model) % 8 == 0, "Model is copied in 8-byte words");
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(Mglobal);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sM);
+    // Programmatic dependent launch (when the host enables it): the next step's launch and this copy
+    // of the immutable model overlap the previous step's tail; everything after the wait sees the
+    // previous kernel complete.  Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = __ldg(src + i);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   __syncthreads();
   const Model& M = sM;
