@@ -236,6 +236,12 @@ int32_t psb_next_step_deposits(psb_handle* h);
 psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64_t n,
                           uint32_t* out_host);
 /* Kernel launches issued since creation (for bench.py's gpu_launches) and the launch shape. */
+/* Options: "pdl" (default 1; PSB_NO_PDL=1 in the environment sets 0): consecutive step kernels of a
+ * stream use programmatic dependent launch -- the next step's launch, model copy and its gather of the
+ * engine arrays this library never writes (ids, positions, images, velocities) overlap the previous
+ * step's finalizer / scatter; forces, method state and workspaces are touched only after the previous
+ * kernel has completed.  A kernel that follows an engine kernel is never launched early. */
+psb_status psb_set_option(psb_handle* h, const char* name, int64_t value);
 int64_t psb_launch_count(psb_handle* h);
 /* 1 when the last psb_run_cycle replayed a CUDA graph, 0 when it issued plain launches. */
 int32_t psb_cycle_uses_graph(psb_handle* h);

@@ -117,6 +117,7 @@ EXPORTS = {
     "psb_walker_record_doubles": (c_int32, [c_void_p]),
     "psb_next_step_deposits": (c_int32, [c_void_p]),
     "psb_grid_index": (c_int32, [POINTER(GridDesc), POINTER(c_double), c_int64, POINTER(c_uint32)]),
+    "psb_set_option": (c_int32, [c_void_p, c_char_p, c_int64]),
     "psb_launch_count": (c_int64, [c_void_p]),
     "psb_cycle_uses_graph": (c_int32, [c_void_p]),
     "psb_launch_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),

@@ -59,6 +59,7 @@ struct psb_handle {
   int grid = 1;
   size_t dyn_smem = 0;
   int cooperative = 0;
+  int pdl = 1;           // programmatic dependent launch between consecutive step kernels (psb_set_option)
   int step_method = 0;   // StepMethod code of the kernel instantiation
   int step_general = 0;  // StepClass code of the kernel instantiation
   long long launches = 0;
@@ -192,7 +193,7 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
       CUDA_TRY(cudaMemsetAsync(M.jac_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms * M.k, stream));
   }
   CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, h->step_general, h->d_model, &S, h->grid,
-                                               h->dyn_smem, stream));
+                                               h->dyn_smem, stream, h->pdl));
   ++h->launches;
   return PSB_OK;
 }
@@ -686,6 +687,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     cudaError_t e = cudaMemcpy(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(fail(PSB_ERR_CUDA, "CUDA error %s uploading the model", cudaGetErrorString(e)));
   }
+  if (getenv("PSB_NO_PDL")) h->pdl = 0;
   *out = h;
   return PSB_OK;
 }
@@ -968,6 +970,19 @@ psb_status psb_latency_probe(double* out_host16) {
   cudaFree(d);
   if (e != cudaSuccess) return fail(PSB_ERR_CUDA, "CUDA error %s in psb_latency_probe", cudaGetErrorString(e));
   return PSB_OK;
+}
+
+psb_status psb_set_option(psb_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(PSB_ERR_VALUE, "NULL argument");
+  const std::string n(name);
+  if (n == "pdl") {
+    h->pdl = value ? 1 : 0;
+    if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);  // captured launches carry the old attribute
+    h->cycle_exec = nullptr;
+    h->cycle_key.clear();
+    return PSB_OK;
+  }
+  return fail(PSB_ERR_KEY, "unknown option '%s'", name);
 }
 
 int64_t psb_launch_count(psb_handle* h) { return h ? h->launches : 0; }

@@ -12,7 +12,7 @@ namespace psb {
 struct StepVTable {
   // `method` is a StepMethod code, `general` a StepClass code (psb_step.cuh)
   cudaError_t (*launch_step)(int method, int general, const Model* M, const Snap* S, int grid, size_t dyn_smem,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int pdl);
   int (*occupancy)(int method, int general, size_t dyn_smem);
   void (*launch_gather)(const Model* M, const Snap* S, int cv, double* xa, int na_pad, double* xb,
                         int nb_pad, cudaStream_t stream);
@@ -42,12 +42,11 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
       PSB_STEP_ROW(L, R, SM_UNBIASED), PSB_STEP_ROW(L, R, SM_HARMONIC), PSB_STEP_ROW(L, R, SM_METAD_DIRECT), \
       PSB_STEP_ROW(L, R, SM_ABF), PSB_STEP_ROW(L, R, SM_METAD_GRID)};                               \
   static cudaError_t NAME##_launch(int method, int general, const Model* M, const Snap* S, int grid, \
-                                   size_t smem, cudaStream_t stream) {                              \
+                                   size_t smem, cudaStream_t stream, int pdl) {                     \
     void* args[] = {(void*)&M, (void*)S}; /* M: device pointer, S: by value */                     \
     const void* fn = NAME##_entry[method][general];                                         \
     /* programmatic dependent launch: the next step's launch + model copy overlap this step's tail   \
-       (griddepcontrol.* in step_kernel); PSB_NO_PDL=1 falls back to plain stream order */          \
-    static const bool pdl = getenv("PSB_NO_PDL") == nullptr;                                        \
+       (griddepcontrol.* in step_kernel); pdl == 0: plain stream order */                            \
     if (pdl) {                                                                                      \
       cudaLaunchConfig_t cfg = {};                                                                  \
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \

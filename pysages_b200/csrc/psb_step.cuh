@@ -107,6 +107,7 @@ __device__ __forceinline__ long long global_ns() {
 
 struct StepShared {
   double red[NWARPS][NACC];
+  double stage[NACC];  // this CTA's block-reduced pass-A sums, published to `partials` after griddepcontrol.wait
   double tot[MAXG + 1][NACC];
   Fin fin;  // this CTA's copy of the finalizer results
   Pre pre;  // method-state scalars as they were when the step began
@@ -826,12 +827,12 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     static_assert(sizeof(Model) % 8 == 0, "Model is copied in 8-byte words");
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(Mglobal);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sM);
-    // Programmatic dependent launch (when the host enables it): the next step's launch and this copy
-    // of the immutable model overlap the previous step's tail; everything after the wait sees the
-    // previous kernel complete.  Without the launch attribute both instructions are no-ops.
+    // Programmatic dependent launch (when the host enables it): the next step's launch, this copy of
+    // the immutable model and -- see pass A -- its gather of engine arrays this library never writes
+    // overlap the previous step's tail; everything after griddepcontrol.wait sees the previous kernel
+    // complete.  Without the launch attribute both instructions are no-ops.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = __ldg(src + i);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   __syncthreads();
   const Model& M = sM;
@@ -855,6 +856,99 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   constexpr bool slot_major = SLOT;  // the host picks this instantiation only for multi-CTA, non-walker handles
   const bool will_scatter = (METHOD != SM_UNBIASED) &&
                             (S.mode == MODE_STEP || (WALK && S.mode == MODE_WALKER_FINISH));
+
+  // ---- this CTA's terms ----------------------------------------------------------------------
+  // gridDim.x > 1: exactly one group per CTA, an even share of its terms; gridDim.x == 1: all terms.
+  // Up to CT terms per thread are "cached": slot, group, position and the prefetched force row stay
+  // in registers until the scatter.
+  int seg_g = -1;
+  uint32_t lo = 0, hi = 0;
+  if (!skip_cv) {
+    if (slot_major) {
+      // no per-CTA group: handled by the slot-ordered passes below
+    } else if (nb > 1) {
+      for (int g = 0; g < M.ngroups; ++g)
+        if (b >= M.cta_lo[g] && b <= M.cta_hi[g]) seg_g = g;
+      if (seg_g >= 0) {
+        const GroupDev& G = M.grp[seg_g];
+        const uint32_t nc = (uint32_t)(M.cta_hi[seg_g] - M.cta_lo[seg_g] + 1);
+        const uint32_t per = (G.t1 - G.t0 + nc - 1) / nc;
+        lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_lo[seg_g]) * per);
+        hi = min(G.t1, lo + per);
+      }
+    } else {
+      hi = M.T;
+    }
+  }
+  const bool cached = !skip_cv && !slot_major && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
+  const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
+  const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
+  uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
+  uint32_t cslot[CT];
+  int cg[CT];
+  V3 cr[CT], cp[CT];
+  FV cfv[CT];
+
+  // ---- pass A, early part: engine arrays this library never writes (tag -> slot map, positions,
+  // images, velocities) may be read while the previous step kernel is still finishing (PDL) ---------
+  PSB_CLKA(9);
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < CT; ++i) {
+      const uint32_t t = lo + tid + i * BLOCK;
+      cslot[i] = 0;
+      cg[i] = -1;
+      if (t < hi) {
+        cg[i] = (nb == 1) ? (int)__ldg(M.term_group + t) : seg_g;
+        cslot[i] = A::slot(S, M, term_tag_of(M, M.grp[cg[i]], t));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CT; ++i) {
+      cp[i] = v3(0, 0, 0);
+      if (cg[i] >= 0) {
+        cr[i] = A::position(S, cslot[i]);
+        if (momenta_sums) cp[i] = A::momentum(S, cslot[i]);
+      }
+    }
+  }
+  int stage_na = 0;  // multi-CTA cached mode: accumulator rows of this CTA's group waiting in sh.stage
+  if (cached) {
+    if (nb == 1) {  // bare indices (groups of one atom): the owner writes the "sums", no reduction
+#pragma unroll
+      for (int i = 0; i < CT; ++i)
+        if (cg[i] >= 0 && M.grp[cg[i]].t1 - M.grp[cg[i]].t0 == 1 &&
+            (!GENERAL || is_point_kind(M.cv[M.grp[cg[i]].cv].kind))) {
+          double* tot = sh.tot[cg[i]];
+          tot[0] = cr[i].x; tot[1] = cr[i].y; tot[2] = cr[i].z;
+          tot[3] = cp[i].x; tot[4] = cp[i].y; tot[5] = cp[i].z;
+        }
+    }
+    for (int g = g_begin; g < g_end; ++g) {
+      const GroupDev& G = M.grp[g];
+      const CvDev& cv = M.cv[G.cv];
+      if (nb == 1 && G.t1 - G.t0 == 1 && (!GENERAL || is_point_kind(cv.kind))) continue;  // done above
+      const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
+      if (na == 0) continue;
+      const bool with_p = (na == 6);
+      double acc[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+#pragma unroll
+      for (int i = 0; i < CT; ++i)
+        if (cg[i] == g) accumulate_term<GENERAL>(cv, with_p, G.inv_n, lo + tid + i * BLOCK, cr[i], cp[i], acc);
+      PSB_CLKA(10);
+      if (nb > 1) {  // one group per CTA: the sums wait in shared memory until the previous kernel is done
+        block_reduce_store(sh, acc, na, sh.stage, 1, false);
+        stage_na = na;
+      } else {
+        block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
+      }
+      PSB_CLKA(11);
+    }
+  }
+  // everything below may depend on the previous kernel of the stream: forces, method state, workspaces
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- prologue: method-state scalars as they are when the step begins --------------------------
   // The loads are issued here but land in shared memory only after this thread has issued its
@@ -924,72 +1018,17 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
   }
 
-  // ---- this CTA's terms ----------------------------------------------------------------------
-  // gridDim.x > 1: exactly one group per CTA, an even share of its terms; gridDim.x == 1: all terms.
-  // Up to CT terms per thread are "cached": slot, group, position and the prefetched force row stay
-  // in registers until the scatter.
-  int seg_g = -1;
-  uint32_t lo = 0, hi = 0;
-  if (!skip_cv) {
-    if (slot_major) {
-      // no per-CTA group: handled by the slot-ordered passes below
-    } else if (nb > 1) {
-      for (int g = 0; g < M.ngroups; ++g)
-        if (b >= M.cta_lo[g] && b <= M.cta_hi[g]) seg_g = g;
-      if (seg_g >= 0) {
-        const GroupDev& G = M.grp[seg_g];
-        const uint32_t nc = (uint32_t)(M.cta_hi[seg_g] - M.cta_lo[seg_g] + 1);
-        const uint32_t per = (G.t1 - G.t0 + nc - 1) / nc;
-        lo = min(G.t1, G.t0 + (uint32_t)(b - M.cta_lo[seg_g]) * per);
-        hi = min(G.t1, lo + per);
-      }
-    } else {
-      hi = M.T;
-    }
-  }
-  const bool cached = !skip_cv && !slot_major && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
-  const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
-  const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
-  uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
-  uint32_t cslot[CT];
-  int cg[CT];
-  V3 cr[CT], cp[CT];
-  FV cfv[CT];
-
   // ---- pass A ---------------------------------------------------------------------------------
-  PSB_CLKA(9);
   if (!skip_cv) {
     if (cached) {
 #pragma unroll
       for (int i = 0; i < CT; ++i) {
-        const uint32_t t = lo + tid + i * BLOCK;
-        cslot[i] = 0;
-        cg[i] = -1;
-        if (t < hi) {
-          cg[i] = (nb == 1) ? (int)__ldg(M.term_group + t) : seg_g;
-          cslot[i] = A::slot(S, M, term_tag_of(M, M.grp[cg[i]], t));
-          if (need_term_slot) M.term_slot[t] = cslot[i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < CT; ++i) {
-        cp[i] = v3(0, 0, 0);
         if (cg[i] >= 0) {
-          cr[i] = A::position(S, cslot[i]);
-          if (momenta_sums) cp[i] = A::momentum(S, cslot[i]);
+          if (need_term_slot) M.term_slot[lo + tid + i * BLOCK] = cslot[i];
           if (will_scatter) cfv[i] = A::load_force(S, cslot[i]);
         }
       }
-      if (nb == 1) {  // bare indices (groups of one atom): the owner writes the "sums", no reduction
-#pragma unroll
-        for (int i = 0; i < CT; ++i)
-          if (cg[i] >= 0 && M.grp[cg[i]].t1 - M.grp[cg[i]].t0 == 1 &&
-              (!GENERAL || is_point_kind(M.cv[M.grp[cg[i]].cv].kind))) {
-            double* tot = sh.tot[cg[i]];
-            tot[0] = cr[i].x; tot[1] = cr[i].y; tot[2] = cr[i].z;
-            tot[3] = cp[i].x; tot[4] = cp[i].y; tot[5] = cp[i].z;
-          }
-      }
+      if (tid < stage_na) __stcg(M.partials + (size_t)(seg_g * NACC + tid) * nb + b, sh.stage[tid]);
     }
     commit_pre();
     // ---- slot-major gather (most atoms selected, too many to keep in registers) ---------------
@@ -1079,37 +1118,26 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         if (g < M.ngroups) block_reduce_store(sh, acc4[g], na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
     }
 
-    for (int g = g_begin; g < g_end; ++g) {
+    // groups too large for the register cache (and not slot-ordered): gather loop, slots published
+    for (int g = cached ? g_end : g_begin; g < g_end; ++g) {
       const GroupDev& G = M.grp[g];
       const CvDev& cv = M.cv[G.cv];
-      if (nb == 1 && cached && G.t1 - G.t0 == 1 && (!GENERAL || is_point_kind(cv.kind))) continue;  // done above
       const int na = nacc_for_kind(cv.kind, 0, momenta_sums);
       const bool with_p = (na == 6);
       double acc[NACC];
 #pragma unroll
       for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-      if (cached) {
-#pragma unroll
-        for (int i = 0; i < CT; ++i)
-          if (cg[i] == g) accumulate_term<GENERAL>(cv, with_p, G.inv_n, lo + tid + i * BLOCK, cr[i], cp[i], acc);
-      } else {
-        const uint32_t tlo = max(lo, G.t0), thi = min(hi, G.t1);
+      const uint32_t tlo = max(lo, G.t0), thi = min(hi, G.t1);
 #pragma unroll 4
-        for (uint32_t t = tlo + tid; t < thi; t += BLOCK) {
-          const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
-          M.term_slot[t] = slot;
-          const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
-          accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
-        }
+      for (uint32_t t = tlo + tid; t < thi; t += BLOCK) {
+        const uint32_t slot = A::slot(S, M, term_tag_of(M, G, t));
+        M.term_slot[t] = slot;
+        const V3 p = with_p ? A::momentum(S, slot) : v3(0, 0, 0);
+        accumulate_term<GENERAL>(cv, with_p, G.inv_n, t, A::position(S, slot), p, acc);
       }
       if (na == 0) continue;
-      PSB_CLKA(10);
-      if (nb > 1) {
-        block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
-        PSB_CLKA(11);
-      } else {
-        block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
-      }
+      if (nb > 1) block_reduce_store(sh, acc, na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+      else block_reduce_store(sh, acc, na, &sh.tot[g][0], 1, false);
     }
 
     PSB_STAMP(1);

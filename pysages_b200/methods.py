@@ -192,6 +192,9 @@ class NativeStep:
     def record_doubles(self):
         return int(self.lib.psb_walker_record_doubles(self.handle))
 
+    def set_option(self, name, value):
+        N.check(self.lib.psb_set_option(self.handle, name.encode(), int(value)))
+
     def launch_info(self):
         g, b, c, nbytes = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
         N.check(self.lib.psb_launch_info(self.handle, ctypes.byref(g), ctypes.byref(b), ctypes.byref(c),
