@@ -454,17 +454,23 @@ def test_run_cycle_graph_replay_matches_single_steps_and_oracle(method, launch_s
         N.check(nat_g.lib.psb_run_cycle(nat_g.handle, descs, nring, nsteps, sp))
     stream.synchronize()
     assert nat_g.lib.psb_cycle_uses_graph(nat_g.handle) == 1
-    # (b) one psb_step per step
+    # (b) one psb_step per step (programmatic dependent launch between consecutive steps, the default)
     nat_s, snaps_s = build()
     for t in range(nsteps):
         nat_s.step(snaps_s[t % nring], t)
+    # (b') the same without programmatic dependent launch: plain stream order
+    nat_p, snaps_p = build()
+    nat_p.set_option("pdl", 0)
+    for t in range(nsteps):
+        nat_p.step(snaps_p[t % nring], t)
     torch.cuda.synchronize()
     fields = ["xi", "cv_force", "ncalls"] + (["hist", "Fsum", "force", "Wp", "Wp_"] if method == "abf" else
                                              ["heights", "centers", "idx"] + (["grid_potential", "grid_gradient"] if method == "metad-grid" else []))
     for f in fields:
         assert torch.equal(nat_g.view(f), nat_s.view(f)), f
-    for a, b in zip(snaps_g, snaps_s):
-        assert torch.equal(a.forces, b.forces)
+        assert torch.equal(nat_p.view(f), nat_s.view(f)), f
+    for a, b, c in zip(snaps_g, snaps_s, snaps_p):
+        assert torch.equal(a.forces, b.forces) and torch.equal(c.forces, b.forces)
     # (c) the oracle over the same ring
     om = make_method("oracle", spec, make_cvs(oracle.colvars, cvs))
     helpers, bias = oracle.backends.build_helpers("hoomd", om.snapshot_flags, True)
