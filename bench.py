@@ -547,7 +547,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-multi", action="store_true", help="skip the cfg5 walker / umbrella-window legs")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiler runs: the timed region only (no series / cpu / e2e / multi legs, no clock-sampling load, no floor)")
     args = ap.parse_args()
+    if args.profile:
+        args.no_series = args.no_cpu = args.no_e2e = args.no_multi = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -612,7 +616,7 @@ def main():
         # a short timed region can end before nvidia-smi (100 ms period) has sampled it: keep the SAME load
         # running, untimed, until a few samples under load exist (the timed number above is not touched)
         t_end = time.perf_counter() + 1.5
-        while len(clocks.rows) < 5 and time.perf_counter() < t_end:
+        while not args.profile and len(clocks.rows) < 5 and time.perf_counter() < t_end:
             time_cycle(native, descs, 4000, 0, stream)
         barrier()
     info = native.launch_info()
@@ -667,7 +671,8 @@ def main():
         stream.synchronize()
         return round(e0.elapsed_time(e1) * 1e3 / 2000, 3)
 
-    info["floor_us"] = dict(empty_cooperative_launch=floor(0), empty_launch_with_one_grid_barrier=floor(1))
+    if not args.profile:
+        info["floor_us"] = dict(empty_cooperative_launch=floor(0), empty_launch_with_one_grid_barrier=floor(1))
 
     hbm, peak_src = peaks()
     us = ms * 1e3 / args.steps
