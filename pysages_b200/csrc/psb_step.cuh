@@ -250,7 +250,7 @@ __device__ __forceinline__ void put3(double* dst, V3 v) {
 // CV `c`: value and Jacobian factors after pass A (one lane per CV).  Only the rows
 // gpt[g][j < ncomp] of a CV's groups are ever read, and every case writes them completely.
 template <bool GENERAL>
-static __device__ __noinline__ void finalize_cv_A(const Model& M, StepShared& sh, int c) {
+static __device__ __forceinline__ void finalize_cv_A(const Model& M, StepShared& sh, int c) {
   Fin& f = sh.fin;
   const CvDev& cv = M.cv[c];
   const int g0 = cv.g0;
@@ -505,7 +505,7 @@ __device__ __forceinline__ void metad_grid_force(const Model& M, Fin& f, int lan
 
 // Everything that can be decided once xi is complete (warp 0, all lanes).
 template <int METHOD, bool GENERAL>
-static __device__ __noinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
+static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
   Fin& f = sh.fin;
   const MethodDev& m = M.m;
   const int k = M.k;
