@@ -200,7 +200,8 @@ def time_cycle(native, descs, steps, warmup, stream, plain=False):
                 N.check(lib.psb_run_cycle(h, descs, n, c, sp))
                 k -= c
 
-    issue(warmup)
+    # the warm-up must also build (capture + instantiate) the CUDA graph, not the timed region
+    issue(warmup if plain else max(warmup, 2 * n))
     stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.psb_launch_count(h)

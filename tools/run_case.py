@@ -1,7 +1,6 @@
 """Run one named workload for a few plain-launch steps (profiling driver): python tools/run_case.py <case> [steps]
 cases: cfg3 (pair kernel), harmonic1m / abf1m (slot-ordered kernels), cfg4 / cfg4grid, abf100k"""
 import os, sys, ctypes
-os.environ.setdefault("PSB_NO_GRAPH", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
@@ -29,14 +28,21 @@ elif case in ("cfg4", "cfg4grid"):
     else:
         extra = prefill
     specs = (cvs4, ("Metadynamics", md))
+elif case in ("openmm100k", "lammps100k"):
+    layout, dtype = ("openmm-cuda", np.float32) if case == "openmm100k" else ("lammps", np.float64)
+    snaps, L = bench.device_layout_snapshots(layout, dtype, 100_000, 16, dev, seed=20240 + 2000)
+    specs = bench.workload_specs("abf2d", 100_000, L)
+    frames = None
 else:
     n = 100_000
     frames, L, _ = bench.device_hoomd_frames(n, 8, dev, seed=3)
     specs = bench.workload_specs("abf2d", n, L)
-snaps = bench.snapshots_of(frames, L, 0.005)
-method, native = bench.build_ours(specs[0], specs[1], snaps[0])
+if frames is not None:
+    snaps = bench.snapshots_of(frames, L, 0.005)
+layout_name = {"openmm100k": "openmm-cuda", "lammps100k": "lammps"}.get(case, "hoomd")
+method, native = bench.build_ours(specs[0], specs[1], snaps[0], layout=layout_name)
 if extra:
     extra(native)
 descs = bench.snapdesc_array(native, snaps)
-ms, launches = bench.time_cycle(native, descs, steps, 3, stream, plain=True)
+ms, launches = bench.time_cycle(native, descs, steps, 3, stream, plain=bool(os.environ.get("PSB_NO_GRAPH")))
 print(case, "us/step", ms * 1e3 / steps, "launches/step", launches / steps, native.launch_info())
