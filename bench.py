@@ -485,6 +485,18 @@ def run_series(device, stream, hbm):
         measure(f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), name, natoms, steps, frames, L)
         del frames
 
+    # row K (FUNN, funn.py:187-296): the headline workload with the force taken from a (2, 14, 14, 2)
+    # tanh network evaluated inside the step kernel instead of the binned average
+    def with_network(native):
+        from pysages_b200 import ml
+
+        net = ml.MLP(2, 2, (14, 14), (0.0, 0.0), (1.0, 1.0), seed=1)
+        native.set_force_net(net.widths, net.parameters, [0.0, 0.0], [1.0, 1.0], predict_after=0)
+
+    frames, L, _ = device_hoomd_frames(100_000, 64, device, seed=20240 + 2000)
+    measure("abf2d S=N=100000 hoomd-f32 + FUNN network force (14,14)", "abf2d", 100_000, 2000, frames, L, extra=with_network)
+    del frames
+
     # the headline workload on the other engine layouts (OpenMM-CUDA: fixed-point forces, permuted order,
     # one extra inverse-permutation kernel per step; LAMMPS: (N,3) doubles, packed images, per-type masses)
     for layout, dtype in (("openmm-cuda", np.float32), ("lammps", np.float64)):

@@ -242,6 +242,35 @@ psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64
  * step's finalizer / scatter; forces, method state and workspaces are touched only after the previous
  * kernel has completed.  A kernel that follows an engine kernel is never launched early. */
 psb_status psb_set_option(psb_handle* h, const char* name, int64_t value);
+/* Continuous force model of the ABF family (row K of SURVEY.md 8a).  FUNN (methods/funn.py:187-210)
+ * and CFF (methods/cff.py:223-244) run the ABF accumulation every step and, once
+ * `ncalls > predict_after` (funn.py:190: 2 * train_freq, cff.py:226: train_freq), take the
+ * generalized force from a multilayer perceptron instead of the binned average
+ * (funn.py:261-296 build_force_estimator, cff.py:315-350):
+ *     F = std * mlp(scale(float32(xi))) + mean
+ * with scale(x) = (x - grid.lower) * 2 / grid.size - 1 (approxfun/core.py:99-104), dense layers
+ * h W + b with the activation between them (ml/models.py:44-82) and all arithmetic in fp64 after the
+ * float32 rounding of xi (funn.py:283).  Restraints outside the grid take precedence as in ABF.
+ * `params` is the flat parameter vector of ml/utils.py:43-53: for every dense layer W (in, out)
+ * row-major, then b (out).  The fit itself is cadenced host-side work (every train_freq steps) and
+ * hands its result over through this call; the copy is ordered on `cuda_stream`, so steps already
+ * enqueued keep the previous network.  Only PSB_METHOD_ABF handles accept it. */
+#define PSB_MAX_DENSE 8   /* dense layers, output layer included */
+#define PSB_MAX_WIDTH 128 /* units per layer */
+typedef enum { PSB_ACT_TANH = 0, PSB_ACT_SIN = 1 } psb_activation;
+typedef struct {
+  int32_t n_dense;                   /* 0 removes the network (plain ABF again) */
+  int32_t widths[PSB_MAX_DENSE + 1]; /* widths[0] = widths[n_dense] = k */
+  int32_t activation;                /* psb_activation; PSB_ACT_SIN is sin(omega * x) (ml/models.py:113-121,140-143) */
+  int32_t params_on_device;          /* `params` is a device pointer */
+  double omega0, omega;              /* PSB_ACT_SIN only: frequency of the first / of the other layers */
+  int64_t predict_after;
+  const double* params;
+  double mean[PSB_MAX_K];
+  double std[PSB_MAX_K];
+} psb_force_net;
+psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda_stream);
+
 int64_t psb_launch_count(psb_handle* h);
 /* 1 when the last psb_run_cycle replayed a CUDA graph, 0 when it issued plain launches. */
 int32_t psb_cycle_uses_graph(psb_handle* h);

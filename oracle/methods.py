@@ -5,7 +5,7 @@ Restates, in torch-fp64 (CPU):
   pysages/methods/harmonic_bias.py:78-132   HarmonicBias
   pysages/methods/metad.py:156-323          Metadynamics (standard / well-tempered, direct / grid)
   pysages/methods/abf.py:142-258            ABF
-  pysages/methods/funn.py:187-210,271-273   FUNN per-step accumulation (shares ABF's scatter)
+  pysages/methods/funn.py:97-296            FUNN (per-step accumulation, network force, cadenced refit via oracle/ml.py)
   pysages/methods/restraints.py:49-73       CVRestraints
   pysages/methods/core.py:463-474           generalize
   pysages/utils/core.py:113-136             gaussian, linear_solver
@@ -414,5 +414,111 @@ class ABF(SamplingMethod):
             force = estimate_force(xi, I_xi, Fsum, hist).reshape(dims)
             bias = (-Jxi.T.to(F64) @ force).reshape(state.bias.shape)
             return ABFState(xi, bias, hist, Fsum, force, Wp, state.Wp, state.ncalls + 1)
+
+        return snapshot, initialize, generalize(update, helpers)
+
+
+# --------------------------------------------------------------------------- #
+# FUNN (funn.py:97-296)
+# --------------------------------------------------------------------------- #
+
+
+class FUNNState(NamedTuple):  # funn.py:41-86
+    xi: Any
+    bias: Any
+    hist: Any
+    Fsum: Any
+    F: Any
+    Wp: Any
+    Wp_: Any
+    nn: Any
+    ncalls: int = 0
+
+
+class FUNN(ABF):
+    """funn.py:97-210: ABF accumulation every step; after 2 * train_freq calls the force is
+    std * mlp(scale(f32(xi))) + mean, the network being refitted every train_freq calls to the
+    Blackman-smoothed, normalized binned mean force."""
+
+    def __init__(self, cvs, grid, topology, **kwargs):
+        super().__init__(cvs, grid, **kwargs)
+        from . import ml
+
+        self.topology = tuple(topology)
+        self.train_freq = kwargs.get("train_freq", 5000)
+        dims = grid.shape.size
+        self.widths = ml.layer_sizes(dims, self.topology, dims)
+        self.initial_params = kwargs.get("initial_params", None)
+        if self.initial_params is None:
+            self.initial_params = ml.init_params(self.widths, kwargs.get("seed", 0))
+        self.reg = kwargs.get("reg", 1e-6)  # funn.py:153
+        self.max_iters = kwargs.get("max_iters", 500)
+
+    def build(self, snapshot, helpers):
+        from . import ml
+
+        cv, grid = self.cv, self.grid
+        dt = snapshot.dt
+        dims = grid.shape.size
+        gshape = tuple(int(s) for s in grid.shape)
+        natoms = _natoms(snapshot)
+        tsolve = linear_solver(self.use_pinv)
+        get_grid_index = grids.build_indexer(grid)
+        N = int(self.N)
+        restraints = self.restraints
+        train_freq = self.train_freq
+        widths = self.widths
+        lower, upper = np.asarray(grid.lower, dtype=np.float64), np.asarray(grid.upper, dtype=np.float64)
+        inputs = grids.compute_mesh(grid)
+        kernel = ml.blackman_kernel(dims, 7)
+        padding = "wrap" if grid.is_periodic else "edge"
+        query, dimensionality, to_force_units = helpers
+
+        def learn(state):  # funn.py:213-249
+            hist = state.hist.numpy().astype(np.float64)[..., None]
+            y = state.Fsum.numpy() / np.maximum(hist, 1)
+            axes = tuple(range(y.ndim - 1))
+            y, mean, std = ml.normalize(y, axes=axes)
+            reference = ml.smooth(y, kernel, padding)
+            params = ml.lm_fit(state.nn.params, widths, inputs, reference, lower, upper,
+                               reg=self.reg, max_iters=self.max_iters)
+            return ml.NNData(params, mean, std / reference.std(axis=axes))
+
+        def estimate_force(xi, I_xi, Fsum, hist, nn, pred):  # funn.py:252-296
+            ob = any(int(i) == s for i, s in zip(I_xi, gshape))
+            if restraints is not None and ob:
+                lo, hi, kl, kh = restraints
+                return apply_restraints(lo, hi, kl, kh, xi.reshape(dims).to(F64))
+            if pred:
+                x = xi.detach().numpy().astype(np.float32).astype(np.float64)
+                out = ml.mlp_apply(nn.params, widths, x, lower, upper).reshape(dims)
+                return torch.as_tensor(nn.std * out + nn.mean)
+            return _gather(Fsum, I_xi) / max(N, int(_gather(hist, I_xi)))
+
+        def initialize():  # funn.py:175-185
+            xi, _ = cv(query(snapshot))
+            bias = torch.zeros((natoms, dimensionality()), dtype=F64)
+            hist = torch.zeros(gshape, dtype=torch.int64)
+            Fsum = torch.zeros((*gshape, dims), dtype=F64)
+            z = torch.zeros(dims, dtype=F64)
+            nn = ml.NNData(np.asarray(self.initial_params, dtype=np.float64), np.zeros(dims), np.zeros(dims))
+            return FUNNState(xi, bias, hist, Fsum, z, z.clone(), z.clone(), nn)
+
+        def update(state, data):  # funn.py:187-210
+            ncalls = state.ncalls + 1
+            in_training_regime = ncalls > 2 * train_freq
+            in_training_step = in_training_regime and (ncalls % train_freq == 1)
+            nn = learn(state) if in_training_step else state.nn
+            xi, Jxi = cv(data)
+            p = torch.as_tensor(data.momenta)
+            Jd = Jxi.to(F64) if (Jxi.dtype == F64 or p.dtype == F64) else Jxi
+            Wp = tsolve(Jd, p.to(Jd.dtype)).to(F64)
+            dWp_dt = (1.5 * Wp - 2.0 * state.Wp + 0.5 * state.Wp_) / dt
+            I_xi = get_grid_index(xi.detach().numpy())
+            hist = _scatter_add(state.hist, I_xi, 1)
+            Fsum = _scatter_add(state.Fsum, I_xi, to_force_units(dWp_dt) + state.F)
+            F = estimate_force(xi, I_xi, Fsum, hist, nn, in_training_regime).reshape(dims)
+            bias = (-Jxi.T.to(F64) @ F).reshape(state.bias.shape)
+            return FUNNState(xi, bias, hist, Fsum, F, Wp, state.Wp, nn, ncalls)
 
         return snapshot, initialize, generalize(update, helpers)

@@ -1,0 +1,195 @@
+"""
+Oracle (test infrastructure): the neural-network pieces of the ABF family, restated in numpy fp64.
+
+  pysages/ml/models.py:44-82          MLP = Flatten, elementwise(transform), (Dense, Tanh)*, Dense
+  pysages/ml/utils.py:43-64,121-131   flat parameter vector (W (in,out) row-major then b, per dense layer),
+                                      Blackman smoothing kernel
+  pysages/ml/training.py:17-56        normalize, convolve (pad + "valid" convolution), fitting loop
+  pysages/ml/objectives.py            SSE + L2 regularisation: errors cast to float32, cost, damped Hessian, J^T e
+  pysages/ml/optimizers.py:188-232    Levenberg-Marquardt (mu kept in float32)
+  pysages/approxfun/core.py:99-104    scale(x, grid)
+
+Parity unpinned: the reference draws its initial weights from JAX's threefry PRNG through stax
+(glorot-normal W, N(0, 1e-2) b), which cannot be reproduced without JAX; `init_params` uses the same
+distributions from numpy's PCG64.  No reference test holds golden values for any of this.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
+"""
+
+import numpy as np
+import scipy.linalg
+import scipy.signal
+
+F32 = np.float32
+
+
+def layer_sizes(indim, topology, outdim):
+    return [int(indim), *[int(t) for t in topology], int(outdim)]
+
+
+def number_of_params(widths):
+    return sum(a * b + b for a, b in zip(widths[:-1], widths[1:]))
+
+
+def init_params(widths, seed=0):
+    """stax.Dense defaults: W ~ glorot normal, b ~ N(0, 1e-2) (different PRNG than the reference)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for a, b in zip(widths[:-1], widths[1:]):
+        out.append((rng.standard_normal((a, b)) * np.sqrt(2.0 / (a + b))).ravel())
+        out.append(rng.standard_normal(b) * 1e-2)
+    return np.concatenate(out)
+
+
+def split_params(ps, widths):
+    """ml/utils.py:56-64 pack: [(W, b), ...] views of the flat vector."""
+    layers, o = [], 0
+    for a, b in zip(widths[:-1], widths[1:]):
+        W = ps[o:o + a * b].reshape(a, b)
+        o += a * b
+        bias = ps[o:o + b]
+        o += b
+        layers.append((W, bias))
+    return layers
+
+
+def scale(x, lower, upper):
+    # approxfun/core.py:99-104
+    return (x - lower) * 2 / (upper - lower) - 1
+
+
+def mlp_apply(ps, widths, x, lower=None, upper=None, activation="tanh", omega0=1.0, omega=1.0):
+    """ml/models.py:44-82 (and :84-152 for sin).  x: (n, indim); the transform is `scale` when bounds are given."""
+    h = np.asarray(x, dtype=np.float64).reshape(-1, widths[0])
+    if lower is not None:
+        h = scale(h, np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64))
+    layers = split_params(np.asarray(ps, dtype=np.float64), widths)
+    for l, (W, b) in enumerate(layers):
+        h = h @ W + b
+        if l + 1 < len(layers):
+            h = np.tanh(h) if activation == "tanh" else np.sin((omega0 if l == 0 else omega) * h)
+    return h
+
+
+def mlp_jacobian(ps, widths, x, lower=None, upper=None):
+    """d mlp(x)[n, o] / d ps -> (n * outdim, nparams), tanh activations (what jax.jacobian(error) yields)."""
+    h = np.asarray(x, dtype=np.float64).reshape(-1, widths[0])
+    if lower is not None:
+        h = scale(h, np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64))
+    layers = split_params(np.asarray(ps, dtype=np.float64), widths)
+    acts = [h]
+    for l, (W, b) in enumerate(layers):
+        h = h @ W + b
+        if l + 1 < len(layers):
+            h = np.tanh(h)
+        acts.append(h)
+    n, outdim = acts[-1].shape
+    J = np.zeros((n, outdim, ps.size))
+    for o in range(outdim):
+        delta = np.zeros((n, outdim))
+        delta[:, o] = 1.0
+        off = ps.size
+        for l in range(len(layers) - 1, -1, -1):
+            W, b = layers[l]
+            a_in = acts[l]
+            off -= b.size
+            J[:, o, off:off + b.size] = delta
+            off -= W.size
+            J[:, o, off:off + W.size] = (a_in[:, :, None] * delta[:, None, :]).reshape(n, -1)
+            if l > 0:
+                delta = (delta @ W.T) * (1.0 - a_in * a_in)
+    return J.reshape(n * outdim, ps.size)
+
+
+# ---- training data ----------------------------------------------------------------------------
+
+def normalize(data, axes=None):
+    # ml/training.py:17-20
+    mean = data.mean(axis=axes)
+    std = data.std(axis=axes)
+    return (data - mean) / std, mean, std
+
+
+def blackman(M, n):
+    # ml/utils.py:121-123
+    x = 2 * np.pi * n / (M - 1)
+    return 0.42 + 0.5 * np.cos(x) + 0.08 * np.cos(2 * x)
+
+
+def blackman_kernel(dims, M):
+    # ml/utils.py:126-131
+    n = M - 2
+    inds = np.stack(np.meshgrid(*(np.arange(1 - n, n, 2) for _ in range(dims))), axis=-1)
+    kernel = blackman(M, np.linalg.norm(inds.reshape(-1, dims).astype(np.float64), axis=1) / 2)
+    return (kernel / kernel.sum()).reshape(*(n for _ in range(dims)))
+
+
+def convolve(data, kernel, boundary="edge"):
+    # ml/training.py:23-39
+    if kernel.ndim == 1:
+        padding = (kernel.size - 1) // 2
+    else:
+        padding = [((s - 1) // 2, (s - 1) // 2) for s in kernel.shape]
+    return scipy.signal.convolve(np.pad(data, padding, mode=boundary), kernel, mode="valid")
+
+
+def smooth(y, kernel, boundary):
+    """funn.py:226: vmap(conv)(y.T).T -- every output component is smoothed over the grid axes."""
+    return np.stack([convolve(y[..., c], kernel, boundary) for c in range(y.shape[-1])], axis=-1)
+
+
+# ---- Levenberg-Marquardt ------------------------------------------------------------------------
+
+class LMParams:
+    # ml/optimizers.py:40-51
+    mu_0 = 1e-1
+    mu_c = 10.0
+    mu_min = 1e-8
+    mu_max = 1e8
+    rho_c = 1e-1
+    rho_min = 1e-4
+
+
+def lm_fit(ps, widths, x, y, lower, upper, reg=1e-6, max_iters=500, params=LMParams, history=None):
+    """ml/optimizers.py:188-232 + ml/training.py:42-56 with SSE loss and L2 regularisation
+    (funn.py:153: LevenbergMarquardt(reg=L2Regularization(1e-6)))."""
+    y = np.asarray(y, dtype=np.float64)
+
+    def error(p):  # objectives.py build_error_function: float32 residuals
+        pred = mlp_apply(p, widths, x, lower, upper).reshape(y.shape)
+        return (pred - y).astype(F32).ravel().astype(np.float64)
+
+    def cost(e, p):
+        return (np.sum(e * e) + reg * np.sum(p * p)) / 2
+
+    c = F32(params.mu_c)
+    p_, e_, C_, mu = np.asarray(ps, dtype=np.float64), error(ps), np.inf, F32(params.mu_0)
+    iters, improved = 0, True
+    while improved and iters < max_iters and mu < params.mu_max:
+        mu = F32(mu)
+        J = mlp_jacobian(p_, widths, x, lower, upper)
+        H = J.T @ J
+        H[np.diag_indices_from(H)] += float(F32(reg) + mu)  # python float + f32 scalar stays f32 in JAX
+        Je = J.T @ e_ + reg * p_
+        dp = scipy.linalg.solve(H, Je, assume_a="pos")
+        p = p_ - dp
+        e = error(p)
+        C = cost(e, p)
+        rho = (C_ - C) / (dp @ (float(mu) * dp + Je))
+        if rho > params.rho_c:
+            mu = max(F32(mu / c), F32(params.mu_min))
+        bad = bool(rho < params.rho_min) or bool(np.any(np.isnan(p)))
+        if bad:
+            mu = min(F32(c * mu), F32(params.mu_max))
+            p, e, C = p_, e_, C_
+        improved = bool(C_ > C) or bad
+        iters += 0 if bad else 1
+        p_, e_, C_ = p, e, C
+        if history is not None:
+            history.append((p_.copy(), float(C_), float(mu)))
+    return p_
+
+
+class NNData:
+    # ml/training.py:11-14
+    def __init__(self, params, mean, std):
+        self.params, self.mean, self.std = params, mean, std

@@ -73,6 +73,26 @@ class MethodDesc(Structure):
     ]
 
 
+MAX_DENSE = 8
+MAX_WIDTH = 128
+ACT_TANH, ACT_SIN = 0, 1
+
+
+class ForceNetDesc(Structure):  # psb_force_net
+    _fields_ = [
+        ("n_dense", c_int32),
+        ("widths", c_int32 * (MAX_DENSE + 1)),
+        ("activation", c_int32),
+        ("params_on_device", c_int32),
+        ("omega0", c_double),
+        ("omega", c_double),
+        ("predict_after", c_int64),
+        ("params", c_void_p),
+        ("mean", c_double * MAX_K),
+        ("std", c_double * MAX_K),
+    ]
+
+
 class LayoutDesc(Structure):
     _fields_ = [
         ("layout", c_int32),
@@ -118,6 +138,7 @@ EXPORTS = {
     "psb_next_step_deposits": (c_int32, [c_void_p]),
     "psb_grid_index": (c_int32, [POINTER(GridDesc), POINTER(c_double), c_int64, POINTER(c_uint32)]),
     "psb_set_option": (c_int32, [c_void_p, c_char_p, c_int64]),
+    "psb_set_force_net": (c_int32, [c_void_p, POINTER(ForceNetDesc), c_void_p]),
     "psb_launch_count": (c_int64, [c_void_p]),
     "psb_cycle_uses_graph": (c_int32, [c_void_p]),
     "psb_launch_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),

@@ -43,11 +43,15 @@ def _run(method_or_result, context_generator, timesteps, context_args=None, call
         sampler.restore(method_or_result.snapshots)
         native = sampler._method_update.native
         prev = method_or_result.states
-        for field in prev._fields:
-            value = getattr(prev, field)
-            if value is not None and field != "bias":
-                native.set_state(field, value.cpu().numpy() if hasattr(value, "cpu") else value)
-        sampler.state = method._make_state(native)
+        restore = getattr(sampler._method_update, "restore", None)
+        if restore is not None:  # methods whose state holds more than flat device arrays (FUNN's network)
+            sampler.state = restore(prev)
+        else:
+            for field in prev._fields:
+                value = getattr(prev, field)
+                if value is not None and field != "bias":
+                    native.set_state(field, value.cpu().numpy() if hasattr(value, "cpu") else value)
+            sampler.state = method._make_state(native)
     with sampling_context:
         sampling_context.run(timesteps, **kwargs)
         if post_run_action:

@@ -50,6 +50,8 @@ struct CoordWork {
 struct psb_handle {
   Model model;
   Model* d_model = nullptr;  // device copy read by the step kernel (uploaded at the end of psb_create)
+  char* d_nn = nullptr;      // ForceNet header + parameters (psb_set_force_net)
+  size_t nn_capacity = 0;
   psb_layout_desc layout;
   psb_method_desc method;
   std::vector<void*> allocs;
@@ -983,6 +985,62 @@ psb_status psb_set_option(psb_handle* h, const char* name, int64_t value) {
     return PSB_OK;
   }
   return fail(PSB_ERR_KEY, "unknown option '%s'", name);
+}
+
+// funn.py:261-296 / cff.py:315-350: the network that replaces the binned average (psb_force_net).
+psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda_stream) {
+  if (!h || !net) return fail(PSB_ERR_VALUE, "NULL argument");
+  Model& M = h->model;
+  if (M.m.kind != PSB_METHOD_ABF)
+    return fail(PSB_ERR_VALUE, "a force network needs an ABF-family method (funn.py:187-210)");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const ForceNet* target = nullptr;
+  if (net->n_dense != 0) {
+    if (net->n_dense < 1 || net->n_dense > PSB_MAX_DENSE)
+      return fail(PSB_ERR_VALUE, "force network: between 1 and %d dense layers (got %d)", PSB_MAX_DENSE, net->n_dense);
+    if (net->widths[0] != M.k || net->widths[net->n_dense] != M.k)
+      return fail(PSB_ERR_VALUE, "force network: input and output width must equal the %d CV components", M.k);
+    if (net->activation != PSB_ACT_TANH && net->activation != PSB_ACT_SIN)
+      return fail(PSB_ERR_VALUE, "force network: unknown activation %d", net->activation);
+    if (!net->params) return fail(PSB_ERR_VALUE, "force network: NULL parameters");
+    if (M.m.grid_kind == PSB_GRID_NONE) return fail(PSB_ERR_VALUE, "force network: the method has no grid");
+    ForceNet hn{};
+    hn.n_dense = net->n_dense;
+    hn.activation = net->activation;
+    hn.omega0 = net->omega0;
+    hn.omega = net->omega;
+    hn.predict_after = net->predict_after;
+    size_t nparams = 0;
+    for (int l = 0; l <= net->n_dense; ++l) {
+      if (net->widths[l] < 1 || net->widths[l] > PSB_MAX_WIDTH)
+        return fail(PSB_ERR_VALUE, "force network: layer widths must lie in [1, %d] (got %d)", PSB_MAX_WIDTH, net->widths[l]);
+      hn.widths[l] = net->widths[l];
+      if (l < net->n_dense) {
+        hn.w_off[l] = (int32_t)nparams;
+        nparams += (size_t)net->widths[l] * net->widths[l + 1] + net->widths[l + 1];
+      }
+    }
+    for (int c = 0; c < MAXK; ++c) { hn.mean[c] = net->mean[c]; hn.std[c] = net->std[c]; }
+    const size_t bytes = sizeof(ForceNet) + nparams * sizeof(double);
+    if (bytes > h->nn_capacity) {  // first network, or a larger topology than before
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      char* p = nullptr;
+      psb_status st = dev_alloc(h, &p, bytes, false);  // the old block stays alive until psb_destroy
+      if (st != PSB_OK) return st;
+      h->d_nn = p;
+      h->nn_capacity = bytes;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_nn, &hn, sizeof(ForceNet), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_nn + sizeof(ForceNet), net->params, nparams * sizeof(double),
+                             net->params_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    target = reinterpret_cast<const ForceNet*>(h->d_nn);
+  }
+  if (M.nn != target) {
+    M.nn = target;
+    // the step kernel reads the model from device memory; the copy is ordered after every step enqueued so far
+    CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
+  }
+  return PSB_OK;
 }
 
 int64_t psb_launch_count(psb_handle* h) { return h ? h->launches : 0; }

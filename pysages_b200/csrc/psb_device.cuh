@@ -67,6 +67,20 @@ struct MethodDev {
   long long grid_points;
 };
 
+// Force network of the ABF family (psb_force_net, include/pysages_b200.h): header followed in the
+// same allocation by the flat parameter vector.
+struct ForceNet {
+  int32_t n_dense;
+  int32_t widths[PSB_MAX_DENSE + 1];
+  int32_t activation;
+  int32_t pad;
+  double omega0, omega;  // PSB_ACT_SIN: first layer / other layers
+  long long predict_after;
+  double mean[MAXK], std[MAXK];
+  int32_t w_off[PSB_MAX_DENSE];  // offset of layer l's W in the parameter vector; b follows W
+  __host__ __device__ const double* params() const { return reinterpret_cast<const double*>(this + 1); }
+};
+
 struct StateDev {
   double* xi;        // (k)
   double* F;         // (k) generalized force dV/dxi
@@ -157,6 +171,7 @@ struct Model {
   int32_t cross_overlap;      // some atom belongs to two different groups
   int32_t jjt_const;          // ABF: J J^T does not depend on positions; jjt_inv holds its inverse
   double jjt_inv[MAXK * MAXK];  // (leading dimension 4)
+  const ForceNet* nn;         // ABF family: force network or nullptr (psb_set_force_net)
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr

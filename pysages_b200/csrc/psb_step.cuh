@@ -114,6 +114,7 @@ struct StepShared {
   unsigned long long epoch[NBARS];  // completed uses of each grid barrier when the step began
   uint32_t bars_used;               // barriers this launch arrived on (thread 0)
   uint64_t mbar[2];
+  double nnbuf[2][PSB_MAX_WIDTH];  // force network activations (force_net_eval)
 };
 
 // Block-wide sum of acc[0..nacc); result lands in out[0..nacc) (shared or global, stride ostride).
@@ -396,6 +397,42 @@ __device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int
   }
 }
 
+// funn.py:279-284 / cff.py:328-332 predict_force, one warp: F = std * mlp(scale(float32(xi))) + mean with
+// scale = approxfun/core.py:99-104 and the dense / activation stack of ml/models.py:44-82.  Lane j
+// owns output unit j (+32, ...) of every layer; activations ping-pong through shared memory.
+// Returns component `lane` of the force.  Kept out of line: plain ABF never reaches it.
+static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const MethodDev& m, const double* xi,
+                                              double* buf, int lane) {
+  const int nd = nn->n_dense;
+  const double* P = nn->params();
+  double* cur = buf;
+  double* nxt = buf + PSB_MAX_WIDTH;
+  int in = nn->widths[0];
+  if (lane < in) {
+    const double x = (double)(float)xi[lane];  // funn.py:283: f32(x), promoted back by the fp64 grid bounds
+    cur[lane] = (x - m.g_lower[lane]) * 2.0 / (m.g_upper[lane] - m.g_lower[lane]) - 1.0;
+  }
+  __syncwarp();
+  for (int l = 0; l < nd; ++l) {
+    const int out = nn->widths[l + 1];
+    const double* W = P + nn->w_off[l];
+    const double* b = W + (size_t)in * out;
+    const double om = l == 0 ? nn->omega0 : nn->omega;
+    for (int j = lane; j < out; j += 32) {
+      double acc = 0.0;
+#pragma unroll 4
+      for (int i = 0; i < in; ++i) acc = fma(cur[i], __ldg(W + (size_t)i * out + j), acc);
+      acc += __ldg(b + j);
+      if (l + 1 < nd) acc = nn->activation == PSB_ACT_SIN ? sin(om * acc) : tanh(acc);
+      nxt[j] = acc;
+    }
+    __syncwarp();
+    double* t = cur; cur = nxt; nxt = t;
+    in = out;
+  }
+  return lane < in ? nn->std[lane] * cur[lane] + nn->mean[lane] : 0.0;
+}
+
 // abf.py:210-225 once f.JJt / f.Jp are known (warp 0, all lanes).  Every CTA derives the new
 // histogram count and force sum of bin I from the values the step began with; CTA 0 stores them
 // after the last reader is done (end of the kernel).
@@ -438,6 +475,10 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   PSB_CLK(13);
   const bool oob = f.oob != 0;
   if (lane == 0) f.in_range = oob ? 0 : 1;  // .at[I].add drops out-of-range updates
+  // funn.py:190,286-296: past the ABF-only stage the force comes from the network (restraints first)
+  const ForceNet* nn = M.nn;
+  const bool use_net = nn != nullptr && !(m.has_restraints && oob) && sh.pre.ncalls + 1 > __ldg(&nn->predict_after);
+  const double f_net = use_net ? force_net_eval(nn, m, f.xi, &sh.nnbuf[0][0], lane) : 0.0;
   if (lane < k) {
     const int c = lane;
     uint32_t h = (uint32_t)f.hist_old;
@@ -450,6 +491,8 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
     double fc;
     if (m.has_restraints && oob) {
       fc = restraint_force(m.r_lower[c], m.r_upper[c], m.r_kl[c], m.r_ku[c], f.xi[c]);
+    } else if (use_net) {
+      fc = f_net;
     } else {
       const unsigned long long hh = h;
       const double den = (double)((unsigned long long)m.abf_N > hh ? (unsigned long long)m.abf_N : hh);

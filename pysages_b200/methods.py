@@ -195,6 +195,30 @@ class NativeStep:
     def set_option(self, name, value):
         N.check(self.lib.psb_set_option(self.handle, name.encode(), int(value)))
 
+    def set_force_net(self, widths, params, mean, std, predict_after, activation=N.ACT_TANH, omega0=1.0, omega=1.0):
+        """psb_set_force_net: `params` is a flat fp64 torch tensor (device or host) or numpy array."""
+        d = N.ForceNetDesc()
+        d.n_dense = len(widths) - 1 if widths else 0
+        for i, w in enumerate(list(widths or ())[: N.MAX_DENSE + 1]):  # longer lists fail on n_dense in the library
+            d.widths[i] = int(w)
+        d.activation, d.omega0, d.omega = int(activation), float(omega0), float(omega)
+        d.predict_after = int(predict_after)
+        keep = None
+        if d.n_dense:
+            if isinstance(params, torch.Tensor):
+                keep = params.detach().to(torch.float64).contiguous()
+                d.params_on_device = int(keep.is_cuda)
+                d.params = keep.data_ptr()
+            else:
+                keep = np.ascontiguousarray(params, dtype=np.float64)
+                d.params = keep.ctypes.data
+            mean = np.asarray(torch.as_tensor(mean).detach().cpu(), dtype=np.float64).ravel()
+            std = np.asarray(torch.as_tensor(std).detach().cpu(), dtype=np.float64).ravel()
+            for i in range(self.k):
+                d.mean[i], d.std[i] = float(mean[i]), float(std[i])
+        N.check(self.lib.psb_set_force_net(self.handle, ctypes.byref(d), self._stream()))
+        self._force_net_params = keep  # a device source must outlive the stream-ordered copy
+
     def launch_info(self):
         g, b, c, nbytes = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
         N.check(self.lib.psb_launch_info(self.handle, ctypes.byref(g), ctypes.byref(b), ctypes.byref(c),
@@ -521,6 +545,123 @@ class ABF(GriddedSamplingMethod):
             native.view("xi", (1, k)), bias, native.view("hist", gshape), native.view("Fsum", (*gshape, k)),
             native.view("force")[:k], native.view("Wp")[:k], native.view("Wp_")[:k], native.ncalls,
         )
+
+
+class FUNNState(NamedTuple):  # funn.py:41-86
+    xi: Any
+    bias: Any
+    hist: Any
+    Fsum: Any
+    F: Any
+    Wp: Any
+    Wp_: Any
+    nn: Any
+    ncalls: int = 0
+
+
+class NNSamplingMethod(GriddedSamplingMethod):
+    """methods/core.py:144-153"""
+
+    def __init__(self, cvs, grid, topology, **kwargs):
+        super().__init__(cvs, grid, **kwargs)
+        self.topology = topology
+
+
+class FUNN(NNSamplingMethod):
+    """
+    methods/funn.py:97-296.  Every step is the fused ABF step (hist / Fsum accumulation, W p solve,
+    force scatter); once `ncalls > 2 * train_freq` the kernel takes the generalized force from the
+    network handed over with psb_set_force_net (funn.py:190,279-284).  The refit (funn.py:213-249:
+    binned mean force -> normalize -> Blackman smoothing -> Levenberg-Marquardt) runs every
+    `train_freq` calls on the method's device, before the step that first uses its result.
+    """
+
+    snapshot_flags = {"positions", "indices", "momenta"}
+    _kind = N.METHOD_ABF
+
+    def __init__(self, cvs, grid, topology, **kwargs):
+        from . import ml
+
+        super().__init__(cvs, grid, topology, **kwargs)
+        self.N = np.asarray(self.kwargs.get("N", 500))
+        self.train_freq = self.kwargs.get("train_freq", 5000)
+        dims = grid.shape.size
+        self.model = ml.MLP(dims, dims, topology, grid.lower, grid.upper, seed=self.kwargs.get("seed", 0),
+                            parameters=self.kwargs.get("initial_params", None))
+        default_optimizer = ml.LevenbergMarquardt(reg=ml.L2Regularization(1e-6))
+        self.optimizer = self.kwargs.get("optimizer", default_optimizer)
+        self.use_pinv = self.kwargs.get("use_pinv", False)
+
+    describe = ABF.describe
+
+    def build(self, snapshot, helpers, *args, **kwargs):
+        from . import ml
+        from .grids import compute_mesh
+
+        native = NativeStep(self, snapshot, helpers, dense_outputs=self.dense_bias)
+        self.native = native
+        grid, model, train_freq = self.grid, self.model, int(self.train_freq)
+        k = native.k
+        gshape = tuple(int(s) for s in grid.shape)
+        dev = native.device
+        inputs = torch.as_tensor(compute_mesh(grid), dtype=torch.float64, device=dev)
+        kernel = ml.blackman_kernel(k, 7)
+        padding = "wrap" if grid.is_periodic else "edge"
+        fit = ml.build_fitting_function(model, self.optimizer)
+        zeros = torch.zeros(k, dtype=torch.float64, device=dev)
+        holder = {"nn": ml.NNData(torch.as_tensor(model.parameters, device=dev), zeros, zeros.clone())}
+
+        def push(nn):
+            native.set_force_net(model.widths, nn.params, nn.mean, nn.std, predict_after=2 * train_freq)
+
+        def learn():  # funn.py:228-239 on the state as it is before this step's sample is added
+            hist = native.view("hist", gshape).to(torch.float64).unsqueeze(-1)
+            y = native.view("Fsum", (*gshape, k)) / torch.clamp(hist, min=1.0)
+            axes = tuple(range(y.ndim - 1))
+            y, mean, std = ml.normalize(y, axes=axes)
+            reference = ml.smooth(y, kernel, padding)
+            params = fit(holder["nn"].params, inputs, reference)
+            return ml.NNData(params, mean, std / reference.std(dim=axes, unbiased=False))
+
+        def make_state():
+            bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+            return FUNNState(
+                native.view("xi", (1, k)), bias, native.view("hist", gshape), native.view("Fsum", (*gshape, k)),
+                native.view("force")[:k], native.view("Wp")[:k], native.view("Wp_")[:k], holder["nn"], native.ncalls,
+            )
+
+        def initialize():
+            native.evaluate(snapshot)
+            push(holder["nn"])  # untrained network: never used before the first fit (funn.py:190-191)
+            return make_state()
+
+        def update(snapshot, state, timestep=0):
+            ncalls = native.ncalls + 1
+            if ncalls > 2 * train_freq and ncalls % train_freq == 1:  # funn.py:190-193
+                holder["nn"] = learn()
+                push(holder["nn"])
+            native.step(snapshot, timestep)
+            return make_state()
+
+        def set_network(nn):
+            """Restart / tests: install a network (NNData) as if it had just been fitted."""
+            holder["nn"] = ml.NNData(*(torch.as_tensor(np.asarray(t) if not isinstance(t, torch.Tensor) else t,
+                                                       dtype=torch.float64, device=dev) for t in nn))
+            push(holder["nn"])
+
+        def restore(prev):
+            """Restart (methods/core.py:327-413): push a saved FUNNState into this handle."""
+            for name, fld in (("xi", "xi"), ("hist", "hist"), ("Fsum", "Fsum"), ("force", "F"), ("Wp", "Wp"),
+                              ("Wp_", "Wp_"), ("ncalls", "ncalls")):
+                value = getattr(prev, fld)
+                native.set_state(name, value.cpu().numpy() if hasattr(value, "cpu") else value)
+            set_network(prev.nn)
+            return make_state()
+
+        update.native = native
+        update.set_network = set_network
+        update.restore = restore
+        return snapshot, initialize, update
 
 
 class UmbrellaIntegration(SamplingMethod):

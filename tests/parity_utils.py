@@ -52,6 +52,12 @@ def make_method(which, spec, cvs):
         return mod.Metadynamics(cvs, *args, kwargs.pop("deltaT", None), **kwargs)
     if name == "ABF":
         return mod.ABF(cvs, kwargs.pop("grid"), **kwargs)
+    if name == "FUNN":
+        if which != "oracle" and "max_iters" in kwargs:  # the oracle takes the LM iteration cap directly
+            from pysages_b200 import ml
+            kwargs["optimizer"] = ml.LevenbergMarquardt(reg=ml.L2Regularization(kwargs.pop("reg", 1e-6)),
+                                                        max_iters=kwargs.pop("max_iters"))
+        return mod.FUNN(cvs, kwargs.pop("grid"), kwargs.pop("topology"), **kwargs)
     raise ValueError(name)
 
 
@@ -191,11 +197,11 @@ class ParityRun:
         else:
             ftol = 2e-7 if f.dtype == np.float32 else 1e-13
             close(f, fo, max(ftol, rtol if f.dtype == np.float64 else ftol), what="forces")
-        for name in ("heights", "centers", "Fsum", "force", "Wp", "Wp_", "grid_potential", "grid_gradient"):
+        for name in ("heights", "centers", "Fsum", "force", "F", "Wp", "Wp_", "grid_potential", "grid_gradient"):
             if hasattr(o, name) and getattr(o, name) is not None:
                 ov = getattr(o, name).numpy()
                 sv = getattr(s, name).cpu().numpy().reshape(ov.shape)
-                close(sv, ov, max(rtol, 1e-9) if name in ("Fsum", "force", "Wp", "Wp_") else rtol, what=name)
+                close(sv, ov, max(rtol, 1e-9) if name in ("Fsum", "force", "F", "Wp", "Wp_") else rtol, what=name)
         if hasattr(o, "hist"):
             assert np.array_equal(s.hist.cpu().numpy().astype(np.int64), o.hist.numpy()), "hist must be bit-exact"
         if hasattr(o, "idx"):

@@ -118,3 +118,37 @@ def test_save_load_restart_matches_uninterrupted_run(tmp_path):
     for name in ("xi", "heights", "centers", "grid_potential", "grid_gradient"):
         np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=name)
     assert int(a.idx) == int(b.idx) == 3 and int(a.ncalls) == int(b.ncalls) == 8
+
+
+def test_funn_run_save_load_restart(tmp_path):
+    """FUNN through `pysages_b200.run` (funn.py:97-210): 10 steps with train_freq = 2 (refits before calls
+    5, 7, 9), checkpoint after 6, resume for 4 == the uninterrupted run: the network travels with the state."""
+    from pysages_b200 import ml
+
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=10, step=0.05)
+
+    def make_method():
+        cvs = [ps.colvars.Distance([G1, G2]), ps.colvars.Component([5, 6, 7], 1)]
+        grid = ps.Grid[ps.Regular]((0.0, -6.0), (12.0, 6.0), (8, 8))
+        opt = ml.LevenbergMarquardt(reg=ml.L2Regularization(1e-6), max_iters=3)
+        return ps.methods.FUNN(cvs, grid, (6, 4), N=2, train_freq=2, optimizer=opt, seed=5)
+
+    def generator(first=0, **kw):
+        return mock.MockEngine("hoomd", snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda",
+                               trajectory=traj[first:])
+
+    full = ps.run(make_method(), generator, 10)
+    part = ps.run(make_method(), generator, 6)
+    ps.save(part, tmp_path / "funn.pkl")
+    loaded = ps.load(tmp_path / "funn.pkl")
+    assert isinstance(loaded.states[0].nn.params, np.ndarray) and int(loaded.states[0].ncalls) == 6
+    resumed = ps.run(loaded, generator, 4, context_args=dict(first=6))
+    torch.cuda.synchronize()
+    a, b = resumed.states[0], full.states[0]
+    for name in ("xi", "hist", "Fsum", "F", "Wp", "Wp_"):
+        np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=name)
+    for name in ("params", "mean", "std"):
+        np.testing.assert_array_equal(getattr(a.nn, name).cpu().numpy(), getattr(b.nn, name).cpu().numpy(), err_msg=name)
+    assert int(a.ncalls) == int(b.ncalls) == 10
+    assert not np.array_equal(b.nn.params.cpu().numpy(), make_method().model.parameters)  # it was refitted

@@ -52,3 +52,24 @@ def test_step_errors():
     state = update(device_snapshot(snap), init())
     torch.cuda.synchronize()
     assert int(state.ncalls) == 1
+
+
+def test_force_net_errors():
+    snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
+    _, _, update = build(ps.methods.HarmonicBias([ps.colvars.Distance([1, 2])], 1.0, [0.0]), snap)
+    with pytest.raises(ValueError, match="ABF-family"):
+        update.native.set_force_net([1, 4, 1], np.zeros(13), [0.0], [1.0], predict_after=0)
+    grid = ps.Grid((0.0,), (5.0,), (8,))
+    _, _, update = build(ps.methods.ABF([ps.colvars.Distance([1, 2])], grid), snap)
+    native = update.native
+    with pytest.raises(ValueError, match="input and output width"):
+        native.set_force_net([2, 4, 1], np.zeros(17), [0.0], [1.0], predict_after=0)
+    with pytest.raises(ValueError, match="layer widths"):
+        native.set_force_net([1, 129, 1], np.zeros(388), [0.0], [1.0], predict_after=0)
+    with pytest.raises(ValueError, match="dense layers"):
+        native.set_force_net([1] * 11, np.zeros(20), [0.0], [1.0], predict_after=0)
+    with pytest.raises(ValueError, match="unknown activation"):
+        native.set_force_net([1, 4, 1], np.zeros(13), [0.0], [1.0], predict_after=0, activation=7)
+    native.set_force_net([1, 4, 1], np.zeros(13), [0.0], [1.0], predict_after=0)  # and a valid one is accepted
+    with pytest.raises(ValueError, match="expected 13 network parameters"):
+        ps.methods.FUNN([ps.colvars.Distance([1, 2])], grid, (4,), initial_params=np.zeros(12))

@@ -565,3 +565,81 @@ def test_shared_hills_single_walker_equals_plain_metadynamics(golden, grid):
     for name in ("heights", "centers", "idx"):
         assert torch.equal(getattr(plain.state, name), getattr(shared.state, name)), name
     assert int(shared.state.idx) == 3
+
+
+# ---- FUNN: ABF accumulation + force from the network (row K) ----------------------------------------
+FUNN_GRID = ((0.0, 0.0), (8.0, 8.0), (8, 8), "regular")
+
+
+@pytest.mark.parametrize("layout, dtype", LAYOUTS)
+@pytest.mark.parametrize("restraints", [None, ((0.0, 0.0), (8.0, 8.0), (20.0, 20.0), (20.0, 20.0))])
+def test_funn_network_force(layout, dtype, restraints):
+    """funn.py:187-296 with train_freq = 2: calls 1-4 are plain ABF, call 5 refits (LM capped at 0
+    iterations so both sides keep the SAME weights; mean / std come from the normalized, Blackman-
+    smoothed binned force) and from then on F = std * mlp(scale(f32(xi))) + mean inside the kernel."""
+    snap = snapshot(layout, dtype)
+    kw = dict(grid=FUNN_GRID, topology=(7, 5), N=2, train_freq=2, restraints=restraints, max_iters=0, seed=4)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("FUNN", kw), units="real" if layout == "lammps" else None)
+    for pos in perturbed(snap, 9, 0.1):
+        run.step(pos)
+    assert run.native.ncalls == 9
+    nn, onn = run.state.nn, run.ostate.nn
+    tol = max(1e-9, 10 * run.rtol)  # fp32 engines: Fsum itself only agrees to single precision
+    np.testing.assert_allclose(nn.mean.cpu().numpy(), onn.mean, rtol=tol)
+    np.testing.assert_allclose(nn.std.cpu().numpy(), onn.std, rtol=tol)
+    assert np.any(nn.std.cpu().numpy() != 0.0)  # the network force was live, not a zero
+
+
+def test_funn_refit_tracks_oracle():
+    """The cadenced Levenberg-Marquardt refit (ml/optimizers.py:188-232) on the device against the numpy
+    restatement: same start, a few iterations -> same weights to solver rounding, same network force."""
+    snap = snapshot("hoomd", np.float64)
+    kw = dict(grid=FUNN_GRID, topology=(6,), N=2, train_freq=3, max_iters=4, seed=9)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("FUNN", kw))
+    frames = perturbed(snap, 8, 0.1)
+    for pos in frames[:6]:
+        run.step(pos)
+    ours, ref = run.step(frames[6], check=False)  # call 7 = 2 * train_freq + 1: first fit
+    p, po = ours.nn.params.cpu().numpy(), ref.nn.params
+    assert not np.array_equal(po, run.omethod.initial_params)
+    np.testing.assert_allclose(p, po, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ours.F.cpu().numpy(), ref.F.numpy(), rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(ours.bias.cpu().numpy(), ref.bias.numpy(), rtol=1e-5, atol=1e-8)
+    assert np.array_equal(ours.hist.cpu().numpy().astype(np.int64), ref.hist.numpy())
+
+
+@pytest.mark.parametrize("activation", ["tanh", "sin"])
+@pytest.mark.parametrize("topology", [(), (128,) * 7, (3, 128, 1, 40)])
+def test_force_net_kernel_against_oracle_mlp(activation, topology):
+    """psb_set_force_net directly: widest / deepest networks the ABI admits, tanh and sine layers,
+    weights handed over from device memory; F read back from the state against oracle.ml.mlp_apply."""
+    from oracle import ml as oml
+    from pysages_b200 import _native as N
+
+    snap = snapshot("hoomd", np.float64)
+    grid = ((0.0, 0.0), (8.0, 8.0), (8, 8), "regular")
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("ABF", dict(grid=grid, N=2)))
+    widths = oml.layer_sizes(2, topology, 2)
+    rng = np.random.default_rng(len(topology))
+    params = oml.init_params(widths, seed=21) * (3.0 if activation == "tanh" else 1.0)
+    mean, std = rng.normal(size=2), rng.uniform(0.5, 2.0, size=2)
+    dev_params = torch.as_tensor(params, device="cuda")
+    run.native.set_force_net(widths, dev_params, mean, std, predict_after=2,
+                             activation=N.ACT_SIN if activation == "sin" else N.ACT_TANH, omega0=16.0, omega=1.5)
+    frames = perturbed(snap, 5, 0.1)
+    for i, pos in enumerate(frames):
+        ours, ref = run.step(pos, check=i < 2)  # calls 1, 2: still the binned average == the oracle's ABF
+        if i >= 2:
+            xi = ours.xi.cpu().numpy().astype(np.float32).astype(np.float64)
+            want = std * oml.mlp_apply(params, widths, xi, grid[0], grid[1], activation, 16.0, 1.5).ravel() + mean
+            np.testing.assert_allclose(ours.force.cpu().numpy(), want, rtol=1e-10, atol=1e-12)
+            # hist / Fsum keep accumulating exactly as in ABF, with the network force as F_prev
+            assert int(ours.hist.sum()) == i + 1
+    run.native.set_force_net([], None, None, None, predict_after=0)  # n_dense = 0: plain ABF again
+    ours, _ = run.step(frames[0], check=False)
+    import pysages_b200 as ps
+
+    idx = [int(v) for v in ps.grids.build_indexer(run.method.grid)(ours.xi.cpu().numpy().reshape(1, -1))]
+    flat = int(np.ravel_multi_index(tuple(min(v, 7) for v in idx), (8, 8)))  # gathers clamp
+    want = ours.Fsum.reshape(-1, 2)[flat].cpu().numpy() / max(2, int(ours.hist.reshape(-1)[flat]))
+    np.testing.assert_allclose(ours.force.cpu().numpy(), want, rtol=1e-12)
