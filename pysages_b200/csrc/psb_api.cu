@@ -52,6 +52,7 @@ struct psb_handle {
   Model* d_model = nullptr;  // device copy read by the step kernel (uploaded at the end of psb_create)
   char* d_nn = nullptr;      // ForceNet header + parameters (psb_set_force_net)
   size_t nn_capacity = 0;
+  unsigned long long* d_cta_seq = nullptr;  // per-CTA launch counters (LL exchange)
   psb_layout_desc layout;
   psb_method_desc method;
   std::vector<void*> allocs;
@@ -141,6 +142,7 @@ Snap make_snap(const psb_handle* h, const psb_snapshot* s, int mode) {
   S.need_momenta = h->layout.need_momenta;
   S.mode = mode;
   S.dbg = h->dbg ? h->dbg + (size_t)(h->launches & 1) * 16 * h->grid : nullptr;
+  S.cta_seq = h->model.ll_reduce ? h->d_cta_seq : nullptr;
   return S;
 }
 
@@ -335,6 +337,8 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       if (gd.shape[d] < 1) return bail(fail(PSB_ERR_VALUE, "grid shape must be positive"));
       m.g_lower[d] = gd.lower[d];
       m.g_upper[d] = gd.upper[d];
+      m.g_h[d] = (gd.upper[d] - gd.lower[d]) / (double)gd.shape[d];  // the same two IEEE divisions as grid_index_1d
+      m.g_inv_h[d] = 1.0 / m.g_h[d];
       m.g_shape[d] = gd.shape[d];
       m.grid_points *= gd.shape[d];
     }
@@ -611,6 +615,17 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       M.cta_hi[g] = first + n - 1;
       first += n;
     }
+    // Pass-A partials through flagged words instead of a counter barrier (reduce_rows_ll, psb_step.cuh):
+    // point-CV class, methods whose finalizer needs nothing else from other CTAs, and every CTA's share
+    // small enough for the register cache, so that all of them publish from the staged sums.
+    const bool ll_method = method->kind == PSB_METHOD_UNBIASED || method->kind == PSB_METHOD_HARMONIC ||
+                           method->kind == PSB_METHOD_ABF;
+    if (h->step_general == SC_POINT && ll_method && per <= (long long)CT * BLOCK && !getenv("PSB_NO_LL")) {
+      M.ll_reduce = 1;
+      psb_status st = dev_alloc(h, &M.ll, (size_t)MAXG * NACC * h->grid);
+      if (st == PSB_OK) st = dev_alloc(h, &h->d_cta_seq, (size_t)h->grid);
+      if (st != PSB_OK) return bail(st);
+    }
   }
   {
     const bool momenta_sums = layout->need_momenta && M.abf_fast;
@@ -725,7 +740,10 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
   // replayed (the kernels keep no host-side counters: barrier epochs and method state live on the
   // device, so replays are exact).  PSB_NO_GRAPH=1 or debug timing fall back to plain launches.
   static const bool no_graph = getenv("PSB_NO_GRAPH") != nullptr;
-  if (!no_graph && !h->dbg && stream != nullptr && nsteps >= 2 * (int64_t)nsnaps) {
+  // PSB_DEBUG_TIMING=graph keeps the graph: captured nodes alternate between the two stamp halves,
+  // which stays consistent across replays when the ring has an even number of snapshots
+  static const bool dbg_graph = getenv("PSB_DEBUG_TIMING") && std::string(getenv("PSB_DEBUG_TIMING")) == "graph";
+  if (!no_graph && (!h->dbg || (dbg_graph && nsnaps % 2 == 0)) && stream != nullptr && nsteps >= 2 * (int64_t)nsnaps) {
     const bool same = h->cycle_exec && h->cycle_stream == stream && (int)h->cycle_key.size() == nsnaps &&
                       memcmp(h->cycle_key.data(), snaps, sizeof(psb_snapshot) * nsnaps) == 0;
     if (!same) {

@@ -15,6 +15,7 @@ constexpr int MAXCV = PSB_MAX_CVS;
 constexpr int NACC = 16;           // fp64 accumulators per group and pass
 constexpr int VGROUP = MAXG;       // virtual group slot used by grid-wide method reductions
 constexpr int BLOCK = 256;         // threads per CTA of the step kernel
+constexpr int CT = 4;              // terms per thread the step kernel keeps in registers (slot, position, prefetched force)
 constexpr int NWARPS = BLOCK / 32;
 constexpr int HILL_STAGE_BYTES = 20480;  // per TMA stage (2 stages)
 constexpr int PAIR_BLOCK = 256;          // threads per CTA of the pair kernel
@@ -63,6 +64,7 @@ struct MethodDev {
   double force_unit_factor;
   int32_t grid_kind, grid_ndim;
   double g_lower[PSB_MAX_GRID_DIMS], g_upper[PSB_MAX_GRID_DIMS];
+  double g_h[PSB_MAX_GRID_DIMS], g_inv_h[PSB_MAX_GRID_DIMS];  // bin width (upper - lower) / shape and fl(1 / h)
   int32_t g_shape[PSB_MAX_GRID_DIMS];
   long long grid_points;
 };
@@ -117,7 +119,8 @@ struct Fin {
   double Wp[MAXK];          // ABF: solve(J J^T, J p)
   double Fsum_new[MAXK];    // ABF: Fsum[I] after this step's scatter-add
   double Fsum_old[MAXK];    // ABF: Fsum[I] as gathered (helper warp)
-  unsigned long long hist_old;  // ABF: hist[I] as gathered (helper warp)
+  double den;               // ABF: max(N, hist[I] after the scatter-add) (helper warp)
+  double rforce[MAXK];      // ABF: restraint force when xi is outside the grid (helper warp)
   long long flat;           // clamped flat grid offset of xi
   long long nh;             // number of hills summed this step
   uint32_t I[PSB_MAX_GRID_DIMS];
@@ -166,6 +169,9 @@ struct Model {
   StateDev st;
   Fin* fin;
   double* partials;           // ((MAXG+1) * NACC, gridDim) fp64
+  ulonglong2* ll;             // (MAXG * NACC, gridDim) pass-A partials as two {32 data bits, 32-bit launch stamp} words
+  int32_t ll_reduce;          // pass A exchanges its partials through `ll` (no counter barrier): see reduce_rows_ll
+  int32_t ll_pad;
   BarrierState* bars;         // (NBARS) monotonic arrival counters
   unsigned long long* epochs; // (NBARS) completed uses of each barrier
   int32_t cross_overlap;      // some atom belongs to two different groups
@@ -196,6 +202,7 @@ struct Snap {
   const double* records;  // walker finish: gathered hill records
   double* record_out;     // walker begin: this walker's record
   long long* dbg;         // optional (PSB_DEBUG_TIMING=1): phase timestamps [2][grid][16], by launch parity
+  unsigned long long* cta_seq;  // (gridDim) launches of this handle seen by each CTA; nullptr unless Model::ll_reduce
 };
 
 enum { MODE_STEP = 0, MODE_EVAL = 1, MODE_WALKER_BEGIN = 2, MODE_WALKER_FINISH = 3 };

@@ -119,15 +119,16 @@ PSB_HD double jax_remainder(double x1, double x2) {
   return plus ? t + x2 : t;
 }
 
-// The same value as jax_floor_divide(a, b) for b > 0 and |a / b| < 2^50, without fmod and with
-// one division: floor of the EXACT quotient.  Work on |a| like fmod does: t = floor(fl(|a| / b))
-// is off by at most one, and the remainder |a| - t * b of the correct t is exactly representable,
-// so one fma gives it exactly (for a wrong t the sign / range test below is still decided
-// correctly because rounding is monotonic).  jax's (a - mod) / b differs from the resulting
-// integer by < 2^-51 * |q|, so its final round() returns it unchanged.
-PSB_HD bool fast_floor_divide(double a, double b, double* out) {
+// The same value as jax_floor_divide(a, b) for b > 0 and |a / b| < 2^50, without fmod and without a
+// division on the critical path: floor of the EXACT quotient.  Work on |a| like fmod does:
+// t = floor(fl(|a| * fl(1 / b))) is off by at most one (two roundings: < 2^-52 |a / b| < 1/4), and the
+// remainder |a| - t * b of the correct t is exactly representable, so one fma gives it exactly (for a
+// wrong t the sign / range test below is still decided correctly because rounding is monotonic).
+// jax's (a - mod) / b differs from the resulting integer by < 2^-51 * |q|, so its final round()
+// returns it unchanged.  inv_b must be fl(1 / b).
+PSB_HD bool fast_floor_divide(double a, double b, double inv_b, double* out) {
   const double A = fabs(a);
-  double t = floor(A / b);
+  double t = floor(A * inv_b);
   if (!(t < 1125899906842624.0) || !(b > 0.0)) return false;  // also rejects NaN / inf
   double r = fma(-t, b, A);
   if (r < 0.0) t -= 1.0;
@@ -159,13 +160,14 @@ PSB_HD_COLD uint32_t grid_index_slow(int kind, double x, double lower, double up
   return (uint32_t)idx;
 }
 
-// Regular / periodic grids take the division-only path; anything unusual (Chebyshev, huge or
+// Regular / periodic grids take the fma-corrected path; anything unusual (Chebyshev, huge or
 // non-finite quotients, non-positive bin width) goes through the literal restatement above.
-PSB_HD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape) {
+// h = (upper - lower) / shape and inv_h = 1 / h are per-axis constants (the step kernel gets them
+// from psb_create, computed with the same two IEEE divisions).
+PSB_HD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape, double h, double inv_h) {
   if (kind == 1 || kind == 2) {
-    const double h = (upper - lower) / (double)shape;
     double q;
-    if (fast_floor_divide(x - lower, h, &q)) {
+    if (fast_floor_divide(x - lower, h, inv_h, &q)) {
       if (kind == 1) return (q < 0.0 || q > (double)shape) ? (uint32_t)shape : (uint32_t)q;  // grids.py:117-121
       if (fabs(q) < 2147483648.0) {  // grids.py:134-138: idx % shape (Python sign convention)
         int r = (int)q % shape;
@@ -175,6 +177,10 @@ PSB_HD uint32_t grid_index_1d(int kind, double x, double lower, double upper, in
     }
   }
   return grid_index_slow(kind, x, lower, upper, shape);
+}
+PSB_HD uint32_t grid_index_1d(int kind, double x, double lower, double upper, int32_t shape) {
+  const double h = (upper - lower) / (double)shape;
+  return grid_index_1d(kind, x, lower, upper, shape, h, 1.0 / h);
 }
 
 // approxfun/core.py:107-136: centre of bin k along one axis

@@ -28,7 +28,6 @@
 
 namespace psb {
 
-constexpr int CT = 4;  // terms per thread kept in registers (slot, position, prefetched force)
 
 // The step kernel is compiled once per (engine layout, dtype, method, CV class): the finalizer
 // code is executed once per launch by one warp, so it runs at instruction-fetch speed; keeping
@@ -113,6 +112,7 @@ struct StepShared {
   Pre pre;  // method-state scalars as they were when the step began
   unsigned long long epoch[NBARS];  // completed uses of each grid barrier when the step began
   uint32_t bars_used;               // barriers this launch arrived on (thread 0)
+  unsigned long long seq;           // launches of this handle before this one (Snap::cta_seq), LL stamp source
   uint64_t mbar[2];
   double nnbuf[2][PSB_MAX_WIDTH];  // force network activations (force_net_eval)
 };
@@ -223,12 +223,16 @@ __device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int 
       double v = 0.0;
       if (p.dst >= 0) {
         const double* src = M.partials + (size_t)p.dst * nb;
-        for (int bb = p.blo + sub; bb <= p.bhi; bb += 32) {
+        // six loads in flight per lane: a group spread over <= 48 CTAs (the group-aligned split of
+        // the headline shape gives 37) costs ONE L2 round trip
+        for (int bb = p.blo + sub; bb <= p.bhi; bb += 48) {
           const double a0 = __ldcg(src + bb);
           const double a1 = bb + 8 <= p.bhi ? __ldcg(src + bb + 8) : 0.0;
           const double a2 = bb + 16 <= p.bhi ? __ldcg(src + bb + 16) : 0.0;
           const double a3 = bb + 24 <= p.bhi ? __ldcg(src + bb + 24) : 0.0;
-          v += (a0 + a1) + (a2 + a3);
+          const double a4 = bb + 32 <= p.bhi ? __ldcg(src + bb + 32) : 0.0;
+          const double a5 = bb + 40 <= p.bhi ? __ldcg(src + bb + 40) : 0.0;
+          v += ((a0 + a1) + (a2 + a3)) + (a4 + a5);
         }
       }
       v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -238,6 +242,63 @@ __device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int 
     }
   }
   __syncthreads();
+}
+
+// ---- pass-A exchange without a counter barrier ("LL": the flag travels with the data) -----------
+// The counter barrier costs three dependent L2 round trips after griddepcontrol.wait: the epoch load
+// (the arrival target), arrive -> poll, then the loads of the partials.  Here every partial sum is
+// stored as two 8-byte words {32 data bits | 32-bit launch stamp}; an 8-byte store is single-copy
+// atomic, so a reader that sees the stamp of this launch in both words has the value -- no fence, no
+// counter, and the readers poll the data itself: one round trip after the last CTA has published.
+// The stamp is the number of launches this handle has made (Snap::cta_seq: one counter per CTA,
+// bumped at kernel entry BEFORE the dependent launch is released, so every CTA of a launch reads the
+// same value without any cross-CTA synchronisation) + 1.  Every (row, CTA) entry a launch reads is
+// rewritten by that launch, so a stale stamp is always an older one.
+// What the barrier also ordered -- CTA 0 overwriting state scalars that other CTAs read in their
+// prologue -- is ordered by the readers-done counter instead (end of the kernel).
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, uint32_t stamp) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long tag = (unsigned long long)stamp << 32;
+  const unsigned long long lo = (bits & 0xFFFFFFFFULL) | tag, hi = (bits >> 32) | tag;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ void ll_load(const ulonglong2* p, unsigned long long& lo, unsigned long long& hi) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+}
+// reduce_rows for pass A over the LL buffer; the caller ends it with __syncthreads().
+__device__ __forceinline__ void reduce_rows_ll(const Model& M, StepShared& sh, RowPlan first, uint32_t stamp) {
+  const int nb = gridDim.x;
+  const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int nrows = M.row_first[0][M.ngroups];
+  for (int r0 = 0; r0 < nrows; r0 += BLOCK / 8) {
+    const RowPlan p = (r0 == 0) ? first : row_plan(M, 0, 0, r0 + rl);
+    double v = 0.0;
+    if (p.dst >= 0) {
+      const ulonglong2* src = M.ll + (size_t)p.dst * nb;
+      for (int bb = p.blo + sub; bb <= p.bhi; bb += 48) {
+        unsigned long long lo[6], hi[6];
+        bool ok;
+        do {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            lo[j] = hi[j] = (unsigned long long)stamp << 32;  // absent entries read as +0.0
+            if (bb + 8 * j <= p.bhi) ll_load(src + bb + 8 * j, lo[j], hi[j]);
+          }
+          ok = true;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) ok = ok && (uint32_t)(lo[j] >> 32) == stamp && (uint32_t)(hi[j] >> 32) == stamp;
+        } while (!ok);
+        double a[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a[j] = __longlong_as_double((long long)((lo[j] & 0xFFFFFFFFULL) | (hi[j] << 32)));
+        v += ((a[0] + a[1]) + (a[2] + a[3])) + (a[4] + a[5]);
+      }
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (p.dst >= 0 && sub == 0) (&sh.tot[0][0])[p.dst] = v;
+  }
 }
 
 // ---- finalizers (warp 0 of every CTA) ----------------------------------------------------------
@@ -357,7 +418,8 @@ __device__ __forceinline__ long long grid_flat_clamped(const MethodDev& m, const
 // flag (any index == shape, grids.py:120) and the clamped flat offset.
 __device__ __forceinline__ void grid_bin_warp(const MethodDev& m, Fin& f, int lane) {
   if (lane < m.grid_ndim)
-    f.I[lane] = grid_index_1d(m.grid_kind, f.xi[lane], m.g_lower[lane], m.g_upper[lane], m.g_shape[lane]);
+    f.I[lane] = grid_index_1d(m.grid_kind, f.xi[lane], m.g_lower[lane], m.g_upper[lane], m.g_shape[lane],
+                              m.g_h[lane], m.g_inv_h[lane]);
   __syncwarp();
   if (lane == 0) {
     bool oob = false;
@@ -392,7 +454,7 @@ __device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int
     if (lane < M.k) M.st.F[lane] = f.F[lane];
     if (lane == 0) {
       *M.st.energy = f.energy;
-      *M.st.ncalls = sh.pre.ncalls + 1;
+      if (!M.ll_reduce) *M.st.ncalls = sh.pre.ncalls + 1;  // LL exchange: stored after the readers-done wait
     }
   }
 }
@@ -436,17 +498,38 @@ static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const M
 // abf.py:210-225 once f.JJt / f.Jp are known (warp 0, all lanes).  Every CTA derives the new
 // histogram count and force sum of bin I from the values the step began with; CTA 0 stores them
 // after the last reader is done (end of the kernel).
-// warp 1, concurrently with warp 0's J J^T / solve: bin index of xi and the gather of hist[I] / Fsum[I]
-__device__ __forceinline__ void abf_helper(const Model& M, StepShared& sh, int lane) {
+// Everything of abf.py:213-258 that depends on xi alone: the bin of xi, the gathered hist[I] / Fsum[I]
+// (gathers clamp, JAX default), the new count, max(N, count) as a double and the restraint force
+// outside the grid.  Point-CV kernels run it on warp 1 while warp 0 does J p / solve.
+__device__ __forceinline__ void abf_bin_gather(const Model& M, StepShared& sh, int lane) {
   Fin& f = sh.fin;
-  pair_sync(1);  // xi is final
-  grid_bin_warp(M.m, f, lane);
-  if (lane < M.k) f.Fsum_old[lane] = __ldcg(M.st.Fsum + f.flat * M.k + lane);
-  if (lane == 0) f.hist_old = __ldcg(M.st.hist + f.flat);  // gather clamps (JAX default)
+  const MethodDev& m = M.m;
+  grid_bin_warp(m, f, lane);  // ends with __syncwarp
+  if (lane < M.k) {
+    const bool oob = f.oob != 0;
+    f.Fsum_old[lane] = __ldcg(M.st.Fsum + f.flat * M.k + lane);
+    f.rforce[lane] = (m.has_restraints && oob)
+                         ? restraint_force(m.r_lower[lane], m.r_upper[lane], m.r_kl[lane], m.r_ku[lane], f.xi[lane])
+                         : 0.0;
+    if (lane == 0) {
+      const uint32_t h = __ldcg(M.st.hist + f.flat) + (oob ? 0u : 1u);  // .at[I].add drops out-of-range updates
+      const unsigned long long hh = h, nmin = (unsigned long long)m.abf_N;
+      f.hist_new = h;
+      f.in_range = oob ? 0 : 1;
+      f.den = (double)(nmin > hh ? nmin : hh);
+    }
+  }
   __syncwarp();
+}
+__device__ __forceinline__ void abf_helper(const Model& M, StepShared& sh, int lane) {
+  pair_sync(1);  // xi is final
+  abf_bin_gather(M, sh, lane);
   pair_sync(2);  // bin + gathered values are in shared memory
 }
 
+// abf.py:210-225 once f.Jp (and f.JJt, or f.Wp) are known (warp 0, all lanes).  Every CTA derives the
+// new histogram count and force sum of bin I from the values the step began with; CTA 0 stores them
+// after the last reader is done (end of the kernel).
 __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0,
                                            bool helped, bool have_Wp) {
   Fin& f = sh.fin;
@@ -467,44 +550,29 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
     __syncwarp();
     pair_sync(2);  // warp 1 has binned xi and gathered hist[I], Fsum[I]
   } else {
-    grid_bin_warp(m, f, lane);  // ends with __syncwarp
-    if (lane < k) f.Fsum_old[lane] = __ldcg(M.st.Fsum + f.flat * k + lane);
-    if (lane == 0) f.hist_old = __ldcg(M.st.hist + f.flat);  // gather clamps (JAX default)
-    __syncwarp();
+    abf_bin_gather(M, sh, lane);
   }
   PSB_CLK(13);
   const bool oob = f.oob != 0;
-  if (lane == 0) f.in_range = oob ? 0 : 1;  // .at[I].add drops out-of-range updates
   // funn.py:190,286-296: past the ABF-only stage the force comes from the network (restraints first)
   const ForceNet* nn = M.nn;
   const bool use_net = nn != nullptr && !(m.has_restraints && oob) && sh.pre.ncalls + 1 > __ldg(&nn->predict_after);
   const double f_net = use_net ? force_net_eval(nn, m, f.xi, &sh.nnbuf[0][0], lane) : 0.0;
   if (lane < k) {
     const int c = lane;
-    uint32_t h = (uint32_t)f.hist_old;
+    const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
     double fs = f.Fsum_old[c];
     if (!oob) {
-      h += 1u;
-      const double dWp_dt = (1.5 * f.Wp[c] - 2.0 * sh.pre.Wp[c] + 0.5 * sh.pre.Wp_[c]) / S.dt;
+      const double dWp_dt = (1.5 * Wp_now - 2.0 * Wp_1 + 0.5 * sh.pre.Wp_[c]) / S.dt;
       fs += m.force_unit_factor * dWp_dt + sh.pre.force[c];
     }
-    double fc;
-    if (m.has_restraints && oob) {
-      fc = restraint_force(m.r_lower[c], m.r_upper[c], m.r_kl[c], m.r_ku[c], f.xi[c]);
-    } else if (use_net) {
-      fc = f_net;
-    } else {
-      const unsigned long long hh = h;
-      const double den = (double)((unsigned long long)m.abf_N > hh ? (unsigned long long)m.abf_N : hh);
-      fc = fs / den;
-    }
+    const double fc = (m.has_restraints && oob) ? f.rforce[c] : (use_net ? f_net : fs / f.den);
     f.F[c] = fc;
     f.Fsum_new[c] = fs;
-    if (c == 0) f.hist_new = h;
-    if (cta0) {  // scalars nobody reads after the first barrier
+    if (cta0 && !M.ll_reduce) {  // scalars nobody reads after the first barrier (LL exchange: stored at the end)
       M.st.force[c] = fc;
-      M.st.Wp_[c] = sh.pre.Wp[c];
-      M.st.Wp[c] = f.Wp[c];
+      M.st.Wp_[c] = Wp_1;
+      M.st.Wp[c] = Wp_now;
     }
   }
   if (lane == 0) f.energy = 0.0;
@@ -874,10 +942,16 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     // the immutable model and -- see pass A -- its gather of engine arrays this library never writes
     // overlap the previous step's tail; everything after griddepcontrol.wait sees the previous kernel
     // complete.  Without the launch attribute both instructions are no-ops.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // LL exchange (Snap::cta_seq set): this CTA's launch count must be bumped before the next launch of
+    // the handle may start, so the trigger follows the atomic (one round trip, shared with the copy).
+    unsigned long long seq = 0;
+    if (S.cta_seq == nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else if (tid == 0) seq = atomicAdd(S.cta_seq + blockIdx.x, 1ULL);
     for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = __ldg(src + i);
+    if (tid == 0) sh.seq = seq;
   }
   __syncthreads();
+  if (S.cta_seq != nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const Model& M = sM;
   PSB_CLKA(8);
 
@@ -924,6 +998,10 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
   }
   const bool cached = !skip_cv && !slot_major && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
+  // pass-A partials through the LL buffer (host: every CTA with a group is `cached`, nothing but the
+  // partials crosses CTAs before the finalizer); grid-uniform
+  const bool ll = !GENERAL && !SLOT && !WALK && M.ll_reduce && nb > 1;
+  const uint32_t ll_stamp = (uint32_t)(sh.seq + 1ULL);
   const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
   const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
   uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
@@ -1071,9 +1149,12 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
           if (will_scatter) cfv[i] = A::load_force(S, cslot[i]);
         }
       }
-      if (tid < stage_na) __stcg(M.partials + (size_t)(seg_g * NACC + tid) * nb + b, sh.stage[tid]);
+      if (tid < stage_na) {
+        if (ll) ll_store(M.ll + (size_t)(seg_g * NACC + tid) * nb + b, sh.stage[tid], ll_stamp);
+        else __stcg(M.partials + (size_t)(seg_g * NACC + tid) * nb + b, sh.stage[tid]);
+      }
     }
-    commit_pre();
+    if (!ll) commit_pre();  // LL exchange: the prologue values are not needed before the reduction
     // ---- slot-major gather (most atoms selected, too many to keep in registers) ---------------
     // A random tag -> slot permutation makes the tag-ordered gather pay one L1 tag lookup per
     // 16-byte row (measured: ~6 lookups per atom, 1 lookup/clk/SM -> 20 us per 1e6 atoms, far
@@ -1185,10 +1266,18 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
 
     PSB_STAMP(1);
     const RowPlan planA = row_plan(M, 0, 0, tid >> 3);
-    grid_sync(M, sh, BAR_A);
-    PSB_STAMP(2);
-    PSB_CLK(8);
-    reduce_rows(M, sh, 0, 0, planA);
+    if (ll) {
+      PSB_STAMP(2);
+      PSB_CLK(8);
+      reduce_rows_ll(M, sh, planA, ll_stamp);
+      commit_pre();
+      __syncthreads();
+    } else {
+      grid_sync(M, sh, BAR_A);
+      PSB_STAMP(2);
+      PSB_CLK(8);
+      reduce_rows(M, sh, 0, 0, planA);
+    }
     PSB_CLK(9);
     if (warp == 0) {
       if (any_coord) reduce_coordination(M, sh, lane);
@@ -1439,7 +1528,8 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   // its own scatter is done (no tail wait).
   unsigned long long readers_want = 0;
   const bool abf_commit = (is_abf && nb > 1 && S.mode == MODE_STEP);
-  if (abf_commit && tid == 0) {
+  const bool readers = abf_commit || ll;  // LL exchange: also orders CTA 0's state stores after every prologue
+  if (readers && tid == 0) {
     red_add_u64(&M.bars[BAR_READERS].arrive, 1ULL);
     sh.bars_used |= 1u << BAR_READERS;
     readers_want = (sh.epoch[BAR_READERS] + 1ULL) * gridDim.x;
@@ -1553,15 +1643,24 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   PSB_STAMP(5);
 
   // ---- ABF commit: CTA 0 stores the new count / force sum of bin I (abf.py:216-218) -------------
-  if (is_abf && cta0 && S.mode == MODE_STEP && tid == 0) {
-    if (abf_commit) grid_wait(M, BAR_READERS, readers_want);
+  if (cta0 && tid == 0) {
+    if (readers) grid_wait(M, BAR_READERS, readers_want);
     const Fin& f = sh.fin;
-    if (f.in_range) {
-      M.st.hist[f.flat] = f.hist_new;
-      for (int c = 0; c < k; ++c) M.st.Fsum[f.flat * k + c] = f.Fsum_new[c];
+    if (is_abf && S.mode == MODE_STEP) {
+      if (f.in_range) {
+        M.st.hist[f.flat] = f.hist_new;
+        for (int c = 0; c < k; ++c) M.st.Fsum[f.flat * k + c] = f.Fsum_new[c];
+      }
+      if (ll)  // deferred from abf_finish
+        for (int c = 0; c < k; ++c) {
+          M.st.force[c] = f.F[c];
+          M.st.Wp_[c] = sh.pre.Wp[c];
+          M.st.Wp[c] = f.Wp[c];
+        }
     }
+    if (ll && S.mode != MODE_EVAL) *M.st.ncalls = sh.pre.ncalls + 1;  // deferred from finish_force
+    commit_epochs(M, sh);
   }
-  if (cta0 && tid == 0) commit_epochs(M, sh);
   PSB_STAMP(6);
 }
 

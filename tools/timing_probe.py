@@ -1,7 +1,7 @@
 """Per-phase timestamps of the fused step kernel (PSB_DEBUG_TIMING=1), for latency work.
    python tools/timing_probe.py            (on the GPU box)"""
 import os, sys
-os.environ["PSB_DEBUG_TIMING"] = "1"
+os.environ.setdefault("PSB_DEBUG_TIMING", "1")  # "graph": keep CUDA-graph replay + PDL while stamping
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
@@ -50,6 +50,9 @@ for wl, natoms in cases:
             continue
         col = rel(t[:, i])
         print(f"  {nme:15s}: min {col.min():6.2f} median {np.median(col):6.2f} max {col.max():6.2f}")
+    pe = prev[:, 6].max()
+    print("  relative to the END of the previous kernel (max over CTAs): " + ", ".join(
+        f"{nme}={np.median(t[:, i] - pe) / 1e3:.2f}" for i, nme in enumerate(names[:7])))
     c = t[0, 8:16]
     cn = ["pre-reduce", "reduce_rows", "finalize_cv", "JJt/Jp", "solve", "grid_bin", "hist gather+F", "finish_force(end post_cv)"]
     base = c[0]
