@@ -1013,6 +1013,7 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
     return fail(PSB_ERR_VALUE, "a force network needs an ABF-family method (funn.py:187-210)");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   const ForceNet* target = nullptr;
+  size_t nparams_total = 0;
   if (net->n_dense != 0) {
     if (net->n_dense < 1 || net->n_dense > PSB_MAX_DENSE)
       return fail(PSB_ERR_VALUE, "force network: between 1 and %d dense layers (got %d)", PSB_MAX_DENSE, net->n_dense);
@@ -1039,6 +1040,7 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
       }
     }
     for (int c = 0; c < MAXK; ++c) { hn.mean[c] = net->mean[c]; hn.std[c] = net->std[c]; }
+    nparams_total = nparams;
     const size_t bytes = sizeof(ForceNet) + nparams * sizeof(double);
     if (bytes > h->nn_capacity) {  // first network, or a larger topology than before
       CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1053,8 +1055,10 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
                              net->params_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     target = reinterpret_cast<const ForceNet*>(h->d_nn);
   }
-  if (M.nn != target) {
+  const int32_t staged = (target && nparams_total <= (size_t)NN_STAGE) ? (int32_t)nparams_total : 0;
+  if (M.nn != target || M.nn_np != staged) {
     M.nn = target;
+    M.nn_np = staged;
     // the step kernel reads the model from device memory; the copy is ordered after every step enqueued so far
     CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
   }

@@ -15,6 +15,7 @@ constexpr int MAXCV = PSB_MAX_CVS;
 constexpr int NACC = 16;           // fp64 accumulators per group and pass
 constexpr int VGROUP = MAXG;       // virtual group slot used by grid-wide method reductions
 constexpr int BLOCK = 256;         // threads per CTA of the step kernel
+constexpr int NN_STAGE = 1024;     // force-network parameters staged in shared memory per CTA (8 KB)
 constexpr int CT = 4;              // terms per thread the step kernel keeps in registers (slot, position, prefetched force)
 constexpr int NWARPS = BLOCK / 32;
 constexpr int HILL_STAGE_BYTES = 20480;  // per TMA stage (2 stages)
@@ -178,6 +179,8 @@ struct Model {
   int32_t jjt_const;          // ABF: J J^T does not depend on positions; jjt_inv holds its inverse
   double jjt_inv[MAXK * MAXK];  // (leading dimension 4)
   const ForceNet* nn;         // ABF family: force network or nullptr (psb_set_force_net)
+  int32_t nn_np;              // its parameter count when it fits the shared-memory staging area (NN_STAGE), else 0
+  int32_t nn_pad;
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr

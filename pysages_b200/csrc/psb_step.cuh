@@ -115,6 +115,8 @@ struct StepShared {
   unsigned long long seq;           // launches of this handle before this one (Snap::cta_seq), LL stamp source
   uint64_t mbar[2];
   double nnbuf[2][PSB_MAX_WIDTH];  // force network activations (force_net_eval)
+  ForceNet nnh;                    // force network header and (when they fit) parameters, staged after the
+  double nnw[NN_STAGE];            // dependency wait by the two warps that have no rows to reduce
 };
 
 // Block-wide sum of acc[0..nacc); result lands in out[0..nacc) (shared or global, stride ostride).
@@ -463,10 +465,9 @@ __device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int
 // scale = approxfun/core.py:99-104 and the dense / activation stack of ml/models.py:44-82.  Lane j
 // owns output unit j (+32, ...) of every layer; activations ping-pong through shared memory.
 // Returns component `lane` of the force.  Kept out of line: plain ABF never reaches it.
-static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const MethodDev& m, const double* xi,
-                                              double* buf, int lane) {
+static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const double* P, const MethodDev& m,
+                                                     const double* xi, double* buf, int lane) {
   const int nd = nn->n_dense;
-  const double* P = nn->params();
   double* cur = buf;
   double* nxt = buf + PSB_MAX_WIDTH;
   int in = nn->widths[0];
@@ -483,8 +484,8 @@ static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const M
     for (int j = lane; j < out; j += 32) {
       double acc = 0.0;
 #pragma unroll 4
-      for (int i = 0; i < in; ++i) acc = fma(cur[i], __ldg(W + (size_t)i * out + j), acc);
-      acc += __ldg(b + j);
+      for (int i = 0; i < in; ++i) acc = fma(cur[i], W[(size_t)i * out + j], acc);
+      acc += b[j];
       if (l + 1 < nd) acc = nn->activation == PSB_ACT_SIN ? sin(om * acc) : tanh(acc);
       nxt[j] = acc;
     }
@@ -495,9 +496,6 @@ static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const M
   return lane < in ? nn->std[lane] * cur[lane] + nn->mean[lane] : 0.0;
 }
 
-// abf.py:210-225 once f.JJt / f.Jp are known (warp 0, all lanes).  Every CTA derives the new
-// histogram count and force sum of bin I from the values the step began with; CTA 0 stores them
-// after the last reader is done (end of the kernel).
 // Everything of abf.py:213-258 that depends on xi alone: the bin of xi, the gathered hist[I] / Fsum[I]
 // (gathers clamp, JAX default), the new count, max(N, count) as a double and the restraint force
 // outside the grid.  Point-CV kernels run it on warp 1 while warp 0 does J p / solve.
@@ -555,9 +553,9 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   PSB_CLK(13);
   const bool oob = f.oob != 0;
   // funn.py:190,286-296: past the ABF-only stage the force comes from the network (restraints first)
-  const ForceNet* nn = M.nn;
-  const bool use_net = nn != nullptr && !(m.has_restraints && oob) && sh.pre.ncalls + 1 > __ldg(&nn->predict_after);
-  const double f_net = use_net ? force_net_eval(nn, m, f.xi, &sh.nnbuf[0][0], lane) : 0.0;
+  const bool use_net = M.nn != nullptr && !(m.has_restraints && oob) && sh.pre.ncalls + 1 > sh.nnh.predict_after;
+  const double f_net =
+      use_net ? force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0], lane) : 0.0;
   if (lane < k) {
     const int c = lane;
     const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
@@ -1070,6 +1068,16 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   }
   // everything below may depend on the previous kernel of the stream: forces, method state, workspaces
   asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- force network (psb_set_force_net): header + parameters into shared memory -----------------
+  if (is_abf && M.nn != nullptr && tid >= BLOCK - 64) {
+    static_assert(sizeof(ForceNet) % 8 == 0 && offsetof(StepShared, nnw) == offsetof(StepShared, nnh) + sizeof(ForceNet),
+                  "header and staged parameters are copied as one block");
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(M.nn);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.nnh);
+    const int words = (int)(sizeof(ForceNet) / 8) + M.nn_np;
+    for (int i = tid - (BLOCK - 64); i < words; i += 64) dst[i] = __ldcg(src + i);
+  }
 
   // ---- prologue: method-state scalars as they are when the step begins --------------------------
   // The loads are issued here but land in shared memory only after this thread has issued its
