@@ -581,7 +581,23 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        rng_frames, _, _ = (None, None, None)
+        if world > 1 and not os.environ.get("PSB_BENCH_REF_CHILD"):
+            # torchrun pins OMP_NUM_THREADS=1 for its workers, which would cripple the CPU arm: run it in a
+            # clean child process (all host cores, no rendezvous variables) and relabel the line for N GPUs
+            import subprocess
+
+            env = {k: v for k, v in os.environ.items()
+                   if k not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                                "ROLE_RANK", "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT") and not k.startswith("TORCHELASTIC")}
+            env["PSB_BENCH_REF_CHILD"] = "1"
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1",
+                                  "--steps", str(args.steps), "--warmup", str(args.warmup), "--natoms", str(natoms)],
+                                 env=env, capture_output=True, text=True, check=True).stdout
+            line = json.loads(out.strip().splitlines()[-1])
+            line["n_gpus"] = args.gpus
+            line["config"] = config
+            print(json.dumps(line))
+            return
         from pysages_b200 import synthetic
 
         snap_host = synthetic.make_snapshot(natoms, layout="hoomd", dtype=np.float32, seed=20240 + 2000)
@@ -694,12 +710,12 @@ def main():
                     traffic=traffic_from_profiles("abf2d_100k"),
                     kernel="psb::step_kernel<HOOMD,float,ABF,point> (1 cooperative launch per step, CUDA-graph replay)",
                     algorithmic_bytes_per_launch=info["algorithmic_bytes_per_step"], peak_source=peak_src,
-                    note="latency-bound at S=1e5: 8.4 MB/step is 1.3 us of HBM time inside a ~12 us dependent chain "
-                         "(gather -> grid barrier -> finalizer -> scatter), see launch.floor_us and DESIGN.md 4.1; "
+                    note="latency-bound at S=1e5: 8.4 MB/step is 1.3 us of HBM time inside a ~9 us dependent chain "
+                         "(gather -> flag-in-data exchange -> single-warp finalizer -> scatter), see launch.floor_us and DESIGN.md 4.1; "
                          "the S=N=1e6 rows of `series` are the bandwidth regime")
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # reported at N = 1 only (torchrun workers run with OMP_NUM_THREADS=1)
         snap_host = host_arrays(frames[0], L, dt)
         rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=12.0)
         cpu = dict(value=round(rate, 3), unit=UNIT, cores=cores, kind="port",
