@@ -175,7 +175,7 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
   const Model& M = h->model;
   const bool eval_cvs = (mode != MODE_WALKER_FINISH);
 
-  if (eval_cvs && h->layout.layout == PSB_LAYOUT_OPENMM_CUDA) {
+  if (eval_cvs && h->layout.layout == PSB_LAYOUT_OPENMM_CUDA && !M.slot_major) {  // slot-ordered class: no inverse needed
     const long long n = h->layout.natoms;
     const int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * h->num_sms);
     launch_inverse_permutation(reinterpret_cast<const int*>(s->ids), M.inv_perm, n, blocks, stream);
@@ -576,6 +576,11 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     const bool eligible = h->grid > 1 && !h->step_general && !method->shared_hills && ng <= 4 &&
                           layout->natoms < 0xFFFFFFF0LL;
     bool wanted = (long long)M.T > (long long)CT * BLOCK * h->grid && 2LL * M.T >= layout->natoms;
+    // OpenMM-CUDA: `ids` already IS slot -> atom, so the slot-ordered passes need no tag -> slot inverse at
+    // all (the reference's per-step ids.argsort(), openmm.py:106-107, and our inverse-permutation launch
+    // disappear); worth it as soon as a fair share of the system is selected
+    const bool omm = layout->layout == PSB_LAYOUT_OPENMM_CUDA;
+    if (omm && 4LL * M.T >= layout->natoms) wanted = true;
     if (const char* env = getenv("PSB_SLOT_MAJOR")) wanted = atoi(env) != 0;
     M.slot_major = (eligible && wanted) ? 1 : 0;
     if (M.slot_major) {
@@ -590,7 +595,16 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     }
     if (M.slot_major) {
       h->step_general = SC_SLOT;
-      psb_status st = dev_alloc(h, &M.slot_map, (size_t)layout->natoms);
+      psb_status st = PSB_OK;
+      if (omm) {
+        std::vector<uint8_t> tag_group((size_t)layout->natoms, 0);
+        for (uint32_t t = 0; t < M.T; ++t) tag_group[term_tag[t]] = (uint8_t)(term_group[t] + 1);
+        uint8_t* p = nullptr;
+        st = dev_upload(h, &p, tag_group);
+        M.tag_group = p;
+      } else {
+        st = dev_alloc(h, &M.slot_map, (size_t)layout->natoms);
+      }
       if (st != PSB_OK) return bail(st);
     }
   }

@@ -170,6 +170,7 @@ struct Model {
   StateDev st;
   Fin* fin;
   double* partials;           // ((MAXG+1) * NACC, gridDim) fp64
+  const uint8_t* tag_group;   // slot-ordered class on the OpenMM layout: tag -> group + 1 (0: not selected), (natoms)
   ulonglong2* ll;             // (MAXG * NACC, gridDim) pass-A partials as two {32 data bits, 32-bit launch stamp} words
   int32_t ll_reduce;          // pass A exchanges its partials through `ll` (no counter barrier): see reduce_rows_ll
   int32_t ll_pad;

@@ -969,6 +969,9 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   const bool skip_cv = WALK && !SLOT && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
   const bool momenta_sums = S.need_momenta && abf_fast;
   constexpr bool slot_major = SLOT;  // the host picks this instantiation only for multi-CTA, non-walker handles
+  // slot-ordered class on the OpenMM layout: ids is slot -> atom (openmm.py:100-107), so the group of a slot
+  // comes from a tag -> group byte table and neither a tag -> slot inverse nor pass 0 is needed
+  constexpr bool TAGMAP = SLOT && (LAYOUT == PSB_LAYOUT_OPENMM_CUDA);
   const bool will_scatter = (METHOD != SM_UNBIASED) &&
                             (S.mode == MODE_STEP || (WALK && S.mode == MODE_WALKER_FINISH));
 
@@ -1003,6 +1006,15 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
   const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
   uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
+  auto slot_word = [&](uint32_t sl) -> uint32_t {  // stamp | group + 1 when slot `sl` holds a selected atom
+    if constexpr (TAGMAP) {
+      const uint32_t tag = (uint32_t)__ldg(reinterpret_cast<const int*>(S.ids) + sl);
+      const uint32_t g = tag < (uint32_t)M.natoms ? (uint32_t)__ldg(M.tag_group + tag) : 0u;
+      return g ? (stamp | g) : 0u;
+    } else {
+      return __ldcg(M.slot_map + sl);
+    }
+  };
   uint32_t cslot[CT];
   int cg[CT];
   V3 cr[CT], cp[CT];
@@ -1169,7 +1181,8 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     // below HBM speed).  Instead: pass 0 scatters one word per selected atom into slot_map
     // (stamp | group), and the gather and the force update then stream positions, images,
     // velocities and forces in SLOT order, fully coalesced.  At most 4 groups (fast-class only).
-    if (slot_major) {
+    if (slot_major && TAGMAP) stamp = 16u;  // ids is slot -> atom: group of a slot = tag_group[ids[slot]], no pass 0
+    if (slot_major && !TAGMAP) {
       __syncthreads();  // sh.epoch
       stamp = ((uint32_t)(sh.epoch[BAR_SLOT] + 1ULL) & 0x0FFFFFFFu) << 4;
       const uint32_t chunk0 = (M.T + nb - 1) / nb;
@@ -1203,6 +1216,8 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       }
       PSB_STAMP(7);
       grid_sync(M, sh, BAR_SLOT);
+    }
+    if (slot_major) {
       const uint32_t N = (uint32_t)M.natoms;
       uint32_t schunk = (N + nb - 1) / nb;
       schunk = (schunk + 31u) & ~31u;  // warp-aligned slices
@@ -1222,7 +1237,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
           const uint32_t sl = min(base + u * BLOCK, s_hi - 1);  // clamped: no branch around the loads
-          e[u] = __ldcg(M.slot_map + sl);
+          e[u] = slot_word(sl);
           r[u] = A::position(S, sl);
           p[u] = momenta_sums ? A::momentum(S, sl) : v3(0, 0, 0);
         }
@@ -1555,7 +1570,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
           const uint32_t sl = min(base + u * BLOCK, s_hi - 1);
-          e[u] = __ldcg(M.slot_map + sl);
+          e[u] = slot_word(sl);
           fv[u] = A::load_force(S, sl);
         }
 #pragma unroll
