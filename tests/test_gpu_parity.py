@@ -643,3 +643,35 @@ def test_force_net_kernel_against_oracle_mlp(activation, topology):
     flat = int(np.ravel_multi_index(tuple(min(v, 7) for v in idx), (8, 8)))  # gathers clamp
     want = ours.Fsum.reshape(-1, 2)[flat].cpu().numpy() / max(2, int(ours.hist.reshape(-1)[flat]))
     np.testing.assert_allclose(ours.force.cpu().numpy(), want, rtol=1e-12)
+
+
+# ---- the two grid-wide exchanges of the point-CV class ------------------------------------------------
+@pytest.mark.parametrize("method", ["harmonic", "abf"])
+@pytest.mark.parametrize("exchange", ["flags", "counter"])
+def test_pass_a_exchange_variants(method, exchange, monkeypatch, launch_shape):
+    """HarmonicBias / ABF (and Unbiased) on point CVs exchange their per-CTA partial sums through flagged words
+    (ll_store / reduce_rows_ll, psb_step.cuh); PSB_NO_LL=1 keeps the counter barrier every other
+    configuration uses.  Both against the oracle, and bitwise against each other (same reduction order)."""
+    if launch_shape != "grid24":
+        pytest.skip("needs the multi-CTA launch shape")
+    if exchange == "counter":
+        monkeypatch.setenv("PSB_NO_LL", "1")
+    snap = snapshot("hoomd", np.float64, n=3000, seed=31)
+    cvs = [("Distance", ([list(range(0, 900)), list(range(1000, 1700))],), {}),
+           ("Component", (list(range(2000, 2600)), 2), {})]
+    spec = {"harmonic": harmonic([[3.0, 0.5], [0.5, 2.0]], [4.0, 1.0]),
+            "abf": ("ABF", dict(grid=((0.0, -12.0), (12.0, 12.0), (8, 8), "regular"), N=2))}[method]
+    run = ParityRun(snap, cvs, spec)
+    info = run.native.launch_info()
+    assert info["grid_blocks"] > 1 and info["cooperative"]
+    states = []
+    for pos in perturbed(snap, 5, 0.05):
+        ours, _ = run.step(pos)
+        states.append((ours.xi.cpu().numpy().copy(), ours.bias.cpu().numpy().copy()))
+    key = (method,)
+    seen = test_pass_a_exchange_variants.__dict__.setdefault("seen", {})
+    if key in seen:  # second variant of the same method: bit-identical to the first
+        for (xa, ba), (xb, bb) in zip(seen[key], states):
+            assert np.array_equal(xa, xb) and np.array_equal(ba, bb)
+    else:
+        seen[key] = states
