@@ -56,9 +56,15 @@ typedef enum {
   PSB_CV_ROG = 6,          /* colvars/shape.py:14-57 (value = <r.r>, reference quirk) */
   PSB_CV_RMSD = 7,         /* colvars/orientation.py:27-126  */
   PSB_CV_COORDINATION = 8, /* extension, absent from the reference */
-  PSB_CV_GYRATION = 9      /* colvars/shape.py:85-344: functions of the eigenvalues of the (uncentred)
+  PSB_CV_GYRATION = 9,     /* colvars/shape.py:85-344: functions of the eigenvalues of the (uncentred)
                               gyration tensor sum_i r_i r_i^T / n; `axis` selects the function */
+  PSB_CV_RING = 10         /* colvars/angles.py:131-281: Cremer-Pople puckering of a monocyclic ring (one group,
+                              atoms in ring order, >= 3); `axis` selects amplitude q or phase phi.  The
+                              two-component RingPuckeringCoordinates is two CVs over the same atoms */
 } psb_cv_kind;
+
+/* psb_cv_desc.axis for PSB_CV_RING */
+typedef enum { PSB_RING_AMPLITUDE = 0, PSB_RING_PHASE = 1 } psb_ring_mode;
 
 /* psb_cv_desc.axis for PSB_CV_GYRATION (eigenvalues ascending, l[0] <= l[1] <= l[2]) */
 typedef enum {

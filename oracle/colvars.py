@@ -214,6 +214,46 @@ class RadiusOfGyration(CollectiveVariable):
         return radius_of_gyration
 
 
+def ring_puckering_coordinates(rs):
+    """angles.py:158-205: Cremer-Pople amplitude q and phase phi (m = 2) of a monocyclic ring."""
+    N = rs.shape[0]
+    rc = rs - rs.mean(dim=0)  # barycenter, coordinates.py:14-28
+    theta = 2 * math.pi * torch.arange(N, dtype=torch.float64) / N
+    R1 = rc.T @ torch.sin(theta).to(rs.dtype)  # imag(exp(i theta))
+    R2 = rc.T @ torch.cos(theta).to(rs.dtype)
+    n = torch.linalg.cross(R1, R2)
+    n = n / torch.linalg.norm(n)
+    z = rc @ n
+    a = math.sqrt(2 / N) * torch.sum(z * torch.cos(2 * theta).to(rs.dtype))
+    b = -math.sqrt(2 / N) * torch.sum(z * torch.sin(2 * theta).to(rs.dtype))
+    q = torch.sqrt(a**2 + b**2)
+    phi = torch.atan2(b, a)
+    return torch.stack([q, phi])
+
+
+class RingPuckeringCoordinates(CollectiveVariable):
+    # angles.py:131-155 (@multicomponent: [q, phi])
+    multicomponent = True
+
+    @property
+    def function(self):
+        return ring_puckering_coordinates
+
+
+class RingPhaseAngle(CollectiveVariable):
+    # angles.py:208-242
+    @property
+    def function(self):
+        return lambda rs: ring_puckering_coordinates(rs)[1]
+
+
+class RingAmplitude(CollectiveVariable):
+    # angles.py:245-281
+    @property
+    def function(self):
+        return lambda rs: ring_puckering_coordinates(rs)[0]
+
+
 def gyration_tensor(positions):
     # shape.py:118-135: sum_i outer(r_i, r_i) / n  (uncentred)
     return positions.T @ positions / positions.shape[0]

@@ -248,6 +248,52 @@ class ShapeAnisotropy(_GyrationCV):
     _mode = N.GYR_ANISOTROPY
 
 
+class _RingCV(CollectiveVariable):
+    """Cremer-Pople puckering (m = 2) of a monocyclic ring (colvars/angles.py:131-281): the indices
+    are the ring atoms in ring order.  Gradient in closed form (csrc/psb_math.cuh: ring_cv)."""
+
+    _kind = N.CV_RING
+    _mode = N.RING_AMPLITUDE
+
+    def describe(self, keep):
+        if len(self.indices) < 3:
+            raise ValueError("a ring needs at least 3 atoms")
+        d = super().describe(keep)
+        d.axis = self._mode
+        return d
+
+
+class RingAmplitude(_RingCV):
+    """colvars/angles.py:245-281: puckering amplitude q (same unit as the coordinates)."""
+
+    _mode = N.RING_AMPLITUDE
+
+
+class RingPhaseAngle(_RingCV):
+    """colvars/angles.py:208-242: puckering phase phi in (-pi, pi] (not treated as periodic by
+    get_periods, like the reference: colvars/utils.py:13-19 only knows Angle / DihedralAngle)."""
+
+    _mode = N.RING_PHASE
+
+
+class RingPuckeringCoordinates(_RingCV):
+    """colvars/angles.py:131-155 (multicomponent, k = 2): [q, phi].  Lowered to two kernel-level CVs
+    over the same atoms (amplitude, phase)."""
+
+    _multicomponent = True
+
+    @property
+    def ncomponents(self):
+        return 2
+
+    def describe(self, keep):
+        out = []
+        for mode in (N.RING_AMPLITUDE, N.RING_PHASE):
+            self._mode = mode
+            out.append(super().describe(keep))
+        return out
+
+
 class RMSD(CollectiveVariable):
     """colvars/orientation.py:98-126 (Kabsch-fitted RMSD to `references`)."""
 

@@ -105,7 +105,7 @@ psb_status dev_upload(psb_handle* h, T** out, const std::vector<T>& v) {
 
 int expected_groups(int kind) {
   switch (kind) {
-    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: case PSB_CV_GYRATION: return 1;
+    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: case PSB_CV_GYRATION: case PSB_CV_RING: return 1;
     case PSB_CV_DISTANCE: case PSB_CV_DISPLACEMENT: case PSB_CV_COORDINATION: return 2;
     case PSB_CV_ANGLE: return 3;
     case PSB_CV_DIHEDRAL: return 4;
@@ -451,6 +451,11 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         if ((st = dev_upload(h, &p, w)) != PSB_OK) return bail(st);
         cv.w = p;
       }
+    }
+    if (d.kind == PSB_CV_RING) {
+      if (d.axis != PSB_RING_AMPLITUDE && d.axis != PSB_RING_PHASE)
+        return bail(fail(PSB_ERR_VALUE, "CV %d: ring puckering mode must be amplitude (0) or phase (1)", c));
+      if (n < 3) return bail(fail(PSB_ERR_VALUE, "CV %d: a ring needs at least 3 atoms (got %u)", c, n));
     }
     if (d.kind == PSB_CV_GYRATION) {
       if (d.axis < PSB_GYR_MOMENT_0 || d.axis > PSB_GYR_ANISOTROPY)

@@ -95,6 +95,45 @@ PSB_HD double wrap_period(double x, double P) {
   return x;
 }
 
+// ---- colvars/angles.py:158-205: Cremer-Pople ring puckering (m = 2) ---------------------------------
+// Coefficients of ring atom t of N: s = sin(2 pi t / N), c = cos(2 pi t / N), S = sin(4 pi t / N),
+// C = cos(4 pi t / N).  All four sum to zero over the ring (N >= 3), so the reference's centring
+// (rs - barycenter) drops out of every sum below.
+PSB_HD void ring_coefficients(uint32_t t, uint32_t N, double* s, double* c, double* S, double* C) {
+  const double x = 2.0 * (double)t / (double)N;
+#ifdef __CUDA_ARCH__
+  sincospi(x, s, c);
+  sincospi(2.0 * x, S, C);
+#else
+  *s = sin(3.141592653589793 * x); *c = cos(3.141592653589793 * x);
+  *S = sin(6.283185307179586 * x); *C = cos(6.283185307179586 * x);
+#endif
+}
+// sums[0..11] = R1 = sum s r, R2 = sum c r, A = sum C r, B = sum S r.  Returns q (mode 0) or phi (mode 1)
+// and E[0..11]: the gradient with respect to ring atom t is C_t E[0:3] + S_t E[3:6] + s_t E[6:9] + c_t E[9:12].
+// With n = R1 x R2, nh = n / |n|, kappa = sqrt(2 / N): a = kappa A.nh, b = -kappa B.nh (angles.py:196-201),
+// d(A.nh)/dr_t = C_t nh + s_t R2 x PA + c_t PA x R1 with PA = (A - nh (nh.A)) / |n| (and the same for B).
+PSB_HD double ring_cv(int mode, uint32_t N, const double* sums, double* E) {
+  const V3 R1 = v3(sums[0], sums[1], sums[2]), R2 = v3(sums[3], sums[4], sums[5]);
+  const V3 A = v3(sums[6], sums[7], sums[8]), B = v3(sums[9], sums[10], sums[11]);
+  const V3 n = cross(R1, R2);
+  const double nn = norm(n);
+  const V3 nh = (1.0 / nn) * n;
+  const double kappa = sqrt(2.0 / (double)N);
+  const double a = kappa * dot(A, nh), b = -kappa * dot(B, nh);
+  const V3 PA = (1.0 / nn) * (A - dot(nh, A) * nh), PB = (1.0 / nn) * (B - dot(nh, B) * nh);
+  const V3 Ua = cross(R2, PA), Va = cross(PA, R1), Ub = cross(R2, PB), Vb = cross(PB, R1);
+  const double q2 = a * a + b * b, q = sqrt(q2);
+  // d xi = wa d(a) + wb d(b);  d(a) = kappa [...A], d(b) = -kappa [...B]
+  const double wa = (mode == 0 ? a / q : -b / q2) * kappa, wb = -(mode == 0 ? b / q : a / q2) * kappa;
+  const V3 e1 = wa * nh, e2 = wb * nh, e3 = wa * Ua + wb * Ub, e4 = wa * Va + wb * Vb;
+  E[0] = e1.x; E[1] = e1.y; E[2] = e1.z;
+  E[3] = e2.x; E[4] = e2.y; E[5] = e2.z;
+  E[6] = e3.x; E[7] = e3.y; E[8] = e3.z;
+  E[9] = e4.x; E[10] = e4.y; E[11] = e4.z;
+  return mode == 0 ? q : atan2(b, a);
+}
+
 // ---- methods/restraints.py:68-73 -------------------------------------------------------
 PSB_HD double restraint_force(double lo, double hi, double kl, double kh, double xi) {
   if (xi < lo) return kl * (xi - lo);

@@ -183,6 +183,7 @@ __host__ __device__ __forceinline__ int nacc_for_kind(int kind, int pass, bool m
     if (is_point_kind(kind)) return momenta_sums ? 6 : 3;
     if (kind == PSB_CV_ROG) return 1;
     if (kind == PSB_CV_GYRATION) return 6;
+    if (kind == PSB_CV_RING) return 12;
     if (kind == PSB_CV_RMSD) return 15;
     return 0;
   }
@@ -389,6 +390,9 @@ static __device__ __forceinline__ void finalize_cv_A(const Model& M, StepShared&
       double* x = f.cvx[c];
       f.xi[cv.comp0] = gyration_cv(cv.axis, cv.nn, cv.mm, gt, x);
       for (int a = 0; a < 9; ++a) x[a] *= 2.0 * inv_n;  // d xi / d r_i = x r_i
+    } break;
+    case PSB_CV_RING: {  // angles.py:131-281
+      f.xi[cv.comp0] = ring_cv(cv.axis, cv.t1 - cv.t0, sh.tot[g0], f.cvx[c]);
     } break;
     default: break;
   }
@@ -804,6 +808,13 @@ static __device__ __noinline__ void accumulate_nonpoint(const CvDev& cv, double 
   } else if (cv.kind == PSB_CV_GYRATION) {  // shape.py:118-135: sum_i r_i r_i^T (uncentred, like the reference)
     acc[0] += r.x * r.x; acc[1] += r.x * r.y; acc[2] += r.x * r.z;
     acc[3] += r.y * r.y; acc[4] += r.y * r.z; acc[5] += r.z * r.z;
+  } else if (cv.kind == PSB_CV_RING) {  // angles.py:186-199: the four Fourier sums over the ring
+    double s, c, S, C;
+    ring_coefficients(t - cv.t0, cv.t1 - cv.t0, &s, &c, &S, &C);
+    acc[0] += s * r.x; acc[1] += s * r.y; acc[2] += s * r.z;
+    acc[3] += c * r.x; acc[4] += c * r.y; acc[5] += c * r.z;
+    acc[6] += C * r.x; acc[7] += C * r.y; acc[8] += C * r.z;
+    acc[9] += S * r.x; acc[10] += S * r.y; acc[11] += S * r.z;
   } else if (cv.kind == PSB_CV_RMSD) {  // weighted centroid, plain sum, raw covariance sum_i r_i (x) Q_i
     const double w = cv.w ? __ldg(cv.w + (t - cv.t0)) : inv_n;
     const double* q = cv.ref + 3 * (size_t)(t - cv.t0);
@@ -849,6 +860,13 @@ static __device__ __noinline__ V3 nonpoint_gradient(const Fin& f, const CvDev& c
     const double* x = f.cvx[c];
     return v3(x[0] * r.x + x[1] * r.y + x[2] * r.z, x[3] * r.x + x[4] * r.y + x[5] * r.z,
               x[6] * r.x + x[7] * r.y + x[8] * r.z);
+  }
+  if (cv.kind == PSB_CV_RING) {
+    const double* E = f.cvx[c];
+    double s, cc, S, C;
+    ring_coefficients(t - cv.t0, cv.t1 - cv.t0, &s, &cc, &S, &C);
+    return v3(C * E[0] + S * E[3] + s * E[6] + cc * E[9], C * E[1] + S * E[4] + s * E[7] + cc * E[10],
+              C * E[2] + S * E[5] + s * E[8] + cc * E[11]);
   }
   if (cv.kind == PSB_CV_RMSD) {
     const double* x = f.cvx[c];
@@ -1230,7 +1248,10 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         for (int a = 0; a < 6; ++a) acc4[g][a] = 0.0;
       // SU independent rows per thread in flight: every load is issued before the first use (rows of
       // unselected slots are loaded too -- they exist, and almost every slot is selected here)
-      constexpr int SU = 4;
+#ifndef PSB_SLOT_SUA
+#define PSB_SLOT_SUA 8
+#endif
+      constexpr int SU = is_abf ? 4 : PSB_SLOT_SUA;  // momenta double the registers per row in flight
       for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
         uint32_t e[SU];
         V3 r[SU], p[SU];
@@ -1563,7 +1584,10 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     const Fin& f = sh.fin;
     const bool dense = GENERAL && (M.bias_dense != nullptr);
     if (slot_major) {
-      constexpr int SU = 4;
+#ifndef PSB_SLOT_SUS
+#define PSB_SLOT_SUS 8
+#endif
+      constexpr int SU = PSB_SLOT_SUS;
       for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
         uint32_t e[SU];
         FV fv[SU];

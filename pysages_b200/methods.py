@@ -128,7 +128,11 @@ class NativeStep:
         self.device = (torch.device("cuda", torch.cuda.current_device()) if self.host_buffers
                        else snapshot.positions.device)
         keep = []
-        cvs = (N.CvDesc * len(method.cvs))(*[cv.describe(keep) for cv in method.cvs])
+        descs = []
+        for cv in method.cvs:  # a multicomponent ring CV lowers to two kernel-level CVs
+            d = cv.describe(keep)
+            descs.extend(d if isinstance(d, list) else [d])
+        cvs = (N.CvDesc * len(descs))(*descs)
         mdesc = method.describe(helpers)
         ldesc = _snap.describe_layout(
             snapshot,
@@ -142,7 +146,7 @@ class NativeStep:
         self.dense_outputs = bool(dense_outputs)
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            N.check(self.lib.psb_create(cvs, len(method.cvs), ctypes.byref(mdesc), ctypes.byref(ldesc),
+            N.check(self.lib.psb_create(cvs, len(descs), ctypes.byref(mdesc), ctypes.byref(ldesc),
                                         ctypes.byref(handle)))
         self.handle = handle
         self._snapdesc = N.SnapshotDesc()

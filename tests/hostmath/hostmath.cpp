@@ -31,6 +31,28 @@ double hm_dihedral(const double* p, double* g) {
 }
 
 double hm_gyration(int mode, int ja, int jb, const double* g6, double* W9) { return gyration_cv(mode, ja, jb, g6, W9); }
+// Cremer-Pople ring puckering exactly as the step kernel evaluates it: Fourier sums over the ring
+// (accumulate_nonpoint), ring_cv, then the per-atom gradient (nonpoint_gradient)
+double hm_ring(int mode, int n, const double* pos, double* grad) {
+  double sums[12] = {0}, E[12];
+  for (int t = 0; t < n; ++t) {
+    double s, c, S, C;
+    ring_coefficients((uint32_t)t, (uint32_t)n, &s, &c, &S, &C);
+    for (int a = 0; a < 3; ++a) {
+      sums[a] += s * pos[3 * t + a];
+      sums[3 + a] += c * pos[3 * t + a];
+      sums[6 + a] += C * pos[3 * t + a];
+      sums[9 + a] += S * pos[3 * t + a];
+    }
+  }
+  const double v = ring_cv(mode, (uint32_t)n, sums, E);
+  for (int t = 0; t < n; ++t) {
+    double s, c, S, C;
+    ring_coefficients((uint32_t)t, (uint32_t)n, &s, &c, &S, &C);
+    for (int a = 0; a < 3; ++a) grad[3 * t + a] = C * E[a] + S * E[3 + a] + s * E[6 + a] + c * E[9 + a];
+  }
+  return v;
+}
 void hm_kabsch(const double* C, double* U) { kabsch_rotation(C, U); }
 void hm_kabsch_eig(const double* C, double* U) { kabsch_rotation_eig(C, U); }
 

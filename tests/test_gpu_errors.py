@@ -73,3 +73,23 @@ def test_force_net_errors():
     native.set_force_net([1, 4, 1], np.zeros(13), [0.0], [1.0], predict_after=0)  # and a valid one is accepted
     with pytest.raises(ValueError, match="expected 13 network parameters"):
         ps.methods.FUNN([ps.colvars.Distance([1, 2])], grid, (4,), initial_params=np.zeros(12))
+
+
+def test_ring_cv_errors():
+    snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
+    with pytest.raises(ValueError, match="at least 3 atoms"):
+        build(ps.methods.Unbiased([ps.colvars.RingAmplitude([1, 2])]), snap)
+    d = N.CvDesc()
+    keep = []
+    good = ps.colvars.RingPhaseAngle([1, 2, 3, 4, 5]).describe(keep)
+    good.axis = 7
+    handle = ctypes.c_void_p()
+    _, _, update = build(ps.methods.Unbiased([ps.colvars.RingPhaseAngle([1, 2, 3, 4, 5])]), snap)
+    native = update.native
+    mdesc = ps.methods.Unbiased([ps.colvars.RingPhaseAngle([1, 2, 3, 4, 5])]).describe(device_helpers("hoomd"))
+    from pysages_b200.backends import snapshot as S
+    ldesc = S.describe_layout(device_snapshot(snap), device_helpers("hoomd").layout, unwrap=True, need_momenta=False,
+                              dense_outputs=False)
+    cvs = (N.CvDesc * 1)(good)
+    st = native.lib.psb_create(cvs, 1, ctypes.byref(mdesc), ctypes.byref(ldesc), ctypes.byref(handle))
+    assert st == N.ERR_VALUE and b"amplitude (0) or phase (1)" in native.lib.psb_last_error()

@@ -675,3 +675,42 @@ def test_pass_a_exchange_variants(method, exchange, monkeypatch, launch_shape):
             assert np.array_equal(xa, xb) and np.array_equal(ba, bb)
     else:
         seen[key] = states
+
+
+# ---- Cremer-Pople ring puckering (colvars/angles.py:131-281) ------------------------------------------
+RING6, RING5, RING7 = [40, 7, 313, 99, 150, 508], [3, 77, 140, 201, 333], [10, 20, 30, 45, 50, 60, 75]
+
+
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float64), ("hoomd", np.float32), ("lammps", np.float64),
+                                           ("openmm-cuda", np.float64)])
+@pytest.mark.parametrize("cv", ["RingAmplitude", "RingPhaseAngle", "RingPuckeringCoordinates"])
+def test_ring_puckering_bias(layout, dtype, cv):
+    snap = snapshot(layout, dtype)
+    if cv == "RingPuckeringCoordinates":  # HarmonicBias takes one centre per CV (bias.py:62-65): use metadynamics
+        method = ("Metadynamics", dict(height=0.7, sigma=[0.4, 0.3], stride=2, ngaussians=6))
+    else:
+        method = harmonic(3.0, [0.5])
+    run = ParityRun(snap, [(cv, (RING6,), {})], method)
+    for pos in perturbed(snap, 3, 0.1):
+        run.step(pos)
+
+
+def test_ring_puckering_with_other_cvs_metadynamics():
+    """Phase of a 5-ring + amplitude of a 7-ring + a Distance sharing atoms with the 5-ring, direct-sum
+    metadynamics: general class, unique-atom scatter."""
+    snap = snapshot("hoomd", np.float64)
+    specs = [("RingPhaseAngle", (RING5,), {}), ("RingAmplitude", (RING7,), {}), ("Distance", ([[3, 77], B],), {})]
+    kw = dict(height=0.8, sigma=[0.3, 0.2, 0.5], stride=2, ngaussians=8)
+    run = ParityRun(snap, specs, ("Metadynamics", kw))
+    for pos in perturbed(snap, 6, 0.05):
+        run.step(pos)
+    assert int(run.state.idx) == 2  # calls 3 and 5 deposit (metad.py:192-193)
+
+
+def test_ring_amplitude_abf_position_dependent_jacobian():
+    snap = snapshot("hoomd", np.float64)
+    specs = [("RingAmplitude", (RING6,), {}), ("Component", ([A], 0), {})]
+    kw = dict(grid=((0.0, -6.0), (12.0, 6.0), (6, 6), "regular"), N=1)
+    run = ParityRun(snap, specs, ("ABF", kw))
+    for pos in perturbed(snap, 4, 0.05):
+        run.step(pos)

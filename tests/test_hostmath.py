@@ -32,6 +32,8 @@ def hm():
     lib.hm_gyration.restype = ctypes.c_double
     lib.hm_gyration.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
     lib.hm_kabsch_eig.argtypes = [dp, dp]
+    lib.hm_ring.restype = ctypes.c_double
+    lib.hm_ring.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp]
     lib.hm_grid_index.restype = ctypes.c_uint
     lib.hm_grid_index.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
     lib.hm_mesh_coord.restype = ctypes.c_double
@@ -232,3 +234,27 @@ def test_small_solvers(hm):
     assert hm.hm_spd_solve(1, _ptr(A4), _ptr(np.ones(1)), _ptr(np.zeros(4))) == 0
     A4 = np.zeros((4, 4)); A4[:2, :2] = [[1.0, 2.0], [2.0, 1.0]]  # indefinite
     assert hm.hm_spd_solve(2, _ptr(A4), _ptr(np.ones(2)), _ptr(np.zeros(4))) == 0
+
+
+@pytest.mark.parametrize("n", [5, 6, 7, 9])
+def test_ring_puckering_matches_autodiff(hm, n):
+    """Cremer-Pople q / phi (angles.py:158-205) and their closed-form gradients against the oracle's
+    autodiff of the reference formula, for rings far from the origin too (the centring drops out)."""
+    from oracle import colvars as oc
+
+    rng = np.random.default_rng(n)
+    for shift in (0.0, 150.0):
+        ang = 2 * np.pi * np.arange(n) / n
+        ring = np.stack([np.cos(ang), np.sin(ang), 0.35 * rng.normal(size=n)], axis=1) * 1.4
+        ring += 0.1 * rng.normal(size=(n, 3)) + shift
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        pos = np.ascontiguousarray(ring @ Q.T)
+        r = torch.tensor(pos, dtype=torch.float64, requires_grad=True)
+        ref = oc.ring_puckering_coordinates(r)
+        for mode in (0, 1):
+            grad = np.zeros((n, 3))
+            val = hm.hm_ring(mode, n, _ptr(pos), _ptr(grad))
+            (gref,) = torch.autograd.grad(ref[mode], r, retain_graph=True)
+            assert abs(val - ref[mode].item()) <= 1e-11 * max(1.0, abs(ref[mode].item())), (n, mode, shift)
+            scale = np.abs(gref.numpy()).max()
+            assert np.allclose(grad, gref.numpy(), rtol=1e-8, atol=1e-10 * scale), (n, mode, shift)
