@@ -118,13 +118,64 @@ def _run_umbrella(method_or_result, context_generator, timesteps, context_args, 
                   [r.snapshots for r in results])
 
 
+def _metapotential(state, periods):
+    """metad.py:318-323 sum_of_gaussians, batched over the query points, on the device the hills live on."""
+    import numpy as np
+    import torch
+
+    as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v))
+    heights, centers, sigmas = as_t(state.heights), as_t(state.centers), as_t(state.sigmas).reshape(-1)
+    nh = min(int(state.idx), heights.shape[0])  # slots beyond idx hold zero heights anyway
+    heights, centers = heights[:nh].to(torch.float64), centers[:nh].to(torch.float64)
+    P = torch.as_tensor(np.asarray(periods, dtype=np.float64), device=heights.device)
+
+    def metapotential(x):
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64), device=heights.device).reshape(-1, centers.shape[1])
+        out = torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
+        for lo in range(0, x.shape[0], 4096):  # (points, hills, k) blocks
+            d = x[lo:lo + 4096, None, :] - centers[None, :, :]
+            finite = torch.isfinite(P)
+            Pf = torch.where(finite, P, torch.zeros_like(P))
+            d = torch.where(finite & (d.abs() > Pf / 2), d - torch.sign(d) * Pf, d)  # colvars/utils.py:22-26
+            out[lo:lo + 4096] = (heights[None, :] * torch.exp(-((d / sigmas) ** 2).sum(-1) / 2)).sum(-1)
+        return out.cpu().numpy()
+
+    return metapotential
+
+
 def analyze(result):
-    """umbrella_integration.py:220-261 (host-side, trivial) -- other methods' analysis is out of scope."""
+    """Post-run analysis.  UmbrellaIntegration: umbrella_integration.py:220-261.  Metadynamics:
+    metad.py:326-383 (heights + the deposited bias potential as a callable).  ABF / FUNN: the binned
+    estimates (histogram, mean force, mesh) of abf.py / funn.py `analyze`; their free-energy
+    integration through a fitted network is out of scope."""
     import numpy as np
 
+    from . import methods as _m
+    from .colvars import get_periods
+    from .grids import compute_mesh
+    from .serialization import numpyfy
+
     method = result.method
+    if isinstance(method, _m.Metadynamics):
+        P = get_periods(method.cvs)
+        states = list(result.states)
+        heights = [numpyfy(s).heights for s in states]
+        pots = [_metapotential(s, P) for s in states]
+        if len(states) == 1:
+            return dict(heights=heights[0], metapotential=pots[0])
+        return dict(heights=heights, metapotential=pots)
+    if isinstance(method, (_m.ABF, _m.FUNN)):
+        out = dict(histogram=[], mean_force=[], mesh=compute_mesh(method.grid))
+        for s in result.states:
+            h = numpyfy(s)
+            hist = np.asarray(h.hist, dtype=np.float64)
+            out["histogram"].append(np.asarray(h.hist))
+            out["mean_force"].append(np.asarray(h.Fsum) / np.maximum(hist[..., None], 1))
+        if len(result.states) == 1:
+            out["histogram"], out["mean_force"] = out["histogram"][0], out["mean_force"][0]
+        return out
     if not isinstance(method, UmbrellaIntegration):
-        raise NotImplementedError("analyze() is implemented for UmbrellaIntegration only (DESIGN.md scope)")
+        raise NotImplementedError(f"analyze() is not implemented for {type(method).__name__} (DESIGN.md scope)")
     ksprings = [s.kspring for s in method.submethods]
     centers = [s.center for s in method.submethods]
     hist_means = [cb.get_means() for cb in result.callbacks]

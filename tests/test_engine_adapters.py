@@ -152,3 +152,48 @@ def test_funn_run_save_load_restart(tmp_path):
         np.testing.assert_array_equal(getattr(a.nn, name).cpu().numpy(), getattr(b.nn, name).cpu().numpy(), err_msg=name)
     assert int(a.ncalls) == int(b.ncalls) == 10
     assert not np.array_equal(b.nn.params.cpu().numpy(), make_method().model.parameters)  # it was refitted
+
+
+def _mock(snap, traj, first=0):
+    return mock.MockEngine("hoomd", snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda",
+                           trajectory=traj[first:])
+
+
+def test_analyze_metadynamics_metapotential():
+    """metad.py:326-383: the deposited bias potential as a callable, against the oracle's sum_of_gaussians."""
+    from oracle import methods as om
+
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=9, step=0.05)
+    cvs = [ps.colvars.Distance([G1, G2]), ps.colvars.DihedralAngle([1, 50, 120, 200])]
+    res = ps.run(ps.methods.Metadynamics(cvs, 1.2, [0.4, 0.3], 2, 16), lambda **kw: _mock(snap, traj), 9)
+    out = ps.analyze(res)
+    st = ps.serialization.numpyfy(res.states[0])
+    assert int(st.idx) == 4 and np.array_equal(out["heights"], st.heights)
+    rng = np.random.default_rng(0)
+    x = np.stack([rng.uniform(5, 9, 7), rng.uniform(-np.pi, np.pi, 7)], axis=1)
+    want = [float(om.sum_of_gaussians(torch.as_tensor(xi).reshape(1, 2), torch.as_tensor(st.heights),
+                                      torch.as_tensor(st.centers), torch.as_tensor(st.sigmas).reshape(1, 2),
+                                      torch.tensor([np.inf, 2 * np.pi], dtype=torch.float64))) for xi in x]
+    np.testing.assert_allclose(out["metapotential"](x), want, rtol=1e-12)
+    assert np.all(out["metapotential"](st.centers[:4]) > 0)
+
+
+def test_analyze_abf_and_umbrella_integration():
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=6, step=0.05)
+    res = ps.run(method(), lambda **kw: _mock(snap, traj), 6)  # ABF (abf.py analyze: binned estimates)
+    out = ps.analyze(res)
+    st = ps.serialization.numpyfy(res.states[0])
+    assert out["histogram"].sum() == st.hist.sum() and out["mesh"].shape == (256, 2)
+    np.testing.assert_array_equal(out["mean_force"], st.Fsum / np.maximum(st.hist[..., None].astype(np.float64), 1))
+    # umbrella_integration.py:220-261: mean force per window and its running integral
+    cv = [ps.colvars.Distance([G1, G2])]
+    centers = [6.0, 6.5, 7.0]
+    ui = ps.methods.UmbrellaIntegration(cv, 50.0, centers, 1)
+    res = ps.run(ui, lambda **kw: _mock(snap, traj), 6)
+    out = ps.analyze(res)
+    means = np.array([cb.get_means() for cb in res.callbacks]).reshape(3)
+    mf = -50.0 * (means - np.array(centers))
+    np.testing.assert_allclose(out["mean_forces"].reshape(3), mf, rtol=1e-12)
+    np.testing.assert_allclose(out["free_energy"].reshape(3), [0.0, mf[0] * 0.5, mf[0] * 0.5 + mf[1] * 0.5], rtol=1e-12)
