@@ -12,7 +12,8 @@ cvs, m = bench.workload_specs("abf2d", n, L)
 method, native = bench.build_ours(cvs, m, snaps[0])
 descs = bench.snapdesc_array(native, snaps)
 f0 = [f["forces"].clone() for f in frames]
-steps = 50_000 - 50_000 % 64
+steps = int(os.environ.get("PSB_LONG_STEPS", 50_000))
+steps -= steps % 64
 N.check(native.lib.psb_run_cycle(native.handle, descs, 64, steps, ctypes.c_void_p(stream.cuda_stream)))
 stream.synchronize()
 hist = native.view("hist").cpu().numpy(); Fsum = native.view("Fsum").cpu().numpy()
