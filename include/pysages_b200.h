@@ -277,6 +277,28 @@ typedef struct {
 } psb_force_net;
 psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda_stream);
 
+/* SpectralABF (methods/spectral_abf.py:181-268): ABF accumulation every step; once `ncalls > predict_after`
+ * (fit_threshold) the force is the gradient of a series fitted to the binned mean force
+ * (approxfun/core.py:311-336 build_grad_evaluator), with x = scale(xi) in [-1, 1]^n (core.py:99-104):
+ *   Fourier  (periodic grid):  F_d = scale * sum_k (2 pi / size_d) n_kd [cos(pi n_k.x) c_{K+k} - sin(pi n_k.x) c_k]
+ *   monomial (Chebyshev grid): F_d = scale * sum_k (2 / size_d) n_kd x_d^(n_kd - 1) prod_{e != d} x_e^(n_ke) c_k
+ * `exponents` are the K integer tuples of collect_exponents (core.py:73-96); `values` = [scale, c_0 ...]
+ * (2K coefficients for Fourier: the block multiplying the imaginary parts first, core.py:321-324; K for
+ * monomials) and may live in device memory, so a refit never synchronises with the host.  Outside the
+ * grid the restraint force applies, or -- `oob_zero` -- no force at all (spectral_abf.py:250-266).
+ * Replaces a force network set earlier, and vice versa.  1-D and 2-D grids only, like the reference. */
+typedef enum { PSB_SERIES_FOURIER = 1, PSB_SERIES_MONOMIAL = 2 } psb_series_kind;
+typedef struct {
+  int32_t kind;             /* psb_series_kind; 0 removes the series (plain ABF again) */
+  int32_t n_terms;          /* K */
+  int32_t oob_zero;
+  int32_t values_on_device;
+  int64_t predict_after;
+  const int32_t* exponents; /* (K, ndim) row-major, host memory */
+  const double* values;     /* 1 + 2K (Fourier) or 1 + K (monomial) doubles */
+} psb_force_series;
+psb_status psb_set_force_series(psb_handle* h, const psb_force_series* series, void* cuda_stream);
+
 int64_t psb_launch_count(psb_handle* h);
 /* 1 when the last psb_run_cycle replayed a CUDA graph, 0 when it issued plain launches. */
 int32_t psb_cycle_uses_graph(psb_handle* h);

@@ -522,3 +522,97 @@ class FUNN(ABF):
             return FUNNState(xi, bias, hist, Fsum, F, Wp, state.Wp, nn, ncalls)
 
         return snapshot, initialize, generalize(update, helpers)
+
+
+# --------------------------------------------------------------------------- #
+# SpectralABF (spectral_abf.py:95-260)
+# --------------------------------------------------------------------------- #
+
+
+class SpectralABFState(NamedTuple):  # spectral_abf.py:36-84
+    xi: Any
+    bias: Any
+    hist: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    fun: Any
+    ncalls: int = 0
+
+
+class SpectralABF(ABF):
+    """spectral_abf.py:95-260: ABF accumulation; past `fit_threshold` calls the force is the gradient of
+    a Fourier (periodic grid) or monomial (grid converted to Chebyshev) series refitted every `fit_freq`
+    calls by one pseudo-inverse product.  Outside the grid: restraints, or ZERO force without them."""
+
+    def __init__(self, cvs, grid, **kwargs):
+        super().__init__(cvs, grid, **kwargs)
+        from . import approxfun
+
+        self.fit_freq = kwargs.get("fit_freq", 100)
+        self.fit_threshold = kwargs.get("fit_threshold", 500)
+        if not self.grid.is_periodic:  # spectral_abf.py:140: convert(grid, Grid[Chebyshev])
+            self.grid = grids.Grid(self.grid.lower, self.grid.upper, self.grid.shape, kind=grids.Chebyshev)
+        self.exponents = approxfun.collect_exponents(self.grid)
+        self.pinv = approxfun.gradient_pinv(self.grid, self.exponents)
+
+    def build(self, snapshot, helpers):
+        from . import approxfun
+
+        cv, grid = self.cv, self.grid
+        dt = snapshot.dt
+        dims = grid.shape.size
+        gshape = tuple(int(s) for s in grid.shape)
+        natoms = _natoms(snapshot)
+        tsolve = linear_solver(self.use_pinv)
+        get_grid_index = grids.build_indexer(grid)
+        N = int(self.N)
+        restraints = self.restraints
+        fit_freq, fit_threshold = self.fit_freq, self.fit_threshold
+        query, dimensionality, to_force_units = helpers
+
+        def fit(dy):
+            return approxfun.fit_gradient(grid, self.pinv, dy)
+
+        def estimate_force(xi, I_xi, Fsum, hist, fun, pred):  # spectral_abf.py:236-268
+            ob = any(int(i) == s for i, s in zip(I_xi, gshape))
+            if ob:
+                if restraints is None:
+                    return torch.zeros(dims, dtype=F64)
+                lo, hi, kl, kh = restraints
+                return apply_restraints(lo, hi, kl, kh, xi.reshape(dims).to(F64))
+            if pred:
+                g = approxfun.get_gradient(grid, self.exponents, fun, xi.detach().numpy().astype(np.float64))
+                return torch.as_tensor(g.reshape(dims))
+            return _gather(Fsum, I_xi) / max(int(_gather(hist, I_xi)), N)
+
+        def initialize():  # spectral_abf.py:169-179
+            xi, _ = cv(query(snapshot))
+            bias = torch.zeros((natoms, dimensionality()), dtype=F64)
+            hist = torch.zeros(gshape, dtype=torch.int64)
+            Fsum = torch.zeros((*gshape, dims), dtype=F64)
+            z = torch.zeros(dims, dtype=F64)
+            return SpectralABFState(xi, bias, hist, Fsum, z, z.clone(), z.clone(), fit(Fsum.numpy()))
+
+        def update(state, data):  # spectral_abf.py:181-205
+            ncalls = state.ncalls + 1
+            in_fitting_regime = ncalls > fit_threshold
+            in_fitting_step = in_fitting_regime and (ncalls % fit_freq == 1)
+            fun = state.fun
+            if in_fitting_step:  # spectral_abf.py:216-219
+                hist = state.hist.numpy().astype(np.float64).reshape(*gshape, 1)
+                fun = fit(state.Fsum.numpy() / np.maximum(hist, 1))
+            xi, Jxi = cv(data)
+            p = torch.as_tensor(data.momenta)
+            Jd = Jxi.to(F64) if (Jxi.dtype == F64 or p.dtype == F64) else Jxi
+            Wp = tsolve(Jd, p.to(Jd.dtype)).to(F64)
+            dWp_dt = (1.5 * Wp - 2.0 * state.Wp + 0.5 * state.Wp_) / dt
+            I_xi = get_grid_index(xi.detach().numpy())
+            hist = _scatter_add(state.hist, I_xi, 1)
+            Fsum = _scatter_add(state.Fsum, I_xi, to_force_units(dWp_dt) + state.force)
+            force = estimate_force(xi, I_xi, Fsum, hist, fun, in_fitting_regime).reshape(dims)
+            bias = (-Jxi.T.to(F64) @ force).reshape(state.bias.shape)
+            return SpectralABFState(xi, bias, hist, Fsum, force, Wp, state.Wp, fun, ncalls)
+
+        return snapshot, initialize, generalize(update, helpers)

@@ -94,6 +94,21 @@ class ForceNetDesc(Structure):  # psb_force_net
     ]
 
 
+SERIES_FOURIER, SERIES_MONOMIAL = 1, 2
+
+
+class ForceSeriesDesc(Structure):  # psb_force_series
+    _fields_ = [
+        ("kind", c_int32),
+        ("n_terms", c_int32),
+        ("oob_zero", c_int32),
+        ("values_on_device", c_int32),
+        ("predict_after", c_int64),
+        ("exponents", c_void_p),
+        ("values", c_void_p),
+    ]
+
+
 class LayoutDesc(Structure):
     _fields_ = [
         ("layout", c_int32),
@@ -140,6 +155,7 @@ EXPORTS = {
     "psb_grid_index": (c_int32, [POINTER(GridDesc), POINTER(c_double), c_int64, POINTER(c_uint32)]),
     "psb_set_option": (c_int32, [c_void_p, c_char_p, c_int64]),
     "psb_set_force_net": (c_int32, [c_void_p, POINTER(ForceNetDesc), c_void_p]),
+    "psb_set_force_series": (c_int32, [c_void_p, POINTER(ForceSeriesDesc), c_void_p]),
     "psb_launch_count": (c_int64, [c_void_p]),
     "psb_cycle_uses_graph": (c_int32, [c_void_p]),
     "psb_launch_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),

@@ -52,6 +52,8 @@ struct psb_handle {
   Model* d_model = nullptr;  // device copy read by the step kernel (uploaded at the end of psb_create)
   char* d_nn = nullptr;      // ForceNet header + parameters (psb_set_force_net)
   size_t nn_capacity = 0;
+  unsigned long long* d_fs = nullptr;  // ForceSeries block (psb_set_force_series)
+  size_t fs_capacity = 0;
   unsigned long long* d_cta_seq = nullptr;  // per-CTA launch counters (LL exchange)
   psb_layout_desc layout;
   psb_method_desc method;
@@ -1075,10 +1077,74 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
     target = reinterpret_cast<const ForceNet*>(h->d_nn);
   }
   const int32_t staged = (target && nparams_total <= (size_t)NN_STAGE) ? (int32_t)nparams_total : 0;
-  if (M.nn != target || M.nn_np != staged) {
+  if (M.nn != target || M.nn_np != staged || (target && M.fs)) {
     M.nn = target;
     M.nn_np = staged;
+    if (target) {  // a handle carries a network or a series
+      M.fs = nullptr;
+      M.fs_staged = 0;
+    }
     // the step kernel reads the model from device memory; the copy is ordered after every step enqueued so far
+    CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
+  }
+  return PSB_OK;
+}
+
+// spectral_abf.py:181-268: the fitted series whose gradient replaces the binned average (psb_force_series).
+psb_status psb_set_force_series(psb_handle* h, const psb_force_series* ser, void* cuda_stream) {
+  if (!h || !ser) return fail(PSB_ERR_VALUE, "NULL argument");
+  Model& M = h->model;
+  if (M.m.kind != PSB_METHOD_ABF)
+    return fail(PSB_ERR_VALUE, "a force series needs an ABF-family method (spectral_abf.py:181-205)");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const ForceSeries* target = nullptr;
+  int32_t staged = 0;
+  if (ser->kind != 0) {
+    if (ser->kind != PSB_SERIES_FOURIER && ser->kind != PSB_SERIES_MONOMIAL)
+      return fail(PSB_ERR_VALUE, "force series: unknown kind %d", ser->kind);
+    if (M.m.grid_ndim < 1 || M.m.grid_ndim > 2)
+      return fail(PSB_ERR_VALUE, "Only 1D and 2D grids are supported");  // approxfun/core.py:74-75
+    if (ser->n_terms < 1 || !ser->exponents || !ser->values)
+      return fail(PSB_ERR_VALUE, "force series: exponents and values are required");
+    const int dims = M.m.grid_ndim, K = ser->n_terms;
+    for (int i = 0; i < K * dims; ++i)
+      if (ser->exponents[i] < -63 || ser->exponents[i] > 63 || (ser->kind == PSB_SERIES_MONOMIAL && ser->exponents[i] < 0))
+        return fail(PSB_ERR_VALUE, "force series: exponent %d out of range", ser->exponents[i]);
+    const size_t exp_words = ((size_t)K * dims + 1) / 2;
+    const size_t nval = 1 + (size_t)K * (ser->kind == PSB_SERIES_FOURIER ? 2 : 1);
+    const size_t head_words = sizeof(ForceSeries) / 8 + exp_words;
+    const size_t words = head_words + nval;
+    std::vector<unsigned long long> block(head_words, 0ULL);
+    ForceSeries* hs = reinterpret_cast<ForceSeries*>(block.data());
+    hs->kind = ser->kind;
+    hs->K = K;
+    hs->dims = dims;
+    hs->oob_zero = ser->oob_zero ? 1 : 0;
+    hs->predict_after = ser->predict_after;
+    hs->val_off = (int32_t)head_words;
+    hs->words = (int32_t)words;
+    memcpy(block.data() + sizeof(ForceSeries) / 8, ser->exponents, sizeof(int32_t) * (size_t)K * dims);
+    if (words * 8 > h->fs_capacity) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      unsigned long long* p = nullptr;
+      psb_status st = dev_alloc(h, &p, words, false);  // the old block stays alive until psb_destroy
+      if (st != PSB_OK) return st;
+      h->d_fs = p;
+      h->fs_capacity = words * 8;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_fs, block.data(), head_words * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_fs + head_words, ser->values, nval * 8,
+                             ser->values_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    target = reinterpret_cast<const ForceSeries*>(h->d_fs);
+    staged = words <= sizeof(ForceNet) / 8 + (size_t)NN_STAGE ? (int32_t)words : 0;
+  }
+  if (M.fs != target || M.fs_staged != staged || (target && M.nn)) {
+    M.fs = target;
+    M.fs_staged = staged;
+    if (target) {  // a handle carries a network or a series
+      M.nn = nullptr;
+      M.nn_np = 0;
+    }
     CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
   }
   return PSB_OK;

@@ -84,6 +84,17 @@ struct ForceNet {
   __host__ __device__ const double* params() const { return reinterpret_cast<const double*>(this + 1); }
 };
 
+// Force series of SpectralABF (psb_force_series): header, then the exponents (int32, padded to an even
+// count), then [scale, coefficients...] as doubles, all in one allocation.
+struct ForceSeries {
+  int32_t kind, K, dims, oob_zero;
+  long long predict_after;
+  int32_t val_off;  // offset of the values, in 8-byte words from the start of the block
+  int32_t words;    // size of the whole block in 8-byte words
+  __host__ __device__ const int32_t* exponents() const { return reinterpret_cast<const int32_t*>(this + 1); }
+  __host__ __device__ const double* values() const { return reinterpret_cast<const double*>(this) + val_off; }
+};
+
 struct StateDev {
   double* xi;        // (k)
   double* F;         // (k) generalized force dV/dxi
@@ -181,7 +192,8 @@ struct Model {
   double jjt_inv[MAXK * MAXK];  // (leading dimension 4)
   const ForceNet* nn;         // ABF family: force network or nullptr (psb_set_force_net)
   int32_t nn_np;              // its parameter count when it fits the shared-memory staging area (NN_STAGE), else 0
-  int32_t nn_pad;
+  int32_t fs_staged;          // the force series block fits the staging area
+  const ForceSeries* fs;      // SpectralABF: force series or nullptr (psb_set_force_series)
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr

@@ -500,6 +500,41 @@ static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const d
   return lane < in ? nn->std[lane] * cur[lane] + nn->mean[lane] : 0.0;
 }
 
+// spectral_abf.py:245-246 interpolate_force, one warp: gradient of the fitted Fourier / monomial series at
+// xi (approxfun/core.py:170-201, 311-336), lanes striding over the K terms; returns component `lane`.
+static __device__ __noinline__ double force_series_eval(const ForceSeries* fs, const MethodDev& m, const double* xi,
+                                                        int lane) {
+  const int K = fs->K, dims = fs->dims;
+  const int32_t* ns = fs->exponents();
+  const double* val = fs->values();
+  double x[2] = {0.0, 0.0}, sd[2] = {0.0, 0.0};
+  for (int d = 0; d < dims; ++d) {
+    const double size = m.g_upper[d] - m.g_lower[d];
+    x[d] = (xi[d] - m.g_lower[d]) * 2.0 / size - 1.0;  // approxfun/core.py:99-104
+    sd[d] = 2.0 * (fs->kind == PSB_SERIES_FOURIER ? 3.141592653589793 : 1.0) / size;
+  }
+  double acc[2] = {0.0, 0.0};
+  for (int k = lane; k < K; k += 32) {
+    const int n0 = ns[k * dims], n1 = dims > 1 ? ns[k * dims + 1] : 0;
+    if (fs->kind == PSB_SERIES_FOURIER) {  // imag(exp(-i t)) = -sin t multiplies c_k, real = cos t multiplies c_{K+k}
+      double sn, cs;
+      sincospi((double)n0 * x[0] + (double)n1 * x[1], &sn, &cs);
+      const double w = cs * val[1 + K + k] - sn * val[1 + k];
+      acc[0] += sd[0] * (double)n0 * w;
+      acc[1] += sd[1] * (double)n1 * w;
+    } else {  // x^n by repeated multiplication (n < 64)
+      double p0 = 1.0, p0m = 1.0, p1 = 1.0, p1m = 1.0;  // x^n and x^max(n-1, 0)
+      for (int e = 0; e < n0; ++e) { p0m = p0; p0 *= x[0]; }
+      for (int e = 0; e < n1; ++e) { p1m = p1; p1 *= x[1]; }
+      const double c = val[1 + k];
+      acc[0] += sd[0] * (double)n0 * p0m * p1 * c;
+      acc[1] += sd[1] * (double)n1 * p1m * p0 * c;
+    }
+  }
+  const double a0 = warp_sum(acc[0]), a1 = warp_sum(acc[1]);
+  return lane < dims ? val[0] * (lane == 0 ? a0 : a1) : 0.0;
+}
+
 // Everything of abf.py:213-258 that depends on xi alone: the bin of xi, the gathered hist[I] / Fsum[I]
 // (gathers clamp, JAX default), the new count, max(N, count) as a double and the restraint force
 // outside the grid.  Point-CV kernels run it on warp 1 while warp 0 does J p / solve.
@@ -558,8 +593,13 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   const bool oob = f.oob != 0;
   // funn.py:190,286-296: past the ABF-only stage the force comes from the network (restraints first)
   const bool use_net = M.nn != nullptr && !(m.has_restraints && oob) && sh.pre.ncalls + 1 > sh.nnh.predict_after;
-  const double f_net =
+  double f_net =
       use_net ? force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0], lane) : 0.0;
+  // spectral_abf.py:186,245-266: series gradient past fit_threshold; outside the grid restraints or nothing
+  const ForceSeries* ser = M.fs == nullptr ? nullptr : (M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.nnh) : M.fs);
+  const bool zero_oob = ser != nullptr && ser->oob_zero && oob && !m.has_restraints;
+  const bool use_series = ser != nullptr && !oob && sh.pre.ncalls + 1 > ser->predict_after;
+  if (use_series) f_net = force_series_eval(ser, m, f.xi, lane);
   if (lane < k) {
     const int c = lane;
     const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
@@ -568,7 +608,8 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
       const double dWp_dt = (1.5 * Wp_now - 2.0 * Wp_1 + 0.5 * sh.pre.Wp_[c]) / S.dt;
       fs += m.force_unit_factor * dWp_dt + sh.pre.force[c];
     }
-    const double fc = (m.has_restraints && oob) ? f.rforce[c] : (use_net ? f_net : fs / f.den);
+    const double fc = (m.has_restraints && oob) ? f.rforce[c]
+                      : (zero_oob ? 0.0 : ((use_net || use_series) ? f_net : fs / f.den));
     f.F[c] = fc;
     f.Fsum_new[c] = fs;
     if (cta0 && !M.ll_reduce) {  // scalars nobody reads after the first barrier (LL exchange: stored at the end)
@@ -1100,12 +1141,14 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- force network (psb_set_force_net): header + parameters into shared memory -----------------
-  if (is_abf && M.nn != nullptr && tid >= BLOCK - 64) {
+  if (is_abf && (M.nn != nullptr || (M.fs != nullptr && M.fs_staged)) && tid >= BLOCK - 64) {
     static_assert(sizeof(ForceNet) % 8 == 0 && offsetof(StepShared, nnw) == offsetof(StepShared, nnh) + sizeof(ForceNet),
                   "header and staged parameters are copied as one block");
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(M.nn);
+    const bool net = M.nn != nullptr;  // a handle has a network or a series, never both
+    const unsigned long long* src = net ? reinterpret_cast<const unsigned long long*>(M.nn)
+                                        : reinterpret_cast<const unsigned long long*>(M.fs);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.nnh);
-    const int words = (int)(sizeof(ForceNet) / 8) + M.nn_np;
+    const int words = net ? (int)(sizeof(ForceNet) / 8) + M.nn_np : M.fs_staged;
     for (int i = tid - (BLOCK - 64); i < words; i += 64) dst[i] = __ldcg(src + i);
   }
 

@@ -223,6 +223,27 @@ class NativeStep:
         N.check(self.lib.psb_set_force_net(self.handle, ctypes.byref(d), self._stream()))
         self._force_net_params = keep  # a device source must outlive the stream-ordered copy
 
+    def set_force_series(self, kind, exponents, values, predict_after, oob_zero=True):
+        """psb_set_force_series: `values` = [scale, coefficients...], a torch tensor (device or host) or array;
+        kind None removes the series."""
+        d = N.ForceSeriesDesc()
+        keep = None
+        if kind is not None:
+            ex = np.ascontiguousarray(exponents, dtype=np.int32)
+            d.kind, d.n_terms = int(kind), int(ex.shape[0])
+            d.oob_zero, d.predict_after = int(bool(oob_zero)), int(predict_after)
+            d.exponents = ex.ctypes.data
+            if isinstance(values, torch.Tensor):
+                vals = values.detach().to(torch.float64).contiguous()
+                d.values_on_device = int(vals.is_cuda)
+                d.values = vals.data_ptr()
+            else:
+                vals = np.ascontiguousarray(values, dtype=np.float64)
+                d.values = vals.ctypes.data
+            keep = (ex, vals)
+        N.check(self.lib.psb_set_force_series(self.handle, ctypes.byref(d), self._stream()))
+        self._force_series = keep  # a device source must outlive the stream-ordered copy
+
     def launch_info(self):
         g, b, c, nbytes = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
         N.check(self.lib.psb_launch_info(self.handle, ctypes.byref(g), ctypes.byref(b), ctypes.byref(c),
@@ -664,6 +685,106 @@ class FUNN(NNSamplingMethod):
 
         update.native = native
         update.set_network = set_network
+        update.restore = restore
+        return snapshot, initialize, update
+
+
+class SpectralABFState(NamedTuple):  # spectral_abf.py:36-84
+    xi: Any
+    bias: Any
+    hist: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    fun: Any
+    ncalls: int = 0
+
+
+class Fun(NamedTuple):  # approxfun/core.py:18-27
+    scale: Any
+    coefficients: Any
+    c0: Any = 0.0
+
+
+class SpectralABF(GriddedSamplingMethod):
+    """
+    methods/spectral_abf.py:95-268.  Every step is the fused ABF step; past `fit_threshold` calls the
+    kernel takes the force from the gradient of a Fourier (periodic grid) or monomial (grid converted to
+    Chebyshev, spectral_abf.py:140) series (psb_set_force_series).  The refit -- binned mean force,
+    normalisation, one pseudo-inverse product (approxfun/core.py:232-258) -- runs every `fit_freq` calls on
+    the method's device and never touches the host.  Outside the grid: restraints, or no force at all.
+    """
+
+    snapshot_flags = {"positions", "indices", "momenta"}
+    _kind = N.METHOD_ABF
+
+    def __init__(self, cvs, grid, **kwargs):
+        from . import approxfun
+        from .grids import Chebyshev, Grid, convert
+
+        super().__init__(cvs, grid, **kwargs)
+        self.N = np.asarray(self.kwargs.get("N", 500))
+        self.fit_freq = self.kwargs.get("fit_freq", 100)
+        self.fit_threshold = self.kwargs.get("fit_threshold", 500)
+        self.grid = self.grid if self.grid.is_periodic else convert(self.grid, Grid[Chebyshev])
+        self.model = approxfun.SpectralGradientFit(self.grid)
+        self.use_pinv = self.kwargs.get("use_pinv", False)
+
+    describe = ABF.describe
+
+    def build(self, snapshot, helpers, *args, **kwargs):
+        from . import approxfun
+
+        native = NativeStep(self, snapshot, helpers, dense_outputs=self.dense_bias)
+        self.native = native
+        grid, model = self.grid, self.model
+        fit_freq, fit_threshold = int(self.fit_freq), int(self.fit_threshold)
+        k = native.k
+        gshape = tuple(int(s) for s in grid.shape)
+        fit = approxfun.build_fitter(model, native.device)
+        kind = N.SERIES_FOURIER if grid.is_periodic else N.SERIES_MONOMIAL
+        holder = {}
+
+        def push(values):
+            holder["values"] = values
+            native.set_force_series(kind, model.exponents, values, predict_after=fit_threshold, oob_zero=True)
+
+        def refit():  # spectral_abf.py:216-219 on the state as it is before this step's sample is added
+            hist = native.view("hist", gshape).to(torch.float64).unsqueeze(-1)
+            return fit(native.view("Fsum", (*gshape, k)) / torch.clamp(hist, min=1.0))
+
+        def make_state():
+            bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+            v = holder["values"]
+            return SpectralABFState(
+                native.view("xi", (1, k)), bias, native.view("hist", gshape), native.view("Fsum", (*gshape, k)),
+                native.view("force")[:k], native.view("Wp")[:k], native.view("Wp_")[:k], Fun(v[0], v[1:], 0.0),
+                native.ncalls,
+            )
+
+        def initialize():
+            native.evaluate(snapshot)
+            push(fit(native.view("Fsum", (*gshape, k))))  # spectral_abf.py:178: fit of the empty force sums
+            return make_state()
+
+        def update(snapshot, state, timestep=0):
+            ncalls = native.ncalls + 1
+            if ncalls > fit_threshold and ncalls % fit_freq == 1:  # spectral_abf.py:184-185
+                push(refit())
+            native.step(snapshot, timestep)
+            return make_state()
+
+        def restore(prev):
+            for name in ("xi", "hist", "Fsum", "force", "Wp", "Wp_", "ncalls"):
+                value = getattr(prev, name)
+                native.set_state(name, value.cpu().numpy() if hasattr(value, "cpu") else value)
+            to_t = lambda v: torch.as_tensor(np.asarray(v.cpu() if hasattr(v, "cpu") else v), dtype=torch.float64,
+                                             device=native.device)
+            push(torch.cat([to_t(prev.fun.scale).reshape(1), to_t(prev.fun.coefficients).reshape(-1)]))
+            return make_state()
+
+        update.native = native
         update.restore = restore
         return snapshot, initialize, update
 

@@ -52,6 +52,8 @@ def make_method(which, spec, cvs):
         return mod.Metadynamics(cvs, *args, kwargs.pop("deltaT", None), **kwargs)
     if name == "ABF":
         return mod.ABF(cvs, kwargs.pop("grid"), **kwargs)
+    if name == "SpectralABF":
+        return mod.SpectralABF(cvs, kwargs.pop("grid"), **kwargs)
     if name == "FUNN":
         if which != "oracle" and "max_iters" in kwargs:  # the oracle takes the LM iteration cap directly
             from pysages_b200 import ml

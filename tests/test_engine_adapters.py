@@ -197,3 +197,28 @@ def test_analyze_abf_and_umbrella_integration():
     mf = -50.0 * (means - np.array(centers))
     np.testing.assert_allclose(out["mean_forces"].reshape(3), mf, rtol=1e-12)
     np.testing.assert_allclose(out["free_energy"].reshape(3), [0.0, mf[0] * 0.5, mf[0] * 0.5 + mf[1] * 0.5], rtol=1e-12)
+
+
+def test_spectral_abf_run_save_load_restart(tmp_path):
+    """SpectralABF through `pysages_b200.run`: 10 steps (fit_threshold 3, fit_freq 2), checkpoint after 6, resume
+    == the uninterrupted run; the fitted series travels with the state."""
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=10, step=0.05)
+
+    def make_method():
+        cvs = [ps.colvars.Distance([G1, G2]), ps.colvars.Component([5, 6, 7], 1)]
+        return ps.methods.SpectralABF(cvs, ps.Grid((0.0, -6.0), (12.0, 6.0), (8, 8)), N=2, fit_threshold=3, fit_freq=2)
+
+    full = ps.run(make_method(), lambda **kw: _mock(snap, traj), 10)
+    part = ps.run(make_method(), lambda **kw: _mock(snap, traj), 6)
+    ps.save(part, tmp_path / "sabf.pkl")
+    loaded = ps.load(tmp_path / "sabf.pkl")
+    assert isinstance(loaded.states[0].fun.coefficients, np.ndarray)
+    resumed = ps.run(loaded, lambda first=0, **kw: _mock(snap, traj, first), 4, context_args=dict(first=6))
+    torch.cuda.synchronize()
+    a, b = resumed.states[0], full.states[0]
+    for name in ("xi", "hist", "Fsum", "force", "Wp", "Wp_"):
+        np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=name)
+    np.testing.assert_array_equal(a.fun.coefficients.cpu().numpy(), b.fun.coefficients.cpu().numpy())
+    assert float(a.fun.scale) == float(b.fun.scale) and int(a.ncalls) == int(b.ncalls) == 10
+    assert np.any(b.fun.coefficients.cpu().numpy() != 0.0)

@@ -93,3 +93,27 @@ def test_ring_cv_errors():
     cvs = (N.CvDesc * 1)(good)
     st = native.lib.psb_create(cvs, 1, ctypes.byref(mdesc), ctypes.byref(ldesc), ctypes.byref(handle))
     assert st == N.ERR_VALUE and b"amplitude (0) or phase (1)" in native.lib.psb_last_error()
+
+
+def test_force_series_errors():
+    snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
+    ex = np.array([[1], [2]], dtype=np.int32)
+    _, _, update = build(ps.methods.HarmonicBias([ps.colvars.Distance([1, 2])], 1.0, [0.0]), snap)
+    with pytest.raises(ValueError, match="ABF-family"):
+        update.native.set_force_series(N.SERIES_MONOMIAL, ex, np.zeros(3), predict_after=0)
+    grid = ps.Grid((0.0,), (5.0,), (8,))
+    _, _, update = build(ps.methods.ABF([ps.colvars.Distance([1, 2])], grid), snap)
+    native = update.native
+    with pytest.raises(ValueError, match="unknown kind"):
+        native.set_force_series(9, ex, np.zeros(3), predict_after=0)
+    with pytest.raises(ValueError, match="out of range"):
+        native.set_force_series(N.SERIES_MONOMIAL, np.array([[-1]], dtype=np.int32), np.zeros(2), predict_after=0)
+    native.set_force_series(N.SERIES_MONOMIAL, ex, np.zeros(3), predict_after=0)
+    native.set_force_series(None, None, None, predict_after=0)  # removed again
+    grid3 = ps.Grid((0.0,) * 3, (5.0,) * 3, (4, 4, 4))
+    cvs3 = [ps.colvars.Component([i], i) for i in range(3)]
+    _, _, update = build(ps.methods.ABF(cvs3, grid3), snap)
+    with pytest.raises(ValueError, match="Only 1D and 2D grids"):
+        update.native.set_force_series(N.SERIES_MONOMIAL, np.ones((2, 3), dtype=np.int32), np.zeros(3), predict_after=0)
+    with pytest.raises(ValueError, match="Only 1D and 2D grids"):  # approxfun/core.py:74-75 at construction
+        ps.methods.SpectralABF(cvs3, grid3)

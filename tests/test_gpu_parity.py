@@ -714,3 +714,40 @@ def test_ring_amplitude_abf_position_dependent_jacobian():
     run = ParityRun(snap, specs, ("ABF", kw))
     for pos in perturbed(snap, 4, 0.05):
         run.step(pos)
+
+
+# ---- SpectralABF: ABF accumulation + force from the fitted series (spectral_abf.py:95-268) --------------
+@pytest.mark.parametrize("case", ["fourier-2d", "monomial-1d", "monomial-2d-restraints", "monomial-2d-oob-zero"])
+def test_spectral_abf(case, golden):
+    """fit_threshold = 3, fit_freq = 2: calls 1-3 plain ABF, refits before calls 5, 7, 9 (pinv product on the
+    device vs numpy), force = gradient of the series evaluated in the kernel; outside the grid restraints,
+    or -- without them -- zero force (not the clamped bin average ABF / FUNN use)."""
+    if case == "fourier-2d":
+        snap = adp(golden)
+        cvs = ADP_CVS
+        kw = dict(grid=((-math.pi, -math.pi), (math.pi, math.pi), (12, 10), "periodic"), N=2)
+        step = 0.02
+    else:
+        snap = snapshot("hoomd", np.float64)
+        step = 0.1
+        if case == "monomial-1d":
+            cvs = POINT_CVS["distance-groups"]
+            kw = dict(grid=((0.0,), (14.0,), (24,), "regular"), N=2)
+        else:
+            cvs = POINT_CVS["two-distances"]
+            hi = 8.0 if case.endswith("restraints") else 4.5  # the smaller box leaves xi outside most of the time
+            kw = dict(grid=((0.0, 0.0), (hi, hi), (8, 8), "regular"), N=2)
+            if case.endswith("restraints"):
+                kw["restraints"] = ((0.0, 0.0), (hi, hi), (20.0, 20.0), (20.0, 20.0))
+    kw.update(fit_threshold=3, fit_freq=2)
+    run = ParityRun(snap, cvs, ("SpectralABF", kw))
+    oob_steps = 0
+    for pos in perturbed(snap, 10, step):
+        ours, ref = run.step(pos)
+        oob_steps += int(not np.any(ref.force.numpy()))
+    fun, ofun = run.state.fun, run.ostate.fun
+    np.testing.assert_allclose(float(fun.scale), ofun.scale, rtol=1e-10)
+    np.testing.assert_allclose(fun.coefficients.cpu().numpy(), ofun.coefficients, rtol=1e-8,
+                               atol=1e-11 * np.abs(ofun.coefficients).max())
+    if case == "monomial-2d-oob-zero":
+        assert oob_steps > 0  # the zero-force branch was taken
