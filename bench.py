@@ -495,6 +495,21 @@ def run_series(device, stream, hbm):
 
     frames, L, _ = device_hoomd_frames(100_000, 64, device, seed=20240 + 2000)
     measure("abf2d S=N=100000 hoomd-f32 + FUNN network force (14,14)", "abf2d", 100_000, 2000, frames, L, extra=with_network)
+
+    # SpectralABF (spectral_abf.py:181-268): the same workload with the force from the gradient of the series the
+    # reference would fit on this grid (64x64 -> Chebyshev grid, monomial basis, collect_exponents terms)
+    def with_series(native):
+        import pysages_b200 as ps
+        from pysages_b200 import _native as N
+        from pysages_b200 import approxfun
+
+        ns = approxfun.collect_exponents(ps.Grid[ps.Chebyshev]((0.0, 0.0), (L / 2, L / 2), (64, 64)))
+        vals = np.concatenate([[1.0], np.random.default_rng(0).normal(size=ns.shape[0]) * 1e-3])
+        native.set_force_series(N.SERIES_MONOMIAL, ns, vals, predict_after=0, oob_zero=False)
+        with_series.terms = int(ns.shape[0])
+
+    row = measure("abf2d S=N=100000 hoomd-f32 + SpectralABF series force", "abf2d", 100_000, 2000, frames, L, extra=with_series)
+    row["workload"] += f" ({with_series.terms} monomial terms)"
     del frames
 
     # the headline workload on the other engine layouts (OpenMM-CUDA: fixed-point forces, permuted order,

@@ -503,7 +503,7 @@ static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const d
 // spectral_abf.py:245-246 interpolate_force, one warp: gradient of the fitted Fourier / monomial series at
 // xi (approxfun/core.py:170-201, 311-336), lanes striding over the K terms; returns component `lane`.
 static __device__ __noinline__ double force_series_eval(const ForceSeries* fs, const MethodDev& m, const double* xi,
-                                                        int lane) {
+                                                        double* pw, int lane) {
   const int K = fs->K, dims = fs->dims;
   const int32_t* ns = fs->exponents();
   const double* val = fs->values();
@@ -512,6 +512,17 @@ static __device__ __noinline__ double force_series_eval(const ForceSeries* fs, c
     const double size = m.g_upper[d] - m.g_lower[d];
     x[d] = (xi[d] - m.g_lower[d]) * 2.0 / size - 1.0;  // approxfun/core.py:99-104
     sd[d] = 2.0 * (fs->kind == PSB_SERIES_FOURIER ? 3.141592653589793 : 1.0) / size;
+  }
+  if (fs->kind == PSB_SERIES_MONOMIAL) {  // power tables pw[d * 64 + j] = x_d^j, j < 64 (binary exponentiation)
+    for (int j = lane; j < 128; j += 32) {
+      double base = x[j >> 6], r = 1.0;
+      for (int e = j & 63; e > 0; e >>= 1) {
+        if (e & 1) r *= base;
+        base *= base;
+      }
+      pw[j] = r;
+    }
+    __syncwarp();
   }
   double acc[2] = {0.0, 0.0};
   for (int k = lane; k < K; k += 32) {
@@ -522,10 +533,8 @@ static __device__ __noinline__ double force_series_eval(const ForceSeries* fs, c
       const double w = cs * val[1 + K + k] - sn * val[1 + k];
       acc[0] += sd[0] * (double)n0 * w;
       acc[1] += sd[1] * (double)n1 * w;
-    } else {  // x^n by repeated multiplication (n < 64)
-      double p0 = 1.0, p0m = 1.0, p1 = 1.0, p1m = 1.0;  // x^n and x^max(n-1, 0)
-      for (int e = 0; e < n0; ++e) { p0m = p0; p0 *= x[0]; }
-      for (int e = 0; e < n1; ++e) { p1m = p1; p1 *= x[1]; }
+    } else {  // x^n and x^max(n - 1, 0) from the tables (0 <= n < 64, checked by psb_set_force_series)
+      const double p0 = pw[n0], p0m = pw[max(n0 - 1, 0)], p1 = pw[64 + n1], p1m = pw[64 + max(n1 - 1, 0)];
       const double c = val[1 + k];
       acc[0] += sd[0] * (double)n0 * p0m * p1 * c;
       acc[1] += sd[1] * (double)n1 * p1m * p0 * c;
@@ -599,7 +608,7 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   const ForceSeries* ser = M.fs == nullptr ? nullptr : (M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.nnh) : M.fs);
   const bool zero_oob = ser != nullptr && ser->oob_zero && oob && !m.has_restraints;
   const bool use_series = ser != nullptr && !oob && sh.pre.ncalls + 1 > ser->predict_after;
-  if (use_series) f_net = force_series_eval(ser, m, f.xi, lane);
+  if (use_series) f_net = force_series_eval(ser, m, f.xi, &sh.nnbuf[0][0], lane);
   if (lane < k) {
     const int c = lane;
     const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
