@@ -117,7 +117,8 @@ typedef enum {
 
 typedef struct {
   int32_t kind; /* psb_method_kind */
-  int32_t reserved;
+  int32_t variant; /* PSB_METHOD_ABF only: 0 = ABF / FUNN / SpectralABF; 1 = histogram only (ANN, methods/ann.py:153-167:
+                      no momenta, no force sums; the force is the network gradient or zero) */
   /* HarmonicBias: harmonic_bias.py:78-107 canonical (k x k) spring matrix, row-major; center (k) */
   double kspring[PSB_MAX_K * PSB_MAX_K];
   double center[PSB_MAX_K];
@@ -269,6 +270,8 @@ typedef struct {
   int32_t widths[PSB_MAX_DENSE + 1]; /* widths[0] = widths[n_dense] = k */
   int32_t activation;                /* psb_activation; PSB_ACT_SIN is sin(omega * x) (ml/models.py:113-121,140-143) */
   int32_t params_on_device;          /* `params` is a device pointer */
+  int32_t gradient;                  /* 1: F = std * d(sum of outputs)/d xi (ANN, ann.py:240-248) instead of std * output + mean */
+  int32_t reserved;
   double omega0, omega;              /* PSB_ACT_SIN only: frequency of the first / of the other layers */
   int64_t predict_after;
   const double* params;

@@ -616,3 +616,104 @@ class SpectralABF(ABF):
             return SpectralABFState(xi, bias, hist, Fsum, force, Wp, state.Wp, fun, ncalls)
 
         return snapshot, initialize, generalize(update, helpers)
+
+
+# --------------------------------------------------------------------------- #
+# ANN (ann.py:65-258)
+# --------------------------------------------------------------------------- #
+
+
+class ANNState(NamedTuple):  # ann.py:38-62
+    xi: Any
+    bias: Any
+    hist: Any
+    phi: Any
+    prob: Any
+    nn: Any
+    ncalls: int = 0
+
+
+class ANN(SamplingMethod):
+    """ann.py:65-258: histogram of visits; every train_freq calls a network is fitted to the (smoothed,
+    normalized) free energy estimate kT log(prob); the bias force is std * d net / d xi inside the grid once
+    ncalls > train_freq, zero otherwise."""
+
+    snapshot_flags = {"positions", "indices"}
+
+    def __init__(self, cvs, grid, topology, kT, **kwargs):
+        if len(cvs) != grid.shape.size:
+            raise ValueError("Grid and Collective Variable dimensions must match.")
+        super().__init__(cvs, **kwargs)
+        from . import ml
+
+        self.grid = grid
+        self.topology = tuple(topology)
+        self.kT = kT
+        self.train_freq = kwargs.get("train_freq", 5000)
+        dims = grid.shape.size
+        self.widths = ml.layer_sizes(dims, self.topology, 1)
+        self.initial_params = kwargs.get("initial_params", None)
+        if self.initial_params is None:
+            self.initial_params = ml.init_params(self.widths, kwargs.get("seed", 0))
+        self.reg = kwargs.get("reg", 1e-6)
+        self.max_iters = kwargs.get("max_iters", 500)
+
+    def build(self, snapshot, helpers):
+        from . import ml
+
+        cv, grid, kT = self.cv, self.grid, self.kT
+        dims = grid.shape.size
+        gshape = tuple(int(s) for s in grid.shape)
+        shape = gshape if dims > 1 else (*gshape, 1)
+        natoms = _natoms(snapshot)
+        get_grid_index = grids.build_indexer(grid)
+        train_freq, widths = self.train_freq, self.widths
+        lower, upper = np.asarray(grid.lower, dtype=np.float64), np.asarray(grid.upper, dtype=np.float64)
+        inputs = grids.compute_mesh(grid)
+        kernel = ml.blackman_kernel(dims, 7)
+        padding = "wrap" if grid.is_periodic else "edge"
+        query, dimensionality, _ = helpers
+
+        def smooth(y):  # ann.py:189: conv if dims > 1 else vmap(conv)(y.T).T
+            if dims > 1:
+                return ml.convolve(y, kernel, padding)
+            return ml.convolve(y[:, 0], kernel, padding)[:, None]
+
+        def learn(state):  # ann.py:194-211
+            hist = state.hist.numpy().astype(np.float64).reshape(shape)
+            prob = state.prob + hist * np.exp(state.phi / kT)
+            phi = kT * np.log(prob)
+            y, mean, std = ml.normalize(phi)
+            reference = smooth(y)
+            params = ml.lm_fit(state.nn.params, widths, inputs, reference, lower, upper, reg=self.reg,
+                               max_iters=self.max_iters)
+            nn = ml.NNData(params, mean, std / reference.std())
+            phi = nn.std * ml.mlp_apply(params, widths, inputs, lower, upper).reshape(phi.shape)
+            phi = phi - phi.min()
+            return torch.zeros_like(state.hist), prob, phi, nn
+
+        def initialize():  # ann.py:143-151
+            xi, _ = cv(query(snapshot))
+            bias = torch.zeros((natoms, dimensionality()), dtype=F64)
+            hist = torch.zeros(gshape, dtype=torch.int64)
+            nn = ml.NNData(np.asarray(self.initial_params, dtype=np.float64), 0.0, 1.0)
+            return ANNState(xi, bias, hist, np.zeros(shape), np.ones(shape), nn)
+
+        def update(state, data):  # ann.py:153-167
+            ncalls = state.ncalls + 1
+            in_training_regime = ncalls > train_freq
+            in_training_step = in_training_regime and (ncalls % train_freq == 1)
+            hist, prob, phi, nn = learn(state) if in_training_step else (state.hist, state.prob, state.phi, state.nn)
+            xi, Jxi = cv(data)
+            I_xi = get_grid_index(xi.detach().numpy())
+            hist = _scatter_add(hist, I_xi, 1)
+            in_bounds = all(int(i) != s for i, s in zip(I_xi, gshape))
+            if in_training_regime and in_bounds:  # ann.py:243-256
+                x = xi.detach().numpy().astype(np.float32).astype(np.float64)
+                F = torch.as_tensor(nn.std * ml.mlp_input_gradient(nn.params, widths, x, lower, upper))
+            else:
+                F = torch.zeros(dims, dtype=F64)
+            bias = (-Jxi.T.to(F64) @ F).reshape(state.bias.shape)
+            return ANNState(xi, bias, hist, phi, prob, nn, ncalls)
+
+        return snapshot, initialize, generalize(update, helpers)

@@ -193,3 +193,23 @@ class NNData:
     # ml/training.py:11-14
     def __init__(self, params, mean, std):
         self.params, self.mean, self.std = params, mean, std
+
+
+def mlp_input_gradient(ps, widths, x, lower, upper):
+    """jax.grad(lambda p, x: model.apply(p, x).sum(), argnums=1) of ann.py:240 for ONE point x (tanh layers),
+    chain rule through `scale` included."""
+    u = scale(np.asarray(x, dtype=np.float64).reshape(1, widths[0]), np.asarray(lower, dtype=np.float64),
+              np.asarray(upper, dtype=np.float64))
+    layers = split_params(np.asarray(ps, dtype=np.float64), widths)
+    h, acts = u, []
+    for l, (W, b) in enumerate(layers):
+        h = h @ W + b
+        if l + 1 < len(layers):
+            h = np.tanh(h)
+            acts.append(h)
+    delta = np.ones((1, widths[-1]))
+    for l in range(len(layers) - 1, -1, -1):
+        delta = delta @ layers[l][0].T
+        if l > 0:
+            delta = delta * (1.0 - acts[l - 1] ** 2)
+    return (delta * 2 / (np.asarray(upper, dtype=np.float64) - np.asarray(lower, dtype=np.float64))).reshape(-1)

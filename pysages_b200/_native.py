@@ -50,7 +50,7 @@ class GridDesc(Structure):
 class MethodDesc(Structure):
     _fields_ = [
         ("kind", c_int32),
-        ("reserved", c_int32),
+        ("variant", c_int32),
         ("kspring", c_double * (MAX_K * MAX_K)),
         ("center", c_double * MAX_K),
         ("height", c_double),
@@ -85,6 +85,8 @@ class ForceNetDesc(Structure):  # psb_force_net
         ("widths", c_int32 * (MAX_DENSE + 1)),
         ("activation", c_int32),
         ("params_on_device", c_int32),
+        ("gradient", c_int32),
+        ("reserved", c_int32),
         ("omega0", c_double),
         ("omega", c_double),
         ("predict_after", c_int64),

@@ -164,6 +164,31 @@ def analyze(result):
         if len(states) == 1:
             return dict(heights=heights[0], metapotential=pots[0])
         return dict(heights=heights, metapotential=pots)
+    if isinstance(method, _m.ANN):  # ann.py:261-322: histogram, free energy on the grid, the network and fes_fn
+        import torch
+
+        out = dict(histogram=[], free_energy=[], nn=[], fes_fn=[], mesh=compute_mesh(method.grid))
+        model = method.model
+
+        def build_fes_fn(nn):
+            def fes_fn(x):
+                ps = torch.as_tensor(np.asarray(nn.params), dtype=torch.float64)
+                A = float(np.asarray(nn.std)) * model.apply(ps, torch.as_tensor(np.asarray(x, dtype=np.float64))) + float(
+                    np.asarray(nn.mean))
+                return (A.max() - A).numpy()
+
+            return fes_fn
+
+        for s in result.states:
+            h = numpyfy(s)
+            out["histogram"].append(np.asarray(h.hist))
+            out["free_energy"].append(np.asarray(h.phi).max() - np.asarray(h.phi))
+            out["nn"].append(h.nn)
+            out["fes_fn"].append(build_fes_fn(h.nn))
+        if len(result.states) == 1:
+            for key in ("histogram", "free_energy", "nn", "fes_fn"):
+                out[key] = out[key][0]
+        return out
     if isinstance(method, (_m.ABF, _m.FUNN, _m.SpectralABF)):
         out = dict(histogram=[], mean_force=[], mesh=compute_mesh(method.grid))
         for s in result.states:

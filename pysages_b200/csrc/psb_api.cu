@@ -364,6 +364,9 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   m.abf_N = method->abf_N;
   m.use_pinv = method->use_pinv;
   m.has_restraints = method->has_restraints;
+  if (method->variant != 0 && !(method->kind == PSB_METHOD_ABF && method->variant == 1))
+    return bail(fail(PSB_ERR_VALUE, "unknown method variant %d", method->variant));
+  m.hist_only = method->kind == PSB_METHOD_ABF && method->variant == 1;
   m.force_unit_factor = method->force_unit_factor == 0.0 ? 1.0 : method->force_unit_factor;
   if (method->kind == PSB_METHOD_METAD) {
     if (method->stride < 1) return bail(fail(PSB_ERR_VALUE, "Metadynamics stride must be >= 1"));
@@ -371,9 +374,9 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     for (int c = 0; c < k; ++c)
       if (!(method->sigma[c] > 0.0)) return bail(fail(PSB_ERR_VALUE, "Metadynamics sigma must be positive"));
   }
-  if (method->kind == PSB_METHOD_ABF && !layout->need_momenta)
+  if (method->kind == PSB_METHOD_ABF && !layout->need_momenta && !m.hist_only)
     return bail(fail(PSB_ERR_VALUE, "ABF needs momenta (layout.need_momenta)"));
-  M.abf_fast = (method->kind == PSB_METHOD_ABF && M.all_point) ? 1 : 0;
+  M.abf_fast = (method->kind == PSB_METHOD_ABF && (M.all_point || m.hist_only)) ? 1 : 0;  // histogram only: no J p pass
 
   // ---- unique atoms (CSR) and group overlaps ---------------------------------------------------
   {
@@ -1038,7 +1041,7 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
   if (net->n_dense != 0) {
     if (net->n_dense < 1 || net->n_dense > PSB_MAX_DENSE)
       return fail(PSB_ERR_VALUE, "force network: between 1 and %d dense layers (got %d)", PSB_MAX_DENSE, net->n_dense);
-    if (net->widths[0] != M.k || net->widths[net->n_dense] != M.k)
+    if (net->widths[0] != M.k || (!net->gradient && net->widths[net->n_dense] != M.k))
       return fail(PSB_ERR_VALUE, "force network: input and output width must equal the %d CV components", M.k);
     if (net->activation != PSB_ACT_TANH && net->activation != PSB_ACT_SIN)
       return fail(PSB_ERR_VALUE, "force network: unknown activation %d", net->activation);
@@ -1047,6 +1050,7 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
     ForceNet hn{};
     hn.n_dense = net->n_dense;
     hn.activation = net->activation;
+    hn.gradient = net->gradient ? 1 : 0;
     hn.omega0 = net->omega0;
     hn.omega = net->omega;
     hn.predict_after = net->predict_after;

@@ -61,6 +61,8 @@ struct MethodDev {
   long long abf_N;
   int32_t use_pinv;
   int32_t has_restraints;
+  int32_t hist_only;  // ABF variant 1 (ANN): histogram only, force from the network gradient or zero
+  int32_t m_pad;
   double r_lower[MAXK], r_upper[MAXK], r_kl[MAXK], r_ku[MAXK];
   double force_unit_factor;
   int32_t grid_kind, grid_ndim;
@@ -76,7 +78,7 @@ struct ForceNet {
   int32_t n_dense;
   int32_t widths[PSB_MAX_DENSE + 1];
   int32_t activation;
-  int32_t pad;
+  int32_t gradient;  // 1: force = std * d(sum of outputs) / d xi (ANN)
   double omega0, omega;  // PSB_ACT_SIN: first layer / other layers
   long long predict_after;
   double mean[MAXK], std[MAXK];

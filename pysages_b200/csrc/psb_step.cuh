@@ -115,6 +115,7 @@ struct StepShared {
   unsigned long long seq;           // launches of this handle before this one (Snap::cta_seq), LL stamp source
   uint64_t mbar[2];
   double nnbuf[2][PSB_MAX_WIDTH];  // force network activations (force_net_eval)
+  double nndact[PSB_MAX_DENSE - 1][PSB_MAX_WIDTH];  // activation derivatives per hidden layer (gradient mode)
   ForceNet nnh;                    // force network header and (when they fit) parameters, staged after the
   double nnw[NN_STAGE];            // dependency wait by the two warps that have no rows to reduce
 };
@@ -470,7 +471,7 @@ __device__ __forceinline__ void finish_force(const Model& M, StepShared& sh, int
 // owns output unit j (+32, ...) of every layer; activations ping-pong through shared memory.
 // Returns component `lane` of the force.  Kept out of line: plain ABF never reaches it.
 static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const double* P, const MethodDev& m,
-                                                     const double* xi, double* buf, int lane) {
+                                                     const double* xi, double* buf, double* dact, int lane) {
   const int nd = nn->n_dense;
   double* cur = buf;
   double* nxt = buf + PSB_MAX_WIDTH;
@@ -490,14 +491,43 @@ static __device__ __noinline__ double force_net_eval(const ForceNet* nn, const d
 #pragma unroll 4
       for (int i = 0; i < in; ++i) acc = fma(cur[i], W[(size_t)i * out + j], acc);
       acc += b[j];
-      if (l + 1 < nd) acc = nn->activation == PSB_ACT_SIN ? sin(om * acc) : tanh(acc);
+      if (l + 1 < nd) {
+        if (nn->activation == PSB_ACT_SIN) {
+          double sn, cs;
+          sincos(om * acc, &sn, &cs);
+          if (dact) dact[l * PSB_MAX_WIDTH + j] = om * cs;
+          acc = sn;
+        } else {
+          acc = tanh(acc);
+          if (dact) dact[l * PSB_MAX_WIDTH + j] = 1.0 - acc * acc;
+        }
+      }
       nxt[j] = acc;
     }
     __syncwarp();
     double* t = cur; cur = nxt; nxt = t;
     in = out;
   }
-  return lane < in ? nn->std[lane] * cur[lane] + nn->mean[lane] : 0.0;
+  if (!nn->gradient) return lane < in ? nn->std[lane] * cur[lane] + nn->mean[lane] : 0.0;
+  // ann.py:240-248: gradient of the summed outputs with respect to xi (through `scale`), by back-propagation:
+  // delta over the units of a layer, lane i owns unit i (+32, ...)
+  for (int j = lane; j < in; j += 32) cur[j] = 1.0;
+  __syncwarp();
+  for (int l = nd - 1; l >= 0; --l) {
+    const int out = nn->widths[l + 1], inw = nn->widths[l];
+    const double* W = P + nn->w_off[l];
+    for (int i = lane; i < inw; i += 32) {
+      double acc = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < out; ++j) acc = fma(W[(size_t)i * out + j], cur[j], acc);
+      if (l > 0) acc *= dact[(l - 1) * PSB_MAX_WIDTH + i];
+      nxt[i] = acc;
+    }
+    __syncwarp();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  const int k0 = nn->widths[0];
+  return lane < k0 ? nn->std[lane] * cur[lane] * 2.0 / (m.g_upper[lane] - m.g_lower[lane]) : 0.0;
 }
 
 // spectral_abf.py:245-246 interpolate_force, one warp: gradient of the fitted Fourier / monomial series at
@@ -601,9 +631,11 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   PSB_CLK(13);
   const bool oob = f.oob != 0;
   // funn.py:190,286-296: past the ABF-only stage the force comes from the network (restraints first)
-  const bool use_net = M.nn != nullptr && !(m.has_restraints && oob) && sh.pre.ncalls + 1 > sh.nnh.predict_after;
-  double f_net =
-      use_net ? force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0], lane) : 0.0;
+  const bool use_net = M.nn != nullptr && !((m.has_restraints || m.hist_only) && oob) &&
+                       sh.pre.ncalls + 1 > sh.nnh.predict_after;
+  double f_net = use_net ? force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0],
+                                          sh.nnh.gradient ? &sh.nndact[0][0] : nullptr, lane)
+                         : 0.0;
   // spectral_abf.py:186,245-266: series gradient past fit_threshold; outside the grid restraints or nothing
   const ForceSeries* ser = M.fs == nullptr ? nullptr : (M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.nnh) : M.fs);
   const bool zero_oob = ser != nullptr && ser->oob_zero && oob && !m.has_restraints;
@@ -613,11 +645,13 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
     const int c = lane;
     const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
     double fs = f.Fsum_old[c];
-    if (!oob) {
+    if (!oob && !m.hist_only) {
       const double dWp_dt = (1.5 * Wp_now - 2.0 * Wp_1 + 0.5 * sh.pre.Wp_[c]) / S.dt;
       fs += m.force_unit_factor * dWp_dt + sh.pre.force[c];
     }
-    const double fc = (m.has_restraints && oob) ? f.rforce[c]
+    // ann.py:250-256: the histogram-only variant knows the network gradient or no force at all
+    const double fc = m.hist_only ? (use_net ? f_net : 0.0)
+                      : (m.has_restraints && oob) ? f.rforce[c]
                       : (zero_oob ? 0.0 : ((use_net || use_series) ? f_net : fs / f.den));
     f.F[c] = fc;
     f.Fsum_new[c] = fs;
@@ -704,6 +738,11 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
       if (!GENERAL) {  // point-CV kernels: warp 1 bins xi and gathers the histogram meanwhile
         __syncwarp();
         pair_sync(1);
+      }
+      if (m.hist_only) {  // ann.py:153-167: no momenta, no W p
+        if (lane < MAXK) f.Wp[lane] = 0.0;
+        abf_finish(M, S, sh, lane, cta0, !GENERAL, true);
+        break;
       }
       // J J^T and J p from per-group sums: point-CV Jacobians are constant within a group.
       if (M.jjt_const) {

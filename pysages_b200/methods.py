@@ -199,7 +199,8 @@ class NativeStep:
     def set_option(self, name, value):
         N.check(self.lib.psb_set_option(self.handle, name.encode(), int(value)))
 
-    def set_force_net(self, widths, params, mean, std, predict_after, activation=N.ACT_TANH, omega0=1.0, omega=1.0):
+    def set_force_net(self, widths, params, mean, std, predict_after, activation=N.ACT_TANH, omega0=1.0, omega=1.0,
+                      gradient=False):
         """psb_set_force_net: `params` is a flat fp64 torch tensor (device or host) or numpy array."""
         d = N.ForceNetDesc()
         d.n_dense = len(widths) - 1 if widths else 0
@@ -207,6 +208,7 @@ class NativeStep:
             d.widths[i] = int(w)
         d.activation, d.omega0, d.omega = int(activation), float(omega0), float(omega)
         d.predict_after = int(predict_after)
+        d.gradient = int(bool(gradient))
         keep = None
         if d.n_dense:
             if isinstance(params, torch.Tensor):
@@ -216,10 +218,10 @@ class NativeStep:
             else:
                 keep = np.ascontiguousarray(params, dtype=np.float64)
                 d.params = keep.ctypes.data
-            mean = np.asarray(torch.as_tensor(mean).detach().cpu(), dtype=np.float64).ravel()
-            std = np.asarray(torch.as_tensor(std).detach().cpu(), dtype=np.float64).ravel()
-            for i in range(self.k):
-                d.mean[i], d.std[i] = float(mean[i]), float(std[i])
+            host = lambda v: np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v, dtype=np.float64).ravel()
+            mean, std = host(mean), host(std)  # (python floats must not pass through torch's float32 default)
+            for i in range(self.k):  # scalars (ANN: one std for every component) are broadcast
+                d.mean[i], d.std[i] = float(mean[i % mean.size]), float(std[i % std.size])
         N.check(self.lib.psb_set_force_net(self.handle, ctypes.byref(d), self._stream()))
         self._force_net_params = keep  # a device source must outlive the stream-ordered copy
 
@@ -685,6 +687,123 @@ class FUNN(NNSamplingMethod):
 
         update.native = native
         update.set_network = set_network
+        update.restore = restore
+        return snapshot, initialize, update
+
+
+class ANNState(NamedTuple):  # ann.py:38-62
+    xi: Any
+    bias: Any
+    hist: Any
+    phi: Any
+    prob: Any
+    nn: Any
+    ncalls: int = 0
+
+
+class ANN(NNSamplingMethod):
+    """
+    methods/ann.py:65-258.  Per step the fused kernel (the histogram-only variant of the ABF instantiation:
+    no momenta, no force sums) evaluates the CVs, counts the visit and applies `std * d net / d xi`
+    (back-propagation through the network inside the kernel) once `ncalls > train_freq` and xi is inside the
+    grid, zero force otherwise.  Every `train_freq` calls the network is refitted on the device to the
+    smoothed, normalized free-energy estimate `kT log(prob)` (ann.py:170-217) and the histogram is reset.
+    """
+
+    snapshot_flags = {"positions", "indices"}
+    _kind = N.METHOD_ABF
+
+    def __init__(self, cvs, grid, topology, kT, **kwargs):
+        from numbers import Real
+
+        from . import ml
+
+        assert isinstance(kT, Real)  # ann.py:110
+        super().__init__(cvs, grid, topology, **kwargs)
+        self.kT = kT
+        self.train_freq = self.kwargs.get("train_freq", 5000)
+        dims = grid.shape.size
+        self.model = ml.MLP(dims, 1, topology, grid.lower, grid.upper, seed=self.kwargs.get("seed", 0),
+                            parameters=self.kwargs.get("initial_params", None))
+        self.optimizer = self.kwargs.get("optimizer", ml.LevenbergMarquardt(reg=ml.L2Regularization(1e-6)))
+
+    def describe(self, helpers):
+        d = self._base_desc(helpers)
+        d.variant = 1  # histogram only
+        d.abf_N = 1
+        grid = self.grid
+        d.grid = grid.describe()
+        return d
+
+    def build(self, snapshot, helpers, *args, **kwargs):
+        from . import ml
+        from .grids import compute_mesh
+
+        native = NativeStep(self, snapshot, helpers, dense_outputs=self.dense_bias)
+        self.native = native
+        grid, model, train_freq, kT = self.grid, self.model, int(self.train_freq), float(self.kT)
+        k = native.k
+        gshape = tuple(int(s) for s in grid.shape)
+        shape = gshape if k > 1 else (*gshape, 1)
+        dev = native.device
+        inputs = torch.as_tensor(compute_mesh(grid), dtype=torch.float64, device=dev)
+        kernel = ml.blackman_kernel(k, 7)
+        padding = "wrap" if grid.is_periodic else "edge"
+        fit = ml.build_fitting_function(model, self.optimizer)
+        one = lambda v: torch.tensor(float(v), dtype=torch.float64, device=dev)
+        holder = dict(nn=ml.NNData(torch.as_tensor(model.parameters, device=dev), one(0.0), one(1.0)),
+                      phi=torch.zeros(shape, dtype=torch.float64, device=dev),
+                      prob=torch.ones(shape, dtype=torch.float64, device=dev))
+
+        def push(nn):
+            native.set_force_net(model.widths, nn.params, [0.0], nn.std.reshape(1), predict_after=train_freq,
+                                 gradient=True)
+
+        def smooth(y):  # ann.py:189: conv if dims > 1 else vmap(conv)(y.T).T
+            return ml.convolve(y, kernel, padding) if k > 1 else ml.convolve(y[:, 0], kernel, padding)[:, None]
+
+        def learn():  # ann.py:194-211 on the histogram as it is before this step's visit is counted
+            hist = native.view("hist", gshape)
+            prob = holder["prob"] + hist.to(torch.float64).reshape(shape) * torch.exp(holder["phi"] / kT)
+            phi = kT * torch.log(prob)
+            y, mean, std = ml.normalize(phi)
+            reference = smooth(y)
+            params = fit(holder["nn"].params, inputs, reference)
+            nn = ml.NNData(params, mean, std / reference.std(unbiased=False))
+            phi = nn.std * model.apply(params, inputs).reshape(phi.shape)
+            holder.update(nn=nn, prob=prob, phi=phi - phi.min())
+            hist.zero_()
+
+        def make_state():
+            bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+            return ANNState(native.view("xi", (1, k)), bias, native.view("hist", gshape), holder["phi"], holder["prob"],
+                            holder["nn"], native.ncalls)
+
+        def initialize():
+            native.evaluate(snapshot)
+            push(holder["nn"])  # untrained network: not used before the first fit (ann.py:155-158)
+            return make_state()
+
+        def update(snapshot, state, timestep=0):
+            ncalls = native.ncalls + 1
+            if ncalls > train_freq and ncalls % train_freq == 1:
+                learn()
+                push(holder["nn"])
+            native.step(snapshot, timestep)
+            return make_state()
+
+        def restore(prev):
+            to_t = lambda v: torch.as_tensor(np.asarray(v.cpu() if hasattr(v, "cpu") else v), dtype=torch.float64,
+                                             device=dev)
+            for name in ("xi", "hist", "ncalls"):
+                value = getattr(prev, name)
+                native.set_state(name, value.cpu().numpy() if hasattr(value, "cpu") else value)
+            holder.update(phi=to_t(prev.phi).reshape(shape), prob=to_t(prev.prob).reshape(shape),
+                          nn=ml.NNData(to_t(prev.nn.params), to_t(prev.nn.mean), to_t(prev.nn.std)))
+            push(holder["nn"])
+            return make_state()
+
+        update.native = native
         update.restore = restore
         return snapshot, initialize, update
 

@@ -124,9 +124,11 @@ class MLP:
 
 
 def normalize(data, axes=None):
-    # ml/training.py:17-20 (population standard deviation, like numpy's default)
-    mean = data.mean(dim=axes)
-    std = data.std(dim=axes, unbiased=False)
+    # ml/training.py:17-20 (population standard deviation, like numpy's default); axes=None: all elements
+    if axes is None:
+        mean, std = data.mean(), data.std(unbiased=False)
+    else:
+        mean, std = data.mean(dim=axes), data.std(dim=axes, unbiased=False)
     return (data - mean) / std, mean, std
 
 

@@ -52,6 +52,12 @@ def make_method(which, spec, cvs):
         return mod.Metadynamics(cvs, *args, kwargs.pop("deltaT", None), **kwargs)
     if name == "ABF":
         return mod.ABF(cvs, kwargs.pop("grid"), **kwargs)
+    if name == "ANN":
+        if which != "oracle" and "max_iters" in kwargs:
+            from pysages_b200 import ml
+            kwargs["optimizer"] = ml.LevenbergMarquardt(reg=ml.L2Regularization(kwargs.pop("reg", 1e-6)),
+                                                        max_iters=kwargs.pop("max_iters"))
+        return mod.ANN(cvs, kwargs.pop("grid"), kwargs.pop("topology"), kwargs.pop("kT"), **kwargs)
     if name == "SpectralABF":
         return mod.SpectralABF(cvs, kwargs.pop("grid"), **kwargs)
     if name == "FUNN":

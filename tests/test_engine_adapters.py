@@ -222,3 +222,33 @@ def test_spectral_abf_run_save_load_restart(tmp_path):
     np.testing.assert_array_equal(a.fun.coefficients.cpu().numpy(), b.fun.coefficients.cpu().numpy())
     assert float(a.fun.scale) == float(b.fun.scale) and int(a.ncalls) == int(b.ncalls) == 10
     assert np.any(b.fun.coefficients.cpu().numpy() != 0.0)
+
+
+def test_ann_run_save_load_restart_and_analyze(tmp_path):
+    """ANN through `pysages_b200.run`: 9 steps with train_freq = 2, checkpoint after 5, resume == uninterrupted;
+    analyze() returns the free energy on the grid and a callable built from the saved network (ann.py:261-322)."""
+    from pysages_b200 import ml
+
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=9, step=0.05)
+
+    def make_method():
+        cvs = [ps.colvars.Distance([G1, G2]), ps.colvars.Component([5, 6, 7], 1)]
+        opt = ml.LevenbergMarquardt(reg=ml.L2Regularization(1e-6), max_iters=3)
+        return ps.methods.ANN(cvs, ps.Grid((0.0, -6.0), (12.0, 6.0), (8, 8)), (5,), 2.5, train_freq=2, optimizer=opt)
+
+    full = ps.run(make_method(), lambda **kw: _mock(snap, traj), 9)
+    part = ps.run(make_method(), lambda **kw: _mock(snap, traj), 5)
+    ps.save(part, tmp_path / "ann.pkl")
+    resumed = ps.run(ps.load(tmp_path / "ann.pkl"), lambda first=0, **kw: _mock(snap, traj, first), 4,
+                     context_args=dict(first=5))
+    torch.cuda.synchronize()
+    a, b = resumed.states[0], full.states[0]
+    for name in ("xi", "hist", "phi", "prob"):
+        np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=name)
+    np.testing.assert_array_equal(a.nn.params.cpu().numpy(), b.nn.params.cpu().numpy())
+    assert int(a.ncalls) == int(b.ncalls) == 9
+    out = ps.analyze(full)
+    assert out["free_energy"].shape == (8, 8) and out["free_energy"].min() == 0.0
+    fes = out["fes_fn"](out["mesh"])
+    assert fes.shape == (64, 1) and fes.min() == 0.0 and np.all(np.isfinite(fes))

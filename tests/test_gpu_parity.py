@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from parity_utils import ParityRun, close
+import pysages_b200 as ps_
 from pysages_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
@@ -751,3 +752,82 @@ def test_spectral_abf(case, golden):
                                atol=1e-11 * np.abs(ofun.coefficients).max())
     if case == "monomial-2d-oob-zero":
         assert oob_steps > 0  # the zero-force branch was taken
+
+
+# ---- ANN: histogram + force from the gradient of the network (ann.py:65-258) -------------------------------
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float64), ("hoomd", np.float32), ("lammps", np.float64),
+                                           ("openmm-cuda", np.float64)])
+@pytest.mark.parametrize("dims", [1, 2])
+def test_ann_network_gradient_force(layout, dtype, dims):
+    """train_freq = 2: calls 1-2 unbiased histogramming, refits before calls 3, 5, 7 (LM capped at 0 iterations:
+    both sides keep the same weights, std comes from the normalized / smoothed kT log(prob)), force =
+    std * d net / d xi by back-propagation inside the kernel, zero outside the grid; histogram reset at refits."""
+    snap = snapshot(layout, dtype)
+    if dims == 1:
+        cvs, grid = POINT_CVS["distance-groups"], ((0.0,), (14.0,), (16,), "regular")
+    else:
+        cvs, grid = POINT_CVS["two-distances"], ((0.0, 0.0), (8.0, 8.0), (8, 8), "regular")
+    kw = dict(grid=grid, topology=(6, 5), kT=2.5, train_freq=2, max_iters=0, seed=7)
+    run = ParityRun(snap, cvs, ("ANN", kw), units="real" if layout == "lammps" else None)
+    for pos in perturbed(snap, 8, 0.1):
+        ours, ref = run.step(pos)
+        np.testing.assert_allclose(ours.phi.cpu().numpy(), ref.phi, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(ours.prob.cpu().numpy(), ref.prob, rtol=1e-10)
+    assert int(run.state.hist.sum()) <= 2  # reset at the refit before call 7, then calls 7 and 8
+    np.testing.assert_allclose(float(run.state.nn.std), run.ostate.nn.std, rtol=1e-8)
+
+
+def test_ann_refit_tracks_oracle():
+    snap = snapshot("hoomd", np.float64)
+    kw = dict(grid=((0.0, 0.0), (8.0, 8.0), (8, 8), "regular"), topology=(6,), kT=2.5, train_freq=3, max_iters=4, seed=3)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("ANN", kw))
+    frames = perturbed(snap, 5, 0.1)
+    for pos in frames[:3]:
+        run.step(pos)
+    ours, ref = run.step(frames[3], check=False)  # call 4 = train_freq + 1: first fit
+    np.testing.assert_allclose(ours.nn.params.cpu().numpy(), ref.nn.params, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ours.bias.cpu().numpy(), ref.bias.numpy(), rtol=1e-5, atol=1e-9)
+    assert np.array_equal(ours.hist.cpu().numpy().astype(np.int64), ref.hist.numpy())
+
+
+@pytest.mark.parametrize("activation", ["tanh", "sin"])
+def test_force_net_gradient_mode_against_oracle(activation):
+    """psb_set_force_net(gradient=1) on a deep / wide network, weights from device memory: F against the
+    oracle's back-propagation (tanh) or autograd of the sine network."""
+    from oracle import ml as oml
+    from pysages_b200 import _native as N
+
+    snap = snapshot("hoomd", np.float64)
+    grid = ((0.0, 0.0), (8.0, 8.0), (8, 8), "regular")
+    cvs = [ps_.colvars.Distance([A, B]), ps_.colvars.Distance([C, D])]
+    method = ps_.methods.ANN(cvs, ps_.Grid((0.0, 0.0), (8.0, 8.0), (8, 8)), (4,), 2.5, train_freq=10**9, dense_bias=True)
+    from parity_utils import device_helpers, device_snapshot
+
+    dsnap = device_snapshot(snap)
+    _, init, update = method.build(dsnap, device_helpers("hoomd"))
+    state = init()
+    widths = oml.layer_sizes(2, (128, 3, 64, 128, 128, 9, 128), 1)
+    params = oml.init_params(widths, seed=5)  # glorot scale: gain ~1 per layer keeps the gradient well conditioned
+    update.native.set_force_net(widths, torch.as_tensor(params, device="cuda"), [0.0], [1.7], predict_after=0,
+                                activation=N.ACT_SIN if activation == "sin" else N.ACT_TANH, omega0=3.0, omega=1.5,
+                                gradient=True)
+    for pos in perturbed(snap, 3, 0.1):
+        dsnap = dsnap._replace(positions=torch.as_tensor(np.ascontiguousarray(pos)).cuda())
+        state = update(dsnap, state)
+        torch.cuda.synchronize()
+        xi = state.xi.cpu().numpy().astype(np.float32).astype(np.float64).ravel()
+        if activation == "tanh":
+            want = 1.7 * oml.mlp_input_gradient(params, widths, xi, grid[0], grid[1])
+        else:
+            x = torch.tensor(xi, dtype=torch.float64, requires_grad=True)
+            h = (x - torch.tensor(grid[0])) * 2 / (torch.tensor(grid[1]) - torch.tensor(grid[0])) - 1
+            layers = oml.split_params(params, widths)
+            h = h.reshape(1, 2)
+            for l, (W, b) in enumerate(layers):
+                h = h @ torch.as_tensor(W) + torch.as_tensor(b)
+                if l + 1 < len(layers):
+                    h = torch.sin((3.0 if l == 0 else 1.5) * h)
+            (g,) = torch.autograd.grad(h.sum(), x)
+            want = 1.7 * g.numpy()
+        got = update.native.view("force").cpu().numpy()[:2]
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
