@@ -377,6 +377,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   if (method->kind == PSB_METHOD_ABF && !layout->need_momenta && !m.hist_only)
     return bail(fail(PSB_ERR_VALUE, "ABF needs momenta (layout.need_momenta)"));
   M.abf_fast = (method->kind == PSB_METHOD_ABF && (M.all_point || m.hist_only)) ? 1 : 0;  // histogram only: no J p pass
+  M.fm_mode = m.hist_only ? FM_HIST_ONLY : 0;
 
   // ---- unique atoms (CSR) and group overlaps ---------------------------------------------------
   {
@@ -1088,6 +1089,7 @@ psb_status psb_set_force_net(psb_handle* h, const psb_force_net* net, void* cuda
       M.fs = nullptr;
       M.fs_staged = 0;
     }
+    M.fm_mode = (M.fm_mode & FM_HIST_ONLY) | (M.nn ? FM_NET : 0) | (M.fs ? FM_SERIES : 0);
     // the step kernel reads the model from device memory; the copy is ordered after every step enqueued so far
     CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
   }
@@ -1149,6 +1151,7 @@ psb_status psb_set_force_series(psb_handle* h, const psb_force_series* ser, void
       M.nn = nullptr;
       M.nn_np = 0;
     }
+    M.fm_mode = (M.fm_mode & FM_HIST_ONLY) | (M.nn ? FM_NET : 0) | (M.fs ? FM_SERIES : 0);
     CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
   }
   return PSB_OK;

@@ -97,6 +97,8 @@ struct ForceSeries {
   __host__ __device__ const double* values() const { return reinterpret_cast<const double*>(this) + val_off; }
 };
 
+enum { FM_NET = 1, FM_SERIES = 2, FM_HIST_ONLY = 4 };
+
 struct StateDev {
   double* xi;        // (k)
   double* F;         // (k) generalized force dV/dxi
@@ -195,6 +197,8 @@ struct Model {
   const ForceNet* nn;         // ABF family: force network or nullptr (psb_set_force_net)
   int32_t nn_np;              // its parameter count when it fits the shared-memory staging area (NN_STAGE), else 0
   int32_t fs_staged;          // the force series block fits the staging area
+  int32_t fm_mode;            // FM_* bits: what abf_finish has to consider besides plain ABF (0 for ABF itself)
+  int32_t fm_pad;
   const ForceSeries* fs;      // SpectralABF: force series or nullptr (psb_set_force_series)
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
   double* bias_dense;         // (N,3) or nullptr

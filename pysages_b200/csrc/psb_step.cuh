@@ -630,29 +630,38 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   }
   PSB_CLK(13);
   const bool oob = f.oob != 0;
-  // funn.py:190,286-296: past the ABF-only stage the force comes from the network (restraints first)
-  const bool use_net = M.nn != nullptr && !((m.has_restraints || m.hist_only) && oob) &&
-                       sh.pre.ncalls + 1 > sh.nnh.predict_after;
-  double f_net = use_net ? force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0],
-                                          sh.nnh.gradient ? &sh.nndact[0][0] : nullptr, lane)
-                         : 0.0;
-  // spectral_abf.py:186,245-266: series gradient past fit_threshold; outside the grid restraints or nothing
-  const ForceSeries* ser = M.fs == nullptr ? nullptr : (M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.nnh) : M.fs);
-  const bool zero_oob = ser != nullptr && ser->oob_zero && oob && !m.has_restraints;
-  const bool use_series = ser != nullptr && !oob && sh.pre.ncalls + 1 > ser->predict_after;
-  if (use_series) f_net = force_series_eval(ser, m, f.xi, &sh.nnbuf[0][0], lane);
+  // Force model, if the handle has one (Model::fm_mode: plain ABF pays one shared-memory load here; kept out of line).
+  //   network (funn.py:190,286-296; cff.py:328-332): past predict_after, restraints first;
+  //   network gradient, histogram-only variant (ann.py:240-256): inside the grid past predict_after, else zero;
+  //   series (spectral_abf.py:186,245-266): past fit_threshold inside the grid; outside restraints or nothing.
+  const int fm = M.fm_mode;
+  const bool hist_only = (fm & FM_HIST_ONLY) != 0;
+  bool use_model = false, zero_force = hist_only;
+  double f_model = 0.0;
+  if (fm != 0) {
+    const long long ncalls = sh.pre.ncalls + 1;
+    if (fm & FM_NET) {
+      use_model = !((m.has_restraints || hist_only) && oob) && ncalls > sh.nnh.predict_after;
+      if (use_model)
+        f_model = force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0],
+                                 sh.nnh.gradient ? &sh.nndact[0][0] : nullptr, lane);
+    } else if (fm & FM_SERIES) {
+      const ForceSeries* ser = M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.nnh) : M.fs;
+      zero_force = ser->oob_zero && oob && !m.has_restraints;
+      use_model = !oob && ncalls > ser->predict_after;
+      if (use_model) f_model = force_series_eval(ser, m, f.xi, &sh.nnbuf[0][0], lane);
+    }
+  }
   if (lane < k) {
     const int c = lane;
     const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
     double fs = f.Fsum_old[c];
-    if (!oob && !m.hist_only) {
+    if (!oob && !hist_only) {
       const double dWp_dt = (1.5 * Wp_now - 2.0 * Wp_1 + 0.5 * sh.pre.Wp_[c]) / S.dt;
       fs += m.force_unit_factor * dWp_dt + sh.pre.force[c];
     }
-    // ann.py:250-256: the histogram-only variant knows the network gradient or no force at all
-    const double fc = m.hist_only ? (use_net ? f_net : 0.0)
-                      : (m.has_restraints && oob) ? f.rforce[c]
-                      : (zero_oob ? 0.0 : ((use_net || use_series) ? f_net : fs / f.den));
+    const double fc = use_model ? f_model
+                      : (zero_force ? 0.0 : ((m.has_restraints && oob) ? f.rforce[c] : fs / f.den));
     f.F[c] = fc;
     f.Fsum_new[c] = fs;
     if (cta0 && !M.ll_reduce) {  // scalars nobody reads after the first barrier (LL exchange: stored at the end)
@@ -739,7 +748,7 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
         __syncwarp();
         pair_sync(1);
       }
-      if (m.hist_only) {  // ann.py:153-167: no momenta, no W p
+      if (M.fm_mode & FM_HIST_ONLY) {  // ann.py:153-167: no momenta, no W p
         if (lane < MAXK) f.Wp[lane] = 0.0;
         abf_finish(M, S, sh, lane, cta0, !GENERAL, true);
         break;
