@@ -831,3 +831,22 @@ def test_force_net_gradient_mode_against_oracle(activation):
             want = 1.7 * g.numpy()
         got = update.native.view("force").cpu().numpy()[:2]
         np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("nblocks", [2, 3, 7, 37, 96, 148])
+def test_pass_a_exchange_grid_sizes(nblocks, monkeypatch, launch_shape):
+    """The flagged-word exchange over grids from 2 CTAs to one CTA per SM: group-aligned splits with 1 ... 74
+    CTAs per group (more than the 48 entries one polling round covers), ABF with restraints against the oracle."""
+    if launch_shape != "auto":
+        pytest.skip("sets its own launch shape")
+    monkeypatch.setenv("PSB_GRID_BLOCKS", str(nblocks))
+    snap = snapshot("hoomd", np.float32, n=40000, seed=5)
+    h = 20000
+    cvs = [("Distance", ([list(range(0, h)), list(range(h, 2 * h))],), {})]
+    kw = dict(grid=((0.0,), (30.0,), (16,), "regular"), N=2, restraints=((0.0,), (30.0,), (5.0,), (5.0,)))
+    run = ParityRun(snap, cvs, ("ABF", kw))
+    info = run.native.launch_info()
+    assert info["grid_blocks"] == nblocks
+    for pos in perturbed(snap, 3, 0.05):
+        run.step(pos, check=False)
+        run.check(jacobian=False)  # the dense (1, 3N) Jacobian compare is covered elsewhere; keep this one fast
