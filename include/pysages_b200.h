@@ -118,7 +118,8 @@ typedef enum {
 typedef struct {
   int32_t kind; /* psb_method_kind */
   int32_t variant; /* PSB_METHOD_ABF only: 0 = ABF / FUNN / SpectralABF; 1 = histogram only (ANN, methods/ann.py:153-167:
-                      no momenta, no force sums; the force is the network gradient or zero) */
+                      no momenta, no force sums; the force is the network gradient or zero); 2 = ABF plus the second
+                      histogram `histp` of CFF (methods/cff.py:236-239), reset by the host at every training step */
   /* HarmonicBias: harmonic_bias.py:78-107 canonical (k x k) spring matrix, row-major; center (k) */
   double kspring[PSB_MAX_K * PSB_MAX_K];
   double center[PSB_MAX_K];

@@ -717,3 +717,140 @@ class ANN(SamplingMethod):
             return ANNState(xi, bias, hist, phi, prob, nn, ncalls)
 
         return snapshot, initialize, generalize(update, helpers)
+
+
+# --------------------------------------------------------------------------- #
+# CFF (cff.py:109-350)
+# --------------------------------------------------------------------------- #
+
+
+class CFFState(NamedTuple):  # cff.py:36-98
+    xi: Any
+    bias: Any
+    hist: Any
+    histp: Any
+    prob: Any
+    fe: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    nn: Any
+    fnn: Any
+    ncalls: int = 0
+
+
+class CFF(ABF):
+    """cff.py:109-350: ABF accumulation plus a second histogram; every train_freq calls an energy network is
+    fitted (Sobolev loss) to the frequency-based free energy and the binned mean force, a force network to the
+    mean force; past train_freq calls the bias force is fnn.std * fmodel(f32(xi)) + fnn.mean."""
+
+    def __init__(self, cvs, grid, topology, kT, **kwargs):
+        super().__init__(cvs, grid, **kwargs)
+        from . import ml
+
+        self.topology = tuple(topology)
+        self.kT = kT
+        self.train_freq = kwargs.get("train_freq", 5000)
+        dims = grid.shape.size
+        self.widths = ml.layer_sizes(dims, self.topology, 1)
+        self.fwidths = ml.layer_sizes(dims, self.topology, dims)
+        seed = kwargs.get("seed", 0)
+        self.initial_params = ml.init_params(self.widths, seed)
+        self.initial_fparams = ml.init_params(self.fwidths, seed)
+        self.reg = kwargs.get("reg", 1e-4)  # cff.py:163
+        self.max_iters = kwargs.get("max_iters", 1000)  # cff.py:164
+        self.fmax_iters = kwargs.get("fmax_iters", 500)  # cff.py:165 (LevenbergMarquardt default)
+
+    def build(self, snapshot, helpers):
+        from . import ml
+
+        cv, grid, kT = self.cv, self.grid, self.kT
+        dt = snapshot.dt
+        dims = grid.shape.size
+        gshape = tuple(int(s) for s in grid.shape)
+        shape = gshape if dims > 1 else (*gshape, 1)
+        natoms = _natoms(snapshot)
+        tsolve = linear_solver(self.use_pinv)
+        get_grid_index = grids.build_indexer(grid)
+        N = int(self.N)
+        restraints = self.restraints
+        train_freq = self.train_freq
+        lower, upper = np.asarray(grid.lower, dtype=np.float64), np.asarray(grid.upper, dtype=np.float64)
+        inputs = grids.compute_mesh(grid).astype(np.float32).astype(np.float64)  # cff.py:263: f32(compute_mesh)
+        kernel = ml.blackman_kernel(dims, 7).astype(np.float32).astype(np.float64)
+        padding = "wrap" if grid.is_periodic else "edge"
+        f32 = lambda a: np.asarray(a).astype(np.float32).astype(np.float64)
+        query, dimensionality, to_force_units = helpers
+
+        def vsmooth(y):  # vmap(conv)(y.T).T
+            return np.stack([ml.convolve(y[..., c], kernel, padding) for c in range(y.shape[-1])], axis=-1)
+
+        def smooth(y):
+            return ml.convolve(y, kernel, padding) if dims > 1 else vsmooth(y)
+
+        def learn(state):  # cff.py:295-307
+            histp = state.histp.numpy().astype(np.float64).reshape(shape)
+            prob = state.prob + histp * np.exp(state.fe / kT)
+            fe = kT * np.log(np.maximum(1, prob))
+            hist = state.hist.numpy().astype(np.float64).reshape(*gshape, 1)
+            force = state.Fsum.numpy() / np.maximum(1, hist)
+            # preprocess, cff.py:280-286
+            axes = tuple(range(force.ndim - 1))
+            dy, dy_mean, dy_std = ml.normalize(force, axes=axes)
+            s = max(fe.std(), dy_std.max())
+            y = smooth(f32(fe / s))
+            dy = vsmooth(f32(dy * dy_std / s))
+            params = ml.lm_fit_sobolev(state.nn.params, self.widths, inputs, y, dy, lower, upper, reg=self.reg,
+                                       max_iters=self.max_iters)
+            fparams = ml.lm_fit(state.fnn.params, self.fwidths, inputs, dy, lower, upper, reg=self.reg,
+                                max_iters=self.fmax_iters)
+            nn, fnn = ml.NNData(params, state.nn.mean, s), ml.NNData(fparams, dy_mean, s)
+            fe = nn.std * ml.mlp_apply(params, self.widths, inputs, lower, upper).reshape(fe.shape)
+            return torch.zeros_like(state.histp), prob, fe - fe.min(), nn, fnn
+
+        def estimate_force(xi, I_xi, Fsum, hist, fnn, pred):  # cff.py:315-350
+            ob = any(int(i) == s for i, s in zip(I_xi, gshape))
+            if restraints is not None and ob:
+                lo, hi, kl, kh = restraints
+                return apply_restraints(lo, hi, kl, kh, xi.reshape(dims).to(F64))
+            if pred:
+                x = xi.detach().numpy().astype(np.float32).astype(np.float64)
+                out = ml.mlp_apply(fnn.params, self.fwidths, x, lower, upper).reshape(dims)
+                return torch.as_tensor(fnn.std * out + fnn.mean)
+            return _gather(Fsum, I_xi) / max(N, int(_gather(hist, I_xi)))
+
+        def initialize():  # cff.py:197-217
+            xi, _ = cv(query(snapshot))
+            bias = torch.zeros((natoms, dimensionality()), dtype=F64)
+            hist = torch.zeros(gshape, dtype=torch.int64)
+            histp = torch.zeros(gshape, dtype=torch.int64)
+            Fsum = torch.zeros((*gshape, dims), dtype=F64)
+            z = torch.zeros(dims, dtype=F64)
+            nn = ml.NNData(np.asarray(self.initial_params, dtype=np.float64), 0.0, 1.0)
+            fnn = ml.NNData(np.asarray(self.initial_fparams, dtype=np.float64), np.zeros(dims), 1.0)
+            return CFFState(xi, bias, hist, histp, np.zeros(shape), np.zeros(shape), Fsum, z, z.clone(), z.clone(),
+                            nn, fnn)
+
+        def update(state, data):  # cff.py:223-244
+            ncalls = state.ncalls + 1
+            in_training_regime = ncalls > train_freq
+            in_training_step = in_training_regime and (ncalls % train_freq == 1)
+            if in_training_step:
+                histp, prob, fe, nn, fnn = learn(state)
+            else:
+                histp, prob, fe, nn, fnn = state.histp, state.prob, state.fe, state.nn, state.fnn
+            xi, Jxi = cv(data)
+            p = torch.as_tensor(data.momenta)
+            Jd = Jxi.to(F64) if (Jxi.dtype == F64 or p.dtype == F64) else Jxi
+            Wp = tsolve(Jd, p.to(Jd.dtype)).to(F64)
+            dWp_dt = (1.5 * Wp - 2.0 * state.Wp + 0.5 * state.Wp_) / dt
+            I_xi = get_grid_index(xi.detach().numpy())
+            hist = _scatter_add(state.hist, I_xi, 1)
+            Fsum = _scatter_add(state.Fsum, I_xi, to_force_units(dWp_dt) + state.force)
+            histp = _scatter_add(histp, I_xi, 1)
+            force = estimate_force(xi, I_xi, Fsum, hist, fnn, in_training_regime).reshape(dims)
+            bias = (-Jxi.T.to(F64) @ force).reshape(state.bias.shape)
+            return CFFState(xi, bias, hist, histp, prob, fe, Fsum, force, Wp, state.Wp, nn, fnn, ncalls)
+
+        return snapshot, initialize, generalize(update, helpers)

@@ -213,3 +213,80 @@ def mlp_input_gradient(ps, widths, x, lower, upper):
         if l > 0:
             delta = delta * (1.0 - acts[l - 1] ** 2)
     return (delta * 2 / (np.asarray(upper, dtype=np.float64) - np.asarray(lower, dtype=np.float64))).reshape(-1)
+
+
+# ---- Sobolev-loss Levenberg-Marquardt (CFF, cff.py:164 `LevenbergMarquardt(loss=Sobolev1SSE(), ...)`) ------
+
+def _torch_mlp(p, widths, x, lower, upper):
+    import torch
+
+    h = (x - torch.as_tensor(lower)) * 2 / (torch.as_tensor(upper) - torch.as_tensor(lower)) - 1
+    o = 0
+    n = len(widths) - 1
+    for l, (a, b) in enumerate(zip(widths[:-1], widths[1:])):
+        W = p[o:o + a * b].reshape(a, b)
+        o += a * b
+        h = h @ W + p[o:o + b]
+        o += b
+        if l + 1 < n:
+            h = torch.tanh(h)
+    return h
+
+
+def lm_fit_sobolev(ps, widths, x, y, dy, lower, upper, reg=1e-4, max_iters=1000, params=LMParams, history=None):
+    """ml/optimizers.py:188-232 with ml/objectives.py's Sobolev1SSE pieces: errors (e, ge) of the values and of
+    the input-gradients (both float32), cost (|e|^2 + |ge|^2 + r |p|^2) / 2, damped Hessian J^T J + gJ^T gJ +
+    (r + mu) I, J^T e + gJ^T ge + r p.  Derivatives by torch autograd (reverse over reverse)."""
+    import torch
+
+    xt = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    yt, dyt = torch.as_tensor(np.asarray(y, dtype=np.float64)), torch.as_tensor(np.asarray(dy, dtype=np.float64))
+
+    def grads(p, create_graph):
+        xx = xt.clone().requires_grad_(True)
+        out = _torch_mlp(p, widths, xx, lower, upper).sum()
+        (g,) = torch.autograd.grad(out, xx, create_graph=create_graph)
+        return g
+
+    def error(p_np):
+        p = torch.as_tensor(p_np)
+        e = (_torch_mlp(p, widths, xt, lower, upper).reshape(yt.shape) - yt).to(torch.float32).flatten().to(torch.float64)
+        ge = (grads(p, False).reshape(dyt.shape) - dyt).to(torch.float32).flatten().to(torch.float64)
+        return torch.cat([e, ge]).numpy()
+
+    def jacobians(p_np):
+        J = mlp_jacobian(p_np, widths, x, lower, upper)
+        p = torch.as_tensor(p_np).clone().requires_grad_(True)
+        gJ = torch.autograd.functional.jacobian(lambda q: grads(q, True).reshape(-1), p)
+        return np.vstack([J, gJ.numpy()])
+
+    def cost(e, p):
+        return (np.sum(e * e) + reg * np.sum(p * p)) / 2
+
+    c = F32(params.mu_c)
+    p_, C_, mu = np.asarray(ps, dtype=np.float64), np.inf, F32(params.mu_0)
+    e_ = error(p_)
+    iters, improved = 0, True
+    while improved and iters < max_iters and mu < params.mu_max:
+        mu = F32(mu)
+        J = jacobians(p_)
+        H = J.T @ J
+        H[np.diag_indices_from(H)] += float(F32(reg) + mu)
+        Je = J.T @ e_ + reg * p_
+        dp = scipy.linalg.solve(H, Je, assume_a="pos")
+        p = p_ - dp
+        e = error(p)
+        C = cost(e, p)
+        rho = (C_ - C) / (dp @ (float(mu) * dp + Je))
+        if rho > params.rho_c:
+            mu = max(F32(mu / c), F32(params.mu_min))
+        bad = bool(rho < params.rho_min) or bool(np.any(np.isnan(p)))
+        if bad:
+            mu = min(F32(c * mu), F32(params.mu_max))
+            p, e, C = p_, e_, C_
+        improved = bool(C_ > C) or bad
+        iters += 0 if bad else 1
+        p_, e_, C_ = p, e, C
+        if history is not None:
+            history.append((p_.copy(), float(C_), float(mu)))
+    return p_

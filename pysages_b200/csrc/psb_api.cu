@@ -364,7 +364,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   m.abf_N = method->abf_N;
   m.use_pinv = method->use_pinv;
   m.has_restraints = method->has_restraints;
-  if (method->variant != 0 && !(method->kind == PSB_METHOD_ABF && method->variant == 1))
+  if (method->variant != 0 && !(method->kind == PSB_METHOD_ABF && (method->variant == 1 || method->variant == 2)))
     return bail(fail(PSB_ERR_VALUE, "unknown method variant %d", method->variant));
   m.hist_only = method->kind == PSB_METHOD_ABF && method->variant == 1;
   m.force_unit_factor = method->force_unit_factor == 0.0 ? 1.0 : method->force_unit_factor;
@@ -527,6 +527,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       if ((st = dev_alloc(h, &s.force, MAXK)) != PSB_OK) return bail(st);
       if ((st = dev_alloc(h, &s.Wp, MAXK)) != PSB_OK) return bail(st);
       if ((st = dev_alloc(h, &s.Wp_, MAXK)) != PSB_OK) return bail(st);
+      if (method->variant == 2 && (st = dev_alloc(h, &s.histp, (size_t)m.grid_points)) != PSB_OK) return bail(st);
     }
     if ((st = dev_alloc(h, &M.fin, 1)) != PSB_OK) return bail(st);
     if ((st = dev_alloc(h, &M.bars, NBARS)) != PSB_OK) return bail(st);
@@ -855,6 +856,7 @@ psb_status psb_state_info(psb_handle* h, const char* field, int64_t* nbytes, int
   else if (f == "grid_gradient") { p = s.gg; n = 8 * G * k; }
   else if (f == "idx") { p = s.idx; n = 8; code = 1; }
   else if (f == "hist") { p = s.hist; n = 4 * G; code = 2; }
+  else if (f == "histp") { p = s.histp; n = 4 * G; code = 2; }
   else if (f == "Fsum") { p = s.Fsum; n = 8 * G * k; }
   else if (f == "force") { p = s.force; n = 8 * k; }
   else if (f == "Wp") { p = s.Wp; n = 8 * k; }

@@ -113,6 +113,7 @@ struct StateDev {
   long long* idx;    // (1)
   // ABF
   uint32_t* hist;    // (G)
+  uint32_t* histp;   // (G) CFF: visits since the last training step (cff.py:239), or nullptr
   double* Fsum;      // (G, k)
   double* force;     // (k)
   double* Wp;        // (k)

@@ -1797,6 +1797,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       if (f.in_range) {
         M.st.hist[f.flat] = f.hist_new;
         for (int c = 0; c < k; ++c) M.st.Fsum[f.flat * k + c] = f.Fsum_new[c];
+        if (M.st.histp) M.st.histp[f.flat] += 1u;  // cff.py:239 (nobody else touches it inside a launch)
       }
       if (ll)  // deferred from abf_finish
         for (int c = 0; c < k; ++c) {

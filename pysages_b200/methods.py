@@ -808,6 +808,148 @@ class ANN(NNSamplingMethod):
         return snapshot, initialize, update
 
 
+class CFFState(NamedTuple):  # cff.py:36-98
+    xi: Any
+    bias: Any
+    hist: Any
+    histp: Any
+    prob: Any
+    fe: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    nn: Any
+    fnn: Any
+    ncalls: int = 0
+
+
+class CFF(NNSamplingMethod):
+    """
+    methods/cff.py:109-350.  Every step is the fused ABF step plus a second histogram (`variant = 2`); past
+    `train_freq` calls the kernel takes the force from the force network (psb_set_force_net, cff.py:328-332).
+    Every `train_freq` calls, on the method's device (cff.py:249-313): frequency-based free energy
+    `kT log(max(1, prob))`, binned mean force, normalisation, Blackman smoothing, an energy network fitted with
+    the Sobolev loss (values and input-gradients) and a force network fitted to the mean force.
+    """
+
+    snapshot_flags = {"positions", "indices", "momenta"}
+    _kind = N.METHOD_ABF
+
+    def __init__(self, cvs, grid, topology, kT, **kwargs):
+        from numbers import Real
+
+        from . import ml
+
+        assert isinstance(kT, Real)  # cff.py:151
+        super().__init__(cvs, grid, topology, **kwargs)
+        self.kT = kT
+        self.N = np.asarray(self.kwargs.get("N", 500))
+        self.train_freq = self.kwargs.get("train_freq", 5000)
+        dims = grid.shape.size
+        seed = self.kwargs.get("seed", 0)
+        reg = ml.L2Regularization(1e-4)
+        self.model = ml.MLP(dims, 1, topology, grid.lower, grid.upper, seed=seed)
+        self.fmodel = ml.MLP(dims, dims, topology, grid.lower, grid.upper, seed=seed)
+        self.optimizer = self.kwargs.get("optimizer", ml.LevenbergMarquardt(loss=ml.Sobolev1SSE(), reg=reg, max_iters=1000))
+        self.foptimizer = self.kwargs.get("foptimizer", ml.LevenbergMarquardt(reg=reg))
+        self.use_pinv = self.kwargs.get("use_pinv", False)
+
+    def describe(self, helpers):
+        d = ABF.describe(self, helpers)
+        d.variant = 2  # ABF + histp
+        return d
+
+    def build(self, snapshot, helpers, *args, **kwargs):
+        from . import ml
+        from .grids import compute_mesh
+
+        native = NativeStep(self, snapshot, helpers, dense_outputs=self.dense_bias)
+        self.native = native
+        grid, model, fmodel = self.grid, self.model, self.fmodel
+        train_freq, kT = int(self.train_freq), float(self.kT)
+        k = native.k
+        gshape = tuple(int(s) for s in grid.shape)
+        shape = gshape if k > 1 else (*gshape, 1)
+        dev = native.device
+        f32 = lambda t: t.to(torch.float32).to(torch.float64)
+        inputs = f32(torch.as_tensor(compute_mesh(grid), dtype=torch.float64, device=dev))  # cff.py:263
+        kernel = ml.blackman_kernel(k, 7).astype(np.float32).astype(np.float64)
+        padding = "wrap" if grid.is_periodic else "edge"
+        fit = ml.build_fitting_function(model, self.optimizer)
+        ffit = ml.build_fitting_function(fmodel, self.foptimizer)
+        one = lambda v: torch.tensor(float(v), dtype=torch.float64, device=dev)
+        holder = dict(
+            nn=ml.NNData(torch.as_tensor(model.parameters, device=dev), one(0.0), one(1.0)),
+            fnn=ml.NNData(torch.as_tensor(fmodel.parameters, device=dev), torch.zeros(k, dtype=torch.float64, device=dev), one(1.0)),
+            prob=torch.zeros(shape, dtype=torch.float64, device=dev),
+            fe=torch.zeros(shape, dtype=torch.float64, device=dev),
+        )
+
+        def push(fnn):
+            native.set_force_net(fmodel.widths, fnn.params, fnn.mean, fnn.std.reshape(1), predict_after=train_freq)
+
+        def vsmooth(y):
+            return ml.smooth(y, kernel, padding)
+
+        def smooth(y):
+            return ml.convolve(y, kernel, padding) if k > 1 else vsmooth(y)
+
+        def learn():  # cff.py:280-307 on the state as it is before this step's sample is added
+            histp = native.view("histp", gshape)
+            prob = holder["prob"] + histp.to(torch.float64).reshape(shape) * torch.exp(holder["fe"] / kT)
+            fe = kT * torch.log(torch.clamp(prob, min=1.0))
+            hist = native.view("hist", gshape).to(torch.float64).unsqueeze(-1)
+            force = native.view("Fsum", (*gshape, k)) / torch.clamp(hist, min=1.0)
+            axes = tuple(range(force.ndim - 1))
+            dy, dy_mean, dy_std = ml.normalize(force, axes=axes)
+            s = torch.maximum(fe.std(unbiased=False), dy_std.max())
+            y = smooth(f32(fe / s))
+            dy = vsmooth(f32(dy * dy_std / s))
+            params = fit(holder["nn"].params, inputs, (y, dy))
+            fparams = ffit(holder["fnn"].params, inputs, dy)
+            nn, fnn = ml.NNData(params, holder["nn"].mean, s), ml.NNData(fparams, dy_mean, s)
+            fe = nn.std * model.apply(params, inputs).reshape(fe.shape)
+            holder.update(nn=nn, fnn=fnn, prob=prob, fe=fe - fe.min())
+            histp.zero_()
+
+        def make_state():
+            bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+            return CFFState(
+                native.view("xi", (1, k)), bias, native.view("hist", gshape), native.view("histp", gshape), holder["prob"],
+                holder["fe"], native.view("Fsum", (*gshape, k)), native.view("force")[:k], native.view("Wp")[:k],
+                native.view("Wp_")[:k], holder["nn"], holder["fnn"], native.ncalls,
+            )
+
+        def initialize():
+            native.evaluate(snapshot)
+            push(holder["fnn"])  # untrained network: not used before the first fit (cff.py:226-228)
+            return make_state()
+
+        def update(snapshot, state, timestep=0):
+            ncalls = native.ncalls + 1
+            if ncalls > train_freq and ncalls % train_freq == 1:
+                learn()
+                push(holder["fnn"])
+            native.step(snapshot, timestep)
+            return make_state()
+
+        def restore(prev):
+            to_t = lambda v: torch.as_tensor(np.asarray(v.cpu() if hasattr(v, "cpu") else v), dtype=torch.float64,
+                                             device=dev)
+            for name in ("xi", "hist", "histp", "Fsum", "force", "Wp", "Wp_", "ncalls"):
+                value = getattr(prev, name)
+                native.set_state(name, value.cpu().numpy() if hasattr(value, "cpu") else value)
+            holder.update(prob=to_t(prev.prob).reshape(shape), fe=to_t(prev.fe).reshape(shape),
+                          nn=ml.NNData(*(to_t(t) for t in prev.nn)), fnn=ml.NNData(*(to_t(t) for t in prev.fnn)))
+            push(holder["fnn"])
+            return make_state()
+
+        update.native = native
+        update.restore = restore
+        return snapshot, initialize, update
+
+
 class SpectralABFState(NamedTuple):  # spectral_abf.py:36-84
     xi: Any
     bias: Any

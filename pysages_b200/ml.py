@@ -45,9 +45,18 @@ class LevenbergMarquardtParams(NamedTuple):  # ml/optimizers.py:40-51
     rho_min: float = 1e-4
 
 
+class SSE:  # ml/objectives.py: sum of squared errors
+    pass
+
+
+class Sobolev1SSE:  # ml/objectives.py: squared errors of the values AND of the input-gradients
+    pass
+
+
 @dataclass
 class LevenbergMarquardt:  # ml/optimizers.py:121-131
     params: LevenbergMarquardtParams = LevenbergMarquardtParams()
+    loss: object = field(default_factory=SSE)
     reg: L2Regularization = L2Regularization(0.0)
     max_iters: int = 500
 
@@ -171,12 +180,31 @@ def build_fitting_function(model, optimizer):
     r = float(optimizer.reg.coeff)
     f32 = np.float32
 
+    sobolev = isinstance(optimizer.loss, Sobolev1SSE)
+
+    def input_gradients(p, x):
+        """d (sum of outputs) / d x for every point: (n, indim) -- functional, so that forward-mode
+        differentiation with respect to p can run through it."""
+        point = lambda q, xi: model.apply(q, xi[None]).sum()
+        return torch.func.vmap(torch.func.grad(point, argnums=1), in_dims=(None, 0))(p, x)
+
     def error(p, x, y, with_jacobian=False):
+        """objectives.py build_error_function: float32 residuals; Sobolev: (values, input-gradients) stacked."""
+        x = x.to(F64)
+        ref = y
+        if sobolev:
+            ref, dref = y
         if with_jacobian:
             pred, J = model.apply(p, x, True)
         else:
             pred, J = model.apply(p, x), None
-        e = (pred.reshape(y.shape) - y).to(torch.float32).flatten().to(F64)  # objectives.py: float32 residuals
+        e = (pred.reshape(ref.shape) - ref).to(torch.float32).flatten().to(F64)
+        if sobolev:
+            ge = (input_gradients(p, x).reshape(dref.shape) - dref).to(torch.float32).flatten().to(F64)
+            e = torch.cat([e, ge])
+            if with_jacobian:  # forward-over-reverse: one tangent per parameter
+                gJ = torch.func.jacfwd(lambda q: input_gradients(q, x).reshape(-1))(p)
+                J = torch.cat([J, gJ], dim=0)
         return (e, J) if with_jacobian else e
 
     def cost(e, p):

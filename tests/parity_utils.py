@@ -52,6 +52,13 @@ def make_method(which, spec, cvs):
         return mod.Metadynamics(cvs, *args, kwargs.pop("deltaT", None), **kwargs)
     if name == "ABF":
         return mod.ABF(cvs, kwargs.pop("grid"), **kwargs)
+    if name == "CFF":
+        if which != "oracle":
+            from pysages_b200 import ml
+            reg = ml.L2Regularization(1e-4)
+            kwargs["optimizer"] = ml.LevenbergMarquardt(loss=ml.Sobolev1SSE(), reg=reg, max_iters=kwargs.pop("max_iters", 1000))
+            kwargs["foptimizer"] = ml.LevenbergMarquardt(reg=reg, max_iters=kwargs.pop("fmax_iters", 500))
+        return mod.CFF(cvs, kwargs.pop("grid"), kwargs.pop("topology"), kwargs.pop("kT"), **kwargs)
     if name == "ANN":
         if which != "oracle" and "max_iters" in kwargs:
             from pysages_b200 import ml

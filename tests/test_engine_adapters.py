@@ -252,3 +252,34 @@ def test_ann_run_save_load_restart_and_analyze(tmp_path):
     assert out["free_energy"].shape == (8, 8) and out["free_energy"].min() == 0.0
     fes = out["fes_fn"](out["mesh"])
     assert fes.shape == (64, 1) and fes.min() == 0.0 and np.all(np.isfinite(fes))
+
+
+def test_cff_run_save_load_restart(tmp_path):
+    """CFF through `pysages_b200.run`: 9 steps with train_freq = 2, checkpoint after 5, resume == uninterrupted
+    (both networks, prob, fe and histp travel with the state)."""
+    from pysages_b200 import ml
+
+    snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=9, step=0.05)
+
+    def make_method():
+        cvs = [ps.colvars.Distance([G1, G2]), ps.colvars.Component([5, 6, 7], 1)]
+        reg = ml.L2Regularization(1e-4)
+        return ps.methods.CFF(cvs, ps.Grid((0.0, -6.0), (12.0, 6.0), (6, 6)), (4,), 1.0e4, N=2, train_freq=2,
+                              optimizer=ml.LevenbergMarquardt(loss=ml.Sobolev1SSE(), reg=reg, max_iters=2),
+                              foptimizer=ml.LevenbergMarquardt(reg=reg, max_iters=2))
+
+    full = ps.run(make_method(), lambda **kw: _mock(snap, traj), 9)
+    part = ps.run(make_method(), lambda **kw: _mock(snap, traj), 5)
+    ps.save(part, tmp_path / "cff.pkl")
+    resumed = ps.run(ps.load(tmp_path / "cff.pkl"), lambda first=0, **kw: _mock(snap, traj, first), 4,
+                     context_args=dict(first=5))
+    torch.cuda.synchronize()
+    a, b = resumed.states[0], full.states[0]
+    for name in ("xi", "hist", "histp", "prob", "fe", "Fsum", "force", "Wp", "Wp_"):
+        np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=name)
+    for net in ("nn", "fnn"):
+        np.testing.assert_array_equal(getattr(a, net).params.cpu().numpy(), getattr(b, net).params.cpu().numpy())
+    assert int(a.ncalls) == int(b.ncalls) == 9
+    out = ps.analyze(full)
+    assert out["histogram"].sum() == 9 - 0 and out["mean_force"].shape == (6, 6, 2)

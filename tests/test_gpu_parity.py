@@ -850,3 +850,43 @@ def test_pass_a_exchange_grid_sizes(nblocks, monkeypatch, launch_shape):
     for pos in perturbed(snap, 3, 0.05):
         run.step(pos, check=False)
         run.check(jacobian=False)  # the dense (1, 3N) Jacobian compare is covered elsewhere; keep this one fast
+
+
+# ---- CFF: ABF + second histogram + force network; Sobolev-loss energy network (cff.py:109-350) -------------
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float64), ("hoomd", np.float32), ("lammps", np.float64)])
+@pytest.mark.parametrize("restraints", [None, ((0.0, 0.0), (8.0, 8.0), (20.0, 20.0), (20.0, 20.0))])
+def test_cff_network_force(layout, dtype, restraints):
+    """train_freq = 2, both Levenberg-Marquardt fits capped at 0 iterations (same weights on both sides): the
+    per-step kernel path (ABF + histp + force network with the scalar std and the per-component mean) and the
+    host pipeline of cff.py:280-307 (prob, fe, normalisation, float32 smoothing) against the oracle."""
+    snap = snapshot(layout, dtype)
+    # kT far above the synthetic mean-force scale: the untrained energy network times that scale must not
+    # overflow exp(fe / kT) (it does in the reference algorithm itself for a small kT)
+    kw = dict(grid=FUNN_GRID, topology=(6, 4), kT=1.0e4, N=2, train_freq=2, restraints=restraints, max_iters=0,
+              fmax_iters=0, seed=2)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("CFF", kw))
+    tol = max(1e-8, 10 * run.rtol)
+    for pos in perturbed(snap, 8, 0.1):
+        ours, ref = run.step(pos)
+        assert np.array_equal(ours.histp.cpu().numpy().astype(np.int64), ref.histp.numpy())
+        np.testing.assert_allclose(ours.prob.cpu().numpy(), ref.prob, rtol=tol)
+        np.testing.assert_allclose(ours.fe.cpu().numpy(), ref.fe, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(float(run.state.fnn.std), run.ostate.fnn.std, rtol=tol)
+    np.testing.assert_allclose(run.state.fnn.mean.cpu().numpy(), run.ostate.fnn.mean, rtol=tol, atol=1e-12)
+
+
+def test_cff_refit_tracks_oracle():
+    """Three Sobolev-loss LM iterations of the energy network and three SSE iterations of the force network on
+    the device (forward-over-reverse Jacobian) against the oracle's reverse-over-reverse autograd."""
+    snap = snapshot("hoomd", np.float64)
+    kw = dict(grid=((0.0, 0.0), (8.0, 8.0), (6, 6), "regular"), topology=(4,), kT=1.0e4, N=2, train_freq=3,
+              max_iters=3, fmax_iters=3, seed=6)
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("CFF", kw))
+    frames = perturbed(snap, 5, 0.1)
+    for pos in frames[:3]:
+        run.step(pos)
+    ours, ref = run.step(frames[3], check=False)  # call 4 = train_freq + 1: first fit
+    np.testing.assert_allclose(ours.nn.params.cpu().numpy(), ref.nn.params, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ours.fnn.params.cpu().numpy(), ref.fnn.params, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ours.force.cpu().numpy(), ref.force.numpy(), rtol=1e-4, atol=1e-8)
+    assert int(ours.histp.sum()) == 1  # reset at the fit, then this step's visit
