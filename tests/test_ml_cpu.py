@@ -118,3 +118,23 @@ def test_levenberg_marquardt_rejects_bad_steps():
     assert all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))  # monotone: rejected steps keep the cost
     mus = [mu for _, _, mu in hist]
     assert min(mus) >= 1e-8 * (1 - 1e-6) and max(mus) <= 1e8
+
+
+def test_sobolev_levenberg_marquardt_follows_oracle():
+    """cff.py:164: LevenbergMarquardt(loss=Sobolev1SSE()) -- values AND input-gradients are fitted.  The product
+    differentiates the input-gradients forward-over-reverse, the oracle reverse-over-reverse."""
+    m = pml.MLP(2, 1, (4,), LOWER, UPPER, seed=5)
+    g = np.stack(np.meshgrid(np.linspace(-0.9, 1.9, 6), np.linspace(0.6, 2.9, 5), indexing="ij"), -1).reshape(-1, 2)
+    u = oml.scale(g, LOWER, UPPER)
+    y = (np.sin(2 * u[:, 0]) * u[:, 1]).reshape(6, 5, 1)
+    dy = np.stack([2 * np.cos(2 * u[:, 0]) * u[:, 1] * 2 / 3.0, np.sin(2 * u[:, 0]) * 2 / 2.5], -1).reshape(6, 5, 2)
+    opt = pml.LevenbergMarquardt(loss=pml.Sobolev1SSE(), reg=pml.L2Regularization(1e-4), max_iters=12)
+    hp, ho = [], []
+    pml.build_fitting_function(m, opt)(torch.as_tensor(m.parameters), torch.as_tensor(g),
+                                       (torch.as_tensor(y), torch.as_tensor(dy)), history=hp)
+    oml.lm_fit_sobolev(m.parameters, m.widths, g, y, dy, LOWER, UPPER, reg=1e-4, max_iters=12, history=ho)
+    assert len(hp) == len(ho) >= 8
+    for (pp, cp, mp), (qo, co, mo) in list(zip(hp, ho))[:4]:
+        np.testing.assert_allclose(pp.numpy(), qo, rtol=1e-6, atol=1e-8)
+        assert mp == mo
+    assert hp[-1][1] < 0.05 * hp[0][1]  # and it fits: the cost drops by more than 20x
