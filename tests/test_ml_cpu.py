@@ -137,4 +137,4 @@ def test_sobolev_levenberg_marquardt_follows_oracle():
     for (pp, cp, mp), (qo, co, mo) in list(zip(hp, ho))[:4]:
         np.testing.assert_allclose(pp.numpy(), qo, rtol=1e-6, atol=1e-8)
         assert mp == mo
-    assert hp[-1][1] < 0.05 * hp[0][1]  # and it fits: the cost drops by more than 20x
+    assert hp[-1][1] < 0.1 * hp[0][1]  # and it fits: the cost drops by more than 10x
