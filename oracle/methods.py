@@ -854,3 +854,151 @@ class CFF(ABF):
             return CFFState(xi, bias, hist, histp, prob, fe, Fsum, force, Wp, state.Wp, nn, fnn, ncalls)
 
         return snapshot, initialize, generalize(update, helpers)
+
+
+# --------------------------------------------------------------------------- #
+# Sirens (sirens.py:95-420)
+# --------------------------------------------------------------------------- #
+
+
+class SirensState(NamedTuple):  # sirens.py:40-92
+    xi: Any
+    bias: Any
+    hist: Any
+    histp: Any
+    prob: Any
+    fe: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    nn: Any
+    ncalls: int = 0
+
+
+class Sirens(ABF):
+    """sirens.py:95-420: ABF accumulation (+ histp / prob / fe in mode "cff"); every train_freq calls a Siren
+    network of the free energy is fitted to the binned mean force (mode "abf": gradients loss) or to force and
+    frequency-based free energy (mode "cff": Sobolev loss); past train_freq calls the bias force is
+    nn.std * d net / d xi at f32(xi)."""
+
+    def __init__(self, cvs, grid, topology, **kwargs):
+        mode = kwargs.get("mode", "abf")
+        kT = kwargs.get("kT", None)
+        if mode not in ("abf", "cff"):
+            raise ValueError(f"Invalid mode {mode}. Possible values are 'abf' and 'cff'")
+        if mode == "cff" and kT is None:
+            raise KeyError("When running in 'cff' mode, a keyword argument `kT` in the same "
+                           "units as the backend internal energy units must be provided.")
+        super().__init__(cvs, grid, **kwargs)
+        from . import ml
+
+        self.mode, self.kT = mode, kT
+        self.topology = tuple(topology)
+        self.train_freq = kwargs.get("train_freq", 5000)
+        self.omega_0, self.omega = kwargs.get("omega_0", 16), kwargs.get("omega", 1)  # ml/models.py:95
+        self.widths = ml.layer_sizes(grid.shape.size, self.topology, 1)
+        self.initial_params = ml.init_siren_params(self.widths, self.omega, kwargs.get("seed", 0))
+        self.reg = kwargs.get("reg", 1e-4)
+        self.max_iters = kwargs.get("max_iters", 250)
+
+    def build(self, snapshot, helpers):
+        from . import ml
+
+        cv, grid, kT, mode = self.cv, self.grid, self.kT, self.mode
+        dt = snapshot.dt
+        dims = grid.shape.size
+        gshape = tuple(int(s) for s in grid.shape)
+        shape = gshape if dims > 1 else (*gshape, 1)
+        natoms = _natoms(snapshot)
+        tsolve = linear_solver(self.use_pinv)
+        get_grid_index = grids.build_indexer(grid)
+        N = int(self.N)
+        restraints = self.restraints
+        train_freq, widths = self.train_freq, self.widths
+        lower, upper = np.asarray(grid.lower, dtype=np.float64), np.asarray(grid.upper, dtype=np.float64)
+        f32 = lambda a: np.asarray(a).astype(np.float32).astype(np.float64)
+        inputs = f32(grids.compute_mesh(grid))
+        kernel = f32(ml.blackman_kernel(dims, 5))  # sirens.py:291
+        padding = "wrap" if grid.is_periodic else "edge"
+        net = dict(activation="sin", omega0=float(self.omega_0), omega=float(self.omega))
+        query, dimensionality, to_force_units = helpers
+
+        def vsmooth(y):
+            return np.stack([ml.convolve(y[..., c], kernel, padding) for c in range(y.shape[-1])], axis=-1)
+
+        def smooth(y):
+            return ml.convolve(y, kernel, padding) if dims > 1 else vsmooth(y)
+
+        def normalize_gradients(data):  # sirens.py:399-417
+            axes = tuple(range(data.ndim - 1))
+            if grid.is_periodic:
+                return data - data.mean(axis=axes), data.std(axis=axes).max()
+            return data, data.std(axis=axes).max()
+
+        def learn(state):  # sirens.py:340-347
+            hist = state.hist.numpy().astype(np.float64).reshape(*gshape, 1)
+            force = state.Fsum.numpy() / np.maximum(1, hist)
+            histp, prob, fe = state.histp, state.prob, state.fe
+            if mode == "cff":
+                prob = state.prob + state.histp.numpy().astype(np.float64).reshape(shape) * np.exp(state.fe / kT)
+                fe = kT * np.log(np.maximum(1, prob))
+                histp = torch.zeros_like(state.histp)
+                dy, dy_std = normalize_gradients(force)
+                s = max(fe.std(), dy_std)
+                params = ml.lm_fit_autograd(state.nn.params, widths, inputs, (smooth(f32(fe / s)), dy / s), "sobolev",
+                                            lower, upper, reg=self.reg, max_iters=self.max_iters, **net)
+            else:
+                dy, s = normalize_gradients(force)
+                params = ml.lm_fit_autograd(state.nn.params, widths, inputs, dy / s, "gradients", lower, upper,
+                                            reg=self.reg, max_iters=self.max_iters, **net)
+            nn = ml.NNData(params, state.nn.mean, s)
+            if mode == "cff":
+                fe = nn.std * ml.mlp_apply(params, widths, inputs, lower, upper, "sin", net["omega0"], net["omega"]
+                                           ).reshape(fe.shape)
+                fe = fe - fe.min()
+            return histp, prob, fe, nn
+
+        def estimate_force(xi, I_xi, Fsum, hist, nn, pred):  # sirens.py:350-396
+            ob = any(int(i) == s for i, s in zip(I_xi, gshape))
+            if restraints is not None and ob:
+                lo, hi, kl, kh = restraints
+                return apply_restraints(lo, hi, kl, kh, xi.reshape(dims).to(F64))
+            if pred:
+                x = xi.detach().numpy().astype(np.float32).astype(np.float64)
+                return torch.as_tensor(nn.std * ml.net_input_gradient(nn.params, widths, x, lower, upper, **net))
+            return _gather(Fsum, I_xi) / max(N, int(_gather(hist, I_xi)))
+
+        def initialize():  # sirens.py:229-251
+            xi, _ = cv(query(snapshot))
+            bias = torch.zeros((natoms, dimensionality()), dtype=F64)
+            hist = torch.zeros(gshape, dtype=torch.int64)
+            Fsum = torch.zeros((*gshape, dims), dtype=F64)
+            z = torch.zeros(dims, dtype=F64)
+            nn = ml.NNData(np.asarray(self.initial_params, dtype=np.float64), 0.0, 1.0)
+            if mode == "cff":
+                histp, prob, fe = torch.zeros(gshape, dtype=torch.int64), np.zeros(shape), np.zeros(shape)
+            else:
+                histp = prob = fe = None
+            return SirensState(xi, bias, hist, histp, prob, fe, Fsum, z, z.clone(), z.clone(), nn)
+
+        def update(state, data):  # sirens.py:253-275
+            ncalls = state.ncalls + 1
+            in_training_regime = ncalls > train_freq
+            in_training_step = in_training_regime and (ncalls % train_freq == 1)
+            histp, prob, fe, nn = learn(state) if in_training_step else (state.histp, state.prob, state.fe, state.nn)
+            xi, Jxi = cv(data)
+            p = torch.as_tensor(data.momenta)
+            Jd = Jxi.to(F64) if (Jxi.dtype == F64 or p.dtype == F64) else Jxi
+            Wp = tsolve(Jd, p.to(Jd.dtype)).to(F64)
+            dWp_dt = (1.5 * Wp - 2.0 * state.Wp + 0.5 * state.Wp_) / dt
+            I_xi = get_grid_index(xi.detach().numpy())
+            hist = _scatter_add(state.hist, I_xi, 1)
+            Fsum = _scatter_add(state.Fsum, I_xi, to_force_units(dWp_dt) + state.force)
+            if mode == "cff":
+                histp = _scatter_add(histp, I_xi, 1)
+            force = estimate_force(xi, I_xi, Fsum, hist, nn, in_training_regime).reshape(dims)
+            bias = (-Jxi.T.to(F64) @ force).reshape(state.bias.shape)
+            return SirensState(xi, bias, hist, histp, prob, fe, Fsum, force, Wp, state.Wp, nn, ncalls)
+
+        return snapshot, initialize, generalize(update, helpers)

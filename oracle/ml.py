@@ -217,7 +217,7 @@ def mlp_input_gradient(ps, widths, x, lower, upper):
 
 # ---- Sobolev-loss Levenberg-Marquardt (CFF, cff.py:164 `LevenbergMarquardt(loss=Sobolev1SSE(), ...)`) ------
 
-def _torch_mlp(p, widths, x, lower, upper):
+def _torch_mlp(p, widths, x, lower, upper, activation="tanh", omega0=1.0, omega=1.0):
     import torch
 
     h = (x - torch.as_tensor(lower)) * 2 / (torch.as_tensor(upper) - torch.as_tensor(lower)) - 1
@@ -229,8 +229,98 @@ def _torch_mlp(p, widths, x, lower, upper):
         h = h @ W + p[o:o + b]
         o += b
         if l + 1 < n:
-            h = torch.tanh(h)
+            h = torch.tanh(h) if activation == "tanh" else torch.sin((omega0 if l == 0 else omega) * h)
     return h
+
+
+def init_siren_params(widths, omega=1.0, seed=0):
+    """ml/models.py:113-147 + ml/utils.py:67-100: U(-1, 1) * scale; first layer 1 / fan_in, others
+    sqrt(6 / omega^2 / fan_in), biases sqrt(1 / fan_in) (different PRNG than the reference)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for l, (a, b) in enumerate(zip(widths[:-1], widths[1:])):
+        ws = 1.0 / a if l == 0 else np.sqrt(6.0 / omega**2 / a)
+        out.append((rng.uniform(-1.0, 1.0, (a, b)) * ws).ravel())
+        out.append(rng.uniform(-1.0, 1.0, b) * np.sqrt(1.0 / a))
+    return np.concatenate(out)
+
+
+def lm_fit_autograd(ps, widths, x, targets, loss, lower, upper, reg=1e-4, max_iters=250, activation="tanh",
+                    omega0=1.0, omega=1.0, params=LMParams, history=None):
+    """ml/optimizers.py:188-232 for the three losses of ml/objectives.py -- "sse" (values), "gradients"
+    (input-gradients, sirens.py:162 mode "abf") and "sobolev" (both) -- and either activation, every
+    derivative by torch autograd (reverse over reverse)."""
+    import torch
+
+    xt = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    if loss == "sobolev":
+        yt, dyt = (torch.as_tensor(np.asarray(t, dtype=np.float64)) for t in targets)
+    elif loss == "gradients":
+        yt, dyt = None, torch.as_tensor(np.asarray(targets, dtype=np.float64))
+    else:
+        yt, dyt = torch.as_tensor(np.asarray(targets, dtype=np.float64)), None
+    net = lambda p, xx: _torch_mlp(p, widths, xx, lower, upper, activation, omega0, omega)
+
+    def grads(p, create_graph):
+        xx = xt.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(net(p, xx).sum(), xx, create_graph=create_graph)
+        return g
+
+    def residuals(p, create_graph=False):
+        parts = []
+        if yt is not None:
+            parts.append((net(p, xt).reshape(yt.shape) - yt).flatten())
+        if dyt is not None:
+            parts.append((grads(p, create_graph).reshape(dyt.shape) - dyt).flatten())
+        return torch.cat(parts)
+
+    def error(p_np):  # float32 residuals (objectives.py)
+        return residuals(torch.as_tensor(p_np)).detach().to(torch.float32).to(torch.float64).numpy()
+
+    def jacobian(p_np):
+        p = torch.as_tensor(p_np).clone().requires_grad_(True)
+        return torch.autograd.functional.jacobian(lambda q: residuals(q, True), p).numpy()
+
+    def cost(e, p):
+        return (np.sum(e * e) + reg * np.sum(p * p)) / 2
+
+    c = F32(params.mu_c)
+    p_, C_, mu = np.asarray(ps, dtype=np.float64), np.inf, F32(params.mu_0)
+    e_ = error(p_)
+    iters, improved = 0, True
+    while improved and iters < max_iters and mu < params.mu_max:
+        mu = F32(mu)
+        J = jacobian(p_)
+        H = J.T @ J
+        H[np.diag_indices_from(H)] += float(F32(reg) + mu)
+        Je = J.T @ e_ + reg * p_
+        dp = scipy.linalg.solve(H, Je, assume_a="pos")
+        p = p_ - dp
+        e = error(p)
+        C = cost(e, p)
+        rho = (C_ - C) / (dp @ (float(mu) * dp + Je))
+        if rho > params.rho_c:
+            mu = max(F32(mu / c), F32(params.mu_min))
+        bad = bool(rho < params.rho_min) or bool(np.any(np.isnan(p)))
+        if bad:
+            mu = min(F32(c * mu), F32(params.mu_max))
+            p, e, C = p_, e_, C_
+        improved = bool(C_ > C) or bad
+        iters += 0 if bad else 1
+        p_, e_, C_ = p, e, C
+        if history is not None:
+            history.append((p_.copy(), float(C_), float(mu)))
+    return p_
+
+
+def net_input_gradient(ps, widths, x, lower, upper, activation="tanh", omega0=1.0, omega=1.0):
+    """grad(lambda p, x: model.apply(p, x).sum(), argnums=-1) at ONE point (sirens.py:367,375-379)."""
+    import torch
+
+    xx = torch.tensor(np.asarray(x, dtype=np.float64).reshape(1, widths[0]), requires_grad=True)
+    out = _torch_mlp(torch.as_tensor(np.asarray(ps, dtype=np.float64)), widths, xx, lower, upper, activation, omega0, omega)
+    (g,) = torch.autograd.grad(out.sum(), xx)
+    return g.numpy().reshape(-1)
 
 
 def lm_fit_sobolev(ps, widths, x, y, dy, lower, upper, reg=1e-4, max_iters=1000, params=LMParams, history=None):

@@ -145,7 +145,7 @@ def _metapotential(state, periods):
 
 def analyze(result):
     """Post-run analysis.  UmbrellaIntegration: umbrella_integration.py:220-261.  Metadynamics:
-    metad.py:326-383 (heights + the deposited bias potential as a callable).  ABF / FUNN / SpectralABF / CFF: the binned
+    metad.py:326-383 (heights + the deposited bias potential as a callable).  ABF / FUNN / SpectralABF / CFF / Sirens: the binned
     estimates (histogram, mean force, mesh) of abf.py / funn.py `analyze`; their free-energy
     integration through a fitted network is out of scope."""
     import numpy as np
@@ -189,7 +189,7 @@ def analyze(result):
             for key in ("histogram", "free_energy", "nn", "fes_fn"):
                 out[key] = out[key][0]
         return out
-    if isinstance(method, (_m.ABF, _m.FUNN, _m.SpectralABF, _m.CFF)):
+    if isinstance(method, (_m.ABF, _m.FUNN, _m.SpectralABF, _m.CFF, _m.Sirens)):
         out = dict(histogram=[], mean_force=[], mesh=compute_mesh(method.grid))
         for s in result.states:
             h = numpyfy(s)

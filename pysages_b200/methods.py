@@ -950,6 +950,161 @@ class CFF(NNSamplingMethod):
         return snapshot, initialize, update
 
 
+class SirensState(NamedTuple):  # sirens.py:40-92
+    xi: Any
+    bias: Any
+    hist: Any
+    histp: Any
+    prob: Any
+    fe: Any
+    Fsum: Any
+    force: Any
+    Wp: Any
+    Wp_: Any
+    nn: Any
+    ncalls: int = 0
+
+
+class Sirens(NNSamplingMethod):
+    """
+    methods/sirens.py:95-420.  Every step is the fused ABF step (mode "cff": plus `histp`); past `train_freq`
+    calls the kernel back-propagates through the staged Siren network and applies `nn.std * d net / d xi`
+    (psb_set_force_net with sine layers and `gradient = 1`; restraints outside the grid first).  Every
+    `train_freq` calls the free-energy network is refitted on the device: gradients loss on the binned mean
+    force (mode "abf") or Sobolev loss on force + frequency-based free energy (mode "cff").
+    """
+
+    snapshot_flags = {"positions", "indices", "momenta"}
+    _kind = N.METHOD_ABF
+
+    def __init__(self, cvs, grid, topology, **kwargs):
+        from numbers import Real
+
+        from . import ml
+
+        mode = kwargs.get("mode", "abf")
+        kT = kwargs.get("kT", None)
+        loss = ml.GradientsSSE() if mode == "abf" else ml.Sobolev1SSE()
+        optimizer = kwargs.get("optimizer", ml.LevenbergMarquardt(loss=loss, reg=ml.L2Regularization(1e-4), max_iters=250))
+        # sirens.py:181-196
+        if mode not in ("abf", "cff"):
+            raise ValueError(f"Invalid mode {mode}. Possible values are 'abf' and 'cff'")
+        if mode == "cff":
+            if kT is None:
+                raise KeyError("When running in 'cff' mode, a keyword argument `kT` in the same "
+                               "units as the backend internal energy units must be provided.")
+            assert isinstance(kT, Real)
+            assert isinstance(optimizer.loss, ml.Sobolev1SSE)
+        else:
+            assert isinstance(optimizer.loss, ml.GradientsSSE)
+        super().__init__(cvs, grid, topology, **kwargs)
+        self.mode, self.kT = mode, kT
+        self.N = np.asarray(self.kwargs.get("N", 500))
+        self.train_freq = self.kwargs.get("train_freq", 5000)
+        self.model = ml.Siren(grid.shape.size, 1, topology, grid.lower, grid.upper, omega_0=self.kwargs.get("omega_0", 16),
+                              omega=self.kwargs.get("omega", 1), seed=self.kwargs.get("seed", 0))
+        self.optimizer = optimizer
+        self.use_pinv = self.kwargs.get("use_pinv", False)
+
+    def describe(self, helpers):
+        d = ABF.describe(self, helpers)
+        d.variant = 2 if self.mode == "cff" else 0
+        return d
+
+    def build(self, snapshot, helpers, *args, **kwargs):
+        from . import ml
+        from .grids import compute_mesh
+
+        native = NativeStep(self, snapshot, helpers, dense_outputs=self.dense_bias)
+        self.native = native
+        grid, model, mode = self.grid, self.model, self.mode
+        train_freq = int(self.train_freq)
+        kT = None if self.kT is None else float(self.kT)
+        k = native.k
+        gshape = tuple(int(s) for s in grid.shape)
+        shape = gshape if k > 1 else (*gshape, 1)
+        dev = native.device
+        f32 = lambda t: t.to(torch.float32).to(torch.float64)
+        inputs = f32(torch.as_tensor(compute_mesh(grid), dtype=torch.float64, device=dev))  # sirens.py:290
+        kernel = ml.blackman_kernel(k, 5).astype(np.float32).astype(np.float64)  # sirens.py:291
+        padding = "wrap" if grid.is_periodic else "edge"
+        fit = ml.build_fitting_function(model, self.optimizer)
+        one = lambda v: torch.tensor(float(v), dtype=torch.float64, device=dev)
+        holder = dict(nn=ml.NNData(torch.as_tensor(model.parameters, device=dev), one(0.0), one(1.0)), prob=None, fe=None)
+        if mode == "cff":
+            holder.update(prob=torch.zeros(shape, dtype=torch.float64, device=dev),
+                          fe=torch.zeros(shape, dtype=torch.float64, device=dev))
+
+        def push(nn):
+            native.set_force_net(model.widths, nn.params, [0.0], nn.std.reshape(1), predict_after=train_freq,
+                                 activation=N.ACT_SIN, omega0=model.omega_0, omega=model.omega, gradient=True)
+
+        def smooth(y):
+            return ml.convolve(y, kernel, padding) if k > 1 else ml.smooth(y, kernel, padding)
+
+        def normalize_gradients(data):  # sirens.py:399-417
+            axes = tuple(range(data.ndim - 1))
+            std = data.std(dim=axes, unbiased=False).max()
+            return (data - data.mean(dim=axes), std) if grid.is_periodic else (data, std)
+
+        def learn():  # sirens.py:340-347 on the state as it is before this step's sample is added
+            hist = native.view("hist", gshape).to(torch.float64).unsqueeze(-1)
+            force = native.view("Fsum", (*gshape, k)) / torch.clamp(hist, min=1.0)
+            if mode == "cff":
+                histp = native.view("histp", gshape)
+                prob = holder["prob"] + histp.to(torch.float64).reshape(shape) * torch.exp(holder["fe"] / kT)
+                fe = kT * torch.log(torch.clamp(prob, min=1.0))
+                dy, dy_std = normalize_gradients(force)
+                s = torch.maximum(fe.std(unbiased=False), dy_std)
+                params = fit(holder["nn"].params, inputs, (smooth(f32(fe / s)), dy / s))
+                nn = ml.NNData(params, holder["nn"].mean, s)
+                fe = nn.std * model.apply(params, inputs).reshape(fe.shape)
+                holder.update(nn=nn, prob=prob, fe=fe - fe.min())
+                histp.zero_()
+            else:
+                dy, s = normalize_gradients(force)
+                holder["nn"] = ml.NNData(fit(holder["nn"].params, inputs, dy / s), holder["nn"].mean, s)
+
+        def make_state():
+            bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None
+            histp = native.view("histp", gshape) if mode == "cff" else None
+            return SirensState(
+                native.view("xi", (1, k)), bias, native.view("hist", gshape), histp, holder["prob"], holder["fe"],
+                native.view("Fsum", (*gshape, k)), native.view("force")[:k], native.view("Wp")[:k],
+                native.view("Wp_")[:k], holder["nn"], native.ncalls,
+            )
+
+        def initialize():
+            native.evaluate(snapshot)
+            push(holder["nn"])  # untrained network: not used before the first fit (sirens.py:255-258)
+            return make_state()
+
+        def update(snapshot, state, timestep=0):
+            ncalls = native.ncalls + 1
+            if ncalls > train_freq and ncalls % train_freq == 1:
+                learn()
+                push(holder["nn"])
+            native.step(snapshot, timestep)
+            return make_state()
+
+        def restore(prev):
+            to_t = lambda v: torch.as_tensor(np.asarray(v.cpu() if hasattr(v, "cpu") else v), dtype=torch.float64,
+                                             device=dev)
+            names = ("xi", "hist", "Fsum", "force", "Wp", "Wp_", "ncalls") + (("histp",) if mode == "cff" else ())
+            for name in names:
+                value = getattr(prev, name)
+                native.set_state(name, value.cpu().numpy() if hasattr(value, "cpu") else value)
+            if mode == "cff":
+                holder.update(prob=to_t(prev.prob).reshape(shape), fe=to_t(prev.fe).reshape(shape))
+            holder["nn"] = ml.NNData(*(to_t(t) for t in prev.nn))
+            push(holder["nn"])
+            return make_state()
+
+        update.native = native
+        update.restore = restore
+        return snapshot, initialize, update
+
+
 class SpectralABFState(NamedTuple):  # spectral_abf.py:36-84
     xi: Any
     bias: Any

@@ -53,6 +53,10 @@ class Sobolev1SSE:  # ml/objectives.py: squared errors of the values AND of the 
     pass
 
 
+class GradientsSSE:  # ml/objectives.py: squared errors of the input-gradients only
+    pass
+
+
 @dataclass
 class LevenbergMarquardt:  # ml/optimizers.py:121-131
     params: LevenbergMarquardtParams = LevenbergMarquardtParams()
@@ -72,6 +76,9 @@ class MLP:
     upper: np.ndarray
     seed: int = 0
     parameters: np.ndarray = field(default=None, repr=False)
+    activation: str = "tanh"  # "sin": Siren layers sin(omega * (x W + b)) (ml/models.py:84-152)
+    omega_0: float = 1.0
+    omega: float = 1.0
 
     def __post_init__(self):
         self.topology = tuple(int(t) for t in self.topology)
@@ -81,9 +88,14 @@ class MLP:
         if self.parameters is None:
             rng = np.random.Generator(np.random.PCG64(self.seed))
             chunks = []
-            for a, b in zip(self.widths[:-1], self.widths[1:]):
-                chunks.append((rng.standard_normal((a, b)) * np.sqrt(2.0 / (a + b))).ravel())
-                chunks.append(rng.standard_normal(b) * 1e-2)
+            for l, (a, b) in enumerate(zip(self.widths[:-1], self.widths[1:])):
+                if self.activation == "sin":  # ml/models.py:113-147 + ml/utils.py:67-100 (uniform_scaling, fan_in)
+                    ws = 1.0 / a if l == 0 else np.sqrt(6.0 / self.omega**2 / a)
+                    chunks.append((rng.uniform(-1.0, 1.0, (a, b)) * ws).ravel())
+                    chunks.append(rng.uniform(-1.0, 1.0, b) * np.sqrt(1.0 / a))
+                else:
+                    chunks.append((rng.standard_normal((a, b)) * np.sqrt(2.0 / (a + b))).ravel())
+                    chunks.append(rng.standard_normal(b) * 1e-2)
             self.parameters = np.concatenate(chunks)
         self.parameters = np.asarray(self.parameters, dtype=np.float64)
         expected = sum(a * b + b for a, b in zip(self.widths[:-1], self.widths[1:]))
@@ -108,6 +120,15 @@ class MLP:
         """x (n, indim) -> (n, outdim) [, d out / d ps as (n * outdim, nparams)]."""
         h = self._scaled(x.to(F64).reshape(-1, self.widths[0]))
         layers = self._layers(ps)
+        if self.activation == "sin":
+            for l, (W, b) in enumerate(layers):
+                h = h @ W + b
+                if l + 1 < len(layers):
+                    h = torch.sin((self.omega_0 if l == 0 else self.omega) * h)
+            if not with_jacobian:
+                return h
+            J = torch.func.jacfwd(lambda q: self.apply(q, x).reshape(-1))(ps)  # no closed form kept for sine layers
+            return h, J
         acts = [h]
         for l, (W, b) in enumerate(layers):
             h = h @ W + b
@@ -181,6 +202,7 @@ def build_fitting_function(model, optimizer):
     f32 = np.float32
 
     sobolev = isinstance(optimizer.loss, Sobolev1SSE)
+    gradients_only = isinstance(optimizer.loss, GradientsSSE)
 
     def input_gradients(p, x):
         """d (sum of outputs) / d x for every point: (n, indim) -- functional, so that forward-mode
@@ -191,6 +213,11 @@ def build_fitting_function(model, optimizer):
     def error(p, x, y, with_jacobian=False):
         """objectives.py build_error_function: float32 residuals; Sobolev: (values, input-gradients) stacked."""
         x = x.to(F64)
+        if gradients_only:  # objectives.py: build_error_function(model, GradientsLoss)
+            e = (input_gradients(p, x).reshape(y.shape) - y).to(torch.float32).flatten().to(F64)
+            if not with_jacobian:
+                return e
+            return e, torch.func.jacfwd(lambda q: input_gradients(q, x).reshape(-1))(p)
         ref = y
         if sobolev:
             ref, dref = y
@@ -243,3 +270,9 @@ def build_fitting_function(model, optimizer):
         return p_
 
     return fit
+
+
+def Siren(indim, outdim, topology, lower, upper, omega_0=16, omega=1, seed=0, parameters=None):
+    """ml/models.py:84-152: sinusoidal representation network (first layer frequency omega_0)."""
+    return MLP(indim, outdim, topology, lower, upper, seed=seed, parameters=parameters, activation="sin",
+               omega_0=float(omega_0), omega=float(omega))

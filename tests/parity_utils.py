@@ -52,6 +52,13 @@ def make_method(which, spec, cvs):
         return mod.Metadynamics(cvs, *args, kwargs.pop("deltaT", None), **kwargs)
     if name == "ABF":
         return mod.ABF(cvs, kwargs.pop("grid"), **kwargs)
+    if name == "Sirens":
+        if which != "oracle" and "max_iters" in kwargs:
+            from pysages_b200 import ml
+            loss = ml.Sobolev1SSE() if kwargs.get("mode", "abf") == "cff" else ml.GradientsSSE()
+            kwargs["optimizer"] = ml.LevenbergMarquardt(loss=loss, reg=ml.L2Regularization(1e-4),
+                                                        max_iters=kwargs.pop("max_iters"))
+        return mod.Sirens(cvs, kwargs.pop("grid"), kwargs.pop("topology"), **kwargs)
     if name == "CFF":
         if which != "oracle":
             from pysages_b200 import ml

@@ -890,3 +890,39 @@ def test_cff_refit_tracks_oracle():
     np.testing.assert_allclose(ours.fnn.params.cpu().numpy(), ref.fnn.params, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(ours.force.cpu().numpy(), ref.force.numpy(), rtol=1e-4, atol=1e-8)
     assert int(ours.histp.sum()) == 1  # reset at the fit, then this step's visit
+
+
+# ---- Sirens: Siren free-energy network, force = its gradient (sirens.py:95-420) ---------------------------
+@pytest.mark.parametrize("mode", ["abf", "cff"])
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float64), ("hoomd", np.float32)])
+@pytest.mark.parametrize("restraints", [None, ((0.0, 0.0), (8.0, 8.0), (20.0, 20.0), (20.0, 20.0))])
+def test_sirens_network_gradient_force(mode, layout, dtype, restraints):
+    """train_freq = 2, LM capped at 0 iterations (same weights on both sides): per-step kernel path (ABF
+    [+ histp], back-propagation through sine layers with omega_0 = 16) and the host-side targets / scale."""
+    snap = snapshot(layout, dtype)
+    kw = dict(grid=FUNN_GRID, topology=(6, 5), N=2, train_freq=2, restraints=restraints, max_iters=0, seed=4, mode=mode)
+    if mode == "cff":
+        kw["kT"] = 1.0e4
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("Sirens", kw))
+    for pos in perturbed(snap, 8, 0.1):
+        ours, ref = run.step(pos)
+        if mode == "cff":
+            assert np.array_equal(ours.histp.cpu().numpy().astype(np.int64), ref.histp.numpy())
+            np.testing.assert_allclose(ours.fe.cpu().numpy(), ref.fe, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(float(run.state.nn.std), run.ostate.nn.std, rtol=max(1e-8, 10 * run.rtol))
+
+
+@pytest.mark.parametrize("mode", ["abf", "cff"])
+def test_sirens_refit_tracks_oracle(mode):
+    snap = snapshot("hoomd", np.float64)
+    kw = dict(grid=((0.0, 0.0), (8.0, 8.0), (6, 6), "regular"), topology=(4,), N=2, train_freq=3, max_iters=3, seed=6,
+              mode=mode, omega_0=4)
+    if mode == "cff":
+        kw["kT"] = 1.0e4
+    run = ParityRun(snap, POINT_CVS["two-distances"], ("Sirens", kw))
+    frames = perturbed(snap, 5, 0.1)
+    for pos in frames[:3]:
+        run.step(pos)
+    ours, ref = run.step(frames[3], check=False)  # call 4 = train_freq + 1: first fit
+    np.testing.assert_allclose(ours.nn.params.cpu().numpy(), ref.nn.params, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ours.force.cpu().numpy(), ref.force.numpy(), rtol=1e-4, atol=1e-8)
