@@ -214,6 +214,57 @@ class RadiusOfGyration(CollectiveVariable):
         return radius_of_gyration
 
 
+def _local_reference_systems(rs):
+    # orientation.py:177-216: rs (n, 3, 3) -> unit axes (n, 3, 3) [x, y, z] and origins (n, 3)
+    origins = rs.mean(dim=1)
+    x = rs[:, 0] - origins
+    x_hat = x / torch.linalg.norm(x, dim=-1, keepdim=True)
+    z = torch.linalg.cross(x_hat, rs[:, 1] - origins, dim=1)
+    z_hat = z / torch.linalg.norm(z, dim=-1, keepdim=True)
+    y = torch.linalg.cross(z_hat, x_hat, dim=1)
+    y_hat = y / torch.linalg.norm(y, dim=1, keepdim=True)
+    return torch.stack((x_hat, y_hat, z_hat), dim=1), origins
+
+
+def _g_vector(systems, origins, cutoff, a, b):
+    # orientation.py:219-288
+    pairs = origins[:, None] - origins[None, :]
+    r = torch.einsum("ijk,jlk->ijl", pairs, systems)
+    n = r.shape[0]
+    eye = torch.eye(n, dtype=torch.bool)
+    r = torch.where(eye[:, :, None], torch.full_like(r, 10.0), r)  # masked self entries: outside the cutoff
+    r_tilde = r * torch.tensor([1 / a, 1 / a, 1 / b], dtype=r.dtype)
+    norm = torch.linalg.norm(r_tilde, dim=-1)
+    gamma = math.pi / cutoff
+    inv = torch.where(norm != 0, 1 / norm, torch.zeros_like(norm))
+    G123 = r_tilde * (torch.sin(gamma * norm) * inv)[:, :, None]
+    G4 = 1 + torch.cos(gamma * norm)
+    G = torch.cat((G123, G4[:, :, None]), dim=-1)
+    return G * ((cutoff - norm > 0).to(r.dtype) / gamma)[:, :, None]
+
+
+def ermsd(rs, reference, cutoff, a, b):
+    # orientation.py:291-378
+    n = rs.shape[0] // 3
+    sys_, org = _local_reference_systems(rs.reshape(n, 3, 3))
+    ref = torch.as_tensor(np.asarray(reference, dtype=np.float64)).reshape(n, 3, 3).to(rs.dtype)
+    rsys, rorg = _local_reference_systems(ref)
+    Gs, Gr = _g_vector(sys_, org, cutoff, a, b), _g_vector(rsys, rorg, cutoff, a, b)
+    return torch.sqrt(torch.sum((Gs - Gr) ** 2) / n)
+
+
+class ERMSD(CollectiveVariable):
+    # orientation.py:129-175
+    def __init__(self, indices, references, cutoff=2.4, a=0.5, b=0.3):
+        super().__init__(indices)
+        self.references = np.asarray(references)
+        self.cutoff, self.a, self.b = cutoff, a, b
+
+    @property
+    def function(self):
+        return lambda r: ermsd(r, self.references, self.cutoff, self.a, self.b)
+
+
 def ring_puckering_coordinates(rs):
     """angles.py:158-205: Cremer-Pople amplitude q and phase phi (m = 2) of a monocyclic ring."""
     N = rs.shape[0]

@@ -15,6 +15,7 @@ OK, ERR_VALUE, ERR_RUNTIME, ERR_KEY, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 
 CV_COMPONENT, CV_DISTANCE, CV_DISPLACEMENT, CV_ANGLE, CV_DIHEDRAL, CV_ROG, CV_RMSD, CV_COORDINATION, CV_GYRATION, CV_RING = range(1, 11)
 RING_AMPLITUDE, RING_PHASE = 0, 1
+CV_ERMSD = 11
 GYR_ASPHERICITY, GYR_ACYLINDRICITY, GYR_ANISOTROPY = 3, 4, 5
 GRID_NONE, GRID_REGULAR, GRID_PERIODIC, GRID_CHEBYSHEV = range(4)
 METHOD_UNBIASED, METHOD_HARMONIC, METHOD_METAD, METHOD_ABF = range(4)

@@ -318,6 +318,33 @@ class RMSD(CollectiveVariable):
         return d
 
 
+class ERMSD(CollectiveVariable):
+    """colvars/orientation.py:129-175: eRMSD of n nucleotides to `references` (Bottaro et al., NAR 2014).
+    `indices`: 3 ring atoms per base -- C2, C6, C4 for A / G and C2, C4, C6 for U / C -- as one flat list;
+    `references` (3n, 3) in the same order.  Evaluated by one CTA with hand-written adjoints
+    (csrc/psb_ermsd.cuh); up to 256 bases."""
+
+    _kind = N.CV_ERMSD
+
+    def __init__(self, indices, references, cutoff=2.4, a=0.5, b=0.3):
+        super().__init__(indices)
+        self.references = np.ascontiguousarray(references, dtype=np.float64)
+        if len(self.indices) % 3 != 0:
+            raise ValueError(f"Please make sure the indices are in dimension 3 * n_nucleotides! Now it's {len(self.indices)}.")
+        if self.references.shape != (len(self.indices), 3):
+            raise ValueError("references must have shape (len(indices), 3)")
+        self.cutoff, self.a, self.b = float(cutoff), float(a), float(b)
+
+    def describe(self, keep):
+        d = super().describe(keep)
+        ab = np.array([self.a, self.b], dtype=np.float64)
+        keep += [self.references, ab]
+        d.reference = self.references.ctypes.data_as(N.POINTER(N.c_double))
+        d.weights = ab.ctypes.data_as(N.POINTER(N.c_double))
+        d.r0 = self.cutoff
+        return d
+
+
 class CoordinationNumber(TwoPointCV):
     """
     Pairwise coordination number between two groups (extension; absent from the reference):

@@ -38,6 +38,39 @@ psb_status fail(psb_status code, const char* fmt, ...) {
                   __FILE__, __LINE__, #expr);                                               \
   } while (0)
 
+// G vectors of the REFERENCE structure (orientation.py:177-288), the constant half of the eRMSD sum: (n, n, 4)
+std::vector<double> ermsd_reference_g(const double* ref, int n, double cutoff, double a, double b) {
+  struct F3 { double x, y, z; };
+  auto sub = [](F3 p, F3 q) { return F3{p.x - q.x, p.y - q.y, p.z - q.z}; };
+  auto dotp = [](F3 p, F3 q) { return p.x * q.x + p.y * q.y + p.z * q.z; };
+  auto crossp = [](F3 p, F3 q) { return F3{p.y * q.z - p.z * q.y, p.z * q.x - p.x * q.z, p.x * q.y - p.y * q.x}; };
+  auto unit = [&](F3 p) { const double s = 1.0 / std::sqrt(dotp(p, p)); return F3{p.x * s, p.y * s, p.z * s}; };
+  std::vector<F3> o(n), xh(n), yh(n), zh(n);
+  for (int j = 0; j < n; ++j) {
+    const double* r = ref + 9 * (size_t)j;
+    const F3 r0{r[0], r[1], r[2]}, r1{r[3], r[4], r[5]}, r2{r[6], r[7], r[8]};
+    o[j] = F3{(r0.x + r1.x + r2.x) / 3.0, (r0.y + r1.y + r2.y) / 3.0, (r0.z + r1.z + r2.z) / 3.0};
+    xh[j] = unit(sub(r0, o[j]));
+    zh[j] = unit(crossp(xh[j], sub(r1, o[j])));
+    yh[j] = unit(crossp(zh[j], xh[j]));
+  }
+  const double gamma = 3.141592653589793 / cutoff;
+  std::vector<double> G((size_t)n * n * 4, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;  // masked self entry: outside the cutoff
+      const F3 p = sub(o[i], o[j]);
+      const F3 rt{dotp(p, xh[j]) / a, dotp(p, yh[j]) / a, dotp(p, zh[j]) / b};
+      const double rho = std::sqrt(dotp(rt, rt));
+      if (!(cutoff - rho > 0.0)) continue;
+      const double inv = rho != 0.0 ? 1.0 / rho : 0.0;
+      const double s = std::sin(gamma * rho) * inv / gamma;
+      double* g = &G[((size_t)i * n + j) * 4];
+      g[0] = s * rt.x; g[1] = s * rt.y; g[2] = s * rt.z; g[3] = (1.0 + std::cos(gamma * rho)) / gamma;
+    }
+  return G;
+}
+
 struct CoordWork {
   int cv = -1;
   int nA = 0, nB = 0, na_pad = 0, nb_pad = 0, nrt = 0, ncs = 0, R = 1, H = 3;
@@ -59,6 +92,7 @@ struct psb_handle {
   psb_method_desc method;
   std::vector<void*> allocs;
   std::vector<CoordWork> coord;
+  std::vector<int> ermsd;  // CVs evaluated by ermsd_kernel before the step kernel
   int device = 0;
   int num_sms = 0;
   int grid = 1;
@@ -107,7 +141,8 @@ psb_status dev_upload(psb_handle* h, T** out, const std::vector<T>& v) {
 
 int expected_groups(int kind) {
   switch (kind) {
-    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: case PSB_CV_GYRATION: case PSB_CV_RING: return 1;
+    case PSB_CV_COMPONENT: case PSB_CV_ROG: case PSB_CV_RMSD: case PSB_CV_GYRATION: case PSB_CV_RING:
+    case PSB_CV_ERMSD: return 1;
     case PSB_CV_DISTANCE: case PSB_CV_DISPLACEMENT: case PSB_CV_COORDINATION: return 2;
     case PSB_CV_ANGLE: return 3;
     case PSB_CV_DIHEDRAL: return 4;
@@ -193,6 +228,11 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
       h->launches += 2;
     }
   }
+  if (eval_cvs)
+    for (int c : h->ermsd) {
+      pick_vtable(h->layout)->launch_ermsd(&M, &S, c, stream);
+      ++h->launches;
+    }
   if (M.bias_dense && mode != MODE_EVAL && mode != MODE_WALKER_BEGIN) {
     CUDA_TRY(cudaMemsetAsync(M.bias_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms, stream));
     if (M.jac_dense)
@@ -314,7 +354,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     cv.t1 = (uint32_t)term_tag.size();
     if (!is_point(d.kind)) M.all_point = 0;
     if (d.kind == PSB_CV_RMSD) M.any_rmsd = 1;
-    if (d.kind == PSB_CV_COORDINATION) M.any_coord = 1;
+    if (d.kind == PSB_CV_COORDINATION || d.kind == PSB_CV_ERMSD) M.any_coord = 1;  // value / gradient from a pre-kernel
   }
   M.k = k;
   M.ngroups = ng;
@@ -457,6 +497,26 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         if ((st = dev_upload(h, &p, w)) != PSB_OK) return bail(st);
         cv.w = p;
       }
+    }
+    if (d.kind == PSB_CV_ERMSD) {  // orientation.py:129-175
+      if (n % 3 != 0)
+        return bail(fail(PSB_ERR_VALUE, "Please make sure the indices are in dimension 3 * n_nucleotides! Now it's %u.", n));
+      const int nb = (int)n / 3;
+      if (nb < 2 || nb > ERMSD_MAX_N)
+        return bail(fail(PSB_ERR_VALUE, "CV %d: eRMSD takes between 2 and %d nucleotides (got %d)", c, ERMSD_MAX_N, nb));
+      if (!d.reference || !d.weights || !(d.r0 > 0.0) || !(d.weights[0] > 0.0) || !(d.weights[1] > 0.0))
+        return bail(fail(PSB_ERR_VALUE, "CV %d: eRMSD needs reference coordinates, a positive cutoff and rescaling lengths", c));
+      cv.r0 = d.r0;
+      cv.sumQ[0] = d.weights[0];  // a
+      cv.sumQ[1] = d.weights[1];  // b
+      const std::vector<double> gref = ermsd_reference_g(d.reference, nb, d.r0, d.weights[0], d.weights[1]);
+      double* p = nullptr;
+      if ((st = dev_upload(h, &p, gref)) != PSB_OK) return bail(st);
+      cv.ref = p;
+      if ((st = dev_alloc(h, &cv.grad, 3 * (size_t)n)) != PSB_OK) return bail(st);
+      if ((st = dev_alloc(h, &cv.xi_part, 1)) != PSB_OK) return bail(st);
+      cv.n_part = 1;
+      h->ermsd.push_back(c);
     }
     if (d.kind == PSB_CV_RING) {
       if (d.axis != PSB_RING_AMPLITUDE && d.axis != PSB_RING_PHASE)

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "psb_device.cuh"
+#include "psb_ermsd.cuh"
 #include "psb_step.cuh"
 
 namespace psb {
@@ -16,6 +17,7 @@ struct StepVTable {
   int (*occupancy)(int method, int general, size_t dyn_smem);
   void (*launch_gather)(const Model* M, const Snap* S, int cv, double* xa, int na_pad, double* xb,
                         int nb_pad, cudaStream_t stream);
+  void (*launch_ermsd)(const Model* M, const Snap* S, int cv, cudaStream_t stream);
 };
 
 using PairLaunchFn = void (*)(int grid, cudaStream_t stream, const double* xa, int na_pad,
@@ -76,6 +78,9 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
     coord_gather_kernel<L, R><<<(total + 255) / 256, 256, 0, stream>>>(*M, *S, cv, xa, na_pad, xb,  \
                                                                        nb_pad);                     \
   }                                                                                                 \
-  const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_gather};
+  static void NAME##_ermsd(const Model* M, const Snap* S, int cv, cudaStream_t stream) {           \
+    ermsd_kernel<L, R><<<1, ERMSD_BLOCK, 0, stream>>>(*M, *S, cv);                                  \
+  }                                                                                                 \
+  const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_gather, NAME##_ermsd};
 
 }  // namespace psb

@@ -381,6 +381,7 @@ static __device__ __forceinline__ void finalize_cv_A(const Model& M, StepShared&
       for (int a = 0; a < 3; ++a)
         x[12 + a] = sp[a] - (cv.sumQ[0] * x[a * 3 + 0] + cv.sumQ[1] * x[a * 3 + 1] + cv.sumQ[2] * x[a * 3 + 2]);
     } break;
+    case PSB_CV_ERMSD:  // value and gradient come from ermsd_kernel, like the pair kernel's
     case PSB_CV_COORDINATION: {
       f.xi[cv.comp0] = sh.tot[g0][0];
     } break;
@@ -402,7 +403,7 @@ static __device__ __forceinline__ void finalize_cv_A(const Model& M, StepShared&
 // coordination CVs: the pair kernel left per-CTA partial sums; warp 0 adds them up (fixed order)
 __device__ __forceinline__ void reduce_coordination(const Model& M, StepShared& sh, int lane) {
   for (int c = 0; c < M.ncv; ++c) {
-    if (M.cv[c].kind != PSB_CV_COORDINATION) continue;
+    if (M.cv[c].kind != PSB_CV_COORDINATION && M.cv[c].kind != PSB_CV_ERMSD) continue;
     double v = 0.0;
     for (int i = lane; i < M.cv[c].n_part; i += 32) v += __ldcg(M.cv[c].xi_part + i);
     v = warp_sum(v);
@@ -1000,7 +1001,7 @@ __device__ __forceinline__ int term_gradient(const Model& M, const Snap& S, cons
                                              int g, uint32_t slot, V3* gv) {
   V3 r = v3(0, 0, 0);
   const int kind = M.cv[M.grp[g].cv].kind;
-  if (!is_point_kind(kind) && kind != PSB_CV_COORDINATION) r = A::position(S, slot);
+  if (!is_point_kind(kind) && kind != PSB_CV_COORDINATION && kind != PSB_CV_ERMSD) r = A::position(S, slot);
   return term_gradient_at(M, f, t, g, r, gv);
 }
 // Unique atom u of the selection: its tag, slot and CSR range of terms.  The slot comes straight from
@@ -1735,7 +1736,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
             for (uint32_t t = tlo + tid; t < thi; t += BLOCK) {
               const uint32_t slot = __ldcg(M.term_slot + t);
               V3 r = v3(0, 0, 0);
-              if (cv.kind != PSB_CV_COORDINATION) r = A::position(S, slot);
+              if (cv.kind != PSB_CV_COORDINATION && cv.kind != PSB_CV_ERMSD) r = A::position(S, slot);
               add_force<A>(S, slot, Fc * nonpoint_gradient(f, cv, G.cv, G.inv_n, t, r));
             }
           }

@@ -117,3 +117,13 @@ def test_force_series_errors():
         update.native.set_force_series(N.SERIES_MONOMIAL, np.ones((2, 3), dtype=np.int32), np.zeros(3), predict_after=0)
     with pytest.raises(ValueError, match="Only 1D and 2D grids"):  # approxfun/core.py:74-75 at construction
         ps.methods.SpectralABF(cvs3, grid3)
+
+
+def test_ermsd_errors():
+    snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
+    with pytest.raises(ValueError, match="3 \\* n_nucleotides"):
+        ps.colvars.ERMSD(list(range(7)), np.zeros((7, 3)))
+    with pytest.raises(ValueError, match="references must have shape"):
+        ps.colvars.ERMSD(list(range(6)), np.zeros((5, 3)))
+    with pytest.raises(ValueError, match="between 2 and 256 nucleotides"):
+        build(ps.methods.Unbiased([ps.colvars.ERMSD([1, 2, 3], np.eye(3))]), snap)

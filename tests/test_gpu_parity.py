@@ -926,3 +926,51 @@ def test_sirens_refit_tracks_oracle(mode):
     ours, ref = run.step(frames[3], check=False)  # call 4 = train_freq + 1: first fit
     np.testing.assert_allclose(ours.nn.params.cpu().numpy(), ref.nn.params, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(ours.force.cpu().numpy(), ref.force.numpy(), rtol=1e-4, atol=1e-8)
+
+
+# ---- eRMSD (colvars/orientation.py:129-378) -----------------------------------------------------------
+def _rna_like(n_bases, seed, box=None):
+    """n bases: three ring atoms each around points of a loose helix (nm-like units, neighbours within the cutoff)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_bases)
+    centres = np.stack([0.9 * np.cos(0.6 * t), 0.9 * np.sin(0.6 * t), 0.33 * t], axis=1)
+    tri = np.array([[0.14, 0.0, 0.0], [-0.07, 0.12, 0.0], [-0.07, -0.12, 0.0]])
+    out = []
+    for c in centres:
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        out.append(c + tri @ Q.T + 0.01 * rng.normal(size=(3, 3)))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("layout, dtype, nb", [("hoomd", np.float64, 12), ("lammps", np.float64, 7),
+                                               ("openmm-cuda", np.float64, 20), ("hoomd", np.float64, 64)])
+def test_ermsd_harmonic(layout, dtype, nb):
+    """eRMSD of nb bases against a perturbed reference + HarmonicBias: value, the hand-written adjoints (dense
+    Jacobian against the oracle's autograd of the reference formula) and the applied forces."""
+    snap = snapshot(layout, dtype, n=max(N, 3 * nb + 50))
+    rng = np.random.default_rng(nb)
+    idx = rng.permutation(snap["arrays"]["positions"].shape[0] if layout != "openmm-cuda" else N)[: 3 * nb].tolist()
+    structure = _rna_like(nb, seed=nb)
+    reference = structure + 0.03 * rng.normal(size=structure.shape)
+    pos = snap["arrays"]["positions"]
+    tags = np.asarray(idx)
+    specs = [("ERMSD", (idx, reference), dict(cutoff=2.4, a=0.5, b=0.3))]
+    # place the selected atoms on the structure through the oracle's own tag -> row map, so that every layout
+    # (HOOMD rtag, OpenMM permuted order, LAMMPS tag map) is written consistently; zero image flags
+    import oracle
+    helpers, _ = oracle.backends.build_helpers(layout, {"positions", "indices"}, True)
+    from parity_utils import oracle_snapshot
+    osnap = oracle_snapshot(snap)
+    index_of = np.asarray(helpers.query(osnap).indices).astype(np.int64)
+    rows = index_of[tags]
+    pos[rows, :3] = structure.astype(pos.dtype)
+    if "images" in snap["arrays"]:
+        img = snap["arrays"]["images"]
+        if img.ndim == 2:
+            img[rows] = 0
+        else:  # LAMMPS packed image flags: zero image = 512 in every 10-bit field
+            img[rows] = 512 | (512 << 10) | (512 << 20)
+    run = ParityRun(snap, specs, harmonic(5.0, [0.3]))
+    for frame in perturbed(snap, 3, 0.01):
+        run.step(frame)
+    assert float(run.state.xi[0, 0]) > 0.0
