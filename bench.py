@@ -512,8 +512,9 @@ def run_series(device, stream, hbm):
     row["workload"] += f" ({with_series.terms} monomial terms)"
     del frames
 
-    # the headline workload on the other engine layouts (OpenMM-CUDA: fixed-point forces, permuted order,
-    # one extra inverse-permutation kernel per step; LAMMPS: (N,3) doubles, packed images, per-type masses)
+    # the headline workload on the other engine layouts (OpenMM-CUDA: fixed-point forces, permuted order -- the
+    # slot-ordered class reads ids as slot -> atom, no inverse permutation; LAMMPS: (N,3) doubles, packed images,
+    # per-type masses)
     for layout, dtype in (("openmm-cuda", np.float32), ("lammps", np.float64)):
         snaps, L = device_layout_snapshots(layout, dtype, 100_000, 16, device, seed=20240 + 2000)
         cvs, m = workload_specs("abf2d", 100_000, L)

@@ -661,6 +661,9 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         M.slot_major = 0;
       } else if (!getenv("PSB_GRID_BLOCKS")) {
         h->grid = std::min(occ_slot, SLOT_CTAS_PER_SM) * h->num_sms;  // streaming: fill the machine
+        // OpenMM layout, moderate sizes: one CTA per SM leaves room for the NEXT step's CTAs, whose gather runs
+        // before their dependency wait (psb_step.cuh), i.e. under this step's finalizer and scatter
+        if (omm && layout->natoms <= 8LL * BLOCK * h->num_sms) h->grid = h->num_sms;
       } else if ((long long)occ_slot * h->num_sms < h->grid) {
         M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
       }

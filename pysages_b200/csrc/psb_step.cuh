@@ -107,6 +107,7 @@ __device__ __forceinline__ long long global_ns() {
 struct StepShared {
   double red[NWARPS][NACC];
   double stage[NACC];  // this CTA's block-reduced pass-A sums, published to `partials` after griddepcontrol.wait
+  double stage4[4][6]; // slot-ordered class on the OpenMM layout: the same for its (up to) four groups
   double tot[MAXG + 1][NACC];
   Fin fin;  // this CTA's copy of the finalizer results
   Pre pre;  // method-state scalars as they were when the step began
@@ -1195,6 +1196,63 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       PSB_CLKA(11);
     }
   }
+  // ---- slot-ordered gather (most atoms selected, too many to keep in registers): see pass A below.  The loop
+  // only reads engine arrays (and, on the OpenMM layout, the immutable tag -> group table), so that layout runs
+  // it BEFORE the dependency wait, like the register-cached gather of the other classes.
+  auto slot_gather = [&](double (&acc4)[4][6]) {
+    const uint32_t N = (uint32_t)M.natoms;
+    uint32_t schunk = (N + nb - 1) / nb;
+    schunk = (schunk + 31u) & ~31u;  // warp-aligned slices
+    s_lo = min(N, (uint32_t)b * schunk);
+    s_hi = min(N, s_lo + schunk);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc4[g][a] = 0.0;
+    // SU independent rows per thread in flight: every load is issued before the first use (rows of
+    // unselected slots are loaded too -- they exist, and almost every slot is selected here)
+#ifndef PSB_SLOT_SUA
+#define PSB_SLOT_SUA 8
+#endif
+    constexpr int SU = is_abf ? 4 : PSB_SLOT_SUA;  // momenta double the registers per row in flight
+    for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
+      uint32_t e[SU];
+      V3 r[SU], p[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const uint32_t sl = min(base + u * BLOCK, s_hi - 1);  // clamped: no branch around the loads
+        e[u] = slot_word(sl);
+        r[u] = A::position(S, sl);
+        p[u] = momenta_sums ? A::momentum(S, sl) : v3(0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const bool hit = (base + u * BLOCK < s_hi) && ((e[u] & ~15u) == stamp);
+        const int g = hit ? (int)(e[u] & 15u) - 1 : -1;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {  // branch-free select: lanes of a warp hold different groups
+          const double w = (g == gg) ? 1.0 : 0.0;
+          acc4[gg][0] = fma(w, r[u].x, acc4[gg][0]);
+          acc4[gg][1] = fma(w, r[u].y, acc4[gg][1]);
+          acc4[gg][2] = fma(w, r[u].z, acc4[gg][2]);
+          if (momenta_sums) {
+            acc4[gg][3] = fma(w, p[u].x, acc4[gg][3]);
+            acc4[gg][4] = fma(w, p[u].y, acc4[gg][4]);
+            acc4[gg][5] = fma(w, p[u].z, acc4[gg][5]);
+          }
+        }
+      }
+    }
+  };
+  if (slot_major && TAGMAP && !skip_cv) {
+    stamp = 16u;  // ids is slot -> atom: group of a slot = tag_group[ids[slot]], no pass 0, no stamp to expire
+    double acc4[4][6];
+    slot_gather(acc4);
+    const int na = momenta_sums ? 6 : 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < M.ngroups) block_reduce_store(sh, acc4[g], na, &sh.stage4[g][0], 1, false);
+  }
   // everything below may depend on the previous kernel of the stream: forces, method state, workspaces
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -1300,7 +1358,6 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     // below HBM speed).  Instead: pass 0 scatters one word per selected atom into slot_map
     // (stamp | group), and the gather and the force update then stream positions, images,
     // velocities and forces in SLOT order, fully coalesced.  At most 4 groups (fast-class only).
-    if (slot_major && TAGMAP) stamp = 16u;  // ids is slot -> atom: group of a slot = tag_group[ids[slot]], no pass 0
     if (slot_major && !TAGMAP) {
       __syncthreads();  // sh.epoch
       stamp = ((uint32_t)(sh.epoch[BAR_SLOT] + 1ULL) & 0x0FFFFFFFu) << 4;
@@ -1336,55 +1393,18 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       PSB_STAMP(7);
       grid_sync(M, sh, BAR_SLOT);
     }
-    if (slot_major) {
-      const uint32_t N = (uint32_t)M.natoms;
-      uint32_t schunk = (N + nb - 1) / nb;
-      schunk = (schunk + 31u) & ~31u;  // warp-aligned slices
-      s_lo = min(N, (uint32_t)b * schunk);
-      s_hi = min(N, s_lo + schunk);
+    if (slot_major && !TAGMAP) {
       double acc4[4][6];
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int a = 0; a < 6; ++a) acc4[g][a] = 0.0;
-      // SU independent rows per thread in flight: every load is issued before the first use (rows of
-      // unselected slots are loaded too -- they exist, and almost every slot is selected here)
-#ifndef PSB_SLOT_SUA
-#define PSB_SLOT_SUA 8
-#endif
-      constexpr int SU = is_abf ? 4 : PSB_SLOT_SUA;  // momenta double the registers per row in flight
-      for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
-        uint32_t e[SU];
-        V3 r[SU], p[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          const uint32_t sl = min(base + u * BLOCK, s_hi - 1);  // clamped: no branch around the loads
-          e[u] = slot_word(sl);
-          r[u] = A::position(S, sl);
-          p[u] = momenta_sums ? A::momentum(S, sl) : v3(0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          const bool hit = (base + u * BLOCK < s_hi) && ((e[u] & ~15u) == stamp);
-          const int g = hit ? (int)(e[u] & 15u) - 1 : -1;
-#pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {  // branch-free select: lanes of a warp hold different groups
-            const double w = (g == gg) ? 1.0 : 0.0;
-            acc4[gg][0] = fma(w, r[u].x, acc4[gg][0]);
-            acc4[gg][1] = fma(w, r[u].y, acc4[gg][1]);
-            acc4[gg][2] = fma(w, r[u].z, acc4[gg][2]);
-            if (momenta_sums) {
-              acc4[gg][3] = fma(w, p[u].x, acc4[gg][3]);
-              acc4[gg][4] = fma(w, p[u].y, acc4[gg][4]);
-              acc4[gg][5] = fma(w, p[u].z, acc4[gg][5]);
-            }
-          }
-        }
-      }
+      slot_gather(acc4);
       const int na = momenta_sums ? 6 : 3;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         if (g < M.ngroups) block_reduce_store(sh, acc4[g], na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+    }
+    if (slot_major && TAGMAP) {  // gathered and block-reduced before the dependency wait (see above)
+      const int na = momenta_sums ? 6 : 3;
+      if (tid < 4 * 6 && tid / 6 < M.ngroups && tid % 6 < na)
+        __stcg(M.partials + (size_t)((tid / 6) * NACC + tid % 6) * nb + b, sh.stage4[tid / 6][tid % 6]);
     }
 
     // groups too large for the register cache (and not slot-ordered): gather loop, slots published
