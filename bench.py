@@ -52,6 +52,9 @@ def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, glob
         x0 = (torch.rand((natoms, 3), generator=g, device=device, dtype=torch.float64) - 0.5) * L
     frames = []
     cur = x0
+    # the globule is one object followed over time: ONE tag -> slot permutation for all its frames (tag i is the
+    # same atom in every frame, as the RMSD reference requires); the liquid-like frames draw one per frame
+    fixed_rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32) if globule else None
     for _ in range(nframes):
         cur = cur + 0.02 * torch.randn((natoms, 3), generator=g, device=device, dtype=torch.float64)
         img = torch.randint(-1, 2, (natoms, 3), generator=g, device=device, dtype=torch.int32)
@@ -66,6 +69,8 @@ def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, glob
         f[:, :3] = torch.randn((natoms, 3), generator=g, device=device, dtype=dtype)
         if sorted_tags:  # a freshly sorted system: tag order == memory order
             rtag = torch.arange(natoms, device=device, dtype=torch.int32)
+        elif fixed_rtag is not None:
+            rtag = fixed_rtag
         else:  # random permutation (the worst case for the gathers)
             rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32)
         frames.append(dict(positions=pos, vel_mass=vm, forces=f, rtags=rtag, images=img))
@@ -434,7 +439,11 @@ def cfg4_case(device, natoms=50_000, H=100_000):
     frames, L, x0 = device_hoomd_frames(natoms, 16, device, seed=20240 + 4000, globule=True)
     gen = np.random.Generator(np.random.PCG64(20240 + 4000))
     q, _ = np.linalg.qr(gen.normal(size=(3, 3)))
-    ref = (x0.cpu().numpy() @ q.T + gen.normal(scale=0.1, size=(natoms, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]  # a proper rotation ("random rotation of x_0")
+    rtag = frames[0]["rtags"].cpu().numpy().astype(np.int64)
+    # reference row i belongs to TAG i, whose atom sits in slot rtag[i] of the frames
+    ref = (x0.cpu().numpy()[rtag] @ q.T + gen.normal(scale=0.1, size=(natoms, 3)))
     allatoms = list(range(natoms))
     cvs4 = [("RMSD", (allatoms, ref), {}), ("RadiusOfGyration", (allatoms,), {})]
 
