@@ -64,7 +64,9 @@ typedef enum {
 } psb_cv_kind;
 #define PSB_CV_ERMSD 11 /* colvars/orientation.py:129-175,177-378: eRMSD of n nucleotides to a reference; one group of 3n
                            ring atoms (C2, then C6/C4 or C4/C6 per base, the reference's order), `reference` (3n, 3),
-                           `r0` = unitless cutoff, `weights` -> {a, b} (rescaling lengths); n <= 256 */
+                           `r0` = unitless cutoff, `weights` -> {a, b} (rescaling lengths); n <= 256.
+                           `axis` = 1: coarse-grained ERMSDCG (orientation.py:380-560): the 3 sites per base are B1/B2/B3,
+                           `weights` -> {a, b, local_coordinates (4, 3, 3), sequence (n values 0..3 as doubles)} */
 
 /* psb_cv_desc.axis for PSB_CV_RING */
 typedef enum { PSB_RING_AMPLITUDE = 0, PSB_RING_PHASE = 1 } psb_ring_mode;

@@ -265,6 +265,48 @@ class ERMSD(CollectiveVariable):
         return lambda r: ermsd(r, self.references, self.cutoff, self.a, self.b)
 
 
+ERMSDCG_LOCAL_COORDINATES = [  # orientation.py:440-461 (RACER-like B1/B2/B3 -> C2/C6/C4 or C2/C4/C6, nm)
+    [[-0.1333021, -0.1762476, -0.0000001], [-0.0857174, 0.0499809, -0.0000033], [0.0795015, -0.1210861, -0.0001387]],
+    [[-0.0253117, -0.1224880, 0.0003341], [-0.0236469, 0.1239022, -0.0006548], [0.1811280, 0.0000000, -0.0000000]],
+    [[-0.1167570, -0.1372227, -0.0002264], [-0.0409667, 0.0959927, -0.0012938], [0.1013132, -0.0983306, 0.0005419]],
+    [[-0.0267224, -0.1188717, 0.0004939], [-0.0254680, 0.1138277, 0.0008671], [0.1815304, -0.0000000, -0.0000000]],
+]
+
+
+def _infer_base_coordinates(systems, origins, sequence, local_coordinates):
+    # orientation.py:499-540: einsum("jlk,jml->jmk", systems, local_coordinates[sequence]) + origins
+    lc = torch.as_tensor(np.asarray(local_coordinates, dtype=np.float64))[torch.as_tensor(np.asarray(sequence, dtype=np.int64))]
+    return torch.einsum("jlk,jml->jmk", systems, lc.to(systems.dtype)) + origins[:, None, :]
+
+
+def ermsd_cg(rs, reference, sequence, local_coordinates, cutoff, a, b):
+    # orientation.py:543-590
+    n = rs.shape[0] // 3
+    ref = torch.as_tensor(np.asarray(reference, dtype=np.float64)).reshape(n, 3, 3).to(rs.dtype)
+    sys_, org = _local_reference_systems(rs.reshape(n, 3, 3))
+    rsys, rorg = _local_reference_systems(ref)
+    atoms = _infer_base_coordinates(sys_, org, sequence, local_coordinates)
+    ratoms = _infer_base_coordinates(rsys, rorg, sequence, local_coordinates)
+    s2, o2 = _local_reference_systems(atoms)
+    rs2, ro2 = _local_reference_systems(ratoms)
+    Gs, Gr = _g_vector(s2, o2, cutoff, a, b), _g_vector(rs2, ro2, cutoff, a, b)
+    return torch.sqrt(torch.sum((Gs - Gr) ** 2) / n)
+
+
+class ERMSDCG(CollectiveVariable):
+    # orientation.py:380-497 (decorated @multicomponent in the reference although it returns one number)
+    def __init__(self, indices, reference, sequence, local_coordinates=None, cutoff=2.4, a=0.5, b=0.3):
+        super().__init__(indices)
+        self.reference = np.asarray(reference)
+        self.sequence = np.asarray(sequence)
+        self.local_coordinates = np.asarray(ERMSDCG_LOCAL_COORDINATES if local_coordinates is None else local_coordinates)
+        self.cutoff, self.a, self.b = cutoff, a, b
+
+    @property
+    def function(self):
+        return lambda r: ermsd_cg(r, self.reference, self.sequence, self.local_coordinates, self.cutoff, self.a, self.b)
+
+
 def ring_puckering_coordinates(rs):
     """angles.py:158-205: Cremer-Pople amplitude q and phase phi (m = 2) of a monocyclic ring."""
     N = rs.shape[0]

@@ -345,6 +345,40 @@ class ERMSD(CollectiveVariable):
         return d
 
 
+class ERMSDCG(ERMSD):
+    """colvars/orientation.py:380-497: eRMSD of a coarse-grained RNA model.  `indices`: the three base sites
+    B1 / B2 / B3 per nucleotide (A: C8, N6, C2; U: C6, O4, O2; G: C8, O6, N2; C: C6, N4, O2); `sequence`: 0 (A),
+    1 (U), 2 (G), 3 (C) per nucleotide; `local_coordinates` (4, 3, 3): the ideal C2 / C6 / C4 (A, G) or C2 / C4 / C6
+    (U, C) atoms in the frame of the sites (default: the reference's RACER -> SPQR table, nm).  The kernel
+    reconstructs those atoms, runs the eRMSD on them and back-propagates through the reconstruction."""
+
+    DEFAULT_LOCAL_COORDINATES = [
+        [[-0.1333021, -0.1762476, -0.0000001], [-0.0857174, 0.0499809, -0.0000033], [0.0795015, -0.1210861, -0.0001387]],
+        [[-0.0253117, -0.1224880, 0.0003341], [-0.0236469, 0.1239022, -0.0006548], [0.1811280, 0.0000000, -0.0000000]],
+        [[-0.1167570, -0.1372227, -0.0002264], [-0.0409667, 0.0959927, -0.0012938], [0.1013132, -0.0983306, 0.0005419]],
+        [[-0.0267224, -0.1188717, 0.0004939], [-0.0254680, 0.1138277, 0.0008671], [0.1815304, -0.0000000, -0.0000000]],
+    ]
+
+    def __init__(self, indices, reference, sequence, local_coordinates=None, cutoff=2.4, a=0.5, b=0.3):
+        super().__init__(indices, reference, cutoff, a, b)
+        self.reference = self.references
+        self.sequence = np.asarray(sequence, dtype=np.int64)
+        if self.sequence.shape != (len(self.indices) // 3,) or self.sequence.min() < 0 or self.sequence.max() > 3:
+            raise ValueError("sequence needs one entry in {0 (A), 1 (U), 2 (G), 3 (C)} per nucleotide")
+        lc = self.DEFAULT_LOCAL_COORDINATES if local_coordinates is None else local_coordinates
+        self.local_coordinates = np.ascontiguousarray(lc, dtype=np.float64)
+        if self.local_coordinates.shape != (4, 3, 3):
+            raise ValueError("local_coordinates must have shape (4, 3, 3)")
+
+    def describe(self, keep):
+        d = super().describe(keep)
+        packed = np.concatenate([[self.a, self.b], self.local_coordinates.ravel(), self.sequence.astype(np.float64)])
+        keep.append(packed)
+        d.weights = packed.ctypes.data_as(N.POINTER(N.c_double))
+        d.axis = 1
+        return d
+
+
 class CoordinationNumber(TwoPointCV):
     """
     Pairwise coordination number between two groups (extension; absent from the reference):

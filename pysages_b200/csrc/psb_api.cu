@@ -71,6 +71,31 @@ std::vector<double> ermsd_reference_g(const double* ref, int n, double cutoff, d
   return G;
 }
 
+// ERMSDCG (orientation.py:380-560): the ideal C2 / C4 / C6 atoms of every base from its three coarse-grained
+// sites: frame of the sites (orientation.py:177-216), then origin + local_coordinates[sequence] . axes
+std::vector<double> ermsd_reconstruct(const double* sites, int n, const double* lc36, const double* seq) {
+  std::vector<double> out(9 * (size_t)n);
+  for (int j = 0; j < n; ++j) {
+    const double* r = sites + 9 * (size_t)j;
+    double o[3], x[3], c[3], z[3], y[3];
+    for (int d = 0; d < 3; ++d) o[d] = (r[d] + r[3 + d] + r[6 + d]) / 3.0;
+    double nx = 0.0;
+    for (int d = 0; d < 3; ++d) { x[d] = r[d] - o[d]; nx += x[d] * x[d]; }
+    for (int d = 0; d < 3; ++d) { x[d] /= std::sqrt(nx); c[d] = r[3 + d] - o[d]; }
+    z[0] = x[1] * c[2] - x[2] * c[1]; z[1] = x[2] * c[0] - x[0] * c[2]; z[2] = x[0] * c[1] - x[1] * c[0];
+    const double nz = std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+    for (int d = 0; d < 3; ++d) z[d] /= nz;
+    y[0] = z[1] * x[2] - z[2] * x[1]; y[1] = z[2] * x[0] - z[0] * x[2]; y[2] = z[0] * x[1] - z[1] * x[0];
+    const double ny = std::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+    for (int d = 0; d < 3; ++d) y[d] /= ny;
+    const double* lc = lc36 + 9 * (int)seq[j];
+    for (int m = 0; m < 3; ++m)
+      for (int d = 0; d < 3; ++d)
+        out[9 * (size_t)j + 3 * m + d] = o[d] + lc[3 * m] * x[d] + lc[3 * m + 1] * y[d] + lc[3 * m + 2] * z[d];
+  }
+  return out;
+}
+
 struct CoordWork {
   int cv = -1;
   int nA = 0, nB = 0, na_pad = 0, nb_pad = 0, nrt = 0, ncs = 0, R = 1, H = 3;
@@ -509,7 +534,21 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
       cv.r0 = d.r0;
       cv.sumQ[0] = d.weights[0];  // a
       cv.sumQ[1] = d.weights[1];  // b
-      const std::vector<double> gref = ermsd_reference_g(d.reference, nb, d.r0, d.weights[0], d.weights[1]);
+      if (d.axis != 0 && d.axis != 1) return bail(fail(PSB_ERR_VALUE, "CV %d: eRMSD variant must be 0 (all-atom) or 1 (coarse-grained)", c));
+      std::vector<double> ref_atoms(d.reference, d.reference + 9 * (size_t)nb);
+      if (d.axis == 1) {  // weights = {a, b, local_coordinates (4, 3, 3), sequence (n, as doubles)}
+        const double* lc = d.weights + 2;
+        const double* seq = d.weights + 38;
+        for (int j = 0; j < nb; ++j)
+          if (!(seq[j] >= 0.0 && seq[j] <= 3.0 && seq[j] == (double)(int)seq[j]))
+            return bail(fail(PSB_ERR_VALUE, "CV %d: sequence entries must be 0 (A), 1 (U), 2 (G) or 3 (C)", c));
+        ref_atoms = ermsd_reconstruct(d.reference, nb, lc, seq);
+        std::vector<double> w(d.weights + 2, d.weights + 38 + nb);
+        double* pw = nullptr;
+        if ((st = dev_upload(h, &pw, w)) != PSB_OK) return bail(st);
+        cv.w = pw;
+      }
+      const std::vector<double> gref = ermsd_reference_g(ref_atoms.data(), nb, d.r0, d.weights[0], d.weights[1]);
       double* p = nullptr;
       if ((st = dev_upload(h, &p, gref)) != PSB_OK) return bail(st);
       cv.ref = p;

@@ -24,6 +24,43 @@ struct ErmsdFrame {
   V3 o, xh, yh, zh;
 };
 
+// orientation.py:177-216: x = cog -> site 0, z = x^ x (cog -> site 1), y = z^ x x^ -- and its adjoint.
+struct FrameAux {
+  double nu, nw, nv;  // |u|, |w|, |v| before the normalisations
+  V3 cvec;            // cog -> site 1
+};
+__device__ __forceinline__ ErmsdFrame ermsd_make_frame(V3 r0, V3 r1, V3 r2, FrameAux* aux) {
+  ErmsdFrame f;
+  f.o = (1.0 / 3.0) * (r0 + r1 + r2);
+  const V3 u = r0 - f.o;
+  aux->nu = norm(u);
+  f.xh = (1.0 / aux->nu) * u;
+  aux->cvec = r1 - f.o;
+  const V3 w = cross(f.xh, aux->cvec);
+  aux->nw = norm(w);
+  f.zh = (1.0 / aux->nw) * w;
+  const V3 v = cross(f.zh, f.xh);
+  aux->nv = norm(v);
+  f.yh = (1.0 / aux->nv) * v;
+  return f;
+}
+// adjoints of the axes (gxh, gyh, gzh) and of the origin (go) -> the three sites
+__device__ __forceinline__ void ermsd_frame_backward(const ErmsdFrame& f, const FrameAux& aux, V3 gxh, V3 gyh, V3 gzh,
+                                                     V3 go, V3* g0, V3* g1, V3* g2) {
+  // y^ = v / |v|, v = z^ x x^; z^ = w / |w|, w = x^ x c; x^ = u / |u|; u = r0 - o, c = r1 - o;  d(a x b): g_a = b x g, g_b = g x a
+  const V3 gv = (1.0 / aux.nv) * (gyh - dot(f.yh, gyh) * f.yh);
+  gzh = gzh + cross(f.xh, gv);
+  gxh = gxh + cross(gv, f.zh);
+  const V3 gw = (1.0 / aux.nw) * (gzh - dot(f.zh, gzh) * f.zh);
+  gxh = gxh + cross(aux.cvec, gw);
+  const V3 gc = cross(gw, f.xh);
+  const V3 gu = (1.0 / aux.nu) * (gxh - dot(f.xh, gxh) * f.xh);
+  const V3 gshare = (1.0 / 3.0) * (go - gu - gc);  // every site's share through the centre of geometry
+  *g0 = gshare + gu;
+  *g1 = gshare + gc;
+  *g2 = gshare;
+}
+
 // G(r~) of orientation.py:219-288 for p = o_i - o_j in frame F_j; returns |G - Gref|^2 contribution pieces.
 // out: G[4]; aux for the adjoint: rt (r~), rho, inside (rho < cutoff)
 __device__ __forceinline__ void ermsd_g(const ErmsdFrame& Fj, V3 p, double inv_a, double inv_b, double cutoff,
@@ -88,26 +125,26 @@ ermsd_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S, in
     P[t][0] = r.x; P[t][1] = r.y; P[t][2] = r.z;
   }
   __syncthreads();
-  // local reference systems (orientation.py:177-216): x = cog -> atom 0, z = x^ x (cog -> atom 1), y = z^ x x^
-  double nu = 0.0, nw = 0.0, nv = 0.0;
-  V3 cvec = v3(0, 0, 0);
+  // local reference systems (orientation.py:177-216).  Coarse-grained variant (ERMSDCG, orientation.py:380-560): the
+  // three sites first define a frame of their own in which the ideal C2 / C4 / C6 positions of the base are known
+  // (local_coordinates[sequence]); the eRMSD frame is then built on those reconstructed atoms.
+  const bool cg = cv.axis == 1;
+  FrameAux aux{}, aux_cg{};
+  ErmsdFrame f_cg{};
+  double lc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (tid < n) {
-    const V3 r0 = v3(P[3 * tid][0], P[3 * tid][1], P[3 * tid][2]);
-    const V3 r1 = v3(P[3 * tid + 1][0], P[3 * tid + 1][1], P[3 * tid + 1][2]);
-    const V3 r2 = v3(P[3 * tid + 2][0], P[3 * tid + 2][1], P[3 * tid + 2][2]);
-    ErmsdFrame f;
-    f.o = (1.0 / 3.0) * (r0 + r1 + r2);
-    const V3 u = r0 - f.o;
-    nu = norm(u);
-    f.xh = (1.0 / nu) * u;
-    cvec = r1 - f.o;
-    const V3 w = cross(f.xh, cvec);
-    nw = norm(w);
-    f.zh = (1.0 / nw) * w;
-    const V3 v = cross(f.zh, f.xh);
-    nv = norm(v);
-    f.yh = (1.0 / nv) * v;
-    F[tid] = f;
+    V3 r0 = v3(P[3 * tid][0], P[3 * tid][1], P[3 * tid][2]);
+    V3 r1 = v3(P[3 * tid + 1][0], P[3 * tid + 1][1], P[3 * tid + 1][2]);
+    V3 r2 = v3(P[3 * tid + 2][0], P[3 * tid + 2][1], P[3 * tid + 2][2]);
+    if (cg) {
+      f_cg = ermsd_make_frame(r0, r1, r2, &aux_cg);
+      const int base = (int)__ldg(cv.w + 36 + tid);
+      for (int q = 0; q < 9; ++q) lc[q] = __ldg(cv.w + 9 * base + q);
+      r0 = f_cg.o + lc[0] * f_cg.xh + lc[1] * f_cg.yh + lc[2] * f_cg.zh;  // orientation.py infer_base_coordinates
+      r1 = f_cg.o + lc[3] * f_cg.xh + lc[4] * f_cg.yh + lc[5] * f_cg.zh;
+      r2 = f_cg.o + lc[6] * f_cg.xh + lc[7] * f_cg.yh + lc[8] * f_cg.zh;
+    }
+    F[tid] = ermsd_make_frame(r0, r1, r2, &aux);
   }
   __syncthreads();
   // value
@@ -167,16 +204,15 @@ ermsd_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S, in
         go = go + ermsd_g_adjoint(fi, p2, rt, rho, inv_a, inv_b, gamma, gG, nullptr, nullptr, nullptr);
       }
     }
-    // back through frame j: y^ = v / |v|, v = z^ x x^; z^ = w / |w|, w = x^ x c; x^ = u / |u|; u = r0 - o, c = r1 - o
-    const V3 gv = (1.0 / nv) * (gyh - dot(fj.yh, gyh) * fj.yh);
-    gzh = gzh + cross(fj.xh, gv);  // d(a x b): g_a = b x g, g_b = g x a
-    gxh = gxh + cross(gv, fj.zh);
-    const V3 gw = (1.0 / nw) * (gzh - dot(fj.zh, gzh) * fj.zh);
-    gxh = gxh + cross(cvec, gw);
-    const V3 gc = cross(gw, fj.xh);
-    const V3 gu = (1.0 / nu) * (gxh - dot(fj.xh, gxh) * fj.xh);
-    const V3 gshare = (1.0 / 3.0) * (go - gu - gc);  // every ring atom's share through the centre of geometry
-    const V3 g0 = gshare + gu, g1 = gshare + gc, g2 = gshare;
+    V3 g0, g1, g2;
+    ermsd_frame_backward(fj, aux, gxh, gyh, gzh, go, &g0, &g1, &g2);
+    if (cg) {  // back through the reconstruction: V_m = o' + sum_l lc[m][l] axis'_l
+      const V3 go2 = g0 + g1 + g2;
+      const V3 gx2 = lc[0] * g0 + lc[3] * g1 + lc[6] * g2;
+      const V3 gy2 = lc[1] * g0 + lc[4] * g1 + lc[7] * g2;
+      const V3 gz2 = lc[2] * g0 + lc[5] * g1 + lc[8] * g2;
+      ermsd_frame_backward(f_cg, aux_cg, gx2, gy2, gz2, go2, &g0, &g1, &g2);
+    }
     double* out = cv.grad + 9 * (size_t)j;
     out[0] = g0.x; out[1] = g0.y; out[2] = g0.z;
     out[3] = g1.x; out[4] = g1.y; out[5] = g1.z;

@@ -974,3 +974,32 @@ def test_ermsd_harmonic(layout, dtype, nb):
     for frame in perturbed(snap, 3, 0.01):
         run.step(frame)
     assert float(run.state.xi[0, 0]) > 0.0
+
+
+@pytest.mark.parametrize("layout, nb", [("hoomd", 10), ("lammps", 17)])
+def test_ermsd_coarse_grained_harmonic(layout, nb):
+    """ERMSDCG (orientation.py:380-590): sites -> reconstructed ring atoms -> eRMSD, adjoints through both frame
+    constructions; dense Jacobian against autograd of the reference formula."""
+    import oracle
+    from parity_utils import oracle_snapshot
+
+    snap = snapshot(layout, np.float64, n=max(N, 3 * nb + 50))
+    rng = np.random.default_rng(100 + nb)
+    idx = rng.permutation(snap["arrays"]["positions"].shape[0])[: 3 * nb].tolist()
+    structure = _rna_like(nb, seed=nb + 1)
+    reference = structure + 0.03 * rng.normal(size=structure.shape)
+    sequence = rng.integers(0, 4, size=nb).tolist()
+    helpers, _ = oracle.backends.build_helpers(layout, {"positions", "indices"}, True)
+    rows = np.asarray(helpers.query(oracle_snapshot(snap)).indices).astype(np.int64)[np.asarray(idx)]
+    pos = snap["arrays"]["positions"]
+    pos[rows, :3] = structure.astype(pos.dtype)
+    img = snap["arrays"]["images"]
+    if img.ndim == 2:
+        img[rows] = 0
+    else:
+        img[rows] = 512 | (512 << 10) | (512 << 20)
+    specs = [("ERMSDCG", (idx, reference, sequence), dict(cutoff=2.4, a=0.5, b=0.3))]
+    run = ParityRun(snap, specs, harmonic(5.0, [0.3]))
+    for frame in perturbed(snap, 3, 0.01):
+        run.step(frame)
+    assert float(run.state.xi[0, 0]) > 0.0
