@@ -46,7 +46,7 @@ typedef enum {
   PSB_ERR_UNSUPPORTED = 5
 } psb_status;
 
-/* ---- collective variables: pysages/colvars/*.py ----------------------------------- */
+/* ---- collective variables: pysages/colvars/ (all modules) ----------------------------------- */
 typedef enum {
   PSB_CV_COMPONENT = 1,    /* colvars/coordinates.py:56-71   */
   PSB_CV_DISTANCE = 2,     /* colvars/coordinates.py:74-109  */
