@@ -494,6 +494,18 @@ def run_series(device, stream, hbm):
         measure(f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), name, natoms, steps, frames, L)
         del frames
 
+    # SURVEY.md 8d scaling series, third family: RadiusOfGyration over ALL atoms + metadynamics on a 1-D grid
+    # (general kernel class: non-point CV, per-atom gradient 2 r_i / n, grid lookup of the bias)
+    for natoms, steps in ((10_000, 2000), (100_000, 2000), (1_000_000, 500)):
+        nfr = 64 if natoms <= 100_000 else 8
+        frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 971)
+        rog = [("RadiusOfGyration", (list(range(natoms)),), {})]
+        md = dict(height=1.0, sigma=[L * L / 40.0], stride=500, ngaussians=64,
+                  grid=((0.0,), (L * L,), (256,), "regular"))
+        measure(f"RoG(all) + metadynamics on a 256-bin grid S=N={natoms} hoomd-f32", None, natoms, steps, frames, L,
+                specs=(rog, ("Metadynamics", md)))
+        del frames
+
     # row K (FUNN, funn.py:187-296): the headline workload with the force taken from a (2, 14, 14, 2)
     # tanh network evaluated inside the step kernel instead of the binned average
     def with_network(native):
