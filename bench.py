@@ -500,8 +500,8 @@ def run_series(device, stream, hbm):
         nfr = 64 if natoms <= 100_000 else 8
         frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 971)
         rog = [("RadiusOfGyration", (list(range(natoms)),), {})]
-        md = dict(height=1.0, sigma=[L * L / 40.0], stride=500, ngaussians=64,
-                  grid=((0.0,), (L * L,), (256,), "regular"))
+        md = dict(height=1.0, sigma=[L * L / 10.0], stride=500, ngaussians=64,
+                  grid=((0.0,), (4.0 * L * L,), (256,), "regular"))  # unwrapped <r.r> reaches a few L^2
         measure(f"RoG(all) + metadynamics on a 256-bin grid S=N={natoms} hoomd-f32", None, natoms, steps, frames, L,
                 specs=(rog, ("Metadynamics", md)))
         del frames

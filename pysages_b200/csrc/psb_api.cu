@@ -661,6 +661,9 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     default: h->step_method = gridded ? SM_METAD_GRID : SM_METAD_DIRECT; break;
   }
   h->step_general = (!M.all_point || !M.all_unique || layout->dense_outputs) ? SC_GENERAL : SC_POINT;
+  // the slot-ordered class also takes RadiusOfGyration groups next to point groups (not under ABF: its J J^T pass)
+  bool slot_kinds = M.all_unique && !layout->dense_outputs && method->kind != PSB_METHOD_ABF;
+  for (int c = 0; c < ncvs; ++c) slot_kinds = slot_kinds && (is_point(cvs[c].kind) || cvs[c].kind == PSB_CV_ROG);
   const int occ = pick_vtable(*layout)->occupancy(h->step_method, h->step_general, h->dyn_smem);
   if (occ < 1)
     return bail(fail(PSB_ERR_CUDA, "step kernel cannot be made resident (%s)", cudaGetErrorString(cudaGetLastError())));
@@ -684,7 +687,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   // slot-ordered gather/scatter (psb_step.cuh): worth it when most atoms are selected and the terms do
   // not fit the register cache; PSB_SLOT_MAJOR=1 forces it wherever it is valid (tests), =0 disables it
   {
-    const bool eligible = h->grid > 1 && !h->step_general && !method->shared_hills && ng <= 4 &&
+    const bool eligible = h->grid > 1 && (!h->step_general || slot_kinds) && !method->shared_hills && ng <= 4 &&
                           layout->natoms < 0xFFFFFFF0LL;
     bool wanted = (long long)M.T > (long long)CT * BLOCK * h->grid && 2LL * M.T >= layout->natoms;
     // OpenMM-CUDA: `ids` already IS slot -> atom, so the slot-ordered passes need no tag -> slot inverse at

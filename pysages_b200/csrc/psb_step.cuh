@@ -360,7 +360,14 @@ static __device__ __forceinline__ void finalize_cv_A(const Model& M, StepShared&
     }
     return;
   }
-  if (!GENERAL) return;
+  if (!GENERAL) {
+    // the slot-ordered class also takes RadiusOfGyration groups (shape.py:52-57: sum r.r / n; d/dr_i = 2 r_i / n)
+    if (kind == PSB_CV_ROG) {
+      f.xi[cv.comp0] = sh.tot[g0][0] * M.grp[g0].inv_n;
+      f.cvx[c][0] = 2.0 * M.grp[g0].inv_n;
+    }
+    return;
+  }
   switch (kind) {
     case PSB_CV_ROG: {  // shape.py:52-57: sum r.r / n ; d/dr_i = 2 r_i / n
       f.xi[cv.comp0] = sh.tot[g0][0] * M.grp[g0].inv_n;
@@ -1124,6 +1131,11 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
   const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
   uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
+  // slot-ordered class: groups whose CV is RadiusOfGyration (bit g); all others are point groups
+  uint32_t rog_bits = 0;
+  if (SLOT)
+    for (int g = 0; g < M.ngroups && g < 4; ++g)
+      if (M.cv[M.grp[g].cv].kind == PSB_CV_ROG) rog_bits |= 1u << g;
   auto slot_word = [&](uint32_t sl) -> uint32_t {  // stamp | group + 1 when slot `sl` holds a selected atom
     if constexpr (TAGMAP) {
       const uint32_t tag = (uint32_t)__ldg(reinterpret_cast<const int*>(S.ids) + sl);
@@ -1230,9 +1242,11 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         const bool hit = (base + u * BLOCK < s_hi) && ((e[u] & ~15u) == stamp);
         const int g = hit ? (int)(e[u] & 15u) - 1 : -1;
 #pragma unroll
+        const double rr = r[u].x * r[u].x + r[u].y * r[u].y + r[u].z * r[u].z;
+#pragma unroll
         for (int gg = 0; gg < 4; ++gg) {  // branch-free select: lanes of a warp hold different groups
           const double w = (g == gg) ? 1.0 : 0.0;
-          acc4[gg][0] = fma(w, r[u].x, acc4[gg][0]);
+          acc4[gg][0] = fma(w, (rog_bits >> gg) & 1u ? rr : r[u].x, acc4[gg][0]);  // RoG groups: sum of r.r
           acc4[gg][1] = fma(w, r[u].y, acc4[gg][1]);
           acc4[gg][2] = fma(w, r[u].z, acc4[gg][2]);
           if (momenta_sums) {
@@ -1709,21 +1723,33 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
 #define PSB_SLOT_SUS 8
 #endif
       constexpr int SU = PSB_SLOT_SUS;
+      // -F dxi/dr_i = rs_g * r_i for the atoms of RoG group g (scalars, selected without indexing an array)
+      double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0, rs3 = 0.0;
+      if (rog_bits) {
+        auto scale_of = [&](int g) {
+          return ((rog_bits >> g) & 1u) ? -f.F[M.cv[M.grp[g].cv].comp0] * f.cvx[M.grp[g].cv][0] : 0.0;
+        };
+        rs0 = scale_of(0); rs1 = scale_of(1); rs2 = scale_of(2); rs3 = scale_of(3);
+      }
       for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
         uint32_t e[SU];
         FV fv[SU];
+        V3 rp[SU];
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
           const uint32_t sl = min(base + u * BLOCK, s_hi - 1);
           e[u] = slot_word(sl);
           fv[u] = A::load_force(S, sl);
+          rp[u] = rog_bits ? A::position(S, sl) : v3(0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
           const uint32_t sl = base + u * BLOCK;
           if (sl < s_hi && (e[u] & ~15u) == stamp) {
             const int g = (int)(e[u] & 15u) - 1;
-            A::store_force(S, sl, fv[u], v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]));
+            V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
+            if (rog_bits && ((rog_bits >> g) & 1u)) fo = (g == 0 ? rs0 : (g == 1 ? rs1 : (g == 2 ? rs2 : rs3))) * rp[u];
+            A::store_force(S, sl, fv[u], fo);
           }
         }
       }

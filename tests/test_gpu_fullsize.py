@@ -153,3 +153,52 @@ def test_cfg4_rmsd_rog_50k_direct_hills_against_oracle_and_numpy():
     for f in range(4):
         run.step(traj[f])
     assert int(run.state.idx) == H - 4
+
+
+@pytest.mark.parametrize("layout", ["hoomd", "openmm-cuda"])
+def test_radius_of_gyration_slot_ordered_against_general_class(layout, monkeypatch):
+    """RadiusOfGyration over all atoms + a Distance CV + grid metadynamics: the slot-ordered class (sum of r.r in
+    slot order, force rog_scale * r_i from a second streaming read of the positions) against the general class
+    (tag-ordered gather), which the parity suite checks against the oracle.  OpenMM: the tag -> group table path."""
+    import bench
+
+    monkeypatch.delenv("PSB_GRID_BLOCKS", raising=False)
+    n = 300_000
+    dev = torch.device("cuda:0")
+    if layout == "hoomd":
+        frames, L, _ = bench.device_hoomd_frames(n, 1, dev, seed=11)
+        snaps = bench.snapshots_of(frames, L, 0.005)
+        forces = frames[0]["forces"]
+    else:
+        snaps, L = bench.device_layout_snapshots(layout, np.float32, n, 1, dev, seed=12)
+        forces = snaps[0].forces
+    half = n // 2
+    cvs = [("RadiusOfGyration", (list(range(0, half)),), {}),
+           ("Distance", ([list(range(half, half + n // 4)), list(range(half + n // 4, n))],), {})]
+    # (the image flags put unwrapped coordinates up to 1.5 L from the origin: <r.r> reaches a few L^2)
+    md = dict(height=1.0e6, sigma=[L * L / 10.0, 0.5], stride=2, ngaussians=16,
+              grid=((0.0, 0.0), (4.0 * L * L, L), (64, 32), "regular"))
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "0")
+    _, general = bench.build_ours(cvs, ("Metadynamics", md), snaps[0], layout=layout)
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "1")
+    _, slot = bench.build_ours(cvs, ("Metadynamics", md), snaps[0], layout=layout)
+    assert slot.launch_info()["grid_blocks"] > 1
+    f0 = forces.clone()
+    positions = snaps[0].positions
+    p0 = positions.clone()
+    outs = []
+    for native in (general, slot):
+        forces.copy_(f0)
+        positions.copy_(p0)
+        for _ in range(3):  # call 3 deposits a hill (stride 2) at the current xi
+            native.step(snaps[0])
+        positions[:, 0] += 0.05  # move off the hill centre: the bias force is non-zero now
+        native.step(snaps[0])
+        torch.cuda.synchronize()
+        outs.append((native.view("xi").cpu().numpy().copy(), native.view("cv_force").cpu().numpy().copy(),
+                     forces.cpu().numpy().astype(np.float64).copy()))
+    close(outs[1][0], outs[0][0], 1e-12, what="xi slot- vs tag-ordered")
+    close(outs[1][1], outs[0][1], 1e-9, what="generalized force slot- vs tag-ordered")
+    scale = np.abs(outs[0][2] - f0.cpu().numpy().astype(np.float64)).max()
+    assert scale > 0  # the bias was applied
+    assert np.abs(outs[1][2] - outs[0][2]).max() <= max(2e-7 * np.abs(outs[0][2]).max(), 4.0 if layout != "hoomd" else 0.0)
