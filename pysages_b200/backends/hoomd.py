@@ -1,160 +1,192 @@
 """
-HOOMD-blue adapter (drop-in for pysages/backends/hoomd.py): binds a sampling method to a HOOMD
-simulation through the `hoomd.dlext` plugin.  Same public surface as the reference -- `Sampler`
-with `state`, `snapshot`, `callback`, `take_snapshot()`, `restore()`, and `bind()` / `detach()` --
-but the per-step callback makes ONE native call on the arrays HOOMD exposes (zero copy) instead of
-`method_update` (XLA) + `sync_backend` + `block_until_ready` + cupy add (hoomd.py:168-173,219-230).
+HOOMD-blue adapter: binds a sampling method to a HOOMD simulation through the `hoomd.dlext` plugin
+(the role of pysages/backends/hoomd.py; same `bind()` / `detach()` / `Sampler` surface).
 
-Requires `hoomd` and `hoomd.dlext` (third-party, not shipped here); importing this module without
-them raises ImportError, and a CPU-only HOOMD build is rejected: there is no CPU bias path.
-HOOMD launches its kernels on the legacy default stream, which is also torch's current stream in
-the stepping thread, so the bias step is ordered after the force computation and before the second
-half of the integrator without any host synchronisation.
+Per step the plugin calls `Sampler.on_half_step(positions, vel_mass, rtags, images, forces, timestep)`
+with five DLPack capsules (argument order of hoomd.py:159-168).  The adapter does not turn them into
+arrays: it reads the five device addresses out of the capsules, refreshes the pre-filled `psb_snapshot`
+when HOOMD has moved a buffer (it double-buffers while sorting particles), and makes one native call.
+HOOMD issues its kernels on the legacy default stream, which is also torch's current stream in the
+stepping thread, so the bias lands between the force computation and the second half step by stream
+order alone: no `sync_backend()` / `block_until_ready()` / `sync_forces()` (hoomd.py:219-230).
+
+Needs `hoomd` and `hoomd.dlext` (third party, not shipped here); a CPU-only HOOMD build is rejected,
+there is no CPU bias path.
 """
 
 from warnings import warn
 
 import hoomd
-from hoomd import md
-from hoomd.dlext import AccessLocation, AccessMode, DLExtSampler, SystemView
+from hoomd import dlext as _dlext
 
-from ._common import LAYOUTS, fused_helpers, tensor_from_capsule
-from .snapshot import Box, Snapshot, copy
-from .snapshot import restore as _restore
+from . import _common as C
+from .snapshot import Box, Snapshot
 
-SamplerBase = DLExtSampler
-CONTEXTS_SAMPLERS = {}
-
-# ---- HOOMD 2.x / 3.x+ API differences (hoomd.py:33-78) -------------------------------------------
-if getattr(hoomd, "__version__", "").startswith("2."):
-
-    def is_on_gpu(context):
-        return context.on_gpu()
-
-    def get_integrator(context):
-        return context.integrator
-
-    def get_run_method(context):
-        return hoomd.run
-
-    def get_system(context):
-        return context.system
-
-    def set_half_step_hook(context, hook):
-        context.integrator.cpp_integrator.setHalfStepHook(hook)
-
-    def remove_half_step_hook(context):
-        context.integrator.cpp_integrator.removeHalfStepHook()
-
-else:
-    if not hasattr(hoomd.dlext, "__version__"):
-
-        class SamplerBase(DLExtSampler, md.HalfStepHook):  # noqa: F811
-            def __init__(self, sysview, update, location, mode):
-                md.HalfStepHook.__init__(self)
-                DLExtSampler.__init__(self, sysview, update, location, mode)
-
-    def is_on_gpu(context):
-        return not isinstance(context.device, hoomd.device.CPU)
-
-    def get_integrator(context):
-        return context.operations.integrator
-
-    def get_run_method(context):
-        context.run(0)  # make sure the simulation is fully initialised
-        return context.run
-
-    def get_system(context):
-        return context._cpp_sys
-
-    def set_half_step_hook(context, hook):
-        context.operations.integrator.half_step_hook = hook
-
-    def remove_half_step_hook(context):
-        context.operations.integrator.half_step_hook = None
+AccessLocation, AccessMode = _dlext.AccessLocation, _dlext.AccessMode
 
 
-def default_location():
-    if not hasattr(AccessLocation, "OnDevice"):
-        raise RuntimeError("pysages_b200 needs a CUDA-enabled HOOMD-blue / hoomd-dlext build (no CPU bias path)")
-    return AccessLocation.OnDevice
+class _ApiV2:
+    """hoomd 2.x: global `hoomd.run`, the SimulationContext owns system and integrator (hoomd.py:33-56)."""
+
+    @staticmethod
+    def on_gpu(sim):
+        return sim.on_gpu()
+
+    @staticmethod
+    def integrator(sim):
+        return sim.integrator
+
+    @staticmethod
+    def runner(sim):
+        return hoomd.run  # acts on the currently entered context: SamplingContext forwards __enter__/__exit__
+
+    @staticmethod
+    def cpp_system(sim):
+        return sim.system
+
+    @staticmethod
+    def install(sim, hook):
+        sim.integrator.cpp_integrator.setHalfStepHook(hook)
+
+    @staticmethod
+    def remove(sim):
+        sim.integrator.cpp_integrator.removeHalfStepHook()
 
 
-class Sampler(SamplerBase):
-    """HalfStepHook connecting a pysages_b200 sampling method to a HOOMD-blue simulation."""
+class _ApiV3:
+    """hoomd >= 3: everything hangs off `hoomd.Simulation` (hoomd.py:58-90)."""
 
-    def __init__(self, context, sampling_method, callback=None, location=None):
-        location = default_location() if location is None else location
-        if not is_on_gpu(context) or location != AccessLocation.OnDevice:
+    @staticmethod
+    def on_gpu(sim):
+        return not isinstance(sim.device, hoomd.device.CPU)
+
+    @staticmethod
+    def integrator(sim):
+        return sim.operations.integrator
+
+    @staticmethod
+    def runner(sim):
+        sim.run(0)  # attaches operations, so the first real step finds the hook in place
+        return sim.run
+
+    @staticmethod
+    def cpp_system(sim):
+        return sim._cpp_sys
+
+    @staticmethod
+    def install(sim, hook):
+        sim.operations.integrator.half_step_hook = hook
+
+    @staticmethod
+    def remove(sim):
+        sim.operations.integrator.half_step_hook = None
+
+
+API = _ApiV2 if str(getattr(hoomd, "__version__", "3")).startswith("2.") else _ApiV3
+
+# hoomd-dlext releases without a version attribute predate its own HalfStepHook base: the sampler then has to
+# derive from hoomd.md.HalfStepHook as well to be accepted by the integrator (hoomd.py:60-67)
+_BASES = (_dlext.DLExtSampler,)
+if API is _ApiV3 and not hasattr(_dlext, "__version__"):
+    _BASES = (_dlext.DLExtSampler, hoomd.md.HalfStepHook)
+
+SAMPLERS = {}            # simulation -> Sampler
+CONTEXTS_SAMPLERS = SAMPLERS  # the reference's name for the same table
+
+
+class Sampler(C.SamplerCore, *_BASES):
+    """Half-step hook that runs the fused bias step on HOOMD's own buffers."""
+
+    ordering = "stream"
+
+    def __init__(self, simulation, sampling_method, callback=None, location=None):
+        if not hasattr(AccessLocation, "OnDevice"):
+            raise RuntimeError("pysages_b200 needs a CUDA-enabled HOOMD-blue / hoomd-dlext build (no CPU bias path)")
+        location = AccessLocation.OnDevice if location is None else location
+        if location != AccessLocation.OnDevice or not API.on_gpu(simulation):
             raise RuntimeError("pysages_b200 runs the bias step on the GPU only: use a hoomd GPU device")
-        self.context = context
-        self.callback = callback
+        self.context = simulation
         self.location = location
-        self.view = SystemView(get_system(context))
-        self.box = Box(*get_global_box(self.view))
-        self.dt = get_timestep(context)
-        self.update_box = lambda: self.box  # NOTE: extend for NPT simulations (hoomd.py:123)
-        super().__init__(self.view, self._update_callback, location, AccessMode.Read)
+        self.view = _dlext.SystemView(API.cpp_system(simulation))
+        self.box = Box(*global_box(self.view))
+        self.dt = API.integrator(simulation).dt
+        self.update_box = lambda: self.box  # constant-volume runs; replace for NPT (hoomd.py:123)
+        for base in _BASES[1:]:
+            base.__init__(self)
+        _dlext.DLExtSampler.__init__(self, self.view, self.on_half_step, location, AccessMode.Read)
+        self._last = None
+        self._bind_method(sampling_method, C.LAYOUTS["hoomd"], callback)
 
-        snapshot = self.take_snapshot()
-        _, initialize, self._method_update = sampling_method.build(snapshot, fused_helpers(LAYOUTS["hoomd"]))
-        self.state = initialize()
+    # ---- plugin callbacks: (positions, vel_mass, rtags, images, forces, timestep) -----------------
+    def on_half_step(self, positions, vel_mass, rtags, images, forces, timestep):
+        if not self._fused:
+            return self.advance_snapshot(self._wrap(positions, vel_mass, rtags, images, forces), timestep)
+        (p, n, dev), (v, _, _), (r, _, _), (i, _, _), (f, _, _) = (
+            C.capsule_address(c) for c in (positions, vel_mass, rtags, images, forces))
+        if n != self._native.natoms or dev != C.KDL_CUDA:
+            raise RuntimeError(f"HOOMD now exposes {n} particles on device type {dev}; the method was built for "
+                               f"{self._native.natoms} on the GPU")
+        self._last = (positions, vel_mass, rtags, images, forces)
 
-    def restore(self, prev_snapshot):
-        self.snapshot = prev_snapshot
-        self.forward_data(self._restore_callback, self.location, AccessMode.Overwrite, 0)
+        def fill(d):
+            d.positions, d.vel_mass, d.ids, d.images, d.forces = p, v, r, i, f
+            H = self.update_box().H
+            d.box_diag[0], d.box_diag[1], d.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
+            d.dt = float(self.dt)
 
-    def take_snapshot(self):
-        self.forward_data(self._snapshot_callback, self.location, AccessMode.Read, 0)
-        return self.snapshot
+        try:
+            self.advance_pointers(timestep, (p, v, r, i, f), fill)
+        finally:
+            self._last = None  # HOOMD's capsules are only valid inside the half step (hoomd.py:164-166)
 
-    def _pack_snapshot(self, positions, vel_mass, forces, rtags, images):
-        t = tensor_from_capsule
+    def _wrap(self, positions, vel_mass, rtags, images, forces):
+        t = C.tensor_from_capsule
         return Snapshot(t(positions), t(vel_mass), t(forces), t(rtags), self.update_box(), self.dt,
                         dict(images=t(images)))
 
-    # the plugin's argument order differs from Snapshot's field order (hoomd.py:159)
-    def _restore_callback(self, positions, vel_mass, rtags, images, forces, _):
-        _restore(self._pack_snapshot(positions, vel_mass, forces, rtags, images), self.snapshot)
+    def _views(self):
+        """Zero-copy views of HOOMD's current buffers: inside a half step the capsules of that step, otherwise a
+        fresh `forward_data` round trip (hoomd.py:141-146)."""
+        if self._last is not None:
+            caps, self._last = self._last, None
+            return self._wrap(*caps)
+        out = []
+        self.forward_data(lambda p, v, r, i, f, _: out.append(self._wrap(p, v, r, i, f)), self.location,
+                          AccessMode.Read, 0)
+        return out[0]
 
-    def _snapshot_callback(self, positions, vel_mass, rtags, images, forces, _):
-        self.snapshot = copy(self._pack_snapshot(positions, vel_mass, forces, rtags, images))
+    def restore(self, prev_snapshot):
+        def overwrite(p, v, r, i, f, _):
+            C.restore_arrays(self._wrap(p, v, r, i, f), prev_snapshot)
 
-    def _update_callback(self, positions, vel_mass, rtags, images, forces, timestep):
-        snapshot = self._pack_snapshot(positions, vel_mass, forces, rtags, images)
-        self.state = self._method_update(snapshot, self.state, timestep)  # CVs + bias + in-place force update
-        if self.callback:
-            self.callback(snapshot, self.state, timestep)
-
-
-def get_global_box(system_view):
-    """hoomd.py:243-253"""
-    box = system_view.particle_data.getGlobalBox()
-    L = box.getL()
-    xy, xz, yz = box.getTiltFactorXY(), box.getTiltFactorXZ(), box.getTiltFactorYZ()
-    lo = box.getLo()
-    H = ((L.x, xy * L.y, xz * L.z), (0.0, L.y, yz * L.z), (0.0, 0.0, L.z))
-    return H, (lo.x, lo.y, lo.z)
+        self.forward_data(overwrite, self.location, AccessMode.Overwrite, 0)
+        self.snapshot = prev_snapshot
 
 
-def get_timestep(context):
-    return get_integrator(context).dt
+def global_box(system_view):
+    """Upper-triangular box matrix and origin from HOOMD's BoxDim (hoomd.py:243-253)."""
+    dim = system_view.particle_data.getGlobalBox()
+    L, lo = dim.getL(), dim.getLo()
+    xy, xz, yz = dim.getTiltFactorXY(), dim.getTiltFactorXZ(), dim.getTiltFactorYZ()
+    return ((L.x, xy * L.y, xz * L.z), (0.0, L.y, yz * L.z), (0.0, 0.0, L.z)), (lo.x, lo.y, lo.z)
+
+
+get_global_box = global_box
 
 
 def bind(sampling_context, callback, **kwargs):
-    """hoomd.py:261-271"""
-    context = sampling_context.context
-    sampler = Sampler(context, sampling_context.method, callback)
-    set_half_step_hook(context, sampler)
-    CONTEXTS_SAMPLERS[context] = sampler
-    sampling_context.run = get_run_method(context)
+    """Entry point used by SamplingContext (hoomd.py:261-271)."""
+    sim = sampling_context.context
+    sampler = Sampler(sim, sampling_context.method, callback)
+    API.install(sim, sampler)
+    SAMPLERS[sim] = sampler
+    sampling_context.run = API.runner(sim)
     return sampler
 
 
-def detach(context):
+def detach(simulation):
     """hoomd.py:274-284"""
-    if context in CONTEXTS_SAMPLERS:
-        remove_half_step_hook(context)
-        del CONTEXTS_SAMPLERS[context]
-    else:
+    if SAMPLERS.pop(simulation, None) is None:
         warn("This context has no sampler bound to it.")
+    else:
+        API.remove(simulation)

@@ -1,97 +1,94 @@
 """
-LAMMPS adapter (drop-in for pysages/backends/lammps.py) on top of the `lammps.dlext` fix.
+LAMMPS adapter on top of the `lammps.dlext` fix (the role of pysages/backends/lammps.py).
 
-With Kokkos-CUDA the fix exposes device arrays that are used in place; otherwise the host arrays
-are staged through the GPU every step (psb_step_host).  Layout: x, v, f (N, 3) doubles, `tags_map`
-(tag t at index t + 1), packed image flags, per-type masses + per-atom types; force units follow
-lammps.py:33,137-139.
+With Kokkos-CUDA the fix exposes device arrays that are used in place; otherwise the host arrays are
+staged through the GPU every step (psb_step_host).  Layout: x, v, f (N, 3) doubles, `tags_map` (tag t at
+index t + 1), packed image flags, per-type masses + per-atom types; force units follow lammps.py:33,137-139.
+Ordering on the device: `view.synchronize()` before the step, and the host waits for the bias kernel after
+it (the reference's `sync_forces()`, lammps.py:163-170): Kokkos may integrate on an execution-space
+instance of its own.
 """
 
 import weakref
 
 from lammps import dlext
-from lammps.dlext import ExecutionSpace, FixDLExt, LAMMPSView, has_kokkos_cuda_enabled
 
-from ._common import LAMMPS_CONVERSION, LAYOUTS, fused_helpers, tensor_from_capsule
-from .snapshot import Box, Snapshot, copy
-from .snapshot import restore as _restore
+from . import _common as C
+from .snapshot import Box, Snapshot
 
-kDefaultLocation = dlext.kOnHost if not hasattr(ExecutionSpace, "kOnDevice") else dlext.kOnDevice
-
-
-class Sampler(FixDLExt):
-    """LAMMPS fix connecting a pysages_b200 sampling method to a LAMMPS instance."""
-
-    def __init__(self, context, sampling_method, callback=None, location=kDefaultLocation):
-        super().__init__(context)
-        on_gpu = (location != dlext.kOnHost) and bool(has_kokkos_cuda_enabled(context))
-        self.context = context
-        self.location = location if on_gpu else dlext.kOnHost
-        self.view = LAMMPSView(context)
-        self.callback = callback
-        self.snapshot = self.take_snapshot()
-        layout = LAYOUTS["lammps"]
-        units = context.extract_global("units")
-        if units in LAMMPS_CONVERSION:
-            layout = layout._replace(force_unit_factor=LAMMPS_CONVERSION[units])
-        _, initialize, method_update = sampling_method.build(self.snapshot, fused_helpers(layout))
-        self.state = initialize()
-        self._update_box = lambda: self.snapshot.box
-
-        def update(timestep):
-            self.view.synchronize()
-            self.snapshot = self._update_snapshot()
-            self.state = method_update(self.snapshot, self.state, timestep)
-            if self.callback:
-                self.callback(self.snapshot, self.state, timestep)
-
-        self.set_callback(update)
-
-    def _partial_snapshot(self, include_masses=False):
-        v, loc, t = self.view, self.location, tensor_from_capsule
-        positions, types = t(dlext.positions(v, loc)), t(dlext.types(v, loc))
-        velocities, forces = t(dlext.velocities(v, loc)), t(dlext.forces(v, loc))
-        tags_map, images = t(dlext.tags_map(v, loc)), t(dlext.images(v, loc))
-        masses = t(dlext.masses(v, loc)) if include_masses else None
-        return Snapshot(positions, (velocities, (masses, types)), forces, tags_map, None, None, dict(images=images))
-
-    def _update_snapshot(self):
-        s = self._partial_snapshot()
-        velocities, (_, types) = s.vel_mass
-        _, (masses, _) = self.snapshot.vel_mass
-        return Snapshot(s.positions, (velocities, (masses, types)), s.forces, s.ids[1:], self._update_box(),
-                        self.snapshot.dt, s.extras)
-
-    def restore(self, prev_snapshot):
-        _restore(self.snapshot, prev_snapshot)
-
-    def take_snapshot(self):
-        s = self._partial_snapshot(include_masses=True)
-        box = Box(*get_global_box(self.context))
-        # the arrays stay views of the engine's buffers; use `copy()` for a persistent snapshot
-        return Snapshot(s.positions, s.vel_mass, s.forces, s.ids[1:], box, get_timestep(self.context), s.extras)
-
-    def copy_snapshot(self):
-        return copy(self.snapshot)
+# The native step unpacks LAMMPS' SMALLBIG image word: 10 + 10 + 12 bits, offset 512 (lammps.py:188-202 reads
+# the same constants from the plugin).  A BIGBIG build (64-bit words, 21-bit fields) would be unwrapped wrongly.
+_IMAGE_PACKING = dict(kImgBitSize=32, kImgBits=10, kImg2Bits=20, kImgMask=1023, kImgMax=512)
 
 
-def get_global_box(context):
-    """lammps.py:225-233"""
-    boxlo, boxhi, xy, yz, xz, *_ = context.extract_box()
-    Lx, Ly, Lz = (boxhi[i] - boxlo[i] for i in range(3))
-    H = ((Lx, xy * Ly, xz * Lz), (0.0, Ly, yz * Lz), (0.0, 0.0, Lz))
-    return H, boxlo
+def check_image_packing():
+    seen = {name: getattr(dlext, name) for name in _IMAGE_PACKING if hasattr(dlext, name)}
+    bad = {name: v for name, v in seen.items() if int(v) != _IMAGE_PACKING[name]}
+    if bad:
+        raise RuntimeError(f"this LAMMPS build packs image flags as {bad}; pysages_b200 supports the 32-bit "
+                           f"SMALLBIG packing {_IMAGE_PACKING} only")
 
 
-def get_timestep(context):
-    return context.extract_global("dt")
+class Sampler(C.SamplerCore, dlext.FixDLExt):
+    ordering = "host"
+
+    def __init__(self, lmp, sampling_method, callback=None, location=None):
+        dlext.FixDLExt.__init__(self, lmp)
+        check_image_packing()
+        device_ok = hasattr(dlext.ExecutionSpace, "kOnDevice") and bool(dlext.has_kokkos_cuda_enabled(lmp))
+        wanted = dlext.kOnDevice if location is None and device_ok else (dlext.kOnHost if location is None else location)
+        self.location = wanted if device_ok else dlext.kOnHost
+        self.context = lmp
+        self.view = dlext.LAMMPSView(lmp)
+        self.box = Box(*global_box(lmp))
+        self.dt = lmp.extract_global("dt")
+        self._masses = None
+        layout = C.LAYOUTS["lammps"]
+        factor = C.LAMMPS_CONVERSION.get(lmp.extract_global("units"))
+        if factor is not None:
+            layout = layout._replace(force_unit_factor=factor)
+        self._bind_method(sampling_method, layout, callback)
+        self.set_callback(self.on_post_force)
+
+    def _views(self):
+        """LAMMPS may reallocate per-atom arrays between steps: the capsules are asked for again every time
+        (lammps.py:87-113); per-type masses do not change."""
+        t, v, loc = C.tensor_from_capsule, self.view, self.location
+        if self._masses is None:
+            self._masses = t(dlext.masses(v, loc))
+        tags_map = t(dlext.tags_map(v, loc))
+        return Snapshot(t(dlext.positions(v, loc)), (t(dlext.velocities(v, loc)), (self._masses, t(dlext.types(v, loc)))),
+                        t(dlext.forces(v, loc)), tags_map[1:], self.box, self.dt, dict(images=t(dlext.images(v, loc))))
+
+    def on_post_force(self, timestep):
+        self.view.synchronize()
+        views = self._views()
+        if self._fused:
+            key = (views.positions.data_ptr(), views.forces.data_ptr(), views.ids.data_ptr(),
+                   views.vel_mass[0].data_ptr(), views.vel_mass[1][1].data_ptr(), views.extras["images"].data_ptr())
+            self._current = views
+            self.advance_pointers(timestep, key, lambda d: self.describe_into(views))
+        else:
+            self.advance_snapshot(views, timestep)
+
+
+def global_box(lmp):
+    """Box matrix and lower corner from `extract_box` (lammps.py:225-233)."""
+    lo, hi, xy, yz, xz, *_ = lmp.extract_box()
+    Lx, Ly, Lz = (hi[d] - lo[d] for d in range(3))
+    return ((Lx, xy * Ly, xz * Lz), (0.0, Ly, yz * Lz), (0.0, 0.0, Lz)), lo
+
+
+get_global_box = global_box
 
 
 def bind(sampling_context, callback, **kwargs):
-    """lammps.py:241-268"""
-    context = sampling_context.context
-    sampler = Sampler(context, sampling_context.method, callback)
-    sampling_context.run = lambda n, **kw: context.command(f"run {n}")
-    context.__exit__ = lambda *args: None  # keep the instance alive after `with`
-    weakref.finalize(context, context.finalize)
+    """SamplingContext entry point (lammps.py:241-268)."""
+    lmp = sampling_context.context
+    sampler = Sampler(lmp, sampling_context.method, callback)
+    sampling_context.run = lambda n, **kw: lmp.command(f"run {int(n)}")
+    # `with SamplingContext(...)` must not close the instance (results are read afterwards): it is finalized
+    # when the last reference goes away instead
+    lmp.__exit__ = lambda *exc: None
+    weakref.finalize(lmp, lmp.finalize)
     return sampler

@@ -7,19 +7,18 @@ or benchmark environment, so these classes stand in for them at the plugin bound
 calls the installed hook with DLPack capsules the way the plugins do
 (hoomd.dlext.DLExtSampler.forward_data -> cb(positions, vel_mass, rtags, images, forces, timestep),
 pysages/backends/hoomd.py:159-173; openmm_dlext.Force callback, openmm.py:50-56; lammps FixDLExt,
-lammps.py:79-95).  The `Sampler` below is the drop-in for the reference's per-backend samplers:
-same attributes (`state`, `snapshot`, `callback`, `take_snapshot`, `restore`) and the same
-callback order (method update -> bias -> user callback).
+lammps.py:79-95).  The `Sampler` below drives the same
+`SamplerCore` as the real adapters: same attributes (`state`, `snapshot`, `callback`, `take_snapshot`,
+`restore`) and the same callback order (fused method update + bias -> user callback).
 """
 
 import numpy as np
 import torch
 from torch.utils.dlpack import from_dlpack, to_dlpack
 
-from .. import _native as N
-from .snapshot import Box, HelperMethods, Layout, Snapshot, copy, restore
-
-from ._common import LAMMPS_CONVERSION, LAYOUTS  # noqa: E402,F401
+from . import _common as C
+from ._common import LAMMPS_CONVERSION, LAYOUTS  # noqa: F401
+from .snapshot import Box, Snapshot
 
 
 class MockEngine:
@@ -107,29 +106,26 @@ class MockEngine:
             self.timestep += 1
 
 
-class Sampler:
-    """Per-step driver (hoomd.py:93-173, openmm.py:32-89, lammps.py:37-127)."""
+class Sampler(C.SamplerCore):
+    """Per-step driver for the stand-in engines: the same `SamplerCore` the real adapters use (hoomd.py, openmm.py,
+    lammps.py), fed with the capsules `MockEngine.capsules()` hands out the way the plugins do."""
+
+    ordering = "stream"  # MockEngine works on torch's current stream
 
     def __init__(self, context, sampling_method, callback=None):
         self.context = context
-        self.callback = callback
-        self.layout = LAYOUTS[context.layout_name]
+        layout = LAYOUTS[context.layout_name]
         if context.layout_name == "lammps" and context.units in LAMMPS_CONVERSION:
-            self.layout = self.layout._replace(force_unit_factor=LAMMPS_CONVERSION[context.units])
+            layout = layout._replace(force_unit_factor=LAMMPS_CONVERSION[context.units])
         self.box = Box(*context.get_global_box())
         self.dt = context.dt
-        self.update_box = lambda: self.box  # NOTE: extend for NPT simulations (hoomd.py:123)
+        self.update_box = lambda: self.box  # constant-volume runs
+        self._bind_method(sampling_method, layout, callback)
 
-        snapshot = self.take_snapshot()
-        helpers, self._restore, self._bias = build_helpers(context, sampling_method, self.layout)
-        _, initialize, method_update = sampling_method.build(snapshot, helpers)
-        self.state = initialize()
-        self._method_update = method_update
-
-    def _pack_snapshot(self):
-        """Re-wrap the plugin's capsules (zero copy), like hoomd.py:148-157 / lammps.py:87-101."""
+    def _pack_snapshot(self, caps=None):
+        """Wrap the plugin's capsules (zero copy), like hoomd.py:148-157 / lammps.py:87-101."""
         name = self.context.layout_name
-        caps = [from_dlpack(c) for c in self.context.capsules()]
+        caps = [from_dlpack(c) for c in (self.context.capsules() if caps is None else caps)]
         if name == "hoomd":
             positions, vel_mass, rtags, images, forces = caps
             return Snapshot(positions, vel_mass, forces, rtags, self.update_box(), self.dt, dict(images=images))
@@ -143,46 +139,30 @@ class Sampler:
         return Snapshot(positions, (velocities, (masses, types)), forces, tags_map[1:], self.update_box(),
                         self.dt, dict(images=images))
 
-    def take_snapshot(self):
-        self.snapshot = copy(self._pack_snapshot())
-        return self.snapshot
+    _views = _pack_snapshot
 
-    def restore(self, prev_snapshot):
-        self._restore(self._pack_snapshot(), prev_snapshot)
-        self.snapshot = prev_snapshot
+    def on_hoomd_half_step(self, positions, vel_mass, rtags, images, forces, timestep):
+        """The hoomd.dlext callback signature (hoomd.py:159-168) on the pointer-only fast path."""
+        (p, _, _), (v, _, _), (r, _, _), (i, _, _), (f, _, _) = (
+            C.capsule_address(c) for c in (positions, vel_mass, rtags, images, forces))
+
+        def fill(d):
+            d.positions, d.vel_mass, d.ids, d.images, d.forces = p, v, r, i, f
+            H = self.box.H
+            d.box_diag[0], d.box_diag[1], d.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
+            d.dt = float(self.dt)
+
+        self.advance_pointers(timestep, (p, v, r, i, f), fill)
 
     def _update_callback(self, timestep):
-        snapshot = self._pack_snapshot()
-        self.state = self._method_update(snapshot, self.state, timestep)
-        self._bias(snapshot, self.state, self.context.synchronize)
-        if self.callback:
-            self.callback(snapshot, self.state, timestep)
-
-
-def build_helpers(context, sampling_method, layout):
-    """hoomd.py:205-240 / openmm.py:132-180 / lammps.py:130-179"""
-
-    def bias(snapshot, state, sync_backend=None):
-        # The in-place force update is fused into the native step (same stream, no host sync),
-        # so the reference's sync_backend() / block_until_ready() / cupy add have nothing left to do.
-        return None
-
-    def dimensionality():
-        return 3
-
-    def query(snapshot):
-        raise NotImplementedError(
-            "the snapshot gather (positions / indices / momenta) is fused into the CUDA step; "
-            "there is no separate query stage"
-        )
-
-    factor = layout.force_unit_factor
-    helpers = HelperMethods(query, dimensionality, (lambda x: factor * x), layout)
-    return helpers, restore, bias
+        caps = self.context.capsules()
+        if self._fused and self.context.layout_name == "hoomd":
+            return self.on_hoomd_half_step(*caps, timestep)
+        self.advance_snapshot(self._pack_snapshot(caps), timestep)
 
 
 def bind(sampling_context, callback, **kwargs):
-    """hoomd.py:261-271"""
+    """SamplingContext entry point"""
     context = sampling_context.context
     sampler = Sampler(context, sampling_context.method, callback)
     context.hook = sampler._update_callback

@@ -1,86 +1,75 @@
 """
-OpenMM adapter (drop-in for pysages/backends/openmm.py) on top of the `openmm_dlext` plugin.
+OpenMM adapter on top of the `openmm_dlext` plugin (the role of pysages/backends/openmm.py).
 
-CUDA platform: the plugin's persistent views are used in place -- positions / velocities (Np, 4),
-fixed-point forces (3, Np) int64, atom ids (slot -> atom); the per-step `ids.argsort()` of
-openmm.py:106-107 runs on the device.  CPU / Reference platforms (the reference's own
-alanine-dipeptide example): the host arrays are staged through the GPU every step
-(psb_step_host) -- the bias is still computed on the device, there is no CPU path.
+CUDA platform: the plugin's views persist for the life of the context, so the `psb_snapshot` is filled
+once -- positions / velocities (Np, 4), fixed-point forces (3, Np) int64, atom ids (slot -> atom; the
+per-step `ids.argsort()` of openmm.py:106-107 happens inside the native step) -- and every step is one
+native call.  Ordering: OpenMM computes forces and integrates on its context's own stream, which the
+plugin does not expose.  Before the step `view.synchronize()` makes OpenMM's force kernels visible; after
+it the host waits for the bias kernel, exactly where the reference calls `sync_forces()`
+(openmm.py:160-170, backends/utils.py:24-26) -- otherwise the integrator, launched on the other stream,
+could read the force buffer before the bias has been added.
+CPU / Reference platforms (the reference's own alanine-dipeptide example): the host arrays are staged
+through the GPU every step (psb_step_host, synchronous) -- the bias is still computed on the device.
 """
 
 import numpy as np
 import openmm_dlext as dlext
-from openmm_dlext import DeviceType, Force
 
-from ._common import LAYOUTS, fused_helpers, tensor_from_capsule
-from .snapshot import Box, Snapshot, copy
-from .snapshot import restore as _restore
+from . import _common as C
+from .snapshot import Box, Snapshot
 
 try:
     import openmm
     import openmm.unit as unit
-except ImportError:  # older releases
+except ImportError:  # releases that still live under simtk
     from simtk import openmm, unit  # type: ignore
 
 
-def is_on_gpu(view):
-    return view.device_type() == DeviceType.GPU
+class Sampler(C.SamplerCore):
+    ordering = "host"
 
-
-class Sampler:
     def __init__(self, context, sampling_method, callback=None):
-        force = Force()
-        force.add_to(context)  # OpenMM owns the force from here on
+        self._force = dlext.Force()
+        self._force.add_to(context)  # OpenMM owns the force object from here on
         self.context = context
-        self.view = force.view(context)
-        self.callback = callback
-        self.snapshot = self._take_snapshot()
-        layout = LAYOUTS["openmm-cuda" if is_on_gpu(self.view) else "openmm-cpu"]
-        _, initialize, method_update = sampling_method.build(self.snapshot, fused_helpers(layout))
-        self.state = initialize()
-        self._method_update = method_update
+        self.view = self._force.view(context)
+        self.on_gpu = self.view.device_type() == dlext.DeviceType.GPU
+        self._arrays = None
+        self._bind_method(sampling_method, C.LAYOUTS["openmm-cuda" if self.on_gpu else "openmm-cpu"], callback)
+        self._force.set_callback_in(context, self.on_forces_ready)
 
-        def update(timestep=0):
-            if is_on_gpu(self.view):
-                self.view.synchronize()  # the plugin's stream is not exposed: order after OpenMM's force kernels
-            self.state = method_update(self.snapshot, self.state, timestep)
-            if self.callback:
-                self.callback(self.snapshot, self.state, timestep)
+    def _views(self):
+        """The plugin's buffers as one Snapshot of zero-copy views (taken once: they persist, openmm.py:64-89)."""
+        if self._arrays is None:
+            t, v = C.tensor_from_capsule, self.view
+            velocities = t(dlext.velocities(v))
+            vel_mass = velocities if self.on_gpu else (velocities, t(dlext.inverse_masses(v)).reshape(-1, 1))
+            cols = [c.value_in_unit(unit.nanometer) for c in self.context.getSystem().getDefaultPeriodicBoxVectors()]
+            H = np.asarray(cols, dtype=np.float64).T  # box vectors are the columns of H
+            dt = self.context.getIntegrator().getStepSize() / unit.picosecond
+            self._arrays = Snapshot(t(dlext.positions(v)), vel_mass, t(dlext.forces(v)), t(dlext.atom_ids(v)),
+                                    Box(H, np.zeros(3)), dt)
+        return self._arrays
 
-        force.set_callback_in(context, update)
-
-    def restore(self, prev_snapshot):
-        _restore(self.snapshot, prev_snapshot)
-
-    def take_snapshot(self):
-        return copy(self.snapshot)
-
-    def _take_snapshot(self):
-        view, t = self.view, tensor_from_capsule
-        positions = t(dlext.positions(view))
-        forces = t(dlext.forces(view))
-        ids = t(dlext.atom_ids(view))
-        velocities = t(dlext.velocities(view))
-        if is_on_gpu(view):
-            vel_mass = velocities
+    def on_forces_ready(self, timestep=0):
+        views = self._views()
+        if self.on_gpu:
+            self.view.synchronize()  # OpenMM's force kernels (its own stream) before our reads
+        if self._fused:
+            self.advance_pointers(timestep, "persistent", lambda d: self.describe_into(views))
         else:
-            vel_mass = (velocities, t(dlext.inverse_masses(view)).reshape(-1, 1))
-        vectors = self.context.getSystem().getDefaultPeriodicBoxVectors()
-        a, b, c = (v.value_in_unit(unit.nanometer) for v in vectors)
-        H = ((a[0], b[0], c[0]), (a[1], b[1], c[1]), (a[2], b[2], c[2]))
-        dt = self.context.getIntegrator().getStepSize() / unit.picosecond
-        return Snapshot(positions, vel_mass, forces, ids, Box(np.asarray(H), np.zeros(3)), dt)
+            self.advance_snapshot(views, timestep)
 
 
 def check_integrator(context):
-    """openmm.py:183-188"""
-    integrator = context.getIntegrator()
-    if isinstance(integrator, (openmm.VariableLangevinIntegrator, openmm.VariableVerletIntegrator)):
+    """Variable-step integrators change dt behind the method's back (openmm.py:183-188)."""
+    if isinstance(context.getIntegrator(), (openmm.VariableLangevinIntegrator, openmm.VariableVerletIntegrator)):
         raise ValueError("Variable step size integrators are not supported")
 
 
 def bind(sampling_context, callback, **kwargs):
-    """openmm.py:191-199: the context object is an openmm.app.Simulation"""
+    """SamplingContext entry point; the wrapped object is an openmm.app.Simulation (openmm.py:191-199)."""
     simulation = sampling_context.context
     check_integrator(simulation.context)
     sampler = Sampler(simulation.context, sampling_context.method, callback)

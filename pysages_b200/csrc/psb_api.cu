@@ -236,12 +236,18 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
   S.record_out = record_out;
   const Model& M = h->model;
   const bool eval_cvs = (mode != MODE_WALKER_FINISH);
+  // A helper kernel of this library in front of the step kernel (inverse permutation, coordination gather + pairs,
+  // eRMSD) writes tables the step kernel reads in its EARLY part, before griddepcontrol.wait (tag -> slot through
+  // inv_perm in the register-cached gather).  Programmatic dependent launch only makes the previous kernel's
+  // writes visible after that wait, so such a step kernel is launched in plain stream order instead.
+  bool helper_before = false;
 
   if (eval_cvs && h->layout.layout == PSB_LAYOUT_OPENMM_CUDA && !M.slot_major) {  // slot-ordered class: no inverse needed
     const long long n = h->layout.natoms;
     const int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * h->num_sms);
     launch_inverse_permutation(reinterpret_cast<const int*>(s->ids), M.inv_perm, n, blocks, stream);
     ++h->launches;
+    helper_before = true;
   }
   if (eval_cvs) {
     for (const CoordWork& cw : h->coord) {
@@ -251,12 +257,14 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
                                 cw.nrt, 1.0 / (cv.r0 * cv.r0), cv.grad, cv.grad + 3 * (size_t)cw.nA,
                                 cv.xi_part);
       h->launches += 2;
+      helper_before = true;
     }
   }
   if (eval_cvs)
     for (int c : h->ermsd) {
       pick_vtable(h->layout)->launch_ermsd(&M, &S, c, stream);
       ++h->launches;
+      helper_before = true;
     }
   if (M.bias_dense && mode != MODE_EVAL && mode != MODE_WALKER_BEGIN) {
     CUDA_TRY(cudaMemsetAsync(M.bias_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms, stream));
@@ -264,7 +272,7 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
       CUDA_TRY(cudaMemsetAsync(M.jac_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms * M.k, stream));
   }
   CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, h->step_general, h->d_model, &S, h->grid,
-                                               h->dyn_smem, stream, h->pdl));
+                                               h->dyn_smem, stream, h->pdl && !helper_before));
   ++h->launches;
   return PSB_OK;
 }
@@ -1132,6 +1140,12 @@ psb_status psb_set_option(psb_handle* h, const char* name, int64_t value) {
     if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);  // captured launches carry the old attribute
     h->cycle_exec = nullptr;
     h->cycle_key.clear();
+    return PSB_OK;
+  }
+  if (n == "slot_stamp_period") {  // tests: make the slot_map launch stamps repeat after `value` launches
+    if (value < 0 || value > 0x0FFFFFFF) return fail(PSB_ERR_VALUE, "slot_stamp_period out of range");
+    h->model.stamp_period = (uint32_t)value;
+    CUDA_TRY(cudaMemcpy(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice));
     return PSB_OK;
   }
   return fail(PSB_ERR_KEY, "unknown option '%s'", name);

@@ -171,7 +171,7 @@ struct Model {
   int32_t comp_cv[MAXK];      // CV owning component c
   int32_t cta_lo[MAXG], cta_hi[MAXG];  // gridDim.x > 1: CTAs cta_lo[g] .. cta_hi[g] hold partial sums of group g
   int32_t slot_major;         // gather / scatter in slot order through slot_map (most atoms selected)
-  int32_t pad1;
+  uint32_t stamp_period;      // tests: clear slot_map every `stamp_period` launches as if the 28-bit stamp had wrapped (0: off)
   uint32_t* slot_map;         // (N) slot -> (launch stamp << 4 | group + 1), rewritten every launch
   int32_t row_first[2][MAXG + 1];  // prefix of accumulator rows per group, pass A / pass B
   uint32_t ov[MAXG][MAXG];    // group overlap counts (ABF fast path)

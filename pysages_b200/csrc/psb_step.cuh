@@ -1374,7 +1374,18 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     // velocities and forces in SLOT order, fully coalesced.  At most 4 groups (fast-class only).
     if (slot_major && !TAGMAP) {
       __syncthreads();  // sh.epoch
-      stamp = ((uint32_t)(sh.epoch[BAR_SLOT] + 1ULL) & 0x0FFFFFFFu) << 4;
+      // 28-bit launch stamp in 1 .. 2^28 - 1.  Only the slots of currently selected atoms are rewritten each
+      // step, so an entry left behind by an atom that has since moved to another slot would look current again
+      // once the stamps repeat: the launch that restarts the sequence (the first, then every 2^28 - 1 launches)
+      // clears the whole map first -- one extra grid barrier on that launch only.  Model::stamp_period shortens
+      // the cycle (tests).
+      const unsigned long long period = M.stamp_period ? (unsigned long long)M.stamp_period : 0x0FFFFFFFULL;
+      const uint32_t stamp_val = (uint32_t)(sh.epoch[BAR_SLOT] % period) + 1u;
+      stamp = stamp_val << 4;
+      if (stamp_val == 1u) {
+        for (size_t i = (size_t)b * BLOCK + tid; i < (size_t)M.natoms; i += (size_t)nb * BLOCK) M.slot_map[i] = 0u;
+        grid_sync(M, sh, BAR_C);  // not used otherwise by this class (its ABF variant has no pass C)
+      }
       const uint32_t chunk0 = (M.T + nb - 1) / nb;
       const uint32_t q0 = min(M.T, (uint32_t)b * chunk0), q1 = min(M.T, q0 + chunk0);
       // group of a term and its tag without branches (<= 4 groups): bounds and range starts in registers

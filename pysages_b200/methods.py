@@ -180,6 +180,12 @@ class NativeStep:
             N.check(self.lib.psb_step(self.handle, ctypes.byref(self._desc(snapshot)), int(timestep), self._stream()))
         self.ncalls += 1
 
+    def step_desc(self, desc, timestep=0):
+        """psb_step on a psb_snapshot the caller keeps filled (engine adapters: device pointers read straight
+        out of the plugin's DLPack capsules, backends/_common.py)."""
+        N.check(self.lib.psb_step(self.handle, ctypes.byref(desc), int(timestep), self._stream()))
+        self.ncalls += 1
+
     def next_step_deposits(self):
         return bool(self.lib.psb_next_step_deposits(self.handle))
 
@@ -362,6 +368,7 @@ class SamplingMethod:
             return self._make_state(native)
 
         update.native = native
+        update.fused = True  # nothing but the native step: adapters may call native.step_desc directly
         return snapshot, initialize, update
 
 

@@ -110,7 +110,7 @@ def install_hoomd():
 # ---------------------------------------------------------------------------------------------------
 # OpenMM + openmm_dlext
 # ---------------------------------------------------------------------------------------------------
-def install_openmm():
+def install_openmm(own_stream=False):
     class DeviceType:
         CPU, GPU = 0, 1
 
@@ -121,9 +121,10 @@ def install_openmm():
         def device_type(self):
             return DeviceType.GPU if self.context.engine.layout_name == "openmm-cuda" else DeviceType.CPU
 
-        def synchronize(self):
+        def synchronize(self):  # openmm_dlext: waits for OpenMM's OWN context stream, not for anybody else's
             if self.context.engine.device.type == "cuda":
-                self.context.engine.synchronize()
+                stream = self.context.engine_stream
+                stream.synchronize() if stream is not None else self.context.engine.synchronize()
 
     class Force:
         def add_to(self, context):
@@ -145,6 +146,10 @@ def install_openmm():
     class Context:
         def __init__(self, engine):
             self.engine, self.forces, self.callback = engine, [], None
+            # own_stream: like the real CUDA platform, force computation and integration run on a non-blocking
+            # stream of the context; `seen_forces` is what the "integrator" read right after the callback
+            self.engine_stream = torch.cuda.Stream() if (own_stream and engine.device.type == "cuda") else None
+            self.seen_forces = None
 
         def getSystem(self):
             H = self.engine.box_H
@@ -164,8 +169,17 @@ def install_openmm():
                 # OpenMM's buffers persist (the plugin's views are taken once): update them in place
                 if eng.trajectory is not None:
                     eng.t["positions"].copy_(eng.trajectory[eng.timestep % eng.trajectory.shape[0]])
+                es = self.context.engine_stream
+                if es is not None:
+                    es.wait_stream(torch.cuda.current_stream())  # the position update above
+                    # work already queued on the stream the bias step will use (another library's kernels):
+                    # the bias kernel starts late, the engine's integrator below does not wait for it by itself
+                    torch.cuda._sleep(40_000_000)
                 if self.context.callback is not None:
                     self.context.callback(self.currentStep)
+                if es is not None:
+                    with torch.cuda.stream(es):  # "integrator": reads the force buffer on the engine's stream
+                        self.context.seen_forces = eng.t["forces"].clone()
                 eng.timestep += 1
                 self.currentStep += 1
 
@@ -185,7 +199,7 @@ def install_openmm():
 # ---------------------------------------------------------------------------------------------------
 # LAMMPS + lammps.dlext
 # ---------------------------------------------------------------------------------------------------
-def install_lammps(kokkos_cuda=True):
+def install_lammps(kokkos_cuda=True, own_stream=False):
     class ExecutionSpace:
         kOnHost, kOnDevice = 0, 1
 
@@ -201,9 +215,10 @@ def install_lammps(kokkos_cuda=True):
         def __init__(self, context):
             self.context = context
 
-        def synchronize(self):
+        def synchronize(self):  # Kokkos fence of LAMMPS' own execution-space instance
             if self.context.engine.device.type == "cuda":
-                self.context.engine.synchronize()
+                stream = self.context.engine_stream
+                stream.synchronize() if stream is not None else self.context.engine.synchronize()
 
     def _cap(view, key):
         return to_dlpack(view.context.engine.t[key])
@@ -211,6 +226,8 @@ def install_lammps(kokkos_cuda=True):
     class lammps:  # noqa: N801  (the real class is lower-case)
         def __init__(self, engine):
             self.engine, self.fixes, self.closed = engine, [], False
+            self.engine_stream = torch.cuda.Stream() if (own_stream and engine.device.type == "cuda") else None
+            self.seen_forces = None
 
         def extract_global(self, name):
             return {"units": self.engine.units or "lj", "dt": self.engine.dt}[name]
@@ -225,9 +242,15 @@ def install_lammps(kokkos_cuda=True):
             assert word == "run"
             for _ in range(int(n)):
                 self.engine._advance()
+                if self.engine_stream is not None:
+                    self.engine_stream.wait_stream(torch.cuda.current_stream())
+                    torch.cuda._sleep(40_000_000)  # see install_openmm
                 for fix in self.fixes:
                     if fix._callback is not None:
                         fix._callback(self.engine.timestep)
+                if self.engine_stream is not None:
+                    with torch.cuda.stream(self.engine_stream):
+                        self.seen_forces = self.engine.t["forces"].clone()
                 self.engine.timestep += 1
 
         def finalize(self):
@@ -237,6 +260,7 @@ def install_lammps(kokkos_cuda=True):
     lmp = _module("lammps", lammps=lammps)
     lmp.dlext = _module("lammps.dlext", ExecutionSpace=ExecutionSpace, FixDLExt=FixDLExt, LAMMPSView=LAMMPSView,
                         kOnHost=0, kOnDevice=1, has_kokkos_cuda_enabled=lambda ctx: kokkos_cuda,
+                        kImgBitSize=32, kImgBits=10, kImg2Bits=20, kImgMask=1023, kImgMax=512,
                         positions=lambda v, loc: _cap(v, "positions"), velocities=lambda v, loc: _cap(v, "velocities"),
                         forces=lambda v, loc: _cap(v, "forces"), types=lambda v, loc: _cap(v, "types"),
                         tags_map=lambda v, loc: _cap(v, "tags_map"), images=lambda v, loc: _cap(v, "images"),

@@ -156,6 +156,9 @@ class ParityRun:
 
     def __init__(self, snap, cv_specs, method_spec, device="cuda", units=None):
         self.snap = snap
+        # CVs whose Jacobian entries are products, not differences of large terms: their bias is gated elementwise
+        self.elementwise = all(name in ("Component", "Distance", "Displacement", "Angle", "DihedralAngle",
+                                        "RadiusOfGyration") for (name, _, _) in cv_specs)
         self.layout = snap["layout"]
         self.device = device
         self.rtol = F32_RTOL if fp32_compute(snap) else X64_RTOL
@@ -199,16 +202,38 @@ class ParityRun:
         return J.numpy()
 
     def check(self, jacobian=True):
+        """Gates.  rtol = 1e-10 (x64) / 1e-5 (fp32 compute), always relative to the magnitude
+        of the TERMS a quantity is summed from -- the forward-error scale of a floating-point sum:
+          xi, J, heights, centers, grids ... max |reference| of the field;
+          bias (N,3)                      (a) max |reference| overall, and (b) ELEMENTWISE, after taking out the
+                                          generalized-force difference dF (gated by (a)): |d bias + J^T dF| <=
+                                          rtol * (|J|^T |F|) for every atom and axis (CVs whose Jacobian entries
+                                          are products: point CVs and RadiusOfGyration; the RMSD / gyration /
+                                          puckering gradients are differences of O(|r|) terms and keep (a));
+          Wp, Wp_ = solve(J J^T, J p)     |(J J^T)^-1| (|J| |p|): J p is a signed sum over 3N products that
+                                          cancels (thermal momenta), two summation orders differ by eps * sum |terms|;
+          Fsum, force, F                  max |field| or the finite difference (1.5 Wp - 2 Wp' + 0.5 Wp'') / dt
+                                          of abf.py:213 evaluated on that Wp scale, per accumulated call."""
         s, o, rtol = self.state, self.ostate, self.rtol
         close(s.xi.cpu().numpy(), o.xi.numpy(), rtol, what="xi")
         assert int(s.ncalls) == int(o.ncalls)
         obias = o.bias.numpy()
         scale = max(np.max(np.abs(obias)), 1e-300)
-        close(s.bias.cpu().numpy(), obias, rtol, scale=scale, what="bias")
+        sbias = s.bias.cpu().numpy()
+        close(sbias, obias, rtol, scale=scale, what="bias")
+        Jo = None
         if jacobian:
             J = self.native.view("jacobian", (self.native.k, -1)).cpu().numpy()
             Jo = self.jacobian()
             close(J, Jo, rtol, what="jacobian")
+        if jacobian and self.elementwise:
+            # (b) elementwise: bias = -J^T F (harmonic_bias.py:127, metad.py:200, abf.py:223)
+            F = self.native.view("cv_force").cpu().numpy().ravel()[: Jo.shape[0]]
+            Fo = np.linalg.lstsq(-Jo.T, obias.ravel(), rcond=None)[0] if np.any(Jo) else np.zeros_like(F)
+            resid = (sbias - obias).ravel() + Jo.T @ (F - Fo)
+            terms = np.abs(Jo).T @ np.maximum(np.abs(F), np.abs(Fo))
+            worst = np.max(np.abs(resid) - rtol * terms)
+            assert worst <= 1e-13 * scale + 1e-300, f"bias, elementwise: {worst:.3e} beyond rtol * |J|^T |F| (scale {scale:.3e})"
         # forces after the in-place apply
         f = forces_xyz(self.layout, self.dsnap.forces.cpu().numpy())
         fo = forces_xyz(self.layout, self.osnap.forces)
@@ -219,11 +244,26 @@ class ParityRun:
         else:
             ftol = 2e-7 if f.dtype == np.float32 else 1e-13
             close(f, fo, max(ftol, rtol if f.dtype == np.float64 else ftol), what="forces")
+        w_scale = None
+        if hasattr(o, "Wp") and getattr(o, "Wp") is not None:
+            data = self.ohelpers.query(self.osnap)
+            Jd = Jo if Jo is not None else self.jacobian()
+            p = np.abs(np.asarray(data.momenta, dtype=np.float64).ravel())
+            absJp = np.abs(Jd) @ p
+            w_scale = float(np.max(np.abs(np.linalg.pinv(Jd @ Jd.T)) @ absJp))
+            self._w_scale = max(getattr(self, "_w_scale", 0.0), w_scale)
         for name in ("heights", "centers", "Fsum", "force", "F", "Wp", "Wp_", "grid_potential", "grid_gradient"):
             if hasattr(o, name) and getattr(o, name) is not None:
                 ov = getattr(o, name).numpy()
                 sv = getattr(s, name).cpu().numpy().reshape(ov.shape)
-                close(sv, ov, max(rtol, 1e-9) if name in ("Fsum", "force", "F", "Wp", "Wp_") else rtol, what=name)
+                ref = None
+                if w_scale is not None and name in ("Wp", "Wp_"):
+                    ref = max(np.max(np.abs(ov)), self._w_scale)
+                elif w_scale is not None and name in ("Fsum", "force", "F"):
+                    unit = abs(float(self.ohelpers.to_force_units(1.0)))
+                    calls = int(o.ncalls) if name == "Fsum" else 1
+                    ref = max(np.max(np.abs(ov)), calls * 4.0 * self._w_scale * unit / float(self.osnap.dt))
+                close(sv, ov, rtol, scale=ref, what=name)
         if hasattr(o, "hist"):
             assert np.array_equal(s.hist.cpu().numpy().astype(np.int64), o.hist.numpy()), "hist must be bit-exact"
         if hasattr(o, "idx"):

@@ -33,6 +33,14 @@ def reference_run(snap, traj, units=None):
     return res.states[0], eng.t["forces"].cpu().numpy()
 
 
+def reference_run2(snap, traj, nsteps, units=None):
+    eng = mock.MockEngine(snap["layout"], snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda",
+                          trajectory=traj, units=units)
+    res = ps.run(method(), lambda **kw: eng, nsteps)
+    torch.cuda.synchronize()
+    return res.states[0], eng.t["forces"].cpu().numpy()
+
+
 def check(result, forces, ref_state, ref_forces):
     s = result.states[0]
     torch.cuda.synchronize()
@@ -79,6 +87,66 @@ def test_lammps_adapter(kokkos_cuda):
     ctx = lammps(eng)
     res = ps.run(method(), lambda **kw: ctx, NSTEPS)
     check(res, eng.t["forces"].cpu().numpy(), ref_state, ref_forces)
+
+
+def test_openmm_cuda_integrator_on_its_own_stream_sees_the_bias():
+    """OpenMM integrates on its context's stream: after the callback returns the integrator must find the biased
+    forces even when the bias kernel was queued behind other work (openmm.py:160-170 blocks in sync_forces())."""
+    snap = synthetic.make_snapshot(400, layout="openmm-cuda", dtype=np.float64, seed=6)
+    traj = synthetic.make_trajectory(snap, frames=2, step=0.05)
+    _, ref_forces = reference_run2(snap, traj, 2)
+    Simulation = fake_engines.install_openmm(own_stream=True)
+    sim = Simulation(fake_engines.engine(snap, "cuda", traj))
+    ps.run(method(), lambda **kw: sim, 2)
+    seen = sim.context.seen_forces
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(seen.cpu().numpy(), ref_forces)
+
+
+def test_lammps_kokkos_integrator_on_its_own_stream_sees_the_bias():
+    snap = synthetic.make_snapshot(400, layout="lammps", dtype=np.float64, seed=7)
+    traj = synthetic.make_trajectory(snap, frames=2, step=0.05)
+    _, ref_forces = reference_run2(snap, traj, 2, units="real")
+    lammps = fake_engines.install_lammps(True, own_stream=True)
+    ctx = lammps(fake_engines.engine(snap, "cuda", traj, units="real"))
+    ps.run(method(), lambda **kw: ctx, 2)
+    seen = ctx.seen_forces
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(seen.cpu().numpy(), ref_forces)
+
+
+def test_lammps_bigbig_image_packing_is_rejected():
+    lammps = fake_engines.install_lammps(True)
+    import lammps as fake
+
+    fake.dlext.kImgBitSize, fake.dlext.kImgBits = 64, 21
+    snap = synthetic.make_snapshot(64, layout="lammps", dtype=np.float64, seed=8)
+    with pytest.raises(RuntimeError, match="image flags"):
+        ps.run(ps.methods.Unbiased([ps.colvars.Component([1], 0)]), lambda **kw: lammps(fake_engines.engine(snap, "cuda")), 1)
+
+
+def test_sampling_context_enters_and_leaves_the_engine_context():
+    """backends/core.py:59-73: `with sampling_context` trampolines to the engine's context (hoomd 2.x: the global
+    hoomd.run steps whichever SimulationContext is entered)."""
+    snap = synthetic.make_snapshot(64, layout="hoomd", dtype=np.float32, seed=8)
+    events = []
+
+    class Engine(mock.MockEngine):
+        def __enter__(self):
+            events.append("enter")
+            return self
+
+        def __exit__(self, *exc):
+            events.append("exit")
+
+        def run(self, n, **kw):
+            events.append("run")
+            super().run(n, **kw)
+
+    Engine.__module__ = mock.__name__
+    eng = Engine("hoomd", snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda")
+    ps.run(ps.methods.Unbiased([ps.colvars.Component([1], 0)]), lambda **kw: eng, 2)
+    assert events == ["enter", "run", "exit"]
 
 
 def test_openmm_variable_step_integrators_are_rejected():

@@ -202,3 +202,72 @@ def test_radius_of_gyration_slot_ordered_against_general_class(layout, monkeypat
     scale = np.abs(outs[0][2] - f0.cpu().numpy().astype(np.float64)).max()
     assert scale > 0  # the bias was applied
     assert np.abs(outs[1][2] - outs[0][2]).max() <= max(2e-7 * np.abs(outs[0][2]).max(), 4.0 if layout != "hoomd" else 0.0)
+
+
+def test_cfg4_bench_generator_1e5_hills_through_a_deposit_against_numpy():
+    """BASELINE config 4 at its stated size, on bench.py's own generator and production handle (no dense
+    outputs): RMSD + RoG over a 5e4-atom globule, direct sum over 1e5 TMA-staged hills, through a deposit.
+    Known answers from numpy: Kabsch by SVD (orientation.py:63-95), <r.r> (shape.py:52-57), the Gaussian sum and
+    its gradient (metad.py:318-323), -J^T F with the closed-form Jacobians."""
+    import bench
+
+    dev = torch.device("cuda:0")
+    n, H = 50_000, 100_000
+    frames, L, cvs4, md, prefill = bench.cfg4_case(dev, natoms=n, H=H)
+    assert md["ngaussians"] == H
+    snaps = bench.snapshots_of(frames, L, 0.005)
+    _, native = bench.build_ours(cvs4, ("Metadynamics", dict(md)), snaps[0])
+    prefill(native)
+    native.set_state("ncalls", np.array([md["stride"]], dtype=np.int64))  # the next call deposits (metad.py:192-193)
+    heights = native.view("heights").cpu().numpy().copy()
+    centers = native.view("centers", (-1, 2)).cpu().numpy().copy()
+    idx0 = int(native.view("idx").item())
+    assert idx0 == H - 8 and np.count_nonzero(heights[:H]) == H - 8
+    sigma = np.asarray(md["sigma"])
+    ref_by_tag = np.asarray(cvs4[0][1][1], dtype=np.float64)
+
+    def numpy_step(frame, heights, centers, nh):
+        a = {k: v.cpu().numpy() for k, v in frame.items()}
+        slot = a["rtags"].astype(np.int64)
+        r = a["positions"][:, :3].astype(np.float64) + L * a["images"].astype(np.float64)
+        x = r[slot]  # tag order
+        P, Q = x - x.mean(0), ref_by_tag - ref_by_tag.mean(0)
+        V_, _, Wt = np.linalg.svd(P.T @ Q)
+        V_[:, -1] *= np.sign(np.linalg.det(V_) * np.linalg.det(Wt))
+        U = V_ @ Wt
+        rmsd = math.sqrt(((P @ U - Q) ** 2).sum() / n)
+        rog = (x**2).sum() / n
+        xi = np.array([rmsd, rog])
+        d = xi - centers[:nh]
+        e = heights[:nh] * np.exp(-0.5 * ((d / sigma) ** 2).sum(-1))
+        F = (-e[:, None] * d / sigma**2).sum(0)
+        terms = np.abs(e[:, None] * d / sigma**2).sum(0)  # conditioning of the signed sum
+        J0 = (P - Q @ U.T) / (n * rmsd)
+        J1 = 2.0 * x / n
+        bias_by_tag = -(F[0] * J0 + F[1] * J1)
+        bias = np.zeros((n, 3))
+        bias[slot] = bias_by_tag
+        return xi, e.sum(), F, terms, bias
+
+    for step in range(2):
+        frame = frames[step]
+        f0 = frame["forces"].clone()
+        xi, V, F, terms, bias = numpy_step(frame, heights, centers, min(idx0 + step, H))
+        native.step(snaps[step])
+        torch.cuda.synchronize()
+        close(native.view("xi").cpu().numpy().ravel()[:2], xi, 1e-10, what="xi")
+        got_F = native.view("cv_force").cpu().numpy().ravel()[:2]
+        assert np.all(np.abs(got_F - F) <= 1e-10 * np.maximum(terms, np.abs(F))), (got_F, F, terms)
+        energy = float(native.view("energy").item())
+        deposited = step == 0
+        want_E = V + (md["height"] if deposited else 0.0)
+        assert abs(energy - want_E) <= 1e-10 * abs(want_E)
+        df = (frame["forces"] - f0).cpu().numpy()[:, :3].astype(np.float64)
+        fscale = np.abs(frame["forces"].cpu().numpy()).max()
+        assert np.abs(df - bias).max() <= 2e-7 * max(fscale, np.abs(bias).max())
+        if deposited:  # metad.py:262-271: plain height, centre = xi, stored at idx
+            heights[idx0], centers[idx0] = md["height"], xi
+            assert int(native.view("idx").item()) == idx0 + 1
+            close(native.view("heights").cpu().numpy()[idx0], heights[idx0], 1e-15, what="deposited height")
+            close(native.view("centers", (-1, 2)).cpu().numpy()[idx0], centers[idx0], 1e-10, what="deposited centre")
+    assert int(native.view("ncalls").item()) == md["stride"] + 2
