@@ -321,6 +321,11 @@ psb_status psb_launch_floor(int32_t grid_blocks, int32_t cooperative, int32_t bi
 /* Dependent-issue latency (SM cycles per operation) of DFMA, DADD, FFMA, IMAD, LDS, sqrt, 1/x,
  * rsqrt, floor, fmod, atan2, exp in one warp: the floor of the single-warp finalizer code. */
 psb_status psb_latency_probe(double* out_host16);
+/* Sustained arithmetic throughput of the device, operations per second over all SMs, measured with 8 independent
+ * chains per thread and 8 x 256 threads per SM: out[0] DFMA (x 2 = FP64 FLOP/s: the roofline of the pairwise
+ * coordination kernel), out[1] FFMA, out[2] float -> double conversions, out[3] int -> double
+ * conversions, out[4] DADD.  Synchronous. */
+psb_status psb_fma_peak(double* out_host5);
 int32_t psb_abi_version(void);
 
 #ifdef __cplusplus

@@ -164,6 +164,7 @@ EXPORTS = {
     "psb_launch_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]),
     "psb_launch_floor": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "psb_latency_probe": (c_int32, [POINTER(c_double)]),
+    "psb_fma_peak": (c_int32, [POINTER(c_double)]),
     "psb_abi_version": (c_int32, []),
 }
 

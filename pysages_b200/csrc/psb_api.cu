@@ -271,8 +271,15 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
     if (M.jac_dense)
       CUDA_TRY(cudaMemsetAsync(M.jac_dense, 0, sizeof(double) * 3 * (size_t)h->layout.natoms * M.k, stream));
   }
-  CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, h->step_general, h->d_model, &S, h->grid,
-                                               h->dyn_smem, stream, h->pdl && !helper_before));
+  int cls = h->step_general;
+  size_t dyn = h->dyn_smem;
+  if (cls == SC_STREAM) {  // bulk copies need 16-byte aligned streams; anything else takes the register-staged class
+    const uintptr_t bits = (uintptr_t)s->positions | (uintptr_t)s->forces | (S.unwrap ? (uintptr_t)s->images : 0) |
+                           (S.need_momenta ? (uintptr_t)s->vel_mass : 0);
+    if (bits & 15u) { cls = SC_SLOT; dyn = 0; }
+  }
+  CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, cls, h->d_model, &S, h->grid, dyn, stream,
+                                               h->pdl && !helper_before));
   ++h->launches;
   return PSB_OK;
 }
@@ -720,6 +727,50 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     }
     if (M.slot_major) {
       h->step_general = SC_SLOT;
+      // TMA-staged streaming (SC_STREAM, psb_stream.cuh): HOOMD layout, two CTAs per SM, per-warp rings over all the
+      // shared memory the instantiation leaves free.  Opt-in (PSB_STREAM=1): measured on B200 it does NOT beat the
+      // register-staged slot-ordered class (the passes are issue-bound at 16 warps x fp64, not short
+      // of bytes in flight).  Metadynamics by direct summation keeps the slot-ordered class in any case (its hill
+      // staging lives in dynamic shared memory too).
+      if (layout->layout == PSB_LAYOUT_HOOMD && !metad_direct && getenv("PSB_STREAM") && atoi(getenv("PSB_STREAM")) != 0) {
+        const size_t stat = pick_vtable(*layout)->static_smem(h->step_method, SC_STREAM);
+        const size_t limit = 227 * 1024;  // per-CTA shared memory on sm_100 (the SM keeps 1 KB per CTA for itself)
+        bool any_rog = false;
+        for (int c = 0; c < ncvs; ++c) any_rog = any_rog || cvs[c].kind == PSB_CV_ROG;
+        const uint32_t P = 4u * (uint32_t)layout->real_bytes, I = layout->unwrap ? 12u : 0u;
+        StreamGeom g{};
+        g.ch = 32 * STREAM_RPL;  // slots per warp chunk: fine-grained stages, so the whole run of a warp fits its ring
+        g.early = STREAM_MAX_STAGES;
+        if (const char* env = getenv("PSB_STREAM_EARLY")) g.early = atoi(env);
+        if (const char* env = getenv("PSB_STREAM_FLAGS")) g.flags = atoi(env);
+        const uint32_t ch = (uint32_t)g.ch;
+        uint32_t gbytes = ch * P;
+        if (I) { g.g_img = gbytes; gbytes += ch * I; }
+        if (layout->need_momenta) { g.g_vel = gbytes; gbytes += ch * P; }
+        uint32_t sbytes = ch * P;
+        if (any_rog) {
+          g.s_pos = sbytes; sbytes += ch * P;
+          if (I) { g.s_img = sbytes; sbytes += ch * I; }
+        }
+        g.stage_bytes = (std::max(gbytes, sbytes) + 127u) & ~127u;
+        // two CTAs per SM (16 warps: the passes over the staged rows are issue-bound), each with half of what the
+        // SM has left after the static allocations (+ 1 KB per CTA the hardware keeps)
+        const size_t per_cta = stat == (size_t)-1 ? 0 : (limit + 1024) / 2 - 1024 - std::min<size_t>(stat, limit / 2);
+        const size_t per_warp = per_cta / NWARPS;
+        if (per_warp >= 2 * (size_t)g.stage_bytes) {
+          g.stages = (int)std::min<size_t>(STREAM_MAX_STAGES, per_warp / g.stage_bytes);
+          if (const char* env = getenv("PSB_STREAM_STAGES")) g.stages = std::max(2, std::min(g.stages, atoi(env)));
+          const size_t dyn = (size_t)NWARPS * g.stages * g.stage_bytes;
+          const int occ_s = pick_vtable(*layout)->occupancy(h->step_method, SC_STREAM, dyn);
+          if (occ_s >= 1) {
+            h->step_general = SC_STREAM;
+            h->dyn_smem = dyn;
+            M.sg = g;
+            if (!getenv("PSB_GRID_BLOCKS")) h->grid = std::min(occ_s, 2) * h->num_sms;
+            else h->grid = std::min(h->grid, std::min(occ_s, 2) * h->num_sms);
+          }
+        }
+      }
       psb_status st = PSB_OK;
       if (omm) {
         std::vector<uint8_t> tag_group((size_t)layout->natoms, 0);
@@ -1129,6 +1180,16 @@ psb_status psb_latency_probe(double* out_host16) {
   if (e == cudaSuccess) e = cudaMemcpy(out_host16, d, 16 * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return fail(PSB_ERR_CUDA, "CUDA error %s in psb_latency_probe", cudaGetErrorString(e));
+  return PSB_OK;
+}
+
+psb_status psb_fma_peak(double* out_host5) {
+  if (!out_host5) return fail(PSB_ERR_VALUE, "NULL argument");
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaError_t e = measure_throughput(out_host5, sms);
+  if (e != cudaSuccess) return fail(PSB_ERR_CUDA, "CUDA error %s in psb_fma_peak", cudaGetErrorString(e));
   return PSB_OK;
 }
 

@@ -160,6 +160,20 @@ struct BarrierState {
 
 enum { BAR_A = 0, BAR_B = 1, BAR_C = 2, BAR_H = 3, BAR_D = 4, BAR_READERS = 5, BAR_PRE_D = 6, BAR_SLOT = 7, NBARS = 8 };
 
+// SC_STREAM (psb_step.cuh): shared-memory layout of one ring stage, fixed per handle (psb_create)
+constexpr int STREAM_MAX_STAGES = 8;  // per warp
+constexpr int STREAM_RPL = 4;         // rows per lane and chunk: a warp chunk is 32 * STREAM_RPL slots
+struct StreamGeom {
+  int32_t ch;            // slots per warp chunk (32 * STREAM_RPL)
+  int32_t stages;        // S, per warp
+  uint32_t stage_bytes;  // multiple of 128
+  uint32_t g_img, g_vel; // gather chunk = [positions | images | velocities]: byte offsets (0: absent)
+  uint32_t s_pos, s_img; // scatter chunk = [forces | positions | images]: byte offsets (RoG groups only; 0: absent)
+  int32_t early;         // gather chunks requested before the dependency wait (<= stages)
+  int32_t flags;         // experiments: 1 = no scatter chunk is requested before the gather is over
+  int32_t pad;
+};
+
 struct Model {
   int32_t ncv, k, ngroups, all_unique;
   uint32_t T, Su;
@@ -202,6 +216,7 @@ struct Model {
   int32_t fm_pad;
   const ForceSeries* fs;      // SpectralABF: force series or nullptr (psb_set_force_series)
   uint32_t* inv_perm;         // OpenMM-CUDA: atom -> slot, rebuilt every step
+  StreamGeom sg;              // SC_STREAM ring geometry
   double* bias_dense;         // (N,3) or nullptr
   double* jac_dense;          // (k,3N) or nullptr
   long long natoms;

@@ -99,6 +99,72 @@ cudaError_t launch_latency_probe(double* out_dev, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// Sustained issue throughput of the arithmetic the streaming and pair kernels are made of: every thread runs
+// 8 independent chains (enough to cover the pipe latency at 8+ warps per scheduler), the whole device is filled.
+// which: 0 DFMA, 1 FFMA, 2 F2F.F64.F32 (float -> double), 3 I2F.F64 (int -> double), 4 DADD
+template <int WHICH>
+__global__ void __launch_bounds__(256) throughput_kernel(double* out, int iters, double seed) {
+  double x[8];
+  float xf[8];
+  int xi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    x[j] = seed + j + threadIdx.x * 1e-3;
+    xf[j] = (float)x[j];
+    xi[j] = (int)threadIdx.x + j;
+  }
+  const double y = 1.0 + seed * 1e-9;
+  const float yf = (float)y;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (WHICH == 0) x[j] = fma(x[j], y, 1e-30);
+      if (WHICH == 1) xf[j] = fmaf(xf[j], yf, 1e-30f);
+      if (WHICH == 2) { x[j] = (double)xf[j]; xf[j] = __double2float_rn(x[j]) + yf; }  // one F2F up, one down, one FADD
+      if (WHICH == 3) { x[j] = (double)xi[j]; xi[j] = __double2int_rn(x[j]) ^ i; }      // one I2F, one F2I, one LOP
+      if (WHICH == 4) x[j] = x[j] + y;
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += x[j] + (double)xf[j] + (double)xi[j];
+  if (s == 123.456) out[0] = s;  // keeps the chains alive
+}
+
+// -> out_host[5]: operations per second (DFMA, FFMA, F2F.F64.F32, I2F.F64, DADD), whole device
+cudaError_t measure_throughput(double* out_host, int num_sms) {
+  double* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 8);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = num_sms * 8, iters = 4096;
+  for (int which = 0; which < 5 && e == cudaSuccess; ++which) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      switch (which) {
+        case 0: throughput_kernel<0><<<grid, 256>>>(d, iters, 1.5); break;
+        case 1: throughput_kernel<1><<<grid, 256>>>(d, iters, 1.5); break;
+        case 2: throughput_kernel<2><<<grid, 256>>>(d, iters, 1.5); break;
+        case 3: throughput_kernel<3><<<grid, 256>>>(d, iters, 1.5); break;
+        default: throughput_kernel<4><<<grid, 256>>>(d, iters, 1.5); break;
+      }
+      cudaEventRecord(e1);
+      e = cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    out_host[which] = (double)grid * 256.0 * 8.0 * iters / (best * 1e-3);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return e;
+}
+
 cudaError_t launch_floor(int grid, int cooperative, int big_params, int use_barrier, long long n,
                          unsigned long long* counter, cudaStream_t stream) {
   BigParams P{};

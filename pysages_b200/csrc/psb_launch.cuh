@@ -15,6 +15,7 @@ struct StepVTable {
   cudaError_t (*launch_step)(int method, int general, const Model* M, const Snap* S, int grid, size_t dyn_smem,
                              cudaStream_t stream, int pdl);
   int (*occupancy)(int method, int general, size_t dyn_smem);
+  size_t (*static_smem)(int method, int general);  // statically allocated shared memory of that instantiation
   void (*launch_gather)(const Model* M, const Snap* S, int cv, double* xa, int na_pad, double* xb,
                         int nb_pad, cudaStream_t stream);
   void (*launch_ermsd)(const Model* M, const Snap* S, int cv, cudaStream_t stream);
@@ -29,6 +30,7 @@ PairLaunchFn pair_launcher(int R, int H);
 cudaError_t launch_floor(int grid, int cooperative, int big_params, int use_barrier, long long n,
                          unsigned long long* counter, cudaStream_t stream);
 cudaError_t launch_latency_probe(double* out_dev, cudaStream_t stream);
+cudaError_t measure_throughput(double* out_host5, int num_sms);
 void launch_inverse_permutation(const int* ids, uint32_t* inv, long long n, int blocks, cudaStream_t stream);
 void launch_grid_index(const psb_grid_desc& g, const double* x, long long n, uint32_t* out);
 
@@ -36,9 +38,15 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
     vt_plain3_f32, vt_plain3_f64;
 
 // kernel entry points of one (layout, dtype): [method][general]
+// the TMA-staged streaming class exists for the HOOMD layout; the other layouts fall back to the slot-ordered class
+template <int L, typename R, int M>
+const void* stream_entry() {
+  if constexpr (L == PSB_LAYOUT_HOOMD) return (const void*)step_kernel<L, R, M, SC_STREAM>;
+  else return (const void*)step_kernel<L, R, M, SC_SLOT>;
+}
 #define PSB_STEP_ROW(L, R, M)                                                                     \
   {(const void*)step_kernel<L, R, M, SC_POINT>, (const void*)step_kernel<L, R, M, SC_GENERAL>,    \
-   (const void*)step_kernel<L, R, M, SC_SLOT>}
+   (const void*)step_kernel<L, R, M, SC_SLOT>, stream_entry<L, R, M>()}
 #define PSB_DEFINE_STEP_VTABLE(NAME, L, R)                                                          \
   static const void* const NAME##_entry[SM_COUNT][SC_COUNT] = {                                            \
       PSB_STEP_ROW(L, R, SM_UNBIASED), PSB_STEP_ROW(L, R, SM_HARMONIC), PSB_STEP_ROW(L, R, SM_METAD_DIRECT), \
@@ -72,6 +80,11 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BLOCK, smem) != cudaSuccess) return 0; \
     return occ;                                                                                     \
   }                                                                                                 \
+  static size_t NAME##_static_smem(int method, int general) {                                       \
+    cudaFuncAttributes at{};                                                                        \
+    if (cudaFuncGetAttributes(&at, NAME##_entry[method][general]) != cudaSuccess) return (size_t)-1; \
+    return at.sharedSizeBytes;                                                                      \
+  }                                                                                                 \
   static void NAME##_gather(const Model* M, const Snap* S, int cv, double* xa, int na_pad,          \
                             double* xb, int nb_pad, cudaStream_t stream) {                          \
     const int total = na_pad + nb_pad;                                                              \
@@ -81,6 +94,6 @@ extern const StepVTable vt_hoomd_f32, vt_hoomd_f64, vt_openmm_f32, vt_openmm_f64
   static void NAME##_ermsd(const Model* M, const Snap* S, int cv, cudaStream_t stream) {           \
     ermsd_kernel<L, R><<<1, ERMSD_BLOCK, 0, stream>>>(*M, *S, cv);                                  \
   }                                                                                                 \
-  const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_gather, NAME##_ermsd};
+  const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_static_smem, NAME##_gather, NAME##_ermsd};
 
 }  // namespace psb

@@ -24,6 +24,8 @@
 // (unless Model::jac_dense / bias_dense are set for the parity tests).
 #pragma once
 
+#include <type_traits>
+
 #include "psb_device.cuh"
 
 namespace psb {
@@ -38,7 +40,9 @@ enum StepMethod { SM_UNBIASED = 0, SM_HARMONIC = 1, SM_METAD_DIRECT = 2, SM_ABF 
 // SC_POINT: the fast class above; SC_GENERAL: everything; SC_SLOT: the fast class with the slot-ordered
 // gather / scatter (most atoms of a very large system selected), kept in its own instantiation so its
 // register and code footprint stay out of the latency-critical kernels.
-enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_COUNT = 3 };
+// SC_STREAM: the slot-ordered class with its streams moved by TMA bulk copies through a shared-memory ring, one CTA
+// per SM (psb_stream.cuh); HOOMD layout.
+enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_STREAM = 3, SC_COUNT = 4 };
 #ifndef PSB_SLOT_CTAS
 #define PSB_SLOT_CTAS 2
 #endif
@@ -80,6 +84,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+}  // namespace psb
+#include "psb_stream.cuh"
+namespace psb {
+
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -99,6 +107,16 @@ __device__ __forceinline__ long long global_ns() {
 #else
 #define PSB_CLKA(slot) do {} while (0)
 #endif
+#ifdef PSB_PROBE_STREAM  // experiment builds: clock stamps inside the streaming passes (warp 0 of each CTA)
+#define PSB_STAMPS(slot)                                                             \
+  do {                                                                               \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
+#undef PSB_CLK
+#define PSB_CLK(slot) do {} while (0)
+#else
+#define PSB_STAMPS(slot) do {} while (0)
+#endif
 #define PSB_STAMP(slot)                                                              \
   do {                                                                               \
     if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
@@ -115,6 +133,11 @@ struct StepShared {
   uint32_t bars_used;               // barriers this launch arrived on (thread 0)
   unsigned long long seq;           // launches of this handle before this one (Snap::cta_seq), LL stamp source
   uint64_t mbar[2];
+  uint64_t full[NWARPS * STREAM_MAX_STAGES];  // SC_STREAM: one "stage filled" barrier per warp and ring stage
+  struct NetShared* net;           // ABF instantiations: force-model scratch (nullptr elsewhere)
+};
+// Force-model scratch of the ABF family (17 KB): only the ABF instantiations allocate it
+struct NetShared {
   double nnbuf[2][PSB_MAX_WIDTH];  // force network activations (force_net_eval)
   double nndact[PSB_MAX_DENSE - 1][PSB_MAX_WIDTH];  // activation derivatives per hidden layer (gradient mode)
   ForceNet nnh;                    // force network header and (when they fit) parameters, staged after the
@@ -245,6 +268,33 @@ __device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int 
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       if (p.dst >= 0 && sub == 0) (&sh.tot[0][0])[p.dst] = v;
     }
+  }
+  __syncthreads();
+}
+
+// reduce_rows for the slot-ordered classes, whose groups span ALL CTAs (148 .. 296 partials per row): one warp per
+// row, every lane with up to WIDE_U independent loads in flight, so a row costs one L2 round trip instead of
+// gridDim / 48.  Fixed summation order (lane-strided partial sums, then the xor tree): bit-identical in every CTA.
+constexpr int WIDE_U = 10;
+__device__ __forceinline__ void reduce_rows_wide(const Model& M, StepShared& sh) {
+  const int nb = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = M.row_first[0][M.ngroups];
+  for (int r = warp; r < nrows; r += NWARPS) {
+    int g = 0;
+    while (r >= M.row_first[0][g + 1]) ++g;
+    const int dst = g * NACC + (r - M.row_first[0][g]);
+    const double* src = M.partials + (size_t)dst * nb;
+    double v = 0.0;
+    for (int b0 = lane; b0 < nb; b0 += 32 * WIDE_U) {
+      double a[WIDE_U];
+#pragma unroll
+      for (int j = 0; j < WIDE_U; ++j) a[j] = (b0 + 32 * j < nb) ? __ldcg(src + b0 + 32 * j) : 0.0;
+#pragma unroll
+      for (int j = 0; j < WIDE_U; ++j) v += a[j];
+    }
+    v = warp_sum(v);
+    if (lane == 0) (&sh.tot[0][0])[dst] = v;
   }
   __syncthreads();
 }
@@ -650,15 +700,15 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   if (fm != 0) {
     const long long ncalls = sh.pre.ncalls + 1;
     if (fm & FM_NET) {
-      use_model = !((m.has_restraints || hist_only) && oob) && ncalls > sh.nnh.predict_after;
+      use_model = !((m.has_restraints || hist_only) && oob) && ncalls > sh.net->nnh.predict_after;
       if (use_model)
-        f_model = force_net_eval(&sh.nnh, M.nn_np > 0 ? sh.nnw : M.nn->params(), m, f.xi, &sh.nnbuf[0][0],
-                                 sh.nnh.gradient ? &sh.nndact[0][0] : nullptr, lane);
+        f_model = force_net_eval(&sh.net->nnh, M.nn_np > 0 ? sh.net->nnw : M.nn->params(), m, f.xi, &sh.net->nnbuf[0][0],
+                                 sh.net->nnh.gradient ? &sh.net->nndact[0][0] : nullptr, lane);
     } else if (fm & FM_SERIES) {
-      const ForceSeries* ser = M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.nnh) : M.fs;
+      const ForceSeries* ser = M.fs_staged ? reinterpret_cast<const ForceSeries*>(&sh.net->nnh) : M.fs;
       zero_force = ser->oob_zero && oob && !m.has_restraints;
       use_model = !oob && ncalls > ser->predict_after;
-      if (use_model) f_model = force_series_eval(ser, m, f.xi, &sh.nnbuf[0][0], lane);
+      if (use_model) f_model = force_series_eval(ser, m, f.xi, &sh.net->nnbuf[0][0], lane);
     }
   }
   if (lane < k) {
@@ -1043,12 +1093,18 @@ template <int LAYOUT, typename Real, int METHOD, int CLASS>
 __global__ void __launch_bounds__(BLOCK, (CLASS == SC_SLOT) ? SLOT_CTAS_PER_SM : 2)
 step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   constexpr bool GENERAL = (CLASS == SC_GENERAL);
-  constexpr bool SLOT = (CLASS == SC_SLOT);
+  constexpr bool STREAM = (CLASS == SC_STREAM);  // slot-ordered, streams staged by TMA (HOOMD layout only)
+  constexpr bool SLOT = (CLASS == SC_SLOT) || STREAM;
+  static_assert(!STREAM || LAYOUT == PSB_LAYOUT_HOOMD, "the TMA-staged streams are written for the HOOMD layout");
   using A = Access<LAYOUT, Real>;
   using FV = typename A::FV;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ StepShared sh;
   __shared__ __align__(16) Model sM;
+  if constexpr (METHOD == SM_ABF) {
+    __shared__ NetShared nsh;
+    if (threadIdx.x == 0) sh.net = &nsh;  // read after the first block barrier only
+  }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   PSB_STAMP(0);
@@ -1081,6 +1137,89 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   const int nb = gridDim.x, b = blockIdx.x;
   const bool cta0 = (b == 0);
   const int k = M.k;
+  // ---- SC_STREAM: every WARP owns a contiguous run of slots and a private ring of stages (psb_stream.cuh) ------
+  using R4s = typename Real4<Real>::type;
+  constexpr uint32_t PB = (uint32_t)sizeof(R4s);  // bytes per position / velocity / force row
+  const StreamGeom& SG = M.sg;
+  unsigned char* const ring = dyn_smem + (size_t)warp * SG.stages * SG.stage_bytes;  // this warp's stages
+  uint64_t* const full = sh.full + warp * STREAM_MAX_STAGES;
+  uint32_t st_lo = 0, st_hi = 0;              // this warp's slot range
+  int st_n = 0, st_total = 0, st_issued = 0;  // chunks, items (gather [+ scatter] chunks), items issued so far
+  unsigned long long grp_nib = 0;             // group + 1 of this lane's first 16 rows, one nibble each (gather -> scatter)
+  constexpr int P0U = STREAM ? 16 : 1;        // pass 0: tag -> slot lookups per thread requested in the prologue
+  uint32_t p0_slot[P0U];
+  // item i: gather chunk i (i < st_n) or scatter chunk i - st_n, placed in stage i % S (tracked incrementally:
+  // no divisions on this path); lane 0 arms the stage's barrier and starts the copies
+  int st_pstage = 0;  // stage of the next item to be issued
+  int st_cstage = 0;  // stage of the next item to be consumed ...
+  uint32_t st_cphase = 0;  // ... and the parity its barrier completes with
+  auto stream_issue_upto = [&](int limit) {
+    if constexpr (STREAM) {
+      while (st_issued < limit && st_issued < st_total) {
+        const int i = st_issued++;
+        const int ps = st_pstage;
+        st_pstage = (ps + 1 == SG.stages) ? 0 : ps + 1;
+        if (lane != 0) continue;
+        unsigned char* stage = ring + (uint32_t)ps * SG.stage_bytes;
+        uint64_t* bar = &full[ps];
+        if (i < st_n) {
+          const uint32_t base = st_lo + (uint32_t)i * (uint32_t)SG.ch;
+          const uint32_t cnt = min((uint32_t)SG.ch, st_hi - base), cnt4 = cnt & ~3u;
+          const uint32_t bi = (SG.g_img && cnt4) ? cnt4 * 12u : 0u, bv = SG.g_vel ? cnt * PB : 0u;
+          mbar_expect_tx(bar, cnt * PB + bi + bv);
+          tma_bulk_g2s(stage, reinterpret_cast<const unsigned char*>(S.positions) + (size_t)base * PB, cnt * PB, bar);
+          if (bi) tma_bulk_g2s(stage + SG.g_img, reinterpret_cast<const unsigned char*>(S.images) + (size_t)base * 12u, bi, bar);
+          if (bv) tma_bulk_g2s(stage + SG.g_vel, reinterpret_cast<const unsigned char*>(S.vel_mass) + (size_t)base * PB, bv, bar);
+        } else {
+          const uint32_t base = st_lo + (uint32_t)(i - st_n) * (uint32_t)SG.ch;
+          const uint32_t cnt = min((uint32_t)SG.ch, st_hi - base), cnt4 = cnt & ~3u;
+          const uint32_t bp = SG.s_pos ? cnt * PB : 0u, bi = (SG.s_img && cnt4) ? cnt4 * 12u : 0u;
+          mbar_expect_tx(bar, cnt * PB + bp + bi);
+          tma_bulk_g2s(stage, reinterpret_cast<const unsigned char*>(S.forces) + (size_t)base * PB, cnt * PB, bar);
+          if (bp) tma_bulk_g2s(stage + SG.s_pos, reinterpret_cast<const unsigned char*>(S.positions) + (size_t)base * PB, bp, bar);
+          if (bi) tma_bulk_g2s(stage + SG.s_img, reinterpret_cast<const unsigned char*>(S.images) + (size_t)base * 12u, bi, bar);
+        }
+      }
+    }
+  };
+  // the consumer side: wait for the next item, return its stage, advance
+  auto stream_next_stage = [&]() -> unsigned char* {
+    unsigned char* stage = ring + (uint32_t)st_cstage * SG.stage_bytes;
+    mbar_wait(&full[st_cstage], st_cphase);
+    if (++st_cstage == SG.stages) { st_cstage = 0; st_cphase ^= 1u; }
+    return stage;
+  };
+  if constexpr (STREAM) {
+    const uint32_t N = (uint32_t)M.natoms;
+    const uint32_t wrun = (((N + nb - 1) / nb + NWARPS - 1) / NWARPS + 3u) & ~3u;  // warp runs start on multiples of 4 slots
+    const uint32_t schunk = wrun * NWARPS;                                         // (16-byte aligned image rows)
+    const uint32_t c_lo = min(N, (uint32_t)b * schunk), c_hi = min(N, c_lo + schunk);
+    st_lo = min(c_hi, c_lo + (uint32_t)warp * wrun);
+    st_hi = min(c_hi, st_lo + wrun);
+    st_n = (int)((st_hi - st_lo + (uint32_t)SG.ch - 1u) / (uint32_t)SG.ch);
+    const bool scatters = (METHOD != SM_UNBIASED) && S.mode == MODE_STEP;
+    st_total = scatters ? 2 * st_n : st_n;
+    if (lane == 0) {
+      for (int s2 = 0; s2 < SG.stages; ++s2) mbar_init(&full[s2], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // Engine arrays this library never writes may be fetched before the dependency wait.  First what the critical
+    // path needs first -- the tag -> slot lookups of pass 0, one register batch of P0U per thread -- then the
+    // gather chunks, which then stream in behind them while pass 0 scatters its map words.
+    {
+      const uint32_t chunk0 = (M.T + nb - 1) / nb;
+      const uint32_t q0 = min(M.T, (uint32_t)b * chunk0), q1 = min(M.T, q0 + chunk0);
+#pragma unroll
+      for (int u = 0; u < P0U; ++u) {
+        const uint32_t t = min(q0 + tid + (uint32_t)u * BLOCK, max(q1, 1u) - 1u);  // clamped: loads stay unconditional
+        int g = 0;
+        while (g + 1 < M.ngroups && t >= M.grp[g].t1) ++g;
+        p0_slot[u] = A::slot(S, M, term_tag_of(M, M.grp[g], t));
+      }
+    }
+    stream_issue_upto(min(st_n, min(SG.stages, SG.early)));
+  }
   const MethodDev& m = M.m;
   constexpr bool metad_direct = (METHOD == SM_METAD_DIRECT);
   constexpr bool grid_metad = (METHOD == SM_METAD_GRID);
@@ -1272,12 +1411,12 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
 
   // ---- force network (psb_set_force_net): header + parameters into shared memory -----------------
   if (is_abf && (M.nn != nullptr || (M.fs != nullptr && M.fs_staged)) && tid >= BLOCK - 64) {
-    static_assert(sizeof(ForceNet) % 8 == 0 && offsetof(StepShared, nnw) == offsetof(StepShared, nnh) + sizeof(ForceNet),
+    static_assert(sizeof(ForceNet) % 8 == 0 && offsetof(NetShared, nnw) == offsetof(NetShared, nnh) + sizeof(ForceNet),
                   "header and staged parameters are copied as one block");
     const bool net = M.nn != nullptr;  // a handle has a network or a series, never both
     const unsigned long long* src = net ? reinterpret_cast<const unsigned long long*>(M.nn)
                                         : reinterpret_cast<const unsigned long long*>(M.fs);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.nnh);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.net->nnh);
     const int words = net ? (int)(sizeof(ForceNet) / 8) + M.nn_np : M.fs_staged;
     for (int i = tid - (BLOCK - 64); i < words; i += 64) dst[i] = __ldcg(src + i);
   }
@@ -1399,7 +1538,19 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         gtag0[j] = ok ? M.grp[j].tag0 : 0u;
         all_contig = all_contig && (!ok || M.grp[j].contig);
       }
-      for (uint32_t base = q0 + tid; base < q1; base += 8 * BLOCK) {
+      uint32_t p0_done = q0;  // terms below it are handled by the prologue batch
+      if constexpr (STREAM) {
+        p0_done = min(q1, q0 + (uint32_t)P0U * BLOCK);
+#pragma unroll
+        for (int u = 0; u < P0U; ++u) {
+          const uint32_t t = q0 + tid + (uint32_t)u * BLOCK;
+          if (t < p0_done) {
+            const int g = (int)(t >= gb[0]) + (int)(t >= gb[1]) + (int)(t >= gb[2]);
+            M.slot_map[p0_slot[u]] = stamp | (uint32_t)(g + 1);
+          }
+        }
+      }
+      for (uint32_t base = p0_done + tid; base < q1; base += 8 * BLOCK) {
         uint32_t slot[8], word[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -1418,7 +1569,140 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       PSB_STAMP(7);
       grid_sync(M, sh, BAR_SLOT);
     }
-    if (slot_major && !TAGMAP) {
+    if constexpr (STREAM) {
+      stream_issue_upto(SG.stages);  // force rows may follow now (the dependency wait is behind us)
+      double acc4[4][6];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc4[g][a] = 0.0;
+      const int S_ = SG.stages;
+      const uint32_t CH = (uint32_t)SG.ch;  // 128 slots: four rows per lane
+      // slot_map words (written by pass 0; their sectors were written piecewise, a read costs a DRAM-class latency):
+      // fetched MG chunks ahead so that one latency covers MG chunks of work
+      constexpr int MG = 4;
+      uint32_t wnext[MG][STREAM_RPL];
+      auto map_words = [&](int c0, uint32_t (&w)[MG][STREAM_RPL]) {
+#pragma unroll
+        for (int j = 0; j < MG; ++j) {
+          const uint32_t base = st_lo + (uint32_t)(c0 + j) * CH;
+#pragma unroll
+          for (int u = 0; u < STREAM_RPL; ++u) {
+            const uint32_t sl = base + lane + 32u * u;
+            w[j][u] = (c0 + j < st_n && sl < st_hi) ? __ldcg(M.slot_map + sl) : 0u;
+          }
+        }
+      };
+      map_words(0, wnext);
+      PSB_STAMPS(8);
+      // One instantiation per (group count, RoG present): the loop is issue-bound (conversions run at 16 per clock
+      // and SM, fp64 at 64), so it carries no per-row code it does not need.  Point groups sum the fp64-converted
+      // stored positions and the image flags separately (integers, exact) and unwrap the SUM, sum (p_i + L n_i) =
+      // sum p_i + L sum n_i (hoomd.py:179-181 per atom; equal within a few ulp, far inside the 1e-10 gate); RoG
+      // groups need every unwrapped r_i for r_i . r_i and keep the per-atom form.
+      auto gather_chunks = [&](auto NGc, auto ROGc) {
+        constexpr int NG = decltype(NGc)::value;
+        constexpr bool ROG = decltype(ROGc)::value;
+        int isum[NG][3];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) isum[g][0] = isum[g][1] = isum[g][2] = 0;
+        for (int c0 = 0; c0 < st_n; c0 += MG) {
+          uint32_t wcur[MG][STREAM_RPL];
+#pragma unroll
+          for (int j = 0; j < MG; ++j)
+#pragma unroll
+            for (int u = 0; u < STREAM_RPL; ++u) wcur[j][u] = wnext[j][u];
+          map_words(c0 + MG, wnext);  // in flight while these MG chunks are processed
+#pragma unroll
+          for (int j = 0; j < MG; ++j) {
+          const int c = c0 + j;
+          if (c >= st_n) break;
+          const uint32_t base = st_lo + (uint32_t)c * CH;
+          const uint32_t cnt = min(CH, st_hi - base), cnt4 = cnt & ~3u;
+          uint32_t w[STREAM_RPL];
+#pragma unroll
+          for (int u = 0; u < STREAM_RPL; ++u) w[u] = wcur[j][u];
+          const unsigned char* stage = stream_next_stage();
+          if (c < 3) PSB_STAMPS(9 + 2 * c);
+          R4s p4[STREAM_RPL], v4[STREAM_RPL];
+          int im[STREAM_RPL][3];
+#pragma unroll
+          for (int u = 0; u < STREAM_RPL; ++u) {  // all shared-memory loads of the rows first
+            const uint32_t row = min(lane + 32u * u, cnt - 1u);  // clamped: loads stay unconditional
+            p4[u] = reinterpret_cast<const R4s*>(stage)[row];
+            if (SG.g_img) {
+              if (row < cnt4) {
+                const int* q = reinterpret_cast<const int*>(stage + SG.g_img) + 3 * row;
+                im[u][0] = q[0]; im[u][1] = q[1]; im[u][2] = q[2];
+              } else {  // tail rows of the very last run (bulk copies move multiples of 16 bytes)
+                const int* q = reinterpret_cast<const int*>(S.images) + 3 * (size_t)(base + row);
+                im[u][0] = __ldg(q); im[u][1] = __ldg(q + 1); im[u][2] = __ldg(q + 2);
+              }
+            } else {
+              im[u][0] = im[u][1] = im[u][2] = 0;
+            }
+            if (momenta_sums) v4[u] = reinterpret_cast<const R4s*>(stage + SG.g_vel)[row];
+          }
+#pragma unroll
+          for (int u = 0; u < STREAM_RPL; ++u) {
+            V3 r = v3((double)p4[u].x, (double)p4[u].y, (double)p4[u].z);
+            if (ROG && SG.g_img) {  // hoomd.py:179-181: pos + diag(H) * images, in fp64
+              r.x = __dadd_rn(r.x, __dmul_rn(S.L[0], (double)im[u][0]));
+              r.y = __dadd_rn(r.y, __dmul_rn(S.L[1], (double)im[u][1]));
+              r.z = __dadd_rn(r.z, __dmul_rn(S.L[2], (double)im[u][2]));
+            }
+            V3 pm = v3(0, 0, 0);
+            if (momenta_sums)  // hoomd.py:192-196: (M * V) in the array's own dtype, promoted afterwards
+              pm = v3((double)(Real)(v4[u].w * v4[u].x), (double)(Real)(v4[u].w * v4[u].y), (double)(Real)(v4[u].w * v4[u].z));
+            const bool hit = (lane + 32u * u < cnt) && ((w[u] & ~15u) == stamp);
+            const int g = hit ? (int)(w[u] & 15u) - 1 : -1;
+            if (c * STREAM_RPL + u < 16) grp_nib |= (unsigned long long)(g + 1) << (4 * (c * STREAM_RPL + u));  // for the scatter
+#pragma unroll
+            for (int gg = 0; gg < NG; ++gg) {
+              const bool mine = (g == gg);
+              const double wgt = mine ? 1.0 : 0.0;
+              double a0 = r.x;
+              if (ROG && ((rog_bits >> gg) & 1u)) a0 = r.x * r.x + r.y * r.y + r.z * r.z;  // RoG groups: sum of r.r
+              acc4[gg][0] = fma(wgt, a0, acc4[gg][0]);
+              acc4[gg][1] = fma(wgt, r.y, acc4[gg][1]);
+              acc4[gg][2] = fma(wgt, r.z, acc4[gg][2]);
+              if (!ROG) {
+                const int mi = mine ? 1 : 0;
+                isum[gg][0] += mi * im[u][0]; isum[gg][1] += mi * im[u][1]; isum[gg][2] += mi * im[u][2];
+              }
+              if (momenta_sums) {
+                acc4[gg][3] = fma(wgt, pm.x, acc4[gg][3]);
+                acc4[gg][4] = fma(wgt, pm.y, acc4[gg][4]);
+                acc4[gg][5] = fma(wgt, pm.z, acc4[gg][5]);
+              }
+            }
+          }
+          __syncwarp();  // stage drained
+          if (c < 3) PSB_STAMPS(10 + 2 * c);
+          stream_issue_upto((SG.flags & 1) ? min(c + 1 + S_, st_n) : c + 1 + S_);
+          }
+        }
+        if (!ROG && SG.g_img) {
+#pragma unroll
+          for (int gg = 0; gg < NG; ++gg) {
+            acc4[gg][0] = fma(S.L[0], (double)isum[gg][0], acc4[gg][0]);
+            acc4[gg][1] = fma(S.L[1], (double)isum[gg][1], acc4[gg][1]);
+            acc4[gg][2] = fma(S.L[2], (double)isum[gg][2], acc4[gg][2]);
+          }
+        }
+      };
+      using std::integral_constant;
+      if (rog_bits) gather_chunks(integral_constant<int, 4>{}, integral_constant<bool, true>{});
+      else if (M.ngroups <= 2) gather_chunks(integral_constant<int, 2>{}, integral_constant<bool, false>{});
+      else gather_chunks(integral_constant<int, 4>{}, integral_constant<bool, false>{});
+      PSB_STAMPS(15);
+      if (SG.flags & 1) stream_issue_upto(st_n + S_);
+      const int na = momenta_sums ? 6 : 3;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < M.ngroups) block_reduce_store(sh, acc4[g], na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+    }
+    if (slot_major && !TAGMAP && !STREAM) {
       double acc4[4][6];
       slot_gather(acc4);
       const int na = momenta_sums ? 6 : 3;
@@ -1466,7 +1750,8 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
       grid_sync(M, sh, BAR_A);
       PSB_STAMP(2);
       PSB_CLK(8);
-      reduce_rows(M, sh, 0, 0, planA);
+      if (SLOT && nb > 48) reduce_rows_wide(M, sh);
+      else reduce_rows(M, sh, 0, 0, planA);
     }
     PSB_CLK(9);
     if (warp == 0) {
@@ -1729,7 +2014,94 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   if (will_scatter) {
     const Fin& f = sh.fin;
     const bool dense = GENERAL && (M.bias_dense != nullptr);
-    if (slot_major) {
+    if constexpr (STREAM) {
+      // force rows arrive in the ring (most of them were requested before the grid-wide exchange), are updated in
+      // shared memory and go back with one bulk store per chunk
+      double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0, rs3 = 0.0;
+      if (rog_bits) {
+        auto scale_of = [&](int g) {
+          return ((rog_bits >> g) & 1u) ? -f.F[M.cv[M.grp[g].cv].comp0] * f.cvx[M.grp[g].cv][0] : 0.0;
+        };
+        rs0 = scale_of(0); rs1 = scale_of(1); rs2 = scale_of(2); rs3 = scale_of(3);
+      }
+      const int S_ = SG.stages;
+      const uint32_t CH = (uint32_t)SG.ch;
+      // group of a row: from the nibbles the gather kept (runs of up to 16 rows per lane), else from slot_map again
+      const bool nibbles = st_n * STREAM_RPL <= 16;
+      constexpr int MG = 4;
+      uint32_t wnext[MG][STREAM_RPL];
+      auto map_words = [&](int j0, uint32_t (&w)[MG][STREAM_RPL]) {
+#pragma unroll
+        for (int jj = 0; jj < MG; ++jj) {
+          const uint32_t base = st_lo + (uint32_t)(j0 + jj) * CH;
+#pragma unroll
+          for (int u = 0; u < STREAM_RPL; ++u) {
+            const uint32_t sl = base + lane + 32u * u;
+            w[jj][u] = (!nibbles && j0 + jj < st_n && sl < st_hi) ? __ldcg(M.slot_map + sl) : 0u;
+          }
+        }
+      };
+      map_words(0, wnext);
+      for (int j0 = 0; j0 < st_n; j0 += MG) {
+        uint32_t wcur[MG][STREAM_RPL];
+#pragma unroll
+        for (int jj = 0; jj < MG; ++jj)
+#pragma unroll
+          for (int u = 0; u < STREAM_RPL; ++u) wcur[jj][u] = wnext[jj][u];
+        map_words(j0 + MG, wnext);
+#pragma unroll
+        for (int jj = 0; jj < MG; ++jj) {
+        const int j = j0 + jj;
+        if (j >= st_n) break;
+        const int i = st_n + j;
+        const uint32_t base = st_lo + (uint32_t)j * CH;
+        const uint32_t cnt = min(CH, st_hi - base), cnt4 = cnt & ~3u;
+        unsigned char* stage = stream_next_stage();
+#pragma unroll
+        for (int u = 0; u < STREAM_RPL; ++u) {
+          const uint32_t row = lane + 32u * u;
+          int g;
+          if (nibbles) g = (int)((grp_nib >> (4 * (j * STREAM_RPL + u))) & 15ULL) - 1;
+          else g = ((wcur[jj][u] & ~15u) == stamp) ? (int)(wcur[jj][u] & 15u) - 1 : -1;
+          if (row >= cnt || g < 0) continue;
+          V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
+          if (rog_bits && ((rog_bits >> g) & 1u)) {  // -F d<r.r>/dr_i = rs_g * r_i (unwrapped, shape.py:52-57)
+            const R4s p4 = reinterpret_cast<const R4s*>(stage + SG.s_pos)[row];
+            V3 r = v3((double)p4.x, (double)p4.y, (double)p4.z);
+            if (SG.s_img) {
+              int ix, iy, iz;
+              if (row < cnt4) {
+                const int* q = reinterpret_cast<const int*>(stage + SG.s_img) + 3 * row;
+                ix = q[0]; iy = q[1]; iz = q[2];
+              } else {
+                const int* q = reinterpret_cast<const int*>(S.images) + 3 * (size_t)(base + row);
+                ix = __ldg(q); iy = __ldg(q + 1); iz = __ldg(q + 2);
+              }
+              r.x = __dadd_rn(r.x, __dmul_rn(S.L[0], (double)ix));
+              r.y = __dadd_rn(r.y, __dmul_rn(S.L[1], (double)iy));
+              r.z = __dadd_rn(r.z, __dmul_rn(S.L[2], (double)iz));
+            }
+            fo = (g == 0 ? rs0 : (g == 1 ? rs1 : (g == 2 ? rs2 : rs3))) * r;
+          }
+          R4s* fr = reinterpret_cast<R4s*>(stage) + row;  // hoomd.py:229: fp64 sum, rounded once to the force dtype
+          R4s q4 = *fr;
+          q4.x = (Real)((double)q4.x + fo.x);
+          q4.y = (Real)((double)q4.y + fo.y);
+          q4.z = (Real)((double)q4.z + fo.z);
+          *fr = q4;
+        }
+        fence_proxy_async();  // generic-proxy writes above -> async-proxy read by the bulk store
+        __syncwarp();
+        if (lane == 0) {
+          tma_bulk_s2g(reinterpret_cast<unsigned char*>(S.forces) + (size_t)base * PB, stage, cnt * PB);
+          bulk_commit();
+          bulk_wait_read<1>();  // the store of the PREVIOUS chunk has read its stage: that stage may be refilled
+        }
+        stream_issue_upto(i + S_);  // item (i - 1) + S
+        }
+      }
+      if (lane == 0) bulk_wait_all();
+    } else if (slot_major) {
 #ifndef PSB_SLOT_SUS
 #define PSB_SLOT_SUS 8
 #endif
