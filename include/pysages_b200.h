@@ -219,6 +219,25 @@ psb_status psb_step_host(psb_handle* h, const psb_snapshot* host_snap, int64_t t
  * openmm.py:64-89 with the CPU / Reference platform); synchronises. */
 psb_status psb_evaluate_cvs_host(psb_handle* h, const psb_snapshot* host_snap, void* cuda_stream);
 
+/* ---- many independent simulations per launch ------------------------------------------------- */
+/* Replaces the replica loop of UmbrellaIntegration's run (methods/umbrella_integration.py:128-203: one
+ * `_run_replica` per window, each with its own per-step callback): the windows of one process step in lockstep,
+ * ONE cooperative launch per MD step for all of them.  Every simulation keeps its own handle (state, index
+ * tables, workspaces, barrier counters) and its own CTA range inside the launch, so its results are bit-identical
+ * to psb_step on that handle.  All members of a batch share engine layout, dtype, method kind and kernel class;
+ * CVs that need helper kernels (pairwise coordination, eRMSD), dense outputs and the slot-ordered class are
+ * refused with PSB_ERR_UNSUPPORTED (step those with psb_step).  `snaps` holds one psb_snapshot per simulation, in
+ * the order of `handles`.  Launches are stream-ordered like psb_step; use one stream per batch. */
+typedef struct psb_batch psb_batch;
+psb_status psb_batch_create(psb_handle* const* handles, int32_t n, psb_batch** out);
+void psb_batch_destroy(psb_batch* b);
+psb_status psb_batch_step(psb_batch* b, const psb_snapshot* snaps, int64_t timestep, void* cuda_stream);
+/* psb_run_cycle for a batch: `snaps` is (nsnaps, n) row-major, step i uses row i % nsnaps; one pass over the ring is
+ * captured as a CUDA graph whenever nsteps >= nsnaps. */
+psb_status psb_batch_run_cycle(psb_batch* b, const psb_snapshot* snaps, int32_t nsnaps, int64_t nsteps,
+                               void* cuda_stream);
+int64_t psb_batch_launch_count(psb_batch* b);
+
 /* ---- state access (callbacks, checkpoint/restart: serialization.py:44-93) -------------- */
 /* Field names follow the reference State tuples: "xi", "bias", "ncalls", "heights",
  * "centers", "sigmas", "grid_potential", "grid_gradient", "idx", "hist", "Fsum", "force",

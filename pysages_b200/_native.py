@@ -148,6 +148,11 @@ EXPORTS = {
     "psb_run_cycle": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_int32, c_int64, c_void_p]),
     "psb_step_host": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_int64, c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "psb_evaluate_cvs_host": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_void_p]),
+    "psb_batch_create": (c_int32, [POINTER(c_void_p), c_int32, POINTER(c_void_p)]),
+    "psb_batch_destroy": (None, [c_void_p]),
+    "psb_batch_step": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_int64, c_void_p]),
+    "psb_batch_run_cycle": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_int32, c_int64, c_void_p]),
+    "psb_batch_launch_count": (c_int64, [c_void_p]),
     "psb_state_info": (c_int32, [c_void_p, c_char_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_void_p)]),
     "psb_get_state": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "psb_set_state": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),

@@ -93,12 +93,33 @@ def _nth(seq, i):
     return None if seq is None else seq[i]
 
 
+def _run_umbrella_lockstep(method, context_generator, timesteps, context_args, post_run_action, todo):
+    """All windows of this process advance together, one launch per MD step for all their bias steps
+    (parallel.WindowBatch / psb_batch_step) instead of one replica after the other."""
+    from . import parallel
+
+    contexts = []
+    for n in todo:
+        replica_args = deepcopy(context_args)
+        replica_args["replica_num"] = n
+        contexts.append(SamplingContext(method.submethods[n], context_generator, method.histograms[n], replica_args))
+    parallel.run_lockstep(contexts, timesteps)
+    if post_run_action:
+        for c in contexts:
+            post_run_action(context=c.context)
+    return Result(method, [c.sampler.state for c in contexts], [c.sampler.callback for c in contexts],
+                  [c.sampler.take_snapshot() for c in contexts])
+
+
 def _run_umbrella(method_or_result, context_generator, timesteps, context_args, post_run_action,
-                  executor, executor_shutdown, windows=None, **kwargs):
-    """umbrella_integration.py:128-203; `windows` restricts the run to a subset (multi-GPU partition)."""
+                  executor, executor_shutdown, windows=None, lockstep=False, **kwargs):
+    """umbrella_integration.py:128-203; `windows` restricts the run to a subset (multi-GPU partition);
+    `lockstep=True` steps the windows together with one launch per MD step (engines steppable from outside)."""
     restart = isinstance(method_or_result, Result)
     method = method_or_result.method if restart else method_or_result
     todo = list(range(len(method.submethods))) if windows is None else list(windows)
+    if lockstep and not restart:
+        return _run_umbrella_lockstep(method, context_generator, int(timesteps), context_args, post_run_action, todo)
     futures = []
     for n in todo:
         replica_args = deepcopy(context_args)

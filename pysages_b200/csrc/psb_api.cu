@@ -140,6 +140,8 @@ struct psb_handle {
   // staging for psb_step_host
   psb_snapshot dev_snap{};
   bool have_staging = false;
+  std::vector<std::pair<const void*, size_t>> host_ranges;  // engine arrays seen by psb_step_host (and page-locked by it)
+  std::vector<void*> host_registered;                        // ... the ones this handle registered itself
   size_t hpad = 0;
 };
 
@@ -300,6 +302,7 @@ int32_t psb_abi_version(void) { return 1; }
 void psb_destroy(psb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (void* p : h->host_registered) cudaHostUnregister(p);
   if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
@@ -975,6 +978,209 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
   return PSB_OK;
 }
 
+// ---- many independent simulations per launch (umbrella windows) ---------------------------------------------
+}  // extern "C"
+
+struct psb_batch {
+  std::vector<psb_handle*> hs;
+  const StepVTable* vt = nullptr;
+  int device = 0;
+  int total_ctas = 0;
+  int32_t* d_cta_item = nullptr;  // (total_ctas) CTA -> simulation
+  // Descriptor arrays live in device memory (as a kernel parameter they would cost launch latency): one per distinct
+  // set of snapshot pointers seen, found again by content -- engines re-present the same buffers step after step
+  // (OpenMM: persistent; HOOMD: two alternating sets), a benchmark ring its nsnaps sets.
+  struct Slot {
+    std::vector<BatchItem> host;
+    BatchItem* dev = nullptr;
+  };
+  std::vector<Slot> slots;
+  size_t next_victim = 0;
+  long long launches = 0;
+  cudaGraphExec_t cycle_exec = nullptr;
+  std::vector<psb_snapshot> cycle_key;
+  cudaStream_t cycle_stream = nullptr;
+  int graph_replays = 0;
+};
+
+namespace {
+
+constexpr size_t BATCH_MAX_SLOTS = 256;
+
+// descriptor array for `snaps` (n = hs.size() snapshots), uploaded on `stream` if it is not resident yet
+psb_status batch_items(psb_batch* B, const psb_snapshot* snaps, cudaStream_t stream, const BatchItem** out) {
+  const size_t n = B->hs.size();
+  std::vector<BatchItem> items(n);
+  int cta0 = 0;
+  for (size_t i = 0; i < n; ++i) {
+    psb_handle* h = B->hs[i];
+    psb_status st = check_snapshot(h, snaps + i, true);
+    if (st != PSB_OK) return st;
+    memset(&items[i], 0, sizeof(BatchItem));
+    items[i].model = h->d_model;
+    items[i].snap = make_snap(h, snaps + i, MODE_STEP);
+    items[i].snap.dbg = nullptr;
+    items[i].cta0 = cta0;
+    items[i].ncta = h->grid;
+    cta0 += h->grid;
+  }
+  for (psb_batch::Slot& sl : B->slots)
+    if (memcmp(sl.host.data(), items.data(), n * sizeof(BatchItem)) == 0) {
+      *out = sl.dev;
+      return PSB_OK;
+    }
+  psb_batch::Slot* sl = nullptr;
+  if (B->slots.size() < BATCH_MAX_SLOTS) {
+    B->slots.emplace_back();
+    sl = &B->slots.back();
+    CUDA_TRY(cudaMalloc(&sl->dev, n * sizeof(BatchItem)));
+  } else {  // reuse the oldest array: the copy below is ordered after the launches that read it (same stream)
+    sl = &B->slots[B->next_victim];
+    B->next_victim = (B->next_victim + 1) % BATCH_MAX_SLOTS;
+  }
+  sl->host = items;
+  CUDA_TRY(cudaMemcpyAsync(sl->dev, sl->host.data(), n * sizeof(BatchItem), cudaMemcpyHostToDevice, stream));
+  *out = sl->dev;
+  return PSB_OK;
+}
+
+psb_status batch_enqueue(psb_batch* B, const psb_snapshot* snaps, cudaStream_t stream) {
+  const BatchItem* items = nullptr;
+  psb_status st = batch_items(B, snaps, stream, &items);
+  if (st != PSB_OK) return st;
+  psb_handle* h0 = B->hs[0];
+  CUDA_TRY(B->vt->launch_batch(h0->step_method, h0->step_general, items, B->d_cta_item, B->total_ctas, h0->dyn_smem,
+                               stream, h0->pdl));
+  ++B->launches;
+  return PSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+psb_status psb_batch_create(psb_handle* const* handles, int32_t n, psb_batch** out) {
+  if (!handles || !out || n < 1) return fail(PSB_ERR_VALUE, "invalid arguments");
+  *out = nullptr;
+  psb_handle* h0 = handles[0];
+  if (!h0) return fail(PSB_ERR_VALUE, "NULL handle");
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    psb_handle* h = handles[i];
+    if (!h) return fail(PSB_ERR_VALUE, "NULL handle");
+    for (int j = 0; j < i; ++j)
+      if (handles[j] == h) return fail(PSB_ERR_VALUE, "simulation %d appears twice in the batch", i);
+    // one launch runs one instantiation of the step kernel: same engine layout, dtype, method kind and kernel class
+    if (h->layout.layout != h0->layout.layout || h->layout.real_bytes != h0->layout.real_bytes ||
+        h->step_method != h0->step_method || h->step_general != h0->step_general || h->dyn_smem != h0->dyn_smem ||
+        h->device != h0->device)
+      return fail(PSB_ERR_VALUE, "simulation %d differs from simulation 0 in layout, dtype, method or kernel class: "
+                                 "a batch shares one kernel instantiation", i);
+    if (h->step_general != SC_POINT && h->step_general != SC_GENERAL)
+      return fail(PSB_ERR_UNSUPPORTED, "simulation %d uses the slot-ordered class (most atoms of a very large system "
+                                       "selected): it fills the device by itself, step it with psb_step", i);
+    if (!h->coord.empty() || !h->ermsd.empty() || h->model.bias_dense ||
+        (h->layout.layout == PSB_LAYOUT_OPENMM_CUDA && !h->model.slot_major))
+      return fail(PSB_ERR_UNSUPPORTED, "simulation %d needs helper launches before its step kernel (pairwise / eRMSD "
+                                       "CVs, OpenMM inverse permutation, dense outputs): step it with psb_step", i);
+    total += h->grid;
+  }
+  const StepVTable* vt = pick_vtable(h0->layout);
+  const int occ = vt->batch_occupancy(h0->step_method, h0->step_general, h0->dyn_smem);
+  if ((long long)occ * h0->num_sms < total)
+    return fail(PSB_ERR_VALUE, "the batch needs %d co-resident CTAs, the device holds %d: split it", total, occ * h0->num_sms);
+  psb_batch* B = new psb_batch();
+  B->hs.assign(handles, handles + n);
+  B->vt = vt;
+  B->device = h0->device;
+  B->total_ctas = total;
+  std::vector<int32_t> cta_item((size_t)total);
+  int c = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < handles[i]->grid; ++j) cta_item[c++] = i;
+  cudaError_t e = cudaMalloc(&B->d_cta_item, sizeof(int32_t) * (size_t)total);
+  if (e == cudaSuccess) e = cudaMemcpy(B->d_cta_item, cta_item.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete B;
+    return fail(PSB_ERR_CUDA, "CUDA error %s in psb_batch_create", cudaGetErrorString(e));
+  }
+  *out = B;
+  return PSB_OK;
+}
+
+void psb_batch_destroy(psb_batch* B) {
+  if (!B) return;
+  cudaSetDevice(B->device);
+  if (B->cycle_exec) cudaGraphExecDestroy(B->cycle_exec);
+  for (psb_batch::Slot& sl : B->slots) cudaFree(sl.dev);
+  cudaFree(B->d_cta_item);
+  delete B;
+}
+
+psb_status psb_batch_step(psb_batch* B, const psb_snapshot* snaps, int64_t timestep, void* cuda_stream) {
+  (void)timestep;
+  if (!B || !snaps) return fail(PSB_ERR_VALUE, "NULL argument");
+  psb_status st = batch_enqueue(B, snaps, (cudaStream_t)cuda_stream);
+  if (st != PSB_OK) return st;
+  for (psb_handle* h : B->hs) ++h->host_ncalls;
+  return PSB_OK;
+}
+
+psb_status psb_batch_run_cycle(psb_batch* B, const psb_snapshot* snaps, int32_t nsnaps, int64_t nsteps, void* cuda_stream) {
+  if (!B || !snaps || nsnaps < 1 || nsteps < 0) return fail(PSB_ERR_VALUE, "invalid arguments");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  const size_t n = B->hs.size();
+  int64_t done = 0;
+  B->graph_replays = 0;
+  static const bool no_graph = getenv("PSB_NO_GRAPH") != nullptr;
+  if (!no_graph && stream != nullptr && nsteps >= (int64_t)nsnaps) {
+    const bool same = B->cycle_exec && B->cycle_stream == stream && B->cycle_key.size() == n * (size_t)nsnaps &&
+                      memcmp(B->cycle_key.data(), snaps, sizeof(psb_snapshot) * n * nsnaps) == 0;
+    if (!same) {
+      if (B->cycle_exec) cudaGraphExecDestroy(B->cycle_exec);
+      B->cycle_exec = nullptr;
+      // descriptor uploads must not be part of the captured work: make every ring position resident first
+      for (int r = 0; r < nsnaps; ++r) {
+        const BatchItem* unused = nullptr;
+        psb_status st = batch_items(B, snaps + (size_t)r * n, stream, &unused);
+        if (st != PSB_OK) return st;
+      }
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaGraph_t graph = nullptr;
+      const long long l0 = B->launches;
+      if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        psb_status st = PSB_OK;
+        for (int r = 0; r < nsnaps && st == PSB_OK; ++r) st = batch_enqueue(B, snaps + (size_t)r * n, stream);
+        cudaError_t e = cudaStreamEndCapture(stream, &graph);
+        if (st == PSB_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&B->cycle_exec, graph, 0) == cudaSuccess) {
+          B->cycle_key.assign(snaps, snaps + n * (size_t)nsnaps);
+          B->cycle_stream = stream;
+        } else {
+          B->cycle_exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();
+      B->launches = l0;
+    }
+    if (B->cycle_exec) {
+      const int64_t reps = nsteps / nsnaps;
+      for (int64_t r = 0; r < reps; ++r) CUDA_TRY(cudaGraphLaunch(B->cycle_exec, stream));
+      done = reps * nsnaps;
+      B->launches += done;
+      B->graph_replays = 1;
+    }
+  }
+  for (int64_t i = done; i < nsteps; ++i) {
+    psb_status st = batch_enqueue(B, snaps + (size_t)(i % nsnaps) * n, stream);
+    if (st != PSB_OK) return st;
+  }
+  for (psb_handle* h : B->hs) h->host_ncalls += nsteps;
+  return PSB_OK;
+}
+
+int64_t psb_batch_launch_count(psb_batch* B) { return B ? B->launches : 0; }
+
 psb_status psb_walker_begin(psb_handle* h, const psb_snapshot* snap, int64_t timestep,
                             double* record_dev, void* cuda_stream) {
   (void)timestep;
@@ -1059,6 +1265,26 @@ psb_status psb_set_state(psb_handle* h, const char* field, const void* src_host,
   return PSB_OK;
 }
 
+// Engine arrays that live in ordinary (pageable) host memory cross PCIe at a third of the rate of page-locked
+// memory (measured on the B200 boxes: 19.6 vs 53.7 GB/s, tools/native/pin_probe.cu) because every copy is staged
+// through the driver's bounce buffers.  The arrays of a CPU engine are long-lived, so the first psb_step_host that
+// sees one page-locks it in place (cudaHostRegister; undone by psb_destroy).  PSB_NO_HOST_REGISTER=1 disables it.
+static void pin_host_range(psb_handle* h, const void* p, size_t bytes) {
+  if (!p || !bytes) return;
+  for (const auto& r : h->host_ranges)
+    if (r.first == p && r.second >= bytes) return;
+  h->host_ranges.emplace_back(p, bytes);
+  static const bool off = getenv("PSB_NO_HOST_REGISTER") != nullptr;
+  if (off) return;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+  if (at.type != cudaMemoryTypeUnregistered) return;  // already page-locked (or managed / device memory)
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+    h->host_registered.push_back(const_cast<void*>(p));
+  else
+    cudaGetLastError();  // e.g. part of the range is registered already: copies still work, just slower
+}
+
 // host snapshot -> the handle's device staging buffers (allocated on first use)
 static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cudaStream_t stream, bool with_forces,
                                       psb_snapshot* out, int64_t* h2d_bytes, size_t* force_bytes) {
@@ -1095,16 +1321,18 @@ static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cud
   int64_t up = 0;
   auto push = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
     if (!bytes || !src) return cudaSuccess;
+    pin_host_range(h, src, bytes);
     up += (int64_t)bytes;
     return cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, stream);
   };
-  CUDA_TRY(push(d.positions, hs->positions, b_pos));
-  CUDA_TRY(push(d.vel_mass, hs->vel_mass, b_vel));
-  if (with_forces) CUDA_TRY(push(d.forces, hs->forces, b_frc));
+  // one queue: a second copy stream did not shorten the step (measured: the link is the bound, 198 vs 203 us)
   CUDA_TRY(push(d.ids, hs->ids, b_ids));
+  CUDA_TRY(push(d.positions, hs->positions, b_pos));
   CUDA_TRY(push(d.images, hs->images, b_img));
+  CUDA_TRY(push(d.vel_mass, hs->vel_mass, b_vel));
   CUDA_TRY(push(d.masses, hs->masses, b_mass));
   CUDA_TRY(push(d.types, hs->types, b_types));
+  if (with_forces) CUDA_TRY(push(d.forces, hs->forces, b_frc));
   *out = d;
   if (h2d_bytes) *h2d_bytes = up;
   if (force_bytes) *force_bytes = b_frc;

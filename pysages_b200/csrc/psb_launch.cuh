@@ -16,6 +16,10 @@ struct StepVTable {
                              cudaStream_t stream, int pdl);
   int (*occupancy)(int method, int general, size_t dyn_smem);
   size_t (*static_smem)(int method, int general);  // statically allocated shared memory of that instantiation
+  // psb_batch_step: the CTAs of many simulations in one cooperative launch (classes SC_POINT / SC_GENERAL)
+  cudaError_t (*launch_batch)(int method, int general, const BatchItem* items, const int32_t* cta_item, int grid,
+                              size_t dyn_smem, cudaStream_t stream, int pdl);
+  int (*batch_occupancy)(int method, int general, size_t dyn_smem);
   void (*launch_gather)(const Model* M, const Snap* S, int cv, double* xa, int na_pad, double* xb,
                         int nb_pad, cudaStream_t stream);
   void (*launch_ermsd)(const Model* M, const Snap* S, int cv, cudaStream_t stream);
@@ -80,6 +84,36 @@ const void* stream_entry() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BLOCK, smem) != cudaSuccess) return 0; \
     return occ;                                                                                     \
   }                                                                                                 \
+  static const void* const NAME##_bentry[SM_COUNT][2] = {                                           \
+      {(const void*)step_kernel_batch<L, R, SM_UNBIASED, SC_POINT>, (const void*)step_kernel_batch<L, R, SM_UNBIASED, SC_GENERAL>}, \
+      {(const void*)step_kernel_batch<L, R, SM_HARMONIC, SC_POINT>, (const void*)step_kernel_batch<L, R, SM_HARMONIC, SC_GENERAL>}, \
+      {(const void*)step_kernel_batch<L, R, SM_METAD_DIRECT, SC_POINT>, (const void*)step_kernel_batch<L, R, SM_METAD_DIRECT, SC_GENERAL>}, \
+      {(const void*)step_kernel_batch<L, R, SM_ABF, SC_POINT>, (const void*)step_kernel_batch<L, R, SM_ABF, SC_GENERAL>}, \
+      {(const void*)step_kernel_batch<L, R, SM_METAD_GRID, SC_POINT>, (const void*)step_kernel_batch<L, R, SM_METAD_GRID, SC_GENERAL>}}; \
+  static cudaError_t NAME##_launch_batch(int method, int general, const BatchItem* items, const int32_t* cta_item, \
+                                         int grid, size_t smem, cudaStream_t stream, int pdl) {     \
+    if (general > SC_GENERAL) return cudaErrorInvalidValue;                                         \
+    void* args[] = {(void*)&items, (void*)&cta_item};                                               \
+    cudaLaunchConfig_t cfg = {};                                                                    \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
+    cudaLaunchAttribute at[2];                                                                      \
+    at[0].id = cudaLaunchAttributeCooperative;                                                      \
+    at[0].val.cooperative = 1;                                                                      \
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                  \
+    at[1].val.programmaticStreamSerializationAllowed = 1;                                           \
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;                                                     \
+    return cudaLaunchKernelExC(&cfg, NAME##_bentry[method][general], args);                         \
+  }                                                                                                 \
+  static int NAME##_batch_occupancy(int method, int general, size_t smem) {                         \
+    int occ = 0;                                                                                    \
+    if (general > SC_GENERAL) return 0;                                                             \
+    const void* fn = NAME##_bentry[method][general];                                                \
+    if (smem > 0 &&                                                                                 \
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+      return 0;                                                                                     \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BLOCK, smem) != cudaSuccess) return 0; \
+    return occ;                                                                                     \
+  }                                                                                                 \
   static size_t NAME##_static_smem(int method, int general) {                                       \
     cudaFuncAttributes at{};                                                                        \
     if (cudaFuncGetAttributes(&at, NAME##_entry[method][general]) != cudaSuccess) return (size_t)-1; \
@@ -94,6 +128,7 @@ const void* stream_entry() {
   static void NAME##_ermsd(const Model* M, const Snap* S, int cv, cudaStream_t stream) {           \
     ermsd_kernel<L, R><<<1, ERMSD_BLOCK, 0, stream>>>(*M, *S, cv);                                  \
   }                                                                                                 \
-  const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_static_smem, NAME##_gather, NAME##_ermsd};
+  const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_static_smem, NAME##_launch_batch,   \
+                           NAME##_batch_occupancy, NAME##_gather, NAME##_ermsd};
 
 }  // namespace psb

@@ -95,12 +95,12 @@ __device__ __forceinline__ long long global_ns() {
 }
 #define PSB_CLK(slot)                                                                \
   do {                                                                               \
-    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = clock64(); \
   } while (0)
 #ifdef PSB_PROBE_PASSA  // experiment builds: clock stamps inside pass A instead of the finalizer
 #define PSB_CLKA(slot)                                                               \
   do {                                                                               \
-    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = clock64(); \
   } while (0)
 #undef PSB_CLK
 #define PSB_CLK(slot) do {} while (0)
@@ -110,7 +110,7 @@ __device__ __forceinline__ long long global_ns() {
 #ifdef PSB_PROBE_STREAM  // experiment builds: clock stamps inside the streaming passes (warp 0 of each CTA)
 #define PSB_STAMPS(slot)                                                             \
   do {                                                                               \
-    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = clock64(); \
   } while (0)
 #undef PSB_CLK
 #define PSB_CLK(slot) do {} while (0)
@@ -119,10 +119,12 @@ __device__ __forceinline__ long long global_ns() {
 #endif
 #define PSB_STAMP(slot)                                                              \
   do {                                                                               \
-    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = global_ns(); \
   } while (0)
 
 struct StepShared {
+  int32_t vnb, vb;  // the step's own grid: CTAs of this replica and this CTA's index among them (== gridDim.x, blockIdx.x
+                    // for psb_step; a sub-range of the launch for psb_batch_step)
   double red[NWARPS][NACC];
   double stage[NACC];  // this CTA's block-reduced pass-A sums, published to `partials` after griddepcontrol.wait
   double stage4[4][6]; // slot-ordered class on the OpenMM layout: the same for its (up to) four groups
@@ -176,14 +178,14 @@ __device__ __forceinline__ unsigned long long grid_arrive(const Model& M, StepSh
   __threadfence();
   red_add_u64(&M.bars[id].arrive, 1ULL);
   sh.bars_used |= 1u << id;
-  return (sh.epoch[id] + 1ULL) * gridDim.x;
+  return (sh.epoch[id] + 1ULL) * (unsigned long long)sh.vnb;
 }
 __device__ __forceinline__ void grid_wait(const Model& M, int id, unsigned long long want) {
   while (ld_acquire_u64(&M.bars[id].arrive) < want) {}
 }
 __device__ __forceinline__ void grid_sync(const Model& M, StepShared& sh, int id) {
   __syncthreads();
-  if (gridDim.x == 1) return;
+  if (sh.vnb == 1) return;
   if (threadIdx.x == 0) grid_wait(M, id, grid_arrive(M, sh, id));
   __syncthreads();
 }
@@ -224,10 +226,10 @@ __host__ __device__ __forceinline__ int nacc_for_kind(int kind, int pass, bool m
 struct RowPlan {
   int dst, blo, bhi;  // dst < 0: no row
 };
-__device__ __forceinline__ RowPlan row_plan(const Model& M, int pass, int vrows, int r) {
+__device__ __forceinline__ RowPlan row_plan(const Model& M, int pass, int vrows, int r, int nb) {
   RowPlan p{-1, 0, -1};
   const int nrows = pass < 2 ? M.row_first[pass][M.ngroups] : vrows;
-  if (gridDim.x == 1 || r >= nrows) return p;
+  if (nb == 1 || r >= nrows) return p;
   if (pass < 2) {
     int g = 0;
     while (r >= M.row_first[pass][g + 1]) ++g;
@@ -237,17 +239,17 @@ __device__ __forceinline__ RowPlan row_plan(const Model& M, int pass, int vrows,
   } else {
     p.dst = VGROUP * NACC + r;
     p.blo = 0;
-    p.bhi = (int)gridDim.x - 1;
+    p.bhi = nb - 1;
   }
   return p;
 }
 __device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int pass, int vrows, RowPlan first) {
-  const int nb = gridDim.x;
+  const int nb = sh.vnb;
   if (nb > 1) {
     const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
     const int nrows = pass < 2 ? M.row_first[pass][M.ngroups] : vrows;
     for (int r0 = 0; r0 < nrows; r0 += BLOCK / 8) {
-      const RowPlan p = (r0 == 0) ? first : row_plan(M, pass, vrows, r0 + rl);
+      const RowPlan p = (r0 == 0) ? first : row_plan(M, pass, vrows, r0 + rl, nb);
       double v = 0.0;
       if (p.dst >= 0) {
         const double* src = M.partials + (size_t)p.dst * nb;
@@ -277,7 +279,7 @@ __device__ __forceinline__ void reduce_rows(const Model& M, StepShared& sh, int 
 // gridDim / 48.  Fixed summation order (lane-strided partial sums, then the xor tree): bit-identical in every CTA.
 constexpr int WIDE_U = 10;
 __device__ __forceinline__ void reduce_rows_wide(const Model& M, StepShared& sh) {
-  const int nb = gridDim.x;
+  const int nb = sh.vnb;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nrows = M.row_first[0][M.ngroups];
   for (int r = warp; r < nrows; r += NWARPS) {
@@ -322,11 +324,11 @@ __device__ __forceinline__ void ll_load(const ulonglong2* p, unsigned long long&
 }
 // reduce_rows for pass A over the LL buffer; the caller ends it with __syncthreads().
 __device__ __forceinline__ void reduce_rows_ll(const Model& M, StepShared& sh, RowPlan first, uint32_t stamp) {
-  const int nb = gridDim.x;
+  const int nb = sh.vnb;
   const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int nrows = M.row_first[0][M.ngroups];
   for (int r0 = 0; r0 < nrows; r0 += BLOCK / 8) {
-    const RowPlan p = (r0 == 0) ? first : row_plan(M, 0, 0, r0 + rl);
+    const RowPlan p = (r0 == 0) ? first : row_plan(M, 0, 0, r0 + rl, nb);
     double v = 0.0;
     if (p.dst >= 0) {
       const ulonglong2* src = M.ll + (size_t)p.dst * nb;
@@ -1089,9 +1091,11 @@ __device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
+// The body of the step: `nb` CTAs (this one is CTA `b` of them) step the simulation described by (Mglobal, S).
+// psb_step launches exactly those CTAs (step_kernel); psb_batch_step launches the CTAs of many independent
+// simulations at once and hands every CTA its own (model, snapshot, nb, b) (step_kernel_batch).
 template <int LAYOUT, typename Real, int METHOD, int CLASS>
-__global__ void __launch_bounds__(BLOCK, (CLASS == SC_SLOT) ? SLOT_CTAS_PER_SM : 2)
-step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
+__device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, const Snap& S, const int nb_arg, const int b_arg) {
   constexpr bool GENERAL = (CLASS == SC_GENERAL);
   constexpr bool STREAM = (CLASS == SC_STREAM);  // slot-ordered, streams staged by TMA (HOOMD layout only)
   constexpr bool SLOT = (CLASS == SC_SLOT) || STREAM;
@@ -1107,7 +1111,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  PSB_STAMP(0);
+  if (S.dbg && tid == 0) S.dbg[(size_t)b_arg * 16 + 0] = global_ns();  // PSB_STAMP(0) before sh.vb exists
   // The model (index tables, method constants, state pointers: ~3 KB, fixed per handle) lives in
   // device memory and is copied into shared memory by the whole CTA: one L2 round trip.  As a
   // kernel parameter it cost 2 us of launch latency per step (measured: tools/launch_floor.py), and
@@ -1125,16 +1129,20 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     // the handle may start, so the trigger follows the atomic (one round trip, shared with the copy).
     unsigned long long seq = 0;
     if (S.cta_seq == nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    else if (tid == 0) seq = atomicAdd(S.cta_seq + blockIdx.x, 1ULL);
+    else if (tid == 0) seq = atomicAdd(S.cta_seq + b_arg, 1ULL);
     for (int i = tid; i < (int)(sizeof(Model) / 8); i += BLOCK) dst[i] = __ldg(src + i);
-    if (tid == 0) sh.seq = seq;
+    if (tid == 0) {
+      sh.seq = seq;
+      sh.vnb = nb_arg;
+      sh.vb = b_arg;
+    }
   }
   __syncthreads();
   if (S.cta_seq != nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const Model& M = sM;
   PSB_CLKA(8);
 
-  const int nb = gridDim.x, b = blockIdx.x;
+  const int nb = nb_arg, b = b_arg;
   const bool cta0 = (b == 0);
   const int k = M.k;
   // ---- SC_STREAM: every WARP owns a contiguous run of slots and a private ring of stages (psb_stream.cuh) ------
@@ -1739,7 +1747,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
 
     PSB_STAMP(1);
-    const RowPlan planA = row_plan(M, 0, 0, tid >> 3);
+    const RowPlan planA = row_plan(M, 0, 0, tid >> 3, nb);
     if (ll) {
       PSB_STAMP(2);
       PSB_CLK(8);
@@ -1787,7 +1795,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
         if (nb > 1) block_reduce_store(sh, acc, 1, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
         else block_reduce_store(sh, acc, 1, &sh.tot[g][0], 1, false);
       }
-      const RowPlan planB = row_plan(M, 1, 0, tid >> 3);
+      const RowPlan planB = row_plan(M, 1, 0, tid >> 3, nb);
       grid_sync(M, sh, BAR_B);
       reduce_rows(M, sh, 1, 0, planB);
       if (warp == 0) {
@@ -1842,7 +1850,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
     if (nb == 1) block_reduce_store(sh, acc, 14, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 14, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
-    const RowPlan planC = row_plan(M, 2, 14, tid >> 3);
+    const RowPlan planC = row_plan(M, 2, 14, tid >> 3, nb);
     grid_sync(M, sh, BAR_C);
     reduce_rows(M, sh, 2, 14, planC);
     if (warp == 0) {
@@ -1893,7 +1901,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     }
     if (nb == 1) block_reduce_store(sh, acc, 1 + k, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 1 + k, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
-    const RowPlan planH = row_plan(M, 3, 1 + k, tid >> 3);
+    const RowPlan planH = row_plan(M, 3, 1 + k, tid >> 3, nb);
     grid_sync(M, sh, BAR_H);
     reduce_rows(M, sh, 3, 1 + k, planH);
     if (warp == 0) {
@@ -2007,7 +2015,7 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   if (readers && tid == 0) {
     red_add_u64(&M.bars[BAR_READERS].arrive, 1ULL);
     sh.bars_used |= 1u << BAR_READERS;
-    readers_want = (sh.epoch[BAR_READERS] + 1ULL) * gridDim.x;
+    readers_want = (sh.epoch[BAR_READERS] + 1ULL) * (unsigned long long)nb;
   }
   PSB_STAMP(4);
   // ---- pass S: in-place force scatter ------------------------------------------------------------
@@ -2240,6 +2248,35 @@ step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
     commit_epochs(M, sh);
   }
   PSB_STAMP(6);
+}
+
+template <int LAYOUT, typename Real, int METHOD, int CLASS>
+__global__ void __launch_bounds__(BLOCK, (CLASS == SC_SLOT) ? SLOT_CTAS_PER_SM : 2)
+step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
+  step_body<LAYOUT, Real, METHOD, CLASS>(Mglobal, S, (int)gridDim.x, (int)blockIdx.x);
+}
+
+// Many independent simulations in ONE cooperative launch (psb_batch_step; umbrella windows,
+// umbrella_integration.py:128-203): CTA range [cta0, cta0 + ncta) steps simulation `item`.  Every simulation keeps
+// its own model, state, workspaces and grid-barrier counters, so the arithmetic -- and the result, bit for bit --
+// is that of its own psb_step launch with ncta CTAs.
+struct BatchItem {
+  const Model* model;
+  Snap snap;
+  int32_t cta0, ncta;
+};
+template <int LAYOUT, typename Real, int METHOD, int CLASS>
+__global__ void __launch_bounds__(BLOCK, 2)
+step_kernel_batch(const BatchItem* __restrict__ items, const int32_t* __restrict__ cta_item) {
+  __shared__ __align__(16) BatchItem it;
+  {
+    static_assert(sizeof(BatchItem) % 8 == 0, "BatchItem is copied in 8-byte words");
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(items + __ldg(cta_item + blockIdx.x));
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&it);
+    if (threadIdx.x < sizeof(BatchItem) / 8) dst[threadIdx.x] = __ldg(src + threadIdx.x);
+  }
+  __syncthreads();
+  step_body<LAYOUT, Real, METHOD, CLASS>(it.model, it.snap, it.ncta, (int)blockIdx.x - it.cta0);
 }
 
 }  // namespace psb
