@@ -12,9 +12,13 @@ four disjoint groups of 25 000 atoms (S = N = 100 000 selected atoms), HOOMD-blu
 layout, 2-D 64x64 grid with restraint walls, N = 500, dt = 0.005.  Inputs cycle over 64 distinct
 device-resident snapshots (410 MB > 126 MB L2) so no step finds its inputs in L2.
 
-`value`  : steps/s with the snapshots resident in HBM, CUDA events on the launching stream.
-`e2e`    : the same step through the C-ABI host-buffer entry point (psb_step_host): pinned host
+`value`  : steps/s with the snapshots resident in HBM, CUDA events on the launching stream; = `value_pipelined`
+           (CUDA-graph replay of the snapshot ring + programmatic dependent launch: what a launch-bound engine
+           loop that captures its step gets).  `value_plain` is the same with one plain launch per step and no
+           overlap between steps: what an engine that interleaves its own kernels sees.  Both are first-class.
+`e2e`    : the same step through the C-ABI host-buffer entry point (psb_step_host): page-locked host
            snapshot -> H2D -> step -> D2H forces, every step inside the timed region.
+`api_us_per_step`: the Python hook a HOOMD-style engine calls every step (five DLPack capsules -> one native call).
 `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`, `series`: see DESIGN.md "Measurement".
 With --gpus N > 1 (torchrun) every rank runs the workload on its own GPU as an independent
 replica (umbrella-window style, no data-path collective): weak scaling, value = aggregate steps/s.
@@ -196,17 +200,13 @@ def time_cycle(native, descs, steps, warmup, stream, plain=False):
     sp = ctypes.c_void_p(stream.cuda_stream)
     n = len(descs)
 
+    N.check(lib.psb_set_option(h, b"graph", 0 if plain else 1))
+
     def issue(k):
-        if not plain:
-            N.check(lib.psb_run_cycle(h, descs, n, k, sp))
-        else:  # fewer than two passes over the ring per call: psb_run_cycle issues plain launches
-            while k > 0:
-                c = min(k, n)
-                N.check(lib.psb_run_cycle(h, descs, n, c, sp))
-                k -= c
+        N.check(lib.psb_run_cycle(h, descs, n, k, sp))
 
     # the warm-up must also build (capture + instantiate) the CUDA graph, not the timed region
-    issue(warmup if plain else max(warmup, 2 * n))
+    issue(warmup if plain else max(warmup, n))
     stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.psb_launch_count(h)
@@ -215,6 +215,7 @@ def time_cycle(native, descs, steps, warmup, stream, plain=False):
         issue(steps)
         e1.record(stream)
     stream.synchronize()
+    N.check(lib.psb_set_option(h, b"graph", 1))
     return e0.elapsed_time(e1), lib.psb_launch_count(h) - l0
 
 
@@ -222,10 +223,11 @@ def time_e2e(native, frame, L, dt, steps, warmup, stream):
     """psb_step_host: pinned host snapshot -> H2D -> step -> D2H forces, per step."""
     from pysages_b200 import _native as N
 
-    host = {k: v.cpu().pin_memory() for k, v in frame.items()}
+    # the engine's own host arrays (numpy): psb_step_host page-locks them in place on first sight (cudaHostRegister)
+    host = {k: np.ascontiguousarray(v.cpu().numpy()).copy() for k, v in frame.items()}
     d = N.SnapshotDesc()
-    d.positions, d.vel_mass, d.forces = host["positions"].data_ptr(), host["vel_mass"].data_ptr(), host["forces"].data_ptr()
-    d.ids, d.images = host["rtags"].data_ptr(), host["images"].data_ptr()
+    d.positions, d.vel_mass, d.forces = host["positions"].ctypes.data, host["vel_mass"].ctypes.data, host["forces"].ctypes.data
+    d.ids, d.images = host["rtags"].ctypes.data, host["images"].ctypes.data
     for i in range(3):
         d.box_diag[i] = L
     d.dt = dt
@@ -240,7 +242,55 @@ def time_e2e(native, frame, L, dt, steps, warmup, stream):
     e1.record(stream)
     stream.synchronize()
     ms = e0.elapsed_time(e1)
+    N.check(native.lib.psb_host_release(native.handle))  # the host arrays go away with this function
     return steps / (ms * 1e-3), int(h2d.value), int(d2h.value)
+
+
+def time_api_hook(cv_specs, method_spec, natoms, steps, device, seed):
+    """The per-step Python hook as a HOOMD-style engine drives it (hoomd.py:159-173): five DLPack capsules per
+    step -> `Sampler.on_hoomd_half_step` -> ONE native call.  The engine side (creating the capsules) is not ours
+    and stays outside: the capsules of a 16-snapshot ring are made once and re-presented (the pointer-only hook
+    leaves them unconsumed).  Returns host time per hook call and the end-to-end rate (device work included)."""
+    import pysages_b200 as ps
+    from pysages_b200 import synthetic
+    from pysages_b200.backends import mock
+    from torch.utils.dlpack import to_dlpack
+
+    snap = synthetic.make_snapshot(natoms, layout="hoomd", dtype=np.float32, seed=seed)
+    eng = mock.MockEngine("hoomd", snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device=str(device))
+    cvs = [getattr(ps.colvars, n)(*a, **k) for (n, a, k) in cv_specs]
+    name, kw = method_spec
+    kw = dict(kw)
+    lower, upper, shape, kind = kw.pop("grid")
+    kw["restraints"] = ps.CVRestraints(*kw["restraints"])
+    method = ps.methods.ABF(cvs, ps.Grid[ps.Regular](lower, upper, shape), **kw)
+    sampler = mock.Sampler(eng, method)
+    ring = []
+    for i in range(16):  # an engine's buffers move (HOOMD double-buffers): every ring entry has its own arrays
+        t = {k: (v.clone() if k in ("positions", "vel_mass") else v) for k, v in eng.t.items()}
+        ring.append((t, tuple(to_dlpack(t[k]) for k in ("positions", "vel_mass", "rtags", "images", "forces"))))
+    hook = sampler.on_hoomd_half_step
+    for i in range(64):
+        hook(*ring[i % 16][1], i)
+    # host cost of one hook call: bursts of 256 calls into an empty launch queue (a longer loop would fill the
+    # queue and measure the device's step time instead), best of 8 bursts
+    host_us = 1e30
+    for rep in range(8):
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for i in range(256):
+            hook(*ring[i % 16][1], i)
+        host_us = min(host_us, (time.perf_counter() - t0) * 1e6 / 256)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        hook(*ring[i % 16][1], i)
+    torch.cuda.synchronize(device)
+    t2 = time.perf_counter()
+    _ = sampler.state  # built on demand
+    return dict(host_us_per_hook=round(host_us, 3), us_per_step_incl_device=round((t2 - t0) * 1e6 / steps, 3),
+                steps=steps, path="MockEngine(hoomd) capsules -> mock.Sampler.on_hoomd_half_step (SamplerCore.advance_pointers) -> psb_step",
+                budget_us="5-10 (5 % of a 0.1-0.2 ms MD step at 1e5 atoms, SURVEY.md 8d)")
 
 
 class ClockSampler:
@@ -390,48 +440,52 @@ def run_walkers(device, stream, rank, world, dist, natoms=100_000, total_steps=3
                 us_per_step=round(float(t.item()) * 1e3 / total_steps, 3))
 
 
-def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, steps=2000):
-    """cfg5: UmbrellaIntegration windows partitioned round-robin over the ranks (replicas only)."""
+def run_windows(device, stream, rank, world, dist, nwindows=32, natoms=100_000, steps=2000, per_gpu=False):
+    """cfg5: UmbrellaIntegration windows partitioned round-robin over the ranks (replicas only, no collective); the
+    windows of one rank step in lockstep, ONE cooperative launch per MD step for all of them (psb_batch_run_cycle).
+    per_gpu=True: `nwindows` windows on EVERY rank (weak scaling) instead of `nwindows` in total."""
     from pysages_b200 import parallel
 
-    mine = parallel.partition_windows(nwindows, world, rank)
-    natives, all_descs, keep = [], [], []
+    total = nwindows * world if per_gpu else nwindows
+    mine = parallel.partition_windows(total, world, rank)
+    natives, keep = [], []
     for w in mine:  # every window is its own simulation: own engine arrays, own handle
         frames, L, _ = device_hoomd_frames(natoms, 4, device, seed=20240 + 5500 + w)
         snaps = snapshots_of(frames, L, 0.005)
         cvs, m = workload_specs("window", natoms, L)
-        mm = (m[0], dict(m[1], center=[-L / 4 + (L / 2) * w / max(nwindows - 1, 1)]))
-        natives.append(build_ours(cvs, mm, snaps[0]))
-        all_descs.append(snapdesc_array(natives[-1][1], snaps))
+        mm = (m[0], dict(m[1], center=[-L / 4 + (L / 2) * w / max(total - 1, 1)]))
+        natives.append(build_ours(cvs, mm, snaps[0])[1])
         keep.append((frames, snaps))
-    from pysages_b200 import _native as N
-
-    # one CUDA stream per window: the windows are independent simulations whose small step kernels
-    # (a few CTAs each) run concurrently on the one GPU (SURVEY.md 8e)
-    streams = [torch.cuda.Stream(device=device) for _ in natives]
-    for (_, nat), descs, st in zip(natives, all_descs, streams):
-        time_cycle(nat, descs, 20, 5, st)
+    ms = 0.0
+    if natives:
+        batch = parallel.WindowBatch(natives)
+        ring = batch.ring([[keep[i][1][r] for i in range(len(natives))] for r in range(4)])
+        with torch.cuda.stream(stream):
+            batch.run_cycle(ring, 4, 40)  # warm-up: descriptor upload, graph capture
     torch.cuda.synchronize(device)
     if dist is not None:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for st in streams:
-        st.wait_stream(stream)
-    for (_, nat), descs, st in zip(natives, all_descs, streams):
-        N.check(nat.lib.psb_run_cycle(nat.handle, descs, len(descs), steps, ctypes.c_void_p(st.cuda_stream)))
-    for st in streams:
-        stream.wait_stream(st)
-    e1.record(stream)
-    stream.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if natives:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            batch.run_cycle(ring, 4, steps)
+            e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    means = parallel.gather_window_means({w: nat.view("xi").cpu().numpy().ravel()[:1] for w, (_, nat) in zip(mine, natives)}, nwindows)
-    return dict(workload=f"cfg5 umbrella: {nwindows} HarmonicBias windows (Component CV over 1000 atoms, N={natoms}) "
-                         f"round-robin over {world} GPU(s), one CUDA stream per window, {steps} steps each",
-                windows=nwindows, steps_per_s=round(nwindows * steps / (float(t.item()) * 1e-3), 1),
-                windows_gathered=int(means.shape[0]))
+    means = parallel.gather_window_means({w: nat.view("xi").cpu().numpy().ravel()[:1] for w, nat in zip(mine, natives)}, total)
+    return dict(workload=f"cfg5 umbrella: {total} HarmonicBias windows (Component CV over 1000 atoms, N={natoms}) "
+                         f"round-robin over {world} GPU(s), the {len(mine)} windows of a GPU in one launch per step, {steps} steps each",
+                windows=total, windows_per_gpu=len(mine), scaling="weak" if per_gpu else "strong",
+                steps_per_s=round(total * steps / (float(t.item()) * 1e-3), 1),
+                us_per_batched_step=round(float(t.item()) * 1e3 / steps, 3), launches_per_step=1,
+                windows_gathered=int(means.shape[0]),
+                note="one batched step is one latency-bound launch whatever the number of windows in it (4 or 32): with "
+                     "32 windows in total one GPU already runs them all at once, so adding GPUs cannot add throughput "
+                     "(strong row); the weak row keeps 32 windows per GPU")
 
 
 def cfg4_case(device, natoms=50_000, H=100_000):
@@ -462,7 +516,7 @@ def cfg4_case(device, natoms=50_000, H=100_000):
     return frames, L, cvs4, md, prefill
 
 
-def run_series(device, stream, hbm):
+def run_series(device, stream, hbm, fp64_peak=None):
     """Secondary sizes / configurations (parity-tested elsewhere); short runs, same timing method."""
     out = []
 
@@ -572,7 +626,12 @@ def run_series(device, stream, hbm):
     row = measure("cfg3 CoordinationNumber 10k x 10k (1e8 pairs), HarmonicBias, N=1e6 hoomd-f32", None, natoms, 100, frames, L,
                   specs=([("CoordinationNumber", ([ga, gb],), dict(r0=1.0))], ("HarmonicBias", dict(kspring=10.0, center=[100.0]))))
     row["pair_gflops"] = round(32 * 1e8 / (row["us_per_step"] * 1e-6) / 1e9, 1)  # 32 flop/pair canonical count
-    row["note"] = "FP64-pipe bound pair kernel + gather + step kernel; frac_of_hbm is not the relevant roofline here"
+    if fp64_peak:
+        row["fp64_peak_gflops_measured"] = round(2 * fp64_peak / 1e9, 1)  # psb_fma_peak: DFMA/s x 2
+        row["pair_frac_of_fp64_peak"] = round(row["pair_gflops"] * 1e9 / (2 * fp64_peak), 4)
+    row["note"] = ("FP64-pipe bound pair kernel + gather + step kernel; frac_of_hbm is not the relevant roofline here. "
+                   "pair_frac_of_fp64_peak uses the canonical 32 flop / pair over the whole step and the DFMA rate "
+                   "measured on this device (psb_fma_peak)")
     del frames
 
     # cfg4: RMSD + RadiusOfGyration over a 50k-atom globule, metadynamics with 1e5 pre-filled hills
@@ -638,16 +697,32 @@ def main():
         from pysages_b200 import synthetic
 
         snap_host = synthetic.make_snapshot(natoms, layout="hoomd", dtype=np.float32, seed=20240 + 2000)
-        # warm-up measures the step cost; the timed region is capped to ~120 s of CPU work
-        rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=5.0, warmup=max(1, min(args.warmup, 3)))
-        k_eff = int(max(1, min(args.steps, rate * 120.0)))
-        rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=1e9, max_steps=k_eff, warmup=0)
-        sample = (f"{n} full bias steps of the same workload on one host snapshot (dense (k,3N) autodiff Jacobian, "
-                  f"torch-fp64 CPU, {cores} threads); reference needs JAX, not installable here -> oracle port")
+        # the reference itself (PySAGES on JAX-CPU through the SURVEY 8c recipe) wherever jax + plum import:
+        # baseline/_ref/ or /root/reference; otherwise the restatement in oracle/ (this image has neither wheel)
+        from oracle import ref_jax
+
+        kind, why = "port", ref_jax.reason()
+        cores = os.cpu_count() or 1
+        if ref_jax.available():
+            os.environ.setdefault("JAX_PLATFORMS", "cpu")
+            live = ref_jax.LiveRun(snap_host, cv_specs, method_spec)
+            rate = live.steps_per_second(3, warmup=max(1, min(args.warmup, 3)))  # JIT warm-up + a first estimate
+            n = int(max(1, min(args.steps, rate * 120.0)))
+            rate = live.steps_per_second(n, warmup=0)
+            kind = "reference-jax"
+            sample = (f"{n} full bias steps of the same workload on one host snapshot by PySAGES itself "
+                      f"({why}; JAX-CPU, x64, XLA's own thread pool on {cores} cores)")
+        else:
+            # warm-up measures the step cost; the timed region is capped to ~120 s of CPU work
+            rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=5.0, warmup=max(1, min(args.warmup, 3)))
+            k_eff = int(max(1, min(args.steps, rate * 120.0)))
+            rate, n, cores = cpu_oracle_steps_per_s(snap_host, cv_specs, method_spec, budget_s=1e9, max_steps=k_eff, warmup=0)
+            sample = (f"{n} full bias steps of the same workload on one host snapshot (dense (k,3N) autodiff Jacobian, "
+                      f"torch-fp64 CPU, {cores} threads); live reference probe: {why} -> restatement in oracle/")
         line = dict(impl="reference", metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=n,
                     warmup=args.warmup, ms_per_step=1e3 / rate, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f64", data="synthetic", config=config,
-                    cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample),
+                    cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind=kind, sample=sample),
                     e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -663,7 +738,12 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     stream = torch.cuda.Stream(device=device)
 
-    frames, L, _ = device_hoomd_frames(natoms, NFRAMES, device, seed=20240 + 2000 + rank)
+    # ring of distinct snapshots: 64, or as many as there are timed steps (the driver's 20-step run: 20 snapshots =
+    # 128 MB, still more than the 126 MB L2) so that even a short run replays a captured graph of one ring pass
+    nring = max(1, min(NFRAMES, args.steps))
+    config["l2"] = (f"inputs cycle over {nring} distinct snapshots ({nring * 64 * natoms / 1e6:.0f} MB) "
+                    f"{'>' if nring * 64 * natoms > 126e6 else '<= (!)'} 126 MB L2")
+    frames, L, _ = device_hoomd_frames(natoms, nring, device, seed=20240 + 2000 + rank)
     snaps = snapshots_of(frames, L, dt)
     method, native = build_ours(cv_specs, method_spec, snaps[0])
     descs = snapdesc_array(native, snaps)
@@ -686,22 +766,28 @@ def main():
             time_cycle(native, descs, 4000, 0, stream)
         barrier()
     info = native.launch_info()
+    graph_used = bool(info["cuda_graph"])
     # what an engine that interleaves its own kernels sees: one plain launch per step, no overlap between steps
     native.set_option("pdl", 0)
-    ms_plain, _ = time_cycle(native, descs, min(args.steps, 2000), 3, stream, plain=True)
+    plain_steps = max(args.steps, min(2000, 20 * args.steps))
+    ms_plain, _ = time_cycle(native, descs, plain_steps, 3, stream, plain=True)
     native.set_option("pdl", 1)
-    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    t = torch.tensor([ms, ms_plain / plain_steps], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = float(t[0].item())
     value = world * args.steps / (ms * 1e-3)
-    info["plain_launch_us_per_step"] = round(ms_plain * 1e3 / min(args.steps, 2000), 3)
-    info["pipelining"] = ("value: CUDA-graph replay + programmatic dependent launch (a step's gather of positions / "
-                          "velocities overlaps the previous step's finalizer and scatter; forces and method state only after "
-                          "it completed); plain_launch_us_per_step: one launch per step, no overlap")
+    value_plain = world / (float(t[1].item()) * 1e-3)
+    info["plain_launch_us_per_step"] = round(float(t[1].item()) * 1e3, 3)
+    info["pipelined_us_per_step"] = round(ms * 1e3 / args.steps, 3)
+    info["cuda_graph_in_timed_region"] = graph_used
+    info["pipelining"] = ("value = value_pipelined: CUDA-graph replay + programmatic dependent launch (a step's gather of "
+                          "positions / velocities overlaps the previous step's finalizer and scatter; forces and method state "
+                          "only after it completed); value_plain: one launch per step, no overlap -- what the hook of an "
+                          "engine that interleaves its own kernels gets")
 
     # e2e through the host-buffer C-ABI entry point
-    e2e_steps = max(20, min(args.steps, 300))
+    e2e_steps = 300  # always 300 synchronous steps (~60 ms): a 20-step driver run would be dominated by noise
     if args.no_e2e:
         e2e_rate, h2d, d2h = 0.0, 0, 0
     else:
@@ -715,7 +801,8 @@ def main():
     multi = None
     if not args.no_multi:
         multi = dict(walkers=run_walkers(device, stream, rank, world, dist),
-                     umbrella=run_windows(device, stream, rank, world, dist))
+                     umbrella=run_windows(device, stream, rank, world, dist),
+                     umbrella_weak=run_windows(device, stream, rank, world, dist, per_gpu=True))
 
     if rank != 0:
         if dist is not None:
@@ -740,6 +827,16 @@ def main():
     if not args.profile:
         info["floor_us"] = dict(empty_cooperative_launch=floor(0), empty_launch_with_one_grid_barrier=floor(1))
 
+    api = None
+    fp64_peak = None
+    if not args.profile:
+        api = time_api_hook(cv_specs, method_spec, natoms, 3000, device, seed=20240 + 2000)
+        out5 = (ctypes.c_double * 5)()
+        N.check(native.lib.psb_fma_peak(out5))
+        fp64_peak = float(out5[0])
+        info["arithmetic_peaks_measured"] = dict(dfma_per_s=out5[0], ffma_per_s=out5[1], f2f_f32_f64_pairs_per_s=out5[2],
+                                                 i2f_f64_pairs_per_s=out5[3], dadd_per_s=out5[4],
+                                                 fp64_tflops=round(2 * out5[0] / 1e12, 2), fp32_tflops=round(2 * out5[1] / 1e12, 2))
     hbm, peak_src = peaks()
     us = ms * 1e3 / args.steps
     achieved = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
@@ -748,8 +845,10 @@ def main():
                     kernel="psb::step_kernel<HOOMD,float,ABF,point> (1 cooperative launch per step, CUDA-graph replay)",
                     algorithmic_bytes_per_launch=info["algorithmic_bytes_per_step"], peak_source=peak_src,
                     note="latency-bound at S=1e5: 8.4 MB/step is 1.3 us of HBM time inside a ~9 us dependent chain "
-                         "(gather -> flag-in-data exchange -> single-warp finalizer -> scatter), see launch.floor_us and DESIGN.md 4.1; "
-                         "the S=N=1e6 rows of `series` are the bandwidth regime")
+                         "(gather -> flag-in-data exchange -> single-warp finalizer -> scatter); one step per launch cannot "
+                         "reach 0.5 of HBM at this size -- judge it against launch.floor_us (empty cooperative launch + one "
+                         "grid barrier), see DESIGN.md 4.1; the S=N=1e6 rows of `series` are the bandwidth regime",
+                    frac_plain=round(info["algorithmic_bytes_per_step"] / (info["plain_launch_us_per_step"] * 1e-6) / 1e9 / hbm, 4))
 
     cpu = None
     if not args.no_cpu and world == 1:  # reported at N = 1 only (torchrun workers run with OMP_NUM_THREADS=1)
@@ -758,13 +857,16 @@ def main():
         cpu = dict(value=round(rate, 3), unit=UNIT, cores=cores, kind="port",
                    sample=f"{n} bias steps of the same workload on one snapshot (oracle: torch-fp64 autodiff, dense J)")
 
-    series = [] if (args.no_series or world > 1) else run_series(device, stream, hbm)
+    series = [] if (args.no_series or world > 1) else run_series(device, stream, hbm, fp64_peak)
 
-    line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+    line = dict(metric=METRIC, value=round(value, 1), value_pipelined=round(value, 1), value_plain=round(value_plain, 1),
+                unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", config=config, clocks=clocks.summary(),
                 e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         steps=e2e_steps, path="psb_step_host (pinned host snapshot -> H2D -> step -> D2H forces)"),
+                         steps=e2e_steps, gbs_effective=round((h2d + d2h) * e2e_value / max(world, 1) / 1e9, 2),
+                         path="psb_step_host (the engine's host arrays, page-locked in place by the library -> H2D -> step -> D2H forces -> sync)"),
+                api_us_per_step=api,
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, launch=info, series=series,
                 multi_gpu=multi)
     print(json.dumps(line))

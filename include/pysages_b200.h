@@ -206,8 +206,9 @@ psb_status psb_step(psb_handle* h, const psb_snapshot* snap, int64_t timestep, v
  * evaluates xi on `snap` without touching forces, state counters or histograms. */
 psb_status psb_evaluate_cvs(psb_handle* h, const psb_snapshot* snap, void* cuda_stream);
 
-/* Engine-loop emulation for benchmarks: psb_step on snaps[i % nsnaps] for nsteps steps.  One pass
- * over the ring is captured as a CUDA graph and replayed (PSB_NO_GRAPH=1: plain launches). */
+/* Engine-loop emulation for benchmarks: psb_step on snaps[i % nsnaps] for nsteps steps.  Whenever
+ * nsteps >= nsnaps one pass over the ring is captured as a CUDA graph (once per distinct ring) and replayed;
+ * the remainder, and shorter calls, are plain launches (PSB_NO_GRAPH=1: always plain launches). */
 psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnaps, int64_t nsteps,
                          void* cuda_stream);
 
@@ -215,6 +216,11 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
  * the arrays the method needs to the device, steps, copies forces back, and synchronises. */
 psb_status psb_step_host(psb_handle* h, const psb_snapshot* host_snap, int64_t timestep,
                          void* cuda_stream, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* psb_step_host page-locks the engine's host arrays in place the first time it sees them (cudaHostRegister: a
+ * pageable array crosses PCIe at a third of the rate, 19.6 vs 53.7 GB/s measured) and keeps them registered until
+ * psb_destroy.  An engine that frees or reallocates its arrays earlier calls this first.  PSB_NO_HOST_REGISTER=1
+ * in the environment disables the registration altogether. */
+psb_status psb_host_release(psb_handle* h);
 /* psb_evaluate_cvs for HOST snapshot buffers (initial xi of an engine running on the CPU,
  * openmm.py:64-89 with the CPU / Reference platform); synchronises. */
 psb_status psb_evaluate_cvs_host(psb_handle* h, const psb_snapshot* host_snap, void* cuda_stream);
@@ -273,6 +279,8 @@ psb_status psb_grid_index(const psb_grid_desc* grid, const double* x_host, int64
  * engine arrays this library never writes (ids, positions, images, velocities) overlap the previous
  * step's finalizer / scatter; forces, method state and workspaces are touched only after the previous
  * kernel has completed.  A kernel that follows an engine kernel is never launched early. */
+/* "graph" (default 1): psb_run_cycle may capture and replay a CUDA graph; 0 = one plain launch per step.
+ * "slot_stamp_period" (tests): make the launch stamps of the slot-ordered class repeat after `value` launches. */
 psb_status psb_set_option(psb_handle* h, const char* name, int64_t value);
 /* Continuous force model of the ABF family (row K of SURVEY.md 8a).  FUNN (methods/funn.py:187-210)
  * and CFF (methods/cff.py:223-244) run the ABF accumulation every step and, once

@@ -147,6 +147,7 @@ EXPORTS = {
     "psb_evaluate_cvs": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_void_p]),
     "psb_run_cycle": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_int32, c_int64, c_void_p]),
     "psb_step_host": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_int64, c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "psb_host_release": (c_int32, [c_void_p]),
     "psb_evaluate_cvs_host": (c_int32, [c_void_p, POINTER(SnapshotDesc), c_void_p]),
     "psb_batch_create": (c_int32, [POINTER(c_void_p), c_int32, POINTER(c_void_p)]),
     "psb_batch_destroy": (None, [c_void_p]),

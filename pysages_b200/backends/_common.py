@@ -91,6 +91,16 @@ def capsule_address(capsule):
     return (t.data or 0) + t.byte_offset, (t.shape[0] if t.ndim else 1), t.device.device_type
 
 
+_u64_at = ctypes.c_uint64.from_address
+_OFF_BYTE_OFFSET = _DLTensor.byte_offset.offset
+
+
+def capsule_data(capsule):
+    """Address of the first element only: the per-step path (two 8-byte reads, no struct object)."""
+    a = _get_pointer(capsule, b"dltensor")
+    return _u64_at(a).value + _u64_at(a + _OFF_BYTE_OFFSET).value
+
+
 class SamplerCore:
     """The engine-independent sampler (see the module docstring).  Engine adapters derive from it (or own
     one) and provide `_views()` -> Snapshot of zero-copy torch views of the engine's current buffers."""
@@ -146,9 +156,14 @@ class SamplerCore:
         if key != self._desc_key:
             fill(self._desc)
             self._desc_key = key
+        self.step_current(timestep)
+
+    def step_current(self, timestep):
+        """psb_step on the psb_snapshot as it stands, ordering, user callback."""
         self._native.step_desc(self._desc, timestep)
         self._state_stale = True
-        self.after_step()
+        if self.ordering == "host":
+            self.after_step()
         if self.callback:
             self.callback(self._views(), self.state, timestep)
 
@@ -163,5 +178,5 @@ class SamplerCore:
         return describe_snapshot(snapshot, self.layout, self._desc)
 
 
-__all__ = ["LAMMPS_CONVERSION", "LAYOUTS", "Snapshot", "SamplerCore", "capsule_address", "fused_helpers",
+__all__ = ["LAMMPS_CONVERSION", "LAYOUTS", "Snapshot", "SamplerCore", "capsule_address", "capsule_data", "fused_helpers",
            "tensor_from_capsule", "KDL_CPU", "KDL_CUDA"]

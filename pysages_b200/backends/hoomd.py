@@ -121,21 +121,22 @@ class Sampler(C.SamplerCore, *_BASES):
     def on_half_step(self, positions, vel_mass, rtags, images, forces, timestep):
         if not self._fused:
             return self.advance_snapshot(self._wrap(positions, vel_mass, rtags, images, forces), timestep)
-        (p, n, dev), (v, _, _), (r, _, _), (i, _, _), (f, _, _) = (
-            C.capsule_address(c) for c in (positions, vel_mass, rtags, images, forces))
-        if n != self._native.natoms or dev != C.KDL_CUDA:
-            raise RuntimeError(f"HOOMD now exposes {n} particles on device type {dev}; the method was built for "
-                               f"{self._native.natoms} on the GPU")
+        d = C.capsule_data
+        key = (d(positions), d(vel_mass), d(rtags), d(images), d(forces))
         self._last = (positions, vel_mass, rtags, images, forces)
-
-        def fill(d):
-            d.positions, d.vel_mass, d.ids, d.images, d.forces = p, v, r, i, f
-            H = self.update_box().H
-            d.box_diag[0], d.box_diag[1], d.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
-            d.dt = float(self.dt)
-
         try:
-            self.advance_pointers(timestep, (p, v, r, i, f), fill)
+            if key != self._desc_key:  # HOOMD moved a buffer (it double-buffers while sorting): check, then refill
+                _, n, dev = C.capsule_address(positions)
+                if n != self._native.natoms or dev != C.KDL_CUDA:
+                    raise RuntimeError(f"HOOMD now exposes {n} particles on device type {dev}; the method was built "
+                                       f"for {self._native.natoms} on the GPU")
+                ds = self._desc
+                ds.positions, ds.vel_mass, ds.ids, ds.images, ds.forces = key
+                H = self.update_box().H
+                ds.box_diag[0], ds.box_diag[1], ds.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
+                ds.dt = float(self.dt)
+                self._desc_key = key
+            self.step_current(timestep)
         finally:
             self._last = None  # HOOMD's capsules are only valid inside the half step (hoomd.py:164-166)
 

@@ -143,16 +143,16 @@ class Sampler(C.SamplerCore):
 
     def on_hoomd_half_step(self, positions, vel_mass, rtags, images, forces, timestep):
         """The hoomd.dlext callback signature (hoomd.py:159-168) on the pointer-only fast path."""
-        (p, _, _), (v, _, _), (r, _, _), (i, _, _), (f, _, _) = (
-            C.capsule_address(c) for c in (positions, vel_mass, rtags, images, forces))
-
-        def fill(d):
-            d.positions, d.vel_mass, d.ids, d.images, d.forces = p, v, r, i, f
+        d = C.capsule_data
+        key = (d(positions), d(vel_mass), d(rtags), d(images), d(forces))
+        if key != self._desc_key:
+            ds = self._desc
+            ds.positions, ds.vel_mass, ds.ids, ds.images, ds.forces = key
             H = self.box.H
-            d.box_diag[0], d.box_diag[1], d.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
-            d.dt = float(self.dt)
-
-        self.advance_pointers(timestep, (p, v, r, i, f), fill)
+            ds.box_diag[0], ds.box_diag[1], ds.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
+            ds.dt = float(self.dt)
+            self._desc_key = key
+        self.step_current(timestep)
 
     def _update_callback(self, timestep):
         caps = self.context.capsules()

@@ -124,6 +124,7 @@ struct psb_handle {
   size_t dyn_smem = 0;
   int cooperative = 0;
   int pdl = 1;           // programmatic dependent launch between consecutive step kernels (psb_set_option)
+  int use_graph = 1;     // psb_run_cycle may capture / replay a CUDA graph (psb_set_option "graph")
   int step_method = 0;   // StepMethod code of the kernel instantiation
   int step_general = 0;  // StepClass code of the kernel instantiation
   long long launches = 0;
@@ -936,7 +937,7 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
   // PSB_DEBUG_TIMING=graph keeps the graph: captured nodes alternate between the two stamp halves,
   // which stays consistent across replays when the ring has an even number of snapshots
   static const bool dbg_graph = getenv("PSB_DEBUG_TIMING") && std::string(getenv("PSB_DEBUG_TIMING")) == "graph";
-  if (!no_graph && (!h->dbg || (dbg_graph && nsnaps % 2 == 0)) && stream != nullptr && nsteps >= 2 * (int64_t)nsnaps) {
+  if (!no_graph && h->use_graph && (!h->dbg || (dbg_graph && nsnaps % 2 == 0)) && stream != nullptr && nsteps >= (int64_t)nsnaps) {
     const bool same = h->cycle_exec && h->cycle_stream == stream && (int)h->cycle_key.size() == nsnaps &&
                       memcmp(h->cycle_key.data(), snaps, sizeof(psb_snapshot) * nsnaps) == 0;
     if (!same) {
@@ -1356,6 +1357,15 @@ psb_status psb_step_host(psb_handle* h, const psb_snapshot* hs, int64_t timestep
   return PSB_OK;
 }
 
+psb_status psb_host_release(psb_handle* h) {
+  if (!h) return fail(PSB_ERR_VALUE, "NULL handle");
+  for (void* p : h->host_registered) cudaHostUnregister(p);
+  cudaGetLastError();
+  h->host_registered.clear();
+  h->host_ranges.clear();
+  return PSB_OK;
+}
+
 psb_status psb_evaluate_cvs_host(psb_handle* h, const psb_snapshot* hs, void* cuda_stream) {
   if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -1429,6 +1439,10 @@ psb_status psb_set_option(psb_handle* h, const char* name, int64_t value) {
     if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);  // captured launches carry the old attribute
     h->cycle_exec = nullptr;
     h->cycle_key.clear();
+    return PSB_OK;
+  }
+  if (n == "graph") {  // 0: psb_run_cycle issues one plain launch per step
+    h->use_graph = value ? 1 : 0;
     return PSB_OK;
   }
   if (n == "slot_stamp_period") {  // tests: make the slot_map launch stamps repeat after `value` launches

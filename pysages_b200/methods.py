@@ -150,6 +150,10 @@ class NativeStep:
                                         ctypes.byref(handle)))
         self.handle = handle
         self._snapdesc = N.SnapshotDesc()
+        self._psb_step = self.lib.psb_step
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # int handle of the current stream
+        self._device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._host_keep = {}
         self._views = {}
         self.ncalls = 0
 
@@ -157,15 +161,30 @@ class NativeStep:
         h, self.handle = getattr(self, "handle", None), None
         if h:
             try:
-                self.lib.psb_destroy(h)
+                self.lib.psb_destroy(h)  # also unregisters the host arrays; only then may they be freed
             except Exception:  # interpreter shutdown
                 pass
+        self._host_keep = {}
 
     # ---- stepping ------------------------------------------------------------------------
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _desc(self, snapshot):
+        if self.host_buffers:
+            # psb_step_host page-locks these arrays in place and leaves them registered until the handle dies: keep
+            # them alive that long (a freed-but-still-registered range would poison later allocations at its address)
+            def hold(x):
+                if isinstance(x, (tuple, list)):
+                    for y in x:
+                        hold(y)
+                elif isinstance(x, dict):
+                    for y in x.values():
+                        hold(y)
+                elif isinstance(x, torch.Tensor):
+                    self._host_keep.setdefault(x.data_ptr(), x)
+
+            hold((snapshot.positions, snapshot.vel_mass, snapshot.forces, snapshot.ids, snapshot.extras))
         return _snap.describe_snapshot(snapshot, self.layout, self._snapdesc)
 
     def evaluate(self, snapshot):
@@ -182,9 +201,19 @@ class NativeStep:
 
     def step_desc(self, desc, timestep=0):
         """psb_step on a psb_snapshot the caller keeps filled (engine adapters: device pointers read straight
-        out of the plugin's DLPack capsules, backends/_common.py)."""
-        N.check(self.lib.psb_step(self.handle, ctypes.byref(desc), int(timestep), self._stream()))
+        out of the plugin's DLPack capsules, backends/_common.py).  The per-step Python path: the raw stream handle
+        comes from torch's C accessor, nothing is allocated."""
+        if self._raw_stream is not None:
+            st = self._psb_step(self.handle, ctypes.byref(desc), timestep, self._raw_stream(self._device_index))
+        else:
+            st = self._psb_step(self.handle, ctypes.byref(desc), int(timestep), self._stream())
+        if st:
+            N.check(st)
         self.ncalls += 1
+
+    def release_host_buffers(self):
+        """The engine is about to free / reallocate the host arrays psb_step_host page-locked in place."""
+        N.check(self.lib.psb_host_release(self.handle))
 
     def next_step_deposits(self):
         return bool(self.lib.psb_next_step_deposits(self.handle))

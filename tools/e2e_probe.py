@@ -35,4 +35,5 @@ for kind in ("torch pin_memory()", "numpy (pageable) + library cudaHostRegister"
     e1.record(stream); stream.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / n
     print(f"{kind:48s} {us:7.1f} us/step  {1e6/us:7.0f} steps/s  {(h2d.value + d2h.value) / us / 1e3:5.1f} GB/s effective")
+    N.check(native.lib.psb_host_release(native.handle))
     del native, method
