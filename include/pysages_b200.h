@@ -30,10 +30,10 @@
 extern "C" {
 #endif
 
-#define PSB_MAX_CVS 4        /* collective variables per method            */
-#define PSB_MAX_K 4          /* total CV components (xi has shape (1, k))  */
-#define PSB_MAX_GROUPS 16    /* atom groups ("points") over all CVs        */
-#define PSB_MAX_GRID_DIMS 4
+#define PSB_MAX_CVS 8        /* collective variables per method (colvars/core.py:228-274 stacks any number) */
+#define PSB_MAX_K 8          /* total CV components (xi has shape (1, k))  */
+#define PSB_MAX_GROUPS 32    /* atom groups ("points") over all CVs: eight dihedrals */
+#define PSB_MAX_GRID_DIMS 4  /* gridded methods (ABF family, grid metadynamics): k = grid dimensions <= 4 */
 
 typedef struct psb_handle psb_handle;
 

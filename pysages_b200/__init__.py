@@ -9,7 +9,7 @@ from . import backends, colvars, grids, methods  # noqa: F401
 from .backends.core import supported_backends  # noqa: F401
 from .core import Result, analyze, run  # noqa: F401
 from .grids import Chebyshev, Grid, Periodic, Regular  # noqa: F401
-from .methods import CVRestraints  # noqa: F401
+from .methods import CVRestraints, freeze  # noqa: F401
 from .serialization import load, save  # noqa: F401
 from .utils import HistogramLogger, MetaDLogger, ReplicasConfiguration, SerialExecutor  # noqa: F401
 

@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int32, c_int64, c_uint32, c_void_p
 
-MAX_CVS, MAX_K, MAX_GROUPS, MAX_GRID_DIMS = 4, 4, 16, 4
+MAX_CVS, MAX_K, MAX_GROUPS, MAX_GRID_DIMS = 8, 8, 32, 4
 
 OK, ERR_VALUE, ERR_RUNTIME, ERR_KEY, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 

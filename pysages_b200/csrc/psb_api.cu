@@ -254,7 +254,7 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
   }
   if (eval_cvs) {
     for (const CoordWork& cw : h->coord) {
-      pick_vtable(h->layout)->launch_gather(&M, &S, cw.cv, cw.xa, cw.na_pad, cw.xb, cw.nb_pad, stream);
+      pick_vtable(h->layout)->launch_gather(h->d_model, &S, cw.cv, cw.xa, cw.na_pad, cw.xb, cw.nb_pad, stream);
       const CvDev& cv = M.cv[cw.cv];
       pair_launcher(cw.R, cw.H)(cw.nrt * cw.ncs, stream, cw.xa, cw.na_pad, cw.xb, cw.nb_pad, cw.nA, cw.nB,
                                 cw.nrt, 1.0 / (cv.r0 * cv.r0), cv.grad, cv.grad + 3 * (size_t)cw.nA,
@@ -265,7 +265,7 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
   }
   if (eval_cvs)
     for (int c : h->ermsd) {
-      pick_vtable(h->layout)->launch_ermsd(&M, &S, c, stream);
+      pick_vtable(h->layout)->launch_ermsd(h->d_model, &S, c, stream);
       ++h->launches;
       helper_before = true;
     }
@@ -414,6 +414,8 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     return bail(fail(PSB_ERR_VALUE, "unknown method kind %d", method->kind));
   if (method->kind == PSB_METHOD_ABF && !gridded) return bail(fail(PSB_ERR_VALUE, "ABF requires a grid"));
   if (gridded && (method->kind == PSB_METHOD_ABF || method->kind == PSB_METHOD_METAD)) {
+    if (gd.ndim < 1 || gd.ndim > PSB_MAX_GRID_DIMS)
+      return bail(fail(PSB_ERR_VALUE, "grids have between 1 and %d dimensions (got %d)", PSB_MAX_GRID_DIMS, gd.ndim));
     if (gd.ndim != k)  // methods/core.py:435-438
       return bail(fail(PSB_ERR_VALUE, "Grid and Collective Variable dimensions must match."));
     m.grid_kind = gd.kind;
@@ -464,6 +466,8 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   M.fm_mode = m.hist_only ? FM_HIST_ONLY : 0;
 
   // ---- unique atoms (CSR) and group overlaps ---------------------------------------------------
+  std::vector<uint32_t> ov((size_t)MAXG * MAXG, 0u);  // group overlap counts
+  auto OV = [&](int a, int b2) -> uint32_t& { return ov[(size_t)a * MAXG + b2]; };
   {
     std::vector<std::pair<uint32_t, uint32_t>> order(M.T);
     for (uint32_t t = 0; t < M.T; ++t) order[t] = {term_tag[t], t};
@@ -480,19 +484,24 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         uterm[a] = order[a].second;
         ugrp[a] = term_group[order[a].second];
         for (uint32_t b2 = i; b2 < j; ++b2)
-          M.ov[term_group[order[a].second]][term_group[order[b2].second]] += 1u;
+          OV(term_group[order[a].second], term_group[order[b2].second]) += 1u;
       }
       i = j;
     }
     uptr.push_back(M.T);
     for (int g = 0; g < ng; ++g) {
-      M.grp[g].self_coef = (double)M.ov[g][g] * M.grp[g].inv_n * M.grp[g].inv_n;
+      M.grp[g].self_coef = (double)OV(g, g) * M.grp[g].inv_n * M.grp[g].inv_n;
       for (int g2 = 0; g2 < ng; ++g2)
-        if (g2 != g && M.ov[g][g2]) M.cross_overlap = 1;
+        if (g2 != g && OV(g, g2)) M.cross_overlap = 1;
     }
     M.Su = (uint32_t)uptr.size() - 1;
     M.all_unique = (M.Su == M.T) ? 1 : 0;
     psb_status st;
+    if (M.cross_overlap) {
+      uint32_t* p = nullptr;
+      if ((st = dev_upload(h, &p, ov)) != PSB_OK) return bail(st);
+      M.ov = p;
+    }
     if (!M.all_unique) {
       uint32_t* p = nullptr;
       if ((st = dev_upload(h, &p, uptr)) != PSB_OK) return bail(st);
@@ -839,7 +848,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     }
     for (int g = 0; g < ng && constant; ++g)
       for (int g2 = 0; g2 < ng; ++g2)
-        if (M.grp[g].cv != M.grp[g2].cv && M.ov[g][g2]) constant = false;  // atoms shared between CVs
+        if (M.grp[g].cv != M.grp[g2].cv && OV(g, g2)) constant = false;  // atoms shared between CVs
     if (constant) {
       double A[16] = {0};
       for (int c = 0; c < ncvs; ++c) {
@@ -847,7 +856,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         double d = M.grp[cv.g0].self_coef;
         if (cv.ngroups == 2) {  // gradients of the two centroids are opposite unit vectors / +-identity
           const int g1 = cv.g0, g2 = cv.g0 + 1;
-          d += M.grp[g2].self_coef - 2.0 * (double)M.ov[g1][g2] * M.grp[g1].inv_n * M.grp[g2].inv_n;
+          d += M.grp[g2].self_coef - 2.0 * (double)OV(g1, g2) * M.grp[g1].inv_n * M.grp[g2].inv_n;
         }
         for (int j = 0; j < cv.ncomp; ++j) A[(cv.comp0 + j) * 4 + cv.comp0 + j] = d;
       }

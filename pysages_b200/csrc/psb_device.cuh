@@ -10,6 +10,7 @@
 namespace psb {
 
 constexpr int MAXK = PSB_MAX_K;
+constexpr int KA = PSB_MAX_GRID_DIMS;  // ABF family: k = grid dimensions; J J^T and its solve live in KA x KA storage
 constexpr int MAXG = PSB_MAX_GROUPS;
 constexpr int MAXCV = PSB_MAX_CVS;
 constexpr int NACC = 16;           // fp64 accumulators per group and pass
@@ -131,7 +132,7 @@ struct Fin {
   double gpt[MAXG][3][3];   // dxi_{comp0+j}/dpoint_g
   double cvx[MAXCV][20];    // RMSD: U[0..8], rbar[9..11], sumD[12..14], coef[15]; RoG: coef[0]
   double hill[MAXK + 2];    // candidate / deposited hill: centre[k], height, valid
-  double JJt[16];           // ABF: J J^T (leading dimension 4)
+  double JJt[KA * KA];      // ABF: J J^T (leading dimension KA)
   double Jp[MAXK];          // ABF: J p
   double Wp[MAXK];          // ABF: solve(J J^T, J p)
   double Fsum_new[MAXK];    // ABF: Fsum[I] after this step's scatter-add
@@ -188,7 +189,7 @@ struct Model {
   uint32_t stamp_period;      // tests: clear slot_map every `stamp_period` launches as if the 28-bit stamp had wrapped (0: off)
   uint32_t* slot_map;         // (N) slot -> (launch stamp << 4 | group + 1), rewritten every launch
   int32_t row_first[2][MAXG + 1];  // prefix of accumulator rows per group, pass A / pass B
-  uint32_t ov[MAXG][MAXG];    // group overlap counts (ABF fast path)
+  const uint32_t* ov;         // (MAXG, MAXG) group overlap counts, device memory (ABF with atoms shared between groups)
   const uint32_t* term_tag;   // (T)
   const uint8_t* term_group;  // (T)
   uint32_t* term_slot;        // (T) workspace: slot of each term, written in pass A
@@ -208,7 +209,7 @@ struct Model {
   unsigned long long* epochs; // (NBARS) completed uses of each barrier
   int32_t cross_overlap;      // some atom belongs to two different groups
   int32_t jjt_const;          // ABF: J J^T does not depend on positions; jjt_inv holds its inverse
-  double jjt_inv[MAXK * MAXK];  // (leading dimension 4)
+  double jjt_inv[KA * KA];    // (leading dimension KA)
   const ForceNet* nn;         // ABF family: force network or nullptr (psb_set_force_net)
   int32_t nn_np;              // its parameter count when it fits the shared-memory staging area (NN_STAGE), else 0
   int32_t fs_staged;          // the force series block fits the staging area

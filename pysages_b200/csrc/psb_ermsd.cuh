@@ -104,8 +104,9 @@ __device__ __forceinline__ V3 ermsd_g_adjoint(const ErmsdFrame& Fj, V3 p, V3 rt,
 
 template <int LAYOUT, typename Real>
 __global__ void __launch_bounds__(ERMSD_BLOCK)
-ermsd_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S, int c) {
+ermsd_kernel(const Model* __restrict__ Mdev, const __grid_constant__ Snap S, int c) {
   using A = Access<LAYOUT, Real>;
+  const Model& M = *Mdev;  // the handle's device copy (a by-value parameter would exceed 4 KB)
   __shared__ double P[3 * ERMSD_MAX_N][3];
   __shared__ ErmsdFrame F[ERMSD_MAX_N];
   __shared__ double red[ERMSD_BLOCK / 32];

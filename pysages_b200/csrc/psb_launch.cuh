@@ -122,11 +122,11 @@ const void* stream_entry() {
   static void NAME##_gather(const Model* M, const Snap* S, int cv, double* xa, int na_pad,          \
                             double* xb, int nb_pad, cudaStream_t stream) {                          \
     const int total = na_pad + nb_pad;                                                              \
-    coord_gather_kernel<L, R><<<(total + 255) / 256, 256, 0, stream>>>(*M, *S, cv, xa, na_pad, xb,  \
+    coord_gather_kernel<L, R><<<(total + 255) / 256, 256, 0, stream>>>(M, *S, cv, xa, na_pad, xb,   \
                                                                        nb_pad);                     \
   }                                                                                                 \
   static void NAME##_ermsd(const Model* M, const Snap* S, int cv, cudaStream_t stream) {           \
-    ermsd_kernel<L, R><<<1, ERMSD_BLOCK, 0, stream>>>(*M, *S, cv);                                  \
+    ermsd_kernel<L, R><<<1, ERMSD_BLOCK, 0, stream>>>(M, *S, cv);                                   \
   }                                                                                                 \
   const StepVTable NAME = {NAME##_launch, NAME##_occupancy, NAME##_static_smem, NAME##_launch_batch,   \
                            NAME##_batch_occupancy, NAME##_gather, NAME##_ermsd};

@@ -31,10 +31,11 @@ __device__ __forceinline__ double rcp_fast(double d) {
 // Gather + unwrap the positions of one coordination CV into SoA fp64 arrays (padded to 32) and
 // clear its gradient workspace.  xa: [3][na_pad], xb: [3][nb_pad].
 template <int LAYOUT, typename Real>
-__global__ void coord_gather_kernel(const __grid_constant__ Model M, const __grid_constant__ Snap S,
+__global__ void coord_gather_kernel(const Model* __restrict__ Mdev, const __grid_constant__ Snap S,
                                     int c, double* __restrict__ xa, int na_pad,
                                     double* __restrict__ xb, int nb_pad) {
   using A = Access<LAYOUT, Real>;
+  const Model& M = *Mdev;  // the handle's device copy (a by-value parameter would exceed 4 KB)
   const CvDev& cv = M.cv[c];
   const GroupDev& GA = M.grp[cv.g0];
   const GroupDev& GB = M.grp[cv.g0 + 1];

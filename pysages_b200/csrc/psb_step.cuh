@@ -674,7 +674,7 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
   const int k = M.k;
   __syncwarp();
   if (lane == 0 && !have_Wp) {  // utils/core.py:120-136
-    double Wp[MAXK] = {0, 0, 0, 0};
+    double Wp[MAXK] = {};
     if (m.use_pinv) {
       pinv_sym_solve(k, f.JJt, f.Jp, Wp, 10.0 * (double)(3 * M.natoms) * 2.220446049250313e-16);
     } else if (!spd_solve(k, f.JJt, f.Jp, Wp)) {
@@ -737,11 +737,12 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
 }
 
 // Value/gradient of one Gaussian at xi (utils/core.py:113-117, metad.py:318-323)
+template <int KM = MAXK>  // KM: compile-time bound of k (the direct hill sum picks 2 / 4 / MAXK outside its loop)
 __device__ __forceinline__ double hill_eval(const MethodDev& m, int k, const double* xi,
                                             const double* centre, double height, double* dV) {
-  double d[MAXK], q = 0.0;
+  double d[KM], q = 0.0;
 #pragma unroll
-  for (int c = 0; c < MAXK; ++c)
+  for (int c = 0; c < KM; ++c)
     if (c < k) {
       d[c] = wrap_period(xi[c] - centre[c], m.periods[c]);
       const double z = d[c] / m.sigma[c];
@@ -749,7 +750,7 @@ __device__ __forceinline__ double hill_eval(const MethodDev& m, int k, const dou
     }
   const double e = height * exp(-q / 2.0);
 #pragma unroll
-  for (int c = 0; c < MAXK; ++c)
+  for (int c = 0; c < KM; ++c)
     if (c < k) dV[c] += -e * d[c] / (m.sigma[c] * m.sigma[c]);
   return e;
 }
@@ -837,14 +838,16 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
         __syncwarp();
         if (lane < MAXK) {
           double w = 0.0;
-          for (int bq = 0; bq < k; ++bq) w += M.jjt_inv[lane * MAXK + bq] * f.Jp[bq];
-          f.Wp[lane] = lane < k ? w : 0.0;
+          if (lane < k)
+            for (int bq = 0; bq < k; ++bq) w += M.jjt_inv[lane * KA + bq] * f.Jp[bq];
+          f.Wp[lane] = w;
         }
         PSB_CLK(11);
         abf_finish(M, S, sh, lane, cta0, !GENERAL, true);
         break;
       }
       // lanes 0..15: entry (a, b) of J J^T; lanes 16..19: entry a of J p.
+      static_assert(KA == 4 && 16 + MAXK <= 32, "lanes 0..15: J J^T entries, lanes 16..16+MAXK-1: J p");
       if (lane < 16) {
         const int a = lane >> 2, bq = lane & 3;
         double s = 0.0;
@@ -866,10 +869,11 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
             for (int g = ca.g0; g < ca.g0 + ca.ngroups; ++g)
 #pragma unroll 1
               for (int h = cb.g0; h < cb.g0 + cb.ngroups; ++h) {
-                if (g == h || M.ov[g][h] == 0) continue;
+                const uint32_t ovgh = (g == h) ? 0u : __ldg(M.ov + g * MAXG + h);
+                if (ovgh == 0) continue;
                 const double* ga = f.gpt[g][ja];
                 const double* gb = f.gpt[h][jb];
-                s += (double)M.ov[g][h] * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * M.grp[g].inv_n *
+                s += (double)ovgh * (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * M.grp[g].inv_n *
                      M.grp[h].inv_n;
               }
           }
@@ -1821,9 +1825,9 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
 #pragma unroll
     for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
     for (uint32_t u = u0 + tid; u < u1; u += BLOCK) {
-      V3 G[MAXK];
+      V3 G[KA];
 #pragma unroll
-      for (int c = 0; c < MAXK; ++c) G[c] = v3(0, 0, 0);
+      for (int c = 0; c < KA; ++c) G[c] = v3(0, 0, 0);
       uint32_t e0, e1, slot;
       unique_atom<A>(M, S, all_unique, u, e0, e1, slot);
       const V3 r = M.all_point ? v3(0, 0, 0) : A::position(S, slot);
@@ -1835,18 +1839,18 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
         const int comp0 = M.cv[M.grp[g].cv].comp0;
         for (int j = 0; j < nc; ++j) {
 #pragma unroll
-          for (int c = 0; c < MAXK; ++c)
+          for (int c = 0; c < KA; ++c)
             if (c == comp0 + j) G[c] = G[c] + gv[j];
         }
       }
       const V3 p = A::momentum(S, slot);
       int o = 0;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
+      for (int a = 0; a < KA; ++a)
 #pragma unroll
-        for (int c = a; c < MAXK; ++c) acc[o++] += dot(G[a], G[c]);  // 10 entries
+        for (int c = a; c < KA; ++c) acc[o++] += dot(G[a], G[c]);  // 10 entries
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a) acc[10 + a] += dot(G[a], p);
+      for (int a = 0; a < KA; ++a) acc[10 + a] += dot(G[a], p);
     }
     if (nb == 1) block_reduce_store(sh, acc, 14, &sh.tot[VGROUP][0], 1, false);
     else block_reduce_store(sh, acc, 14, M.partials + (size_t)(VGROUP * NACC) * nb + b, nb, true);
@@ -1856,13 +1860,13 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
     if (warp == 0) {
       if (lane == 0) {
         int o = 0;
-        for (int a = 0; a < MAXK; ++a)
-          for (int c = a; c < MAXK; ++c) {
-            sh.fin.JJt[a * 4 + c] = sh.tot[VGROUP][o];
-            sh.fin.JJt[c * 4 + a] = sh.tot[VGROUP][o];
+        for (int a = 0; a < KA; ++a)
+          for (int c = a; c < KA; ++c) {
+            sh.fin.JJt[a * KA + c] = sh.tot[VGROUP][o];
+            sh.fin.JJt[c * KA + a] = sh.tot[VGROUP][o];
             ++o;
           }
-        for (int a = 0; a < MAXK; ++a) sh.fin.Jp[a] = sh.tot[VGROUP][10 + a];
+        for (int a = 0; a < KA; ++a) sh.fin.Jp[a] = sh.tot[VGROUP][10 + a];
       }
       abf_finish(M, S, sh, lane, cta0, false, false);
     }
@@ -1885,7 +1889,13 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       phase[s] ^= 1;
       const double* cc = stage_c[s];
       const double* hh = stage_h[s];
-      for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
+      if (k <= 2) {
+        for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval<2>(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
+      } else if (k <= 4) {
+        for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval<4>(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
+      } else {
+        for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval<MAXK>(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
+      }
       const long long nxt = a + 2LL * HC;
       if (nxt < h1) {  // refill this stage
         __syncthreads();
@@ -1964,7 +1974,7 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
           rem /= m.g_shape[d];
           x[d] = mesh_coord(m.grid_kind, i, m.g_lower[d], m.g_upper[d], m.g_shape[d]);
         }
-        double val = 0.0, dV[MAXK] = {0, 0, 0, 0};
+        double val = 0.0, dV[MAXK] = {};
         for (int r = 0; r < nrec; ++r) {
           const double* rec = wfinish ? S.records + (size_t)r * rs : sh.fin.hill;
           if (rec[k + 1] == 0.0) continue;
@@ -1989,7 +1999,7 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
           }
           ++idx;
           if (!grid_metad) {  // the other walkers' new hills do push on this walker
-            double dV[MAXK] = {0, 0, 0, 0};
+            double dV[MAXK] = {};
             f.energy += hill_eval(m, k, f.xi, rec, rec[k], dV);
             for (int c = 0; c < k; ++c) f.F[c] += dV[c];
           }

@@ -111,6 +111,25 @@ class ABFState(NamedTuple):  # abf.py:32-72
     ncalls: int = 0
 
 
+def freeze(state):
+    """A persistent VALUE of a state.  The tuples `update` returns are views of the handle's live device memory
+    (zero copy, no per-step allocation): every state of a run aliases the same buffers, so one kept across steps
+    shows the newest values -- unlike the reference, whose `update` is pure-functional and returns fresh arrays
+    (methods/core.py:108-116).  Callbacks that keep history (`Result.states` of intermediate steps, custom loggers)
+    take `freeze(state)`: tensors are cloned on the device (stream-ordered, no host sync), nested tuples recursed."""
+
+    def clone(x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().clone()
+        if isinstance(x, tuple) and hasattr(x, "_fields"):
+            return type(x)(*(clone(v) for v in x))
+        if isinstance(x, (tuple, list)):
+            return type(x)(clone(v) for v in x)
+        return x
+
+    return clone(state)
+
+
 class NativeStep:
     """Owns one psb_handle: the device-resident method state + index tables of one simulation."""
 
@@ -133,6 +152,11 @@ class NativeStep:
             d = cv.describe(keep)
             descs.extend(d if isinstance(d, list) else [d])
         cvs = (N.CvDesc * len(descs))(*descs)
+        k_total = sum(cv.ncomponents for cv in method.cvs)
+        if not 1 <= len(descs) <= N.MAX_CVS:  # the library's own messages; raised here before the descriptors overflow
+            raise ValueError(f"between 1 and {N.MAX_CVS} collective variables are supported (got {len(descs)})")
+        if k_total > N.MAX_K:
+            raise ValueError(f"at most {N.MAX_K} CV components are supported")
         mdesc = method.describe(helpers)
         ldesc = _snap.describe_layout(
             snapshot,

@@ -149,6 +149,26 @@ def test_sampling_context_enters_and_leaves_the_engine_context():
     assert events == ["enter", "run", "exit"]
 
 
+def test_states_are_live_views_and_freeze_gives_values():
+    """`update` returns views of live device memory (documented, methods.freeze): a kept state follows the run,
+    a frozen one does not -- the reference's states are values (methods/core.py:108-116)."""
+    snap = synthetic.make_snapshot(400, layout="hoomd", dtype=np.float32, seed=5)
+    traj = synthetic.make_trajectory(snap, frames=4, step=0.05)
+    kept, frozen = [], []
+
+    def cb(snapshot, state, t):
+        kept.append(state)
+        frozen.append(ps.freeze(state))
+
+    eng = mock.MockEngine(snap["layout"], snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda", trajectory=traj)
+    ps.run(method(), lambda **kw: eng, 4, callback=cb)
+    torch.cuda.synchronize()
+    xs = [f.xi.cpu().numpy().copy() for f in frozen]
+    assert all(np.any(xs[i] != xs[i + 1]) for i in range(3))          # values: one per step
+    assert all(np.array_equal(k.xi.cpu().numpy(), xs[-1]) for k in kept)  # views: all show the last step
+    assert [int(f.hist.sum()) for f in frozen] == [1, 2, 3, 4]
+
+
 def test_openmm_variable_step_integrators_are_rejected():
     Simulation = fake_engines.install_openmm()
     import openmm

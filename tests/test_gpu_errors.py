@@ -22,11 +22,10 @@ def test_create_errors_map_to_reference_exception_types():
     snap = synthetic.make_snapshot(100, layout="hoomd", dtype=np.float32, seed=1)
     with pytest.raises(ValueError, match="out of range"):
         build(ps.methods.HarmonicBias([ps.colvars.Distance([5, 100])], 1.0, [0.0]), snap)
-    with pytest.raises(ValueError, match="between 1 and 4 collective variables"):
-        cvs = [ps.colvars.DihedralAngle([i, i + 1, i + 2, i + 3]) for i in range(0, 20, 4)]
-        build(ps.methods.Unbiased(cvs[:4] + [ps.colvars.Component([50], 0)]), snap)
-    with pytest.raises(ValueError, match="at most"):
-        build(ps.methods.Unbiased([ps.colvars.Displacement([0, 1]), ps.colvars.Displacement([2, 3])]), snap)
+    with pytest.raises(ValueError, match="between 1 and 8 collective variables"):
+        build(ps.methods.Unbiased([ps.colvars.Component([i], 0) for i in range(9)]), snap)
+    with pytest.raises(ValueError, match="at most 8 CV components"):
+        build(ps.methods.Unbiased([ps.colvars.Displacement([2 * i, 2 * i + 1]) for i in range(3)]), snap)
     with pytest.raises(ValueError, match="sigma must be positive"):
         build(ps.methods.Metadynamics([ps.colvars.Distance([0, 1])], 1.0, [0.0], 5, 10), snap)
     with pytest.raises(ValueError, match="stride"):

@@ -119,6 +119,22 @@ def test_cfg3_coordination_1e8_pairs_known_answer():
     assert np.abs(fa + fb).max() <= 1e-5 * scale  # fp32 force array: one rounding per atom
     untouched = np.ones(n, bool); untouched[slot[ga]] = False; untouched[slot[gb]] = False
     assert not df[untouched].any()
+    # every per-atom gradient of the 1e8-pair sum against chunked numpy (SURVEY.md appendix A:
+    # d xi / d r_i = sum_j s'(r_ij) (r_i - r_j) / r_ij, s'(r) = -6 x^5 / (r0 (1 + x^6)^2), x = r / r0; opposite sign for j)
+    gA = np.zeros((len(xa), 3)); gB = np.zeros((len(xb), 3))
+    for i in range(0, len(xa), 500):
+        d = xa[i : i + 500, None, :] - xb[None, :, :]
+        r2 = (d**2).sum(-1)
+        x6 = (r2 / r0**2) ** 3
+        coef = -6.0 * x6 / (r2 * (1.0 + x6) ** 2)  # s'(r) / r
+        t = coef[:, :, None] * d
+        gA[i : i + 500] = t.sum(1); gB -= t.sum(0)
+    F_np = kspring * (total - center)
+    want = np.zeros((n, 3)); want[slot[ga]] = -F_np * gA; want[slot[gb]] = -F_np * gB
+    f0n = f0.cpu().numpy()[:, :3].astype(np.float64)
+    # the force array is fp32: one rounding of (f0 + bias) per component
+    tol = 1.2e-7 * np.maximum(np.abs(f0n + want), np.abs(f0n))
+    assert np.all(np.abs(df - want) <= tol + 1e-9 * np.abs(want).max()), np.abs(df - want).max()
     F = float(update.native.view("cv_force").cpu().numpy().ravel()[0])
     assert abs(F - kspring * (xi - center)) <= 1e-12 * abs(F)
 

@@ -1003,3 +1003,59 @@ def test_ermsd_coarse_grained_harmonic(layout, nb):
     for frame in perturbed(snap, 3, 0.01):
         run.step(frame)
     assert float(run.state.xi[0, 0]) > 0.0
+
+
+# ---- more CVs than the first build allowed (colvars/core.py:228-274 stacks any number; here up to 8 CVs,
+# ---- 8 components, 32 groups) -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout, dtype", [("hoomd", np.float32), ("hoomd", np.float64), ("openmm-cuda", np.float64),
+                                           ("lammps", np.float64)])
+def test_six_distances_harmonic_bias(layout, dtype):
+    """k = 6 with a full 6 x 6 spring matrix over 12 groups."""
+    snap = snapshot(layout, dtype)
+    groups = [list(range(40 * i, 40 * i + 25 + i)) for i in range(12)]
+    specs = [("Distance", ([groups[2 * i], groups[2 * i + 1]],), {}) for i in range(6)]
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(6, 6))
+    kspring = (a @ a.T + 6.0 * np.eye(6)).tolist()
+    run = ParityRun(snap, specs, harmonic(kspring, [0.5 * (i + 1) for i in range(6)]))
+    for pos in perturbed(snap, 3, 0.05):
+        run.step(pos)
+
+
+def test_eight_dihedrals_metadynamics_direct_sum():
+    """8 CVs, k = 8, 32 single-atom groups (the limits), periodic wrap on every component, deposits."""
+    snap = snapshot("hoomd", np.float64)
+    specs = [("DihedralAngle", ([4 + 7 * i, 6 + 7 * i, 8 + 7 * i, 14 + 7 * i],), {}) for i in range(8)]
+    kw = dict(height=1.2, sigma=[0.35] * 8, stride=2, ngaussians=8)
+    run = ParityRun(snap, specs, ("Metadynamics", kw))
+    for pos in perturbed(snap, 6, 0.05):
+        run.step(pos)
+    assert int(run.state.idx) == 2 and run.native.k == 8
+
+
+def test_ring_puckering_coordinates_plus_displacement_unbiased():
+    """RingPuckeringCoordinates (2 components) + Displacement (3): k = 5, rejected by the 4-component build.  Values
+    and the dense Jacobian against the oracle (the reference itself can only run this pair unbiased: its
+    get_periods / HarmonicBias count CVs, not components, colvars/utils.py:13-19, bias.py:62-65)."""
+    import oracle
+    import pysages_b200 as ps
+    from parity_utils import device_helpers, device_snapshot, oracle_snapshot
+
+    snap = snapshot("hoomd", np.float64)
+    cv_o = oracle.colvars.build(oracle.colvars.RingPuckeringCoordinates(RING6), oracle.colvars.Displacement([A, B]))
+    helpers, _ = oracle.backends.build_helpers("hoomd", {"positions", "indices"}, True)
+    xi_o, J_o = cv_o(helpers.query(oracle_snapshot(snap)))
+    m = ps.methods.Unbiased([ps.colvars.RingPuckeringCoordinates(RING6), ps.colvars.Displacement([A, B])], dense_bias=True)
+    dsnap = device_snapshot(snap)
+    _, init, update = m.build(dsnap, device_helpers("hoomd"))
+    st = update(dsnap, init())
+    torch.cuda.synchronize()
+    assert st.xi.shape == (1, 5) and update.native.k == 5
+    close(st.xi.cpu().numpy().ravel(), xi_o.numpy().ravel(), 1e-10, what="xi")
+
+
+def test_limits_are_reported():
+    snap = snapshot("hoomd", np.float64)
+    nine = [("Component", ([i], 0), {}) for i in range(9)]
+    with pytest.raises(ValueError, match="between 1 and 8"):
+        ParityRun(snap, nine, harmonic(1.0, [0.0] * 9))
