@@ -202,6 +202,7 @@ Snap make_snap(const psb_handle* h, const psb_snapshot* s, int mode) {
   S.types = s->types;
   for (int d = 0; d < 3; ++d) S.L[d] = s->box_diag[d];
   S.dt = s->dt;
+  S.inv_dt = s->dt != 0.0 ? 1.0 / s->dt : 0.0;
   S.natoms = h->layout.natoms;
   S.unwrap = h->layout.unwrap && h->layout.layout != PSB_LAYOUT_OPENMM_CUDA;
   S.need_momenta = h->layout.need_momenta;

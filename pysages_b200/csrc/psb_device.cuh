@@ -138,6 +138,7 @@ struct Fin {
   double Fsum_new[MAXK];    // ABF: Fsum[I] after this step's scatter-add
   double Fsum_old[MAXK];    // ABF: Fsum[I] as gathered (helper warp)
   double den;               // ABF: max(N, hist[I] after the scatter-add) (helper warp)
+  double inv_den;           // ABF: 1 / den, formed off the critical path next to the gathers
   double rforce[MAXK];      // ABF: restraint force when xi is outside the grid (helper warp)
   long long flat;           // clamped flat grid offset of xi
   long long nh;             // number of hills summed this step
@@ -233,6 +234,7 @@ struct Snap {
   const void* types;
   double L[3];
   double dt;
+  double inv_dt;  // 1 / dt (host): the finite difference of abf.py:213 multiplies by it instead of dividing
   long long natoms;
   int32_t unwrap;
   int32_t need_momenta;

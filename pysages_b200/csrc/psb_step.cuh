@@ -117,6 +117,19 @@ __device__ __forceinline__ long long global_ns() {
 #else
 #define PSB_STAMPS(slot) do {} while (0)
 #endif
+#ifdef PSB_PROBE_FIN  // experiment builds: finer clock stamps inside the ABF finalizer (replaces PSB_CLK 11..14)
+#define PSB_CLKF(slot)                                                               \
+  do {                                                                               \
+    if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = clock64(); \
+  } while (0)
+#undef PSB_CLK
+#define PSB_CLK(slot)                                                                \
+  do {                                                                               \
+    if ((slot) != 11 && (slot) != 12 && S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define PSB_CLKF(slot) do {} while (0)
+#endif
 #define PSB_STAMP(slot)                                                              \
   do {                                                                               \
     if (S.dbg && threadIdx.x == 0) S.dbg[(size_t)sh.vb * 16 + (slot)] = global_ns(); \
@@ -654,6 +667,7 @@ __device__ __forceinline__ void abf_bin_gather(const Model& M, StepShared& sh, i
       f.hist_new = h;
       f.in_range = oob ? 0 : 1;
       f.den = (double)(nmin > hh ? nmin : hh);
+      f.inv_den = 1.0 / f.den;
     }
   }
   __syncwarp();
@@ -718,11 +732,13 @@ __device__ __forceinline__ void abf_finish(const Model& M, const Snap& S, StepSh
     const double Wp_now = f.Wp[c], Wp_1 = sh.pre.Wp[c];
     double fs = f.Fsum_old[c];
     if (!oob && !hist_only) {
-      const double dWp_dt = (1.5 * Wp_now - 2.0 * Wp_1 + 0.5 * sh.pre.Wp_[c]) / S.dt;
+      // (x / dt and x / den of abf.py:213,244 as products with the reciprocals: one rounding more, ~1e-16 relative;
+      // both divisions were dependent ~200-cycle steps of the single-warp chain)
+      const double dWp_dt = (1.5 * Wp_now - 2.0 * Wp_1 + 0.5 * sh.pre.Wp_[c]) * S.inv_dt;
       fs += m.force_unit_factor * dWp_dt + sh.pre.force[c];
     }
     const double fc = use_model ? f_model
-                      : (zero_force ? 0.0 : ((m.has_restraints && oob) ? f.rforce[c] : fs / f.den));
+                      : (zero_force ? 0.0 : ((m.has_restraints && oob) ? f.rforce[c] : fs * f.inv_den));
     f.F[c] = fc;
     f.Fsum_new[c] = fs;
     if (cta0 && !M.ll_reduce) {  // scalars nobody reads after the first barrier (LL exchange: stored at the end)
@@ -810,6 +826,7 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
         __syncwarp();
         pair_sync(1);
       }
+      PSB_CLKF(11);
       if (M.fm_mode & FM_HIST_ONLY) {  // ann.py:153-167: no momenta, no W p
         if (lane < MAXK) f.Wp[lane] = 0.0;
         abf_finish(M, S, sh, lane, cta0, !GENERAL, true);
@@ -836,6 +853,7 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
           f.Jp[a] = s;
         }
         __syncwarp();
+        PSB_CLKF(12);
         if (lane < MAXK) {
           double w = 0.0;
           if (lane < k)
@@ -1773,7 +1791,13 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       if (!any_rmsd) post_cv<METHOD, GENERAL>(M, S, sh, lane, cta0);
       PSB_CLK(15);
     } else if (warp == 1 && is_abf && !GENERAL && S.mode != MODE_EVAL) {
+#ifdef PSB_PROBE_FIN
+      if (S.dbg && lane == 0) S.dbg[(size_t)sh.vb * 16 + 7] = clock64();  // helper warp reaches its barrier
+#endif
       abf_helper(M, sh, lane);
+#ifdef PSB_PROBE_FIN
+      if (S.dbg && lane == 0) S.dbg[(size_t)sh.vb * 16 + 5] = clock64();  // helper warp done (bin + gathers)
+#endif
     }
     __syncthreads();
     PSB_STAMP(3);

@@ -1,20 +1,22 @@
-"""SASS instruction count per source line for one kernel: python tools/sass_lines.py <nvdisasm -g out> <symbol> [top]"""
-import re, sys, collections
-sassp, sym = sys.argv[1:3]
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-cnt = collections.Counter(); cur = None; inside = False; n = 0
-for l in open(sassp):
-    if l.startswith(".text." + sym + ":"): inside = True; continue
-    if inside and l.startswith("//-----"): break
-    if not inside: continue
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-    if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
-    if re.match(r'\s*/\*[0-9a-f]{4,}\*/', l): cnt[cur] += 1; n += 1
-print("instructions:", n, "=", n * 16, "bytes")
-src = {}
-for (f, ln), c in cnt.most_common(top):
-    if f not in src:
-        try: src[f] = open("/root/repo/pysages_b200/csrc/" + f).read().split("\n")
-        except OSError: src[f] = []
-    text = src[f][ln - 1].strip()[:80] if 0 < ln <= len(src[f]) else ""
-    print(f"{c:6d} {f}:{ln}: {text}")
+"""Short SASS excerpts that show the Blackwell-specific instructions of this library's kernels (run here, no GPU):
+   python tools/sass_lines.py > profiles/r02_sass_excerpt.txt
+UBLKCP = cp.async.bulk (1-D TMA), SYNCS.* = mbarrier operations, per B200_PROFILING.md."""
+import re, subprocess, sys, os
+LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pysages_b200", "lib", "libpysages_b200.so")
+KERNELS = [
+    ("_ZN3psb11step_kernelILi1EfLi2ELi1EEEvPKNS_5ModelENS_4SnapE", "step_kernel<HOOMD, float, METAD_DIRECT, general>: pass H, hills staged by 1-D TMA bulk copies (cfg4)"),
+    ("_ZN3psb11step_kernelILi1EfLi1ELi3EEEvPKNS_5ModelENS_4SnapE", "step_kernel<HOOMD, float, HARMONIC, stream>: opt-in TMA-staged slot-ordered class (per-warp rings, bulk stores)"),
+]
+pat = re.compile(r"UBLKCP|SYNCS|UTMA|FENCE\.VIEW\.ASYNC|CCTL")
+for sym, title in KERNELS:
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", sym, LIB], capture_output=True, text=True).stdout
+    lines = [l for l in out.splitlines() if re.search(r"/\*[0-9a-f]{4,}\*/", l)]
+    hits = [re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip() for l in lines if pat.search(l)]
+    counts = {}
+    for l in hits:
+        m = re.search(r"(UBLKCP[.\w]*|SYNCS[.\w]*|UTMA\w*)", l)
+        if m: counts[m.group(1)] = counts.get(m.group(1), 0) + 1
+    print(f"== {title}\n   symbol {sym}: {len(lines)} SASS instructions; " + ", ".join(f"{k} x{v}" for k, v in sorted(counts.items())))
+    for l in hits[:14]:
+        print("   " + l.strip())
+    print()
