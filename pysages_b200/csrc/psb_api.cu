@@ -543,6 +543,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         for (int a = 0; a < 3; ++a) {
           Q[3 * (size_t)i + a] = d.reference[3 * (size_t)i + a] - cen[a];
           cv.sumQ[a] += Q[3 * (size_t)i + a];
+          cv.gq += Q[3 * (size_t)i + a] * Q[3 * (size_t)i + a];
         }
       double* p = nullptr;
       if ((st = dev_upload(h, &p, Q)) != PSB_OK) return bail(st);

@@ -38,6 +38,7 @@ struct CvDev {
   const double* ref;  // RMSD: centred reference Q (n,3), device
   const double* w;    // RMSD: weights (n), device, or nullptr (uniform 1/n)
   double sumQ[3];     // RMSD: sum_i Q_i (0 up to rounding for uniform weights)
+  double gq;          // RMSD: sum_i |Q_i|^2 of the centred reference
   double r0;          // coordination
   int32_t nn, mm;
   double* grad;       // coordination: per-term gradient workspace (T_cv, 3), device
@@ -130,7 +131,7 @@ struct Fin {
   double energy;
   double fg[MAXG][3];       // -sum_c F_c dxi_c/dpoint_g / n_g   (point CVs)
   double gpt[MAXG][3][3];   // dxi_{comp0+j}/dpoint_g
-  double cvx[MAXCV][20];    // RMSD: U[0..8], rbar[9..11], sumD[12..14], coef[15]; RoG: coef[0]
+  double cvx[MAXCV][20];    // RMSD: U[0..8], rbar[9..11], sumD[12..14], coef[15], [16] != 0: the residual pass is needed; RoG: coef[0]
   double hill[MAXK + 2];    // candidate / deposited hill: centre[k], height, valid
   double JJt[KA * KA];      // ABF: J J^T (leading dimension KA)
   double Jp[MAXK];          // ABF: J p

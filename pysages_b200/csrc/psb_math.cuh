@@ -364,6 +364,8 @@ PSB_HD void kabsch_rotation(const double* c, double* U) {
   const double det0 = x0 * (x4 * x8 - x5 * x7) - x1 * (x3 * x8 - x5 * x6) + x2 * (x3 * x7 - x4 * x6);
   bool ok = fabs(det0) > 1e-6 * fro2 * sqrt(fro2) && fro2 > 0.0;  // sigma_min / sigma_max >~ 1e-6
   bool converged = false;
+  bool scaled = true;  // Higham's scaling only while X is far from orthogonal: near it g -> 1 and its sqrt(sqrt(a / b))
+                       // would be most of the iteration's dependent chain (this runs in one thread, every step)
   for (int it = 0; ok && it < 16; ++it) {
     // adjugate^T / det = X^-T
     const double a0 = x4 * x8 - x5 * x7, a1 = x5 * x6 - x3 * x8, a2 = x3 * x7 - x4 * x6;
@@ -372,10 +374,14 @@ PSB_HD void kabsch_rotation(const double* c, double* U) {
     const double det = x0 * a0 + x1 * a1 + x2 * a2;
     if (det == 0.0 || (det > 0.0) != (det0 > 0.0)) break;
     const double id = 1.0 / det;
-    const double nx = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3 + x4 * x4 + x5 * x5 + x6 * x6 + x7 * x7 + x8 * x8;
-    const double na = (a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7 + a8 * a8) * id * id;
-    const double g = sqrt(sqrt(na / nx));  // sqrt(|X^-1|_F / |X|_F)
-    const double p = 0.5 * g, q = 0.5 * id / g;
+    double p = 0.5, q = 0.5 * id;
+    if (scaled) {
+      const double nx = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3 + x4 * x4 + x5 * x5 + x6 * x6 + x7 * x7 + x8 * x8;
+      const double na = (a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7 + a8 * a8) * id * id;
+      const double g = sqrt(sqrt(na / nx));  // sqrt(|X^-1|_F / |X|_F)
+      p = 0.5 * g;
+      q = 0.5 * id / g;
+    }
     const double y0 = p * x0 + q * a0, y1 = p * x1 + q * a1, y2 = p * x2 + q * a2;
     const double y3 = p * x3 + q * a3, y4 = p * x4 + q * a4, y5 = p * x5 + q * a5;
     const double y6 = p * x6 + q * a6, y7 = p * x7 + q * a7, y8 = p * x8 + q * a8;
@@ -383,6 +389,7 @@ PSB_HD void kabsch_rotation(const double* c, double* U) {
                       (y4 - x4) * (y4 - x4) + (y5 - x5) * (y5 - x5) + (y6 - x6) * (y6 - x6) + (y7 - x7) * (y7 - x7) +
                       (y8 - x8) * (y8 - x8);
     x0 = y0; x1 = y1; x2 = y2; x3 = y3; x4 = y4; x5 = y5; x6 = y6; x7 = y7; x8 = y8;
+    if (d2 <= 1e-2) scaled = false;  // |X_k+1 - X_k|_F <= 0.1: the quadratic regime, plain Newton from here
     if (d2 <= 1e-30) {  // |X_k+1 - X_k|_F <= 1e-15 with |X|_F = sqrt(3): converged (quadratically)
       converged = true;
       break;

@@ -136,6 +136,7 @@ __device__ __forceinline__ long long global_ns() {
   } while (0)
 
 struct StepShared {
+  int32_t need_pass_b;  // some RMSD is too close a fit for the one-pass residual (grid-uniform, see finalize_cv_A)
   int32_t vnb, vb;  // the step's own grid: CTAs of this replica and this CTA's index among them (== gridDim.x, blockIdx.x
                     // for psb_step; a sub-range of the launch for psb_batch_step)
   double red[NWARPS][NACC];
@@ -224,7 +225,7 @@ __host__ __device__ __forceinline__ int nacc_for_kind(int kind, int pass, bool m
     if (kind == PSB_CV_ROG) return 1;
     if (kind == PSB_CV_GYRATION) return 6;
     if (kind == PSB_CV_RING) return 12;
-    if (kind == PSB_CV_RMSD) return 15;
+    if (kind == PSB_CV_RMSD) return 16;
     return 0;
   }
   return kind == PSB_CV_RMSD ? 1 : 0;
@@ -453,6 +454,32 @@ static __device__ __forceinline__ void finalize_cv_A(const Model& M, StepShared&
       const double sp[3] = {sumr.x - n * rbar.x, sumr.y - n * rbar.y, sumr.z - n * rbar.z};
       for (int a = 0; a < 3; ++a)
         x[12 + a] = sp[a] - (cv.sumQ[0] * x[a * 3 + 0] + cv.sumQ[1] * x[a * 3 + 1] + cv.sumQ[2] * x[a * 3 + 2]);
+      // The residual of orientation.py:76-95 without a second pass over the atoms: with U orthogonal,
+      //   sum_i |P_i U - Q_i|^2 = sum |P_i|^2 + sum |Q_i|^2 - 2 sum_ab U_ab C_ab,
+      //   sum |P_i|^2 = sum |r_i|^2 - 2 rbar . sum r_i + n |rbar|^2.
+      // It is a difference of O(n R^2) terms whose tree-reduced fp64 sums carry a few 1e-16 of relative error
+      // each, so it is only taken when it keeps >= 1e-3 of their magnitude (RMSD >~ 5 % of the structure's
+      // size): the RMSD then keeps ~1e-13 relative.  That margin is needed downstream, not here: a metadynamics
+      // landscape of 1e4 narrow hills turns 1e-11 on xi into 1e-8 on the bias force (measured on cfg4, whose
+      // RMSD of 0.2 on a 19-unit globule therefore takes pass B, as does the reference's own ci2 case, 4.9e-4
+      // on a 10-unit structure).  Every CTA holds bit-identical sums: the decision is uniform over the grid.
+      {
+        const double sr2 = sh.tot[g0][15];
+        const double rb_sr = rbar.x * sumr.x + rbar.y * sumr.y + rbar.z * sumr.z;
+        const double rb2 = rbar.x * rbar.x + rbar.y * rbar.y + rbar.z * rbar.z;
+        double uc = 0.0;
+        for (int a = 0; a < 9; ++a) uc += x[a] * C[a];
+        const double res = ((sr2 - 2.0 * rb_sr) + n * rb2) + cv.gq - 2.0 * uc;
+        const double big = sr2 + 2.0 * fabs(rb_sr) + n * rb2 + cv.gq + 2.0 * fabs(uc);
+        if (res > 1e-3 * big) {
+          const double xi = sqrt(res * M.grp[g0].inv_n);
+          f.xi[cv.comp0] = xi;
+          x[15] = M.grp[g0].inv_n / xi;  // 1 / (n rmsd)
+          x[16] = 0.0;
+        } else {
+          x[16] = 1.0;
+        }
+      }
     } break;
     case PSB_CV_ERMSD:  // value and gradient come from ermsd_kernel, like the pair kernel's
     case PSB_CV_COORDINATION: {
@@ -959,7 +986,7 @@ static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, St
 __device__ __forceinline__ void finalize_cv_B(const Model& M, StepShared& sh, int c) {
   Fin& f = sh.fin;
   const CvDev& cv = M.cv[c];
-  if (cv.kind != PSB_CV_RMSD) return;
+  if (cv.kind != PSB_CV_RMSD || f.cvx[c][16] == 0.0) return;  // (value already final from pass A)
   const double inv_n = M.grp[cv.g0].inv_n;
   const double xi = sqrt(sh.tot[cv.g0][0] * inv_n);  // orientation.py:94
   f.xi[cv.comp0] = xi;
@@ -1005,6 +1032,7 @@ static __device__ __noinline__ void accumulate_nonpoint(const CvDev& cv, double 
     acc[6] += r.x * q0; acc[7] += r.x * q1; acc[8] += r.x * q2;
     acc[9] += r.y * q0; acc[10] += r.y * q1; acc[11] += r.y * q2;
     acc[12] += r.z * q0; acc[13] += r.z * q1; acc[14] += r.z * q2;
+    acc[15] += r.x * r.x + r.y * r.y + r.z * r.z;  // for the residual without a second pass (finalize_cv_A)
   }
 }
 template <bool GENERAL>
@@ -1788,7 +1816,17 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       if (any_coord) reduce_coordination(M, sh, lane);
       if (lane < M.ncv) finalize_cv_A<GENERAL>(M, sh, lane);
       PSB_CLK(10);
-      if (!any_rmsd) post_cv<METHOD, GENERAL>(M, S, sh, lane, cta0);
+      if (any_rmsd) {  // does any RMSD need the explicit residual pass?  (uniform over the grid, see finalize_cv_A)
+        __syncwarp();
+        if (lane == 0) {
+          int need = 0;
+          for (int c = 0; c < M.ncv; ++c)
+            if (M.cv[c].kind == PSB_CV_RMSD && sh.fin.cvx[c][16] != 0.0) need = 1;
+          sh.need_pass_b = need;
+        }
+        __syncwarp();
+      }
+      if (!any_rmsd || !sh.need_pass_b) post_cv<METHOD, GENERAL>(M, S, sh, lane, cta0);
       PSB_CLK(15);
     } else if (warp == 1 && is_abf && !GENERAL && S.mode != MODE_EVAL) {
 #ifdef PSB_PROBE_FIN
@@ -1803,11 +1841,11 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
     PSB_STAMP(3);
 
     // ---- pass B: RMSD residual with the optimal rotation ------------------------------------
-    if (any_rmsd) {
+    if (any_rmsd && sh.need_pass_b) {
       for (int g = g_begin; g < g_end; ++g) {
         const GroupDev& G = M.grp[g];
         const CvDev& cv = M.cv[G.cv];
-        if (cv.kind != PSB_CV_RMSD) continue;
+        if (cv.kind != PSB_CV_RMSD || sh.fin.cvx[G.cv][16] == 0.0) continue;
         const double* x = sh.fin.cvx[G.cv];
         double acc[1] = {0.0};
         if (cached) {
