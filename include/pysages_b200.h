@@ -30,9 +30,11 @@
 extern "C" {
 #endif
 
+#ifndef PSB_MAX_CVS          /* (overridable at build time for experiments; the shipped library uses these) */
 #define PSB_MAX_CVS 8        /* collective variables per method (colvars/core.py:228-274 stacks any number) */
 #define PSB_MAX_K 8          /* total CV components (xi has shape (1, k))  */
 #define PSB_MAX_GROUPS 32    /* atom groups ("points") over all CVs: eight dihedrals */
+#endif
 #define PSB_MAX_GRID_DIMS 4  /* gridded methods (ABF family, grid metadynamics): k = grid dimensions <= 4 */
 
 typedef struct psb_handle psb_handle;

@@ -10,6 +10,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int32, c_int64, c_uint32, c_void_p
 
 MAX_CVS, MAX_K, MAX_GROUPS, MAX_GRID_DIMS = 8, 8, 32, 4
+if os.environ.get("PSB_ABI_LIMITS"):  # experiment builds with -DPSB_MAX_CVS=... (tools/ab_limits.sh): same numbers here
+    MAX_CVS, MAX_K, MAX_GROUPS = (int(x) for x in os.environ["PSB_ABI_LIMITS"].split(","))
 
 OK, ERR_VALUE, ERR_RUNTIME, ERR_KEY, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 

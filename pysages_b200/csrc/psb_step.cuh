@@ -814,6 +814,13 @@ __device__ __forceinline__ void metad_grid_force(const Model& M, Fin& f, int lan
   if (lane == 0) f.energy = (!f.oob && M.st.gp) ? __ldcg(M.st.gp + f.flat) : 0.0;
 }
 
+// Direct hill sum over one staged chunk for k > KA components (kept out of line: the common k <= 4 loops then keep
+// their registers; metad.py:318-323)
+static __device__ __noinline__ void hill_chunk_wide(const MethodDev& m, int k, const double* xi, const double* cc,
+                                                    const double* hh, int cnt, int tid, double* acc) {
+  for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval<MAXK>(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
+}
+
 // Everything that can be decided once xi is complete (warp 0, all lanes).
 template <int METHOD, bool GENERAL>
 static __device__ __forceinline__ void post_cv(const Model& M, const Snap& S, StepShared& sh, int lane, bool cta0) {
@@ -1956,7 +1963,7 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       } else if (k <= 4) {
         for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval<4>(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
       } else {
-        for (int i = tid; i < cnt; i += BLOCK) acc[0] += hill_eval<MAXK>(m, k, xi, cc + (size_t)i * k, hh[i], acc + 1);
+        hill_chunk_wide(m, k, xi, cc, hh, cnt, tid, acc);
       }
       const long long nxt = a + 2LL * HC;
       if (nxt < h1) {  // refill this stage
@@ -2029,18 +2036,18 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       // every CTA has read grid_potential[I] (well-tempered height) before any bin is rewritten
       if (S.mode == MODE_STEP && m.well_tempered) grid_sync(M, sh, BAR_PRE_D);
       for (long long p = (long long)b * BLOCK + tid; p < m.grid_points; p += (long long)nb * BLOCK) {
-        double x[MAXK];
+        double x[KA];  // gridded metadynamics: k = grid dimensions <= KA
         long long rem = p;
         for (int d = m.grid_ndim - 1; d >= 0; --d) {
           const int i = (int)(rem % m.g_shape[d]);
           rem /= m.g_shape[d];
           x[d] = mesh_coord(m.grid_kind, i, m.g_lower[d], m.g_upper[d], m.g_shape[d]);
         }
-        double val = 0.0, dV[MAXK] = {};
+        double val = 0.0, dV[KA] = {};
         for (int r = 0; r < nrec; ++r) {
           const double* rec = wfinish ? S.records + (size_t)r * rs : sh.fin.hill;
           if (rec[k + 1] == 0.0) continue;
-          val += hill_eval(m, k, x, rec, rec[k], dV);  // d/dx of the Gaussian centred on rec
+          val += hill_eval<KA>(m, k, x, rec, rec[k], dV);  // d/dx of the Gaussian centred on rec
         }
         if (M.st.gp) M.st.gp[p] += val;
         for (int c = 0; c < k; ++c) M.st.gg[p * k + c] += dV[c];
