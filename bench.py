@@ -735,7 +735,17 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL announces its version on fd 1 at the first collective: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     stream = torch.cuda.Stream(device=device)
 
     # ring of distinct snapshots: 64, or as many as there are timed steps (the driver's 20-step run: 20 snapshots =
