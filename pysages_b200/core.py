@@ -164,13 +164,15 @@ def _metapotential(state, periods):
     return metapotential
 
 
-def analyze(result):
-    """Post-run analysis.  UmbrellaIntegration: umbrella_integration.py:220-261.  Metadynamics:
-    metad.py:326-383 (heights + the deposited bias potential as a callable).  ABF / FUNN / SpectralABF / CFF / Sirens: the binned
-    estimates (histogram, mean force, mesh) of abf.py / funn.py `analyze`; their free-energy
-    integration through a fitted network is out of scope."""
+def analyze(result, **kwargs):
+    """Post-run analysis.  UmbrellaIntegration: umbrella_integration.py:220-261.  Metadynamics: metad.py:326-383
+    (heights + the deposited bias potential as a callable).  ABF / FUNN: gradient learning (analysis.py:44-175: a
+    network whose input-gradient is fitted to the binned mean force; `topology=` as in abf.py:305, funn.py:342).
+    CFF / Sirens / ANN: the free-energy network the run trained.  SpectralABF: the fitted series as a value.
+    Grid-mapped arrays come back transposed along the grid axes, like the reference's."""
     import numpy as np
 
+    from . import analysis as _an
     from . import methods as _m
     from .colvars import get_periods
     from .grids import compute_mesh
@@ -211,14 +213,41 @@ def analyze(result):
                 out[key] = out[key][0]
         return out
     if isinstance(method, (_m.ABF, _m.FUNN, _m.SpectralABF, _m.CFF, _m.Sirens)):
-        out = dict(histogram=[], mean_force=[], mesh=compute_mesh(method.grid))
+        grid = method.grid
+        mesh = compute_mesh(grid)
+        transpose = _an.grid_transposer(grid)
+        d = mesh.shape[-1]
+        hists, forces, energies, fns, extra = [], [], [], [], {}
+        spectral_eval = _an.series_value_evaluator(method.model) if isinstance(method, _m.SpectralABF) else None
         for s in result.states:
             h = numpyfy(s)
-            hist = np.asarray(h.hist, dtype=np.float64)
-            out["histogram"].append(np.asarray(h.hist))
-            out["mean_force"].append(np.asarray(h.Fsum) / np.maximum(hist[..., None], 1))
-        if len(result.states) == 1:
-            out["histogram"], out["mean_force"] = out["histogram"][0], out["mean_force"][0]
+            if isinstance(method, _m.SpectralABF):  # spectral_abf.py:304-346
+                fes_fn = (lambda fun: (lambda x: (lambda A: A.max() - A)(spectral_eval(fun, x))))(h.fun)
+                extra.setdefault("fun", []).append(h.fun)
+            elif isinstance(method, (_m.CFF, _m.Sirens)):  # cff.py:392-424, sirens.py:467-498: the run's own network
+                fes_fn = _an.network_fes_fn(method.model, h.nn)
+                extra.setdefault("nn", []).append(h.nn)
+                if isinstance(method, _m.CFF):
+                    extra.setdefault("fnn", []).append(h.fnn)
+            else:  # ABF, FUNN: gradient learning on the binned mean force
+                topology = kwargs.get("topology", getattr(method, "topology", (8, 8)))
+                dev = s.hist.device if hasattr(s.hist, "device") else None
+                fes_fn, _ = _an.gradient_learning_fes(grid, s.hist, s.Fsum, topology, device=dev,
+                                                      pre_iters=kwargs.get("pre_iters", 250), iters=kwargs.get("iters", 1000))
+                if isinstance(method, _m.FUNN):
+                    extra.setdefault("nn", []).append(h.nn)
+            hists.append(transpose(h.hist))
+            forces.append(transpose(_an.average_forces(h.hist, h.Fsum)))
+            if isinstance(method, _m.CFF):
+                energies.append(transpose(np.asarray(h.fe).max() - np.asarray(h.fe)))
+            else:
+                energies.append(transpose(fes_fn(mesh)))
+            fns.append(fes_fn)
+        out = dict(histogram=_an.first_or_all(hists), mean_force=_an.first_or_all(forces),
+                   free_energy=_an.first_or_all(energies), fes_fn=_an.first_or_all(fns),
+                   mesh=transpose(mesh).reshape(-1, d).squeeze())
+        for key, vals in extra.items():
+            out[key] = _an.first_or_all(vals)
         return out
     if not isinstance(method, UmbrellaIntegration):
         raise NotImplementedError(f"analyze() is not implemented for {type(method).__name__} (DESIGN.md scope)")

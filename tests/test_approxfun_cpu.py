@@ -76,3 +76,34 @@ def test_fit_recovers_known_gradients():
     fun = oaf.fit_gradient(o, P, (3 * m[:, 0] ** 2 - 2).reshape(32, 1))
     xx = np.array([[0.2], [1.0], [3.3]])
     np.testing.assert_allclose(oaf.get_gradient(o, ns, fun, xx).ravel(), 3 * xx.ravel() ** 2 - 2, rtol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["periodic", "chebyshev"])
+def test_series_value_is_the_antiderivative_of_the_kernel_series(kind):
+    """spectral_abf.py:304-346 `analyze`: the fitted series evaluated as a VALUE (approxfun/core.py:149-166, 282-308)
+    must be the function whose gradient the step kernel evaluates: fit the sampled gradient of a known f, then
+    compare values up to the constant the fit cannot see."""
+    import pysages_b200 as ps
+    from pysages_b200 import analysis, approxfun
+    import torch
+
+    if kind == "periodic":
+        grid = ps.Grid[ps.Periodic]((-np.pi, -np.pi), (np.pi, np.pi), (16, 16))
+        f = lambda x: np.cos(x[:, 0]) * np.sin(x[:, 1]) + 0.3 * np.cos(2 * x[:, 0])
+        df = lambda x: np.stack([-np.sin(x[:, 0]) * np.sin(x[:, 1]) - 0.6 * np.sin(2 * x[:, 0]), np.cos(x[:, 0]) * np.cos(x[:, 1])], -1)
+    else:
+        grid = ps.Grid[ps.Chebyshev]((0.0, -1.0), (2.0, 3.0), (16, 16))
+        f = lambda x: 0.5 * x[:, 0] ** 2 * x[:, 1] - x[:, 1] ** 3 / 7
+        df = lambda x: np.stack([x[:, 0] * x[:, 1], 0.5 * x[:, 0] ** 2 - 3 * x[:, 1] ** 2 / 7], -1)
+    model = approxfun.SpectralGradientFit(grid)
+    pts = np.asarray(grid.lower) + (model.mesh + 1) / 2 * np.asarray(grid.size)  # the fit's own sample points
+    fit = approxfun.build_fitter(model, "cpu")
+    v = fit(torch.as_tensor(df(pts).reshape(16, 16, 2))).numpy()
+
+    class Fun:
+        scale, coefficients, c0 = v[0], v[1:], 0.0
+
+    got = analysis.series_value_evaluator(model)(Fun, pts).reshape(-1)
+    want = f(pts)
+    resid = (got - got.mean()) - (want - want.mean())
+    assert np.abs(resid).max() < 1e-6 * np.abs(want - want.mean()).max()

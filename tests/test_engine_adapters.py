@@ -271,10 +271,14 @@ def test_analyze_abf_and_umbrella_integration():
     snap = synthetic.make_snapshot(300, layout="hoomd", dtype=np.float64, seed=9)
     traj = synthetic.make_trajectory(snap, frames=6, step=0.05)
     res = ps.run(method(), lambda **kw: _mock(snap, traj), 6)  # ABF (abf.py analyze: binned estimates)
-    out = ps.analyze(res)
+    out = ps.analyze(res, topology=(4,), pre_iters=3, iters=5)  # abf.py:261-306: gradient learning (short fit here)
     st = ps.serialization.numpyfy(res.states[0])
     assert out["histogram"].sum() == st.hist.sum() and out["mesh"].shape == (256, 2)
-    np.testing.assert_array_equal(out["mean_force"], st.Fsum / np.maximum(st.hist[..., None].astype(np.float64), 1))
+    mf = st.Fsum / np.maximum(st.hist[..., None].astype(np.float64), 1)
+    np.testing.assert_array_equal(out["mean_force"], mf.transpose(1, 0, 2))  # transposed along the grid axes (grids.py:161-178)
+    np.testing.assert_array_equal(out["histogram"], st.hist.T)
+    assert out["free_energy"].shape == (16, 16) and np.isfinite(out["free_energy"]).all() and out["free_energy"].min() == 0.0
+    assert out["fes_fn"]([[3.0, 0.0], [6.0, 1.0]]).shape == (2, 1)
     # umbrella_integration.py:220-261: mean force per window and its running integral
     cv = [ps.colvars.Distance([G1, G2])]
     centers = [6.0, 6.5, 7.0]

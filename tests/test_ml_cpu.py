@@ -138,3 +138,26 @@ def test_sobolev_levenberg_marquardt_follows_oracle():
         np.testing.assert_allclose(pp.numpy(), qo, rtol=1e-6, atol=1e-8)
         assert mp == mo
     assert hp[-1][1] < 0.1 * hp[0][1]  # and it fits: the cost drops by more than 10x
+
+
+def test_gradient_learning_recovers_a_known_free_energy():
+    """analysis.py:44-175 (ABF / FUNN `analyze`): a network whose input-gradient is fitted to binned mean forces.
+    Forces = gradient of a known A(x) on a periodic 1-D grid -> fes_fn reproduces max A - A."""
+    import pysages_b200 as ps
+    from pysages_b200 import analysis
+    from pysages_b200.grids import compute_mesh
+
+    grid = ps.Grid[ps.Periodic]((-np.pi,), (np.pi,), (32,))
+    x = compute_mesh(grid).reshape(-1)
+    A = 2.0 * np.cos(x) + 0.5 * np.sin(2 * x)
+    dA = -2.0 * np.sin(x) + 1.0 * np.cos(2 * x)
+    hist = np.full(32, 7, dtype=np.int64)
+    Fsum = (dA * 7).reshape(32, 1)
+    fes_fn, nn = analysis.gradient_learning_fes(grid, hist, Fsum, (8, 8), device="cpu", pre_iters=60, iters=300)
+    got = fes_fn(x.reshape(-1, 1)).reshape(-1)
+    want = A.max() - A
+    assert np.abs(got - want).max() < 0.05 * (want.max() - want.min())
+    t = analysis.grid_transposer(ps.Grid[ps.Regular]((0.0, 0.0), (1.0, 1.0), (3, 5)))
+    a = np.arange(30).reshape(3, 5, 2)
+    np.testing.assert_array_equal(t(a), a.transpose(1, 0, 2))
+    np.testing.assert_array_equal(t(np.arange(15)), np.arange(15).reshape(3, 5).T)
