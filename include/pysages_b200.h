@@ -337,6 +337,38 @@ typedef struct {
 } psb_force_series;
 psb_status psb_set_force_series(psb_handle* h, const psb_force_series* series, void* cuda_stream);
 
+/* ---- cadenced refit on the device --------------------------------------------------------------- */
+/* Replaces the Levenberg-Marquardt fit FUNN / ANN / CFF's force network run every `train_freq` steps
+ * (ml/training.py:42-56 build_fitting_function + ml/optimizers.py:188-232, sum-of-squared-errors loss with float32
+ * residuals and L2 regularisation, ml/objectives.py) for tanh multilayer perceptrons with `scale` as input
+ * transform (approxfun/core.py:99-104): Jacobian by closed-form back-propagation, J^T J by a tiled fp64 kernel,
+ * damped normal equations by a blocked Cholesky in one CTA, candidate cost, gain ratio and damping update -- the
+ * whole data-dependent loop runs from device-resident control state, enqueued on `cuda_stream` without any host
+ * synchronisation.  `x` (n, widths[0]), `y` (n, widths[n_dense]) and `params` (flat, ml/utils.py:43-53; updated
+ * in place) are device pointers.  At most 1024 parameters.  Sine layers and the gradient / Sobolev losses
+ * (Sirens, CFF's energy network) stay with the host layer (pysages_b200/ml.py). */
+typedef struct {
+  int32_t n_dense;
+  int32_t widths[PSB_MAX_DENSE + 1];
+  int32_t activation; /* PSB_ACT_TANH */
+  int32_t max_iters;  /* accepted steps (ml/optimizers.py:121-131) */
+  int32_t max_loops;  /* loop passes enqueued; 0: 2 * max_iters + 64 */
+  int32_t reserved;
+  int64_t n;          /* samples */
+  const double* x;
+  const double* y;
+  double* params;
+  double lower[PSB_MAX_K], upper[PSB_MAX_K]; /* grid bounds of the input transform */
+  double reg;         /* L2Regularization.coeff */
+  float mu_0, mu_c, mu_min, mu_max, rho_c, rho_min; /* LevenbergMarquardtParams (ml/optimizers.py:40-51) */
+} psb_lm_problem;
+typedef struct psb_lm_workspace psb_lm_workspace;
+/* *ws == NULL: a workspace is created; reuse it for later fits of the same shape (the iteration's CUDA graph is kept) */
+psb_status psb_lm_fit(const psb_lm_problem* problem, psb_lm_workspace** ws, void* cuda_stream);
+/* accepted iterations, final cost, damping and loop passes of the last fit (synchronises `cuda_stream`) */
+psb_status psb_lm_result(psb_lm_workspace* ws, int32_t* iters, double* cost, float* mu, int32_t* loops, void* cuda_stream);
+void psb_lm_destroy(psb_lm_workspace* ws);
+
 int64_t psb_launch_count(psb_handle* h);
 /* 1 when the last psb_run_cycle replayed a CUDA graph, 0 when it issued plain launches. */
 int32_t psb_cycle_uses_graph(psb_handle* h);

@@ -140,6 +140,30 @@ class SnapshotDesc(Structure):
     ]
 
 
+class LmProblem(Structure):
+    _fields_ = [
+        ("n_dense", c_int32),
+        ("widths", c_int32 * (8 + 1)),
+        ("activation", c_int32),
+        ("max_iters", c_int32),
+        ("max_loops", c_int32),
+        ("reserved", c_int32),
+        ("n", c_int64),
+        ("x", c_void_p),
+        ("y", c_void_p),
+        ("params", c_void_p),
+        ("lower", c_double * MAX_K),
+        ("upper", c_double * MAX_K),
+        ("reg", c_double),
+        ("mu_0", ctypes.c_float),
+        ("mu_c", ctypes.c_float),
+        ("mu_min", ctypes.c_float),
+        ("mu_max", ctypes.c_float),
+        ("rho_c", ctypes.c_float),
+        ("rho_min", ctypes.c_float),
+    ]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "psb_create": (c_int32, [POINTER(CvDesc), c_int32, POINTER(MethodDesc), POINTER(LayoutDesc), POINTER(c_void_p)]),
@@ -173,6 +197,9 @@ EXPORTS = {
     "psb_launch_floor": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "psb_latency_probe": (c_int32, [POINTER(c_double)]),
     "psb_fma_peak": (c_int32, [POINTER(c_double)]),
+    "psb_lm_fit": (c_int32, [POINTER(LmProblem), POINTER(c_void_p), c_void_p]),
+    "psb_lm_result": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_double), POINTER(ctypes.c_float), POINTER(c_int32), c_void_p]),
+    "psb_lm_destroy": (None, [c_void_p]),
     "psb_abi_version": (c_int32, []),
 }
 

@@ -299,6 +299,7 @@ bool host_next_deposits(const psb_handle* h) {
 extern "C" {
 
 const char* psb_last_error(void) { return g_error.c_str(); }
+psb_status psbi_fail(psb_status code, const char* msg) { return fail(code, "%s", msg); }  // for the other translation units
 int32_t psb_abi_version(void) { return 1; }
 
 void psb_destroy(psb_handle* h) {

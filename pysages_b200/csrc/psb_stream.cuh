@@ -1,20 +1,16 @@
-// psb_stream.cuh -- TMA-pipelined slot-ordered streaming for the fused step kernel (class SC_STREAM, sm_100a).
+// psb_stream.cuh -- bulk-copy (TMA) helpers of the streaming variant of the slot-ordered step (class SC_STREAM, sm_100a).
 //
 // The slot-ordered class (psb_step.cuh) reads positions / images / velocities and read-modify-writes the force
-// rows of (almost) every slot: a pure stream over the engine's arrays.  Loading it through registers leaves too
-// few bytes in flight (two dependent batches of 8 rows per thread: 3.2 TB/s, ncu warps_active 25 %).  Here ONE
-// CTA per SM owns a contiguous slice of slots and moves it with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP)
-// through a ring of shared-memory stages that fills the SM's whole shared memory (~200 KB in flight per SM):
+// rows of (almost) every slot: a pure stream over the engine's arrays.  SC_STREAM moves that stream with 1-D bulk
+// copies (cp.async.bulk -> SASS UBLKCP) instead of register loads: two CTAs per SM, every WARP owns a ring of
+// shared-memory stages (STREAM_MAX_STAGES x stage_bytes, psb_device.cuh: StreamGeom) and an mbarrier per stage
+// (StepShared::full), gather chunks [positions | images | velocities] first, scatter chunks [forces] behind them,
+// written back with bulk stores (cp.async.bulk.global.shared::cta) once updated in shared memory.  Stage i completes
+// on full[i % S] with parity (i / S) & 1; a stage is re-armed after the warp has consumed it (for scatter stages once
+// the bulk store has read it: cp.async.bulk.wait_group.read).  HOOMD layout ((N,4) rows of Real, (N,3) int32 images).
 //
-//   item 0 .. n-1   gather chunk c : [positions | images | velocities] of CH slots  -> issued before the
-//                                    dependency wait and consumed after pass 0 (their HBM time hides under it)
-//   item n .. 2n-1  scatter chunk c: [forces (| positions | images: RoG groups)]    -> issued as gather stages
-//                                    drain, i.e. the force rows arrive while the grid-wide exchange and the
-//                                    finalizer run; updated in shared memory, written back with bulk stores
-//
-// Item i lives in stage i % S and completes on mbarrier full[i % S] with parity (i / S) & 1; item i + S is issued
-// by thread 0 once item i has been consumed (block barrier; for scatter chunks once the bulk store has read the
-// stage: cp.async.bulk.wait_group.read).  HOOMD layout ((N,4) rows of Real, (N,3) int32 images).
+// Measured slower than the register path on B200 (30.7 vs 27.4 us at 1e6 rows, DESIGN.md 4.1: the slot-map words and
+// the per-pass issue latency bound the step, not the bytes in flight), so the class is opt-in (PSB_STREAM=1).
 #pragma once
 
 #include "psb_device.cuh"

@@ -195,8 +195,40 @@ def smooth(y, kernel, boundary):
     return torch.stack([convolve(y[..., c], kernel, boundary) for c in range(y.shape[-1])], dim=-1)
 
 
-def build_fitting_function(model, optimizer):
-    """ml/training.py:42-56 + ml/optimizers.py:188-232 -> fit(params, x, y) -> params."""
+class _LMWorkspace:
+    """Owns a psb_lm_workspace (device buffers + the captured iteration graph of csrc/psb_refit.cu)."""
+
+    def __init__(self):
+        import ctypes
+
+        self.handle = ctypes.c_void_p()
+        self.keep = None
+        self.lib = None
+
+    def result(self):
+        """(accepted iterations, cost, mu, loop passes) of the last native fit; synchronises the current stream."""
+        import ctypes
+
+        it, loops, cost, mu = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_double(), ctypes.c_float()
+        from . import _native as N
+
+        dev = self.keep[2].device
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N.check(self.lib.psb_lm_result(self.handle, ctypes.byref(it), ctypes.byref(cost), ctypes.byref(mu), ctypes.byref(loops), stream))
+        return it.value, cost.value, mu.value, loops.value
+
+    def __del__(self):
+        if self.lib is not None and self.handle:
+            try:
+                self.lib.psb_lm_destroy(self.handle)
+            except Exception:  # interpreter shutdown
+                pass
+
+
+def build_fitting_function(model, optimizer, force_host=False):
+    """ml/training.py:42-56 + ml/optimizers.py:188-232 -> fit(params, x, y) -> params.  Plain-loss fits of tanh
+    networks on a CUDA device run in hand-written kernels (psb_lm_fit); sine layers, the gradient / Sobolev losses,
+    CPU tensors and `force_host=True` take the torch implementation below (same loop, same float32 conventions)."""
     _, c, mu_min, mu_max, rho_c, rho_min = optimizer.params
     r = float(optimizer.reg.coeff)
     f32 = np.float32
@@ -237,7 +269,46 @@ def build_fitting_function(model, optimizer):
     def cost(e, p):
         return float((e @ e + r * (p @ p)) / 2)
 
+    native_ok = (not sobolev and not gradients_only and model.activation != "sin" and not force_host
+                 and sum(a * b + b for a, b in zip(model.widths[:-1], model.widths[1:])) <= 1024
+                 and len(model.widths) - 1 <= 8 and max(model.widths) <= 128)
+    workspace = _LMWorkspace() if native_ok else None
+
+    def native_fit(params, x, y):
+        """psb_lm_fit (csrc/psb_refit.cu): the same loop with hand-written kernels and device-resident control
+        state -- stream-ordered, no host synchronisation."""
+        import ctypes
+
+        from . import _native as N
+
+        lib = N.load()
+        dev = params.device
+        p = params.detach().to(F64).contiguous().clone()
+        xx = x.detach().to(device=dev, dtype=F64).reshape(-1, model.widths[0]).contiguous()
+        yy = y.detach().to(device=dev, dtype=F64).reshape(xx.shape[0], model.widths[-1]).contiguous()
+        q = N.LmProblem()
+        q.n_dense = len(model.widths) - 1
+        for i, w in enumerate(model.widths):
+            q.widths[i] = int(w)
+        q.activation = N.ACT_TANH
+        q.max_iters = int(optimizer.max_iters)
+        q.n = int(xx.shape[0])
+        q.x, q.y, q.params = xx.data_ptr(), yy.data_ptr(), p.data_ptr()
+        lo, hi = np.asarray(model.lower, dtype=np.float64).ravel(), np.asarray(model.upper, dtype=np.float64).ravel()
+        for d in range(model.widths[0]):
+            q.lower[d], q.upper[d] = float(lo[d]), float(hi[d])
+        q.reg = float(r)
+        q.mu_0, q.mu_c, q.mu_min, q.mu_max, q.rho_c, q.rho_min = (float(v) for v in optimizer.params)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            N.check(lib.psb_lm_fit(ctypes.byref(q), ctypes.byref(workspace.handle), stream))
+        workspace.keep = (xx, yy, p)  # inputs of the stream-ordered kernels stay alive until the next fit
+        workspace.lib = lib
+        return p
+
     def fit(params, x, y, history=None):
+        if native_ok and history is None and params.is_cuda:
+            return native_fit(params, x, y)
         p_ = params.to(F64)
         e_ = error(p_, x, y)
         C_, mu = np.inf, f32(optimizer.params.mu_0)
@@ -269,6 +340,8 @@ def build_fitting_function(model, optimizer):
                 history.append((p_.clone(), float(C_), float(mu)))
         return p_
 
+    fit.workspace = workspace
+    fit.native = native_ok
     return fit
 
 
