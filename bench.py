@@ -77,16 +77,20 @@ def device_hoomd_frames(natoms, nframes, device, seed, dtype=torch.float32, glob
             rtag = fixed_rtag
         else:  # random permutation (the worst case for the gathers)
             rtag = torch.randperm(natoms, generator=g, device=device).to(torch.int32)
-        frames.append(dict(positions=pos, vel_mass=vm, forces=f, rtags=rtag, images=img))
+        # HOOMD keeps both directions of the permutation current: rtag (tag -> slot, what the reference's hook receives)
+        # and tag (slot -> tag, hoomd-dlext `tags`); the slot-ordered kernel class streams in slot order with the latter
+        tags = torch.empty_like(rtag)
+        tags[rtag.long()] = torch.arange(natoms, device=device, dtype=torch.int32)
+        frames.append(dict(positions=pos, vel_mass=vm, forces=f, rtags=rtag, images=img, tags=tags))
     return frames, L, x0
 
 
-def snapshots_of(frames, L, dt):
+def snapshots_of(frames, L, dt, with_tags=True):
     from pysages_b200.backends.snapshot import Box, Snapshot
 
     box = Box(np.diag([L, L, L]), np.full(3, -L / 2))
-    return [Snapshot(f["positions"], f["vel_mass"], f["forces"], f["rtags"], box, dt, dict(images=f["images"]))
-            for f in frames]
+    extras = (lambda f: dict(images=f["images"], tags=f["tags"])) if with_tags else (lambda f: dict(images=f["images"]))
+    return [Snapshot(f["positions"], f["vel_mass"], f["forces"], f["rtags"], box, dt, extras(f)) for f in frames]
 
 
 def device_layout_snapshots(layout, dtype, natoms, nframes, device, seed):
@@ -520,8 +524,8 @@ def run_series(device, stream, hbm, fp64_peak=None):
     """Secondary sizes / configurations (parity-tested elsewhere); short runs, same timing method."""
     out = []
 
-    def measure(label, name, natoms, steps, frames, L, extra=None, specs=None):
-        snaps = snapshots_of(frames, L, 0.005)
+    def measure(label, name, natoms, steps, frames, L, extra=None, specs=None, with_tags=True):
+        snaps = snapshots_of(frames, L, 0.005, with_tags)
         cvs, m = specs if specs is not None else workload_specs(name, natoms, L)
         method, native = build_ours(cvs, m, snaps[0])
         if extra is not None:
@@ -534,6 +538,8 @@ def run_series(device, stream, hbm, fp64_peak=None):
                    algorithmic_bytes=info["algorithmic_bytes_per_step"], achieved_gbs=round(gbs, 1),
                    frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"], launches_per_step=round(launches / steps, 2),
                    distinct_snapshots=len(frames))
+        if native.wants_tags:  # slot-ordered class: says which of its two instantiations ran
+            row["slot_to_tag_array"] = bool(with_tags)
         out.append(row)
         del snaps, native, method
         torch.cuda.empty_cache()
@@ -546,6 +552,8 @@ def run_series(device, stream, hbm, fp64_peak=None):
         nfr = 64 if natoms <= 100_000 else 8
         frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977, sorted_tags=sorted_tags)
         measure(f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), name, natoms, steps, frames, L)
+        if natoms == 1_000_000 and not sorted_tags:  # the same without HOOMD's slot -> tag array: tag -> slot inversion pass in the kernel
+            measure(f"{name} S=N={natoms} hoomd-f32 (rtag only)", name, natoms, steps, frames, L, with_tags=False)
         del frames
 
     # SURVEY.md 8d scaling series, third family: RadiusOfGyration over ALL atoms + metadynamics on a 1-D grid
@@ -558,6 +566,9 @@ def run_series(device, stream, hbm, fp64_peak=None):
                   grid=((0.0,), (4.0 * L * L,), (256,), "regular"))  # unwrapped <r.r> reaches a few L^2
         measure(f"RoG(all) + metadynamics on a 256-bin grid S=N={natoms} hoomd-f32", None, natoms, steps, frames, L,
                 specs=(rog, ("Metadynamics", md)))
+        if natoms == 1_000_000:
+            measure(f"RoG(all) + metadynamics on a 256-bin grid S=N={natoms} hoomd-f32 (rtag only)", None, natoms, steps,
+                    frames, L, specs=(rog, ("Metadynamics", md)), with_tags=False)
         del frames
 
     # row K (FUNN, funn.py:187-296): the headline workload with the force taken from a (2, 14, 14, 2)

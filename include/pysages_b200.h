@@ -189,6 +189,10 @@ typedef struct {
   const void* types;  /* LAMMPS: per-atom types (i32) */
   double box_diag[3]; /* diag(H) -- the reference unwraps with the diagonal only (hoomd.py:180) */
   double dt;
+  /* Optional, HOOMD layout: the slot -> tag array (ParticleData's `tag`, the inverse of `ids` = rtag; hoomd-dlext
+     exports both).  With it the slot-ordered class streams the engine's arrays in memory order and reads the group of
+     a slot from a tag -> group table: no tag -> slot inversion pass, one grid barrier fewer.  NULL: `ids` only. */
+  const void* tags;
 } psb_snapshot;
 
 /* ---- lifecycle -------------------------------------------------------------------- */
@@ -388,6 +392,9 @@ psb_status psb_latency_probe(double* out_host16);
  * conversions, out[4] DADD.  Synchronous. */
 psb_status psb_fma_peak(double* out_host5);
 int32_t psb_abi_version(void);
+/* 1 when the handle steps faster on snapshots that carry `tags` (slot-ordered class on the HOOMD layout): the adapter
+ * then asks the engine for its slot -> tag array each step (hoomd-dlext `tags`), 0 when the field is ignored. */
+int32_t psb_wants_tags(psb_handle* h);
 
 #ifdef __cplusplus
 }

@@ -137,6 +137,7 @@ class SnapshotDesc(Structure):
         ("types", c_void_p),
         ("box_diag", c_double * 3),
         ("dt", c_double),
+        ("tags", c_void_p),
     ]
 
 
@@ -201,6 +202,7 @@ EXPORTS = {
     "psb_lm_result": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_double), POINTER(ctypes.c_float), POINTER(c_int32), c_void_p]),
     "psb_lm_destroy": (None, [c_void_p]),
     "psb_abi_version": (c_int32, []),
+    "psb_wants_tags": (c_int32, [c_void_p]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpysages_b200.so")

@@ -6,6 +6,9 @@ Per step the plugin calls `Sampler.on_half_step(positions, vel_mass, rtags, imag
 with five DLPack capsules (argument order of hoomd.py:159-168).  The adapter does not turn them into
 arrays: it reads the five device addresses out of the capsules, refreshes the pre-filled `psb_snapshot`
 when HOOMD has moved a buffer (it double-buffers while sorting particles), and makes one native call.
+When most of the system is selected the step streams HOOMD's arrays in memory order; it then also asks the
+plugin for the slot -> tag array (`hoomd.dlext.tags`, ParticleData's `tag`: the inverse of `rtags`), which
+saves the kernel its tag -> slot inversion pass.
 HOOMD issues its kernels on the legacy default stream, which is also torch's current stream in the
 stepping thread, so the bias lands between the force computation and the second half step by stream
 order alone: no `sync_backend()` / `block_until_ready()` / `sync_forces()` (hoomd.py:219-230).
@@ -23,6 +26,7 @@ from . import _common as C
 from .snapshot import Box, Snapshot
 
 AccessLocation, AccessMode = _dlext.AccessLocation, _dlext.AccessMode
+_tags_of = getattr(_dlext, "tags", None)  # tags(sysview, location, mode) -> DLPack capsule of slot -> tag
 
 
 class _ApiV2:
@@ -115,14 +119,18 @@ class Sampler(C.SamplerCore, *_BASES):
             base.__init__(self)
         _dlext.DLExtSampler.__init__(self, self.view, self.on_half_step, location, AccessMode.Read)
         self._last = None
+        self._want_tags = False
         self._bind_method(sampling_method, C.LAYOUTS["hoomd"], callback)
+        self._want_tags = _tags_of is not None and self._native.wants_tags
 
     # ---- plugin callbacks: (positions, vel_mass, rtags, images, forces, timestep) -----------------
     def on_half_step(self, positions, vel_mass, rtags, images, forces, timestep):
         if not self._fused:
             return self.advance_snapshot(self._wrap(positions, vel_mass, rtags, images, forces), timestep)
         d = C.capsule_data
-        key = (d(positions), d(vel_mass), d(rtags), d(images), d(forces))
+        # the capsule keeps HOOMD's array handle until it is dropped at the end of this call
+        tags = _tags_of(self.view, self.location, AccessMode.Read) if self._want_tags else None
+        key = (d(positions), d(vel_mass), d(rtags), d(images), d(forces), d(tags) if tags is not None else None)
         self._last = (positions, vel_mass, rtags, images, forces)
         try:
             if key != self._desc_key:  # HOOMD moved a buffer (it double-buffers while sorting): check, then refill
@@ -131,7 +139,7 @@ class Sampler(C.SamplerCore, *_BASES):
                     raise RuntimeError(f"HOOMD now exposes {n} particles on device type {dev}; the method was built "
                                        f"for {self._native.natoms} on the GPU")
                 ds = self._desc
-                ds.positions, ds.vel_mass, ds.ids, ds.images, ds.forces = key
+                ds.positions, ds.vel_mass, ds.ids, ds.images, ds.forces, ds.tags = key
                 H = self.update_box().H
                 ds.box_diag[0], ds.box_diag[1], ds.box_diag[2] = float(H[0][0]), float(H[1][1]), float(H[2][2])
                 ds.dt = float(self.dt)
@@ -142,8 +150,10 @@ class Sampler(C.SamplerCore, *_BASES):
 
     def _wrap(self, positions, vel_mass, rtags, images, forces):
         t = C.tensor_from_capsule
-        return Snapshot(t(positions), t(vel_mass), t(forces), t(rtags), self.update_box(), self.dt,
-                        dict(images=t(images)))
+        extras = dict(images=t(images))
+        if self._want_tags:
+            extras["tags"] = t(_tags_of(self.view, self.location, AccessMode.Read))
+        return Snapshot(t(positions), t(vel_mass), t(forces), t(rtags), self.update_box(), self.dt, extras)
 
     def _views(self):
         """Zero-copy views of HOOMD's current buffers: inside a half step the capsules of that step, otherwise a

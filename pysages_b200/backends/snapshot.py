@@ -136,6 +136,9 @@ def describe_snapshot(snapshot, layout, out=None):
     s.forces = _ptr(snapshot.forces)
     images = snapshot.extras.get("images") if snapshot.extras else None
     s.images = _ptr(images)
+    # HOOMD: the engine's slot -> tag array, when the adapter got one (psb_snapshot.tags)
+    tags = snapshot.extras.get("tags") if (snapshot.extras and kind == N.LAYOUT_HOOMD) else None
+    s.tags = _ptr(tags)
     if kind == N.LAYOUT_LAMMPS:
         velocities, (masses, types) = snapshot.vel_mass
         s.vel_mass = _ptr(velocities)

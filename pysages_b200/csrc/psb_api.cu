@@ -141,6 +141,7 @@ struct psb_handle {
   // staging for psb_step_host
   psb_snapshot dev_snap{};
   bool have_staging = false;
+  bool tags_class = false;  // the SC_TAGS instantiation is co-resident at this handle's grid (HOOMD, slot-ordered)
   std::vector<std::pair<const void*, size_t>> host_ranges;  // engine arrays seen by psb_step_host (and page-locked by it)
   std::vector<void*> host_registered;                        // ... the ones this handle registered itself
   size_t hpad = 0;
@@ -200,6 +201,7 @@ Snap make_snap(const psb_handle* h, const psb_snapshot* s, int mode) {
   S.images = s->images;
   S.masses = s->masses;
   S.types = s->types;
+  S.tags = s->tags;
   for (int d = 0; d < 3; ++d) S.L[d] = s->box_diag[d];
   S.dt = s->dt;
   S.inv_dt = s->dt != 0.0 ? 1.0 / s->dt : 0.0;
@@ -282,6 +284,8 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
                            (S.need_momenta ? (uintptr_t)s->vel_mass : 0);
     if (bits & 15u) { cls = SC_SLOT; dyn = 0; }
   }
+  // the engine's slot -> tag array came along: no tag -> slot inversion pass (HOOMD layout, psb_snapshot.tags)
+  if (cls == SC_SLOT && h->tags_class && s->tags) cls = SC_TAGS;
   CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, cls, h->d_model, &S, h->grid, dyn, stream,
                                                h->pdl && !helper_before));
   ++h->launches;
@@ -300,7 +304,9 @@ extern "C" {
 
 const char* psb_last_error(void) { return g_error.c_str(); }
 psb_status psbi_fail(psb_status code, const char* msg) { return fail(code, "%s", msg); }  // for the other translation units
-int32_t psb_abi_version(void) { return 1; }
+int32_t psb_abi_version(void) { return 2; }
+
+int32_t psb_wants_tags(psb_handle* h) { return (h && h->tags_class) ? 1 : 0; }
 
 void psb_destroy(psb_handle* h) {
   if (!h) return;
@@ -796,6 +802,17 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         M.tag_group = p;
       } else {
         st = dev_alloc(h, &M.slot_map, (size_t)layout->natoms);
+        if (st == PSB_OK && layout->layout == PSB_LAYOUT_HOOMD && h->step_general == SC_SLOT &&
+            !(getenv("PSB_NO_TAGS") && atoi(getenv("PSB_NO_TAGS")) != 0) &&
+            (long long)pick_vtable(*layout)->occupancy(h->step_method, SC_TAGS, h->dyn_smem) * h->num_sms >= h->grid) {
+          // snapshots that carry the engine's slot -> tag array take the SC_TAGS instantiation (enqueue)
+          std::vector<uint8_t> tag_group((size_t)layout->natoms, 0);
+          for (uint32_t t = 0; t < M.T; ++t) tag_group[term_tag[t]] = (uint8_t)(term_group[t] + 1);
+          uint8_t* p = nullptr;
+          st = dev_upload(h, &p, tag_group);
+          M.tag_group = p;
+          h->tags_class = true;
+        }
       }
       if (st != PSB_OK) return bail(st);
     }
@@ -804,6 +821,19 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     for (int g = 0; g < MAXG; ++g) {
       M.cta_lo[g] = 0;
       M.cta_hi[g] = g < ng ? h->grid - 1 : -1;
+    }
+    // The slot-ordered classes (hundreds of CTAs) exchange their pass-A sums through flagged words as well, in two
+    // levels (reduce_rows_ll2, psb_step.cuh): row owners add the partials, everybody reads the totals.  Same methods
+    // as below; not the TMA-staged variant.
+    const bool ll_method = method->kind == PSB_METHOD_UNBIASED || method->kind == PSB_METHOD_HARMONIC ||
+                           method->kind == PSB_METHOD_ABF;
+    if (h->step_general == SC_SLOT && ll_method && !getenv("PSB_NO_LL") &&
+        !(getenv("PSB_NO_LL2") && atoi(getenv("PSB_NO_LL2")) != 0)) {
+      M.ll_reduce = 1;
+      psb_status st = dev_alloc(h, &M.ll, (size_t)MAXG * NACC * h->grid);
+      if (st == PSB_OK) st = dev_alloc(h, &M.ll_tot, (size_t)MAXG * NACC);
+      if (st == PSB_OK) st = dev_alloc(h, &h->d_cta_seq, (size_t)h->grid);
+      if (st != PSB_OK) return bail(st);
     }
   } else if (h->grid > 1) {
     // smallest per-CTA term count whose group-aligned split fits the grid
@@ -1302,7 +1332,7 @@ static void pin_host_range(psb_handle* h, const void* p, size_t bytes) {
 static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cudaStream_t stream, bool with_forces,
                                       psb_snapshot* out, int64_t* h2d_bytes, size_t* force_bytes) {
   const long long N = h->layout.natoms, rb = h->layout.real_bytes;
-  size_t b_pos = 0, b_vel = 0, b_frc = 0, b_ids = 0, b_img = 0, b_mass = 0, b_types = 0;
+  size_t b_pos = 0, b_vel = 0, b_frc = 0, b_ids = 0, b_img = 0, b_mass = 0, b_types = 0, b_tags = 0;
   switch (h->layout.layout) {
     case PSB_LAYOUT_HOOMD: b_pos = b_vel = b_frc = 4 * rb * N; b_ids = 4 * N; b_img = 12 * N; break;
     case PSB_LAYOUT_OPENMM_CUDA: b_pos = b_vel = 4 * rb * N; b_frc = 24 * N; b_ids = 4 * N; break;
@@ -1310,6 +1340,7 @@ static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cud
     default: b_pos = b_vel = b_frc = 3 * rb * N; b_ids = hs->ids ? 4 * N : 0; b_img = hs->images ? 12 * N : 0; b_mass = rb * N; break;
   }
   if (!h->layout.unwrap) b_img = 0;
+  if (h->tags_class && hs->tags) b_tags = 4 * N;
   if (!h->layout.need_momenta) b_vel = b_mass = b_types = 0;
   if (!h->have_staging) {
     psb_status st;
@@ -1323,7 +1354,8 @@ static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cud
     const void* f = nullptr;
     if (grab(b_pos, &h->dev_snap.positions) || grab(b_vel, &h->dev_snap.vel_mass) || grab(b_frc, &f) ||
         grab(b_ids, &h->dev_snap.ids) || grab(b_img, &h->dev_snap.images) ||
-        grab(b_mass, &h->dev_snap.masses) || grab(b_types, &h->dev_snap.types))
+        grab(b_mass, &h->dev_snap.masses) || grab(b_types, &h->dev_snap.types) ||
+        grab(h->tags_class ? 4 * (size_t)N : 0, &h->dev_snap.tags))
       return PSB_ERR_CUDA;
     h->dev_snap.forces = const_cast<void*>(f);
     h->have_staging = true;
@@ -1340,6 +1372,7 @@ static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cud
   };
   // one queue: a second copy stream did not shorten the step (measured: the link is the bound, 198 vs 203 us)
   CUDA_TRY(push(d.ids, hs->ids, b_ids));
+  if (b_tags) CUDA_TRY(push(d.tags, hs->tags, b_tags)); else d.tags = nullptr;
   CUDA_TRY(push(d.positions, hs->positions, b_pos));
   CUDA_TRY(push(d.images, hs->images, b_img));
   CUDA_TRY(push(d.vel_mass, hs->vel_mass, b_vel));

@@ -203,9 +203,10 @@ struct Model {
   StateDev st;
   Fin* fin;
   double* partials;           // ((MAXG+1) * NACC, gridDim) fp64
-  const uint8_t* tag_group;   // slot-ordered class on the OpenMM layout: tag -> group + 1 (0: not selected), (natoms)
+  const uint8_t* tag_group;   // slot-ordered class with a slot -> tag array (OpenMM ids, HOOMD tags): tag -> group + 1 (0: not selected), (natoms)
   ulonglong2* ll;             // (MAXG * NACC, gridDim) pass-A partials as two {32 data bits, 32-bit launch stamp} words
   int32_t ll_reduce;          // pass A exchanges its partials through `ll` (no counter barrier): see reduce_rows_ll
+  ulonglong2* ll_tot;         // slot-ordered classes: flagged row totals published by the row owners (MAXG * NACC)
   int32_t ll_pad;
   BarrierState* bars;         // (NBARS) monotonic arrival counters
   unsigned long long* epochs; // (NBARS) completed uses of each barrier
@@ -233,6 +234,7 @@ struct Snap {
   const void* images;
   const void* masses;
   const void* types;
+  const void* tags;  // HOOMD: slot -> tag (optional; class SC_TAGS)
   double L[3];
   double dt;
   double inv_dt;  // 1 / dt (host): the finite difference of abf.py:213 multiplies by it instead of dividing

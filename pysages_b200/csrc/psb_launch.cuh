@@ -48,9 +48,14 @@ const void* stream_entry() {
   if constexpr (L == PSB_LAYOUT_HOOMD) return (const void*)step_kernel<L, R, M, SC_STREAM>;
   else return (const void*)step_kernel<L, R, M, SC_SLOT>;
 }
+template <int L, typename R, int M>
+const void* tags_entry() {
+  if constexpr (L == PSB_LAYOUT_HOOMD) return (const void*)step_kernel<L, R, M, SC_TAGS>;
+  else return (const void*)step_kernel<L, R, M, SC_SLOT>;
+}
 #define PSB_STEP_ROW(L, R, M)                                                                     \
   {(const void*)step_kernel<L, R, M, SC_POINT>, (const void*)step_kernel<L, R, M, SC_GENERAL>,    \
-   (const void*)step_kernel<L, R, M, SC_SLOT>, stream_entry<L, R, M>()}
+   (const void*)step_kernel<L, R, M, SC_SLOT>, stream_entry<L, R, M>(), tags_entry<L, R, M>()}
 #define PSB_DEFINE_STEP_VTABLE(NAME, L, R)                                                          \
   static const void* const NAME##_entry[SM_COUNT][SC_COUNT] = {                                            \
       PSB_STEP_ROW(L, R, SM_UNBIASED), PSB_STEP_ROW(L, R, SM_HARMONIC), PSB_STEP_ROW(L, R, SM_METAD_DIRECT), \

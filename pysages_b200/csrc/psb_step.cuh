@@ -42,10 +42,13 @@ enum StepMethod { SM_UNBIASED = 0, SM_HARMONIC = 1, SM_METAD_DIRECT = 2, SM_ABF 
 // register and code footprint stay out of the latency-critical kernels.
 // SC_STREAM: the slot-ordered class with its streams moved by TMA bulk copies through a shared-memory ring, one CTA
 // per SM (psb_stream.cuh); HOOMD layout.
-enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_STREAM = 3, SC_COUNT = 4 };
+// SC_TAGS: the slot-ordered class when the engine also hands over its slot -> tag array (HOOMD `tag`,
+// psb_snapshot.tags): the group of a slot comes from a tag -> group table, pass 0 and its grid barrier disappear.
+enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_STREAM = 3, SC_TAGS = 4, SC_COUNT = 5 };
 #ifndef PSB_SLOT_CTAS
 #define PSB_SLOT_CTAS 2
 #endif
+constexpr int ROWG_ROWS = 16;  // rows per thread whose group the slot-ordered gather keeps for the scatter
 constexpr int SLOT_CTAS_PER_SM = PSB_SLOT_CTAS;  // streaming class: more resident warps, fewer registers
 
 // ---- small device utilities -----------------------------------------------------------------
@@ -150,6 +153,7 @@ struct StepShared {
   unsigned long long seq;           // launches of this handle before this one (Snap::cta_seq), LL stamp source
   uint64_t mbar[2];
   uint64_t full[NWARPS * STREAM_MAX_STAGES];  // SC_STREAM: one "stage filled" barrier per warp and ring stage
+  uint8_t rowg[ROWG_ROWS * BLOCK];            // slot-ordered classes: group + 1 of row r of thread t at [r * BLOCK + t]
   struct NetShared* net;           // ABF instantiations: force-model scratch (nullptr elsewhere)
 };
 // Force-model scratch of the ABF family (17 KB): only the ABF instantiations allocate it
@@ -296,21 +300,37 @@ __device__ __forceinline__ void reduce_rows_wide(const Model& M, StepShared& sh)
   const int nb = sh.vnb;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nrows = M.row_first[0][M.ngroups];
-  for (int r = warp; r < nrows; r += NWARPS) {
-    int g = 0;
-    while (r >= M.row_first[0][g + 1]) ++g;
-    const int dst = g * NACC + (r - M.row_first[0][g]);
-    const double* src = M.partials + (size_t)dst * nb;
-    double v = 0.0;
-    for (int b0 = lane; b0 < nb; b0 += 32 * WIDE_U) {
-      double a[WIDE_U];
+  // WIDE_R rows per warp at a time, every load of the batch issued before the first use: one L2 round trip for up to
+  // NWARPS * WIDE_R = 24 rows x 320 CTAs (four groups with momenta) instead of one per row
+  constexpr int WIDE_R = 3;
+  for (int r0 = warp; r0 < nrows; r0 += NWARPS * WIDE_R) {
+    int dst[WIDE_R];
+    double v[WIDE_R];
 #pragma unroll
-      for (int j = 0; j < WIDE_U; ++j) a[j] = (b0 + 32 * j < nb) ? __ldcg(src + b0 + 32 * j) : 0.0;
-#pragma unroll
-      for (int j = 0; j < WIDE_U; ++j) v += a[j];
+    for (int q = 0; q < WIDE_R; ++q) {
+      const int r = min(r0 + q * NWARPS, nrows - 1);
+      int g = 0;
+      while (r >= M.row_first[0][g + 1]) ++g;
+      dst[q] = g * NACC + (r - M.row_first[0][g]);
+      v[q] = 0.0;
     }
-    v = warp_sum(v);
-    if (lane == 0) (&sh.tot[0][0])[dst] = v;
+    for (int b0 = lane; b0 < nb; b0 += 32 * WIDE_U) {
+      double a[WIDE_R][WIDE_U];
+#pragma unroll
+      for (int q = 0; q < WIDE_R; ++q)
+#pragma unroll
+        for (int j = 0; j < WIDE_U; ++j)
+          a[q][j] = (r0 + q * NWARPS < nrows && b0 + 32 * j < nb) ? __ldcg(M.partials + (size_t)dst[q] * nb + b0 + 32 * j) : 0.0;
+#pragma unroll
+      for (int q = 0; q < WIDE_R; ++q)
+#pragma unroll
+        for (int j = 0; j < WIDE_U; ++j) v[q] += a[q][j];
+    }
+#pragma unroll
+    for (int q = 0; q < WIDE_R; ++q) {
+      const double t = warp_sum(v[q]);
+      if (lane == 0 && r0 + q * NWARPS < nrows) (&sh.tot[0][0])[dst[q]] = t;
+    }
   }
   __syncthreads();
 }
@@ -369,6 +389,55 @@ __device__ __forceinline__ void reduce_rows_ll(const Model& M, StepShared& sh, R
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     if (p.dst >= 0 && sub == 0) (&sh.tot[0][0])[p.dst] = v;
+  }
+}
+
+// Two-level LL exchange of the slot-ordered classes (hundreds of CTAs, up to 24 rows): if every CTA summed every row
+// itself, gridDim^2 x rows flagged words would cross the L2 (measured: 1.6 - 2.2 us behind a 1.5 us counter barrier).
+// Instead row r has ONE owner CTA (r * gridDim / rows: spread over the SMs); a warp of the owner polls the row's
+// gridDim flagged partials, adds them in the fixed order of reduce_rows_wide and publishes the total as a flagged
+// word; every CTA then polls the (<= 24) totals.  Two dependent L2 hops, no counter barrier, no fence.
+__device__ __forceinline__ void reduce_rows_ll2(const Model& M, StepShared& sh, uint32_t stamp) {
+  const int nb = sh.vnb, b = sh.vb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = M.row_first[0][M.ngroups];
+  const unsigned long long want = (unsigned long long)stamp << 32;
+  for (int r = warp; r < nrows; r += NWARPS) {
+    if ((int)(((long long)r * nb) / nrows) != b) continue;
+    int g = 0;
+    while (r >= M.row_first[0][g + 1]) ++g;
+    const int dst = g * NACC + (r - M.row_first[0][g]);
+    const ulonglong2* src = M.ll + (size_t)dst * nb;
+    double v = 0.0;
+    for (int b0 = lane; b0 < nb; b0 += 32 * WIDE_U) {
+      unsigned long long lo[WIDE_U], hi[WIDE_U];
+      bool ok;
+      do {
+#pragma unroll
+        for (int j = 0; j < WIDE_U; ++j) {
+          lo[j] = hi[j] = want;  // absent entries read as +0.0
+          if (b0 + 32 * j < nb) ll_load(src + b0 + 32 * j, lo[j], hi[j]);
+        }
+        ok = true;
+#pragma unroll
+        for (int j = 0; j < WIDE_U; ++j) ok = ok && (uint32_t)(lo[j] >> 32) == stamp && (uint32_t)(hi[j] >> 32) == stamp;
+      } while (!ok);
+#pragma unroll
+      for (int j = 0; j < WIDE_U; ++j) v += __longlong_as_double((long long)((lo[j] & 0xFFFFFFFFULL) | (hi[j] << 32)));
+    }
+    v = warp_sum(v);
+    if (lane == 0) ll_store(M.ll_tot + dst, v, stamp);
+  }
+  if ((int)threadIdx.x < nrows) {
+    const int r = threadIdx.x;
+    int g = 0;
+    while (r >= M.row_first[0][g + 1]) ++g;
+    const int dst = g * NACC + (r - M.row_first[0][g]);
+    unsigned long long lo, hi;
+    do {
+      ll_load(M.ll_tot + dst, lo, hi);
+    } while ((uint32_t)(lo >> 32) != stamp || (uint32_t)(hi >> 32) != stamp);
+    (&sh.tot[0][0])[dst] = __longlong_as_double((long long)((lo & 0xFFFFFFFFULL) | (hi << 32)));
   }
 }
 
@@ -1155,7 +1224,8 @@ template <int LAYOUT, typename Real, int METHOD, int CLASS>
 __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, const Snap& S, const int nb_arg, const int b_arg) {
   constexpr bool GENERAL = (CLASS == SC_GENERAL);
   constexpr bool STREAM = (CLASS == SC_STREAM);  // slot-ordered, streams staged by TMA (HOOMD layout only)
-  constexpr bool SLOT = (CLASS == SC_SLOT) || STREAM;
+  constexpr bool TAGS = (CLASS == SC_TAGS);      // slot-ordered, slot -> tag array from the engine (HOOMD layout only)
+  constexpr bool SLOT = (CLASS == SC_SLOT) || STREAM || TAGS;
   static_assert(!STREAM || LAYOUT == PSB_LAYOUT_HOOMD, "the TMA-staged streams are written for the HOOMD layout");
   using A = Access<LAYOUT, Real>;
   using FV = typename A::FV;
@@ -1298,9 +1368,10 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
   const bool skip_cv = WALK && !SLOT && (S.mode == MODE_WALKER_FINISH);  // CVs were evaluated by walker_begin
   const bool momenta_sums = S.need_momenta && abf_fast;
   constexpr bool slot_major = SLOT;  // the host picks this instantiation only for multi-CTA, non-walker handles
-  // slot-ordered class on the OpenMM layout: ids is slot -> atom (openmm.py:100-107), so the group of a slot
-  // comes from a tag -> group byte table and neither a tag -> slot inverse nor pass 0 is needed
-  constexpr bool TAGMAP = SLOT && (LAYOUT == PSB_LAYOUT_OPENMM_CUDA);
+  // slot-ordered class with a slot -> atom array (OpenMM: ids itself, openmm.py:100-107; HOOMD: the optional
+  // psb_snapshot.tags): the group of a slot comes from a tag -> group byte table and neither a tag -> slot inverse
+  // nor pass 0 is needed
+  constexpr bool TAGMAP = SLOT && (LAYOUT == PSB_LAYOUT_OPENMM_CUDA || TAGS);
   const bool will_scatter = (METHOD != SM_UNBIASED) &&
                             (S.mode == MODE_STEP || (WALK && S.mode == MODE_WALKER_FINISH));
 
@@ -1330,11 +1401,14 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
   const bool cached = !skip_cv && !slot_major && (nb == 1 || seg_g >= 0) && (hi - lo <= (uint32_t)(CT * BLOCK));
   // pass-A partials through the LL buffer (host: every CTA with a group is `cached`, nothing but the
   // partials crosses CTAs before the finalizer); grid-uniform
-  const bool ll = !GENERAL && !SLOT && !WALK && M.ll_reduce && nb > 1;
+  const bool ll = !GENERAL && !STREAM && !WALK && M.ll_reduce && nb > 1;  // slot-ordered classes: two-level (reduce_rows_ll2)
   const uint32_t ll_stamp = (uint32_t)(sh.seq + 1ULL);
   const int g_begin = (skip_cv || slot_major) ? 0 : (nb == 1 ? 0 : max(seg_g, 0));
   const int g_end = (skip_cv || slot_major) ? 0 : (nb == 1 ? M.ngroups : seg_g + 1);  // seg_g < 0: empty
   uint32_t stamp = 0, s_lo = 0, s_hi = 0;  // slot-major mode: launch stamp and this CTA's slot range
+  // slot-ordered classes: group + 1 of this thread's rows s_lo + tid + r * BLOCK is kept from the gather for the scatter
+  // (sh.rowg; valid while a CTA's slice has at most ROWG_ROWS rows per thread: no second look at the slot words then)
+  bool nib_ok = false;
   // slot-ordered class: groups whose CV is RadiusOfGyration (bit g); all others are point groups
   uint32_t rog_bits = 0;
   if (SLOT)
@@ -1342,7 +1416,7 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       if (M.cv[M.grp[g].cv].kind == PSB_CV_ROG) rog_bits |= 1u << g;
   auto slot_word = [&](uint32_t sl) -> uint32_t {  // stamp | group + 1 when slot `sl` holds a selected atom
     if constexpr (TAGMAP) {
-      const uint32_t tag = (uint32_t)__ldg(reinterpret_cast<const int*>(S.ids) + sl);
+      const uint32_t tag = (uint32_t)__ldg(reinterpret_cast<const int*>(TAGS ? S.tags : S.ids) + sl);
       const uint32_t g = tag < (uint32_t)M.natoms ? (uint32_t)__ldg(M.tag_group + tag) : 0u;
       return g ? (stamp | g) : 0u;
     } else {
@@ -1431,6 +1505,9 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
 #define PSB_SLOT_SUA 8
 #endif
     constexpr int SU = is_abf ? 4 : PSB_SLOT_SUA;  // momenta double the registers per row in flight
+    // (ABF only: its gather keeps 4 rows per thread in flight and has registers to spare; the 8-row gathers of the
+    // other methods sit at the 128-register limit of two CTAs per SM and would spill)
+    nib_ok = is_abf && (s_hi - s_lo) <= (uint32_t)ROWG_ROWS * BLOCK;
     for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
       uint32_t e[SU];
       V3 r[SU], p[SU];
@@ -1445,6 +1522,8 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       for (int u = 0; u < SU; ++u) {
         const bool hit = (base + u * BLOCK < s_hi) && ((e[u] & ~15u) == stamp);
         const int g = hit ? (int)(e[u] & 15u) - 1 : -1;
+        if constexpr (is_abf)
+          if (nib_ok) sh.rowg[base - s_lo + u * BLOCK] = (uint8_t)(g + 1);  // [row * BLOCK + tid]
 #pragma unroll
         const double rr = r[u].x * r[u].x + r[u].y * r[u].y + r[u].z * r[u].z;
 #pragma unroll
@@ -1569,7 +1648,8 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
         else __stcg(M.partials + (size_t)(seg_g * NACC + tid) * nb + b, sh.stage[tid]);
       }
     }
-    if (!ll) commit_pre();  // LL exchange: the prologue values are not needed before the reduction
+    const bool pre_early = !ll || (SLOT && !TAGMAP);  // pass 0's grid barrier needs the epochs
+    if (pre_early) commit_pre();  // LL exchange: the prologue values are not needed before the reduction
     // ---- slot-major gather (most atoms selected, too many to keep in registers) ---------------
     // A random tag -> slot permutation makes the tag-ordered gather pay one L1 tag lookup per
     // 16-byte row (measured: ~6 lookups per atom, 1 lookup/clk/SM -> 20 us per 1e6 atoms, far
@@ -1773,12 +1853,18 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       const int na = momenta_sums ? 6 : 3;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (g < M.ngroups) block_reduce_store(sh, acc4[g], na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+        if (g < M.ngroups) {
+          if (ll) block_reduce_store(sh, acc4[g], na, &sh.stage4[g][0], 1, false);
+          else block_reduce_store(sh, acc4[g], na, M.partials + (size_t)(g * NACC) * nb + b, nb, true);
+        }
     }
-    if (slot_major && TAGMAP) {  // gathered and block-reduced before the dependency wait (see above)
+    if (slot_major && (TAGMAP || (ll && !STREAM))) {  // TAGMAP: gathered and block-reduced before the dependency wait (see above)
       const int na = momenta_sums ? 6 : 3;
-      if (tid < 4 * 6 && tid / 6 < M.ngroups && tid % 6 < na)
-        __stcg(M.partials + (size_t)((tid / 6) * NACC + tid % 6) * nb + b, sh.stage4[tid / 6][tid % 6]);
+      if (tid < 4 * 6 && tid / 6 < M.ngroups && tid % 6 < na) {
+        const size_t at = (size_t)((tid / 6) * NACC + tid % 6) * nb + b;
+        if (ll) ll_store(M.ll + at, sh.stage4[tid / 6][tid % 6], ll_stamp);
+        else __stcg(M.partials + at, sh.stage4[tid / 6][tid % 6]);
+      }
     }
 
     // groups too large for the register cache (and not slot-ordered): gather loop, slots published
@@ -1808,8 +1894,9 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
     if (ll) {
       PSB_STAMP(2);
       PSB_CLK(8);
-      reduce_rows_ll(M, sh, planA, ll_stamp);
-      commit_pre();
+      if (SLOT) reduce_rows_ll2(M, sh, ll_stamp);
+      else reduce_rows_ll(M, sh, planA, ll_stamp);
+      if (!pre_early) commit_pre();
       __syncthreads();
     } else {
       grid_sync(M, sh, BAR_A);
@@ -2201,27 +2288,39 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
         };
         rs0 = scale_of(0); rs1 = scale_of(1); rs2 = scale_of(2); rs3 = scale_of(3);
       }
-      for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
-        uint32_t e[SU];
-        FV fv[SU];
-        V3 rp[SU];
+      // two copies of the loop: with the groups kept by the gather (sh.rowg) the only loads are the force rows
+      auto scatter_rows = [&](auto cached_groups) {
+        constexpr bool CG = decltype(cached_groups)::value;
+        for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
+          uint32_t e[SU];
+          FV fv[SU];
+          V3 rp[SU];
 #pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          const uint32_t sl = min(base + u * BLOCK, s_hi - 1);
-          e[u] = slot_word(sl);
-          fv[u] = A::load_force(S, sl);
-          rp[u] = rog_bits ? A::position(S, sl) : v3(0, 0, 0);
-        }
+          for (int u = 0; u < SU; ++u) {
+            const uint32_t sl = min(base + u * BLOCK, s_hi - 1);
+            if constexpr (CG) e[u] = (uint32_t)sh.rowg[min(base - s_lo + u * BLOCK, (uint32_t)(ROWG_ROWS * BLOCK - 1))];
+            else e[u] = slot_word(sl);
+            fv[u] = A::load_force(S, sl);
+            rp[u] = rog_bits ? A::position(S, sl) : v3(0, 0, 0);
+          }
 #pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          const uint32_t sl = base + u * BLOCK;
-          if (sl < s_hi && (e[u] & ~15u) == stamp) {
-            const int g = (int)(e[u] & 15u) - 1;
-            V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
-            if (rog_bits && ((rog_bits >> g) & 1u)) fo = (g == 0 ? rs0 : (g == 1 ? rs1 : (g == 2 ? rs2 : rs3))) * rp[u];
-            A::store_force(S, sl, fv[u], fo);
+          for (int u = 0; u < SU; ++u) {
+            const uint32_t sl = base + u * BLOCK;
+            const bool hit = CG ? (e[u] != 0u) : ((e[u] & ~15u) == stamp);
+            if (sl < s_hi && hit) {
+              const int g = (int)(e[u] & 15u) - 1;
+              V3 fo = v3(f.fg[g][0], f.fg[g][1], f.fg[g][2]);
+              if (rog_bits && ((rog_bits >> g) & 1u)) fo = (g == 0 ? rs0 : (g == 1 ? rs1 : (g == 2 ? rs2 : rs3))) * rp[u];
+              A::store_force(S, sl, fv[u], fo);
+            }
           }
         }
+      };
+      if constexpr (is_abf) {
+        if (nib_ok) scatter_rows(std::true_type{});
+        else scatter_rows(std::false_type{});
+      } else {
+        scatter_rows(std::false_type{});
       }
     } else if (all_unique && !dense) {
       if (cached) {
@@ -2330,7 +2429,7 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
 }
 
 template <int LAYOUT, typename Real, int METHOD, int CLASS>
-__global__ void __launch_bounds__(BLOCK, (CLASS == SC_SLOT) ? SLOT_CTAS_PER_SM : 2)
+__global__ void __launch_bounds__(BLOCK, (CLASS == SC_SLOT || CLASS == SC_TAGS) ? SLOT_CTAS_PER_SM : 2)
 step_kernel(const Model* __restrict__ Mglobal, const __grid_constant__ Snap S) {
   step_body<LAYOUT, Real, METHOD, CLASS>(Mglobal, S, (int)gridDim.x, (int)blockIdx.x);
 }

@@ -305,6 +305,11 @@ class NativeStep:
         N.check(self.lib.psb_set_force_series(self.handle, ctypes.byref(d), self._stream()))
         self._force_series = keep  # a device source must outlive the stream-ordered copy
 
+    @property
+    def wants_tags(self):
+        """True when snapshots that carry the engine's slot -> tag array step faster (psb_wants_tags)."""
+        return bool(self.lib.psb_wants_tags(self.handle))
+
     def launch_info(self):
         g, b, c, nbytes = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
         N.check(self.lib.psb_launch_info(self.handle, ctypes.byref(g), ctypes.byref(b), ctypes.byref(c),

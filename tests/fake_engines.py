@@ -75,6 +75,17 @@ def install_hoomd():
         def update(self, timestep):  # what the C++ integrator calls between the two half steps
             self.forward_data(self._update, self._location, self._mode, timestep)
 
+    def tags(sysview, location, mode):
+        # hoomd-dlext: ParticleData's slot -> tag array (the inverse of rtags; HOOMD keeps both current)
+        import torch
+
+        eng = sysview.engine
+        rt = eng.t["rtags"]
+        inv = torch.empty_like(rt)
+        inv[rt.long()] = torch.arange(rt.numel(), device=rt.device, dtype=rt.dtype)
+        eng.tags_calls = getattr(eng, "tags_calls", 0) + 1
+        return to_dlpack(inv)
+
     class CPU:
         pass
 
@@ -102,7 +113,7 @@ def install_hoomd():
     hoomd.md = _module("hoomd.md", HalfStepHook=type("HalfStepHook", (), {}))
     hoomd.device = _module("hoomd.device", CPU=CPU, GPU=GPU)
     hoomd.dlext = _module("hoomd.dlext", __version__="0.4.0", AccessLocation=AccessLocation, AccessMode=AccessMode,
-                          DLExtSampler=DLExtSampler, SystemView=SystemView)
+                          DLExtSampler=DLExtSampler, SystemView=SystemView, tags=tags)
     sys.modules.pop("pysages_b200.backends.hoomd", None)
     return Simulation
 

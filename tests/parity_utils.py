@@ -3,6 +3,8 @@ Shared harness of the GPU parity tests: builds the SAME collective variables / m
 oracle (CPU, torch-fp64 autodiff) and on pysages_b200 (CUDA, through the C ABI) from one spec,
 steps both over the same snapshots and compares every observable of the hot path.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -111,7 +113,12 @@ def device_snapshot(snap, device="cuda", positions=None):
     box = Box(snap["box_H"], snap["origin"])
     L = snap["layout"]
     if L == "hoomd":
-        return Snapshot(a["positions"], a["vel_mass"], a["forces"], a["rtags"], box, snap["dt"], dict(images=a["images"]))
+        extras = dict(images=a["images"])
+        if os.environ.get("PSB_TEST_TAGS") == "1":  # HOOMD's slot -> tag array (hoomd-dlext `tags`): inverse of rtags
+            rt = a["rtags"]
+            extras["tags"] = torch.empty_like(rt)
+            extras["tags"][rt.long()] = torch.arange(rt.numel(), device=rt.device, dtype=rt.dtype)
+        return Snapshot(a["positions"], a["vel_mass"], a["forces"], a["rtags"], box, snap["dt"], extras)
     if L == "openmm-cuda":
         return Snapshot(a["positions"], a["vel_mass"], a["forces"], a["ids"], box, snap["dt"])
     if L == "openmm-cpu":

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(native):
     for name in names:
         assert hasattr(lib, name), f"{name} is declared in include/pysages_b200.h but not exported"
     assert sorted(native.EXPORTS) == names, "pysages_b200/_native.py binds a different set than the header declares"
-    assert lib.psb_abi_version() == 1
+    assert lib.psb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(native, tmp_path):

@@ -68,18 +68,23 @@ def test_million_atoms_slot_ordered_kernels_against_oracle(method, monkeypatch):
     _, tagmajor = bench.build_ours(cv2, m2, snaps[0])
     monkeypatch.delenv("PSB_SLOT_MAJOR")
     _, slotmajor = bench.build_ours(cv2, m2, snaps[0])
+    _, slottags = bench.build_ours(cv2, m2, snaps[0])
+    assert slottags.wants_tags
+    rtag_only = bench.snapshots_of(frames, L2, 0.005, with_tags=False)  # the reference's five arrays, nothing else
     f0 = frames[0]["forces"].clone()
     outs = []
-    for native in (tagmajor, slotmajor):
+    for native, sn in ((tagmajor, rtag_only[0]), (slotmajor, rtag_only[0]), (slottags, snaps[0])):
         frames[0]["forces"].copy_(f0)
-        native.step(snaps[0])
-        native.step(snaps[0])
+        native.step(sn)
+        native.step(sn)
         torch.cuda.synchronize()
         outs.append((native.view("xi").cpu().numpy().copy(), native.view("cv_force").cpu().numpy().copy(),
                      frames[0]["forces"].cpu().numpy().copy()))
-    close(outs[1][0], outs[0][0], 1e-12, what="xi slot- vs tag-ordered")
-    close(outs[1][1], outs[0][1], 1e-9, what="generalized force slot- vs tag-ordered")
-    assert np.abs(outs[1][2] - outs[0][2]).max() <= 2e-7 * np.abs(outs[0][2]).max()
+    for i, what in ((1, "slot-"), (2, "slot- (engine's slot -> tag array)")):
+        close(outs[i][0], outs[0][0], 1e-12, what=f"xi {what} vs tag-ordered")
+        close(outs[i][1], outs[0][1], 1e-9, what=f"generalized force {what} vs tag-ordered")
+        assert np.abs(outs[i][2] - outs[0][2]).max() <= 2e-7 * np.abs(outs[0][2]).max()
+    close(outs[2][0], outs[1][0], 1e-13, what="xi with vs without the tags array")
     assert np.abs(outs[0][2] - f0.cpu().numpy()).max() > 0  # the bias was applied
 
 

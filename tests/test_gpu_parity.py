@@ -16,18 +16,22 @@ from pysages_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "grid24", "slot-major"])
+@pytest.fixture(autouse=True, params=["auto", "grid24", "slot-major", "slot-tags"])
 def launch_shape(request, monkeypatch):
     """Every parity case runs twice: with the library's own launch shape (one CTA for the small
     test snapshots) and forced onto 24 cooperative CTAs (group-aligned CTAs, grid barrier, per-CTA
     partials, redundant finalizer, register-cached scatter) and, third, with the slot-ordered
-    gather / scatter forced on (used for very large selections; point CVs with <= 4 groups)."""
+    gather / scatter forced on (used for very large selections; point CVs with <= 4 groups); fourth, the same
+    with HOOMD's slot -> tag array in the snapshot (psb_snapshot.tags: no tag -> slot inversion pass)."""
     monkeypatch.delenv("PSB_GRID_BLOCKS", raising=False)
     monkeypatch.delenv("PSB_SLOT_MAJOR", raising=False)
-    if request.param in ("grid24", "slot-major"):
+    monkeypatch.delenv("PSB_TEST_TAGS", raising=False)
+    if request.param in ("grid24", "slot-major", "slot-tags"):
         monkeypatch.setenv("PSB_GRID_BLOCKS", "24")
-    if request.param == "slot-major":  # slot-ordered gather / scatter wherever the handle is eligible for it
+    if request.param in ("slot-major", "slot-tags"):  # slot-ordered gather / scatter wherever the handle is eligible for it
         monkeypatch.setenv("PSB_SLOT_MAJOR", "1")
+    if request.param == "slot-tags":
+        monkeypatch.setenv("PSB_TEST_TAGS", "1")
     return request.param
 
 LAYOUTS = [

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
-for wl, natoms in (("harmonic", 1_000_000),):
+for wl, natoms in (("harmonic", 1_000_000), ("abf2d", 1_000_000)):
     frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
     snaps = bench.snapshots_of(frames, L, 0.005)
     cvs, m = bench.workload_specs(wl, natoms, L)
