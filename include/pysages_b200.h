@@ -373,6 +373,25 @@ psb_status psb_lm_fit(const psb_lm_problem* problem, psb_lm_workspace** ws, void
 psb_status psb_lm_result(psb_lm_workspace* ws, int32_t* iters, double* cost, float* mu, int32_t* loops, void* cuda_stream);
 void psb_lm_destroy(psb_lm_workspace* ws);
 
+/* SpectralABF refit (spectral_abf.py:216-219 + approxfun/core.py:232-258) in two kernels, stream-ordered:
+ * out[0] = scale (largest population standard deviation of the mean-force components over the grid, 1 if zero),
+ * out[1 .. nterms] = pinv . ((Fsum / max(hist, 1) [- mean, periodic grids]) / scale).  All pointers are device
+ * pointers; `pinv` is the (nterms, npoints * k) pseudo-inverse of the gradient Vandermonde matrix (row-major, built
+ * once by the host layer), `work` holds npoints * k doubles. */
+typedef struct {
+  int64_t npoints;    /* grid points */
+  int32_t k;          /* force components per point */
+  int32_t nterms;     /* rows of pinv = coefficients */
+  int32_t periodic;   /* 1: remove the mean of every component (Fourier basis) */
+  int32_t reserved;
+  const void* hist;   /* (npoints) uint32 */
+  const double* Fsum; /* (npoints, k) */
+  const double* pinv; /* (nterms, npoints * k) */
+  double* out;        /* (1 + nterms) */
+  double* work;       /* (npoints * k) */
+} psb_series_fit_desc;
+psb_status psb_series_fit(const psb_series_fit_desc* desc, void* cuda_stream);
+
 int64_t psb_launch_count(psb_handle* h);
 /* 1 when the last psb_run_cycle replayed a CUDA graph, 0 when it issued plain launches. */
 int32_t psb_cycle_uses_graph(psb_handle* h);

@@ -141,6 +141,21 @@ class SnapshotDesc(Structure):
     ]
 
 
+class SeriesFitDesc(Structure):
+    _fields_ = [
+        ("npoints", c_int64),
+        ("k", c_int32),
+        ("nterms", c_int32),
+        ("periodic", c_int32),
+        ("reserved", c_int32),
+        ("hist", c_void_p),
+        ("Fsum", c_void_p),
+        ("pinv", c_void_p),
+        ("out", c_void_p),
+        ("work", c_void_p),
+    ]
+
+
 class LmProblem(Structure):
     _fields_ = [
         ("n_dense", c_int32),
@@ -203,9 +218,10 @@ EXPORTS = {
     "psb_lm_destroy": (None, [c_void_p]),
     "psb_abi_version": (c_int32, []),
     "psb_wants_tags": (c_int32, [c_void_p]),
+    "psb_series_fit": (c_int32, [POINTER(SeriesFitDesc), c_void_p]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpysages_b200.so")
+LIB_PATH = os.environ.get("PSB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpysages_b200.so")  # PSB_LIB: A/B runs of two builds on one box
 _lib = None
 
 

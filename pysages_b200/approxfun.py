@@ -77,9 +77,12 @@ class SpectralGradientFit:
         return self.grid.is_periodic
 
 
-def build_fitter(model, device):
-    """approxfun/core.py:232-258 on `device`: dy (*grid.shape, dims) -> tensor [scale, coefficients...]."""
-    pinv = torch.as_tensor(model.pinv, dtype=torch.float64, device=device)
+def build_fitter(model, device, force_host=False):
+    """approxfun/core.py:232-258 on `device`: dy (*grid.shape, dims) -> tensor [scale, coefficients...].
+    On a CUDA device `fit.from_state(hist, Fsum)` runs the whole refit (mean force, normalisation, projection) in two
+    hand-written kernels (psb_series_fit, csrc/psb_refit.cu), stream-ordered; `fit(dy)` is the torch form of the same."""
+    device = torch.device(device)
+    pinv = torch.as_tensor(model.pinv, dtype=torch.float64, device=device).contiguous()
     axes = tuple(range(model.grid.shape.size))
     periodic = model.is_periodic
 
@@ -90,4 +93,38 @@ def build_fitter(model, device):
         dy = (dy - dy.mean(dim=axes)) / std if periodic else dy / std
         return torch.cat([std.reshape(1), pinv @ dy.reshape(-1)])
 
+    def from_state_host(hist, Fsum):
+        h = hist.to(torch.float64).reshape(*Fsum.shape[:-1], 1)
+        return fit(Fsum / torch.clamp(h, min=1.0))
+
+    fit.native = device.type == "cuda" and not force_host
+    if not fit.native:
+        fit.from_state = from_state_host
+        return fit
+
+    import ctypes
+
+    from . import _native as N
+
+    lib = N.load()
+    keep = {}
+
+    def from_state(hist, Fsum):
+        k = int(Fsum.shape[-1])
+        npoints = int(Fsum.numel() // k)
+        if hist.dtype not in (torch.int32, torch.uint32) or Fsum.dtype != torch.float64 or not Fsum.is_contiguous() \
+                or not hist.is_contiguous() or pinv.shape[1] != npoints * k:
+            return from_state_host(hist, Fsum)
+        out = torch.empty(1 + pinv.shape[0], dtype=torch.float64, device=device)
+        work = keep.get("work")
+        if work is None or work.numel() < npoints * k:
+            work = keep["work"] = torch.empty(npoints * k, dtype=torch.float64, device=device)
+        d = N.SeriesFitDesc()
+        d.npoints, d.k, d.nterms, d.periodic = npoints, k, int(pinv.shape[0]), int(bool(periodic))
+        d.hist, d.Fsum, d.pinv, d.out, d.work = hist.data_ptr(), Fsum.data_ptr(), pinv.data_ptr(), out.data_ptr(), work.data_ptr()
+        with torch.cuda.device(device):
+            N.check(lib.psb_series_fit(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        return out
+
+    fit.from_state = from_state
     return fit

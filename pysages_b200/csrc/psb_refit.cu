@@ -561,6 +561,76 @@ __global__ void lm_init(Control* ctl, float mu0, float c, float mu_min, float mu
   ctl->cost_count = 0;
 }
 
+
+// ---- SpectralABF refit (spectral_abf.py:216-219, approxfun/core.py:232-258) ---------------------------------------
+// dy = Fsum / max(hist, 1); scale = max over components of the population standard deviation over the grid (1 if 0);
+// periodic grids also remove the mean; coefficients = pinv (gradient Vandermonde matrix, built once on the host) . dy.
+// series_normalize: ONE CTA (the data is a grid's worth of numbers), two passes for the variance, fixed-order sums.
+// series_project: one CTA per coefficient, 256 lanes striding over the (point, component) columns, fixed-order tree.
+__global__ void __launch_bounds__(1024) series_normalize(const uint32_t* __restrict__ hist, const double* __restrict__ Fsum,
+                                                         long long npoints, int k, int periodic, double* __restrict__ dyn,
+                                                         double* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double s_mean[PSB_MAX_K], s_var[PSB_MAX_K];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto block_sum = [&](double v) -> double {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    return t;
+  };
+  for (int c = 0; c < k; ++c) {
+    double a = 0.0;
+    for (long long p = tid; p < npoints; p += 1024) a += Fsum[p * k + c] / (double)max(hist[p], 1u);
+    const double mean = block_sum(a) / (double)npoints;
+    double q = 0.0;
+    for (long long p = tid; p < npoints; p += 1024) {
+      const double d = Fsum[p * k + c] / (double)max(hist[p], 1u) - mean;
+      q += d * d;
+    }
+    const double var = block_sum(q) / (double)npoints;
+    if (tid == 0) { s_mean[c] = mean; s_var[c] = var; }
+  }
+  __syncthreads();
+  double std = 0.0;
+  for (int c = 0; c < k; ++c) std = fmax(std, sqrt(s_var[c]));
+  if (std == 0.0) std = 1.0;
+  if (tid == 0) out[0] = std;
+  for (long long i = tid; i < npoints * k; i += 1024) {
+    const long long p = i / k;
+    const int c = (int)(i % k);
+    const double v = Fsum[i] / (double)max(hist[p], 1u);
+    dyn[i] = (periodic ? v - s_mean[c] : v) / std;
+  }
+}
+
+__global__ void __launch_bounds__(256) series_project(const double* __restrict__ pinv, const double* __restrict__ dyn,
+                                                      long long ncols, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* row = pinv + (size_t)blockIdx.x * ncols;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  long long j = tid;
+  for (; j + 3 * 256 < ncols; j += 4 * 256) {
+    a0 = fma(row[j], dyn[j], a0);
+    a1 = fma(row[j + 256], dyn[j + 256], a1);
+    a2 = fma(row[j + 512], dyn[j + 512], a2);
+    a3 = fma(row[j + 768], dyn[j + 768], a3);
+  }
+  for (; j < ncols; j += 256) a0 = fma(row[j], dyn[j], a0);
+  double v = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[1 + blockIdx.x] = t;
+  }
+}
+
 }  // namespace psb_refit
 
 using namespace psb_refit;
@@ -698,6 +768,17 @@ psb_status psb_lm_result(psb_lm_workspace* ws, int32_t* iters, double* cost, flo
   if (cost) *cost = c.C_prev;
   if (mu) *mu = c.mu;
   if (loops) *loops = c.total_loops;
+  return PSB_OK;
+}
+
+psb_status psb_series_fit(const psb_series_fit_desc* d, void* cuda_stream) {
+  if (!d || !d->hist || !d->Fsum || !d->pinv || !d->out || !d->work) return psbi_fail(PSB_ERR_VALUE, "psb_series_fit: NULL argument");
+  if (d->npoints < 1 || d->k < 1 || d->k > PSB_MAX_K || d->nterms < 1) return psbi_fail(PSB_ERR_VALUE, "psb_series_fit: empty problem or too many components");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  series_normalize<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint32_t*>(d->hist), d->Fsum, d->npoints, d->k, d->periodic, d->work, d->out);
+  series_project<<<d->nterms, 256, 0, stream>>>(d->pinv, d->work, d->npoints * d->k, d->out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return psbi_fail(PSB_ERR_CUDA, cudaGetErrorString(e));
   return PSB_OK;
 }
 

@@ -1232,8 +1232,7 @@ class SpectralABF(GriddedSamplingMethod):
             native.set_force_series(kind, model.exponents, values, predict_after=fit_threshold, oob_zero=True)
 
         def refit():  # spectral_abf.py:216-219 on the state as it is before this step's sample is added
-            hist = native.view("hist", gshape).to(torch.float64).unsqueeze(-1)
-            return fit(native.view("Fsum", (*gshape, k)) / torch.clamp(hist, min=1.0))
+            return fit.from_state(native.view("hist", gshape), native.view("Fsum", (*gshape, k)))
 
         def make_state():
             bias = native.view("bias", (native.natoms, 3)) if native.dense_outputs else None

@@ -66,6 +66,35 @@ def test_hoomd_adapter():
     assert not adapter.CONTEXTS_SAMPLERS
 
 
+def test_hoomd_adapter_hands_over_the_slot_to_tag_array(monkeypatch):
+    """Most of the system selected -> the slot-ordered class: the sampler fetches hoomd-dlext's `tags` (slot -> tag)
+    each step and the kernel skips its tag -> slot inversion pass; same bias as with the reference's five arrays."""
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "1")
+    monkeypatch.setenv("PSB_GRID_BLOCKS", "24")
+    n = 6000
+    snap = synthetic.make_snapshot(n, layout="hoomd", dtype=np.float32, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=NSTEPS, step=0.05)
+
+    def bias():
+        return ps.methods.HarmonicBias([ps.colvars.Distance([list(range(0, n // 2)), list(range(n // 2, n))])], 50.0, [1.0])
+
+    eng0 = mock.MockEngine(snap["layout"], snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda", trajectory=traj)
+    ref = ps.run(bias(), lambda **kw: eng0, NSTEPS)  # rtags only
+    torch.cuda.synchronize()
+    Simulation = fake_engines.install_hoomd()
+    eng = fake_engines.engine(snap, "cuda", traj)
+    res = ps.run(bias(), lambda **kw: Simulation(eng), NSTEPS)
+    torch.cuda.synchronize()
+    from pysages_b200.backends import hoomd as adapter
+    sampler = next(iter(adapter.CONTEXTS_SAMPLERS.values()))
+    assert sampler._want_tags and eng.tags_calls >= NSTEPS
+    np.testing.assert_allclose(res.states[0].xi.cpu().numpy(), ref.states[0].xi.cpu().numpy(), rtol=1e-13)
+    f, f0 = eng.t["forces"].cpu().numpy(), eng0.t["forces"].cpu().numpy()
+    assert np.abs(f - f0).max() <= 2e-7 * np.abs(f0).max()
+    assert np.abs(f0 - snap["arrays"]["forces"]).max() > 0
+    adapter.detach(next(iter(adapter.CONTEXTS_SAMPLERS)))
+
+
 @pytest.mark.parametrize("layout, device", [("openmm-cuda", "cuda"), ("openmm-cpu", "cpu")])
 def test_openmm_adapter(layout, device):
     snap = synthetic.make_snapshot(400, layout=layout, dtype=np.float64, seed=6)

@@ -107,3 +107,33 @@ def test_gradient_and_sobolev_losses_and_sirens_stay_on_the_host_path():
     assert not ml.build_fitting_function(model, ml.LevenbergMarquardt(loss=ml.Sobolev1SSE())).native
     siren = ml.Siren(1, 1, (8,), [-1.0], [1.0])
     assert not ml.build_fitting_function(siren, ml.LevenbergMarquardt()).native
+
+
+@pytest.mark.parametrize("shape, periodic", [((32,), True), ((24, 20), True), ((16,), False), ((12, 10), False)])
+def test_series_fit_kernels_against_the_torch_form(shape, periodic):
+    """psb_series_fit (SpectralABF refit: mean force, normalisation, projection on the pseudo-inverse) against
+    approxfun.build_fitter's torch implementation of approxfun/core.py:232-258 on the same state."""
+    import pysages_b200 as ps
+    from pysages_b200 import approxfun
+    from pysages_b200.grids import Chebyshev, Grid, convert
+
+    d = len(shape)
+    if periodic:
+        grid = ps.Grid(lower=(-np.pi,) * d, upper=(np.pi,) * d, shape=shape, periodic=True)
+    else:
+        grid = convert(ps.Grid(lower=(0.0,) * d, upper=(2.0,) * d, shape=shape), Grid[Chebyshev])
+    model = approxfun.SpectralGradientFit(grid)
+    rng = np.random.default_rng(7)
+    dev = torch.device("cuda")
+    hist = torch.as_tensor(rng.integers(0, 40, size=shape).astype(np.int32), device=dev)
+    Fsum = torch.as_tensor(rng.normal(size=(*shape, d)) * 50.0 + 3.0, device=dev)
+    native = approxfun.build_fitter(model, dev)
+    host = approxfun.build_fitter(model, dev, force_host=True)
+    assert native.native and not host.native
+    a, b = native.from_state(hist, Fsum), host.from_state(hist, Fsum)
+    torch.cuda.synchronize()
+    assert a.shape == b.shape == (1 + model.pinv.shape[0],)
+    assert abs(float(a[0] - b[0])) <= 1e-13 * abs(float(b[0]))
+    assert float((a[1:] - b[1:]).abs().max()) <= 1e-12 * float(b[1:].abs().max())
+    zero = native.from_state(torch.zeros_like(hist), torch.zeros_like(Fsum))  # spectral_abf.py:178: scale 1, zero series
+    assert float(zero[0]) == 1.0 and float(zero[1:].abs().max()) == 0.0
