@@ -13,6 +13,16 @@ __global__ void zc_write(const float4* __restrict__ src, float4* __restrict__ ds
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// read-modify-write of 16-byte rows of mapped host memory, in place: coalesced (perm == nullptr) or through a permutation
+__global__ void zc_rmw(float4* __restrict__ rows, const int* __restrict__ perm, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = perm ? (size_t)perm[i] : i;
+    float4 v = rows[r];
+    v.x += 1.0f; v.y += 1.0f; v.z += 1.0f;
+    rows[r] = v;
+  }
+}
+
 int main() {
   const size_t up = 6400000, down = 1600000;
   char *h_up, *h_down, *d_up, *d_down;
@@ -65,6 +75,22 @@ int main() {
   timeit("kernel read 6.4 MB (148) then kernel write 1.6 MB (148)", [&] {
     zc_read<<<148, 256, 0, s0>>>((const float4*)m_up, (float4*)d_up, up / 16);
     zc_write<<<148, 256, 0, s0>>>((const float4*)d_down, (float4*)m_down, down / 16); }, up + down);
+  {
+    const size_t n = down / 16;
+    int* hperm = (int*)malloc(n * sizeof(int));
+    for (size_t i = 0; i < n; ++i) hperm[i] = (int)i;
+    unsigned long long st = 88172645463325252ULL;
+    for (size_t i = n - 1; i > 0; --i) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; size_t j = st % (i + 1); int t = hperm[i]; hperm[i] = hperm[j]; hperm[j] = t; }
+    int* dperm; CK(cudaMalloc(&dperm, n * sizeof(int)));
+    CK(cudaMemcpy(dperm, hperm, n * sizeof(int), cudaMemcpyHostToDevice));
+    for (int grid : {148, 296}) {
+      char name[112];
+      snprintf(name, sizeof name, "kernel RMW 1.6 MB of mapped host rows in place, coalesced, %d CTAs", grid);
+      timeit(name, [&] { zc_rmw<<<grid, 256, 0, s0>>>((float4*)m_down, nullptr, n); }, 2 * down);
+      snprintf(name, sizeof name, "kernel RMW 1.6 MB of mapped host rows in place, random rows, %d CTAs", grid);
+      timeit(name, [&] { zc_rmw<<<grid, 256, 0, s0>>>((float4*)m_down, dperm, n); }, 2 * down);
+    }
+  }
   // latency of one synchronous round trip (what psb_step_host pays per step on top of the bytes)
   {
     CK(cudaDeviceSynchronize());
