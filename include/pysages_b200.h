@@ -176,6 +176,10 @@ typedef struct {
   int32_t need_momenta; /* "momenta" in method.snapshot_flags (abf.py:114) */
   int32_t dense_outputs; /* 1: also keep the reference's dense state.bias (N,3) and J (k,3N) */
   int32_t ntypes;        /* LAMMPS: entries of the per-type mass array (ntypes + 1) */
+  int32_t has_tags;      /* HOOMD: the engine will hand over psb_snapshot.tags (slot -> tag) with every snapshot: the
+                            slot-ordered class is then planned for it (one CTA per SM, so that the next step's gather --
+                            engine arrays only -- overlaps this step's tail; chosen from ~1.5e5 selected atoms upward) */
+  int32_t reserved;
 } psb_layout_desc;
 
 /* Device pointers of one snapshot (backends/snapshot.py:34-46).  Unused ones may be NULL. */

@@ -123,6 +123,8 @@ class LayoutDesc(Structure):
         ("need_momenta", c_int32),
         ("dense_outputs", c_int32),
         ("ntypes", c_int32),
+        ("has_tags", c_int32),
+        ("reserved", c_int32),
     ]
 
 

@@ -119,9 +119,9 @@ class Sampler(C.SamplerCore, *_BASES):
             base.__init__(self)
         _dlext.DLExtSampler.__init__(self, self.view, self.on_half_step, location, AccessMode.Read)
         self._last = None
-        self._want_tags = False
+        self._want_tags = _tags_of is not None  # the snapshot the method is built on says so (psb_layout_desc.has_tags)
         self._bind_method(sampling_method, C.LAYOUTS["hoomd"], callback)
-        self._want_tags = _tags_of is not None and self._native.wants_tags
+        self._want_tags = _tags_of is not None and self._native.wants_tags  # per step: only if the handle uses them
 
     # ---- plugin callbacks: (positions, vel_mass, rtags, images, forces, timestep) -----------------
     def on_half_step(self, positions, vel_mass, rtags, images, forces, timestep):

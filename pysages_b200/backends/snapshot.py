@@ -125,6 +125,8 @@ def describe_layout(snapshot, layout, unwrap, need_momenta, dense_outputs=False)
     if layout.kind == N.LAYOUT_LAMMPS and isinstance(snapshot.vel_mass, tuple):
         masses = snapshot.vel_mass[1][0]
         d.ntypes = 0 if masses is None else int(masses.numel())
+    # HOOMD snapshots that carry the slot -> tag array: the handle is planned for it (psb_layout_desc.has_tags)
+    d.has_tags = int(layout.kind == N.LAYOUT_HOOMD and bool(snapshot.extras) and snapshot.extras.get("tags") is not None)
     return d
 
 

@@ -726,7 +726,14 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   {
     const bool eligible = h->grid > 1 && (!h->step_general || slot_kinds) && !method->shared_hills && ng <= 4 &&
                           layout->natoms < 0xFFFFFFF0LL;
-    bool wanted = (long long)M.T > (long long)CT * BLOCK * h->grid && 2LL * M.T >= layout->natoms;
+    // HOOMD with the engine's slot -> tag array announced (psb_layout_desc.has_tags): the slot-ordered class needs no
+    // inversion pass, its gather runs before the dependency wait, and with ONE CTA per SM the next step's CTAs are
+    // co-resident, so that gather overlaps this step's exchange, finalizer and scatter (measured, ABF: 2e5 atoms 17.2 ->
+    // 10.0 us, 1e6 atoms 28.0 -> 24.2 us against two CTAs per SM).  Worth it as soon as the register cache of one
+    // CTA per SM is too small.
+    const bool tags_hint = layout->has_tags && layout->layout == PSB_LAYOUT_HOOMD &&
+                           !(getenv("PSB_NO_TAGS") && atoi(getenv("PSB_NO_TAGS")) != 0);
+    bool wanted = (long long)M.T > (long long)CT * BLOCK * (tags_hint ? h->num_sms : h->grid) && 2LL * M.T >= layout->natoms;
     // OpenMM-CUDA: `ids` already IS slot -> atom, so the slot-ordered passes need no tag -> slot inverse at
     // all (the reference's per-step ids.argsort(), openmm.py:106-107, and our inverse-permutation launch
     // disappear); worth it as soon as a fair share of the system is selected
@@ -740,9 +747,10 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         M.slot_major = 0;
       } else if (!getenv("PSB_GRID_BLOCKS")) {
         h->grid = std::min(occ_slot, SLOT_CTAS_PER_SM) * h->num_sms;  // streaming: fill the machine
-        // OpenMM layout, moderate sizes: one CTA per SM leaves room for the NEXT step's CTAs, whose gather runs
-        // before their dependency wait (psb_step.cuh), i.e. under this step's finalizer and scatter
-        if (omm && layout->natoms <= 8LL * BLOCK * h->num_sms) h->grid = h->num_sms;
+        // OpenMM layout: one CTA per SM leaves room for the NEXT step's CTAs, whose gather runs before their
+        // dependency wait (psb_step.cuh), i.e. under this step's finalizer and scatter (1e6 atoms, ABF: 44.0 -> 39.3 us)
+        if (omm) h->grid = h->num_sms;
+        if (tags_hint) h->grid = h->num_sms;
       } else if ((long long)occ_slot * h->num_sms < h->grid) {
         M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
       }

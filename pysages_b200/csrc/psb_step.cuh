@@ -48,7 +48,7 @@ enum StepClass { SC_POINT = 0, SC_GENERAL = 1, SC_SLOT = 2, SC_STREAM = 3, SC_TA
 #ifndef PSB_SLOT_CTAS
 #define PSB_SLOT_CTAS 2
 #endif
-constexpr int ROWG_ROWS = 16;  // rows per thread whose group the slot-ordered gather keeps for the scatter
+constexpr int ROWG_ROWS = 32;  // rows per thread whose group the slot-ordered gather keeps for the scatter
 constexpr int SLOT_CTAS_PER_SM = PSB_SLOT_CTAS;  // streaming class: more resident warps, fewer registers
 
 // ---- small device utilities -----------------------------------------------------------------

@@ -67,10 +67,11 @@ def test_million_atoms_slot_ordered_kernels_against_oracle(method, monkeypatch):
     monkeypatch.setenv("PSB_SLOT_MAJOR", "0")
     _, tagmajor = bench.build_ours(cv2, m2, snaps[0])
     monkeypatch.delenv("PSB_SLOT_MAJOR")
-    _, slotmajor = bench.build_ours(cv2, m2, snaps[0])
-    _, slottags = bench.build_ours(cv2, m2, snaps[0])
-    assert slottags.wants_tags
     rtag_only = bench.snapshots_of(frames, L2, 0.005, with_tags=False)  # the reference's five arrays, nothing else
+    _, slotmajor = bench.build_ours(cv2, m2, rtag_only[0])  # planned without the tag array: two CTAs per SM
+    _, slottags = bench.build_ours(cv2, m2, snaps[0])       # planned for it: one CTA per SM, gathers overlap
+    assert slottags.wants_tags
+    assert slotmajor.launch_info()["grid_blocks"] == 2 * slottags.launch_info()["grid_blocks"]
     f0 = frames[0]["forces"].clone()
     outs = []
     for native, sn in ((tagmajor, rtag_only[0]), (slotmajor, rtag_only[0]), (slottags, snaps[0])):

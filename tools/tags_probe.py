@@ -4,8 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
-for wl, natoms in (("harmonic", 1_000_000), ("abf2d", 1_000_000)):
-    frames, L, _ = bench.device_hoomd_frames(natoms, 8, dev, seed=1)
+cases = [(c.split(":")[0], int(c.split(":")[1])) for c in sys.argv[1:]] or [("harmonic", 1_000_000), ("abf2d", 1_000_000)]
+for wl, natoms in cases:
+    frames, L, _ = bench.device_hoomd_frames(natoms, 8 if natoms > 200_000 else 64, dev, seed=1)
     for with_tags in (False, True):
         snaps = bench.snapshots_of(frames, L, 0.005, with_tags)
         cvs, m = bench.workload_specs(wl, natoms, L)
