@@ -750,7 +750,11 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         // OpenMM layout: one CTA per SM leaves room for the NEXT step's CTAs, whose gather runs before their
         // dependency wait (psb_step.cuh), i.e. under this step's finalizer and scatter (1e6 atoms, ABF: 44.0 -> 39.3 us)
         if (omm) h->grid = h->num_sms;
-        if (tags_hint) h->grid = h->num_sms;
+        // (not with RadiusOfGyration groups: their scatter streams the positions a second time, the part behind the
+        // dependency wait dominates and wants all 16 warps per SM -- measured 29.2 us at two CTAs per SM, 36.6 at one)
+        bool rog_groups = false;
+        for (int c = 0; c < ncvs; ++c) rog_groups = rog_groups || cvs[c].kind == PSB_CV_ROG;
+        if (tags_hint && !rog_groups) h->grid = h->num_sms;
       } else if ((long long)occ_slot * h->num_sms < h->grid) {
         M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
       }
