@@ -293,3 +293,35 @@ def test_cfg4_bench_generator_1e5_hills_through_a_deposit_against_numpy():
             close(native.view("heights").cpu().numpy()[idx0], heights[idx0], 1e-15, what="deposited height")
             close(native.view("centers", (-1, 2)).cpu().numpy()[idx0], centers[idx0], 1e-10, what="deposited centre")
     assert int(native.view("ncalls").item()) == md["stride"] + 2
+
+
+def test_slot_ordered_handle_takes_snapshots_with_and_without_the_tag_array(monkeypatch):
+    """A handle planned for HOOMD's slot -> tag array also steps snapshots that lack it (the reference's five arrays):
+    the two slot-ordered instantiations alternate on one handle -- same grid, same flag stamps -- and the trajectory of
+    ABF states equals that of a handle that never saw the array."""
+    import bench
+
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "1")
+    monkeypatch.setenv("PSB_GRID_BLOCKS", "24")
+    n = 40_000
+    dev = torch.device("cuda:0")
+    frames, L, _ = bench.device_hoomd_frames(n, 6, dev, seed=21)
+    with_tags = bench.snapshots_of(frames, L, 0.005, with_tags=True)
+    without = bench.snapshots_of(frames, L, 0.005, with_tags=False)
+    cvs, m = bench.workload_specs("abf2d", n, L)
+    f0 = [f["forces"].clone() for f in frames]
+    outs = []
+    for pattern in ("mixed", "never"):
+        for f, f_init in zip(frames, f0):
+            f["forces"].copy_(f_init)
+        _, native = bench.build_ours(cvs, m, with_tags[0] if pattern == "mixed" else without[0])
+        assert native.launch_info()["grid_blocks"] == 24 and native.wants_tags
+        for i in range(6):
+            native.step(with_tags[i] if (pattern == "mixed" and i % 2 == 0) else without[i])
+        torch.cuda.synchronize()
+        outs.append((native.view("xi").cpu().numpy().copy(), native.view("hist").cpu().numpy().copy(),
+                     native.view("Fsum").cpu().numpy().copy(), np.stack([f["forces"].cpu().numpy() for f in frames])))
+    close(outs[0][0], outs[1][0], 1e-13, what="xi")
+    assert np.array_equal(outs[0][1], outs[1][1])
+    close(outs[0][2], outs[1][2], 1e-10, what="Fsum")
+    assert np.abs(outs[0][3] - outs[1][3]).max() <= 2e-7 * np.abs(outs[1][3]).max()
