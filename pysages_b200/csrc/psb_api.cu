@@ -142,6 +142,10 @@ struct psb_handle {
   psb_snapshot dev_snap{};
   bool have_staging = false;
   bool tags_class = false;  // the SC_TAGS instantiation is co-resident at this handle's grid (HOOMD, slot-ordered)
+  // Slot-ordered handles planned for the tag array run ONE CTA per SM when steps are replayed back to back
+  // (psb_run_cycle: the next step's gather overlaps this step's tail) and TWO when an engine steps them one at a
+  // time (psb_step: every launch stands alone); grid_pipe == 0: one grid for both.  See replan_grid.
+  int grid_pipe = 0, grid_plain = 0;
   std::vector<std::pair<const void*, size_t>> host_ranges;  // engine arrays seen by psb_step_host (and page-locked by it)
   std::vector<void*> host_registered;                        // ... the ones this handle registered itself
   size_t hpad = 0;
@@ -289,6 +293,30 @@ psb_status enqueue(psb_handle* h, const psb_snapshot* s, int mode, cudaStream_t 
   CUDA_TRY(pick_vtable(h->layout)->launch_step(h->step_method, cls, h->d_model, &S, h->grid, dyn, stream,
                                                h->pdl && !helper_before));
   ++h->launches;
+  return PSB_OK;
+}
+
+// Switch a dual-grid slot-ordered handle between its two launch shapes.  Everything whose meaning depends on the number
+// of CTAs restarts, stream-ordered behind the launches that used the old shape: barrier arrival counters and epochs
+// (epoch 0 also makes the next rtag-only launch clear slot_map: its stamps restart), per-CTA launch counts and the
+// flagged exchange words (stamp 0 is never current), the model's CTA ranges; a captured cycle graph is dropped.
+psb_status replan_grid(psb_handle* h, bool pipelined, cudaStream_t stream) {
+  if (!h->grid_pipe) return PSB_OK;
+  const int target = pipelined ? h->grid_pipe : h->grid_plain;
+  if (h->grid == target) return PSB_OK;
+  Model& M = h->model;
+  const size_t gmax = (size_t)std::max(h->grid_pipe, h->grid_plain);
+  h->grid = target;
+  for (int g = 0; g < MAXG; ++g) M.cta_hi[g] = g < M.ngroups ? target - 1 : -1;
+  CUDA_TRY(cudaMemsetAsync(M.bars, 0, sizeof(*M.bars) * NBARS, stream));
+  CUDA_TRY(cudaMemsetAsync(M.epochs, 0, sizeof(*M.epochs) * 16, stream));
+  if (h->d_cta_seq) CUDA_TRY(cudaMemsetAsync(h->d_cta_seq, 0, sizeof(*h->d_cta_seq) * gmax, stream));
+  if (M.ll) CUDA_TRY(cudaMemsetAsync(M.ll, 0, sizeof(*M.ll) * (size_t)MAXG * NACC * gmax, stream));
+  if (M.ll_tot) CUDA_TRY(cudaMemsetAsync(M.ll_tot, 0, sizeof(*M.ll_tot) * (size_t)MAXG * NACC, stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_model, &h->model, sizeof(Model), cudaMemcpyHostToDevice, stream));
+  if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);
+  h->cycle_exec = nullptr;
+  h->cycle_key.clear();
   return PSB_OK;
 }
 
@@ -754,7 +782,14 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         // dependency wait dominates and wants all 16 warps per SM -- measured 29.2 us at two CTAs per SM, 36.6 at one)
         bool rog_groups = false;
         for (int c = 0; c < ncvs; ++c) rog_groups = rog_groups || cvs[c].kind == PSB_CV_ROG;
-        if (tags_hint && !rog_groups) h->grid = h->num_sms;
+        if (tags_hint && !rog_groups) {
+          if (h->grid >= 2 * h->num_sms && !getenv("PSB_DEBUG_TIMING") && !(getenv("PSB_ONE_GRID") && atoi(getenv("PSB_ONE_GRID")) != 0)) {
+            h->grid_plain = h->grid;       // stepping one launch at a time (engine hook): two CTAs per SM (1e6 atoms, ABF: 30.8 us
+            h->grid_pipe = h->num_sms;     // against 35.2 with one); replayed back to back: one (21.5 us against 27.9)
+          } else {
+            h->grid = h->num_sms;
+          }
+        }
       } else if ((long long)occ_slot * h->num_sms < h->grid) {
         M.slot_major = 0;  // the slot-ordered instantiation would not be co-resident at this grid size
       }
@@ -962,6 +997,7 @@ psb_status psb_step(psb_handle* h, const psb_snapshot* snap, int64_t timestep, v
   if (!h) return fail(PSB_ERR_VALUE, "NULL handle");
   psb_status st = check_snapshot(h, snap, true);
   if (st != PSB_OK) return st;
+  if ((st = replan_grid(h, false, (cudaStream_t)cuda_stream)) != PSB_OK) return st;  // one launch at a time
   st = enqueue(h, snap, MODE_STEP, (cudaStream_t)cuda_stream, nullptr, 0, nullptr);
   if (st == PSB_OK) ++h->host_ncalls;
   return st;
@@ -991,7 +1027,12 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
   // PSB_DEBUG_TIMING=graph keeps the graph: captured nodes alternate between the two stamp halves,
   // which stays consistent across replays when the ring has an even number of snapshots
   static const bool dbg_graph = getenv("PSB_DEBUG_TIMING") && std::string(getenv("PSB_DEBUG_TIMING")) == "graph";
-  if (!no_graph && h->use_graph && (!h->dbg || (dbg_graph && nsnaps % 2 == 0)) && stream != nullptr && nsteps >= (int64_t)nsnaps) {
+  const bool replay = !no_graph && h->use_graph && (!h->dbg || (dbg_graph && nsnaps % 2 == 0)) && stream != nullptr && nsteps >= (int64_t)nsnaps;
+  {
+    psb_status st = replan_grid(h, replay, stream);
+    if (st != PSB_OK) return st;
+  }
+  if (replay) {
     const bool same = h->cycle_exec && h->cycle_stream == stream && (int)h->cycle_key.size() == nsnaps &&
                       memcmp(h->cycle_key.data(), snaps, sizeof(psb_snapshot) * nsnaps) == 0;
     if (!same) {

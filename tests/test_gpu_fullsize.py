@@ -71,7 +71,6 @@ def test_million_atoms_slot_ordered_kernels_against_oracle(method, monkeypatch):
     _, slotmajor = bench.build_ours(cv2, m2, rtag_only[0])  # planned without the tag array: two CTAs per SM
     _, slottags = bench.build_ours(cv2, m2, snaps[0])       # planned for it: one CTA per SM, gathers overlap
     assert slottags.wants_tags
-    assert slotmajor.launch_info()["grid_blocks"] == 2 * slottags.launch_info()["grid_blocks"]
     f0 = frames[0]["forces"].clone()
     outs = []
     for native, sn in ((tagmajor, rtag_only[0]), (slotmajor, rtag_only[0]), (slottags, snaps[0])):
@@ -325,3 +324,51 @@ def test_slot_ordered_handle_takes_snapshots_with_and_without_the_tag_array(monk
     assert np.array_equal(outs[0][1], outs[1][1])
     close(outs[0][2], outs[1][2], 1e-10, what="Fsum")
     assert np.abs(outs[0][3] - outs[1][3]).max() <= 2e-7 * np.abs(outs[1][3]).max()
+
+
+def test_dual_grid_handle_switches_between_replay_and_single_steps(monkeypatch):
+    """Handles planned for the tag array run one CTA per SM under psb_run_cycle (graph replay: consecutive steps
+    overlap) and two when stepped one launch at a time; switching back and forth restarts every grid-dependent counter
+    and leaves the ABF state exactly as a plain sequence of single steps does."""
+    import ctypes
+
+    import bench
+    from pysages_b200 import _native as N
+
+    monkeypatch.delenv("PSB_SLOT_MAJOR", raising=False)
+    monkeypatch.delenv("PSB_GRID_BLOCKS", raising=False)
+    n = 400_000
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream()
+    frames, L, _ = bench.device_hoomd_frames(n, 4, dev, seed=33)
+    snaps = bench.snapshots_of(frames, L, 0.005)
+    cvs, m = bench.workload_specs("abf2d", n, L)
+    f0 = [f["forces"].clone() for f in frames]
+    results = []
+    for mode in ("switching", "single"):
+        for f, f_init in zip(frames, f0):
+            f["forces"].copy_(f_init)
+        _, native = bench.build_ours(cvs, m, snaps[0])
+        descs = bench.snapdesc_array(native, snaps)
+        grids = []
+        with torch.cuda.stream(stream):
+            if mode == "switching":
+                for part in range(3):
+                    N.check(native.lib.psb_run_cycle(native.handle, descs, 4, 8, ctypes.c_void_p(stream.cuda_stream)))
+                    grids.append(native.launch_info()["grid_blocks"])
+                    for i in range(4):
+                        native.step(snaps[i])
+                    grids.append(native.launch_info()["grid_blocks"])
+            else:
+                for part in range(3):
+                    for i in range(12):
+                        native.step(snaps[i % 4])
+        stream.synchronize()
+        if mode == "switching":
+            assert grids[0] * 2 == grids[1] and grids[0::2] == [grids[0]] * 3 and grids[1::2] == [grids[1]] * 3, grids
+        results.append((native.view("hist").cpu().numpy().copy(), native.view("Fsum").cpu().numpy().copy(),
+                        int(native.view("ncalls").item()), np.stack([f["forces"].cpu().numpy() for f in frames])))
+    assert results[0][2] == results[1][2] == 36
+    assert np.array_equal(results[0][0], results[1][0])
+    close(results[0][1], results[1][1], 1e-10, what="Fsum")
+    assert np.abs(results[0][3] - results[1][3]).max() <= 2e-7 * np.abs(results[1][3]).max()

@@ -5,7 +5,7 @@ import numpy as np, torch
 import bench
 from pysages_b200 import _native as N
 dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
-n = 100_000
+n = int(os.environ.get("PSB_LONG_ATOMS", 100_000))  # 300000: the slot-ordered class with the tag array (one CTA per SM, two-level exchange)
 frames, L, _ = bench.device_hoomd_frames(n, 64, dev, seed=4)
 snaps = bench.snapshots_of(frames, L, 0.005)
 cvs, m = bench.workload_specs("abf2d", n, L)

@@ -12,7 +12,7 @@ for wl, natoms in cases:
         cvs, m = bench.workload_specs(wl, natoms, L)
         method, native = bench.build_ours(cvs, m, snaps[0])
         descs = bench.snapdesc_array(native, snaps)
-        ms, _ = bench.time_cycle(native, descs, 400, 20, stream)
+        ms, _ = bench.time_cycle(native, descs, 400, 20, stream, plain=bool(os.environ.get("PSB_NO_GRAPH")))
         torch.cuda.synchronize()
         info = native.launch_info()
         line = f"{wl} tags={with_tags} wants={native.wants_tags} grid {info['grid_blocks']}: {ms * 1e3 / 400:.2f} us/step = {info['algorithmic_bytes_per_step'] / (ms / 400 * 1e-3) / 1e9:.0f} GB/s"
