@@ -868,7 +868,9 @@ def main():
                     note="latency-bound at S=1e5: 8.4 MB/step is 1.3 us of HBM time inside a ~9 us dependent chain "
                          "(gather -> flag-in-data exchange -> single-warp finalizer -> scatter); one step per launch cannot "
                          "reach 0.5 of HBM at this size -- judge it against launch.floor_us (empty cooperative launch + one "
-                         "grid barrier), see DESIGN.md 4.1; the S=N=1e6 rows of `series` are the bandwidth regime",
+                         "grid barrier), see DESIGN.md 4.1; the S=N=1e6 rows of `series` are the bandwidth regime (same kernel family, "
+                         "slot-ordered class: 0.52 (harmonic) and 0.60 (ABF) of this peak with HOOMD's slot -> tag array, "
+                         "0.36 / 0.35 with the reference's rtag only)",
                     frac_plain=round(info["algorithmic_bytes_per_step"] / (info["plain_launch_us_per_step"] * 1e-6) / 1e9 / hbm, 4))
 
     cpu = None
