@@ -137,3 +137,24 @@ def test_series_fit_kernels_against_the_torch_form(shape, periodic):
     assert float((a[1:] - b[1:]).abs().max()) <= 1e-12 * float(b[1:].abs().max())
     zero = native.from_state(torch.zeros_like(hist), torch.zeros_like(Fsum))  # spectral_abf.py:178: scale 1, zero series
     assert float(zero[0]) == 1.0 and float(zero[1:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("topology, iters", [((5,), 1), ((5,), 4), ((8, 8), 2)])
+def test_native_lm_against_the_oracle_restatement(topology, iters):
+    """psb_lm_fit against oracle/ml.py:lm_fit (numpy / scipy restatement of ml/optimizers.py:188-232 with the float32
+    residual and damping conventions of the reference): parameters, cost and damping after the first iterations."""
+    from oracle import ml as oml
+
+    lower, upper = np.array([-1.0, 0.5]), np.array([2.0, 3.0])
+    g = np.stack(np.meshgrid(np.linspace(-0.9, 1.9, 9), np.linspace(0.6, 2.9, 8), indexing="ij"), -1).reshape(-1, 2)
+    y = np.stack([np.sin(g[:, 0]) * g[:, 1], np.cos(g[:, 1]) + 0.3 * g[:, 0]], -1)
+    model = ml.MLP(2, 2, topology, lower, upper, seed=11)
+    hist = []
+    po = oml.lm_fit(model.parameters, model.widths, g, y, lower, upper, reg=1e-6, max_iters=iters, history=hist)
+    fit = ml.build_fitting_function(model, ml.LevenbergMarquardt(reg=ml.L2Regularization(1e-6), max_iters=iters))
+    dev = torch.device("cuda")
+    pn = fit(torch.as_tensor(model.parameters, device=dev), torch.as_tensor(g, device=dev), torch.as_tensor(y, device=dev))
+    it, cost, mu, loops = fit.workspace.result()
+    assert fit.native and loops == len(hist) and mu == np.float32(hist[-1][2])
+    np.testing.assert_allclose(pn.cpu().numpy(), po, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(cost, hist[-1][1], rtol=1e-6)
