@@ -372,3 +372,43 @@ def test_dual_grid_handle_switches_between_replay_and_single_steps(monkeypatch):
     assert np.array_equal(results[0][0], results[1][0])
     close(results[0][1], results[1][1], 1e-10, what="Fsum")
     assert np.abs(results[0][3] - results[1][3]).max() <= 2e-7 * np.abs(results[1][3]).max()
+
+
+@pytest.mark.parametrize("method", ["harmonic", "abf2d"])
+def test_openmm_slot_ordered_class_at_full_grid_against_tag_ordered(method, monkeypatch):
+    """OpenMM-CUDA layout, 3e5 atoms, the library's own launch shape (one CTA per SM, two-level flagged exchange,
+    gather before the dependency wait): same CVs, generalized forces and fixed-point force updates as the tag-ordered
+    class, over several steps of graph replay and single launches."""
+    import ctypes
+
+    import bench
+    from pysages_b200 import _native as N
+
+    monkeypatch.delenv("PSB_GRID_BLOCKS", raising=False)
+    n = 300_000
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream()
+    snaps, L = bench.device_layout_snapshots("openmm-cuda", np.float32, n, 4, dev, seed=44)
+    cvs, m = bench.workload_specs(method, n, L)
+    f0 = [s.forces.clone() for s in snaps]
+    outs = []
+    for slot in ("0", "1"):
+        monkeypatch.setenv("PSB_SLOT_MAJOR", slot)
+        for s, f in zip(snaps, f0):
+            s.forces.copy_(f)
+        _, native = bench.build_ours(cvs, m, snaps[0], layout="openmm-cuda")
+        descs = bench.snapdesc_array(native, snaps)
+        with torch.cuda.stream(stream):
+            N.check(native.lib.psb_run_cycle(native.handle, descs, 4, 8, ctypes.c_void_p(stream.cuda_stream)))
+            for i in range(4):
+                native.step(snaps[i])
+        stream.synchronize()
+        outs.append((native.view("xi").cpu().numpy().copy(), native.view("cv_force").cpu().numpy().copy(),
+                     np.stack([s.forces.cpu().numpy() for s in snaps]), native.launch_info()["grid_blocks"]))
+    assert outs[1][3] == torch.cuda.get_device_properties(0).multi_processor_count  # slot-ordered: one CTA per SM
+    close(outs[1][0], outs[0][0], 1e-12, what="xi slot- vs tag-ordered")
+    close(outs[1][1], outs[0][1], 1e-9, what="generalized force slot- vs tag-ordered")
+    moved = np.abs(outs[0][2].astype(np.float64) - np.stack([f.cpu().numpy() for f in f0]).astype(np.float64)).max()
+    assert moved > 0
+    # int64 fixed point (2^-32): the two classes add the same twelve biases per atom up to a few units in the last place
+    assert np.abs(outs[1][2].astype(np.float64) - outs[0][2].astype(np.float64)).max() <= max(8.0, 1e-9 * moved)
