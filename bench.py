@@ -547,12 +547,13 @@ def run_series(device, stream, hbm, fp64_peak=None):
 
     for name, natoms, steps, sorted_tags in (("harmonic", 10_000, 2000, False), ("harmonic", 100_000, 2000, False),
                                              ("harmonic", 1_000_000, 500, False), ("abf2d", 10_000, 2000, False),
+                                             ("abf2d", 300_000, 1000, False),
                                              ("abf2d", 1_000_000, 500, False), ("abf2d", 100_000, 2000, True),
                                              ("abf2d", 1_000_000, 500, True)):
-        nfr = 64 if natoms <= 100_000 else 8
+        nfr = 64 if natoms <= 100_000 else (16 if natoms <= 300_000 else 8)
         frames, L, _ = device_hoomd_frames(natoms, nfr, device, seed=20240 + natoms % 977, sorted_tags=sorted_tags)
         measure(f"{name} S=N={natoms} hoomd-f32" + (" (identity rtag)" if sorted_tags else ""), name, natoms, steps, frames, L)
-        if natoms == 1_000_000 and not sorted_tags:  # the same without HOOMD's slot -> tag array: tag -> slot inversion pass in the kernel
+        if natoms >= 300_000 and not sorted_tags:  # the same without HOOMD's slot -> tag array: tag -> slot inversion pass in the kernel
             measure(f"{name} S=N={natoms} hoomd-f32 (rtag only)", name, natoms, steps, frames, L, with_tags=False)
         del frames
 
