@@ -883,6 +883,20 @@ def main():
 
     series = [] if (args.no_series or world > 1) else run_series(device, stream, hbm, fp64_peak)
 
+    # the same host-resident system with a SMALL selection (the usual case of a CPU engine: a solute's CVs in solvent):
+    # psb_step_host ships the rows of the selected atoms only
+    e2e_small = None
+    if not args.no_e2e and world == 1:
+        small = ([("Distance", ([list(range(0, 50)), list(range(50, 100))],), {}),
+                  ("Distance", ([list(range(100, 150)), list(range(150, 200))],), {})], workload_specs("abf2d", natoms, L)[1])
+        _, nat_small = build_ours(small[0], small[1], snapshots_of(frames[:1], L, dt)[0])
+        r, up, down = time_e2e(nat_small, frames[0], L, dt, e2e_steps, 3, stream)
+        e2e_small = dict(workload=f"ABF, 2x Distance over 4 groups of 50 atoms (S=200) in N={natoms} host-resident atoms",
+                         value=round(r, 1), unit=UNIT, us_per_step=round(1e6 / r, 1), h2d_bytes_per_step=up,
+                         d2h_bytes_per_step=down, whole_array_bytes_per_step=h2d + d2h,
+                         path="psb_step_host, selected rows: host gather -> one pinned block up -> step -> force rows back -> host scatter")
+        del nat_small
+
     line = dict(metric=METRIC, value=round(value, 1), value_pipelined=round(value, 1), value_plain=round(value_plain, 1),
                 unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
@@ -890,7 +904,7 @@ def main():
                 e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          steps=e2e_steps, gbs_effective=round((h2d + d2h) * e2e_value / max(world, 1) / 1e9, 2),
                          path="psb_step_host (the engine's host arrays, page-locked in place by the library -> H2D -> step -> D2H forces -> sync)"),
-                api_us_per_step=api,
+                e2e_selected_rows=e2e_small, api_us_per_step=api,
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, launch=info, series=series,
                 multi_gpu=multi)
     print(json.dumps(line))

@@ -223,7 +223,10 @@ psb_status psb_run_cycle(psb_handle* h, const psb_snapshot* snaps, int32_t nsnap
                          void* cuda_stream);
 
 /* Same step with HOST snapshot buffers (engine running on the CPU, bias on the GPU): copies
- * the arrays the method needs to the device, steps, copies forces back, and synchronises. */
+ * the arrays the method needs to the device, steps, copies forces back, and synchronises.
+ * When the CVs touch few atoms (8 * selected <= natoms) only the rows of those atoms travel: gathered on the host
+ * into one pinned block, one transfer up, the force rows back in one transfer and written to their slots (a copy on
+ * the host, no arithmetic); the byte counters report what actually moved. */
 psb_status psb_step_host(psb_handle* h, const psb_snapshot* host_snap, int64_t timestep,
                          void* cuda_stream, int64_t* h2d_bytes, int64_t* d2h_bytes);
 /* psb_step_host page-locks the engine's host arrays in place the first time it sees them (cudaHostRegister: a

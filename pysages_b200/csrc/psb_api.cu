@@ -149,6 +149,13 @@ struct psb_handle {
   std::vector<std::pair<const void*, size_t>> host_ranges;  // engine arrays seen by psb_step_host (and page-locked by it)
   std::vector<void*> host_registered;                        // ... the ones this handle registered itself
   size_t hpad = 0;
+  // psb_step_host with S << N: only the rows of the selected atoms travel (see stage_selected_rows)
+  std::vector<uint32_t> sel_tags;       // sorted unique tags of every atom a CV touches
+  bool compact_ok = false;              // worth it and valid for this handle (decided in psb_create)
+  const void* d_ids_compact = nullptr;  // device: tag -> row of the compact arrays (the layout's own `ids` convention)
+  char* pin = nullptr;                  // pinned host staging: [positions | images | velocities | types-or-masses | forces] rows
+  size_t pin_bytes = 0;
+  std::vector<uint32_t> sel_slots;      // this step's engine slots of sel_tags
 };
 
 namespace {
@@ -340,6 +347,7 @@ void psb_destroy(psb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->host_registered) cudaHostUnregister(p);
+  if (h->pin) cudaFreeHost(h->pin);
   if (h->cycle_exec) cudaGraphExecDestroy(h->cycle_exec);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
@@ -439,6 +447,11 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
   M.k = k;
   M.ngroups = ng;
   M.T = (uint32_t)term_tag.size();
+  {
+    h->sel_tags = term_tag;
+    std::sort(h->sel_tags.begin(), h->sel_tags.end());
+    h->sel_tags.erase(std::unique(h->sel_tags.begin(), h->sel_tags.end()), h->sel_tags.end());
+  }
 
   // ---- method validation -----------------------------------------------------------------------
   MethodDev& m = M.m;
@@ -949,6 +962,13 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     }
     if (getenv("PSB_NO_CONST_JJT")) M.jjt_const = 0;
   }
+  // host-resident engines (psb_step_host): when few atoms are selected only their rows travel
+  {
+    const bool valid = !M.slot_major && !layout->dense_outputs && layout->layout != PSB_LAYOUT_OPENMM_CUDA;
+    bool wanted = 8LL * (long long)h->sel_tags.size() <= layout->natoms;
+    if (const char* env = getenv("PSB_HOST_COMPACT")) wanted = atoi(env) != 0;
+    h->compact_ok = valid && wanted;
+  }
   h->cooperative = h->grid > 1;
   if (h->cooperative) {
     int coop = 0;
@@ -1438,11 +1458,134 @@ static psb_status stage_host_snapshot(psb_handle* h, const psb_snapshot* hs, cud
   return PSB_OK;
 }
 
+// ---- psb_step_host with S << N: selected rows only ----------------------------------------------------------------
+// A CPU engine with a handful of CV atoms (a peptide's dihedrals in 1e5 atoms of solvent) should not ship its whole
+// arrays over PCIe every step.  The rows of the selected atoms are gathered on the host into ONE pinned block
+// [positions | images | velocities | types or inverse masses | forces] (a copy, no arithmetic), go up in ONE transfer
+// into a device block of the same shape, the kernels run on that compact snapshot -- `ids` replaced by a static
+// tag -> compact row table in the layout's own convention, so no kernel knows the difference -- and the force rows
+// come back in one transfer and are written to their slots.
+struct CompactGeom {
+  size_t pos, img, vel, extra, frc;          // bytes per row (0: array not needed)
+  size_t o_pos, o_img, o_vel, o_extra, o_frc, total;  // offsets of the segments for Su rows
+};
+static CompactGeom compact_geom(const psb_handle* h, const psb_snapshot* hs) {
+  CompactGeom g{};
+  const size_t rb = (size_t)h->layout.real_bytes, Su = h->sel_tags.size();
+  switch (h->layout.layout) {
+    case PSB_LAYOUT_HOOMD: g.pos = g.vel = g.frc = 4 * rb; g.img = 12; break;
+    case PSB_LAYOUT_LAMMPS: g.pos = g.vel = g.frc = 24; g.img = 4; g.extra = 4; break;           // extra: per-atom types
+    default: g.pos = g.vel = g.frc = 3 * rb; g.img = hs->images ? 12 : 0; g.extra = rb; break;   // extra: inverse masses
+  }
+  if (!h->layout.unwrap) g.img = 0;
+  if (!h->layout.need_momenta) g.vel = g.extra = 0;
+  auto seg = [&](size_t row, size_t& off, size_t& cursor) { off = cursor; cursor += (row * Su + 255) & ~(size_t)255; };
+  size_t c = 0;
+  seg(g.pos, g.o_pos, c); seg(g.img, g.o_img, c); seg(g.vel, g.o_vel, c); seg(g.extra, g.o_extra, c);
+  const size_t up = c;
+  seg(g.frc, g.o_frc, c);
+  (void)up;
+  g.total = c;
+  return g;
+}
+
+static psb_status stage_selected_rows(psb_handle* h, const psb_snapshot* hs, cudaStream_t stream, bool with_forces,
+                                      psb_snapshot* out, int64_t* h2d_bytes, CompactGeom* geom) {
+  const int L = h->layout.layout;
+  const size_t Su = h->sel_tags.size(), N = (size_t)h->layout.natoms;
+  const CompactGeom g = compact_geom(h, hs);
+  if (!h->have_staging) {  // device block + static tag -> compact row table, pinned host block
+    char* block = nullptr;
+    psb_status st = dev_alloc(h, &block, g.total, false);
+    if (st != PSB_OK) return st;
+    std::vector<int32_t> table(N + 1, 0);  // LAMMPS indexes the map at tag + 1
+    for (size_t u = 0; u < Su; ++u) table[h->sel_tags[u] + (L == PSB_LAYOUT_LAMMPS ? 1 : 0)] = (int32_t)u;
+    int32_t* d_table = nullptr;
+    if ((st = dev_upload(h, &d_table, table)) != PSB_OK) return st;
+    h->d_ids_compact = d_table;
+    if (cudaMallocHost(&h->pin, g.total) != cudaSuccess) return fail(PSB_ERR_CUDA, "cannot allocate pinned staging memory");
+    h->pin_bytes = g.total;
+    h->dev_snap = psb_snapshot{};
+    h->dev_snap.positions = block + g.o_pos;
+    h->dev_snap.images = g.img ? block + g.o_img : nullptr;
+    h->dev_snap.vel_mass = g.vel ? block + g.o_vel : nullptr;
+    h->dev_snap.forces = block + g.o_frc;
+    h->dev_snap.ids = d_table;
+    if (L == PSB_LAYOUT_LAMMPS) {
+      h->dev_snap.types = g.extra ? block + g.o_extra : nullptr;
+      if (g.extra) {
+        char* m = nullptr;
+        if ((st = dev_alloc(h, &m, 8 * (size_t)std::max(h->layout.ntypes, 1), false)) != PSB_OK) return st;
+        h->dev_snap.masses = m;
+      }
+    } else if (L == PSB_LAYOUT_PLAIN3) {
+      h->dev_snap.masses = g.extra ? block + g.o_extra : nullptr;
+    }
+    h->sel_slots.resize(Su);
+    h->have_staging = true;
+  }
+  // engine slots of the selected atoms, then the row copies
+  const int32_t* ids = reinterpret_cast<const int32_t*>(hs->ids);
+  for (size_t u = 0; u < Su; ++u) {
+    const uint32_t tag = h->sel_tags[u];
+    uint32_t slot = tag;
+    if (L == PSB_LAYOUT_LAMMPS) slot = (uint32_t)ids[tag + 1];
+    else if (ids) slot = (uint32_t)ids[tag];
+    if (slot >= N) return fail(PSB_ERR_VALUE, "snapshot.ids maps atom %u outside the arrays", tag);
+    h->sel_slots[u] = slot;
+  }
+  auto gather = [&](const void* src, size_t row, size_t off) {
+    if (!row || !src) return;
+    const char* s = reinterpret_cast<const char*>(src);
+    char* d = h->pin + off;
+    for (size_t u = 0; u < Su; ++u) memcpy(d + u * row, s + (size_t)h->sel_slots[u] * row, row);
+  };
+  gather(hs->positions, g.pos, g.o_pos);
+  gather(hs->images, g.img, g.o_img);
+  gather(hs->vel_mass, g.vel, g.o_vel);
+  gather(L == PSB_LAYOUT_LAMMPS ? hs->types : hs->masses, g.extra, g.o_extra);
+  if (with_forces) gather(hs->forces, g.frc, g.o_frc);
+  char* block = reinterpret_cast<char*>(const_cast<void*>(h->dev_snap.positions)) - g.o_pos;
+  const size_t up = with_forces ? g.total : g.o_frc;
+  CUDA_TRY(cudaMemcpyAsync(block, h->pin, up, cudaMemcpyHostToDevice, stream));
+  int64_t moved = (int64_t)up;
+  if (L == PSB_LAYOUT_LAMMPS && g.extra && hs->masses) {
+    const size_t mb = 8 * (size_t)std::max(h->layout.ntypes, 1);
+    CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(h->dev_snap.masses), hs->masses, mb, cudaMemcpyHostToDevice, stream));
+    moved += (int64_t)mb;
+  }
+  psb_snapshot d = h->dev_snap;
+  memcpy(d.box_diag, hs->box_diag, sizeof(d.box_diag));
+  d.dt = hs->dt;
+  d.tags = nullptr;
+  *out = d;
+  if (h2d_bytes) *h2d_bytes = moved;
+  *geom = g;
+  return PSB_OK;
+}
+
 psb_status psb_step_host(psb_handle* h, const psb_snapshot* hs, int64_t timestep, void* cuda_stream,
                          int64_t* h2d_bytes, int64_t* d2h_bytes) {
   if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   psb_snapshot d;
+  if (h->compact_ok) {
+    psb_status st = check_snapshot(h, hs, true);
+    if (st != PSB_OK) return st;
+    CompactGeom g{};
+    const bool biased = h->method.kind != PSB_METHOD_UNBIASED;
+    if ((st = stage_selected_rows(h, hs, stream, biased, &d, h2d_bytes, &g)) != PSB_OK) return st;
+    if ((st = psb_step(h, &d, timestep, cuda_stream)) != PSB_OK) return st;
+    const size_t down = biased ? g.frc * h->sel_tags.size() : 0;
+    if (down) CUDA_TRY(cudaMemcpyAsync(h->pin + g.o_frc, d.forces, down, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (down) {
+      char* f = reinterpret_cast<char*>(hs->forces);
+      for (size_t u = 0; u < h->sel_tags.size(); ++u) memcpy(f + (size_t)h->sel_slots[u] * g.frc, h->pin + g.o_frc + u * g.frc, g.frc);
+    }
+    if (d2h_bytes) *d2h_bytes = (int64_t)down;
+    return PSB_OK;
+  }
   size_t b_frc = 0;
   psb_status st = stage_host_snapshot(h, hs, stream, true, &d, h2d_bytes, &b_frc);
   if (st != PSB_OK) return st;
@@ -1468,7 +1611,14 @@ psb_status psb_evaluate_cvs_host(psb_handle* h, const psb_snapshot* hs, void* cu
   if (!h || !hs) return fail(PSB_ERR_VALUE, "NULL argument");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   psb_snapshot d;
-  psb_status st = stage_host_snapshot(h, hs, stream, false, &d, nullptr, nullptr);
+  psb_status st;
+  if (h->compact_ok) {
+    if ((st = check_snapshot(h, hs, false)) != PSB_OK) return st;
+    CompactGeom g{};
+    st = stage_selected_rows(h, hs, stream, false, &d, nullptr, &g);
+  } else {
+    st = stage_host_snapshot(h, hs, stream, false, &d, nullptr, nullptr);
+  }
   if (st != PSB_OK) return st;
   st = psb_evaluate_cvs(h, &d, cuda_stream);
   if (st != PSB_OK) return st;
