@@ -95,6 +95,9 @@ def restore(snapshot, prev_snapshot):
     put(snapshot.vel_mass, prev_snapshot.vel_mass)
     if snapshot.extras and prev_snapshot.extras and "images" in snapshot.extras:
         put(snapshot.extras["images"], prev_snapshot.extras["images"])
+    # HOOMD's slot -> tag array goes back together with rtags (`ids`): the two are each other's inverse
+    if snapshot.extras and prev_snapshot.extras and "tags" in snapshot.extras and "tags" in prev_snapshot.extras:
+        put(snapshot.extras["tags"], prev_snapshot.extras["tags"])
 
 
 def _ptr(t):
