@@ -35,5 +35,11 @@ for fr, f in zip(frames, f0):
 N.check(native3.lib.psb_run_cycle(native3.handle, descs, 64, 640, ctypes.c_void_p(stream.cuda_stream)))
 stream.synchronize()
 assert np.array_equal(native3.view("hist").cpu().numpy(), h2)
-assert torch.equal(native3.view("Fsum"), native2.view("Fsum"))
-print("640 steps: graph+PDL == plain steps without PDL (hist, Fsum bitwise)")
+g2, g3 = native2.launch_info()["grid_blocks"], native3.launch_info()["grid_blocks"]
+if g2 == g3:
+    assert torch.equal(native3.view("Fsum"), native2.view("Fsum"))
+    print("640 steps: graph+PDL == plain steps without PDL (hist, Fsum bitwise)")
+else:  # dual launch shape (slot-ordered class with the tag array): other CTA count, other order of the partial sums
+    a, b = native3.view("Fsum").cpu().numpy(), native2.view("Fsum").cpu().numpy()
+    assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+    print(f"640 steps: graph+PDL ({g3} CTAs) == plain steps without PDL ({g2} CTAs): hist bitwise, Fsum to 1e-10")
