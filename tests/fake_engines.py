@@ -30,7 +30,7 @@ class _V3:
 # ---------------------------------------------------------------------------------------------------
 # HOOMD-blue (v3+/v4 API) + hoomd.dlext
 # ---------------------------------------------------------------------------------------------------
-def install_hoomd():
+def install_hoomd(with_tags=True):
     class AccessLocation:
         OnHost, OnDevice = 0, 1
 
@@ -113,7 +113,9 @@ def install_hoomd():
     hoomd.md = _module("hoomd.md", HalfStepHook=type("HalfStepHook", (), {}))
     hoomd.device = _module("hoomd.device", CPU=CPU, GPU=GPU)
     hoomd.dlext = _module("hoomd.dlext", __version__="0.4.0", AccessLocation=AccessLocation, AccessMode=AccessMode,
-                          DLExtSampler=DLExtSampler, SystemView=SystemView, tags=tags)
+                          DLExtSampler=DLExtSampler, SystemView=SystemView)
+    if with_tags:  # older hoomd-dlext builds: no accessor for ParticleData's tag array
+        hoomd.dlext.tags = tags
     sys.modules.pop("pysages_b200.backends.hoomd", None)
     return Simulation
 

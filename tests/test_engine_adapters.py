@@ -66,6 +66,33 @@ def test_hoomd_adapter():
     assert not adapter.CONTEXTS_SAMPLERS
 
 
+def test_hoomd_adapter_without_a_tags_accessor_inverts_rtags_itself(monkeypatch):
+    """A hoomd-dlext build that does not export `tags`: the adapter passes the reference's five arrays only and the
+    slot-ordered class inverts rtags in the kernel; same bias as the mock backend."""
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "1")
+    monkeypatch.setenv("PSB_GRID_BLOCKS", "24")
+    n = 6000
+    snap = synthetic.make_snapshot(n, layout="hoomd", dtype=np.float32, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=NSTEPS, step=0.05)
+
+    def bias():
+        return ps.methods.HarmonicBias([ps.colvars.Distance([list(range(0, n // 2)), list(range(n // 2, n))])], 50.0, [1.0])
+
+    eng0 = mock.MockEngine(snap["layout"], snap["arrays"], snap["box_H"], snap["origin"], snap["dt"], device="cuda", trajectory=traj)
+    ref = ps.run(bias(), lambda **kw: eng0, NSTEPS)
+    torch.cuda.synchronize()
+    Simulation = fake_engines.install_hoomd(with_tags=False)
+    eng = fake_engines.engine(snap, "cuda", traj)
+    res = ps.run(bias(), lambda **kw: Simulation(eng), NSTEPS)
+    torch.cuda.synchronize()
+    from pysages_b200.backends import hoomd as adapter
+    sampler = next(iter(adapter.CONTEXTS_SAMPLERS.values()))
+    assert not sampler._want_tags and not hasattr(eng, "tags_calls")
+    np.testing.assert_array_equal(res.states[0].xi.cpu().numpy(), ref.states[0].xi.cpu().numpy())
+    np.testing.assert_array_equal(eng.t["forces"].cpu().numpy(), eng0.t["forces"].cpu().numpy())
+    adapter.detach(next(iter(adapter.CONTEXTS_SAMPLERS)))
+
+
 def test_hoomd_adapter_hands_over_the_slot_to_tag_array(monkeypatch):
     """Most of the system selected -> the slot-ordered class: the sampler fetches hoomd-dlext's `tags` (slot -> tag)
     each step and the kernel skips its tag -> slot inversion pass; same bias as with the reference's five arrays."""
