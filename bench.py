@@ -602,19 +602,20 @@ def run_series(device, stream, hbm, fp64_peak=None):
     # the headline workload on the other engine layouts (OpenMM-CUDA: fixed-point forces, permuted order -- the
     # slot-ordered class reads ids as slot -> atom, no inverse permutation; LAMMPS: (N,3) doubles, packed images,
     # per-type masses)
-    for layout, dtype in (("openmm-cuda", np.float32), ("lammps", np.float64)):
-        snaps, L = device_layout_snapshots(layout, dtype, 100_000, 16, device, seed=20240 + 2000)
-        cvs, m = workload_specs("abf2d", 100_000, L)
+    for layout, dtype, n_at, nsnap, nst in (("openmm-cuda", np.float32, 100_000, 16, 2000), ("lammps", np.float64, 100_000, 16, 2000),
+                                            ("openmm-cuda", np.float32, 1_000_000, 4, 500)):
+        snaps, L = device_layout_snapshots(layout, dtype, n_at, nsnap, device, seed=20240 + 2000)
+        cvs, m = workload_specs("abf2d", n_at, L)
         method, native = build_ours(cvs, m, snaps[0], layout=layout)
-        ms, launches = time_cycle(native, snapdesc_array(native, snaps), 2000, 20, stream)
+        ms, launches = time_cycle(native, snapdesc_array(native, snaps), nst, 20, stream)
         info = native.launch_info()
-        us = ms * 1e3 / 2000
+        us = ms * 1e3 / nst
         gbs = info["algorithmic_bytes_per_step"] / (us * 1e-6) / 1e9
-        out.append(dict(workload=f"abf2d S=N=100000 {layout}-{'f32' if dtype == np.float32 else 'f64'}",
-                        steps_per_s=round(2000 / (ms * 1e-3), 1), us_per_step=round(us, 3),
+        out.append(dict(workload=f"abf2d S=N={n_at} {layout}-{'f32' if dtype == np.float32 else 'f64'}",
+                        steps_per_s=round(nst / (ms * 1e-3), 1), us_per_step=round(us, 3),
                         algorithmic_bytes=info["algorithmic_bytes_per_step"], achieved_gbs=round(gbs, 1),
                         frac_of_hbm=round(gbs / hbm, 4), grid_blocks=info["grid_blocks"],
-                        launches_per_step=round(launches / 2000, 2), distinct_snapshots=len(snaps)))
+                        launches_per_step=round(launches / nst, 2), distinct_snapshots=len(snaps)))
         del snaps, native, method
         torch.cuda.empty_cache()
 
