@@ -790,7 +790,17 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         h->grid = std::min(occ_slot, SLOT_CTAS_PER_SM) * h->num_sms;  // streaming: fill the machine
         // OpenMM layout: one CTA per SM leaves room for the NEXT step's CTAs, whose gather runs before their
         // dependency wait (psb_step.cuh), i.e. under this step's finalizer and scatter (1e6 atoms, ABF: 44.0 -> 39.3 us)
-        if (omm) h->grid = h->num_sms;
+        if (omm) {
+          // from ~2e5 atoms both launch shapes are kept, like the HOOMD handles below: single launches want the full
+          // machine (plain launches, ABF: 3e5 atoms 22.2 -> 18.8 us, 1e6 atoms 67.5 -> 46.2 us with two CTAs per SM)
+          if (layout->natoms > 5LL * BLOCK * h->num_sms && h->grid >= 2 * h->num_sms && !getenv("PSB_DEBUG_TIMING") &&
+              !(getenv("PSB_ONE_GRID") && atoi(getenv("PSB_ONE_GRID")) != 0)) {
+            h->grid_plain = h->grid;
+            h->grid_pipe = h->num_sms;
+          } else {
+            h->grid = h->num_sms;
+          }
+        }
         // (not with RadiusOfGyration groups: their scatter streams the positions a second time, the part behind the
         // dependency wait dominates and wants all 16 warps per SM -- measured 29.2 us at two CTAs per SM, 36.6 at one)
         bool rog_groups = false;

@@ -405,7 +405,8 @@ def test_openmm_slot_ordered_class_at_full_grid_against_tag_ordered(method, monk
         stream.synchronize()
         outs.append((native.view("xi").cpu().numpy().copy(), native.view("cv_force").cpu().numpy().copy(),
                      np.stack([s.forces.cpu().numpy() for s in snaps]), native.launch_info()["grid_blocks"]))
-    assert outs[1][3] == torch.cuda.get_device_properties(0).multi_processor_count  # slot-ordered: one CTA per SM
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert outs[1][3] == 2 * sms  # slot-ordered, last stepped one launch at a time: two CTAs per SM (one under replay)
     close(outs[1][0], outs[0][0], 1e-12, what="xi slot- vs tag-ordered")
     close(outs[1][1], outs[0][1], 1e-9, what="generalized force slot- vs tag-ordered")
     moved = np.abs(outs[0][2].astype(np.float64) - np.stack([f.cpu().numpy() for f in f0]).astype(np.float64)).max()

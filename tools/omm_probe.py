@@ -9,7 +9,7 @@ for wl, natoms in [(c.split(":")[0], int(c.split(":")[1])) for c in sys.argv[1:]
     cvs, m = bench.workload_specs(wl, natoms, L)
     method, native = bench.build_ours(cvs, m, snaps[0], layout="openmm-cuda")
     descs = bench.snapdesc_array(native, snaps)
-    ms, _ = bench.time_cycle(native, descs, 300, 20, stream)
+    ms, _ = bench.time_cycle(native, descs, 300, 20, stream, plain=bool(os.environ.get("PSB_NO_GRAPH")))
     info = native.launch_info()
     print(f"openmm {wl} N={natoms} grid {info['grid_blocks']}: {ms * 1e3 / 300:.2f} us/step = {info['algorithmic_bytes_per_step'] / (ms / 300 * 1e-3) / 1e9:.0f} GB/s", flush=True)
     del native, method, snaps
