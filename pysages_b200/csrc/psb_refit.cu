@@ -5,7 +5,7 @@
 // sum-of-squared-errors loss with float32 residuals and L2 regularisation (ml/objectives.py).  One LM iteration is
 //
 //   lm_jacobian  J, e = d residuals / d params, residuals   closed-form back-propagation, one warp per sample
-//   lm_normal    H = J^T J, g = J^T e                       fp64 syrk, 64 x 64 tiles, 4 x 4 per thread, split over samples
+//   lm_normal    H = J^T J, g = J^T e                       fp64 syrk, 128 x 128 tiles, 8 x 8 per thread, split over samples
 //   lm_solve     dp = solve(H + (r + mu) I, g + r p)        cooperative blocked Cholesky over all SMs (see there)
 //   lm_cost      C = (|e(p - dp)|^2 + r |p - dp|^2) / 2     forward pass; the last CTA to finish takes the loop's
 //                rho, mu update, accept / reject            decision (float32 mu like the reference)
@@ -30,7 +30,9 @@ constexpr int MAXW = PSB_MAX_WIDTH;       // units per layer
 constexpr int MAXL = PSB_MAX_DENSE;       // dense layers
 constexpr int NB = 32;                    // Cholesky block
 constexpr int MAX_SPLIT = 32;             // sample splits of the normal-equation kernel (summed in fixed order)
-constexpr int TN = 64, TK = 32;           // lm_normal: output tile, rows of J per stage
+constexpr int TN = 128, TK = 16;          // lm_normal: output tile, rows of J per stage
+constexpr int TN64 = 64, TK64 = 32;       // lm_normal64
+constexpr int NORMAL64_MAX_P = 384;       // parameter counts up to which the 64 x 64 tiles are used
 
 struct Net {
   int32_t n_dense, nparams;
@@ -155,9 +157,12 @@ __global__ void __launch_bounds__(256) lm_jacobian(const Problem pr) {
 }
 
 // ---- K2: H = J^T J (full, symmetric), g = J^T e; `splits` partial results over disjoint sample ranges -------------
-// 64 x 64 output tiles of the upper triangle, 256 threads with 4 x 4 accumulators each (16 DFMA per 4 shared-memory
-// loads of 16 bytes); the next 32 rows of J travel through registers while the current ones are multiplied.
-__global__ void __launch_bounds__(256) lm_normal(const Problem pr) {
+// 128 x 128 output tiles of the upper triangle, 256 threads with 8 x 8 fp64 accumulators each: 64 DFMA per eight
+// 16-byte shared-memory loads (a 4 x 4 register tile is bound by shared-memory bandwidth: ncu 62 % short-scoreboard
+// stalls, FP64 pipe 28 %).  A thread's rows are contiguous (broadcast loads), its columns are pairs strided by 32 so
+// that the 16 lanes of a half-warp read 256 contiguous bytes: no bank conflicts.  The next 16 rows of J travel through
+// registers while the current ones are multiplied.
+__global__ void __launch_bounds__(256, 1) lm_normal(const Problem pr) {
   if (pr.ctl->done || !pr.ctl->fresh) return;
   __shared__ __align__(16) double sa[TK][TN], sb[TK][TN];
   __shared__ double se[TK];
@@ -173,6 +178,83 @@ __global__ void __launch_bounds__(256) lm_normal(const Problem pr) {
   per = (per + TK - 1) / TK * TK;
   const long long m0 = min(M, split * per), m1 = min(M, m0 + per);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // loader: 16 rows x 128 columns per matrix and stage = 8 elements per thread and matrix, coalesced along the parameters
+  const int lr = tid >> 4, lc = (tid & 15) * 8;
+  double ra[8], rb[8], re = 0.0;
+  auto fetch = [&](long long m) {
+    const long long row = m + lr;
+    const bool ok = row < m1;
+    const double* Jr = pr.J + (size_t)row * P;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ca = ti * TN + lc + q, cb = tj * TN + lc + q;
+      ra[q] = (ok && ca < P) ? Jr[ca] : 0.0;
+      rb[q] = (ok && cb < P) ? Jr[cb] : 0.0;
+    }
+    if (tid < TK) re = (m + tid < m1) ? pr.e[m + tid] : 0.0;
+  };
+  double acc[8][8] = {}, gacc = 0.0;
+  if (m0 < m1) fetch(m0);
+  for (long long m = m0; m < m1; m += TK) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sa[lr][lc + q] = ra[q]; sb[lr][lc + q] = rb[q]; }
+    if (tid < TK) se[tid] = re;
+    __syncthreads();
+    if (m + TK < m1) fetch(m + TK);
+#pragma unroll 1
+    for (int r = 0; r < TK; ++r) {
+      double a[8], b[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2 av = *reinterpret_cast<const double2*>(&sa[r][ty * 8 + 2 * q]);
+        const double2 bv = *reinterpret_cast<const double2*>(&sb[r][tx * 2 + 32 * q]);
+        a[2 * q] = av.x; a[2 * q + 1] = av.y;
+        b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    if (ti == tj && tid < TN) {
+#pragma unroll
+      for (int r = 0; r < TK; ++r) gacc = fma(sa[r][tid], se[r], gacc);
+    }
+    __syncthreads();
+  }
+  double* H = pr.Hpart + (size_t)split * P * P;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gi = ti * TN + ty * 8 + i, gj = tj * TN + tx * 2 + 32 * (j >> 1) + (j & 1);
+      if (gi < P && gj < P) {
+        H[(size_t)gi * P + gj] = acc[i][j];
+        if (ti != tj) H[(size_t)gj * P + gi] = acc[i][j];
+      }
+    }
+  if (ti == tj && tid < TN && ti * TN + tid < P) pr.gpart[(size_t)split * P + ti * TN + tid] = gacc;
+}
+
+// ---- K2 (up to 384 parameters): the same with 64 x 64 tiles (less padding, more CTAs for small matrices) ------------------
+// 64 x 64 output tiles of the upper triangle, 256 threads with 4 x 4 accumulators each (16 DFMA per 4 shared-memory
+// loads of 16 bytes); the next 32 rows of J travel through registers while the current ones are multiplied.
+__global__ void __launch_bounds__(256) lm_normal64(const Problem pr) {
+  if (pr.ctl->done || !pr.ctl->fresh) return;
+  __shared__ __align__(16) double sa[TK64][TN64], sb[TK64][TN64];
+  __shared__ double se[TK64];
+  const int P = pr.net.nparams;
+  const int tiles = (P + TN64 - 1) / TN64;
+  const long long M = pr.n * pr.nout;
+  const int ntri = tiles * (tiles + 1) / 2;
+  const int tri = blockIdx.x % ntri, split = blockIdx.x / ntri;
+  int ti = 0, rem = tri;
+  while (rem >= tiles - ti) { rem -= tiles - ti; ++ti; }
+  const int tj = ti + rem;
+  long long per = (M + pr.splits - 1) / pr.splits;
+  per = (per + TK64 - 1) / TK64 * TK64;
+  const long long m0 = min(M, split * per), m1 = min(M, m0 + per);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   // loader: 32 rows x 64 columns per matrix and stage = 2 x 4 elements per thread, coalesced along the parameters
   const int lr = tid >> 4, lc = (tid & 15) * 4;
   double ra[2][4], rb[2][4], re = 0.0;
@@ -184,26 +266,26 @@ __global__ void __launch_bounds__(256) lm_normal(const Problem pr) {
       const double* Jr = pr.J + (size_t)row * P;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int ca = ti * TN + lc + q, cb = tj * TN + lc + q;
+        const int ca = ti * TN64 + lc + q, cb = tj * TN64 + lc + q;
         ra[h][q] = (ok && ca < P) ? Jr[ca] : 0.0;
         rb[h][q] = (ok && cb < P) ? Jr[cb] : 0.0;
       }
     }
-    if (tid < TK) re = (m + tid < m1) ? pr.e[m + tid] : 0.0;
+    if (tid < TK64) re = (m + tid < m1) ? pr.e[m + tid] : 0.0;
   };
   double acc[4][4] = {}, gacc = 0.0;
   if (m0 < m1) fetch(m0);
-  for (long long m = m0; m < m1; m += TK) {
+  for (long long m = m0; m < m1; m += TK64) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       sa[lr][lc + q] = ra[0][q]; sb[lr][lc + q] = rb[0][q];
       sa[lr + 16][lc + q] = ra[1][q]; sb[lr + 16][lc + q] = rb[1][q];
     }
-    if (tid < TK) se[tid] = re;
+    if (tid < TK64) se[tid] = re;
     __syncthreads();
-    if (m + TK < m1) fetch(m + TK);
+    if (m + TK64 < m1) fetch(m + TK64);
 #pragma unroll
-    for (int r = 0; r < TK; ++r) {
+    for (int r = 0; r < TK64; ++r) {
       const double2 a01 = *reinterpret_cast<const double2*>(&sa[r][ty * 4]), a23 = *reinterpret_cast<const double2*>(&sa[r][ty * 4 + 2]);
       const double2 b01 = *reinterpret_cast<const double2*>(&sb[r][tx * 4]), b23 = *reinterpret_cast<const double2*>(&sb[r][tx * 4 + 2]);
       const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
@@ -212,9 +294,9 @@ __global__ void __launch_bounds__(256) lm_normal(const Problem pr) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
-    if (ti == tj && tid < TN) {
+    if (ti == tj && tid < TN64) {
 #pragma unroll
-      for (int r = 0; r < TK; ++r) gacc = fma(sa[r][tid], se[r], gacc);
+      for (int r = 0; r < TK64; ++r) gacc = fma(sa[r][tid], se[r], gacc);
     }
     __syncthreads();
   }
@@ -223,13 +305,13 @@ __global__ void __launch_bounds__(256) lm_normal(const Problem pr) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int gi = ti * TN + ty * 4 + i, gj = tj * TN + tx * 4 + j;
+      const int gi = ti * TN64 + ty * 4 + i, gj = tj * TN64 + tx * 4 + j;
       if (gi < P && gj < P) {
         H[(size_t)gi * P + gj] = acc[i][j];
         if (ti != tj) H[(size_t)gj * P + gi] = acc[i][j];
       }
     }
-  if (ti == tj && tid < TN && ti * TN + tid < P) pr.gpart[(size_t)split * P + ti * TN + tid] = gacc;
+  if (ti == tj && tid < TN64 && ti * TN64 + tid < P) pr.gpart[(size_t)split * P + ti * TN64 + tid] = gacc;
 }
 
 // ---- K2b: the partial results added in a fixed order ------------------------------------------------------------------
@@ -679,11 +761,14 @@ psb_status psb_lm_fit(const psb_lm_problem* q, psb_lm_workspace** ws_io, void* c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int cost_ctas = 2 * sms;
   const int T = (P + NB - 1) / NB, Pp = T * NB;
-  const int tiles = (P + TN - 1) / TN, ntri = tiles * (tiles + 1) / 2;
+  const bool small_tiles = P <= NORMAL64_MAX_P;
+  const int tn = small_tiles ? TN64 : TN, tk = small_tiles ? TK64 : TK;
+  const int tiles = (P + tn - 1) / tn, ntri = tiles * (tiles + 1) / 2;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_normal, 256, 0);
+  if (small_tiles) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_normal64, 256, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_normal, 256, 0);
   int splits = std::max(1, std::min(MAX_SPLIT, std::max(1, per_sm) * sms / ntri));  // one balanced wave
-  splits = (int)std::max<long long>(1, std::min<long long>(splits, ((long long)q->n * pr.nout + 4 * TK - 1) / (4 * TK)));
+  splits = (int)std::max<long long>(1, std::min<long long>(splits, ((long long)q->n * pr.nout + 4 * tk - 1) / (4 * tk)));
   pr.T = T;
   pr.splits = splits;
   // workspace layout (doubles unless noted)
@@ -723,7 +808,8 @@ psb_status psb_lm_fit(const psb_lm_problem* q, psb_lm_workspace** ws_io, void* c
   // e of the initial parameters is produced by the first lm_jacobian (fresh = 1)
   auto enqueue_iteration = [&](cudaStream_t s) {
     lm_jacobian<<<jac_ctas, 256, smem_j, s>>>(pr);
-    lm_normal<<<ntri * splits, 256, 0, s>>>(pr);
+    if (small_tiles) lm_normal64<<<ntri * splits, 256, 0, s>>>(pr);
+    else lm_normal<<<ntri * splits, 256, 0, s>>>(pr);
     lm_reduce<<<(P * P + 255) / 256, 256, 0, s>>>(pr);
     void* args[] = {(void*)&pr};
     cudaLaunchCooperativeKernel((const void*)lm_solve, dim3(solve_ctas), dim3(256), args, sizeof(SolveShared), s);
