@@ -93,7 +93,7 @@ def snapshots_of(frames, L, dt, with_tags=True):
     return [Snapshot(f["positions"], f["vel_mass"], f["forces"], f["rtags"], box, dt, extras(f)) for f in frames]
 
 
-def device_layout_snapshots(layout, dtype, natoms, nframes, device, seed):
+def device_layout_snapshots(layout, dtype, natoms, nframes, device, seed, with_tags=True):
     """Snapshots in any engine layout (numpy generator of pysages_b200.synthetic, uploaded once): every frame
     owns its arrays; positions follow a random-walk trajectory."""
     from pysages_b200 import synthetic
@@ -109,8 +109,13 @@ def device_layout_snapshots(layout, dtype, natoms, nframes, device, seed):
         if layout == "openmm-cuda":
             out.append(Snapshot(a["positions"], a["vel_mass"], a["forces"], a["ids"], box, base["dt"]))
         elif layout == "lammps":
+            extras = dict(images=a["images"])
+            if with_tags:  # atom->tag (lammps-dlext `tags`): the 1-based id of the atom in every slot, inverse of tags_map
+                tm = a["tags_map"]
+                extras["tags"] = torch.zeros(tm.numel() - 1, device=device, dtype=tm.dtype)
+                extras["tags"][tm[1:].long()] = torch.arange(1, tm.numel(), device=device, dtype=tm.dtype)
             out.append(Snapshot(a["positions"], (a["velocities"], (a["masses"], a["types"])), a["forces"],
-                                a["tags_map"][1:], box, base["dt"], dict(images=a["images"])))
+                                a["tags_map"][1:], box, base["dt"], extras))
         else:
             raise ValueError(layout)
     return out, base["L"]
@@ -603,7 +608,7 @@ def run_series(device, stream, hbm, fp64_peak=None):
     # slot-ordered class reads ids as slot -> atom, no inverse permutation; LAMMPS: (N,3) doubles, packed images,
     # per-type masses)
     for layout, dtype, n_at, nsnap, nst in (("openmm-cuda", np.float32, 100_000, 16, 2000), ("lammps", np.float64, 100_000, 16, 2000),
-                                            ("openmm-cuda", np.float32, 1_000_000, 4, 500)):
+                                            ("openmm-cuda", np.float32, 1_000_000, 4, 500), ("lammps", np.float64, 1_000_000, 4, 500)):
         snaps, L = device_layout_snapshots(layout, dtype, n_at, nsnap, device, seed=20240 + 2000)
         cvs, m = workload_specs("abf2d", n_at, L)
         method, native = build_ours(cvs, m, snaps[0], layout=layout)

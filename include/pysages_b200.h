@@ -176,7 +176,7 @@ typedef struct {
   int32_t need_momenta; /* "momenta" in method.snapshot_flags (abf.py:114) */
   int32_t dense_outputs; /* 1: also keep the reference's dense state.bias (N,3) and J (k,3N) */
   int32_t ntypes;        /* LAMMPS: entries of the per-type mass array (ntypes + 1) */
-  int32_t has_tags;      /* HOOMD: the engine will hand over psb_snapshot.tags (slot -> tag) with every snapshot: the
+  int32_t has_tags;      /* HOOMD, LAMMPS: the engine will hand over psb_snapshot.tags (slot -> tag) with every snapshot: the
                             slot-ordered class is then planned for it (one CTA per SM, so that the next step's gather --
                             engine arrays only -- overlaps this step's tail; chosen from ~1.5e5 selected atoms upward) */
   int32_t reserved;
@@ -193,8 +193,8 @@ typedef struct {
   const void* types;  /* LAMMPS: per-atom types (i32) */
   double box_diag[3]; /* diag(H) -- the reference unwraps with the diagonal only (hoomd.py:180) */
   double dt;
-  /* Optional, HOOMD layout: the slot -> tag array (ParticleData's `tag`, the inverse of `ids` = rtag; hoomd-dlext
-     exports both).  With it the slot-ordered class streams the engine's arrays in memory order and reads the group of
+  /* Optional, HOOMD and LAMMPS layouts: the slot -> tag array (HOOMD: ParticleData's `tag`, the inverse of `ids` = rtag,
+     hoomd-dlext exports both; LAMMPS: atom->tag, int32 1-based ids, the inverse of `ids` = tags_map).  With it the slot-ordered class streams the engine's arrays in memory order and reads the group of
      a slot from a tag -> group table: no tag -> slot inversion pass, one grid barrier fewer.  NULL: `ids` only. */
   const void* tags;
 } psb_snapshot;

@@ -11,10 +11,13 @@ instance of its own.
 
 import weakref
 
+import torch
 from lammps import dlext
 
 from . import _common as C
 from .snapshot import Box, Snapshot
+
+_tags_of = getattr(dlext, "tags", None)  # tags(view, location) -> atom->tag (slot -> 1-based id); optional
 
 # The native step unpacks LAMMPS' SMALLBIG image word: 10 + 10 + 12 bits, offset 512 (lammps.py:188-202 reads
 # the same constants from the plugin).  A BIGBIG build (64-bit words, 21-bit fields) would be unwrapped wrongly.
@@ -43,11 +46,13 @@ class Sampler(C.SamplerCore, dlext.FixDLExt):
         self.box = Box(*global_box(lmp))
         self.dt = lmp.extract_global("dt")
         self._masses = None
+        self._use_tags = self.location != dlext.kOnHost  # device arrays only; decided for good once the handle exists
         layout = C.LAYOUTS["lammps"]
         factor = C.LAMMPS_CONVERSION.get(lmp.extract_global("units"))
         if factor is not None:
             layout = layout._replace(force_unit_factor=factor)
         self._bind_method(sampling_method, layout, callback)
+        self._use_tags = self._use_tags and _tags_of is not None and self._native.wants_tags
         self.set_callback(self.on_post_force)
 
     def _views(self):
@@ -57,15 +62,22 @@ class Sampler(C.SamplerCore, dlext.FixDLExt):
         if self._masses is None:
             self._masses = t(dlext.masses(v, loc))
         tags_map = t(dlext.tags_map(v, loc))
+        extras = dict(images=t(dlext.images(v, loc)))
+        if _tags_of is not None and self._use_tags:  # atom->tag (slot -> id): the slot-ordered class streams with it
+            tags = t(_tags_of(v, loc))
+            if tags.dtype == torch.int32:  # (BIGBIG builds carry 64-bit ids: the tags_map inversion pass stays)
+                extras["tags"] = tags
         return Snapshot(t(dlext.positions(v, loc)), (t(dlext.velocities(v, loc)), (self._masses, t(dlext.types(v, loc)))),
-                        t(dlext.forces(v, loc)), tags_map[1:], self.box, self.dt, dict(images=t(dlext.images(v, loc))))
+                        t(dlext.forces(v, loc)), tags_map[1:], self.box, self.dt, extras)
 
     def on_post_force(self, timestep):
         self.view.synchronize()
         views = self._views()
         if self._fused:
+            tags = views.extras.get("tags")
             key = (views.positions.data_ptr(), views.forces.data_ptr(), views.ids.data_ptr(),
-                   views.vel_mass[0].data_ptr(), views.vel_mass[1][1].data_ptr(), views.extras["images"].data_ptr())
+                   views.vel_mass[0].data_ptr(), views.vel_mass[1][1].data_ptr(), views.extras["images"].data_ptr(),
+                   tags.data_ptr() if tags is not None else None)
             self._current = views
             self.advance_pointers(timestep, key, lambda d: self.describe_into(views))
         else:

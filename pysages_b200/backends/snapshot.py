@@ -129,7 +129,7 @@ def describe_layout(snapshot, layout, unwrap, need_momenta, dense_outputs=False)
         masses = snapshot.vel_mass[1][0]
         d.ntypes = 0 if masses is None else int(masses.numel())
     # HOOMD snapshots that carry the slot -> tag array: the handle is planned for it (psb_layout_desc.has_tags)
-    d.has_tags = int(layout.kind == N.LAYOUT_HOOMD and bool(snapshot.extras) and snapshot.extras.get("tags") is not None)
+    d.has_tags = int(layout.kind in (N.LAYOUT_HOOMD, N.LAYOUT_LAMMPS) and bool(snapshot.extras) and snapshot.extras.get("tags") is not None)
     return d
 
 
@@ -141,8 +141,8 @@ def describe_snapshot(snapshot, layout, out=None):
     s.forces = _ptr(snapshot.forces)
     images = snapshot.extras.get("images") if snapshot.extras else None
     s.images = _ptr(images)
-    # HOOMD: the engine's slot -> tag array, when the adapter got one (psb_snapshot.tags)
-    tags = snapshot.extras.get("tags") if (snapshot.extras and kind == N.LAYOUT_HOOMD) else None
+    # HOOMD / LAMMPS: the engine's slot -> tag array, when the adapter got one (psb_snapshot.tags)
+    tags = snapshot.extras.get("tags") if (snapshot.extras and kind in (N.LAYOUT_HOOMD, N.LAYOUT_LAMMPS)) else None
     s.tags = _ptr(tags)
     if kind == N.LAYOUT_LAMMPS:
         velocities, (masses, types) = snapshot.vel_mass

@@ -772,7 +772,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
     // co-resident, so that gather overlaps this step's exchange, finalizer and scatter (measured, ABF: 2e5 atoms 17.2 ->
     // 10.0 us, 1e6 atoms 28.0 -> 24.2 us against two CTAs per SM).  Worth it as soon as the register cache of one
     // CTA per SM is too small.
-    const bool tags_hint = layout->has_tags && layout->layout == PSB_LAYOUT_HOOMD &&
+    const bool tags_hint = layout->has_tags && (layout->layout == PSB_LAYOUT_HOOMD || layout->layout == PSB_LAYOUT_LAMMPS) &&
                            !(getenv("PSB_NO_TAGS") && atoi(getenv("PSB_NO_TAGS")) != 0);
     bool wanted = (long long)M.T > (long long)CT * BLOCK * (tags_hint ? h->num_sms : h->grid) && 2LL * M.T >= layout->natoms;
     // OpenMM-CUDA: `ids` already IS slot -> atom, so the slot-ordered passes need no tag -> slot inverse at
@@ -872,7 +872,7 @@ psb_status psb_create(const psb_cv_desc* cvs, int32_t ncvs, const psb_method_des
         M.tag_group = p;
       } else {
         st = dev_alloc(h, &M.slot_map, (size_t)layout->natoms);
-        if (st == PSB_OK && layout->layout == PSB_LAYOUT_HOOMD && h->step_general == SC_SLOT &&
+        if (st == PSB_OK && (layout->layout == PSB_LAYOUT_HOOMD || layout->layout == PSB_LAYOUT_LAMMPS) && h->step_general == SC_SLOT &&
             !(getenv("PSB_NO_TAGS") && atoi(getenv("PSB_NO_TAGS")) != 0) &&
             (long long)pick_vtable(*layout)->occupancy(h->step_method, SC_TAGS, h->dyn_smem) * h->num_sms >= h->grid) {
           // snapshots that carry the engine's slot -> tag array take the SC_TAGS instantiation (enqueue)

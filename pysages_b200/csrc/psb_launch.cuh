@@ -50,7 +50,7 @@ const void* stream_entry() {
 }
 template <int L, typename R, int M>
 const void* tags_entry() {
-  if constexpr (L == PSB_LAYOUT_HOOMD) return (const void*)step_kernel<L, R, M, SC_TAGS>;
+  if constexpr (L == PSB_LAYOUT_HOOMD || L == PSB_LAYOUT_LAMMPS) return (const void*)step_kernel<L, R, M, SC_TAGS>;
   else return (const void*)step_kernel<L, R, M, SC_SLOT>;
 }
 #define PSB_STEP_ROW(L, R, M)                                                                     \

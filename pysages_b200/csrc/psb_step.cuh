@@ -1224,7 +1224,7 @@ template <int LAYOUT, typename Real, int METHOD, int CLASS>
 __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, const Snap& S, const int nb_arg, const int b_arg) {
   constexpr bool GENERAL = (CLASS == SC_GENERAL);
   constexpr bool STREAM = (CLASS == SC_STREAM);  // slot-ordered, streams staged by TMA (HOOMD layout only)
-  constexpr bool TAGS = (CLASS == SC_TAGS);      // slot-ordered, slot -> tag array from the engine (HOOMD layout only)
+  constexpr bool TAGS = (CLASS == SC_TAGS);      // slot-ordered, slot -> tag array from the engine (HOOMD and LAMMPS layouts)
   constexpr bool SLOT = (CLASS == SC_SLOT) || STREAM || TAGS;
   static_assert(!STREAM || LAYOUT == PSB_LAYOUT_HOOMD, "the TMA-staged streams are written for the HOOMD layout");
   using A = Access<LAYOUT, Real>;
@@ -1416,7 +1416,9 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
       if (M.cv[M.grp[g].cv].kind == PSB_CV_ROG) rog_bits |= 1u << g;
   auto slot_word = [&](uint32_t sl) -> uint32_t {  // stamp | group + 1 when slot `sl` holds a selected atom
     if constexpr (TAGMAP) {
-      const uint32_t tag = (uint32_t)__ldg(reinterpret_cast<const int*>(TAGS ? S.tags : S.ids) + sl);
+      // HOOMD: ParticleData's tag array; LAMMPS: atom->tag, whose ids are 1-based (atom `tag` of a CV is LAMMPS id tag + 1)
+      const uint32_t tag = (uint32_t)(__ldg(reinterpret_cast<const int*>(TAGS ? S.tags : S.ids) + sl) -
+                                      ((TAGS && LAYOUT == PSB_LAYOUT_LAMMPS) ? 1 : 0));
       const uint32_t g = tag < (uint32_t)M.natoms ? (uint32_t)__ldg(M.tag_group + tag) : 0u;
       return g ? (stamp | g) : 0u;
     } else {

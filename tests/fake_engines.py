@@ -212,7 +212,7 @@ def install_openmm(own_stream=False):
 # ---------------------------------------------------------------------------------------------------
 # LAMMPS + lammps.dlext
 # ---------------------------------------------------------------------------------------------------
-def install_lammps(kokkos_cuda=True, own_stream=False):
+def install_lammps(kokkos_cuda=True, own_stream=False, with_tags=True):
     class ExecutionSpace:
         kOnHost, kOnDevice = 0, 1
 
@@ -235,6 +235,16 @@ def install_lammps(kokkos_cuda=True, own_stream=False):
 
     def _cap(view, key):
         return to_dlpack(view.context.engine.t[key])
+
+    def tags(view, location):
+        # atom->tag: the 1-based id of the atom in every slot (tags_map is its inverse: tags_map[id] = slot)
+        eng = view.context.engine
+        tm = eng.t["tags_map"]
+        ids = torch.arange(1, tm.numel(), device=tm.device, dtype=tm.dtype)
+        out = torch.zeros(tm.numel() - 1, device=tm.device, dtype=tm.dtype)
+        out[tm[1:].long()] = ids
+        eng.tags_calls = getattr(eng, "tags_calls", 0) + 1
+        return to_dlpack(out)
 
     class lammps:  # noqa: N801  (the real class is lower-case)
         def __init__(self, engine):
@@ -278,6 +288,8 @@ def install_lammps(kokkos_cuda=True, own_stream=False):
                         forces=lambda v, loc: _cap(v, "forces"), types=lambda v, loc: _cap(v, "types"),
                         tags_map=lambda v, loc: _cap(v, "tags_map"), images=lambda v, loc: _cap(v, "images"),
                         masses=lambda v, loc: _cap(v, "masses"))
+    if with_tags:
+        lmp.dlext.tags = tags
     sys.modules.pop("pysages_b200.backends.lammps", None)
     return lammps
 

@@ -124,8 +124,13 @@ def device_snapshot(snap, device="cuda", positions=None):
     if L == "openmm-cpu":
         return Snapshot(a["positions"], (a["velocities"], a["inv_masses"]), a["forces"], a["ids"], box, snap["dt"])
     if L == "lammps":
+        extras = dict(images=a["images"])
+        if os.environ.get("PSB_TEST_TAGS") == "1" and a["positions"].is_cuda:  # atom->tag: 1-based id of the atom in each slot
+            tm = a["tags_map"]
+            extras["tags"] = torch.zeros(tm.numel() - 1, device=tm.device, dtype=tm.dtype)
+            extras["tags"][tm[1:].long()] = torch.arange(1, tm.numel(), device=tm.device, dtype=tm.dtype)
         return Snapshot(a["positions"], (a["velocities"], (a["masses"], a["types"])), a["forces"], a["tags_map"][1:],
-                        box, snap["dt"], dict(images=a["images"]))
+                        box, snap["dt"], extras)
     raise ValueError(L)
 
 

@@ -66,6 +66,31 @@ def test_hoomd_adapter():
     assert not adapter.CONTEXTS_SAMPLERS
 
 
+def test_lammps_adapter_hands_over_atom_tags(monkeypatch):
+    """Kokkos-CUDA LAMMPS, most atoms selected: the fix asks lammps-dlext for atom->tag (slot -> 1-based id) and the
+    slot-ordered class streams with it instead of inverting tags_map; same bias as without the accessor."""
+    monkeypatch.setenv("PSB_SLOT_MAJOR", "1")
+    monkeypatch.setenv("PSB_GRID_BLOCKS", "24")
+    n = 6000
+    snap = synthetic.make_snapshot(n, layout="lammps", dtype=np.float64, seed=9)
+    traj = synthetic.make_trajectory(snap, frames=NSTEPS, step=0.05)
+
+    def bias():
+        return ps.methods.HarmonicBias([ps.colvars.Distance([list(range(0, n // 2)), list(range(n // 2, n))])], 50.0, [1.0])
+
+    results = []
+    for with_tags in (False, True):
+        lammps = fake_engines.install_lammps(kokkos_cuda=True, with_tags=with_tags)
+        eng = fake_engines.engine(snap, "cuda", traj, units="real")
+        res = ps.run(bias(), lambda **kw: lammps(eng), NSTEPS)
+        torch.cuda.synchronize()
+        assert (getattr(eng, "tags_calls", 0) >= NSTEPS) == with_tags
+        results.append((res.states[0].xi.cpu().numpy().copy(), eng.t["forces"].cpu().numpy().copy()))
+    np.testing.assert_allclose(results[1][0], results[0][0], rtol=1e-13)
+    assert np.abs(results[1][1] - results[0][1]).max() <= 1e-12 * np.abs(results[0][1]).max()
+    assert np.abs(results[0][1] - snap["arrays"]["forces"]).max() > 0
+
+
 def test_hoomd_adapter_without_a_tags_accessor_inverts_rtags_itself(monkeypatch):
     """A hoomd-dlext build that does not export `tags`: the adapter passes the reference's five arrays only and the
     slot-ordered class inverts rtags in the kernel; same bias as the mock backend."""

@@ -1,0 +1,16 @@
+"""OpenMM-CUDA layout, slot-ordered class (ids is slot -> atom): grid of one vs two CTAs per SM."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+dev = torch.device("cuda:0"); stream = torch.cuda.Stream()
+for wl, natoms in [(c.split(":")[0], int(c.split(":")[1])) for c in sys.argv[1:]]:
+  for with_tags in (False, True):
+    snaps, L = bench.device_layout_snapshots("lammps", np.float64, natoms, 4, dev, seed=5, with_tags=with_tags)
+    cvs, m = bench.workload_specs(wl, natoms, L)
+    method, native = bench.build_ours(cvs, m, snaps[0], layout="lammps")
+    descs = bench.snapdesc_array(native, snaps)
+    ms, _ = bench.time_cycle(native, descs, 300, 20, stream, plain=bool(os.environ.get("PSB_NO_GRAPH")))
+    info = native.launch_info()
+    print(f"lammps {wl} tags={with_tags} N={natoms} grid {info['grid_blocks']}: {ms * 1e3 / 300:.2f} us/step = {info['algorithmic_bytes_per_step'] / (ms / 300 * 1e-3) / 1e9:.0f} GB/s", flush=True)
+    del native, method, snaps
