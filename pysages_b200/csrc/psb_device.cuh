@@ -345,12 +345,17 @@ struct Access<PSB_LAYOUT_OPENMM_CUDA, Real> {
     const R4 p = ldg4(reinterpret_cast<const R4*>(s.positions) + slot);
     return v3((double)p.x, (double)p.y, (double)p.z);  // never unwrapped (openmm.py:122-123)
   }
-  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) {
-    // openmm.py:96-97,125-127: v / invM, or v when invM == 0
-    const R4 v = ldg4(reinterpret_cast<const R4*>(s.vel_mass) + slot);
+  // openmm.py:96-97,125-127: v / invM, or v when invM == 0.  Split into the load and the arithmetic: a streaming
+  // loop issues the loads of a whole batch first and divides afterwards (the test on invM and the division's slow
+  // path are branches; taken between two loads they serialise the batch -- measured: 48 instead of 11 us per 1e6 rows)
+  static __device__ __forceinline__ R4 load_velocity(const Snap& s, uint32_t slot) {
+    return ldg4(reinterpret_cast<const R4*>(s.vel_mass) + slot);
+  }
+  static __device__ __forceinline__ V3 momentum_of(R4 v) {
     if (v.w == (Real)0) return v3((double)v.x, (double)v.y, (double)v.z);
     return v3((double)(Real)(v.x / v.w), (double)(Real)(v.y / v.w), (double)(Real)(v.z / v.w));
   }
+  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) { return momentum_of(load_velocity(s, slot)); }
   // openmm.py:141-143,167-169: int64(2**32 * bias.T) added to forces (3, Np)
   struct FV { long long x, y, z; };
   static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {

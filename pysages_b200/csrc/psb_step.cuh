@@ -1444,12 +1444,28 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
         cslot[i] = A::slot(S, M, term_tag_of(M, M.grp[cg[i]], t));
       }
     }
+    if constexpr (LAYOUT == PSB_LAYOUT_OPENMM_CUDA) {
+      // raw velocity rows first, v / invM after every load has been issued (see Access<OPENMM_CUDA>::momentum_of)
+      typename Real4<Real>::type cv[CT];
 #pragma unroll
-    for (int i = 0; i < CT; ++i) {
-      cp[i] = v3(0, 0, 0);
-      if (cg[i] >= 0) {
-        cr[i] = A::position(S, cslot[i]);
-        if (momenta_sums) cp[i] = A::momentum(S, cslot[i]);
+      for (int i = 0; i < CT; ++i) {
+        cp[i] = v3(0, 0, 0);
+        if (cg[i] >= 0) {
+          cr[i] = A::position(S, cslot[i]);
+          if (momenta_sums) cv[i] = A::load_velocity(S, cslot[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CT; ++i)
+        if (cg[i] >= 0 && momenta_sums) cp[i] = A::momentum_of(cv[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CT; ++i) {
+        cp[i] = v3(0, 0, 0);
+        if (cg[i] >= 0) {
+          cr[i] = A::position(S, cslot[i]);
+          if (momenta_sums) cp[i] = A::momentum(S, cslot[i]);
+        }
       }
     }
   }
@@ -1510,18 +1526,27 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
     // (ABF only: its gather keeps 4 rows per thread in flight and has registers to spare; the 8-row gathers of the
     // other methods sit at the 128-register limit of two CTAs per SM and would spill)
     nib_ok = is_abf && (s_hi - s_lo) <= (uint32_t)ROWG_ROWS * BLOCK;
+    constexpr bool RAWV = (LAYOUT == PSB_LAYOUT_OPENMM_CUDA);  // momenta from raw velocity rows, after the loads
     for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
       uint32_t e[SU];
       V3 r[SU], p[SU];
+      typename Real4<Real>::type vraw[RAWV ? SU : 1];
 #pragma unroll
       for (int u = 0; u < SU; ++u) {
         const uint32_t sl = min(base + u * BLOCK, s_hi - 1);  // clamped: no branch around the loads
         e[u] = slot_word(sl);
         r[u] = A::position(S, sl);
-        p[u] = momenta_sums ? A::momentum(S, sl) : v3(0, 0, 0);
+        if constexpr (RAWV) {
+          p[u] = v3(0, 0, 0);
+          if (momenta_sums) vraw[u] = A::load_velocity(S, sl);
+        } else {
+          p[u] = momenta_sums ? A::momentum(S, sl) : v3(0, 0, 0);
+        }
       }
 #pragma unroll
       for (int u = 0; u < SU; ++u) {
+        if constexpr (RAWV)
+          if (momenta_sums) p[u] = A::momentum_of(vraw[u]);
         const bool hit = (base + u * BLOCK < s_hi) && ((e[u] & ~15u) == stamp);
         const int g = hit ? (int)(e[u] & 15u) - 1 : -1;
         if constexpr (is_abf)
