@@ -348,10 +348,11 @@ struct Access<PSB_LAYOUT_OPENMM_CUDA, Real> {
   // openmm.py:96-97,125-127: v / invM, or v when invM == 0.  Split into the load and the arithmetic: a streaming
   // loop issues the loads of a whole batch first and divides afterwards (the test on invM and the division's slow
   // path are branches; taken between two loads they serialise the batch -- measured: 48 instead of 11 us per 1e6 rows)
-  static __device__ __forceinline__ R4 load_velocity(const Snap& s, uint32_t slot) {
+  using VR = R4;
+  static __device__ __forceinline__ VR load_velocity(const Snap& s, uint32_t slot) {
     return ldg4(reinterpret_cast<const R4*>(s.vel_mass) + slot);
   }
-  static __device__ __forceinline__ V3 momentum_of(R4 v) {
+  static __device__ __forceinline__ V3 momentum_of(VR v) {
     if (v.w == (Real)0) return v3((double)v.x, (double)v.y, (double)v.z);
     return v3((double)(Real)(v.x / v.w), (double)(Real)(v.y / v.w), (double)(Real)(v.z / v.w));
   }
@@ -437,14 +438,18 @@ struct Access<PSB_LAYOUT_PLAIN3, Real> {
     }
     return r;
   }
-  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) {
-    // openmm.py:96-97,125-127 with (velocities, invMass) stored separately
-    const V3 v = Plain3<Real>::load3(s.vel_mass, slot);
-    const Real im = __ldg(reinterpret_cast<const Real*>(s.masses) + slot);
-    if (im == (Real)0) return v;
-    return v3((double)(Real)((Real)v.x / im), (double)(Real)((Real)v.y / im),
-              (double)(Real)((Real)v.z / im));
+  // openmm.py:96-97,125-127 with (velocities, invMass) stored separately; load and arithmetic split as for the
+  // OpenMM-CUDA layout (the test on invMass and the division are branches: they must not sit between two loads)
+  struct VR { V3 v; Real im; };
+  static __device__ __forceinline__ VR load_velocity(const Snap& s, uint32_t slot) {
+    return VR{Plain3<Real>::load3(s.vel_mass, slot), __ldg(reinterpret_cast<const Real*>(s.masses) + slot)};
   }
+  static __device__ __forceinline__ V3 momentum_of(VR r) {
+    if (r.im == (Real)0) return r.v;
+    return v3((double)(Real)((Real)r.v.x / r.im), (double)(Real)((Real)r.v.y / r.im),
+              (double)(Real)((Real)r.v.z / r.im));
+  }
+  static __device__ __forceinline__ V3 momentum(const Snap& s, uint32_t slot) { return momentum_of(load_velocity(s, slot)); }
   using FV = typename Plain3<Real>::FV;
   static __device__ __forceinline__ FV load_force(const Snap& s, uint32_t slot) {
     return Plain3<Real>::load_force(s, slot);

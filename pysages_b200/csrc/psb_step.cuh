@@ -1216,6 +1216,10 @@ __device__ __forceinline__ void add_force(const Snap& S, uint32_t slot, V3 fo) {
   A::store_force(S, slot, A::load_force(S, slot), fo);
 }
 
+// raw velocity row type of the layouts that split the momentum into a load and the arithmetic (int otherwise)
+template <typename A, bool RAW> struct RawVelocity { using type = int; };
+template <typename A> struct RawVelocity<A, true> { using type = typename A::VR; };
+
 // ---- the kernel -------------------------------------------------------------------------------
 // The body of the step: `nb` CTAs (this one is CTA `b` of them) step the simulation described by (Mglobal, S).
 // psb_step launches exactly those CTAs (step_kernel); psb_batch_step launches the CTAs of many independent
@@ -1444,9 +1448,9 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
         cslot[i] = A::slot(S, M, term_tag_of(M, M.grp[cg[i]], t));
       }
     }
-    if constexpr (LAYOUT == PSB_LAYOUT_OPENMM_CUDA) {
+    if constexpr (LAYOUT == PSB_LAYOUT_OPENMM_CUDA || LAYOUT == PSB_LAYOUT_PLAIN3) {
       // raw velocity rows first, v / invM after every load has been issued (see Access<OPENMM_CUDA>::momentum_of)
-      typename Real4<Real>::type cv[CT];
+      typename A::VR cv[CT];
 #pragma unroll
       for (int i = 0; i < CT; ++i) {
         cp[i] = v3(0, 0, 0);
@@ -1526,11 +1530,11 @@ __device__ __forceinline__ void step_body(const Model* __restrict__ Mglobal, con
     // (ABF only: its gather keeps 4 rows per thread in flight and has registers to spare; the 8-row gathers of the
     // other methods sit at the 128-register limit of two CTAs per SM and would spill)
     nib_ok = is_abf && (s_hi - s_lo) <= (uint32_t)ROWG_ROWS * BLOCK;
-    constexpr bool RAWV = (LAYOUT == PSB_LAYOUT_OPENMM_CUDA);  // momenta from raw velocity rows, after the loads
+    constexpr bool RAWV = (LAYOUT == PSB_LAYOUT_OPENMM_CUDA || LAYOUT == PSB_LAYOUT_PLAIN3);  // momenta from raw velocity rows, after the loads
     for (uint32_t base = s_lo + tid; base < s_hi; base += SU * BLOCK) {
       uint32_t e[SU];
       V3 r[SU], p[SU];
-      typename Real4<Real>::type vraw[RAWV ? SU : 1];
+      typename RawVelocity<A, RAWV>::type vraw[RAWV ? SU : 1];
 #pragma unroll
       for (int u = 0; u < SU; ++u) {
         const uint32_t sl = min(base + u * BLOCK, s_hi - 1);  // clamped: no branch around the loads
